@@ -1,0 +1,120 @@
+// Shared helpers for the egogen_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/egogen_b200.h"
+
+namespace eg {
+
+extern thread_local char g_last_error[512];
+extern std::atomic<int64_t> g_launch_count;
+
+inline int set_error(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_last_error, sizeof(g_last_error), fmt, a, b);
+  return code;
+}
+
+#define EG_CUDA_CHECK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      snprintf(eg::g_last_error, sizeof(eg::g_last_error), "%s:%d %s -> %s", __FILE__,   \
+               __LINE__, #expr, cudaGetErrorString(_e));                                 \
+      return EG_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define EG_REQUIRE(cond, msg)                                                            \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      snprintf(eg::g_last_error, sizeof(eg::g_last_error), "%s:%d invalid argument: %s", \
+               __FILE__, __LINE__, msg);                                                 \
+      return EG_ERR_INVALID_ARG;                                                         \
+    }                                                                                    \
+  } while (0)
+
+// every kernel launch goes through this so eg_launch_count() is the library's own claim
+#define EG_LAUNCH(kernel, grid, block, smem, stream, ...)                                \
+  do {                                                                                   \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+    eg::g_launch_count.fetch_add(1, std::memory_order_relaxed);                          \
+    EG_CUDA_CHECK(cudaGetLastError());                                                   \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+inline int dev_alloc_copy(T** dst, const T* src_host, size_t n) {
+  EG_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T)));
+  EG_CUDA_CHECK(cudaMemcpy(*dst, src_host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return EG_OK;
+}
+
+constexpr int kNumSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- SDF sampling shared by sdf.cu and lbs.cu (ATen grid_sampler_3d semantics) ----------------
+struct SdfGrid {
+  const float* grid;
+  int D0, D1, D2;
+  const float* center;  // device [3]
+  const float* scale;   // device [1]
+};
+
+// un-normalise with align_corners=False then clamp to [0, D-1] (padding_mode='border').
+// Written with explicit round-to-nearest intrinsics so ptxas cannot contract the sequence into
+// FMAs: the floor of this value is a bit-exact parity target.
+__device__ __forceinline__ float sdf_unnormalize(float p, int D) {
+  float i = __fmul_rn(__fadd_rn(p, 1.0f), (float)D);
+  i = __fmul_rn(__fsub_rn(i, 1.0f), 0.5f);
+  return fminf(fmaxf(i, 0.0f), (float)(D - 1));
+}
+
+// returns -trilinear(grid, p) with p the world-space point; writes the base corner indices.
+__device__ __forceinline__ float sdf_sample_point(const SdfGrid& g, float cx, float cy, float cz,
+                                                  float s, float x, float y, float z, int& ox,
+                                                  int& oy, int& oz) {
+  const float px = __fmul_rn(__fsub_rn(x, cx), s);
+  const float py = __fmul_rn(__fsub_rn(y, cy), s);
+  const float pz = __fmul_rn(__fsub_rn(z, cz), s);
+  const float ix = sdf_unnormalize(px, g.D0);
+  const float iy = sdf_unnormalize(py, g.D1);
+  const float iz = sdf_unnormalize(pz, g.D2);
+  const float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
+  const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
+  ox = x0; oy = y0; oz = z0;
+  // ATen weights: (corner+1 - i) and (i - corner); accumulate in ATen's corner order
+  // (x here is ATen's z/D axis, z is ATen's x/W axis): tnw,tne,tsw,tse,bnw,bne,bsw,bse.
+  const float wx1 = __fsub_rn(ix, fx0), wx0 = __fsub_rn(__fadd_rn(fx0, 1.0f), ix);
+  const float wy1 = __fsub_rn(iy, fy0), wy0 = __fsub_rn(__fadd_rn(fy0, 1.0f), iy);
+  const float wz1 = __fsub_rn(iz, fz0), wz0 = __fsub_rn(__fadd_rn(fz0, 1.0f), iz);
+  const bool x1ok = x0 + 1 <= g.D0 - 1, y1ok = y0 + 1 <= g.D1 - 1, z1ok = z0 + 1 <= g.D2 - 1;
+  const int64_t sx = (int64_t)g.D1 * g.D2, sy = g.D2;
+  const float* b = g.grid + x0 * sx + y0 * sy + z0;
+  float acc = 0.0f;
+  // ATen: weight = (wW * wH) * wD with W = our z, H = our y, D = our x
+  acc = __fadd_rn(acc, __fmul_rn(__ldg(b), __fmul_rn(__fmul_rn(wz0, wy0), wx0)));
+  if (z1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(b + 1), __fmul_rn(__fmul_rn(wz1, wy0), wx0)));
+  if (y1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(b + sy), __fmul_rn(__fmul_rn(wz0, wy1), wx0)));
+  if (y1ok && z1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(b + sy + 1), __fmul_rn(__fmul_rn(wz1, wy1), wx0)));
+  if (x1ok) {
+    acc = __fadd_rn(acc, __fmul_rn(__ldg(b + sx), __fmul_rn(__fmul_rn(wz0, wy0), wx1)));
+    if (z1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(b + sx + 1), __fmul_rn(__fmul_rn(wz1, wy0), wx1)));
+    if (y1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(b + sx + sy), __fmul_rn(__fmul_rn(wz0, wy1), wx1)));
+    if (y1ok && z1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(b + sx + sy + 1), __fmul_rn(__fmul_rn(wz1, wy1), wx1)));
+  }
+  return -acc;
+}
+
+}  // namespace eg

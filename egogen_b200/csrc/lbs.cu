@@ -1,0 +1,647 @@
+// SMPL-X linear blend skinning for sm_100a.
+//
+// Replaces smplx.SMPLX.forward / smplx.lbs.lbs as called from SMPLXParser.forward_smplx
+// (reference motion/models/baseops.py:338-398) and the fused consumers in
+// crowd_env_2f.py:133-177 (world transform -> calc_sdf -> feet skip -> per-frame counts).
+//
+// Data layout in HBM (built once in eg_lbs_create):
+//   basis   [KPAD=512][3*n_pad]   rows 0..485 posedirs, 486..505 shapedirs^T, 506..511 zero;
+//                                 columns are vertices (xyz interleaved) padded to 128-vertex tiles.
+//                                 The shape blend is folded into the pose-blend contraction so the
+//                                 vertex kernel is ONE [N,512]x[512,3V] product + skinning epilogue.
+//   vt      [3*n_pad]             v_template
+//   skin    [nnz][n_pad] idx / w  ELL form of lbs_weights (zeros dropped; exact)
+//   Jt,Js   [55,3] / [55,3,20]    J_regressor folded through v_template / shapedirs
+// Per call workspace: Ft [512][Npad] (features, k-major), A [N][55][12], Jp [N][55][3].
+//
+// Kernels: lbs_pose_prep_kernel (1 CTA / body: hand PCA, Rodrigues, features, joint regression,
+// level-parallel kinematic chain) -> lbs_verts_kernel (128 vertices x 32 bodies per CTA,
+// cp.async double-buffered basis tiles, skinning epilogue, optional fused world-transform + SDF
+// sample + penetration count so vertices never reach HBM) -> lbs_finish_kernel (127 joints,
+// markers). The same vertex kernel runs on the full mesh and on a compact gathered vertex set
+// (markers + vertex joints + landmark corners) for the joints-only calls.
+#include <vector>
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace eg {
+
+constexpr int KPAD = 512;      // padded contraction length (486 pose + 20 shape + 6 zero)
+constexpr int TILE_V = 128;    // vertices per CTA
+constexpr int KC = 16;         // k-chunk per pipeline stage
+constexpr int BPG = 16;        // bodies per thread (per body-group)
+constexpr int NGROUPS = 2;     // body-groups per CTA
+constexpr int TILE_B = BPG * NGROUPS;          // 32 bodies per CTA
+constexpr int VERT_THREADS = TILE_V * NGROUPS; // 256
+constexpr int MAXJ = 64;
+constexpr int VERT_SMEM = sizeof(float) * 2 * KC * (TILE_V * 3 + TILE_B) + sizeof(int) * TILE_B;
+
+struct VertexSet {
+  int n = 0, n_pad = 0, nnz = 0;
+  float* basis = nullptr;
+  float* vt = nullptr;
+  int32_t* skin_idx = nullptr;
+  float* skin_w = nullptr;
+};
+
+}  // namespace eg
+
+struct EgLbs {
+  int device = 0;
+  int V = 0, J = 0, S = 0, P = 0, n_extra = 0, n_lmk = 0, n_markers = 0;
+  int n_levels = 0;
+  // prep-kernel constants
+  float *Jt = nullptr, *Js = nullptr, *hand_l = nullptr, *hand_r = nullptr, *pose_mean = nullptr;
+  int32_t *parents = nullptr, *level_joints = nullptr, *level_start = nullptr;
+  float* lmk_bary = nullptr;
+  eg::VertexSet full, compact;
+  // host copies needed to (re)build the compact set
+  std::vector<int32_t> h_extra, h_lmk_verts;
+  // workspace
+  int cap_N = 0;
+  float *Ft = nullptr, *A = nullptr, *Jp = nullptr, *cout_ = nullptr;
+};
+
+namespace eg {
+
+// --------------------------------------------------------------------------------------------
+// prep: one CTA of 64 threads per body
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ betas, int betas_rows,
+                     int N, int Npad, int J, int S, int n_levels,
+                     const float* __restrict__ hand_l, const float* __restrict__ hand_r,
+                     const float* __restrict__ pose_mean, const float* __restrict__ Jt,
+                     const float* __restrict__ Js, const int32_t* __restrict__ parents,
+                     const int32_t* __restrict__ level_joints, const int32_t* __restrict__ level_start,
+                     float* __restrict__ Ft, float* __restrict__ A, float* __restrict__ Jp) {
+  const int n = blockIdx.x;
+  const int t = threadIdx.x;
+  __shared__ float pose[MAXJ * 3];
+  __shared__ float R[MAXJ][9];
+  __shared__ float Jr[MAXJ][3];
+  __shared__ float G[MAXJ][12];
+  __shared__ float shape[32];
+  const float* x = xb + (int64_t)n * EG_XB_DIM;
+  const float* be = betas + (int64_t)(betas_rows == 1 ? 0 : n) * 10;
+
+  // full_pose = [global_orient, body_pose(21), jaw, leye, reye, lhand(15), rhand(15)] + pose_mean
+  for (int i = t; i < J * 3; i += 64) {
+    float v = 0.0f;
+    if (i < 66) {
+      v = x[3 + i];
+    } else if (i >= 75 && i < 120) {          // left hand: einsum('bi,ij->bj', pca12, comps[12,45])
+      const int c = i - 75;
+      for (int k = 0; k < 12; ++k) v += x[69 + k] * __ldg(hand_l + k * 45 + c);
+    } else if (i >= 120 && i < 165) {
+      const int c = i - 120;
+      for (int k = 0; k < 12; ++k) v += x[81 + k] * __ldg(hand_r + k * 45 + c);
+    }
+    pose[i] = v + __ldg(pose_mean + i);
+  }
+  if (t < S) shape[t] = (t < 10) ? be[t] : 0.0f;   // shape components = betas ++ expression(0)
+  __syncthreads();
+
+  // Rodrigues (smplx.lbs.batch_rodrigues): angle = ||r + 1e-8||, R = I + sin K + (1-cos) K K
+  if (t < J) {
+    const float rx = pose[3 * t], ry = pose[3 * t + 1], rz = pose[3 * t + 2];
+    const float ax = rx + 1e-8f, ay = ry + 1e-8f, az = rz + 1e-8f;
+    const float angle = sqrtf(ax * ax + ay * ay + az * az);
+    const float dx = rx / angle, dy = ry / angle, dz = rz / angle;
+    const float s = sinf(angle), c = cosf(angle);
+    const float K[9] = {0.f, -dz, dy, dz, 0.f, -dx, -dy, dx, 0.f};
+    const float omc = 1.0f - c;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        float kk = 0.f;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) kk += K[a * 3 + m] * K[m * 3 + b];
+        R[t][a * 3 + b] = (a == b ? 1.0f : 0.0f) + s * K[a * 3 + b] + omc * kk;
+      }
+    // joint regression folded through the blend shapes: J = Jt + Js . shape
+    for (int cidx = 0; cidx < 3; ++cidx) {
+      float v = __ldg(Jt + t * 3 + cidx);
+      const float* js = Js + (t * 3 + cidx) * S;
+      for (int k = 0; k < S; ++k) v += __ldg(js + k) * shape[k];
+      Jr[t][cidx] = v;
+    }
+  }
+  __syncthreads();
+
+  // features, k-major: rows 0..485 = vec(R_1..54 - I), 486..505 = shape, rest 0
+  for (int k = t; k < KPAD; k += 64) {
+    float v = 0.0f;
+    const int npose = (J - 1) * 9;
+    if (k < npose) {
+      const int j = 1 + k / 9, e = k % 9;
+      v = R[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+    } else if (k < npose + S) {
+      v = shape[k - npose];
+    }
+    Ft[(int64_t)k * Npad + n] = v;
+  }
+
+  // kinematic chain by tree level: G_j = G_parent [R_j | J_j - J_parent]
+  for (int lv = 0; lv < n_levels; ++lv) {
+    const int beg = __ldg(level_start + lv), end = __ldg(level_start + lv + 1);
+    for (int q = beg + t; q < end; q += 64) {
+      const int j = __ldg(level_joints + q);
+      const int p = __ldg(parents + j);
+      if (p < 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          G[j][a * 4 + 0] = R[j][a * 3 + 0];
+          G[j][a * 4 + 1] = R[j][a * 3 + 1];
+          G[j][a * 4 + 2] = R[j][a * 3 + 2];
+          G[j][a * 4 + 3] = Jr[j][a];
+        }
+      } else {
+        const float r0 = Jr[j][0] - Jr[p][0], r1 = Jr[j][1] - Jr[p][1], r2 = Jr[j][2] - Jr[p][2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float g0 = G[p][a * 4 + 0], g1 = G[p][a * 4 + 1], g2 = G[p][a * 4 + 2], g3 = G[p][a * 4 + 3];
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+            G[j][a * 4 + b] = g0 * R[j][0 * 3 + b] + g1 * R[j][1 * 3 + b] + g2 * R[j][2 * 3 + b];
+          G[j][a * 4 + 3] = g0 * r0 + g1 * r1 + g2 * r2 + g3;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // posed joints and relative transforms A_j = G_j with translation minus G_j.R J_j
+  if (t < J) {
+    float* a_out = A + ((int64_t)n * J + t) * 12;
+    float* jp = Jp + ((int64_t)n * J + t) * 3;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float g0 = G[t][a * 4 + 0], g1 = G[t][a * 4 + 1], g2 = G[t][a * 4 + 2], g3 = G[t][a * 4 + 3];
+      a_out[a * 4 + 0] = g0;
+      a_out[a * 4 + 1] = g1;
+      a_out[a * 4 + 2] = g2;
+      a_out[a * 4 + 3] = g3 - (g0 * Jr[t][0] + g1 * Jr[t][1] + g2 * Jr[t][2]);
+      jp[a] = g3;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// vertex kernel
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct VertArgs {
+  const float* basis;     // [KPAD][3*n_pad]
+  const float* vt;        // [3*n_pad]
+  const int32_t* skin_idx;
+  const float* skin_w;
+  int n_real, n_pad, nnz, J;
+  const float* Ft;        // [KPAD][Npad]
+  const float* A;         // [N][J][12]
+  const float* xb;        // [N][93] (transl)
+  int N, Npad;
+  int add_transl;
+  float* out;             // [N][n_real][3] or null
+  // fused SDF
+  SdfGrid sdf;
+  const float* R0;        // [E][9]
+  const float* T0;        // [E][3]
+  int frames_per_env;
+  const uint8_t* skip;
+  int32_t* counts;        // [N]
+};
+
+template <bool FUSE_SDF>
+__global__ void __launch_bounds__(VERT_THREADS, 2)
+lbs_verts_kernel(const VertArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float (*Ps)[KC][TILE_V * 3] = reinterpret_cast<float (*)[KC][TILE_V * 3]>(smem_raw);
+  float (*Fs)[KC][TILE_B] = reinterpret_cast<float (*)[KC][TILE_B]>(smem_raw + sizeof(float) * 2 * KC * TILE_V * 3);
+  int* cnt_s = reinterpret_cast<int*>(smem_raw + sizeof(float) * 2 * KC * (TILE_V * 3 + TILE_B));
+
+  const int tid = threadIdx.x;
+  const int vl = tid % TILE_V;            // vertex within tile
+  const int grp = tid / TILE_V;           // body group
+  const int v0 = blockIdx.x * TILE_V;
+  const int b0 = blockIdx.y * TILE_B;
+  const int64_t brow = (int64_t)a.n_pad * 3;
+
+  if (FUSE_SDF && tid < TILE_B) cnt_s[tid] = 0;
+
+  auto load_stage = [&](int st, int kbase) {
+    // basis tile: KC rows x 384 floats = KC*96 float4
+#pragma unroll
+    for (int i = 0; i < (KC * TILE_V * 3 / 4) / VERT_THREADS; ++i) {
+      const int q = tid + i * VERT_THREADS;
+      const int r = q / (TILE_V * 3 / 4), c4 = q % (TILE_V * 3 / 4);
+      cp_async16(&Ps[st][r][c4 * 4], a.basis + (int64_t)(kbase + r) * brow + (int64_t)v0 * 3 + c4 * 4);
+    }
+    // feature tile: KC rows x 32 floats = KC*8 float4
+    if (tid < KC * TILE_B / 4) {
+      const int r = tid / (TILE_B / 4), c4 = tid % (TILE_B / 4);
+      cp_async16(&Fs[st][r][c4 * 4], a.Ft + (int64_t)(kbase + r) * a.Npad + b0 + c4 * 4);
+    }
+    cp_async_commit();
+  };
+
+  float acc[BPG][3];
+#pragma unroll
+  for (int b = 0; b < BPG; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.0f;
+
+  load_stage(0, 0);
+  constexpr int NCHUNK = KPAD / KC;
+  for (int ch = 0; ch < NCHUNK; ++ch) {
+    const int st = ch & 1;
+    if (ch + 1 < NCHUNK) {
+      load_stage(st ^ 1, (ch + 1) * KC);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      const float p0 = Ps[st][kk][vl * 3 + 0];
+      const float p1 = Ps[st][kk][vl * 3 + 1];
+      const float p2 = Ps[st][kk][vl * 3 + 2];
+      const float4* f4 = reinterpret_cast<const float4*>(&Fs[st][kk][grp * BPG]);
+#pragma unroll
+      for (int q = 0; q < BPG / 4; ++q) {
+        const float4 f = f4[q];
+        acc[q * 4 + 0][0] += f.x * p0; acc[q * 4 + 0][1] += f.x * p1; acc[q * 4 + 0][2] += f.x * p2;
+        acc[q * 4 + 1][0] += f.y * p0; acc[q * 4 + 1][1] += f.y * p1; acc[q * 4 + 1][2] += f.y * p2;
+        acc[q * 4 + 2][0] += f.z * p0; acc[q * 4 + 2][1] += f.z * p1; acc[q * 4 + 2][2] += f.z * p2;
+        acc[q * 4 + 3][0] += f.w * p0; acc[q * 4 + 3][1] += f.w * p1; acc[q * 4 + 3][2] += f.w * p2;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: v_posed -> skinning -> (+transl) -> store / fused SDF ----
+  const int v = v0 + vl;
+  const bool v_ok = v < a.n_real;
+  const float t0 = a.vt[v * 3 + 0], t1 = a.vt[v * 3 + 1], t2 = a.vt[v * 3 + 2];
+  float cx = 0.f, cy = 0.f, cz = 0.f, sc = 0.f;
+  bool skip = false;
+  if (FUSE_SDF) {
+    cx = __ldg(a.sdf.center); cy = __ldg(a.sdf.center + 1); cz = __ldg(a.sdf.center + 2);
+    sc = __ldg(a.sdf.scale);
+    skip = v_ok ? (a.skip != nullptr && a.skip[v] != 0) : true;
+  }
+#pragma unroll
+  for (int b = 0; b < BPG; ++b) {
+    const int n = b0 + grp * BPG + b;
+    if (n >= a.N) continue;                               // warp-uniform (n depends on grp, b only)
+    const float px = t0 + acc[b][0], py = t1 + acc[b][1], pz = t2 + acc[b][2];
+    float T[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) T[e] = 0.0f;
+    const float4* An = reinterpret_cast<const float4*>(a.A + (int64_t)n * a.J * 12);
+    for (int k = 0; k < a.nnz; ++k) {
+      const int j = a.skin_idx[k * a.n_pad + v];
+      const float w = a.skin_w[k * a.n_pad + v];
+      const float4 r0 = __ldg(An + j * 3 + 0), r1 = __ldg(An + j * 3 + 1), r2 = __ldg(An + j * 3 + 2);
+      T[0] += w * r0.x; T[1] += w * r0.y; T[2] += w * r0.z; T[3] += w * r0.w;
+      T[4] += w * r1.x; T[5] += w * r1.y; T[6] += w * r1.z; T[7] += w * r1.w;
+      T[8] += w * r2.x; T[9] += w * r2.y; T[10] += w * r2.z; T[11] += w * r2.w;
+    }
+    float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+    float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+    float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+    if (a.add_transl) {
+      const float* x = a.xb + (int64_t)n * EG_XB_DIM;
+      ox = __fadd_rn(ox, __ldg(x)); oy = __fadd_rn(oy, __ldg(x + 1)); oz = __fadd_rn(oz, __ldg(x + 2));
+    }
+    if (a.out != nullptr && v_ok) {
+      float* o = a.out + ((int64_t)n * a.n_real + v) * 3;
+      o[0] = ox; o[1] = oy; o[2] = oz;
+    }
+    if (FUSE_SDF) {
+      const int e = n / a.frames_per_env;
+      const float* Rw = a.R0 + (int64_t)e * 9;
+      const float* Tw = a.T0 + (int64_t)e * 3;
+      const float wx = __ldg(Rw + 0) * ox + __ldg(Rw + 1) * oy + __ldg(Rw + 2) * oz + __ldg(Tw + 0);
+      const float wy = __ldg(Rw + 3) * ox + __ldg(Rw + 4) * oy + __ldg(Rw + 5) * oz + __ldg(Tw + 1);
+      const float wz = __ldg(Rw + 6) * ox + __ldg(Rw + 7) * oy + __ldg(Rw + 8) * oz + __ldg(Tw + 2);
+      int ix, iy, iz;
+      bool neg = false;
+      if (!skip) neg = sdf_sample_point(a.sdf, cx, cy, cz, sc, wx, wy, wz, ix, iy, iz) < 0.0f;
+      const unsigned m = __ballot_sync(0xffffffffu, neg);
+      if ((tid & 31) == 0 && m) atomicAdd(&cnt_s[grp * BPG + b], __popc(m));
+    }
+  }
+  if (FUSE_SDF) {
+    __syncthreads();
+    if (tid < TILE_B && b0 + tid < a.N && cnt_s[tid] > 0) atomicAdd(a.counts + b0 + tid, cnt_s[tid]);
+  }
+}
+
+// joints [N,127,3] = posed joints ++ vertex joints ++ landmarks (+transl); markers [N,M,3]
+__global__ void __launch_bounds__(128)
+lbs_finish_kernel(const float* __restrict__ Jp, const float* __restrict__ cverts,
+                  const float* __restrict__ xb, const float* __restrict__ lmk_bary, int N, int J,
+                  int n_markers, int n_extra, int n_lmk, int nc, float* __restrict__ joints,
+                  float* __restrict__ markers) {
+  const int n = blockIdx.x;
+  const float* x = xb + (int64_t)n * EG_XB_DIM;
+  const float tx = x[0], ty = x[1], tz = x[2];
+  const float tr[3] = {tx, ty, tz};
+  const float* cv = cverts + (int64_t)n * nc * 3;
+  const int n_out = J + n_extra + n_lmk;
+  if (joints) {
+    for (int i = threadIdx.x; i < n_out * 3; i += blockDim.x) {
+      const int j = i / 3, c = i % 3;
+      float v;
+      if (j < J) {
+        v = Jp[((int64_t)n * J + j) * 3 + c];
+      } else if (j < J + n_extra) {
+        v = cv[(n_markers + (j - J)) * 3 + c];
+      } else {
+        const int l = j - J - n_extra;
+        const float* q = cv + (n_markers + n_extra + 3 * l) * 3;
+        // einsum('blfi,blf->bli'): sum over the 3 face corners in order
+        v = q[0 + c] * __ldg(lmk_bary + 3 * l) + q[3 + c] * __ldg(lmk_bary + 3 * l + 1) +
+            q[6 + c] * __ldg(lmk_bary + 3 * l + 2);
+      }
+      joints[((int64_t)n * n_out + j) * 3 + c] = __fadd_rn(v, tr[c]);
+    }
+  }
+  if (markers) {
+    for (int i = threadIdx.x; i < n_markers * 3; i += blockDim.x)
+      markers[((int64_t)n * n_markers) * 3 + i] = __fadd_rn(cv[i], tr[i % 3]);
+  }
+}
+
+__global__ void gather_vertex_set_kernel(const float* __restrict__ src_basis, int64_t src_row,
+                                         const float* __restrict__ src_vt,
+                                         const int32_t* __restrict__ src_idx,
+                                         const float* __restrict__ src_w, int src_npad, int nnz,
+                                         const int32_t* __restrict__ vids, int n, int n_pad,
+                                         float* __restrict__ basis, float* __restrict__ vt,
+                                         int32_t* __restrict__ idx, float* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = vids[i];
+  for (int k = 0; k < KPAD; ++k)
+    for (int c = 0; c < 3; ++c) basis[(int64_t)k * n_pad * 3 + i * 3 + c] = src_basis[k * src_row + v * 3 + c];
+  for (int c = 0; c < 3; ++c) vt[i * 3 + c] = src_vt[v * 3 + c];
+  for (int k = 0; k < nnz; ++k) {
+    idx[k * n_pad + i] = src_idx[k * src_npad + v];
+    w[k * n_pad + i] = src_w[k * src_npad + v];
+  }
+}
+
+static void free_vertex_set(VertexSet& s) {
+  cudaFree(s.basis); cudaFree(s.vt); cudaFree(s.skin_idx); cudaFree(s.skin_w);
+  s = VertexSet();
+}
+
+static int ensure_workspace(EgLbs* h, int N) {
+  if (N <= h->cap_N) return EG_OK;
+  int cap = std::max(N, 64);
+  cap = (cap + 31) / 32 * 32;
+  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_);
+  h->Ft = h->A = h->Jp = h->cout_ = nullptr;
+  h->cap_N = 0;
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->Ft, (size_t)KPAD * cap * sizeof(float)));
+  EG_CUDA_CHECK(cudaMemset(h->Ft, 0, (size_t)KPAD * cap * sizeof(float)));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->A, (size_t)cap * h->J * 12 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->Jp, (size_t)cap * h->J * 3 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->cout_, (size_t)cap * 512 * 3 * sizeof(float)));
+  h->cap_N = cap;
+  return EG_OK;
+}
+
+static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
+                       float* verts, float* joints, float* markers, bool fuse, int frames_per_env,
+                       const float* R0, const float* T0, SdfGrid sdf, const uint8_t* skip,
+                       int32_t* counts, cudaStream_t st) {
+  EG_REQUIRE(h && xb && betas, "null pointer");
+  EG_REQUIRE(betas_rows == 1 || betas_rows == N, "betas_rows must be 1 or N");
+  EG_REQUIRE(N >= 0, "negative N");
+  if (N == 0) return EG_OK;
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc = ensure_workspace(h, N);
+  if (rc) return rc;
+  const int Npad = h->cap_N;   // row stride of Ft (fixed per workspace so tiles never read OOB)
+  EG_LAUNCH(lbs_pose_prep_kernel, N, 64, 0, st, xb, betas, betas_rows, N, Npad, h->J, h->S,
+            h->n_levels, h->hand_l, h->hand_r, h->pose_mean, h->Jt, h->Js, h->parents,
+            h->level_joints, h->level_start, h->Ft, h->A, h->Jp);
+  VertArgs a{};
+  a.Ft = h->Ft; a.A = h->A; a.xb = xb; a.N = N; a.Npad = Npad; a.J = h->J;
+  const int by = (N + TILE_B - 1) / TILE_B;
+  if (verts != nullptr || fuse) {
+    const VertexSet& s = h->full;
+    a.basis = s.basis; a.vt = s.vt; a.skin_idx = s.skin_idx; a.skin_w = s.skin_w;
+    a.n_real = s.n; a.n_pad = s.n_pad; a.nnz = s.nnz; a.add_transl = 1; a.out = verts;
+    dim3 grid(s.n_pad / TILE_V, by);
+    if (fuse) {
+      a.sdf = sdf; a.R0 = R0; a.T0 = T0; a.frames_per_env = frames_per_env; a.skip = skip;
+      a.counts = counts;
+      EG_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)N * sizeof(int32_t), st));
+      EG_LAUNCH(lbs_verts_kernel<true>, grid, VERT_THREADS, VERT_SMEM, st, a);
+    } else {
+      EG_LAUNCH(lbs_verts_kernel<false>, grid, VERT_THREADS, VERT_SMEM, st, a);
+    }
+  }
+  if (joints != nullptr || markers != nullptr) {
+    const VertexSet& s = h->compact;
+    EG_REQUIRE(s.n > 0, "compact vertex set missing (eg_lbs_set_markers)");
+    VertArgs c = a;
+    c.basis = s.basis; c.vt = s.vt; c.skin_idx = s.skin_idx; c.skin_w = s.skin_w;
+    c.n_real = s.n; c.n_pad = s.n_pad; c.nnz = s.nnz; c.add_transl = 0; c.out = h->cout_;
+    c.counts = nullptr;
+    dim3 grid(s.n_pad / TILE_V, by);
+    EG_LAUNCH(lbs_verts_kernel<false>, grid, VERT_THREADS, VERT_SMEM, st, c);
+    EG_LAUNCH(lbs_finish_kernel, N, 128, 0, st, h->Jp, h->cout_, xb, h->lmk_bary, N, h->J,
+              h->n_markers, h->n_extra, h->n_lmk, s.n, joints, markers);
+  }
+  return EG_OK;
+}
+
+static int build_compact(EgLbs* h, const int32_t* marker_vids, int n_markers) {
+  std::vector<int32_t> vids(marker_vids, marker_vids + n_markers);
+  vids.insert(vids.end(), h->h_extra.begin(), h->h_extra.end());
+  vids.insert(vids.end(), h->h_lmk_verts.begin(), h->h_lmk_verts.end());
+  const int n = (int)vids.size();
+  if (n > 512) return set_error(EG_ERR_INVALID_ARG, "compact vertex set larger than 512 vertices");
+  for (int v : vids)
+    if (v < 0 || v >= h->V) return set_error(EG_ERR_INVALID_ARG, "vertex id out of range");
+  free_vertex_set(h->compact);
+  VertexSet s;
+  s.n = n; s.n_pad = (n + TILE_V - 1) / TILE_V * TILE_V; s.nnz = h->full.nnz;
+  EG_CUDA_CHECK(cudaMalloc((void**)&s.basis, (size_t)KPAD * s.n_pad * 3 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMemset(s.basis, 0, (size_t)KPAD * s.n_pad * 3 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMalloc((void**)&s.vt, (size_t)s.n_pad * 3 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMemset(s.vt, 0, (size_t)s.n_pad * 3 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMalloc((void**)&s.skin_idx, (size_t)s.nnz * s.n_pad * sizeof(int32_t)));
+  EG_CUDA_CHECK(cudaMemset(s.skin_idx, 0, (size_t)s.nnz * s.n_pad * sizeof(int32_t)));
+  EG_CUDA_CHECK(cudaMalloc((void**)&s.skin_w, (size_t)s.nnz * s.n_pad * sizeof(float)));
+  EG_CUDA_CHECK(cudaMemset(s.skin_w, 0, (size_t)s.nnz * s.n_pad * sizeof(float)));
+  int32_t* d_vids = nullptr;
+  int rc = dev_alloc_copy(&d_vids, vids.data(), vids.size());
+  if (rc) return rc;
+  EG_LAUNCH(gather_vertex_set_kernel, (n + 63) / 64, 64, 0, 0, h->full.basis,
+            (int64_t)h->full.n_pad * 3, h->full.vt, h->full.skin_idx, h->full.skin_w, h->full.n_pad,
+            s.nnz, d_vids, n, s.n_pad, s.basis, s.vt, s.skin_idx, s.skin_w);
+  EG_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaFree(d_vids);
+  h->compact = s;
+  h->n_markers = n_markers;
+  return EG_OK;
+}
+
+}  // namespace eg
+
+using namespace eg;
+
+extern "C" int eg_lbs_create(const EgLbsModel* m, int device, EgLbs** out) {
+  EG_REQUIRE(m && out, "null pointer");
+  EG_REQUIRE(m->n_joints > 0 && m->n_joints <= MAXJ, "n_joints must be in (0,64]");
+  EG_REQUIRE((m->n_joints - 1) * 9 == m->n_pose_basis, "n_pose_basis must be 9*(n_joints-1)");
+  EG_REQUIRE(m->n_pose_basis + m->n_shape <= KPAD && m->n_shape <= 32, "basis too large");
+  EG_REQUIRE(m->n_hand_pca == 12 && m->n_joints == 55, "SMPL-X layout expected (55 joints, 12 hand PCA)");
+  EG_CUDA_CHECK(cudaSetDevice(device));
+  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VERT_SMEM));
+  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VERT_SMEM));
+  EgLbs* h = new EgLbs();
+  h->device = device;
+  const int V = h->V = m->n_verts, J = h->J = m->n_joints, S = h->S = m->n_shape, P = h->P = m->n_pose_basis;
+  h->n_extra = m->n_extra; h->n_lmk = m->n_landmarks;
+  h->h_extra.assign(m->extra_vids, m->extra_vids + m->n_extra);
+  for (int l = 0; l < m->n_landmarks; ++l) {
+    const int f = m->lmk_faces_idx[l];
+    if (f < 0 || f >= m->n_faces) { delete h; return set_error(EG_ERR_INVALID_ARG, "landmark face id out of range"); }
+    for (int c = 0; c < 3; ++c) h->h_lmk_verts.push_back(m->faces[3 * f + c]);
+  }
+  // ---- full vertex set ----
+  VertexSet& s = h->full;
+  s.n = V; s.n_pad = (V + TILE_V - 1) / TILE_V * TILE_V;
+  const size_t row = (size_t)s.n_pad * 3;
+  std::vector<float> basis((size_t)KPAD * row, 0.0f);
+  for (int k = 0; k < P; ++k) memcpy(&basis[k * row], m->posedirs + (size_t)k * V * 3, (size_t)V * 3 * sizeof(float));
+  for (int k = 0; k < S; ++k)
+    for (size_t c = 0; c < (size_t)V * 3; ++c) basis[(size_t)(P + k) * row + c] = m->shapedirs[c * S + k];
+  std::vector<float> vt(row, 0.0f);
+  memcpy(vt.data(), m->v_template, (size_t)V * 3 * sizeof(float));
+  int nnz = 1;
+  for (int v = 0; v < V; ++v) {
+    int c = 0;
+    for (int j = 0; j < J; ++j) c += m->lbs_weights[(size_t)v * J + j] != 0.0f;
+    nnz = std::max(nnz, c);
+  }
+  s.nnz = nnz;
+  std::vector<int32_t> sidx((size_t)nnz * s.n_pad, 0);
+  std::vector<float> sw((size_t)nnz * s.n_pad, 0.0f);
+  for (int v = 0; v < V; ++v) {
+    int c = 0;
+    for (int j = 0; j < J; ++j) {                 // ascending joint order = dense matmul order
+      const float w = m->lbs_weights[(size_t)v * J + j];
+      if (w != 0.0f) { sidx[(size_t)c * s.n_pad + v] = j; sw[(size_t)c * s.n_pad + v] = w; ++c; }
+    }
+  }
+  // ---- joint regressor folded through template / shapedirs (double accumulation on host) ----
+  std::vector<float> Jt((size_t)J * 3), Js((size_t)J * 3 * S);
+  for (int j = 0; j < J; ++j) {
+    double t[3] = {0, 0, 0};
+    std::vector<double> sd((size_t)3 * S, 0.0);
+    for (int v = 0; v < V; ++v) {
+      const double w = m->J_regressor[(size_t)j * V + v];
+      if (w == 0.0) continue;
+      for (int c = 0; c < 3; ++c) {
+        t[c] += w * m->v_template[(size_t)v * 3 + c];
+        for (int k = 0; k < S; ++k) sd[c * S + k] += w * m->shapedirs[((size_t)v * 3 + c) * S + k];
+      }
+    }
+    for (int c = 0; c < 3; ++c) {
+      Jt[j * 3 + c] = (float)t[c];
+      for (int k = 0; k < S; ++k) Js[((size_t)j * 3 + c) * S + k] = (float)sd[c * S + k];
+    }
+  }
+  // ---- tree levels ----
+  std::vector<int> depth(J, 0);
+  int maxd = 0;
+  for (int j = 0; j < J; ++j) {
+    const int p = m->parents[j];
+    if (p >= j) { delete h; return set_error(EG_ERR_INVALID_ARG, "parents must precede children"); }
+    depth[j] = p < 0 ? 0 : depth[p] + 1;
+    maxd = std::max(maxd, depth[j]);
+  }
+  std::vector<int32_t> lj, ls;
+  for (int d = 0; d <= maxd; ++d) {
+    ls.push_back((int32_t)lj.size());
+    for (int j = 0; j < J; ++j) if (depth[j] == d) lj.push_back(j);
+  }
+  ls.push_back((int32_t)lj.size());
+  h->n_levels = maxd + 1;
+  int rc = 0;
+  rc |= dev_alloc_copy(&s.basis, basis.data(), basis.size());
+  rc |= dev_alloc_copy(&s.vt, vt.data(), vt.size());
+  rc |= dev_alloc_copy(&s.skin_idx, sidx.data(), sidx.size());
+  rc |= dev_alloc_copy(&s.skin_w, sw.data(), sw.size());
+  rc |= dev_alloc_copy(&h->Jt, Jt.data(), Jt.size());
+  rc |= dev_alloc_copy(&h->Js, Js.data(), Js.size());
+  rc |= dev_alloc_copy(&h->hand_l, m->hand_comp_l, (size_t)12 * 45);
+  rc |= dev_alloc_copy(&h->hand_r, m->hand_comp_r, (size_t)12 * 45);
+  rc |= dev_alloc_copy(&h->pose_mean, m->pose_mean, (size_t)J * 3);
+  rc |= dev_alloc_copy(&h->parents, m->parents, (size_t)J);
+  rc |= dev_alloc_copy(&h->level_joints, lj.data(), lj.size());
+  rc |= dev_alloc_copy(&h->level_start, ls.data(), ls.size());
+  rc |= dev_alloc_copy(&h->lmk_bary, m->lmk_bary, (size_t)m->n_landmarks * 3);
+  if (rc) { eg_lbs_destroy(h); return EG_ERR_CUDA; }
+  rc = build_compact(h, nullptr, 0);   // vertex joints + landmarks only, until markers are set
+  if (rc) { eg_lbs_destroy(h); return rc; }
+  *out = h;
+  return EG_OK;
+}
+
+extern "C" void eg_lbs_destroy(EgLbs* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  free_vertex_set(h->full);
+  free_vertex_set(h->compact);
+  cudaFree(h->Jt); cudaFree(h->Js); cudaFree(h->hand_l); cudaFree(h->hand_r); cudaFree(h->pose_mean);
+  cudaFree(h->parents); cudaFree(h->level_joints); cudaFree(h->level_start); cudaFree(h->lmk_bary);
+  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_);
+  delete h;
+}
+
+extern "C" int eg_lbs_set_markers(EgLbs* h, const int32_t* marker_vids_host, int n_markers) {
+  EG_REQUIRE(h && (marker_vids_host || n_markers == 0) && n_markers >= 0, "bad arguments");
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  return build_compact(h, marker_vids_host, n_markers);
+}
+
+extern "C" int eg_lbs_max_skin_nnz(const EgLbs* h) { return h ? h->full.nnz : 0; }
+
+extern "C" int eg_lbs_forward(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
+                              float* verts, float* joints, float* markers, void* stream) {
+  EG_REQUIRE(h != nullptr, "null handle");
+  EG_REQUIRE(markers == nullptr || h->n_markers > 0, "markers requested but none set");
+  return run_forward(h, xb, betas, betas_rows, N, verts, joints, markers, false, 1, nullptr, nullptr,
+                     SdfGrid{}, nullptr, nullptr, as_stream(stream));
+}
+
+extern "C" int eg_lbs_forward_sdf(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
+                                  int frames_per_env, const float* R0, const float* T0,
+                                  const float* grid, int D0, int D1, int D2, const float* center_dev,
+                                  const float* scale_dev, const uint8_t* skip_mask, int32_t* counts,
+                                  float* joints, float* markers, void* stream) {
+  EG_REQUIRE(h != nullptr, "null handle");
+  EG_REQUIRE(R0 && T0 && grid && center_dev && scale_dev && counts, "null pointer");
+  EG_REQUIRE(frames_per_env > 0 && N % frames_per_env == 0, "N must be a multiple of frames_per_env");
+  EG_REQUIRE(markers == nullptr || h->n_markers > 0, "markers requested but none set");
+  SdfGrid g{grid, D0, D1, D2, center_dev, scale_dev};
+  return run_forward(h, xb, betas, betas_rows, N, nullptr, joints, markers, true, frames_per_env, R0,
+                     T0, g, skip_mask, counts, as_stream(stream));
+}

@@ -1,0 +1,378 @@
+// Dense-layer kernels (fp32 SIMT GEMM with fused bias/activation/residual epilogue, GRU gates,
+// BatchNorm-eval) and the two inference-only network operators of the env step:
+//   * GAMMAPrimitiveCombo.sample_prior  (reference motion/models/models_GAMMA_primitive.py:334-360,
+//     predictor decode :83-101, regressor :222-301, 6-D -> axis-angle :208-219 + baseops.py:120-162)
+//   * VPoser v1 encoder `.loc`         (reference call site crowd_env_2f.py:197-200)
+#include <vector>
+
+#include "geom.cuh"
+#include "nn.cuh"
+
+namespace eg {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case ACT_TANH: return tanhf(v);
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    case ACT_LRELU: return v > 0.0f ? v : v * slope;
+    default: return v;
+  }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      int m, k;
+      if (TA) { k = idx / BM; m = idx % BM; } else { m = idx / BK; k = idx % BK; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.0f;
+      if (gm < g.M && gk < g.K)
+        v = TA ? __ldg(g.A + (int64_t)gk * g.lda + gm) : __ldg(g.A + (int64_t)(gm / g.a_div) * g.lda + gk);
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      int n, k;
+      if (TB) { n = idx / BK; k = idx % BK; } else { k = idx / BN; n = idx % BN; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.0f;
+      if (gn < g.N && gk < g.K)
+        v = TB ? __ldg(g.B + (int64_t)gn * g.ldb + gk) : __ldg(g.B + (int64_t)gk * g.ldb + gn);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = g.alpha * acc[i][j];
+      if (g.bias) v += __ldg(g.bias + n);
+      if (g.beta) v += g.C[(int64_t)m * g.ldc + n];
+      v = apply_act(v, g.act, g.slope);
+      if (g.residual) v += g.residual[(int64_t)m * g.ldr + n];
+      g.C[(int64_t)m * g.ldc + n] = v;
+    }
+  }
+}
+
+int launch_gemm(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return EG_OK;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  if (!TA && TB) EG_LAUNCH((gemm_kernel<false, true>), grid, 256, 0, st, g);
+  else if (!TA && !TB) EG_LAUNCH((gemm_kernel<false, false>), grid, 256, 0, st, g);
+  else if (TA && !TB) EG_LAUNCH((gemm_kernel<true, false>), grid, 256, 0, st, g);
+  else EG_LAUNCH((gemm_kernel<true, true>), grid, 256, 0, st, g);
+  return EG_OK;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ b_hh,
+                const float* __restrict__ h_in, float* __restrict__ h_out, int M, int H, int ld_h_out,
+                float* r_save, float* z_save, float* n_save, float* ghn_save) {
+  const int64_t total = (int64_t)M * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / H), j = (int)(i % H);
+    const float* gim = gi + (int64_t)m * 3 * H;
+    float hr, hz, hn, hp;
+    if (gh) {
+      const float* ghm = gh + (int64_t)m * 3 * H;
+      hr = ghm[j]; hz = ghm[H + j]; hn = ghm[2 * H + j];
+      hp = h_in[(int64_t)m * H + j];
+    } else {
+      hr = __ldg(b_hh + j); hz = __ldg(b_hh + H + j); hn = __ldg(b_hh + 2 * H + j);
+      hp = 0.0f;
+    }
+    const float r = sigmoidf_(gim[j] + hr);
+    const float z = sigmoidf_(gim[H + j] + hz);
+    const float n = tanhf(gim[2 * H + j] + r * hn);
+    h_out[(int64_t)m * ld_h_out + j] = (1.0f - z) * n + z * hp;
+    if (r_save) { r_save[i] = r; z_save[i] = z; n_save[i] = n; ghn_save[i] = hn; }
+  }
+}
+
+int launch_gru_gate(cudaStream_t st, const float* gi, const float* gh, const float* b_hh,
+                    const float* h_in, float* h_out, int M, int H, int ld_h_out, float* r_save,
+                    float* z_save, float* n_save, float* ghn_save) {
+  const int64_t total = (int64_t)M * H;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, kNumSMs * 8);
+  EG_LAUNCH(gru_gate_kernel, grid, 256, 0, st, gi, gh, b_hh, h_in, h_out, M, H, ld_h_out, r_save, z_save,
+            n_save, ghn_save);
+  return EG_OK;
+}
+
+// eval-mode BatchNorm1d: y = (x - mean) / sqrt(var + eps) * gamma + beta
+__global__ void __launch_bounds__(256)
+bn_eval_kernel(const float* __restrict__ x, int ldx, int M, int D, const float* __restrict__ gamma,
+               const float* __restrict__ beta, const float* __restrict__ mean,
+               const float* __restrict__ var, float eps, float* __restrict__ y) {
+  const int64_t total = (int64_t)M * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / D), j = (int)(i % D);
+    const float v = x[(int64_t)m * ldx + j];
+    y[i] = (v - __ldg(mean + j)) / sqrtf(__ldg(var + j) + eps) * __ldg(gamma + j) + __ldg(beta + j);
+  }
+}
+
+// copy the two history frames' markers into Y[B,20,201]
+__global__ void copy_history_kernel(const float* __restrict__ X, int ldx_env, int ldx_frame, int B, int D,
+                                    float* __restrict__ Y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 2 * D) return;
+  const int b = i / (2 * D), t = (i / D) % 2, d = i % D;
+  Y[((int64_t)b * 20 + t) * D + d] = X[(int64_t)b * ldx_env + t * ldx_frame + d];
+}
+
+// regressor tail (models_GAMMA_primitive.py:208-219): 22 x 6-D -> rotmat (Gram-Schmidt) -> axis-angle
+// (torchgeometry 0.1.2 rotation_matrix_to_angle_axis); writes Yb[b][t][93] for frames t >= t_skip.
+__global__ void __launch_bounds__(128)
+regressor_tail_kernel(const float* __restrict__ xb_cont, int M, int frames, int t_skip, float* __restrict__ Yb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (row, joint-or-misc slot)
+  const int row = i / 32, slot = i % 32;
+  if (row >= M) return;
+  if ((row % frames) < t_skip) return;
+  const float* x = xb_cont + (int64_t)row * 159;
+  float* y = Yb + (int64_t)row * 93;
+  if (slot < 22) {
+    float R[9], aa[3];
+    cont6d_to_rotmat(x + 3 + slot * 6, R);
+    tgm_rotmat_to_aa(R, aa);
+    y[3 + slot * 3 + 0] = aa[0]; y[3 + slot * 3 + 1] = aa[1]; y[3 + slot * 3 + 2] = aa[2];
+  } else if (slot == 22) {
+    y[0] = x[0]; y[1] = x[1]; y[2] = x[2];
+  } else if (slot == 23) {
+    for (int k = 0; k < 24; ++k) y[69 + k] = x[135 + k];
+  }
+}
+
+static inline int ew_grid(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, kNumSMs * 8); }
+
+}  // namespace eg
+
+using namespace eg;
+
+// ------------------------------------------------------------------------------------------
+// Motion model (C-VAE predictor + marker->body regressor)
+// ------------------------------------------------------------------------------------------
+struct EgMotion {
+  int device = 0;
+  EgMotionDims d;
+  std::vector<const float*> w;
+  int cap_B = 0;
+  float *gi = nullptr, *gh = nullptr, *h = nullptr, *hx = nullptr, *c = nullptr, *t1 = nullptr, *t2 = nullptr;
+  float *rh = nullptr, *rbase = nullptr, *rt = nullptr, *xbc = nullptr;
+};
+
+namespace {
+enum {  // weight table order (state_dict names in comments)
+  P_XENC_WIH = 0, P_XENC_WHH, P_XENC_BIH, P_XENC_BHH,         // predictor.x_enc.{weight_ih_l0,weight_hh_l0,bias_ih_l0,bias_hh_l0}
+  P_DRNN_W0, P_DRNN_B0, P_DRNN_W1, P_DRNN_B1, P_DRNN_W2, P_DRNN_B2,   // predictor.drnn_mlp.layers.{0,1,2}
+  P_DRNN_WIH, P_DRNN_WHH, P_DRNN_BIH, P_DRNN_BHH,             // predictor.d_rnn.{weight_ih,weight_hh,bias_ih,bias_hh}
+  P_DMLP_W0, P_DMLP_B0, P_DMLP_W1, P_DMLP_B1,                 // predictor.d_mlp.layers.{0,1}
+  P_DOUT_W, P_DOUT_B,                                         // predictor.d_out
+  R_IN_W, R_IN_B,                                             // regressor.pnet.in_fc
+  R_BLOCKS                                                    // then n_blocks x {l0.w,l0.b,l1.w,l1.b}, out_fc.{w,b}
+};
+
+int motion_ws(EgMotion* h, int B) {
+  if (B <= h->cap_B) return EG_OK;
+  const EgMotionDims& d = h->d;
+  float** bufs[] = {&h->gi, &h->gh, &h->h, &h->hx, &h->c, &h->t1, &h->t2, &h->rh, &h->rbase, &h->rt, &h->xbc};
+  for (auto p : bufs) { cudaFree(*p); *p = nullptr; }
+  h->cap_B = 0;
+  const size_t b = (size_t)B, M = b * 20;
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->gi, b * 3 * d.h_dim * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->gh, b * 3 * d.h_dim * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->h, b * d.h_dim * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->hx, b * d.h_dim * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->c, b * 3 * d.h_dim * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->t1, b * d.mlp_dim * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->t2, b * d.mlp_dim * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->rh, M * d.reg_h * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->rbase, M * d.reg_h * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->rt, M * d.reg_h * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->xbc, M * 159 * 4));
+  h->cap_B = B;
+  return EG_OK;
+}
+}  // namespace
+
+extern "C" int eg_motion_create(const EgMotionDims* dims, const void* const* weights_host, int n_weights,
+                                int device, EgMotion** out) {
+  EG_REQUIRE(dims && weights_host && out, "null pointer");
+  EG_REQUIRE(dims->in_dim == 201 && dims->body_dim == 159, "marker dim 201 / cont body dim 159 expected");
+  const int expect = R_BLOCKS + dims->reg_blocks * 4 + 2;
+  EG_REQUIRE(n_weights == expect, "unexpected number of weight tensors");
+  for (int i = 0; i < n_weights; ++i) EG_REQUIRE(weights_host[i] != nullptr, "null weight pointer");
+  EgMotion* h = new EgMotion();
+  h->device = device; h->d = *dims;
+  h->w.assign((const float* const*)weights_host, (const float* const*)weights_host + n_weights);
+  *out = h;
+  return EG_OK;
+}
+
+extern "C" void eg_motion_destroy(EgMotion* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  float* bufs[] = {h->gi, h->gh, h->h, h->hx, h->c, h->t1, h->t2, h->rh, h->rbase, h->rt, h->xbc};
+  for (auto p : bufs) cudaFree(p);
+  delete h;
+}
+
+extern "C" int eg_motion_sample_prior(EgMotion* hd, const float* X, int ldx_env, int ldx_frame,
+                                      const float* z, const float* betas, int B, float* Y, float* Yb,
+                                      void* stream) {
+  EG_REQUIRE(hd && X && z && betas && Y && Yb, "null pointer");
+  EG_REQUIRE(B >= 0, "negative batch");
+  if (B == 0) return EG_OK;
+  EG_CUDA_CHECK(cudaSetDevice(hd->device));
+  int rc = motion_ws(hd, B);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  const EgMotionDims& d = hd->d;
+  const int D = d.in_dim, H = d.h_dim, Z = d.z_dim, Hm = d.mlp_dim, H3 = 3 * H;
+  const float* const* w = hd->w.data();
+#define EG_TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  EG_LAUNCH(copy_history_kernel, (B * 2 * D + 255) / 256, 256, 0, st, X, ldx_env, ldx_frame, B, D, Y);
+  // ---- x_enc GRU over the 2 history frames (h0 = 0) ----
+  const int ldY = 20 * D;
+  EG_TRY(linear(st, Y, ldY, B, w[P_XENC_WIH], D, w[P_XENC_BIH], D, H3, hd->gi, H3));
+  EG_TRY(launch_gru_gate(st, hd->gi, nullptr, w[P_XENC_BHH], nullptr, hd->h, B, H, H));
+  EG_TRY(linear(st, Y + D, ldY, B, w[P_XENC_WIH], D, w[P_XENC_BIH], D, H3, hd->gi, H3));
+  EG_TRY(linear(st, hd->h, H, B, w[P_XENC_WHH], H, w[P_XENC_BHH], H, H3, hd->gh, H3));
+  EG_TRY(launch_gru_gate(st, hd->gi, hd->gh, nullptr, hd->h, hd->hx, B, H, H));
+  // ---- h_rnn = drnn_mlp(hx) ----
+  EG_TRY(linear(st, hd->hx, H, B, w[P_DRNN_W0], H, w[P_DRNN_B0], H, Hm, hd->t1, Hm, ACT_TANH));
+  EG_TRY(linear(st, hd->t1, Hm, B, w[P_DRNN_W1], Hm, w[P_DRNN_B1], Hm, H, hd->t2, H, ACT_TANH));
+  EG_TRY(linear(st, hd->t2, H, B, w[P_DRNN_W2], H, w[P_DRNN_B2], H, H, hd->h, H, ACT_TANH));
+  // ---- step-invariant part of the GRUCell input: [hx, z] W_ih[:, :H+Z]^T + b_ih ----
+  const int Kin = H + Z + D;
+  EG_TRY(linear(st, hd->hx, H, B, w[P_DRNN_WIH], Kin, w[P_DRNN_BIH], H, H3, hd->c, H3));
+  EG_TRY(linear(st, z, Z, B, w[P_DRNN_WIH] + H, Kin, nullptr, Z, H3, hd->c, H3, ACT_NONE, 0.f, nullptr, 0, 1));
+  for (int i = 0; i < 18; ++i) {
+    const float* yp = Y + (1 + i) * D;     // previous frame (history frame 1 for i == 0)
+    float* yo = Y + (2 + i) * D;
+    EG_TRY(linear(st, yp, ldY, B, w[P_DRNN_WIH] + H + Z, Kin, nullptr, D, H3, hd->gi, H3, ACT_NONE, 0.f, hd->c, H3));
+    EG_TRY(linear(st, hd->h, H, B, w[P_DRNN_WHH], H, w[P_DRNN_BHH], H, H3, hd->gh, H3));
+    EG_TRY(launch_gru_gate(st, hd->gi, hd->gh, nullptr, hd->h, hd->h, B, H, H));
+    EG_TRY(linear(st, hd->h, H, B, w[P_DMLP_W0], H, w[P_DMLP_B0], H, Hm, hd->t1, Hm, ACT_TANH));
+    EG_TRY(linear(st, hd->t1, Hm, B, w[P_DMLP_W1], Hm, w[P_DMLP_B1], Hm, H, hd->t2, H, ACT_TANH));
+    EG_TRY(linear(st, hd->t2, H, B, w[P_DOUT_W], H, w[P_DOUT_B], H, D, yo, ldY, ACT_NONE, 0.f, yp, ldY));
+  }
+  // ---- regressor over all B*20 marker frames (frames 0,1 are computed and discarded) ----
+  const int M = B * 20, Hr = d.reg_h, BD = d.body_dim, Kr = D + BD + 10;
+  const float* Win = w[R_IN_W];
+  EG_TRY(linear(st, Y, D, M, Win, Kr, w[R_IN_B], D, Hr, hd->rbase, Hr));
+  EG_TRY(linear(st, betas, 10, M, Win + D + BD, Kr, nullptr, 10, Hr, hd->rbase, Hr, ACT_NONE, 0.f, nullptr, 0, 1, 20));
+  const float* const* wb = w + R_BLOCKS;
+  const float* Wout = wb[d.reg_blocks * 4];
+  const float* Bout = wb[d.reg_blocks * 4 + 1];
+  for (int r = 0; r < d.reg_recur; ++r) {
+    const float* hcur = hd->rbase;
+    if (r > 0) {   // h = base + xb W_in[:, 201:360]^T
+      EG_TRY(linear(st, hd->xbc, BD, M, Win + D, Kr, nullptr, BD, Hr, hd->rh, Hr, ACT_NONE, 0.f, hd->rbase, Hr));
+      hcur = hd->rh;
+    }
+    for (int k = 0; k < d.reg_blocks; ++k) {
+      EG_TRY(linear(st, hcur, Hr, M, wb[k * 4], Hr, wb[k * 4 + 1], Hr, Hr, hd->rt, Hr, ACT_RELU));
+      EG_TRY(linear(st, hd->rt, Hr, M, wb[k * 4 + 2], Hr, wb[k * 4 + 3], Hr, Hr, hd->rh, Hr, ACT_RELU, 0.f, hcur, Hr));
+      hcur = hd->rh;
+    }
+    // xb = out_fc(h) + xb   (xb starts at zero)
+    EG_TRY(linear(st, hcur, Hr, M, Wout, Hr, Bout, Hr, BD, hd->xbc, BD, ACT_NONE, 0.f, r > 0 ? hd->xbc : nullptr, BD));
+  }
+  EG_LAUNCH(regressor_tail_kernel, (M * 32 + 127) / 128, 128, 0, st, hd->xbc, M, 20, 2, Yb);
+#undef EG_TRY
+  return EG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// VPoser v1 encoder (.loc)
+// ------------------------------------------------------------------------------------------
+struct EgVposer {
+  int device = 0;
+  std::vector<const float*> w;   // bn1.{weight,bias,running_mean,running_var}, fc1.{w,b}, bn2.{...}, fc2.{w,b}, mu.{w,b}
+  int cap_M = 0;
+  float *a = nullptr, *b = nullptr;
+};
+
+extern "C" int eg_vposer_create(const void* const* weights_host, int n_weights, int device, EgVposer** out) {
+  EG_REQUIRE(weights_host && out && n_weights == 14, "expected 14 weight tensors");
+  EgVposer* h = new EgVposer();
+  h->device = device;
+  h->w.assign((const float* const*)weights_host, (const float* const*)weights_host + n_weights);
+  *out = h;
+  return EG_OK;
+}
+
+extern "C" void eg_vposer_destroy(EgVposer* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->a); cudaFree(h->b);
+  delete h;
+}
+
+extern "C" int eg_vposer_encode(EgVposer* h, const float* x, int ldx, int M, float* loc, void* stream) {
+  EG_REQUIRE(h && x && loc && M >= 0, "bad arguments");
+  if (M == 0) return EG_OK;
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  if (M > h->cap_M) {
+    cudaFree(h->a); cudaFree(h->b); h->a = h->b = nullptr; h->cap_M = 0;
+    EG_CUDA_CHECK(cudaMalloc((void**)&h->a, (size_t)M * 512 * 4));
+    EG_CUDA_CHECK(cudaMalloc((void**)&h->b, (size_t)M * 512 * 4));
+    h->cap_M = M;
+  }
+  cudaStream_t st = as_stream(stream);
+  const float* const* w = h->w.data();
+  int rc;
+  EG_LAUNCH(bn_eval_kernel, ew_grid((int64_t)M * 63), 256, 0, st, x, ldx, M, 63, w[0], w[1], w[2], w[3], 1e-5f, h->a);
+  if ((rc = linear(st, h->a, 63, M, w[4], 63, w[5], 63, 512, h->b, 512, ACT_LRELU, 0.2f))) return rc;
+  EG_LAUNCH(bn_eval_kernel, ew_grid((int64_t)M * 512), 256, 0, st, h->b, 512, M, 512, w[6], w[7], w[8], w[9], 1e-5f, h->a);
+  if ((rc = linear(st, h->a, 512, M, w[10], 512, w[11], 512, 512, h->b, 512, ACT_LRELU, 0.2f))) return rc;
+  if ((rc = linear(st, h->b, 512, M, w[12], 512, w[13], 512, 32, loc, 32))) return rc;
+  return EG_OK;
+}
+
+// generic dense layer exposed for tests and host-side composition
+extern "C" int eg_linear_forward(const float* x, int ldx, int M, const float* W, const float* b, int in_dim,
+                                 int out_dim, int act, float slope, const float* residual, int ldr, float* y,
+                                 int ldy, void* stream) {
+  EG_REQUIRE(x && W && y && M >= 0 && in_dim > 0 && out_dim > 0, "bad arguments");
+  return linear(as_stream(stream), x, ldx, M, W, in_dim, b, in_dim, out_dim, y, ldy, act, slope, residual, ldr);
+}

@@ -1,0 +1,126 @@
+// SDF-grid kernels: trilinear sample (calc_sdf), penetration count, sphere-traced ego depth.
+// HBM/L2-bound gather work: one thread per query point, coalesced point reads, the 3-D grid stays
+// resident (256^3 fp32 = 67 MB < 126 MB L2) so the 8 corner gathers are L2 hits after first touch.
+#include "common.cuh"
+
+namespace eg {
+
+__global__ void __launch_bounds__(256)
+sdf_sample_kernel(SdfGrid g, const float* __restrict__ pts, int64_t P, float* __restrict__ val,
+                  int32_t* __restrict__ base_idx) {
+  const float cx = __ldg(g.center), cy = __ldg(g.center + 1), cz = __ldg(g.center + 2);
+  const float s = __ldg(g.scale);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
+    int ox, oy, oz;
+    const float v = sdf_sample_point(g, cx, cy, cz, s, x, y, z, ox, oy, oz);
+    val[i] = v;
+    if (base_idx) {
+      base_idx[3 * i] = ox;
+      base_idx[3 * i + 1] = oy;
+      base_idx[3 * i + 2] = oz;
+    }
+  }
+}
+
+// one CTA per body: count sdf<0 over non-skipped vertices (crowd_env_2f.py:171,174-175)
+__global__ void __launch_bounds__(256)
+penetration_count_kernel(const float* __restrict__ sdf, int V, const uint8_t* __restrict__ skip,
+                         int32_t* __restrict__ counts) {
+  const float* row = sdf + (int64_t)blockIdx.x * V;
+  int c = 0;
+  for (int v = threadIdx.x; v < V; v += blockDim.x)
+    c += (row[v] < 0.0f && !(skip && skip[v])) ? 1 : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += part[w];
+    counts[blockIdx.x] = t;
+  }
+}
+
+// Sphere tracing through the calc_sdf field: t += max(d, hit_eps) until d < hit_eps, t > max_range
+// or max_steps (oracle/ego_depth.py defines the same loop). One thread per ray; rays of one camera
+// are adjacent so neighbouring threads walk neighbouring cells.
+__global__ void __launch_bounds__(256)
+ego_depth_kernel(SdfGrid g, const float* __restrict__ cam, int A, int H, int W, float fx, float fy,
+                 float max_range, int max_steps, float hit_eps, float* __restrict__ depth,
+                 int32_t* __restrict__ steps_out) {
+  const float cx = __ldg(g.center), cy = __ldg(g.center + 1), cz = __ldg(g.center + 2);
+  const float s = __ldg(g.scale);
+  const int64_t total = (int64_t)A * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(i / (H * W));
+    const int r = (int)(i % (H * W));
+    const int py = r / W, px = r % W;
+    const float* c = cam + 12 * a;
+    const float u = ((float)px + 0.5f - 0.5f * (float)W) / fx;
+    const float v = ((float)py + 0.5f - 0.5f * (float)H) / fy;
+    float dx = c[9] + u * c[3] - v * c[6];
+    float dy = c[10] + u * c[4] - v * c[7];
+    float dz = c[11] + u * c[5] - v * c[8];
+    const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= inv; dy *= inv; dz *= inv;
+    float t = 0.0f;
+    int it = 0;
+    for (; it < max_steps; ++it) {
+      int ox, oy, oz;
+      const float d = sdf_sample_point(g, cx, cy, cz, s, c[0] + t * dx, c[1] + t * dy, c[2] + t * dz,
+                                       ox, oy, oz);
+      if (d < hit_eps) break;
+      t += fmaxf(d, hit_eps);
+      if (t > max_range) { t = max_range; break; }
+    }
+    depth[i] = fminf(t, max_range);
+    if (steps_out) steps_out[i] = it;
+  }
+}
+
+static inline int grid_for(int64_t n, int block) {
+  int64_t b = (n + block - 1) / block;
+  const int64_t cap = (int64_t)kNumSMs * 16;  // multiple of the SM count, grid-stride beyond
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace eg
+
+using namespace eg;
+
+extern "C" int eg_sdf_sample(const float* grid, int D0, int D1, int D2, const float* center_dev,
+                             const float* scale_dev, const float* pts, int64_t P, float* val,
+                             int32_t* base_idx, void* stream) {
+  EG_REQUIRE(D0 > 0 && D1 > 0 && D2 > 0 && P >= 0, "bad sizes");
+  if (P == 0) return EG_OK;   // empty batch: nothing to do (torch gives NULL data pointers here)
+  EG_REQUIRE(grid && center_dev && scale_dev && val && pts, "null pointer");
+  SdfGrid g{grid, D0, D1, D2, center_dev, scale_dev};
+  EG_LAUNCH(sdf_sample_kernel, grid_for(P, 256), 256, 0, as_stream(stream), g, pts, P, val, base_idx);
+  return EG_OK;
+}
+
+extern "C" int eg_penetration_count(const float* sdf_vals, int N, int V, const uint8_t* skip_mask,
+                                    int32_t* counts, void* stream) {
+  EG_REQUIRE(sdf_vals && counts && N >= 0 && V > 0, "bad arguments");
+  if (N == 0) return EG_OK;
+  EG_LAUNCH(penetration_count_kernel, N, 256, 0, as_stream(stream), sdf_vals, V, skip_mask, counts);
+  return EG_OK;
+}
+
+extern "C" int eg_ego_depth(const float* grid, int D0, int D1, int D2, const float* center_dev,
+                            const float* scale_dev, const float* cam, int A, int H, int W, float fx,
+                            float fy, float max_range, int max_steps, float hit_eps, float* depth,
+                            int32_t* steps_out, void* stream) {
+  EG_REQUIRE(grid && center_dev && scale_dev && cam && depth, "null pointer");
+  EG_REQUIRE(A >= 0 && H > 0 && W > 0 && max_steps > 0, "bad sizes");
+  if (A == 0) return EG_OK;
+  SdfGrid g{grid, D0, D1, D2, center_dev, scale_dev};
+  EG_LAUNCH(ego_depth_kernel, grid_for((int64_t)A * H * W, 256), 256, 0, as_stream(stream), g, cam, A,
+            H, W, fx, fy, max_range, max_steps, hit_eps, depth, steps_out);
+  return EG_OK;
+}

@@ -1,0 +1,173 @@
+/*
+ * egogen_b200 - C ABI of the B200-native crowd_ppo hot path.
+ *
+ * The reference (ligengen/EgoGen @ ce2c590) is pure Python and has no FFI layer; its "operator
+ * API" for this path is a set of Python call surfaces. Each entry point
+ * below replaces the arithmetic behind one of those surfaces and cites it. The Python host side
+ * (egogen_b200/*.py) mirrors the reference's class / function names and calls these through
+ * ctypes; see INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every `const float*` / `float*` / `int32_t*` argument is a DEVICE pointer
+ *     to contiguous row-major memory owned by the caller unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are
+ *     asynchronous w.r.t. the host and ordered on that stream;
+ *   - return 0 on success, a negative EG_ERR_* otherwise; eg_last_error() gives the message
+ *     (thread-local);
+ *   - handles are bound to one device and are not thread-safe; no allocation happens inside a
+ *     hot call unless a batch larger than any seen before forces the workspace to grow.
+ */
+#ifndef EGOGEN_B200_H
+#define EGOGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EG_OK 0
+#define EG_ERR_INVALID_ARG (-1)
+#define EG_ERR_CUDA (-2)
+#define EG_ERR_ALLOC (-3)
+#define EG_ERR_STATE (-4)
+
+#define EG_SMPLX_V 10475
+#define EG_SMPLX_J 55
+#define EG_SMPLX_JOINTS_OUT 127
+#define EG_XB_DIM 93
+
+int eg_version(void);
+const char* eg_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches counter) */
+int64_t eg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * calc_sdf  - replaces motion/crowd_ppo/utils.py:54-84 (F.grid_sample 5-D trilinear,
+ * align_corners=False, padding_mode='border', negated). grid is sdf[D0,D1,D2] with vertex
+ * x -> axis 0 (slowest). pts [P,3] world space. val [P] (negative = penetration).
+ * base_idx (nullable) [P,3] int32 = floor of the clamped un-normalised index per axis, the
+ * bit-exact parity target. center_dev [3], scale_dev [1] are device pointers (the reference keeps
+ * them as CUDA tensors, main_ppo.py:302-304).
+ * ------------------------------------------------------------------------------------------ */
+int eg_sdf_sample(const float* grid, int D0, int D1, int D2, const float* center_dev,
+                  const float* scale_dev, const float* pts, int64_t P, float* val,
+                  int32_t* base_idx, void* stream);
+
+/* crowd_env_2f.py:170-176: per-body count of vertices with sdf < 0, skipping vertices whose
+ * skip_mask byte is non-zero (feet). sdf_vals [N,V]; counts int32 [N]. */
+int eg_penetration_count(const float* sdf_vals, int N, int V, const uint8_t* skip_mask,
+                         int32_t* counts, void* stream);
+
+/* Config-5 ego-depth sweep (no reference implementation): sphere-trace
+ * H*W pinhole rays per camera through the same SDF grid / calc_sdf sampling. cam [A,12] =
+ * (eye xyz, right xyz, up xyz, forward xyz); depth [A,H,W] metres (max_range where nothing hit);
+ * steps_out (nullable) int32 [A,H,W] = sphere-trace iterations used. */
+int eg_ego_depth(const float* grid, int D0, int D1, int D2, const float* center_dev,
+                 const float* scale_dev, const float* cam, int A, int H, int W, float fx, float fy,
+                 float max_range, int max_steps, float hit_eps, float* depth, int32_t* steps_out,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SMPL-X linear blend skinning - replaces smplx.SMPLX.forward / smplx.lbs.lbs behind
+ * SMPLXParser.forward_smplx (motion/models/baseops.py:338-398) and its selectors (:401-463).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EgLbs EgLbs;
+
+typedef struct EgLbsModel {          /* all HOST pointers, float32 / int32, row-major */
+  int32_t n_verts;                   /* 10475 */
+  int32_t n_joints;                  /* 55 */
+  int32_t n_shape;                   /* 20 = 10 betas + 10 expression */
+  int32_t n_pose_basis;              /* 486 */
+  int32_t n_faces;
+  int32_t n_hand_pca;                /* 12 */
+  int32_t n_extra;                   /* 21 vertex joints */
+  int32_t n_landmarks;               /* 51 */
+  const float* v_template;           /* [V,3] */
+  const float* shapedirs;            /* [V,3,n_shape] */
+  const float* posedirs;             /* [n_pose_basis, V*3] */
+  const float* J_regressor;          /* [J,V] */
+  const int32_t* parents;            /* [J], parents[0] = -1 */
+  const float* lbs_weights;          /* [V,J] */
+  const float* hand_comp_l;          /* [n_hand_pca,45] */
+  const float* hand_comp_r;          /* [n_hand_pca,45] */
+  const float* pose_mean;            /* [J*3] */
+  const int32_t* extra_vids;         /* [n_extra] */
+  const int32_t* faces;              /* [n_faces,3] */
+  const int32_t* lmk_faces_idx;      /* [n_landmarks] */
+  const float* lmk_bary;             /* [n_landmarks,3] */
+} EgLbsModel;
+
+int eg_lbs_create(const EgLbsModel* model_host, int device, EgLbs** out);
+void eg_lbs_destroy(EgLbs* h);
+/* marker placement (baseops.py:328-335): vertex ids whose positions eg_lbs_forward returns in
+ * `markers`. Rebuilds the compact vertex set (markers + vertex joints + landmark corners). */
+int eg_lbs_set_markers(EgLbs* h, const int32_t* marker_vids_host, int n_markers);
+int eg_lbs_max_skin_nnz(const EgLbs* h);
+
+/* xb [N,93] = [transl3, global_orient3, body_pose63, lhand_pca12, rhand_pca12] (baseops.py:366-374),
+ * betas [betas_rows,10] with betas_rows in {1,N}; expression / jaw / eye poses are zero as in the
+ * reference. Outputs (each nullable): verts [N,V,3], joints [N,127,3], markers [N,n_markers,3]. */
+int eg_lbs_forward(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
+                   float* verts, float* joints, float* markers, void* stream);
+
+/* Fused crowd_env_2f.py:133-177 for N = E*frames bodies (env-major): LBS, world transform with the
+ * env's R0 [E,3,3] / T0 [E,3], calc_sdf, feet skip, per-body penetration count - vertices are never
+ * written to HBM. counts int32 [N]; joints / markers as above (body-local frame, not world). */
+int eg_lbs_forward_sdf(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
+                       int frames_per_env, const float* R0, const float* T0, const float* grid,
+                       int D0, int D1, int D2, const float* center_dev, const float* scale_dev,
+                       const uint8_t* skip_mask, int32_t* counts, float* joints, float* markers,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Motion model - replaces GAMMAPrimitiveCombo.sample_prior
+ * (motion/models/models_GAMMA_primitive.py:334-360; predictor decode :83-101, regressor :222-301,
+ * 6-D -> axis-angle tail :208-219). Weights stay in the caller's tensors: `weights_host` is a HOST
+ * array of DEVICE pointers in this state_dict order:
+ *   predictor.x_enc.{weight_ih_l0,weight_hh_l0,bias_ih_l0,bias_hh_l0},
+ *   predictor.drnn_mlp.layers.{0,1,2}.{weight,bias}, predictor.d_rnn.{weight_ih,weight_hh,bias_ih,bias_hh},
+ *   predictor.d_mlp.layers.{0,1}.{weight,bias}, predictor.d_out.{weight,bias},
+ *   regressor.pnet.in_fc.{weight,bias}, regressor.pnet.layers.{0..n-1}.layers.{0,1}.{weight,bias},
+ *   regressor.pnet.out_fc.{weight,bias}
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EgMotion EgMotion;
+typedef struct EgMotionDims {
+  int32_t in_dim;      /* 201 marker coords */
+  int32_t h_dim;       /* 256 */
+  int32_t z_dim;       /* 128 */
+  int32_t mlp_dim;     /* 512 */
+  int32_t reg_h;       /* 128 */
+  int32_t reg_blocks;  /* 10 */
+  int32_t reg_recur;   /* 3 */
+  int32_t body_dim;    /* 159 = 3 + 22*6 + 24 */
+} EgMotionDims;
+
+int eg_motion_create(const EgMotionDims* dims, const void* const* weights_host, int n_weights,
+                     int device, EgMotion** out);
+void eg_motion_destroy(EgMotion* h);
+/* X: marker history, frame t of env b at X + b*ldx_env + t*ldx_frame (201 floats); z [B,128];
+ * betas [B,10]. Y [B,20,201] receives the 2 history frames + 18 predicted frames;
+ * Yb [B,20,93]: frames 2..19 are written (axis-angle body params), frames 0..1 are left untouched. */
+int eg_motion_sample_prior(EgMotion* h, const float* X, int ldx_env, int ldx_frame, const float* z,
+                           const float* betas, int B, float* Y, float* Yb, void* stream);
+
+/* VPoser v1.0 encoder, eval mode, `.loc` only (reference call site crowd_env_2f.py:197-200).
+ * weights_host order: bodyprior_enc_bn1.{weight,bias,running_mean,running_var}, bodyprior_enc_fc1.{weight,bias},
+ * bodyprior_enc_bn2.{weight,bias,running_mean,running_var}, bodyprior_enc_fc2.{weight,bias},
+ * bodyprior_enc_mu.{weight,bias}.  x: row m at x + m*ldx (63 floats); loc [M,32]. */
+typedef struct EgVposer EgVposer;
+int eg_vposer_create(const void* const* weights_host, int n_weights, int device, EgVposer** out);
+void eg_vposer_destroy(EgVposer* h);
+int eg_vposer_encode(EgVposer* h, const float* x, int ldx, int M, float* loc, void* stream);
+
+/* y[M,out] = act(x W^T + b) + residual, W [out,in] row-major (nn.Linear; baseops.py:615-641 MLP layers).
+ * act: 0 none, 1 tanh, 2 relu, 3 leaky-relu(slope). */
+int eg_linear_forward(const float* x, int ldx, int M, const float* W, const float* b, int in_dim,
+                      int out_dim, int act, float slope, const float* residual, int ldr, float* y,
+                      int ldy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOGEN_B200_H */

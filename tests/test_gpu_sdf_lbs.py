@@ -1,0 +1,153 @@
+"""GPU parity: calc_sdf and SMPL-X LBS (through the C ABI / Python mirrors) vs the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from egogen_b200 import assets
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def parser(dev, smplx_model):
+    from egogen_b200 import SMPLXParser
+    return SMPLXParser({"n_batch": 8, "device": dev, "marker_placement": "ssm2_67",
+                        "smplx_models": {"male": smplx_model, "female": smplx_model}})
+
+
+def _t(a):
+    return torch.as_tensor(np.asarray(a))
+
+
+def test_calc_sdf_golden_bit_exact_indices(dev, golden_dir):
+    """Golden vectors from the reference's own calc_sdf (utils.py:54-84): values within 2e-6,
+    `<0` masks identical, base indices identical to the explicit ATen index arithmetic."""
+    from egogen_b200 import calc_sdf
+    from oracle import sdf as osdf
+    g = np.load(os.path.join(golden_dir, "sdf_golden.npz"))
+    for k in "ab":
+        d = {"center": _t(g[f"center_{k}"]), "scale": _t(g[f"scale_{k}"]), "sdf": _t(g[f"grid_{k}"])}
+        pts = _t(g[f"pts_{k}"])
+        val, idx = calc_sdf(pts.to(dev), {kk: v.to(dev) for kk, v in d.items()}, return_index=True)
+        ref = _t(g[f"out_{k}"])
+        _, ridx = osdf.calc_sdf_explicit(pts, d)
+        assert torch.equal(idx.cpu(), ridx)
+        assert torch.allclose(val.cpu(), ref, atol=2e-6, rtol=0)
+        assert torch.equal(val.cpu() < 0, ref < 0)
+
+
+def test_calc_sdf_edge_cases(dev):
+    from egogen_b200 import calc_sdf
+    from oracle import sdf as osdf
+    scene = assets.rasterize_scene_sdf(assets.make_box_scene(3, n_boxes=2), D=32)
+    sd = {k: v.to(dev) for k, v in scene.items()}
+    # empty input
+    out = calc_sdf(torch.zeros(2, 0, 3, device=dev), sd)
+    assert out.shape == (2, 0)
+    # far outside (border clamp), exactly on the faces of the cube, huge values
+    pts = torch.tensor([[[100., -100., 50.], [4., 4., 7.], [-4., -4., -1.], [0., 0., 1e20], [1e-30, 0., 0.]]])
+    val, idx = calc_sdf(pts.to(dev), sd, return_index=True)
+    rv, ridx = osdf.calc_sdf_explicit(pts, scene)
+    assert torch.equal(idx.cpu(), ridx) and torch.allclose(val.cpu(), rv, atol=1e-6)
+    # large random batch: linearity of the sampler in the grid values (size-independent property)
+    P = 1 << 20
+    g = torch.Generator().manual_seed(5)
+    pts = ((torch.rand(1, P, 3, generator=g) * 2 - 1) * 4.5).to(dev)
+    v1 = calc_sdf(pts, sd)
+    sd2 = dict(sd); sd2["sdf"] = sd["sdf"] * 2.0
+    v2 = calc_sdf(pts, sd2)
+    assert torch.allclose(v2, 2 * v1, atol=1e-6)
+
+
+def _rand_inputs(n, seed, scale=0.3):
+    g = torch.Generator().manual_seed(seed)
+    xb = torch.randn(n, 93, generator=g) * scale
+    xb[:, :3] = torch.rand(n, 3, generator=g) * 6 - 3
+    return xb, torch.randn(10, generator=g)
+
+
+@pytest.mark.parametrize("n", [1, 4, 8, 37])
+def test_lbs_matches_oracle(dev, parser, smplx_model, n):
+    """LBS vertices / joints within 1e-4 relative (north_star tolerance) of the smplx restatement."""
+    from oracle.smplx_lbs import SMPLXParserOracle
+    xb, betas = _rand_inputs(n, 100 + n)
+    out = parser.forward_smplx(betas.to(dev), "male", xb.to(dev), to_numpy=False, output_type="raw")
+    ref = SMPLXParserOracle(smplx_model, marker=assets.marker_ids()).forward_smplx(betas, "male", xb, "raw")
+    for a, b in ((out.vertices.cpu(), ref.vertices), (out.joints.cpu(), ref.joints)):
+        assert a.shape == b.shape
+        rel = (a - b).norm(dim=-1).max() / b.norm(dim=-1).max()
+        assert rel < 1e-4, rel                      # tolerance stated by BASELINE.json north_star
+        assert (a - b).abs().max() < 2e-5           # and in practice ~1e-6 absolute (fp32 SIMT)
+    mk = parser.get_markers(betas.to(dev), "male", xb.to(dev), to_numpy=False)
+    assert torch.equal(mk, out.vertices[:, parser.marker])         # compact set == gathered full set
+    j22 = parser.get_jts(betas.to(dev), "male", xb.to(dev), to_numpy=False)
+    assert torch.equal(j22, out.joints[:, :22])
+
+
+def test_lbs_zero_pose_and_betas(dev, parser, smplx_model):
+    """The reference's all-zero case (samplers return betas=0): identity rotations, template + hand mean."""
+    from oracle.smplx_lbs import SMPLXParserOracle
+    xb = torch.zeros(4, 93)
+    betas = torch.zeros(10)
+    out = parser.forward_smplx(betas.to(dev), "male", xb.to(dev), to_numpy=False, output_type="raw")
+    ref = SMPLXParserOracle(smplx_model).forward_smplx(betas, "male", xb, "raw")
+    assert (out.vertices.cpu() - ref.vertices).abs().max() < 1e-5
+    assert (out.joints.cpu() - ref.joints).abs().max() < 1e-5
+
+
+def test_lbs_transl_equivariance_large_batch(dev, parser):
+    """Size-independent property at the bench size (5120 bodies): translating xb translates the output."""
+    n = 5120
+    xb, betas = _rand_inputs(n, 7)
+    xb = xb.to(dev)
+    j0 = parser.get_all_jts(betas.to(dev), "male", xb, to_numpy=False)
+    xb2 = xb.clone(); xb2[:, :3] += torch.tensor([1.0, -2.0, 0.5], device=dev)
+    j1 = parser.get_all_jts(betas.to(dev), "male", xb2, to_numpy=False)
+    assert torch.allclose(j1 - j0, torch.tensor([1.0, -2.0, 0.5], device=dev).expand_as(j0), atol=2e-6)
+
+
+def test_fused_lbs_sdf_counts(dev, parser, smplx_model):
+    """Fused LBS->world->SDF->count equals the unfused operator chain on the same GPU vertices
+    bit-for-bit, and the oracle chain up to vertices within 1e-5 of the SDF zero level."""
+    from egogen_b200 import calc_sdf, penetration_count
+    from oracle import sdf as osdf
+    from oracle.smplx_lbs import SMPLXParserOracle
+    E, T = 3, 20
+    xb, betas = _rand_inputs(E * T, 11)
+    xb[:, :3] *= 0.2
+    scene = assets.rasterize_scene_sdf(assets.make_box_scene(1, n_boxes=2), D=64)
+    sd = {k: v.to(dev) for k, v in scene.items()}
+    g = torch.Generator().manual_seed(3)
+    ang = torch.rand(E, generator=g) * 6.28
+    R0 = torch.zeros(E, 3, 3); R0[:, 0, 0] = ang.cos(); R0[:, 0, 1] = -ang.sin()
+    R0[:, 1, 0] = ang.sin(); R0[:, 1, 1] = ang.cos(); R0[:, 2, 2] = 1
+    T0 = torch.rand(E, 1, 3, generator=g) * 3 - 1.5
+    T0[:, :, 2] = 0.9
+    skip = torch.zeros(assets.V_SMPLX, dtype=torch.uint8)
+    skip[assets.feet_vids()] = 1
+    bm = parser.bm_male
+    counts, joints, markers = bm.forward_sdf(xb.to(dev), betas.to(dev), T, R0.to(dev), T0.to(dev), sd, skip.to(dev))
+    # unfused chain on the GPU
+    out = parser.forward_smplx(betas.to(dev), "male", xb.to(dev), to_numpy=False, output_type="raw")
+    vw = torch.einsum("bij,btpj->btpi", R0.to(dev), out.vertices.view(E, T, -1, 3)) + T0.to(dev)[:, None]
+    sv = calc_sdf(vw.reshape(E * T, -1, 3), sd)
+    c2 = penetration_count(sv, skip.to(dev))
+    near = (sv.abs() < 1e-5).sum(dim=1).cpu()
+    assert ((counts.cpu() - c2.cpu()).abs() <= near).all()
+    assert torch.equal(joints, out.joints) and torch.equal(markers, out.vertices[:, parser.marker])
+    assert counts.sum() > 0, "test scene should produce some penetrations"
+    # oracle chain
+    ref = SMPLXParserOracle(smplx_model).forward_smplx(betas, "male", xb, "raw")
+    rvw = torch.einsum("bij,btpj->btpi", R0, ref.vertices.view(E, T, -1, 3)) + T0[:, None]
+    rs = osdf.calc_sdf(rvw.reshape(E * T, -1, 3), scene).reshape(E, T, -1)
+    rc, _, _ = osdf.penetration_counts(rs, assets.feet_vids(), T)
+    near_o = (rs.abs() < 1e-4).sum(dim=-1)
+    assert ((counts.cpu().view(E, T) - rc).abs() <= near_o).all()
