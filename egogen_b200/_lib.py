@@ -27,6 +27,31 @@ class EgLbsModel(C.Structure):
                                           "extra_vids", "faces", "lmk_faces_idx", "lmk_bary")]
 
 
+class EgMotionDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("in_dim", "h_dim", "z_dim", "mlp_dim", "reg_h", "reg_blocks",
+                                         "reg_recur", "body_dim")]
+
+
+class EgPolicyDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("in_dim", "ego_dim", "h_dim", "pe_L", "n_blocks", "z_dim")]
+
+
+class EgEnvConfig(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("finetuning", C.c_int32), ("pene_terminate_count", C.c_int32),
+                ("feet_marker_idx", C.c_int32 * 6), ("reproj_factor", C.c_float), ("goal_thresh", C.c_float)] + \
+               [(n, C.c_float) for n in ("w_skate", "w_floor", "w_face", "w_look", "w_success", "w_dist",
+                                         "w_vp", "w_pene", "ray_len")]
+
+
+ENV_BUFFER_FIELDS = ("state", "seed", "R0", "T0", "betas", "dist", "steps", "goal", "ego", "obs_dist",
+                     "obs_time", "reward", "terminated", "goal_reached", "reward_terms", "out_markers",
+                     "out_params", "out_pelvis")
+
+
+class EgEnvBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ENV_BUFFER_FIELDS]
+
+
 # name -> (restype, argtypes); the test-suite checks every prototype in the header is listed here
 _I, _L, _F, _P = C.c_int, C.c_int64, C.c_float, C.c_void_p
 PROTOTYPES = {
@@ -40,6 +65,30 @@ PROTOTYPES = {
     "eg_lbs_destroy": (None, [_P]),
     "eg_lbs_set_markers": (_I, [_P, _P, _I]),
     "eg_lbs_max_skin_nnz": (_I, [_P]),
+    "eg_lbs_rest_pelvis": (_I, [_P, _P, _I, _I, _P, _P]),
+    "eg_motion_create": (_I, [C.POINTER(EgMotionDims), _P, _I, _I, C.POINTER(_P)]),
+    "eg_motion_destroy": (None, [_P]),
+    "eg_motion_sample_prior": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
+    "eg_vposer_create": (_I, [_P, _I, _I, C.POINTER(_P)]),
+    "eg_vposer_destroy": (None, [_P]),
+    "eg_vposer_encode": (_I, [_P, _P, _I, _I, _P, _P]),
+    "eg_linear_forward": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _F, _P, _I, _P, _I, _P]),
+    "eg_env_create": (_I, [C.POINTER(EgEnvConfig), _P, _P, _P, _I, C.POINTER(_P)]),
+    "eg_env_destroy": (None, [_P]),
+    "eg_env_set_config": (_I, [_P, C.POINTER(EgEnvConfig)]),
+    "eg_env_set_scene": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _I]),
+    "eg_env_step": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P]),
+    "eg_env_reset": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
+    "eg_policy_param_count": (_L, [C.POINTER(EgPolicyDims), C.POINTER(C.c_int64)]),
+    "eg_policy_create": (_I, [C.POINTER(EgPolicyDims), _P, _P, _I, C.POINTER(_P)]),
+    "eg_policy_destroy": (None, [_P]),
+    "eg_policy_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "eg_gauss_sample": (_I, [_P, _P, _I, _I, _F, _F, _P, _P, _P]),
+    "eg_ppo_loss_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _I, _P, _P]),
+    "eg_moments": (_I, [_P, _L, _P, _P]),
+    "eg_adv_normalize": (_I, [_P, _I, _P, _F, _P, _P]),
+    "eg_clip_adamw_step": (_I, [_P, _P, _P, _F, _F, _F, _F, _F, _F, _I, _P]),
+    "eg_gae": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_double, C.c_double, _P, _P, _P]),
     "eg_lbs_forward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "eg_lbs_forward_sdf": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
 }

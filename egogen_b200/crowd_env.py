@@ -1,0 +1,279 @@
+"""Crowd environments - host-side mirror of the reference's motion/crowd_ppo/crowd_env_2f.py.
+
+``CrowdVectorEnv`` steps E agents in ONE call of the CUDA library (eg_env_step): the reference runs
+256 CrowdEnv instances sequentially under tianshou's DummyVectorEnv (main_ppo.py:97) and replicates
+each agent 4x to dodge an smplx batch-size-1 bug (crowd_env_2f.py:29-32); here each agent is one row
+of a device-resident batch and nothing leaves the GPU between the policy output and the next
+observation. ``CrowdEnv`` keeps the reference's single-agent gymnasium surface on top of it
+(``reset() -> (obs, {})``, ``step(z) -> (obs, float, bool, bool, {})``, ``seed``).
+
+All arithmetic is in egogen_b200/csrc/env.cu; torch is used for buffers, RNG sampling and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib, assets
+from .sdf import calc_sdf, _grid3
+
+
+def default_cfg(finetuning: bool = False):
+    """Values of crowd_ppo/cfg_samp20/MPVAEPolicy_samp_collision.yaml that the env reads."""
+    return SimpleNamespace(
+        modelconfig=SimpleNamespace(h_dim=512, z_dim=128, n_blocks=2, body_repr="ssm2_67_condi_marker_map",
+                                    actfun="lrelu", min_logvar=-2.5, max_logvar=2.5, reproj_factor=0.5),
+        lossconfig=SimpleNamespace(weight_vp=0.1, weight_floor=0.1, weight_skate=0.3, weight_target_dist=1.0,
+                                   weight_face_target=0.1, weight_look_target=0.3, weight_success=0.5,
+                                   weight_pene=0.1),
+        trainconfig=SimpleNamespace(goal_thresh=0.1, max_depth=13, pene_thres=3, random_rotation_range=1),
+        args=SimpleNamespace(gpu_index=0, random_seed=0))
+
+
+def load_cfg(path: str):
+    """Read the reference's policy yaml (OmegaConf in the reference, primitive_model.py:78-82)."""
+    import yaml
+    d = yaml.safe_load(open(path))
+    ns = lambda x: SimpleNamespace(**{k: (ns(v) if isinstance(v, dict) else v) for k, v in x.items()})
+    return ns(d)
+
+
+class BoxSceneSampler:
+    """Synthetic stand-in for exp_GAMMAPrimitive/utils/environments.py scene samplers:
+    start pose / goal pairs in the free space of one rasterised scene, returned as world-frame 2-frame
+    SMPL-X seeds. Gender is always 'male' and betas 0 like the reference samplers (environments.py:191,254)."""
+
+    def __init__(self, scene_sdf: dict, lbs_model, device, floor_half: float = 4.0, seed: int = 0,
+                 pose_noise: float = 0.05, min_goal_dist: float = 1.0):
+        self.sdf, self.dev, self.fh = scene_sdf, torch.device(device), floor_half
+        self.gen = torch.Generator(device=self.dev)
+        self.gen.manual_seed(seed)
+        self.pose_noise, self.min_goal = pose_noise, min_goal_dist
+        # upright offset: rest body rotated y-up -> z-up; lift so the lowest non-feet vertex clears the floor
+        xb = torch.zeros(1, 93, device=self.dev)
+        xb[0, 3] = np.pi / 2
+        v, j, _ = lbs_model.forward(xb, torch.zeros(1, 10, device=self.dev), want_verts=True)
+        mask = torch.ones(v.shape[1], dtype=torch.bool, device=self.dev)
+        mask[assets.feet_vids()] = False
+        self.z_lift = float(-v[0, mask, 2].min().item() + 0.08)
+        self.pelvis_h = float(j[0, 0, 2].item()) + self.z_lift
+
+    def seed(self, s: int):
+        self.gen.manual_seed(int(s))
+
+    def _free_xy(self, n):
+        """n points whose column above the floor is at least 0.5 m from any obstacle."""
+        out = torch.empty(0, 2, device=self.dev)
+        while out.shape[0] < n:
+            xy = (torch.rand(4 * n + 64, 2, device=self.dev, generator=self.gen) * 2 - 1) * (self.fh - 0.8)
+            pts = torch.cat([xy, torch.full((xy.shape[0], 1), 0.9, device=self.dev)], dim=1)
+            d = calc_sdf(pts.unsqueeze(0), self.sdf)[0]
+            out = torch.cat([out, xy[d > 0.6]], dim=0)
+        return out[:n]
+
+    def next_body(self, n: int):
+        dev = self.dev
+        start = self._free_xy(n)
+        goal = self._free_xy(n)
+        for _ in range(8):
+            bad = (goal - start).norm(dim=1) < self.min_goal
+            if not bad.any():
+                break
+            goal[bad] = self._free_xy(int(bad.sum()))
+        yaw = torch.rand(n, device=dev, generator=self.gen) * (2 * np.pi)
+        # global_orient = Rz(yaw) Rx(pi/2) as axis-angle
+        cy, sy = torch.cos(yaw), torch.sin(yaw)
+        R = torch.zeros(n, 3, 3, device=dev)
+        R[:, 0, 0] = cy; R[:, 0, 2] = sy
+        R[:, 1, 0] = sy; R[:, 1, 2] = -cy
+        R[:, 2, 1] = 1.0
+        from scipy.spatial.transform import Rotation
+        aa = torch.as_tensor(Rotation.from_matrix(R.cpu().numpy()).as_rotvec(), dtype=torch.float32, device=dev)
+        wp = torch.zeros(n, 2, 93, device=dev)
+        pose = torch.randn(n, 63, device=dev, generator=self.gen) * self.pose_noise
+        fwd = torch.stack([sy, -cy], dim=1)                       # template forward (+z) after the rotation
+        for t in range(2):
+            wp[:, t, 0:2] = start + fwd * (0.02 * t)
+            wp[:, t, 2] = self.z_lift
+            wp[:, t, 3:6] = aa
+            wp[:, t, 6:69] = pose
+        goals = torch.cat([goal, torch.full((n, 1), self.pelvis_h, device=dev)], dim=1)
+        return dict(world_params=wp, goals=goals, betas=torch.zeros(n, 10, device=dev), gender="male")
+
+
+class CrowdVectorEnv:
+    """E device-resident agents. Observation tensors are views of persistent CUDA buffers; copy them
+    (``clone``) if they must survive the next ``step``."""
+
+    def __init__(self, cfg, motion_model, lbs_model, vposer, scene_sdf: dict, scene_rings, sampler,
+                 n_envs: int, device, feet_marker_idx=None, finetuning: bool = False,
+                 capture_rollout: bool = False, debug_terms: bool = False):
+        self.cfg, self.E, self.dev = cfg, int(n_envs), torch.device(device)
+        self.motion, self.lbs, self.vposer, self.sampler = motion_model, lbs_model, vposer, sampler
+        self.finetuning = bool(finetuning)
+        self.feet_marker_idx = list(feet_marker_idx if feet_marker_idx is not None else assets.feet_marker_idx())
+        E, dev = self.E, self.dev
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.buf = dict(state=f(E, 2, 402), seed=f(E, 2, 93), R0=f(E, 3, 3), T0=f(E, 3), betas=f(E, 10), dist=f(E),
+                        steps=torch.zeros(E, dtype=torch.int32, device=dev), goal=f(E, 3), ego=f(E, 2, 32),
+                        obs_dist=f(E), obs_time=f(E), reward=f(E),
+                        terminated=torch.zeros(E, dtype=torch.uint8, device=dev),
+                        goal_reached=torch.zeros(E, dtype=torch.uint8, device=dev),
+                        reward_terms=f(E, 8) if debug_terms else None,
+                        out_markers=f(E, 20, 67, 3) if capture_rollout else None,
+                        out_params=f(E, 20, 93) if capture_rollout else None,
+                        out_pelvis=f(E, 20, 3) if capture_rollout else None)
+        self._cbuf = _lib.EgEnvBuffers(**{k: (C.c_void_p(v.data_ptr()) if v is not None else None)
+                                          for k, v in self.buf.items()})
+        self._h = C.c_void_p()
+        idx = self.dev.index or 0
+        _lib.check(_lib.lib().eg_env_create(C.byref(self._config()), lbs_model._h, motion_model.handle(),
+                                            vposer.handle(), idx, C.byref(self._h)))
+        self.set_scene(scene_sdf, scene_rings)
+        self.action_dim = 128
+
+    def _config(self):
+        c, l, t = self.cfg.modelconfig, self.cfg.lossconfig, self.cfg.trainconfig
+        w_pene = 0.1 if self.finetuning else 1.0                    # crowd_env_2f.py:268-271
+        return _lib.EgEnvConfig(int(t.max_depth), int(self.finetuning), 40, (C.c_int32 * 6)(*self.feet_marker_idx),
+                                float(c.reproj_factor), float(t.goal_thresh), float(l.weight_skate),
+                                float(l.weight_floor), float(l.weight_face_target), float(l.weight_look_target),
+                                float(l.weight_success), float(l.weight_target_dist), float(l.weight_vp),
+                                w_pene, 7.0)
+
+    def set_scene(self, scene_sdf, scene_rings):
+        dev = self.dev
+        self.scene_sdf = scene_sdf
+        self._grid = _grid3(scene_sdf)
+        self._center = scene_sdf["center"].to(torch.float32).reshape(-1).contiguous()
+        self._scale = scene_sdf["scale"].to(torch.float32).reshape(-1).contiguous()
+        skip = torch.zeros(assets.V_SMPLX, dtype=torch.uint8)
+        skip[assets.feet_vids()] = 1
+        self._skip = skip.to(dev)
+        self._segs = torch.as_tensor(assets.rings_to_segments(scene_rings), dtype=torch.float64, device=dev).contiguous()
+        g = self._grid
+        _lib.check(_lib.lib().eg_env_set_scene(self._h, _lib.ptr(g), g.shape[0], g.shape[1], g.shape[2],
+                                               _lib.ptr(self._center), _lib.ptr(self._scale), _lib.ptr(self._skip),
+                                               _lib.ptr(self._segs), self._segs.shape[0]))
+
+    def __len__(self):
+        return self.E
+
+    def seed(self, seed):
+        self.sampler.seed(seed if isinstance(seed, int) else int(seed[0]))
+
+    def observation(self):
+        b = self.buf
+        return {"state": b["state"], "egosensing": b["ego"], "dist": b["obs_dist"].view(-1, 1),
+                "time": b["obs_time"].view(-1, 1)}
+
+    def reset(self, env_ids: Optional[torch.Tensor] = None, max_tries: int = 50):
+        """(Re)start the given envs (all by default): sample, canonicalise, reject starts that touch the scene
+        (crowd_env_2f.py:326-396). One host sync per attempt (the accept mask), none on the step path."""
+        dev = self.dev
+        ids = torch.arange(self.E, dtype=torch.int32, device=dev) if env_ids is None else \
+            torch.as_tensor(env_ids, dtype=torch.int32, device=dev).reshape(-1)
+        tries = 0
+        while ids.numel() > 0:
+            if tries >= max_tries:
+                raise _lib.EgError("reset: could not find collision-free start poses")
+            n = ids.numel()
+            s = self.sampler.next_body(n)
+            accept = torch.zeros(n, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().eg_env_reset(self._h, C.byref(self._cbuf), _lib.ptr(ids.contiguous()), n,
+                                                   _lib.ptr(s["world_params"].contiguous()),
+                                                   _lib.ptr(s["goals"].contiguous()), _lib.ptr(s["betas"].contiguous()),
+                                                   _lib.ptr(accept), _lib.stream_ptr(dev)))
+            ids = ids[accept == 0]
+            tries += 1
+        return self.observation(), {}
+
+    def reset_from(self, env_ids, world_params, goals, betas):
+        """Deterministic reset from explicit candidates (tests / parity); returns the accept mask."""
+        dev = self.dev
+        ids = torch.as_tensor(env_ids, dtype=torch.int32, device=dev).contiguous()
+        accept = torch.zeros(ids.numel(), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().eg_env_reset(self._h, C.byref(self._cbuf), _lib.ptr(ids), ids.numel(),
+                                               _lib.ptr(_lib.f32c(world_params, dev)), _lib.ptr(_lib.f32c(goals, dev)),
+                                               _lib.ptr(_lib.f32c(betas, dev)), _lib.ptr(accept), _lib.stream_ptr(dev)))
+        return accept
+
+    def step(self, action_z: torch.Tensor):
+        """action_z [E,128] CUDA float32 -> (obs, reward [E], terminated [E] uint8, truncated [E], info)."""
+        z = _lib.f32c(action_z, self.dev)
+        if z.shape != (self.E, 128):
+            raise _lib.EgError(f"action must be [{self.E},128]")
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().eg_env_step(self._h, C.byref(self._cbuf), _lib.ptr(z), self.E,
+                                              _lib.stream_ptr(self.dev)))
+        b = self.buf
+        return self.observation(), b["reward"], b["terminated"], torch.zeros_like(b["terminated"]), {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().eg_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CrowdEnv:
+    """Single-agent environment with the reference constructor and gymnasium surface
+    (crowd_env_2f.py:34-51,78,320,519). ``init_env`` is the reference's 12-element list
+    [cfg, genop_male, genop_female, bm_path, scene_sampler, parser_1f, parser_2f, parser_mp,
+     feet_marker_idx, marker_ids, vposer, scene_sdf]; the scene polygon comes from
+    ``scene_sampler.scene_rings`` (the reference reads it from the sampler dict's 'shapely_poly')."""
+
+    def __init__(self, init_env, save_rollout=True, render=False, finetuning=False):
+        if render:
+            raise NotImplementedError("pyrender visualisation is out of scope (SURVEY.md section 2 #17)")
+        (self.cfg, genop_male, _genop_female, _bm_path, self.scene_sampler, _p1, _p2, parser_mp,
+         self.feet_marker_idx, self.marker, self.vposer, self.scene_sdf) = init_env
+        self.save_rollout, self.finetuning = save_rollout, finetuning
+        dev = parser_mp.device
+        self.action_space = SimpleNamespace(low=-6.0, high=6.0, shape=(128,))
+        self.observation_space = {"state": (2, 402), "egosensing": (2, 32), "dist": (1,), "time": (1,)}
+        self._venv = CrowdVectorEnv(self.cfg, genop_male.model, parser_mp.bm_male, self.vposer, self.scene_sdf,
+                                    self.scene_sampler.scene_rings, self.scene_sampler, 1, dev,
+                                    self.feet_marker_idx, finetuning, capture_rollout=save_rollout)
+        self.outmps, self.flag, self.steps = [], False, 0
+
+    def seed(self, seed):
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        self._venv.seed(seed)
+
+    @staticmethod
+    def _single(obs):
+        return {"state": obs["state"][0], "egosensing": obs["egosensing"][0], "dist": obs["dist"][0],
+                "time": obs["time"][0]}
+
+    def reset(self, seed=None, options=None):
+        self.flag, self.steps, self.outmps = False, 0, []
+        obs, info = self._venv.reset()
+        return self._single(obs), info
+
+    def step(self, action_z):
+        if self.flag:
+            raise RuntimeError("the episode should be terminated! do not collect undefined states")
+        z = torch.as_tensor(action_z, dtype=torch.float32, device=self._venv.dev).reshape(1, 128)
+        obs, rew, term, _, _ = self._venv.step(z)
+        self.steps += 1
+        terminated = bool(term[0].item())
+        if self.save_rollout:
+            b = self._venv.buf
+            self.outmps.append([b["out_markers"].clone(), b["out_params"].clone(), b["betas"][0].clone(), "male",
+                                b["R0"][0].clone(), b["T0"][0].clone().view(1, 3), b["out_pelvis"].clone(), "2-frame"])
+            if terminated:
+                self.flag = True
+        return self._single(obs), float(rew[0].item()), terminated, False, {}

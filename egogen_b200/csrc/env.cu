@@ -1,0 +1,475 @@
+// Vectorised crowd_ppo environment transition - replaces CrowdEnv.step / CrowdEnv.reset
+// (reference motion/crowd_ppo/crowd_env_2f.py:78-317, 320-415) for E environments at once with the
+// reference's 4x batch duplication removed (only element [0] of each duplicated batch is ever consumed).
+//
+// Pipeline per step (all on one stream, no host synchronisation):
+//   eg_motion_sample_prior -> env_prepare_params (seed frames + _blend_params) -> eg_lbs_forward_sdf
+//   (LBS + world transform + calc_sdf + feet skip + per-frame counts, vertices never materialised)
+//   -> eg_vposer_encode -> env_reward_recanon_kernel (8 reward terms, termination, new canonical frame,
+//   update_transl_glorot, marker/goal features -> next state) -> eg_lbs_forward (joints of the new
+//   2-frame seed) -> env_egosensing_kernel (2 x 32 fp64 rays against the scene polygon).
+#include <vector>
+
+#include "geom.cuh"
+
+namespace eg {
+
+constexpr int NT = 20;       // frames per primitive (2 history + 18 predicted)
+constexpr int NM = 67;       // markers
+constexpr int NJ = EG_SMPLX_JOINTS_OUT;
+
+struct StepArgs {
+  EgEnvConfig cfg;
+  EgEnvBuffers b;
+  const float* Y;          // [E,20,201]
+  const float* params;     // [E,20,93]
+  const int32_t* counts;   // [E,20]
+  const float* joints;     // [E,20,127,3]
+  const float* mproj;      // [E,20,67,3]
+  const float* vp_loc;     // [E,20,32]
+  const float* pelvis_rest;// [E,3]
+};
+
+__device__ __forceinline__ float norm3_clip(float x, float y, float z) {
+  return fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+}
+
+// SMPLXParser.update_transl_glorot, torch branch (baseops.py:570-596) for one body
+__device__ __forceinline__ void update_transl_glorot(const float* Rn, const float* Tn, const float* delta,
+                                                     const float* xb, float* out) {
+  float Rg[9], Rnew[9], aa[3];
+  tgm_aa_to_rotmat(xb + 3, Rg);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      Rnew[i * 3 + k] = Rn[0 * 3 + i] * Rg[0 * 3 + k] + Rn[1 * 3 + i] * Rg[1 * 3 + k] + Rn[2 * 3 + i] * Rg[2 * 3 + k];
+  tgm_rotmat_to_aa(Rnew, aa);
+  float d[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) d[j] = xb[j] + delta[j] - Tn[j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    out[i] = (Rn[0 * 3 + i] * d[0] + Rn[1 * 3 + i] * d[1] + Rn[2 * 3 + i] * d[2]) - delta[i];
+  out[3] = aa[0]; out[4] = aa[1]; out[5] = aa[2];
+}
+
+// seed frames + _blend_params (crowd_env_2f.py:116-120, 729-739)
+__global__ void __launch_bounds__(128)
+env_prepare_params_kernel(const float* __restrict__ seed, float* __restrict__ params, int E) {
+  const int e = blockIdx.x, i = threadIdx.x;
+  if (i >= 93) return;
+  float* p = params + (int64_t)e * NT * 93;
+  const float p1 = seed[((int64_t)e * 2 + 1) * 93 + i];
+  p[i] = seed[((int64_t)e * 2) * 93 + i];
+  p[93 + i] = p1;
+  if (i >= 6) {
+    const float p2 = (p1 + p[3 * 93 + i]) / 2.0f;
+    p[2 * 93 + i] = p2;
+    p[3 * 93 + i] = (p2 + p[4 * 93 + i]) / 2.0f;   // second blend reads the first blend's output
+  }
+}
+
+// marker / goal features of _get_feature (crowd_env_2f.py:680-707) for one marker
+__device__ __forceinline__ void write_state_marker(float* st, int p, const float* m, const float* goal_l) {
+  const float fx = goal_l[0] - m[0], fy = goal_l[1] - m[1], fz = goal_l[2] - m[2];
+  const float d = norm3_clip(fx, fy, fz);
+  st[p * 3 + 0] = m[0]; st[p * 3 + 1] = m[1]; st[p * 3 + 2] = m[2];
+  st[201 + p * 3 + 0] = fx / d; st[201 + p * 3 + 1] = fy / d; st[201 + p * 3 + 2] = fz / d;
+}
+
+__global__ void __launch_bounds__(256)
+env_reward_recanon_kernel(const StepArgs a) {
+  const int e = blockIdx.x, tid = threadIdx.x;
+  __shared__ float mb[NT * NM * 3];
+  __shared__ float s_skate[18], s_floor[NT], s_vp[NT];
+  __shared__ float Rn[9], Tn[3], R0n[9], T0n[3], goal_l2[3], delta[3];
+  const EgEnvConfig& c = a.cfg;
+  const float* R0 = a.b.R0 + (int64_t)e * 9;
+  const float* T0 = a.b.T0 + (int64_t)e * 3;
+  const float* goal = a.b.goal + (int64_t)e * 3;
+  const float* jall = a.joints + (int64_t)e * NT * NJ * 3;
+
+  // blended markers: reproj_factor * reprojected + (1 - reproj_factor) * predicted (:151-152)
+  const float rf = c.reproj_factor, rf1 = 1.0f - c.reproj_factor;
+  for (int i = tid; i < NT * NM * 3; i += blockDim.x) {
+    const float v = rf * a.mproj[(int64_t)e * NT * NM * 3 + i] + rf1 * a.Y[(int64_t)e * NT * NM * 3 + i];
+    mb[i] = v;
+    if (a.b.out_markers) a.b.out_markers[(int64_t)e * NT * NM * 3 + i] = v;
+  }
+  if (a.b.out_pelvis && tid < NT * 3) a.b.out_pelvis[(int64_t)e * NT * 3 + tid] = jall[(tid / 3) * NJ * 3 + tid % 3];
+  if (a.b.out_params)
+    for (int i = tid; i < NT * 93; i += blockDim.x) a.b.out_params[(int64_t)e * NT * 93 + i] = a.params[(int64_t)e * NT * 93 + i];
+  __syncthreads();
+
+  if (tid < 18) {                       // foot skating (:182-185)
+    float mn = INFINITY;
+    for (int k = 0; k < 6; ++k) {
+      const int p = c.feet_marker_idx[k];
+      const float* m2 = mb + ((tid + 2) * NM + p) * 3;
+      const float* m0 = mb + (tid * NM + p) * 3;
+      const float dx = m2[0] - m0[0], dy = m2[1] - m0[1], dz = m2[2] - m0[2];
+      mn = fminf(mn, sqrtf(dx * dx + dy * dy + dz * dz) / 2.0f / 0.025f);
+    }
+    s_skate[tid] = fmaxf(mn - 0.075f, 0.0f);
+  } else if (tid >= 32 && tid < 32 + NT) {   // floor contact (:191-194)
+    const int t = tid - 32;
+    float mn = INFINITY;
+    for (int k = 0; k < 6; ++k) {
+      const float* m = mb + (t * NM + c.feet_marker_idx[k]) * 3;
+      mn = fminf(mn, R0[6] * m[0] + R0[7] * m[1] + R0[8] * m[2] + T0[2]);
+    }
+    s_floor[t] = fabsf(mn - 0.02f);
+  } else if (tid >= 64 && tid < 64 + NT) {   // VPoser latent norm (:197-200)
+    const int t = tid - 64;
+    const float* l = a.vp_loc + ((int64_t)e * NT + t) * 32;
+    float s = 0.0f;
+    for (int k = 0; k < 32; ++k) s += l[k] * l[k];
+    s_vp[t] = sqrtf(s);
+  }
+  __syncthreads();
+
+  if (tid == 0) {
+    int total = 0, mx = 0;
+    for (int t = 0; t < NT; ++t) { const int v = a.counts[e * NT + t]; total += v; mx = max(mx, v); }
+    const float num_inside = (float)total / (float)NT / 10.0f;
+    const float r_pene = expf(-num_inside);
+    const bool penetration = mx >= c.pene_terminate_count;
+    float s = 0.f;
+    for (int t = 0; t < 18; ++t) s += s_skate[t];
+    const float r_skate = expf(-(s / 18.0f));
+    s = 0.f;
+    for (int t = 0; t < NT; ++t) s += s_floor[t];
+    const float r_floor = expf(-(s / (float)NT));
+    s = 0.f;
+    for (int t = 0; t < NT; ++t) s += s_vp[t];
+    const float r_vp = (s / (float)NT) > 11.0f ? 0.0f : 0.05f;
+    // facing / looking at the goal (:206-229)
+    const float* je = jall + (int64_t)19 * NJ * 3;
+    float x0 = je[2 * 3 + 0] - je[1 * 3 + 0], x1 = je[2 * 3 + 1] - je[1 * 3 + 1];
+    float n = fmaxf(sqrtf(x0 * x0 + x1 * x1 + 0.0f), 1e-12f);
+    x0 /= n; x1 /= n;
+    const float bo0 = -x1, bo1 = x0;                   // cross((0,0,1), x)[:2]
+    float tl[3];
+    const float g0 = goal[0] - T0[0], g1 = goal[1] - T0[1], g2 = goal[2] - T0[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tl[i] = R0[0 * 3 + i] * g0 + R0[1 * 3 + i] * g1 + R0[2 * 3 + i] * g2;
+    float f0 = tl[0] - je[0], f1 = tl[1] - je[1];
+    n = fmaxf(sqrtf(f0 * f0 + f1 * f1), 1e-12f);
+    f0 /= n; f1 /= n;
+    const float r_face = ((f0 * bo0 + f1 * bo1) + 1.0f) / 2.0f;
+    float e0 = je[24 * 3 + 0] - je[23 * 3 + 0], e1 = je[24 * 3 + 1] - je[23 * 3 + 1];
+    n = fmaxf(sqrtf(e0 * e0 + e1 * e1 + 0.0f), 1e-12f);
+    e0 /= n; e1 /= n;
+    const float r_look = ((f0 * (-e1) + f1 * e0) + 1.0f) / 2.0f;
+    // distance to the goal (:231-235)
+    const float dist2 = norm3_clip(tl[0] - je[0], tl[1] - je[1], tl[2] - je[2]);
+    const float r_dist = a.b.dist[e] - dist2;
+    const float r_goal = dist2 < c.goal_thresh ? 1.0f : 0.0f;
+    float reward = r_skate * c.w_skate + r_floor * c.w_floor;
+    reward += r_face * c.w_face;
+    reward += r_look * c.w_look;
+    reward += r_goal * c.w_success;
+    reward += r_dist * c.w_dist;
+    reward += r_pene * c.w_pene;
+    reward += r_vp * c.w_vp;
+    const int steps = a.b.steps[e] + 1;
+    const bool term = (r_goal > 0.0f) || (steps == c.max_depth) || (c.finetuning && penetration);
+    a.b.reward[e] = reward;
+    a.b.terminated[e] = term ? 1 : 0;
+    if (a.b.goal_reached) a.b.goal_reached[e] = r_goal > 0.0f ? 1 : 0;
+    if (a.b.reward_terms) {
+      float* rt = a.b.reward_terms + (int64_t)e * 8;
+      rt[0] = r_skate; rt[1] = r_floor; rt[2] = r_face; rt[3] = r_look; rt[4] = r_goal; rt[5] = r_dist;
+      rt[6] = r_pene; rt[7] = r_vp;
+    }
+    a.b.dist[e] = dist2;
+    a.b.steps[e] = steps;
+    a.b.obs_dist[e] = 1.0f / (dist2 + 1.0f);
+    a.b.obs_time[e] = (float)(1.0 - (double)steps / (double)c.max_depth);
+    // new canonical frame at the second-last body (:238-248)
+    const float* jb = jall + (int64_t)18 * NJ * 3;
+    new_coordinate(jb, jb + 3, jb + 6, Rn, Tn);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      T0n[i] = (R0[i * 3 + 0] * Tn[0] + R0[i * 3 + 1] * Tn[1] + R0[i * 3 + 2] * Tn[2]) + T0[i];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        R0n[i * 3 + k] = R0[i * 3 + 0] * Rn[0 * 3 + k] + R0[i * 3 + 1] * Rn[1 * 3 + k] + R0[i * 3 + 2] * Rn[2 * 3 + k];
+    }
+    const float h0 = goal[0] - T0n[0], h1 = goal[1] - T0n[1], h2 = goal[2] - T0n[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) goal_l2[i] = R0n[0 * 3 + i] * h0 + R0n[1 * 3 + i] * h1 + R0n[2 * 3 + i] * h2;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) delta[i] = a.pelvis_rest[(int64_t)e * 3 + i];
+  }
+  __syncthreads();
+  // all reads of the old R0/T0 happened before this barrier
+  if (tid < 9) a.b.R0[(int64_t)e * 9 + tid] = R0n[tid];
+  if (tid < 3) a.b.T0[(int64_t)e * 3 + tid] = T0n[tid];
+
+  // new 2-frame seed in the new frame (:250-257)
+  const float* p18 = a.params + ((int64_t)e * NT + 18) * 93;
+  float* seed = a.b.seed + (int64_t)e * 2 * 93;
+  if (tid < 2) update_transl_glorot(Rn, Tn, delta, p18 + tid * 93, seed + tid * 93);
+  for (int i = tid; i < 2 * 87; i += blockDim.x) seed[(i / 87) * 93 + 6 + i % 87] = p18[(i / 87) * 93 + 6 + i % 87];
+  // marker seed + goal features -> next state (:259-265)
+  for (int i = tid; i < 2 * NM; i += blockDim.x) {
+    const int k = i / NM, p = i % NM;
+    const float* m = mb + ((18 + k) * NM + p) * 3;
+    const float d0 = m[0] - Tn[0], d1 = m[1] - Tn[1], d2 = m[2] - Tn[2];
+    float ml[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) ml[q] = Rn[0 * 3 + q] * d0 + Rn[1 * 3 + q] * d1 + Rn[2 * 3 + q] * d2;
+    write_state_marker(a.b.state + ((int64_t)e * 2 + k) * 402, p, ml, goal_l2);
+  }
+}
+
+// reset: canonical frame of the sampled 2-frame world seed (_canonicalize_2frame, :615-644)
+__global__ void __launch_bounds__(32)
+env_reset_canon_kernel(const float* __restrict__ wp, const float* __restrict__ joints_w,
+                       const float* __restrict__ pelvis_rest, int n, float* __restrict__ R0c,
+                       float* __restrict__ T0c, float* __restrict__ seedc) {
+  const int i = blockIdx.x, tid = threadIdx.x;
+  __shared__ float Rn[9], Tn[3];
+  if (tid == 0) {
+    const float* j = joints_w + (int64_t)i * 2 * NJ * 3;      // frame 0
+    new_coordinate(j, j + 3, j + 6, Rn, Tn);
+    for (int k = 0; k < 9; ++k) R0c[(int64_t)i * 9 + k] = Rn[k];
+    for (int k = 0; k < 3; ++k) T0c[(int64_t)i * 3 + k] = Tn[k];
+  }
+  __syncwarp();
+  if (tid < 2) update_transl_glorot(Rn, Tn, pelvis_rest + (int64_t)i * 3, wp + ((int64_t)i * 2 + tid) * 93,
+                                    seedc + ((int64_t)i * 2 + tid) * 93);
+  for (int q = tid; q < 2 * 87; q += 32)
+    seedc[((int64_t)i * 2 + q / 87) * 93 + 6 + q % 87] = wp[((int64_t)i * 2 + q / 87) * 93 + 6 + q % 87];
+}
+
+// reset: accept the candidate if no non-feet vertex penetrates (:379-380) and commit it to its env slot
+__global__ void __launch_bounds__(256)
+env_reset_commit_kernel(EgEnvBuffers b, const int32_t* __restrict__ env_ids, int n,
+                        const int32_t* __restrict__ counts, const float* __restrict__ R0c,
+                        const float* __restrict__ T0c, const float* __restrict__ seedc,
+                        const float* __restrict__ joints_c, const float* __restrict__ markers_c,
+                        const float* __restrict__ goals, const float* __restrict__ betas_c,
+                        int32_t* __restrict__ accept) {
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const bool ok = (counts[i * 2] + counts[i * 2 + 1]) == 0;
+  if (tid == 0) accept[i] = ok ? 1 : 0;
+  if (!ok) return;
+  const int e = env_ids[i];
+  __shared__ float goal_l[3];
+  const float* R0 = R0c + (int64_t)i * 9;
+  const float* T0 = T0c + (int64_t)i * 3;
+  if (tid == 0) {
+    const float* goal = goals + (int64_t)i * 3;
+    const float g0 = goal[0] - T0[0], g1 = goal[1] - T0[1], g2 = goal[2] - T0[2];
+    for (int q = 0; q < 3; ++q) goal_l[q] = R0[0 * 3 + q] * g0 + R0[1 * 3 + q] * g1 + R0[2 * 3 + q] * g2;
+    const float* pel = joints_c + (int64_t)i * 2 * NJ * 3;    // pelvis of frame 0
+    const float d = norm3_clip(goal_l[0] - pel[0], goal_l[1] - pel[1], goal_l[2] - pel[2]);
+    b.dist[e] = d;
+    b.obs_dist[e] = 1.0f / (d + 1.0f);
+    b.obs_time[e] = 1.0f;
+    b.steps[e] = 0;
+    for (int q = 0; q < 3; ++q) b.goal[(int64_t)e * 3 + q] = goal[q];
+    for (int q = 0; q < 10; ++q) b.betas[(int64_t)e * 10 + q] = betas_c[(int64_t)i * 10 + q];
+  }
+  __syncthreads();
+  if (tid < 9) b.R0[(int64_t)e * 9 + tid] = R0[tid];
+  if (tid < 3) b.T0[(int64_t)e * 3 + tid] = T0[tid];
+  for (int q = tid; q < 2 * 93; q += blockDim.x) b.seed[(int64_t)e * 2 * 93 + q] = seedc[(int64_t)i * 2 * 93 + q];
+  for (int q = tid; q < 2 * NM; q += blockDim.x) {
+    const int k = q / NM, p = q % NM;
+    write_state_marker(b.state + ((int64_t)e * 2 + k) * 402, p, markers_c + (((int64_t)i * 2 + k) * NM + p) * 3, goal_l);
+  }
+}
+
+// _calc_egosensing (:524-613) in closed form: 2 frames x 32 rays, fp64.
+// joints: local-frame joints of the 2-frame seed, item i frames at joints[(i*2+t)*127*3];
+// world = R0[slot] j + T0[slot] in fp32 like the reference einsum, then numpy float64 arithmetic.
+__global__ void __launch_bounds__(64)
+env_egosensing_kernel(const float* __restrict__ joints, const float* __restrict__ R0a,
+                      const float* __restrict__ T0a, const int32_t* __restrict__ slot_ids,
+                      const int32_t* __restrict__ accept, const double* __restrict__ segs, int S,
+                      double ray_len, float* __restrict__ ego) {
+  const int i = blockIdx.x;
+  if (accept && !accept[i]) return;
+  const int t = threadIdx.x >> 5, ray = threadIdx.x & 31;
+  const int slot = slot_ids ? slot_ids[i] : i;     // output row; R0/T0/joints are indexed by item i
+  const float* R0 = R0a + (int64_t)i * 9;
+  const float* T0 = T0a + (int64_t)i * 3;
+  const float* j = joints + ((int64_t)i * 2 + t) * NJ * 3;
+  float w[4][2];
+  const int ids[4] = {23, 24, 56, 57};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float* p = j + ids[q] * 3;
+    w[q][0] = (R0[0] * p[0] + R0[1] * p[1] + R0[2] * p[2]) + T0[0];
+    w[q][1] = (R0[3] * p[0] + R0[4] * p[1] + R0[5] * p[2]) + T0[1];
+  }
+  // look_at = j57 - j23 + j56 - j24 (float32), then float64, z := 0, normalised
+  double lx = (double)(((w[3][0] - w[0][0]) + w[2][0]) - w[1][0]);
+  double ly = (double)(((w[3][1] - w[0][1]) + w[2][1]) - w[1][1]);
+  const double ln = sqrt(lx * lx + ly * ly);
+  lx /= ln; ly /= ln;
+  const double ex = (double)((w[0][0] + w[1][0]) / 2.0f), ey = (double)((w[0][1] + w[1][1]) / 2.0f);
+  const double PI_2 = 1.57079632679489661923;
+  const double ang = ray == 31 ? PI_2 : -PI_2 + (double)ray * ((PI_2 - (-PI_2)) / 31.0);
+  const double ca = cos(ang), sa = sin(ang);
+  const double dx = lx * ca - ly * sa, dy = ly * ca + lx * sa;
+  // even-odd containment of the eye + nearest boundary crossing along the ray
+  int crossings = 0;
+  double tmin = ray_len;
+  for (int s = 0; s < S; ++s) {
+    const double ax = segs[4 * s], ay = segs[4 * s + 1], bx = segs[4 * s + 2], by = segs[4 * s + 3];
+    if ((ay > ey) != (by > ey)) {
+      const double xi = ax + (ey - ay) * (bx - ax) / (by - ay);
+      if (xi > ex) ++crossings;
+    }
+    const double sx = bx - ax, sy = by - ay;
+    const double den = dx * sy - dy * sx;
+    if (den != 0.0) {
+      const double qx = ax - ex, qy = ay - ey;
+      const double tt = (qx * sy - qy * sx) / den;
+      const double u = (qx * dy - qy * dx) / den;
+      if (tt >= 0.0 && u >= 0.0 && u <= 1.0 && tt < tmin) tmin = tt;
+    }
+  }
+  // the hit point is reconstructed like shapely's end coordinate and its distance re-measured
+  double d = 0.0;
+  if (crossings & 1) {
+    const double hx = ex + tmin * dx, hy = ey + tmin * dy;
+    d = sqrt((hx - ex) * (hx - ex) + (hy - ey) * (hy - ey));
+  }
+  ego[((int64_t)slot * 2 + t) * 32 + ray] = (float)(-1.0 + 2.0 * (d / ray_len));
+}
+
+}  // namespace eg
+
+using namespace eg;
+
+struct EgEnv {
+  int device = 0;
+  EgEnvConfig cfg;
+  EgLbs* lbs = nullptr;
+  EgMotion* motion = nullptr;
+  EgVposer* vposer = nullptr;
+  // scene
+  const float* grid = nullptr; int D0 = 0, D1 = 0, D2 = 0;
+  const float *center = nullptr, *scale = nullptr;
+  const uint8_t* skip = nullptr;
+  const double* segs = nullptr; int S = 0;
+  // workspace
+  int cap = 0;
+  float *Y = nullptr, *params = nullptr, *joints = nullptr, *mproj = nullptr, *vp = nullptr, *prest = nullptr;
+  float *joints2 = nullptr, *R0c = nullptr, *T0c = nullptr, *seedc = nullptr;
+  int32_t* counts = nullptr;
+};
+
+static int env_ws(EgEnv* h, int E) {
+  if (E <= h->cap) return EG_OK;
+  float** fb[] = {&h->Y, &h->params, &h->joints, &h->mproj, &h->vp, &h->prest, &h->joints2, &h->R0c, &h->T0c, &h->seedc};
+  for (auto p : fb) { cudaFree(*p); *p = nullptr; }
+  cudaFree(h->counts); h->counts = nullptr; h->cap = 0;
+  const size_t e = (size_t)E;
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->Y, e * NT * 201 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->params, e * NT * 93 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->joints, e * NT * NJ * 3 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->mproj, e * NT * NM * 3 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->vp, e * NT * 32 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->prest, e * 3 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->joints2, e * 2 * NJ * 3 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->R0c, e * 9 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->T0c, e * 3 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->seedc, e * 2 * 93 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->counts, e * NT * 4));
+  h->cap = E;
+  return EG_OK;
+}
+
+extern "C" int eg_env_create(const EgEnvConfig* cfg, EgLbs* lbs, EgMotion* motion, EgVposer* vposer,
+                             int device, EgEnv** out) {
+  EG_REQUIRE(cfg && lbs && motion && vposer && out, "null pointer");
+  EG_REQUIRE(cfg->max_depth > 0 && cfg->ray_len > 0, "bad config");
+  for (int k = 0; k < 6; ++k) EG_REQUIRE(cfg->feet_marker_idx[k] >= 0 && cfg->feet_marker_idx[k] < NM, "feet marker index");
+  EgEnv* h = new EgEnv();
+  h->device = device; h->cfg = *cfg; h->lbs = lbs; h->motion = motion; h->vposer = vposer;
+  *out = h;
+  return EG_OK;
+}
+
+extern "C" void eg_env_destroy(EgEnv* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  float* fb[] = {h->Y, h->params, h->joints, h->mproj, h->vp, h->prest, h->joints2, h->R0c, h->T0c, h->seedc};
+  for (auto p : fb) cudaFree(p);
+  cudaFree(h->counts);
+  delete h;
+}
+
+extern "C" int eg_env_set_config(EgEnv* h, const EgEnvConfig* cfg) {
+  EG_REQUIRE(h && cfg, "null pointer");
+  h->cfg = *cfg;
+  return EG_OK;
+}
+
+extern "C" int eg_env_set_scene(EgEnv* h, const float* grid, int D0, int D1, int D2, const float* center_dev,
+                                const float* scale_dev, const uint8_t* skip_mask, const double* segments_dev,
+                                int n_segments) {
+  EG_REQUIRE(h && grid && center_dev && scale_dev && segments_dev, "null pointer");
+  EG_REQUIRE(D0 > 0 && D1 > 0 && D2 > 0 && n_segments > 0, "bad sizes");
+  h->grid = grid; h->D0 = D0; h->D1 = D1; h->D2 = D2; h->center = center_dev; h->scale = scale_dev;
+  h->skip = skip_mask; h->segs = segments_dev; h->S = n_segments;
+  return EG_OK;
+}
+
+#define EG_TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+extern "C" int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int E, void* stream) {
+  EG_REQUIRE(h && b && z, "null pointer");
+  EG_REQUIRE(h->grid != nullptr, "scene not set (eg_env_set_scene)");
+  EG_REQUIRE(b->state && b->seed && b->R0 && b->T0 && b->betas && b->dist && b->steps && b->goal && b->ego &&
+             b->obs_dist && b->obs_time && b->reward && b->terminated, "null buffer");
+  if (E <= 0) return EG_OK;
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  EG_TRY(env_ws(h, E));
+  cudaStream_t st = as_stream(stream);
+  // b: C-VAE rollout + body regressor (:109)
+  EG_TRY(eg_motion_sample_prior(h->motion, b->state, 2 * 402, 402, z, b->betas, E, h->Y, h->params, stream));
+  // c: history frames + parameter blending (:116-120)
+  EG_LAUNCH(env_prepare_params_kernel, E, 128, 0, st, b->seed, h->params, E);
+  // d,e: SMPL-X on 20 bodies per env fused with the SDF penetration query (:133-177)
+  EG_TRY(eg_lbs_forward_sdf(h->lbs, h->params, b->betas, E, E * NT, NT, b->R0, b->T0, h->grid, h->D0, h->D1,
+                            h->D2, h->center, h->scale, h->skip, h->counts, h->joints, h->mproj, stream));
+  // f: VPoser latent of every frame's body pose (:197-200)
+  EG_TRY(eg_vposer_encode(h->vposer, h->params + 6, 93, E * NT, h->vp, stream));
+  EG_TRY(eg_lbs_rest_pelvis(h->lbs, b->betas, E, E, h->prest, stream));
+  StepArgs a{h->cfg, *b, h->Y, h->params, h->counts, h->joints, h->mproj, h->vp, h->prest};
+  EG_LAUNCH(env_reward_recanon_kernel, E, 256, 0, st, a);
+  // i: all joints of the re-canonicalised seed for ego-sensing (:290-296)
+  EG_TRY(eg_lbs_forward(h->lbs, b->seed, b->betas, E, E * 2, nullptr, h->joints2, nullptr, stream));
+  EG_LAUNCH(env_egosensing_kernel, E, 64, 0, st, h->joints2, b->R0, b->T0, nullptr, nullptr, h->segs, h->S,
+            (double)h->cfg.ray_len, b->ego);
+  return EG_OK;
+}
+
+extern "C" int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_ids, int n,
+                            const float* world_params, const float* goals, const float* betas_cand,
+                            int32_t* accept, void* stream) {
+  EG_REQUIRE(h && b && env_ids && world_params && goals && betas_cand && accept, "null pointer");
+  EG_REQUIRE(h->grid != nullptr, "scene not set (eg_env_set_scene)");
+  if (n <= 0) return EG_OK;
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  EG_TRY(env_ws(h, n));
+  cudaStream_t st = as_stream(stream);
+  EG_TRY(eg_lbs_rest_pelvis(h->lbs, betas_cand, n, n, h->prest, stream));
+  EG_TRY(eg_lbs_forward(h->lbs, world_params, betas_cand, n, n * 2, nullptr, h->joints, nullptr, stream));
+  EG_LAUNCH(env_reset_canon_kernel, n, 32, 0, st, world_params, h->joints, h->prest, n, h->R0c, h->T0c, h->seedc);
+  EG_TRY(eg_lbs_forward_sdf(h->lbs, h->seedc, betas_cand, n, n * 2, 2, h->R0c, h->T0c, h->grid, h->D0, h->D1, h->D2,
+                            h->center, h->scale, h->skip, h->counts, h->joints2, h->mproj, stream));
+  EG_LAUNCH(env_reset_commit_kernel, n, 256, 0, st, *b, env_ids, n, h->counts, h->R0c, h->T0c, h->seedc,
+            h->joints2, h->mproj, goals, betas_cand, accept);
+  EG_LAUNCH(env_egosensing_kernel, n, 64, 0, st, h->joints2, h->R0c, h->T0c, env_ids, accept, h->segs, h->S,
+            (double)h->cfg.ray_len, b->ego);
+  return EG_OK;
+}

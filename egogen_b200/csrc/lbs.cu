@@ -69,7 +69,7 @@ namespace eg {
 // prep: one CTA of 64 threads per body
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64)
-lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ betas, int betas_rows,
+lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ betas, int betas_div,
                      int N, int Npad, int J, int S, int n_levels,
                      const float* __restrict__ hand_l, const float* __restrict__ hand_r,
                      const float* __restrict__ pose_mean, const float* __restrict__ Jt,
@@ -84,7 +84,7 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
   __shared__ float G[MAXJ][12];
   __shared__ float shape[32];
   const float* x = xb + (int64_t)n * EG_XB_DIM;
-  const float* be = betas + (int64_t)(betas_rows == 1 ? 0 : n) * 10;
+  const float* be = betas + (int64_t)(n / betas_div) * 10;
 
   // full_pose = [global_orient, body_pose(21), jaw, leye, reye, lhand(15), rhand(15)] + pose_mean
   for (int i = t; i < J * 3; i += 64) {
@@ -401,6 +401,20 @@ __global__ void gather_vertex_set_kernel(const float* __restrict__ src_basis, in
   }
 }
 
+// calc_calibrate_offset (baseops.py:494-534): pelvis of the body with zero transl / global_orient.
+// The root joint's posed position is its rest position, so this is J_0(betas) - no LBS pass needed.
+__global__ void rest_pelvis_kernel(const float* __restrict__ betas, int betas_div, int N, int S,
+                                   const float* __restrict__ Jt, const float* __restrict__ Js,
+                                   float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 3) return;
+  const int n = i / 3, c = i % 3;
+  const float* be = betas + (int64_t)(n / betas_div) * 10;
+  float v = __ldg(Jt + c);
+  for (int k = 0; k < S && k < 10; ++k) v += __ldg(Js + c * S + k) * be[k];
+  out[i] = v;
+}
+
 static void free_vertex_set(VertexSet& s) {
   cudaFree(s.basis); cudaFree(s.vt); cudaFree(s.skin_idx); cudaFree(s.skin_w);
   s = VertexSet();
@@ -427,14 +441,15 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
                        const float* R0, const float* T0, SdfGrid sdf, const uint8_t* skip,
                        int32_t* counts, cudaStream_t st) {
   EG_REQUIRE(h && xb && betas, "null pointer");
-  EG_REQUIRE(betas_rows == 1 || betas_rows == N, "betas_rows must be 1 or N");
   EG_REQUIRE(N >= 0, "negative N");
   if (N == 0) return EG_OK;
+  EG_REQUIRE(betas_rows >= 1 && N % betas_rows == 0, "betas_rows must divide N (row = body / (N / betas_rows))");
+  const int betas_div = N / betas_rows;
   EG_CUDA_CHECK(cudaSetDevice(h->device));
   int rc = ensure_workspace(h, N);
   if (rc) return rc;
   const int Npad = h->cap_N;   // row stride of Ft (fixed per workspace so tiles never read OOB)
-  EG_LAUNCH(lbs_pose_prep_kernel, N, 64, 0, st, xb, betas, betas_rows, N, Npad, h->J, h->S,
+  EG_LAUNCH(lbs_pose_prep_kernel, N, 64, 0, st, xb, betas, betas_div, N, Npad, h->J, h->S,
             h->n_levels, h->hand_l, h->hand_r, h->pose_mean, h->Jt, h->Js, h->parents,
             h->level_joints, h->level_start, h->Ft, h->A, h->Jp);
   VertArgs a{};
@@ -644,4 +659,13 @@ extern "C" int eg_lbs_forward_sdf(EgLbs* h, const float* xb, const float* betas,
   SdfGrid g{grid, D0, D1, D2, center_dev, scale_dev};
   return run_forward(h, xb, betas, betas_rows, N, nullptr, joints, markers, true, frames_per_env, R0,
                      T0, g, skip_mask, counts, as_stream(stream));
+}
+
+extern "C" int eg_lbs_rest_pelvis(EgLbs* h, const float* betas, int betas_rows, int N, float* out, void* stream) {
+  EG_REQUIRE(h && betas && out && N >= 0, "bad arguments");
+  if (N == 0) return EG_OK;
+  EG_REQUIRE(betas_rows >= 1 && N % betas_rows == 0, "betas_rows must divide N");
+  EG_LAUNCH(rest_pelvis_kernel, (N * 3 + 127) / 128, 128, 0, as_stream(stream), betas, N / betas_rows, N, h->S,
+            h->Jt, h->Js, out);
+  return EG_OK;
 }

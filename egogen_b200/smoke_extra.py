@@ -1,0 +1,23 @@
+"""Extra smoke stages (called by __graft_entry__.smoke): one vector env step on cuda:0."""
+import torch
+
+from . import assets
+
+
+def run(dev):
+    from .crowd_env import BoxSceneSampler, CrowdVectorEnv, default_cfg
+    from .models_gamma_primitive import GAMMAPrimitiveComboGenOP, load_vposer
+    from .smplx_parser import get_lbs_model
+    lbs = get_lbs_model("male", dev, marker_vids=assets.marker_ids())
+    genop = GAMMAPrimitiveComboGenOP(testconfig={"gpu_index": dev.index or 0})
+    genop.build_model(seed=0)
+    vposer, _ = load_vposer(seed=0, device=dev)
+    scene = assets.make_box_scene(0)
+    sdf = {k: v.to(dev) for k, v in assets.rasterize_scene_sdf(scene, D=64).items()}
+    venv = CrowdVectorEnv(default_cfg(), genop.model, lbs, vposer, sdf, assets.scene_polygon(scene),
+                          BoxSceneSampler(sdf, lbs, dev, seed=0), 4, dev)
+    venv.reset()
+    obs, rew, term, _, _ = venv.step(torch.zeros(4, 128, device=dev))
+    torch.cuda.synchronize(dev)
+    assert torch.isfinite(rew).all() and torch.isfinite(obs["state"]).all()
+    print("smoke env step ok: reward", [round(float(r), 4) for r in rew])

@@ -104,9 +104,12 @@ void eg_lbs_destroy(EgLbs* h);
  * `markers`. Rebuilds the compact vertex set (markers + vertex joints + landmark corners). */
 int eg_lbs_set_markers(EgLbs* h, const int32_t* marker_vids_host, int n_markers);
 int eg_lbs_max_skin_nnz(const EgLbs* h);
+/* SMPLXParser.calc_calibrate_offset (baseops.py:494-534): pelvis of the zero-transl / zero-orient body,
+ * i.e. the rest position of the root joint J_0(betas). out [N,3]. */
+int eg_lbs_rest_pelvis(EgLbs* h, const float* betas, int betas_rows, int N, float* out, void* stream);
 
 /* xb [N,93] = [transl3, global_orient3, body_pose63, lhand_pca12, rhand_pca12] (baseops.py:366-374),
- * betas [betas_rows,10] with betas_rows in {1,N}; expression / jaw / eye poses are zero as in the
+ * betas [betas_rows,10], betas_rows divides N and body n uses row n / (N / betas_rows); expression / jaw / eye poses are zero as in the
  * reference. Outputs (each nullable): verts [N,V,3], joints [N,127,3], markers [N,n_markers,3]. */
 int eg_lbs_forward(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
                    float* verts, float* joints, float* markers, void* stream);
@@ -160,6 +163,113 @@ typedef struct EgVposer EgVposer;
 int eg_vposer_create(const void* const* weights_host, int n_weights, int device, EgVposer** out);
 void eg_vposer_destroy(EgVposer* h);
 int eg_vposer_encode(EgVposer* h, const float* x, int ldx, int M, float* loc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Vectorised environment - replaces CrowdEnv.step / CrowdEnv.reset
+ * (motion/crowd_ppo/crowd_env_2f.py:78-317, 320-415) for E environments per call with the
+ * reference's 4x batch duplication removed. All state lives in caller-owned device buffers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EgEnv EgEnv;
+typedef struct EgEnvConfig {
+  int32_t max_depth;             /* 13 (MPVAEPolicy_samp_collision.yaml:80) */
+  int32_t finetuning;            /* crowd_env_2f.py:268-271,299-302 */
+  int32_t pene_terminate_count;  /* 40 (:176) */
+  int32_t feet_marker_idx[6];    /* main_ppo.py:298-299 */
+  float reproj_factor;           /* 0.5 */
+  float goal_thresh;             /* 0.1 */
+  float w_skate, w_floor, w_face, w_look, w_success, w_dist, w_vp, w_pene;
+  float ray_len;                 /* 7 */
+} EgEnvConfig;
+
+typedef struct EgEnvBuffers {    /* device pointers; (n) = nullable */
+  float* state;          /* [E,2,402] */
+  float* seed;           /* [E,2,93]  body_param_seed */
+  float* R0;             /* [E,3,3] */
+  float* T0;             /* [E,3] */
+  float* betas;          /* [E,10] */
+  float* dist;           /* [E] distance to goal after the previous step */
+  int32_t* steps;        /* [E] */
+  float* goal;           /* [E,3] world-space wpath[-1] */
+  float* ego;            /* [E,2,32] */
+  float* obs_dist;       /* [E] 1/(dist+1) */
+  float* obs_time;       /* [E] 1 - steps/max_depth */
+  float* reward;         /* [E] */
+  uint8_t* terminated;   /* [E] */
+  uint8_t* goal_reached; /* [E] (n) */
+  float* reward_terms;   /* [E,8] (n): skate, floor, face, look, goal, dist, pene, vp */
+  float* out_markers;    /* [E,20,67,3] (n) blended markers of this primitive (rollout writer) */
+  float* out_params;     /* [E,20,93]   (n) */
+  float* out_pelvis;     /* [E,20,3]    (n) */
+} EgEnvBuffers;
+
+int eg_env_create(const EgEnvConfig* cfg, EgLbs* lbs, EgMotion* motion, EgVposer* vposer, int device,
+                  EgEnv** out);
+void eg_env_destroy(EgEnv* h);
+int eg_env_set_config(EgEnv* h, const EgEnvConfig* cfg);
+/* scene: SDF grid as in eg_sdf_sample, feet skip mask [V], 2-D polygon boundary segments
+ * (x0,y0,x1,y1) float64 [n_segments,4] (exterior ring + holes of the reference's shapely polygon) */
+int eg_env_set_scene(EgEnv* h, const float* grid, int D0, int D1, int D2, const float* center_dev,
+                     const float* scale_dev, const uint8_t* skip_mask, const double* segments_dev,
+                     int n_segments);
+/* one transition of all E envs with actions z [E,128] */
+int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int E, void* stream);
+/* try to (re)start the envs env_ids [n] from sampled world-frame 2-frame seeds world_params [n,2,93],
+ * goals [n,3], betas_cand [n,10]; accept [n] = 1 where the start pose is SDF-clean (:379-380) and the
+ * slot was initialised, 0 where the caller must resample. */
+int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_ids, int n, const float* world_params,
+                 const float* goals, const float* betas_cand, int32_t* accept, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PPO policy - replaces GAMMAPolicyBase / GAMMAActor / GAMMACritic forward
+ * (motion/models/models_policy_ppo.py:287-350), GAMMAPPOPolicy.forward / _compute_returns / learn
+ * (motion/crowd_ppo/ppo_policy.py:105-265), tianshou's GAE and torch's clip_grad_norm_ + AdamW
+ * (main_ppo.py:134). Parameters / gradients / Adam moments are four caller-owned flat fp32 device
+ * buffers laid out in ActorCritic(actor, critic, shared_net).parameters() order:
+ *   actor.pnet.layers.{k}.layers.{0,1}.{weight,bias}, actor.pnet.out_fc.{weight,bias},
+ *   critic.vnet.(same), shared_net.x_enc.{weight_ih_l0,weight_hh_l0,bias_ih_l0,bias_hh_l0},
+ *   shared_net.ego_enc.(same).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EgPolicy EgPolicy;
+typedef struct EgPolicyDims {
+  int32_t in_dim;    /* 402 */
+  int32_t ego_dim;   /* 32 */
+  int32_t h_dim;     /* 512 */
+  int32_t pe_L;      /* 32 frequencies per scalar */
+  int32_t n_blocks;  /* 2 */
+  int32_t z_dim;     /* 128 */
+} EgPolicyDims;
+
+int64_t eg_policy_param_count(const EgPolicyDims* dims, int64_t* n_actor_critic);
+int eg_policy_create(const EgPolicyDims* dims, float* params_flat, float* grads_flat, int device, EgPolicy** out);
+void eg_policy_destroy(EgPolicy* h);
+/* obs batch: state [B,2,402], ego [B,2,32], dist [B], time [B]. out_actor [B,256] = raw [mu | logvar]
+ * (nullable), value [B] (nullable), hx_out [B,1152] (nullable). */
+int eg_policy_forward(EgPolicy* h, const float* state, const float* ego, const float* dist, const float* time,
+                      int B, int want_actor, int want_critic, float* out_actor, float* value, float* hx_out,
+                      void* stream);
+/* ppo_policy.py:168-179: act = mu + sqrt(exp(clamp(logvar))) * eps (eps NULL => act = mu), logp [B] (nullable) */
+int eg_gauss_sample(const float* out_actor, const float* eps, int B, int Z, float min_logvar, float max_logvar,
+                    float* act, float* logp, void* stream);
+/* one minibatch of GAMMAPPOPolicy.learn (:189-242): forward, loss, full backward into the flat gradient
+ * buffer. adv_norm is the already normalised advantage; inv_B = 1 / (global minibatch size) so that
+ * summing gradients over ranks reproduces the single-process mean. stats (device float[8], caller-zeroed):
+ * 0 clip loss, 1 value loss, 2 entropy, 3 kld indicator, 4 mean(logp_old - logp_new). */
+int eg_ppo_loss_backward(EgPolicy* h, const float* state, const float* ego, const float* dist, const float* time,
+                         const float* act, const float* logp_old, const float* adv_norm, const float* returns,
+                         int B, float inv_B, float eps_clip, float vf_coef, float ent_coef, float min_logvar,
+                         float max_logvar, int zero_grads, float* stats, void* stream);
+/* out2 (device double[2]) = {sum x, sum x^2} */
+int eg_moments(const float* x, int64_t n, double* out2, void* stream);
+/* (adv - mean) / (std_unbiased + eps) from moments3 (device double[3]) = {sum, sumsq, count} (:192-195) */
+int eg_adv_normalize(const float* adv, int n, const double* moments3, float eps, float* out, void* stream);
+/* clip_grad_norm_ over the actor+critic prefix (max_grad_norm <= 0 disables) fused with one AdamW step */
+int eg_clip_adamw_step(EgPolicy* h, float* exp_avg, float* exp_avg_sq, float max_grad_norm, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, void* stream);
+/* tianshou _gae_return on [T,E] time-major rollouts: v_next must already be critic(obs_next) unmasked;
+ * terminated masks it, end_flag = terminated | truncated | last-stored-step. adv, ret [T,E]. */
+int eg_gae(const float* v_s, const float* v_next, const float* rew, const uint8_t* terminated,
+           const uint8_t* end_flag, int T, int E, double gamma, double gae_lambda, float* adv, float* ret,
+           void* stream);
 
 /* y[M,out] = act(x W^T + b) + residual, W [out,in] row-major (nn.Linear; baseops.py:615-641 MLP layers).
  * act: 0 none, 1 tanh, 2 relu, 3 leaky-relu(slope). */

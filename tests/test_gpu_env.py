@@ -1,0 +1,152 @@
+"""GPU parity: motion model, VPoser, and the vectorised CrowdEnv step / reset vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from egogen_b200 import assets
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def world(dev, smplx_model):
+    """GPU operators + the matching CPU oracle objects built from the same arrays / weights."""
+    from egogen_b200.crowd_env import BoxSceneSampler, CrowdVectorEnv, default_cfg
+    from egogen_b200.models_gamma_primitive import GAMMAPrimitiveComboGenOP, load_vposer
+    from egogen_b200.smplx_parser import get_lbs_model
+    from oracle import nets
+    from oracle.env import CrowdEnvOracle
+    from oracle.smplx_lbs import SMPLXParserOracle
+    markers = assets.marker_ids()
+    lbs = get_lbs_model("male", dev, arrays=smplx_model, marker_vids=markers)
+    genop = GAMMAPrimitiveComboGenOP(testconfig={"gpu_index": 0})
+    genop.build_model(seed=0)
+    vposer, _ = load_vposer(seed=0, device=dev)
+    scene = assets.make_box_scene(2, n_boxes=2)
+    sdf_cpu = assets.rasterize_scene_sdf(scene, D=64)
+    sdf = {k: v.to(dev) for k, v in sdf_cpu.items()}
+    rings = assets.scene_polygon(scene)
+    sampler = BoxSceneSampler(sdf, lbs, dev, seed=0)
+    E = 6
+    venv = CrowdVectorEnv(default_cfg(), genop.model, lbs, vposer, sdf, rings, sampler, E, dev, debug_terms=True,
+                          capture_rollout=True)
+    # oracle twins with identical weights
+    combo = nets.ComboOracle()
+    combo.predictor.load_state_dict(genop.model.predictor.state_dict())
+    combo.regressor.load_state_dict(genop.model.regressor.state_dict())
+    vp_o = nets.VPoserEncoderOracle()
+    vp_o.load_state_dict(vposer.state_dict())
+    orc = CrowdEnvOracle(SMPLXParserOracle(smplx_model, marker=markers), combo.eval(), vp_o.eval(), sdf_cpu,
+                         assets.rings_to_segments(rings), markers, assets.feet_marker_idx(), assets.feet_vids())
+    return dict(venv=venv, orc=orc, genop=genop, vposer=vposer, combo=combo, vp_o=vp_o, sampler=sampler, E=E, lbs=lbs)
+
+
+def test_sample_prior_matches_oracle(dev, world):
+    g = torch.Generator().manual_seed(1)
+    b = 5
+    X = torch.randn(2, b, 201, generator=g) * 0.3
+    z = torch.randn(b, 128, generator=g)
+    betas = torch.randn(b, 10, generator=g) * 0.5
+    Y, Yb = world["genop"].model.sample_prior(X.to(dev), betas.unsqueeze(0).repeat(18, 1, 1).to(dev), z.to(dev))
+    with torch.no_grad():
+        Yo, Ybo = world["combo"].sample_prior(X, betas.unsqueeze(0).repeat(18, 1, 1), z)
+    assert Y.shape == (18, b, 201) and Yb.shape == (18, b, 93)
+    assert torch.allclose(Y.cpu(), Yo, atol=2e-5, rtol=1e-4)
+    # rotation entries go through 6-D -> rotmat -> quaternion -> axis-angle; compare as rotations
+    assert torch.allclose(Yb.cpu()[..., :3], Ybo[..., :3], atol=5e-5, rtol=1e-4)
+    assert torch.allclose(Yb.cpu()[..., 69:], Ybo[..., 69:], atol=5e-5, rtol=1e-4)
+    assert torch.allclose(Yb.cpu()[..., 3:69], Ybo[..., 3:69], atol=2e-4, rtol=1e-3)
+
+
+def test_vposer_matches_oracle(dev, world):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(40, 63, generator=g) * 0.4
+    loc = world["vposer"].encode(x.to(dev)).loc
+    with torch.no_grad():
+        ref = world["vp_o"].encode_loc(x)
+    assert torch.allclose(loc.cpu(), ref, atol=1e-5, rtol=1e-4)
+
+
+def _sync_oracle(orc, venv):
+    b = venv.buf
+    orc.set_state(state=b["state"].cpu(), seed=b["seed"].cpu(), R0=b["R0"].cpu(), T0=b["T0"].cpu().view(-1, 1, 3),
+                  betas=b["betas"].cpu(), dist=b["dist"].cpu(), steps=b["steps"].cpu().to(torch.int64),
+                  goal=b["goal"].cpu())
+
+
+def test_reset_matches_oracle(dev, world):
+    venv, orc, E = world["venv"], world["orc"], world["E"]
+    s = world["sampler"].next_body(E)
+    accept = venv.reset_from(torch.arange(E), s["world_params"], s["goals"], s["betas"])
+    ref = orc.reset_from(s["world_params"].cpu(), s["goals"].cpu(), s["betas"].cpu())
+    assert torch.equal(accept.cpu().bool(), ref["accept"])
+    assert accept.sum() > 0
+    m = ref["accept"]
+    b = venv.buf
+    assert torch.allclose(b["R0"].cpu()[m], ref["R0"][m], atol=1e-5)
+    assert torch.allclose(b["T0"].cpu()[m], ref["T0"][m, 0], atol=1e-5)
+    assert torch.allclose(b["seed"].cpu()[m], ref["seed"][m], atol=2e-5)
+    assert torch.allclose(b["state"].cpu()[m], ref["state"][m], atol=2e-5)
+    assert torch.allclose(b["dist"].cpu()[m], ref["dist"][m], atol=1e-5)
+    assert torch.allclose(b["ego"].cpu()[m], ref["egosensing"][m], atol=1e-3), (b["ego"].cpu()[m] - ref["egosensing"][m]).abs().max()
+
+
+def test_step_matches_oracle(dev, world):
+    """4 consecutive vector steps; the oracle is re-seeded from the GPU state before each step so every
+    step is an operator-level comparison on identical inputs (chaotic end-to-end)."""
+    venv, orc, E = world["venv"], world["orc"], world["E"]
+    venv.sampler.seed(3)
+    venv.reset()
+    g = torch.Generator().manual_seed(4)
+    for it in range(4):
+        _sync_oracle(orc, venv)
+        z = torch.randn(E, 128, generator=g)
+        obs, rew, term, _, _ = venv.step(z.to(dev))
+        ref = orc.step(z)
+        b = venv.buf
+        assert torch.allclose(b["out_params"].cpu(), ref["params"], atol=3e-4, rtol=1e-3)
+        assert torch.allclose(b["out_markers"].cpu(), ref["marker_b"], atol=1e-4)
+        assert torch.allclose(b["reward_terms"].cpu(), ref["terms"], atol=2e-4), (b["reward_terms"].cpu() - ref["terms"]).abs().max(0)
+        assert torch.allclose(rew.cpu(), ref["reward"], atol=5e-4)
+        assert torch.equal(term.cpu().bool(), ref["terminated"])
+        assert torch.allclose(b["R0"].cpu(), ref["R0"], atol=1e-4)
+        assert torch.allclose(b["T0"].cpu(), ref["T0"][:, 0], atol=1e-4)
+        assert torch.allclose(b["seed"].cpu(), ref["seed"], atol=3e-4, rtol=1e-3)
+        assert torch.allclose(obs["state"].cpu(), ref["state"], atol=2e-4)
+        assert torch.allclose(obs["egosensing"].cpu(), ref["egosensing"], atol=2e-3)
+        assert torch.allclose(obs["dist"].cpu()[:, 0], ref["dist"], atol=1e-4)
+        assert torch.allclose(obs["time"].cpu()[:, 0], ref["time"], atol=1e-6)
+        assert int(b["steps"][0]) == it + 1
+
+
+def test_single_env_gym_surface(dev, world, smplx_model):
+    """CrowdEnv keeps the reference's 12-element init_env constructor and 5-tuple step."""
+    from types import SimpleNamespace
+    from egogen_b200 import SMPLXParser
+    from egogen_b200.crowd_env import CrowdEnv, default_cfg
+    parser = SMPLXParser({"n_batch": 20, "device": dev, "marker_placement": "ssm2_67",
+                          "smplx_models": {"male": smplx_model, "female": smplx_model}})
+    sampler = world["sampler"]
+    scene = assets.make_box_scene(2, n_boxes=2)
+    sampler.scene_rings = assets.scene_polygon(scene)
+    genop = world["genop"]
+    init_env = [default_cfg(), genop, genop, None, sampler, parser, parser, parser, assets.feet_marker_idx(),
+                assets.marker_ids(), world["vposer"], world["venv"].scene_sdf]
+    env = CrowdEnv(init_env, save_rollout=True)
+    env.seed(0)
+    obs, info = env.reset()
+    assert obs["state"].shape == (2, 402) and obs["egosensing"].shape == (2, 32)
+    assert obs["dist"].shape == (1,) and obs["time"].shape == (1,) and info == {}
+    n = 0
+    term = False
+    while not term:
+        obs, rew, term, trunc, info = env.step(np.zeros(128, dtype=np.float32))
+        assert isinstance(rew, float) and isinstance(term, bool) and trunc is False
+        n += 1
+    assert 1 <= n <= 13 and len(env.outmps) == n

@@ -1,0 +1,141 @@
+"""GPU parity: policy forward, PPO loss/backward, clip+AdamW and GAE vs the CPU oracle (torch autograd)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from egogen_b200.assets import fill_params_
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"h_dim": 512, "z_dim": 128, "n_blocks": 2, "actfun": "lrelu", "body_repr": "ssm2_67_condi_marker_map",
+       "min_logvar": -2.5, "max_logvar": 2.5}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _make(dev, seed_offset=0):
+    from egogen_b200.models_policy_ppo import GAMMAActor, GAMMACritic, GAMMAPolicyBase
+    from egogen_b200.ppo_policy import GAMMAPPOPolicy
+    from oracle import nets
+    a, c, s = GAMMAActor(CFG), GAMMACritic(CFG), GAMMAPolicyBase(CFG)
+    fill_params_(a, 21 + seed_offset); fill_params_(c, 22 + seed_offset); fill_params_(s, 23 + seed_offset)
+    oa, oc, os_ = nets.ActorOracle(), nets.CriticOracle(), nets.PolicyBaseOracle()
+    oa.load_state_dict(a.state_dict()); oc.load_state_dict(c.state_dict()); os_.load_state_dict(s.state_dict())
+    a, c, s = a.to(dev), c.to(dev), s.to(dev)
+    optim = torch.optim.AdamW(list(a.parameters()) + list(c.parameters()) + list(s.parameters()), lr=3e-4, weight_decay=0.01)
+    pol = GAMMAPPOPolicy(a, c, s, optim, None, discount_factor=0.99, gae_lambda=0.95, max_grad_norm=0.1, vf_coef=1.0,
+                         ent_coef=0.01, eps_clip=0.1, advantage_normalization=1)
+    return pol, (oa, oc, os_)
+
+
+def _obs(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    return {"state": torch.randn(B, 2, 402, generator=g) * 0.5, "egosensing": torch.rand(B, 2, 32, generator=g) * 2 - 1,
+            "dist": torch.rand(B, 1, generator=g), "time": 1 - torch.randint(0, 13, (B, 1), generator=g) / 13.0}
+
+
+def test_policy_forward_golden(dev, golden_dir):
+    """Against outputs of the REFERENCE's own policy classes (tests/golden/nets_policy_golden.npz):
+    logits within 1e-4 relative (north_star tolerance)."""
+    pol, _ = _make(dev)
+    g = np.load(os.path.join(golden_dir, "nets_policy_golden.npz"))
+    obs = {k: torch.as_tensor(g[k]).to(dev) for k in ("state", "egosensing", "dist", "time")}
+    oa, val = pol.net_forward(obs)
+    mu, logvar = oa[:, :128].cpu(), oa[:, 128:].cpu()
+    for got, ref in ((mu, g["mu"]), (logvar, g["logvar"]), (val.cpu(), g["value"][:, 0])):
+        ref = torch.as_tensor(ref)
+        assert (got - ref).abs().max() <= 1e-4 * ref.abs().max() + 1e-6
+
+
+def test_state_dict_layout(dev):
+    """Checkpoint key groups of the reference policy and load round trip."""
+    pol, _ = _make(dev)
+    keys = list(pol.state_dict().keys())
+    groups = []
+    for k in keys:
+        gname = k.split(".pnet")[0].split(".vnet")[0].split(".x_enc")[0].split(".ego_enc")[0]
+        if not groups or groups[-1] != gname:
+            groups.append(gname)
+    assert groups == ["actor", "critic", "_actor_critic.actor", "_actor_critic.critic", "shared_net"]
+    assert "shared_net.x_enc.weight_ih_l0" in keys and "actor.pnet.layers.1.layers.0.weight" in keys
+    assert pol.state_dict()["shared_net.x_enc.weight_ih_l0"].shape == (1536, 402)
+    sd = {k: v.clone() + 1.0 for k, v in pol.state_dict().items()}
+    pol.load_state_dict(sd)
+    assert torch.allclose(pol.flat_params[:10], sd["actor.pnet.layers.0.layers.0.weight"].reshape(-1)[:10])
+    assert sum(p.numel() for p in pol._ordered_params()) == 13168001
+
+
+@pytest.mark.parametrize("B", [256, 32])
+def test_ppo_minibatch_matches_autograd(dev, B):
+    from egogen_b200.ppo_policy import Batch
+    from oracle import ppo as oppo
+    pol, (oa, oc, os_) = _make(dev)
+    obs = _obs(B, 5)
+    g = torch.Generator().manual_seed(6)
+    # actions near the policy mean so ratios straddle the clip range
+    with torch.no_grad():
+        mu, lv = oa(os_(obs))
+        sig = torch.exp(lv.clamp(-2.5, 2.5)) ** 0.5
+        act = mu + sig * torch.randn(B, 128, generator=g)
+        from torch.distributions import Independent, Normal
+        logp_old = Independent(Normal(mu, sig), 1).log_prob(act) + torch.randn(B, generator=g) * 0.08
+    adv = torch.randn(B, generator=g)
+    ret = torch.randn(B, generator=g)
+    ref = oppo.learn_minibatch(oa, oc, os_, obs, act, logp_old, adv, ret)
+    mb = Batch(obs={k: v.to(dev) for k, v in obs.items()}, act=act.to(dev), logp_old=logp_old.to(dev), adv=adv.to(dev),
+               returns=ret.to(dev))
+    pol.loss_backward(mb)
+    st = pol._stats.cpu()
+    assert abs(st[0] - ref["clip"]) < 2e-5 and abs(st[1] - ref["vf"]) < 2e-4 * max(1, ref["vf"])
+    assert abs(st[2] - ref["ent"]) < 1e-3 and abs(st[3] - ref["kld"]) < 1e-5 and abs(st[4] - ref["approx_kl"]) < 2e-5
+    # gradients, tensor by tensor
+    for (name, p), q in zip(list(pol.actor.named_parameters()) + list(pol.critic.named_parameters()) +
+                            list(pol.shared_net.named_parameters()),
+                            list(oa.parameters()) + list(oc.parameters()) + list(os_.parameters())):
+        gg, gr = p.grad.cpu(), q.grad
+        scale = gr.abs().max().item() + 1e-8
+        assert (gg - gr).abs().max().item() <= 2e-3 * scale + 1e-7, (name, (gg - gr).abs().max().item(), scale)
+    # clip (actor+critic only) + AdamW on IDENTICAL gradients (the first Adam step is ~lr*sign(g), so the
+    # optimiser is compared operator-level, not through the 1e-3-relative gradient differences)
+    for p, q in zip(pol._ordered_params(), list(oa.parameters()) + list(oc.parameters()) + list(os_.parameters())):
+        p.grad.copy_(q.grad.to(dev))
+    oppo.clip_and_adamw(oa, oc, os_)
+    pol.optimizer_step()
+    for (name, p), q in zip(list(pol.actor.named_parameters()) + list(pol.critic.named_parameters()) +
+                            list(pol.shared_net.named_parameters()),
+                            list(oa.parameters()) + list(oc.parameters()) + list(os_.parameters())):
+        assert torch.allclose(p.detach().cpu(), q.detach(), atol=2e-6, rtol=0), name
+    sd = pol.export_optim_state()
+    assert len(sd["state"]) == len(pol._ordered_params()) and sd["param_groups"][0]["lr"] == 3e-4
+
+
+def test_gae_matches_tianshou_restatement(dev):
+    from oracle import ppo as oppo
+    pol, _ = _make(dev)
+    T, E = 4, 256
+    g = torch.Generator().manual_seed(9)
+    v_s = torch.randn(T, E, generator=g)
+    v_next = torch.randn(T, E, generator=g)
+    rew = torch.randn(T, E, generator=g) * 3
+    term = torch.rand(T, E, generator=g) < 0.15
+    end = term.clone(); end[-1] = True
+    ret, adv = pol.compute_returns(v_s.to(dev), v_next.to(dev), rew.to(dev), term.to(torch.uint8).to(dev),
+                                   end.to(torch.uint8).to(dev))
+    # oracle in tianshou's env-major flat order
+    flat = lambda x: x.t().reshape(-1).numpy()
+    unfinished = np.zeros(T * E, bool); unfinished[T - 1::T] = ~flat(term)[T - 1::T]
+    r_ref, a_ref = oppo.compute_episodic_return(flat(v_s), flat(v_next), flat(rew).astype(np.float64), flat(term),
+                                                np.zeros(T * E, bool), unfinished)
+    assert np.allclose(adv.cpu().t().reshape(-1).numpy(), a_ref.astype(np.float32), atol=1e-6)
+    assert np.allclose(ret.cpu().t().reshape(-1).numpy(), r_ref.astype(np.float32), atol=1e-6)
+    # empty / single-step edge cases
+    r1, a1 = pol.compute_returns(v_s[:1].to(dev), v_next[:1].to(dev), rew[:1].to(dev), term[:1].to(torch.uint8).to(dev),
+                                 torch.ones(1, E, dtype=torch.uint8, device=dev))
+    exp = rew[:1] + 0.99 * v_next[:1] * (~term[:1]) - v_s[:1]
+    assert torch.allclose(a1.cpu(), exp, atol=1e-6)
