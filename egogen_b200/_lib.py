@@ -58,6 +58,8 @@ PROTOTYPES = {
     "eg_version": (_I, []),
     "eg_last_error": (C.c_char_p, []),
     "eg_launch_count": (_L, []),
+    "eg_profile_enable": (_I, [_I]),
+    "eg_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "eg_sdf_sample": (_I, [_P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P]),
     "eg_penetration_count": (_I, [_P, _I, _I, _P, _P, _P]),
     "eg_ego_depth": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _F, _P, _P, _P]),

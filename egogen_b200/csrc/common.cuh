@@ -47,6 +47,12 @@ inline int set_error(int code, const char* fmt, const char* a = "", const char* 
     EG_CUDA_CHECK(cudaGetLastError());                                                   \
   } while (0)
 
+// Optional device-side timing of one named kernel class (bench.py roofline): CUDA events recorded on the
+// launching stream around the kernel; eg_profile_read() synchronises and sums them.
+struct ProfSlot { cudaEvent_t a, b; int64_t units; };
+void prof_begin(cudaStream_t st, int64_t units);
+void prof_end(cudaStream_t st);
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 template <typename T>

@@ -464,7 +464,9 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
       a.sdf = sdf; a.R0 = R0; a.T0 = T0; a.frames_per_env = frames_per_env; a.skip = skip;
       a.counts = counts;
       EG_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)N * sizeof(int32_t), st));
+      prof_begin(st, N);
       EG_LAUNCH(lbs_verts_kernel<true>, grid, VERT_THREADS, VERT_SMEM, st, a);
+      prof_end(st);
     } else {
       EG_LAUNCH(lbs_verts_kernel<false>, grid, VERT_THREADS, VERT_SMEM, st, a);
     }

@@ -10,7 +10,7 @@
 
 namespace eg {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BK = 16;
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   switch (act) {
@@ -21,64 +21,113 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   }
 }
 
-template <bool TA, bool TB>
+// fp32 SIMT GEMM, BM x BN x 16 tiles, TM x TN outputs per thread, 256 threads, double-buffered shared
+// memory with register prefetch of the next k-tile (one __syncthreads per k-tile). Three tile shapes are
+// instantiated; launch_gemm picks the largest one that still fills the 148 SMs.
+template <int BM, int BN, int TM, int TN, bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_kernel(const GemmArgs g) {
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+  constexpr int NT = 256;
+  static_assert((BM / TM) * (BN / TN) == NT, "tile / thread mismatch");
+  constexpr int LA = BM * BK / NT, LB = BN * BK / NT;      // elements each thread loads per tile
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+  float ra[LA], rb[LB];
 
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
+  auto load_global = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + i * 256;
+    for (int i = 0; i < LA; ++i) {
+      const int idx = tid + i * NT;
       int m, k;
       if (TA) { k = idx / BM; m = idx % BM; } else { m = idx / BK; k = idx % BK; }
       const int gm = m0 + m, gk = k0 + k;
       float v = 0.0f;
       if (gm < g.M && gk < g.K)
         v = TA ? __ldg(g.A + (int64_t)gk * g.lda + gm) : __ldg(g.A + (int64_t)(gm / g.a_div) * g.lda + gk);
-      As[k][m] = v;
+      ra[i] = v;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + i * 256;
+    for (int i = 0; i < LB; ++i) {
+      const int idx = tid + i * NT;
       int n, k;
       if (TB) { n = idx / BK; k = idx % BK; } else { k = idx / BN; n = idx % BN; }
       const int gn = n0 + n, gk = k0 + k;
       float v = 0.0f;
       if (gn < g.N && gk < g.K)
         v = TB ? __ldg(g.B + (int64_t)gn * g.ldb + gk) : __ldg(g.B + (int64_t)gk * g.ldb + gn);
-      Bs[k][n] = v;
+      rb[i] = v;
     }
-    __syncthreads();
+  };
+  auto store_smem = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int idx = tid + i * NT;
+      int m, k;
+      if (TA) { k = idx / BM; m = idx % BM; } else { m = idx / BK; k = idx % BK; }
+      As[buf][k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int idx = tid + i * NT;
+      int n, k;
+      if (TB) { n = idx / BK; k = idx % BK; } else { k = idx / BN; n = idx % BN; }
+      Bs[buf][k][n] = rb[i];
+    }
+  };
+
+  const int nk = (g.K + BK - 1) / BK;
+  load_global(0);
+  store_smem(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) load_global((kt + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
+      float av[TM], bv[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; i += (TM >= 4 ? 4 : TM)) {
+        if (TM >= 4) {
+          const float4 a = *reinterpret_cast<const float4*>(&As[cur][k][ty * TM + i]);
+          av[i] = a.x; av[i + 1] = a.y; av[i + 2] = a.z; av[i + 3] = a.w;
+        } else {
+          const float2 a = *reinterpret_cast<const float2*>(&As[cur][k][ty * TM + i]);
+          av[i] = a.x; av[i + 1] = a.y;
+        }
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+      for (int j = 0; j < TN; j += (TN >= 4 ? 4 : TN)) {
+        if (TN >= 4) {
+          const float4 b = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * TN + j]);
+          bv[j] = b.x; bv[j + 1] = b.y; bv[j + 2] = b.z; bv[j + 3] = b.w;
+        } else {
+          const float2 b = *reinterpret_cast<const float2*>(&Bs[cur][k][tx * TN + j]);
+          bv[j] = b.x; bv[j + 1] = b.y;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += av[i] * bv[j];
     }
+    if (kt + 1 < nk) store_smem(cur ^ 1);
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= g.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
       if (n >= g.N) continue;
       float v = g.alpha * acc[i][j];
       if (g.bias) v += __ldg(g.bias + n);
@@ -90,14 +139,22 @@ gemm_kernel(const GemmArgs g) {
   }
 }
 
+template <int BM, int BN, int TM, int TN>
+static int launch_gemm_cfg(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  if (!TA && TB) EG_LAUNCH((gemm_kernel<BM, BN, TM, TN, false, true>), grid, 256, 0, st, g);
+  else if (!TA && !TB) EG_LAUNCH((gemm_kernel<BM, BN, TM, TN, false, false>), grid, 256, 0, st, g);
+  else if (TA && !TB) EG_LAUNCH((gemm_kernel<BM, BN, TM, TN, true, false>), grid, 256, 0, st, g);
+  else EG_LAUNCH((gemm_kernel<BM, BN, TM, TN, true, true>), grid, 256, 0, st, g);
+  return EG_OK;
+}
+
 int launch_gemm(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return EG_OK;
-  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
-  if (!TA && TB) EG_LAUNCH((gemm_kernel<false, true>), grid, 256, 0, st, g);
-  else if (!TA && !TB) EG_LAUNCH((gemm_kernel<false, false>), grid, 256, 0, st, g);
-  else if (TA && !TB) EG_LAUNCH((gemm_kernel<true, false>), grid, 256, 0, st, g);
-  else EG_LAUNCH((gemm_kernel<true, true>), grid, 256, 0, st, g);
-  return EG_OK;
+  auto ctas = [&](int bm, int bn) { return (int64_t)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn); };
+  if (ctas(128, 64) >= kNumSMs) return launch_gemm_cfg<128, 64, 8, 4>(g, TA, TB, st);
+  if (ctas(64, 64) >= kNumSMs) return launch_gemm_cfg<64, 64, 4, 4>(g, TA, TB, st);
+  return launch_gemm_cfg<32, 32, 2, 2>(g, TA, TB, st);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

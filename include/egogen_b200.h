@@ -41,6 +41,11 @@ int eg_version(void);
 const char* eg_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches counter) */
 int64_t eg_launch_count(void);
+/* device-side timing of the dominant kernel (fused LBS vertex kernel): CUDA events on the launching stream.
+ * eg_profile_enable(1) starts collecting; eg_profile_read synchronises, returns the summed kernel time and the
+ * number of timed launches, and clears the counters. */
+int eg_profile_enable(int on);
+int eg_profile_read(double* total_ms, int64_t* launches, int64_t* units /* bodies processed */);
 
 /* ------------------------------------------------------------------------------------------
  * calc_sdf  - replaces motion/crowd_ppo/utils.py:54-84 (F.grid_sample 5-D trilinear,
