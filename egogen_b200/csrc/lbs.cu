@@ -24,6 +24,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "lbs_tc.cuh"
 
 namespace eg {
 
@@ -40,6 +41,7 @@ constexpr int VERT_SMEM = sizeof(float) * 2 * KC * (TILE_V * 3 + TILE_B) + sizeo
 struct VertexSet {
   int n = 0, n_pad = 0, nnz = 0;
   float* basis = nullptr;
+  float* basisT = nullptr;   // [3][n_pad][tc::KT] planar K-major TF32-rounded copy for the tcgen05 mainloop (full set only)
   float* vt = nullptr;
   int32_t* skin_idx = nullptr;
   float* skin_w = nullptr;
@@ -61,9 +63,20 @@ struct EgLbs {
   // workspace
   int cap_N = 0;
   float *Ft = nullptr, *A = nullptr, *Jp = nullptr, *cout_ = nullptr;
+  float* Ftc = nullptr;       // [cap_N rounded up to 128][tc::KT] features for the tcgen05 mainloop
+  int cap_Ntc = 0;
+  int use_tc = 1;             // 1: tcgen05/TMEM/TMA mainloop for the full mesh, 0: SIMT mainloop
+  void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
+  CUtensorMap mapA;
 };
 
 namespace eg {
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 // --------------------------------------------------------------------------------------------
 // prep: one CTA of 64 threads per body
@@ -75,7 +88,8 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
                      const float* __restrict__ pose_mean, const float* __restrict__ Jt,
                      const float* __restrict__ Js, const int32_t* __restrict__ parents,
                      const int32_t* __restrict__ level_joints, const int32_t* __restrict__ level_start,
-                     float* __restrict__ Ft, float* __restrict__ A, float* __restrict__ Jp) {
+                     float* __restrict__ Ft, float* __restrict__ Ftc, float* __restrict__ A,
+                     float* __restrict__ Jp) {
   const int n = blockIdx.x;
   const int t = threadIdx.x;
   __shared__ float pose[MAXJ * 3];
@@ -142,6 +156,23 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
       v = shape[k - npose];
     }
     Ft[(int64_t)k * Npad + n] = v;
+  }
+  // same features for the tensor-core mainloop: row-major [n][KT], pose part rounded to TF32 (rna), shape
+  // coefficients split hi/lo and laid against the hi/hi, lo/hi, hi/lo shape rows of basisT
+  if (Ftc != nullptr) {
+    const int npose = (J - 1) * 9;
+    for (int k = t; k < tc::KT; k += 64) {
+      float v = 0.0f;
+      if (k < npose) {
+        const int j = 1 + k / 9, e = k % 9;
+        v = tf32_rna(R[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f));
+      } else if (k < npose + 3 * S) {
+        const int seg = (k - npose) / S, q = (k - npose) % S;
+        const float hi = tf32_rna(shape[q]);
+        v = seg == 1 ? tf32_rna(shape[q] - hi) : hi;
+      }
+      Ftc[(int64_t)n * tc::KT + k] = v;
+    }
   }
 
   // kinematic chain by tree level: G_j = G_parent [R_j | J_j - J_parent]
@@ -220,6 +251,48 @@ struct VertArgs {
   const uint8_t* skip;
   int32_t* counts;        // [N]
 };
+
+// One (vertex, body) of the epilogue shared by the SIMT and tcgen05 kernels: skinning T = sum_k w_k A[n][j_k],
+// v = T [v_posed; 1] (+ transl), optional store, optional world transform + calc_sdf sample; returns sdf < 0.
+template <bool FUSE_SDF>
+__device__ __forceinline__ bool vertex_epilogue(const VertArgs& a, int v, bool v_ok, int n, float px, float py,
+                                                float pz, bool skip, float cx, float cy, float cz, float sc) {
+  float T[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) T[e] = 0.0f;
+  const float4* An = reinterpret_cast<const float4*>(a.A + (int64_t)n * a.J * 12);
+  for (int k = 0; k < a.nnz; ++k) {
+    const int j = a.skin_idx[k * a.n_pad + v];
+    const float w = a.skin_w[k * a.n_pad + v];
+    const float4 r0 = __ldg(An + j * 3 + 0), r1 = __ldg(An + j * 3 + 1), r2 = __ldg(An + j * 3 + 2);
+    T[0] += w * r0.x; T[1] += w * r0.y; T[2] += w * r0.z; T[3] += w * r0.w;
+    T[4] += w * r1.x; T[5] += w * r1.y; T[6] += w * r1.z; T[7] += w * r1.w;
+    T[8] += w * r2.x; T[9] += w * r2.y; T[10] += w * r2.z; T[11] += w * r2.w;
+  }
+  float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+  float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+  float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+  if (a.add_transl) {
+    const float* x = a.xb + (int64_t)n * EG_XB_DIM;
+    ox = __fadd_rn(ox, __ldg(x)); oy = __fadd_rn(oy, __ldg(x + 1)); oz = __fadd_rn(oz, __ldg(x + 2));
+  }
+  if (a.out != nullptr && v_ok) {
+    float* o = a.out + ((int64_t)n * a.n_real + v) * 3;
+    o[0] = ox; o[1] = oy; o[2] = oz;
+  }
+  bool neg = false;
+  if (FUSE_SDF) {
+    const int e = n / a.frames_per_env;
+    const float* Rw = a.R0 + (int64_t)e * 9;
+    const float* Tw = a.T0 + (int64_t)e * 3;
+    const float wx = __ldg(Rw + 0) * ox + __ldg(Rw + 1) * oy + __ldg(Rw + 2) * oz + __ldg(Tw + 0);
+    const float wy = __ldg(Rw + 3) * ox + __ldg(Rw + 4) * oy + __ldg(Rw + 5) * oz + __ldg(Tw + 1);
+    const float wz = __ldg(Rw + 6) * ox + __ldg(Rw + 7) * oy + __ldg(Rw + 8) * oz + __ldg(Tw + 2);
+    int ix, iy, iz;
+    if (!skip) neg = sdf_sample_point(a.sdf, cx, cy, cz, sc, wx, wy, wz, ix, iy, iz) < 0.0f;
+  }
+  return neg;
+}
 
 template <bool FUSE_SDF>
 __global__ void __launch_bounds__(VERT_THREADS, 2)
@@ -302,40 +375,9 @@ lbs_verts_kernel(const VertArgs a) {
   for (int b = 0; b < BPG; ++b) {
     const int n = b0 + grp * BPG + b;
     if (n >= a.N) continue;                               // warp-uniform (n depends on grp, b only)
-    const float px = t0 + acc[b][0], py = t1 + acc[b][1], pz = t2 + acc[b][2];
-    float T[12];
-#pragma unroll
-    for (int e = 0; e < 12; ++e) T[e] = 0.0f;
-    const float4* An = reinterpret_cast<const float4*>(a.A + (int64_t)n * a.J * 12);
-    for (int k = 0; k < a.nnz; ++k) {
-      const int j = a.skin_idx[k * a.n_pad + v];
-      const float w = a.skin_w[k * a.n_pad + v];
-      const float4 r0 = __ldg(An + j * 3 + 0), r1 = __ldg(An + j * 3 + 1), r2 = __ldg(An + j * 3 + 2);
-      T[0] += w * r0.x; T[1] += w * r0.y; T[2] += w * r0.z; T[3] += w * r0.w;
-      T[4] += w * r1.x; T[5] += w * r1.y; T[6] += w * r1.z; T[7] += w * r1.w;
-      T[8] += w * r2.x; T[9] += w * r2.y; T[10] += w * r2.z; T[11] += w * r2.w;
-    }
-    float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
-    float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
-    float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-    if (a.add_transl) {
-      const float* x = a.xb + (int64_t)n * EG_XB_DIM;
-      ox = __fadd_rn(ox, __ldg(x)); oy = __fadd_rn(oy, __ldg(x + 1)); oz = __fadd_rn(oz, __ldg(x + 2));
-    }
-    if (a.out != nullptr && v_ok) {
-      float* o = a.out + ((int64_t)n * a.n_real + v) * 3;
-      o[0] = ox; o[1] = oy; o[2] = oz;
-    }
+    const bool neg = vertex_epilogue<FUSE_SDF>(a, v, v_ok, n, t0 + acc[b][0], t1 + acc[b][1], t2 + acc[b][2], skip,
+                                               cx, cy, cz, sc);
     if (FUSE_SDF) {
-      const int e = n / a.frames_per_env;
-      const float* Rw = a.R0 + (int64_t)e * 9;
-      const float* Tw = a.T0 + (int64_t)e * 3;
-      const float wx = __ldg(Rw + 0) * ox + __ldg(Rw + 1) * oy + __ldg(Rw + 2) * oz + __ldg(Tw + 0);
-      const float wy = __ldg(Rw + 3) * ox + __ldg(Rw + 4) * oy + __ldg(Rw + 5) * oz + __ldg(Tw + 1);
-      const float wz = __ldg(Rw + 6) * ox + __ldg(Rw + 7) * oy + __ldg(Rw + 8) * oz + __ldg(Tw + 2);
-      int ix, iy, iz;
-      bool neg = false;
-      if (!skip) neg = sdf_sample_point(a.sdf, cx, cy, cz, sc, wx, wy, wz, ix, iy, iz) < 0.0f;
       const unsigned m = __ballot_sync(0xffffffffu, neg);
       if ((tid & 31) == 0 && m) atomicAdd(&cnt_s[grp * BPG + b], __popc(m));
     }
@@ -343,6 +385,138 @@ lbs_verts_kernel(const VertArgs a) {
   if (FUSE_SDF) {
     __syncthreads();
     if (tid < TILE_B && b0 + tid < a.N && cnt_s[tid] > 0) atomicAdd(a.counts + b0 + tid, cnt_s[tid]);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// tcgen05 vertex kernel (full mesh): persistent, warp-specialised; see lbs_tc.cuh for the tile plan
+// --------------------------------------------------------------------------------------------
+template <bool FUSE_SDF>
+__global__ void __launch_bounds__(tc::THREADS, 1)
+lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const VertArgs a, int n_vt, int n_bt) {
+  using namespace tc;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = n_vt * n_bt;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(tmem_full, 1);
+      mbar_init(tmem_empty, EPI_WARPS);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int vt = tile % n_vt, bt = tile / n_vt;
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* st = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            tma_load_2d(st + c * A_TILE_BYTES, &mapA, &full_bar[stage], ch * BKT, c * a.n_pad + vt * TV);
+          tma_load_2d(st + 3 * A_TILE_BYTES, &mapB, &full_bar[stage], ch * BKT, bt * TB);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    int stage = 0; uint32_t phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(tmem_empty, (it & 1) ^ 1);                 // epilogue has drained the accumulators
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        mbar_wait(&full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t db = make_desc(sbase + 3 * A_TILE_BYTES);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const uint64_t da = make_desc(sbase + c * A_TILE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BKT / 8; ++kk)          // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
+              umma_tf32(tmem_base + c * TB, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), (ch | kk) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
+          if (ch == NCHUNK - 1) umma_commit(tmem_full);    // accumulators complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: lane quarter q (TMEM lanes 32q..32q+31 = vertices), column group cg (32 bodies) =====
+    const int q = warp & 3, cg = (warp - 4) >> 2;
+    float cx = 0.f, cy = 0.f, cz = 0.f, sc = 0.f;
+    if (FUSE_SDF) {
+      cx = __ldg(a.sdf.center); cy = __ldg(a.sdf.center + 1); cz = __ldg(a.sdf.center + 2);
+      sc = __ldg(a.sdf.scale);
+    }
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int vt = tile % n_vt, bt = tile / n_vt;
+      const int v = vt * TV + q * 32 + lane;
+      const bool v_ok = v < a.n_real;
+      const float t0 = a.vt[v * 3 + 0], t1 = a.vt[v * 3 + 1], t2 = a.vt[v * 3 + 2];
+      const bool skip = FUSE_SDF ? (v_ok ? (a.skip != nullptr && a.skip[v] != 0) : true) : false;
+      mbar_wait(tmem_full, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int jb = 0; jb < 4; ++jb) {
+        float ax[8], ay[8], az[8];
+        const uint32_t col = (uint32_t)(cg * 32 + jb * 8);
+        tmem_ld8(trow + col, ax);
+        tmem_ld8(trow + TB + col, ay);
+        tmem_ld8(trow + 2 * TB + col, az);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int n = bt * TB + cg * 32 + jb * 8 + b;
+          if (n >= a.N) continue;                           // warp-uniform
+          const bool neg = vertex_epilogue<FUSE_SDF>(a, v, v_ok, n, t0 + ax[b], t1 + ay[b], t2 + az[b], skip, cx, cy,
+                                                     cz, sc);
+          if (FUSE_SDF) {
+            const unsigned m = __ballot_sync(0xffffffffu, neg);
+            if (lane == 0 && m) atomicAdd(a.counts + n, __popc(m));
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -416,7 +590,7 @@ __global__ void rest_pelvis_kernel(const float* __restrict__ betas, int betas_di
 }
 
 static void free_vertex_set(VertexSet& s) {
-  cudaFree(s.basis); cudaFree(s.vt); cudaFree(s.skin_idx); cudaFree(s.skin_w);
+  cudaFree(s.basis); cudaFree(s.basisT); cudaFree(s.vt); cudaFree(s.skin_idx); cudaFree(s.skin_w);
   s = VertexSet();
 }
 
@@ -424,15 +598,37 @@ static int ensure_workspace(EgLbs* h, int N) {
   if (N <= h->cap_N) return EG_OK;
   int cap = std::max(N, 64);
   cap = (cap + 31) / 32 * 32;
-  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_);
-  h->Ft = h->A = h->Jp = h->cout_ = nullptr;
+  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc);
+  h->Ft = h->A = h->Jp = h->cout_ = h->Ftc = nullptr;
   h->cap_N = 0;
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Ft, (size_t)KPAD * cap * sizeof(float)));
   EG_CUDA_CHECK(cudaMemset(h->Ft, 0, (size_t)KPAD * cap * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->A, (size_t)cap * h->J * 12 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Jp, (size_t)cap * h->J * 3 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->cout_, (size_t)cap * 512 * 3 * sizeof(float)));
+  h->cap_Ntc = (cap + tc::TB - 1) / tc::TB * tc::TB;
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->Ftc, (size_t)h->cap_Ntc * tc::KT * sizeof(float)));
+  EG_CUDA_CHECK(cudaMemset(h->Ftc, 0, (size_t)h->cap_Ntc * tc::KT * sizeof(float)));
   h->cap_N = cap;
+  return EG_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D fp32 tensor [rows][tc::KT] (K contiguous), box = [32 k][box_rows], SWIZZLE_128B
+static int encode_map(EgLbs* h, CUtensorMap* map, const float* base, uint64_t rows, uint32_t box_rows) {
+  if (!h->encode_fn) return set_error(EG_ERR_STATE, "cuTensorMapEncodeTiled unavailable");
+  const cuuint64_t dims[2] = {(cuuint64_t)tc::KT, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)tc::KT * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)tc::BKT, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((EncodeTiledFn)h->encode_fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims,
+                                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(EG_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   return EG_OK;
 }
 
@@ -449,9 +645,10 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
   int rc = ensure_workspace(h, N);
   if (rc) return rc;
   const int Npad = h->cap_N;   // row stride of Ft (fixed per workspace so tiles never read OOB)
+  const bool want_tc = h->use_tc && h->full.basisT != nullptr && (verts != nullptr || fuse);
   EG_LAUNCH(lbs_pose_prep_kernel, N, 64, 0, st, xb, betas, betas_div, N, Npad, h->J, h->S,
             h->n_levels, h->hand_l, h->hand_r, h->pose_mean, h->Jt, h->Js, h->parents,
-            h->level_joints, h->level_start, h->Ft, h->A, h->Jp);
+            h->level_joints, h->level_start, h->Ft, want_tc ? h->Ftc : nullptr, h->A, h->Jp);
   VertArgs a{};
   a.Ft = h->Ft; a.A = h->A; a.xb = xb; a.N = N; a.Npad = Npad; a.J = h->J;
   const int by = (N + TILE_B - 1) / TILE_B;
@@ -464,6 +661,19 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
       a.sdf = sdf; a.R0 = R0; a.T0 = T0; a.frames_per_env = frames_per_env; a.skip = skip;
       a.counts = counts;
       EG_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)N * sizeof(int32_t), st));
+    }
+    if (want_tc) {
+      // B-operand tensor map over the feature matrix of this call (host-side encode, no device work)
+      CUtensorMap mapB;
+      int rc2 = encode_map(h, &mapB, h->Ftc, (uint64_t)h->cap_Ntc, tc::TB);
+      if (rc2) return rc2;
+      const int n_vt = s.n_pad / tc::TV, n_bt = (N + tc::TB - 1) / tc::TB;
+      const int grid_tc = std::min(n_vt * n_bt, kNumSMs);
+      prof_begin(st, N);
+      if (fuse) EG_LAUNCH(lbs_verts_tc_kernel<true>, grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
+      else EG_LAUNCH(lbs_verts_tc_kernel<false>, grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
+      prof_end(st);
+    } else if (fuse) {
       prof_begin(st, N);
       EG_LAUNCH(lbs_verts_kernel<true>, grid, VERT_THREADS, VERT_SMEM, st, a);
       prof_end(st);
@@ -527,12 +737,22 @@ extern "C" int eg_lbs_create(const EgLbsModel* m, int device, EgLbs** out) {
   EG_REQUIRE(m->n_joints > 0 && m->n_joints <= MAXJ, "n_joints must be in (0,64]");
   EG_REQUIRE((m->n_joints - 1) * 9 == m->n_pose_basis, "n_pose_basis must be 9*(n_joints-1)");
   EG_REQUIRE(m->n_pose_basis + m->n_shape <= KPAD && m->n_shape <= 32, "basis too large");
+  EG_REQUIRE(m->n_pose_basis + 3 * m->n_shape <= tc::KT, "basis too large for the tensor-core layout");
   EG_REQUIRE(m->n_hand_pca == 12 && m->n_joints == 55, "SMPL-X layout expected (55 joints, 12 hand PCA)");
   EG_CUDA_CHECK(cudaSetDevice(device));
   EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VERT_SMEM));
   EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VERT_SMEM));
+  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
   EgLbs* h = new EgLbs();
   h->device = device;
+  {
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      h->encode_fn = fn;
+  }
   const int V = h->V = m->n_verts, J = h->J = m->n_joints, S = h->S = m->n_shape, P = h->P = m->n_pose_basis;
   h->n_extra = m->n_extra; h->n_lmk = m->n_landmarks;
   h->h_extra.assign(m->extra_vids, m->extra_vids + m->n_extra);
@@ -602,6 +822,29 @@ extern "C" int eg_lbs_create(const EgLbsModel* m, int device, EgLbs** out) {
   ls.push_back((int32_t)lj.size());
   h->n_levels = maxd + 1;
   int rc = 0;
+  {
+    // planar K-major TF32 copy for the tcgen05 mainloop: basisT[c][v][k]; shape rows in hi/hi, hi(again), lo form
+    auto rnd = [](float x) {
+      uint32_t u; memcpy(&u, &x, 4);
+      u += 0xFFFu + ((u >> 13) & 1u); u &= ~0x1FFFu;
+      float y; memcpy(&y, &u, 4); return y;
+    };
+    std::vector<float> bt((size_t)3 * s.n_pad * tc::KT, 0.0f);
+    for (int c = 0; c < 3; ++c)
+      for (int v = 0; v < V; ++v) {
+        float* dst = &bt[((size_t)c * s.n_pad + v) * tc::KT];
+        for (int k = 0; k < P; ++k) dst[k] = rnd(m->posedirs[(size_t)k * V * 3 + (size_t)v * 3 + c]);
+        for (int k = 0; k < S; ++k) {
+          const float p = m->shapedirs[((size_t)v * 3 + c) * S + k];
+          const float hi = rnd(p), lo = rnd(p - hi);
+          dst[P + k] = hi;            // x shape_hi
+          dst[P + S + k] = hi;        // x shape_lo
+          dst[P + 2 * S + k] = lo;    // x shape_hi
+        }
+      }
+    rc |= dev_alloc_copy(&s.basisT, bt.data(), bt.size());
+    if (!rc && h->encode_fn) rc |= encode_map(h, &h->mapA, s.basisT, (uint64_t)3 * s.n_pad, tc::TV);
+  }
   rc |= dev_alloc_copy(&s.basis, basis.data(), basis.size());
   rc |= dev_alloc_copy(&s.vt, vt.data(), vt.size());
   rc |= dev_alloc_copy(&s.skin_idx, sidx.data(), sidx.size());
@@ -629,7 +872,7 @@ extern "C" void eg_lbs_destroy(EgLbs* h) {
   free_vertex_set(h->compact);
   cudaFree(h->Jt); cudaFree(h->Js); cudaFree(h->hand_l); cudaFree(h->hand_r); cudaFree(h->pose_mean);
   cudaFree(h->parents); cudaFree(h->level_joints); cudaFree(h->level_start); cudaFree(h->lmk_bary);
-  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_);
+  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc);
   delete h;
 }
 
@@ -669,5 +912,12 @@ extern "C" int eg_lbs_rest_pelvis(EgLbs* h, const float* betas, int betas_rows, 
   EG_REQUIRE(betas_rows >= 1 && N % betas_rows == 0, "betas_rows must divide N");
   EG_LAUNCH(rest_pelvis_kernel, (N * 3 + 127) / 128, 128, 0, as_stream(stream), betas, N / betas_rows, N, h->S,
             h->Jt, h->Js, out);
+  return EG_OK;
+}
+
+extern "C" int eg_lbs_set_mainloop(EgLbs* h, int use_tcgen05) {
+  EG_REQUIRE(h != nullptr, "null handle");
+  EG_REQUIRE(!use_tcgen05 || (h->encode_fn && h->full.basisT), "tcgen05 path unavailable (no driver entry point)");
+  h->use_tc = use_tcgen05 ? 1 : 0;
   return EG_OK;
 }

@@ -47,6 +47,10 @@ class LbsModel:
         if marker_vids is not None:
             self.set_markers(marker_vids)
 
+    def set_mainloop(self, use_tcgen05: bool):
+        """Full-mesh mainloop: tcgen05/TMEM/TMA TF32 tiles (default) or fp32 SIMT tiles."""
+        _lib.check(_lib.lib().eg_lbs_set_mainloop(self._h, int(bool(use_tcgen05))))
+
     def set_markers(self, vids):
         v = np.ascontiguousarray(np.asarray(vids, dtype=np.int32))
         _lib.check(_lib.lib().eg_lbs_set_markers(self._h, v.ctypes.data_as(C.c_void_p), len(v)))

@@ -109,6 +109,8 @@ void eg_lbs_destroy(EgLbs* h);
  * `markers`. Rebuilds the compact vertex set (markers + vertex joints + landmark corners). */
 int eg_lbs_set_markers(EgLbs* h, const int32_t* marker_vids_host, int n_markers);
 int eg_lbs_max_skin_nnz(const EgLbs* h);
+/* full-mesh mainloop: 1 (default) = tcgen05/TMEM/TMA TF32 tiles, 0 = fp32 SIMT tiles (debug / comparison) */
+int eg_lbs_set_mainloop(EgLbs* h, int use_tcgen05);
 /* SMPLXParser.calc_calibrate_offset (baseops.py:494-534): pelvis of the zero-transl / zero-orient body,
  * i.e. the rest position of the root joint J_0(betas). out [N,3]. */
 int eg_lbs_rest_pelvis(EgLbs* h, const float* betas, int betas_rows, int N, float* out, void* stream);

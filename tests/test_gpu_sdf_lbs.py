@@ -74,10 +74,13 @@ def _rand_inputs(n, seed, scale=0.3):
     return xb, torch.randn(10, generator=g)
 
 
-@pytest.mark.parametrize("n", [1, 4, 8, 37])
-def test_lbs_matches_oracle(dev, parser, smplx_model, n):
-    """LBS vertices / joints within 1e-4 relative (north_star tolerance) of the smplx restatement."""
+@pytest.mark.parametrize("tcgen05", [True, False])
+@pytest.mark.parametrize("n", [1, 4, 8, 37, 300])
+def test_lbs_matches_oracle(dev, parser, smplx_model, n, tcgen05):
+    """LBS vertices / joints within 1e-4 relative (north_star tolerance) of the smplx restatement, for both
+    full-mesh mainloops (tcgen05 TF32 tiles with hi/lo-split shape rows; fp32 SIMT tiles)."""
     from oracle.smplx_lbs import SMPLXParserOracle
+    parser.bm_male.set_mainloop(tcgen05)
     xb, betas = _rand_inputs(n, 100 + n)
     out = parser.forward_smplx(betas.to(dev), "male", xb.to(dev), to_numpy=False, output_type="raw")
     ref = SMPLXParserOracle(smplx_model, marker=assets.marker_ids()).forward_smplx(betas, "male", xb, "raw")
@@ -85,9 +88,13 @@ def test_lbs_matches_oracle(dev, parser, smplx_model, n):
         assert a.shape == b.shape
         rel = (a - b).norm(dim=-1).max() / b.norm(dim=-1).max()
         assert rel < 1e-4, rel                      # tolerance stated by BASELINE.json north_star
-        assert (a - b).abs().max() < 2e-5           # and in practice ~1e-6 absolute (fp32 SIMT)
+        assert (a - b).abs().max() < (5e-5 if tcgen05 else 2e-5), (a - b).abs().max()
     mk = parser.get_markers(betas.to(dev), "male", xb.to(dev), to_numpy=False)
-    assert torch.equal(mk, out.vertices[:, parser.marker])         # compact set == gathered full set
+    if tcgen05:   # markers come from the fp32 compact-set kernel, full vertices from the TF32 tiles
+        assert torch.allclose(mk, out.vertices[:, parser.marker], atol=5e-5)
+    else:         # same kernel, same arithmetic: compact set == gathered full set bit for bit
+        assert torch.equal(mk, out.vertices[:, parser.marker])
+    parser.bm_male.set_mainloop(True)
     j22 = parser.get_jts(betas.to(dev), "male", xb.to(dev), to_numpy=False)
     assert torch.equal(j22, out.joints[:, :22])
 
@@ -142,7 +149,7 @@ def test_fused_lbs_sdf_counts(dev, parser, smplx_model):
     c2 = penetration_count(sv, skip.to(dev))
     near = (sv.abs() < 1e-5).sum(dim=1).cpu()
     assert ((counts.cpu() - c2.cpu()).abs() <= near).all()
-    assert torch.equal(joints, out.joints) and torch.equal(markers, out.vertices[:, parser.marker])
+    assert torch.equal(joints, out.joints) and torch.allclose(markers, out.vertices[:, parser.marker], atol=5e-5)
     assert counts.sum() > 0, "test scene should produce some penetrations"
     # oracle chain
     ref = SMPLXParserOracle(smplx_model).forward_smplx(betas, "male", xb, "raw")
