@@ -64,6 +64,7 @@ struct EgLbs {
   int cap_N = 0;
   float *Ft = nullptr, *A = nullptr, *Jp = nullptr, *cout_ = nullptr;
   float* Ftc = nullptr;       // [cap_N rounded up to 128][tc::KT] features for the tcgen05 mainloop
+  float* Aw = nullptr;        // [cap_Ntc][J][12] world-composed transforms (fused tensor-core path)
   int cap_Ntc = 0;
   int use_tc = 1;             // 1: tcgen05/TMEM/TMA mainloop for the full mesh, 0: SIMT mainloop
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
@@ -89,7 +90,8 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
                      const float* __restrict__ Js, const int32_t* __restrict__ parents,
                      const int32_t* __restrict__ level_joints, const int32_t* __restrict__ level_start,
                      float* __restrict__ Ft, float* __restrict__ Ftc, float* __restrict__ A,
-                     float* __restrict__ Jp) {
+                     float* __restrict__ Jp, const float* __restrict__ R0w, const float* __restrict__ T0w,
+                     int frames_per_env, float* __restrict__ Aw) {
   const int n = blockIdx.x;
   const int t = threadIdx.x;
   __shared__ float pose[MAXJ * 3];
@@ -216,6 +218,27 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
       a_out[a * 4 + 2] = g2;
       a_out[a * 4 + 3] = g3 - (g0 * Jr[t][0] + g1 * Jr[t][1] + g2 * Jr[t][2]);
       jp[a] = g3;
+    }
+    // world-composed copy for the fused tensor-core path: R0 (A [v;1] + transl) + T0 folded into A
+    // (skinning weights sum to 1, so the translation part can ride inside every A_j)
+    if (Aw != nullptr) {
+      const int e = n / frames_per_env;
+      const float* Rw = R0w + (int64_t)e * 9;
+      const float* Tw = T0w + (int64_t)e * 3;
+      float* w_out = Aw + ((int64_t)n * J + t) * 12;
+      float col[4][3];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) col[b][a] = a_out[a * 4 + b];
+      col[3][0] += x[0]; col[3][1] += x[1]; col[3][2] += x[2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          w_out[a * 4 + b] = Rw[a * 3 + 0] * col[b][0] + Rw[a * 3 + 1] * col[b][1] + Rw[a * 3 + 2] * col[b][2] +
+                             (b == 3 ? Tw[a] : 0.0f);
+      }
     }
   }
 }
@@ -404,6 +427,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+  unsigned char* smemA = smem + STAGES * STAGE_BYTES + 256;     // 2 x ASTAGE_BYTES joint-transform staging
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = n_vt * n_bt;
@@ -470,13 +494,22 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: lane quarter q (TMEM lanes 32q..32q+31 = vertices), column group cg (32 bodies) =====
-    const int q = warp & 3, cg = (warp - 4) >> 2;
+    // ===== epilogue: TMEM lane quarter q (= 32 vertices), body slot cg within each 16-body chunk =====
+    // The joint transforms of a 16-body chunk are staged in shared memory by all 512 epilogue threads
+    // (cp.async, double-buffered) so the per-(vertex, body) skinning gathers hit smem instead of L2.
+    const int q = warp & 3, cg = (warp - 4) >> 2, eidx = tid - 128;
     float cx = 0.f, cy = 0.f, cz = 0.f, sc = 0.f;
     if (FUSE_SDF) {
       cx = __ldg(a.sdf.center); cy = __ldg(a.sdf.center + 1); cz = __ldg(a.sdf.center + 2);
       sc = __ldg(a.sdf.scale);
     }
+    const int chunk_f4 = CHUNK_B * a.J * 3;            // float4 per staged chunk
+    auto stage_chunk = [&](int buf, int n0) {
+      const float4* src = reinterpret_cast<const float4*>(a.A + (int64_t)n0 * a.J * 12);
+      float4* dst = reinterpret_cast<float4*>(smemA + buf * ASTAGE_BYTES);
+      for (int i = eidx; i < chunk_f4; i += EPI_WARPS * 32) cp_async16(dst + i, src + i);
+      cp_async_commit();
+    };
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int vt = tile % n_vt, bt = tile / n_vt;
@@ -484,28 +517,73 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const bool v_ok = v < a.n_real;
       const float t0 = a.vt[v * 3 + 0], t1 = a.vt[v * 3 + 1], t2 = a.vt[v * 3 + 2];
       const bool skip = FUSE_SDF ? (v_ok ? (a.skip != nullptr && a.skip[v] != 0) : true) : false;
+      int sj[4]; float sw[4];                          // first 4 skinning entries live in registers
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sj[k] = k < a.nnz ? a.skin_idx[k * a.n_pad + v] : 0;
+        sw[k] = k < a.nnz ? a.skin_w[k * a.n_pad + v] : 0.0f;
+      }
+      stage_chunk(0, bt * TB);                         // overlaps this tile's MMA
       mbar_wait(tmem_full, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int jb = 0; jb < 4; ++jb) {
-        float ax[8], ay[8], az[8];
-        const uint32_t col = (uint32_t)(cg * 32 + jb * 8);
-        tmem_ld8(trow + col, ax);
-        tmem_ld8(trow + TB + col, ay);
-        tmem_ld8(trow + 2 * TB + col, az);
+      for (int c = 0; c < TB / CHUNK_B; ++c) {
+        if (c + 1 < TB / CHUNK_B) { stage_chunk((c + 1) & 1, bt * TB + (c + 1) * CHUNK_B); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");     // chunk c staged by everyone
+        float ax[4], ay[4], az[4];
+        const uint32_t col = (uint32_t)(c * CHUNK_B + cg * 4);
+        tmem_ld4(trow + col, ax);
+        tmem_ld4(trow + TB + col, ay);
+        tmem_ld4(trow + 2 * TB + col, az);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float4* Ac = reinterpret_cast<const float4*>(smemA + (c & 1) * ASTAGE_BYTES);
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int n = bt * TB + cg * 32 + jb * 8 + b;
-          if (n >= a.N) continue;                           // warp-uniform
-          const bool neg = vertex_epilogue<FUSE_SDF>(a, v, v_ok, n, t0 + ax[b], t1 + ay[b], t2 + az[b], skip, cx, cy,
-                                                     cz, sc);
-          if (FUSE_SDF) {
+        for (int b = 0; b < 4; ++b) {
+          const int bl = cg * 4 + b;
+          const int n = bt * TB + c * CHUNK_B + bl;
+          if (n >= a.N) continue;                       // warp-uniform
+          const float px = t0 + ax[b], py = t1 + ay[b], pz = t2 + az[b];
+          const float4* An = Ac + bl * a.J * 3;
+          float T[12];
+#pragma unroll
+          for (int e = 0; e < 12; ++e) T[e] = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float w = sw[k];
+            const float4 r0 = An[sj[k] * 3 + 0], r1 = An[sj[k] * 3 + 1], r2 = An[sj[k] * 3 + 2];
+            T[0] += w * r0.x; T[1] += w * r0.y; T[2] += w * r0.z; T[3] += w * r0.w;
+            T[4] += w * r1.x; T[5] += w * r1.y; T[6] += w * r1.z; T[7] += w * r1.w;
+            T[8] += w * r2.x; T[9] += w * r2.y; T[10] += w * r2.z; T[11] += w * r2.w;
+          }
+          for (int k = 4; k < a.nnz; ++k) {             // rare: more than 4 non-zero weights
+            const int jj = a.skin_idx[k * a.n_pad + v];
+            const float w = a.skin_w[k * a.n_pad + v];
+            const float4 r0 = An[jj * 3 + 0], r1 = An[jj * 3 + 1], r2 = An[jj * 3 + 2];
+            T[0] += w * r0.x; T[1] += w * r0.y; T[2] += w * r0.z; T[3] += w * r0.w;
+            T[4] += w * r1.x; T[5] += w * r1.y; T[6] += w * r1.z; T[7] += w * r1.w;
+            T[8] += w * r2.x; T[9] += w * r2.y; T[10] += w * r2.z; T[11] += w * r2.w;
+          }
+          float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+          float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+          float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+          if (FUSE_SDF) {                                // transforms are world-composed: (ox,oy,oz) is the world point
+            int ix, iy, iz;
+            bool neg = false;
+            if (!skip) neg = sdf_sample_point(a.sdf, cx, cy, cz, sc, ox, oy, oz, ix, iy, iz) < 0.0f;
             const unsigned m = __ballot_sync(0xffffffffu, neg);
             if (lane == 0 && m) atomicAdd(a.counts + n, __popc(m));
+          } else {
+            const float* x = a.xb + (int64_t)n * EG_XB_DIM;
+            ox = __fadd_rn(ox, __ldg(x)); oy = __fadd_rn(oy, __ldg(x + 1)); oz = __fadd_rn(oz, __ldg(x + 2));
+            if (a.out != nullptr && v_ok) {
+              float* o = a.out + ((int64_t)n * a.n_real + v) * 3;
+              o[0] = ox; o[1] = oy; o[2] = oz;
+            }
           }
         }
+        asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");     // buffer (c&1) free for chunk c+2
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -598,12 +676,16 @@ static int ensure_workspace(EgLbs* h, int N) {
   if (N <= h->cap_N) return EG_OK;
   int cap = std::max(N, 64);
   cap = (cap + 31) / 32 * 32;
-  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc);
-  h->Ft = h->A = h->Jp = h->cout_ = h->Ftc = nullptr;
+  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc); cudaFree(h->Aw);
+  h->Ft = h->A = h->Jp = h->cout_ = h->Ftc = h->Aw = nullptr;
   h->cap_N = 0;
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Ft, (size_t)KPAD * cap * sizeof(float)));
   EG_CUDA_CHECK(cudaMemset(h->Ft, 0, (size_t)KPAD * cap * sizeof(float)));
-  EG_CUDA_CHECK(cudaMalloc((void**)&h->A, (size_t)cap * h->J * 12 * sizeof(float)));
+  const size_t cap128 = ((size_t)cap + tc::TB - 1) / tc::TB * tc::TB;   // the tc epilogue stages whole 16-body chunks
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->A, cap128 * h->J * 12 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMemset(h->A, 0, cap128 * h->J * 12 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->Aw, cap128 * h->J * 12 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMemset(h->Aw, 0, cap128 * h->J * 12 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Jp, (size_t)cap * h->J * 3 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->cout_, (size_t)cap * 512 * 3 * sizeof(float)));
   h->cap_Ntc = (cap + tc::TB - 1) / tc::TB * tc::TB;
@@ -648,7 +730,8 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
   const bool want_tc = h->use_tc && h->full.basisT != nullptr && (verts != nullptr || fuse);
   EG_LAUNCH(lbs_pose_prep_kernel, N, 64, 0, st, xb, betas, betas_div, N, Npad, h->J, h->S,
             h->n_levels, h->hand_l, h->hand_r, h->pose_mean, h->Jt, h->Js, h->parents,
-            h->level_joints, h->level_start, h->Ft, want_tc ? h->Ftc : nullptr, h->A, h->Jp);
+            h->level_joints, h->level_start, h->Ft, want_tc ? h->Ftc : nullptr, h->A, h->Jp, R0, T0,
+            frames_per_env, (want_tc && fuse) ? h->Aw : nullptr);
   VertArgs a{};
   a.Ft = h->Ft; a.A = h->A; a.xb = xb; a.N = N; a.Npad = Npad; a.J = h->J;
   const int by = (N + TILE_B - 1) / TILE_B;
@@ -668,6 +751,7 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
       int rc2 = encode_map(h, &mapB, h->Ftc, (uint64_t)h->cap_Ntc, tc::TB);
       if (rc2) return rc2;
       const int n_vt = s.n_pad / tc::TV, n_bt = (N + tc::TB - 1) / tc::TB;
+      if (fuse) a.A = h->Aw;        // world-composed transforms: the epilogue goes straight to the SDF sample
       const int grid_tc = std::min(n_vt * n_bt, kNumSMs);
       prof_begin(st, N);
       if (fuse) EG_LAUNCH(lbs_verts_tc_kernel<true>, grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
@@ -688,6 +772,7 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
     c.basis = s.basis; c.vt = s.vt; c.skin_idx = s.skin_idx; c.skin_w = s.skin_w;
     c.n_real = s.n; c.n_pad = s.n_pad; c.nnz = s.nnz; c.add_transl = 0; c.out = h->cout_;
     c.counts = nullptr;
+    c.A = h->A;                     // local-frame transforms (the fused path may have switched a.A to Aw)
     dim3 grid(s.n_pad / TILE_V, by);
     EG_LAUNCH(lbs_verts_kernel<false>, grid, VERT_THREADS, VERT_SMEM, st, c);
     EG_LAUNCH(lbs_finish_kernel, N, 128, 0, st, h->Jp, h->cout_, xb, h->lmk_bary, N, h->J,
@@ -872,7 +957,7 @@ extern "C" void eg_lbs_destroy(EgLbs* h) {
   free_vertex_set(h->compact);
   cudaFree(h->Jt); cudaFree(h->Js); cudaFree(h->hand_l); cudaFree(h->hand_r); cudaFree(h->pose_mean);
   cudaFree(h->parents); cudaFree(h->level_joints); cudaFree(h->level_start); cudaFree(h->lmk_bary);
-  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc);
+  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc); cudaFree(h->Aw);
   delete h;
 }
 

@@ -7,7 +7,8 @@
 //            coefficients are split hi/lo against hi/lo shape rows of the basis so the shape blend keeps
 //            ~fp32 accuracy - see build in lbs.cu).
 // Per CTA (persistent, 1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..19 =
-// epilogue. smem ring of 3 stages x (3 A tiles 128x32 + 1 B tile 128x32, SWIZZLE_128B) = 192 KB.
+// epilogue. smem: ring of 2 stages x (3 A tiles 128x32 + 1 B tile 128x32, SWIZZLE_128B) = 128 KB, plus
+// 2 x 48 KB staging of per-body joint transforms for the skinning epilogue.
 // Accumulators: 3 x 128 fp32 columns of TMEM; the epilogue reads its lane (= vertex) with tcgen05.ld,
 // applies skinning (+transl, optional store, optional world transform + SDF sample + penetration count).
 #pragma once
@@ -23,14 +24,16 @@ constexpr int BKT = 32;            // k-chunk per stage: 32 tf32 = 128 B = one s
 constexpr int NCHUNK = KT / BKT;   // 18
 constexpr int TV = 128;            // vertices per tile (UMMA M)
 constexpr int TB = 128;            // bodies per tile (UMMA N)
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
 constexpr int A_TILE_BYTES = TV * BKT * 4;   // 16 KB
 constexpr int B_TILE_BYTES = TB * BKT * 4;   // 16 KB
 constexpr int STAGE_BYTES = 3 * A_TILE_BYTES + B_TILE_BYTES;   // 64 KB
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 128 + EPI_WARPS * 32;   // 640
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers, tmem ptr, counts*/ + TB * 4;
+constexpr int CHUNK_B = 16;                           // bodies per staged joint-transform chunk
+constexpr int ASTAGE_BYTES = CHUNK_B * 64 * 48;        // up to 64 joints x 12 floats per body = 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers, tmem ptr*/ + 2 * ASTAGE_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -87,6 +90,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
