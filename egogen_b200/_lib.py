@@ -61,6 +61,8 @@ PROTOTYPES = {
     "eg_profile_enable": (_I, [_I]),
     "eg_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "eg_sdf_sample": (_I, [_P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P]),
+    "eg_sdf_prepare": (_I, [_P, _I, _I, _I, _P]),
+    "eg_sdf_release": (_I, [_P]),
     "eg_penetration_count": (_I, [_P, _I, _I, _P, _P, _P]),
     "eg_ego_depth": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _F, _P, _P, _P]),
     "eg_lbs_create": (_I, [C.POINTER(EgLbsModel), _I, C.POINTER(_P)]),

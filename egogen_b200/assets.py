@@ -71,9 +71,25 @@ SMPLX_KEYS = ("v_template", "shapedirs", "posedirs", "J_regressor", "parents", "
               "lmk_bary")
 
 
+def vertex_parts():
+    """Per-vertex body-part label (index into index_sets()['parts']) decoded from the run-length form."""
+    rle = index_sets()["part_rle"]
+    return np.concatenate([np.full(c, l, dtype=np.int32) for l, c in rle])
+
+
+# body part (order of index_sets()['parts']) -> SMPL-X joint the part hangs off
+_PART_JOINT = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, -1, -2, 23, 24]
+
+
 def make_surrogate_smplx(seed: int = 0, nnz_per_vertex: int = 4) -> Dict[str, np.ndarray]:
-    """Synthetic SMPL-X-shaped model: real V/J/basis sizes and the real
-    kinematic tree, random but well-conditioned arrays. Keys are SMPLX_KEYS; all float32/int32.
+    """Synthetic SMPL-X-shaped model: real V / J / basis sizes, the real kinematic
+    tree and the REAL vertex-id -> body-part map (motion/data/smplx_vert_segmentation.json via
+    tools/make_index_sets.py), so that - like the licensed model - consecutive vertex ids lie next to each
+    other on the surface and share their skinning joints (runs of 10-500 ids per part). Geometry is a
+    capsule figure: every part's vertices spiral around its bone in id order. Skinning weights have
+    ``nnz_per_vertex`` non-zeros on kinematic neighbours (own joint, parent, child, grand-parent) varying
+    smoothly along the bone. Blend-shape bases are dense Gaussian noise of realistic magnitude.
+    Keys are SMPLX_KEYS; float32 / int32.
 
     posedirs is stored the way smplx keeps it at run time: [486, V*3] row-major
     (smplx reshapes the npz [V,3,486] array to (-1,486).T in SMPL.__init__).
@@ -81,54 +97,96 @@ def make_surrogate_smplx(seed: int = 0, nnz_per_vertex: int = 4) -> Dict[str, np
     rng = np.random.default_rng(seed)
     V, J = V_SMPLX, J_SMPLX
     parents = SMPLX_PARENTS.copy()
-    # rest skeleton: a y-up stick figure. offsets shrink with depth so hands/face stay compact.
+    children = [[c for c in range(J) if parents[c] == j] for j in range(J)]
     depth = np.zeros(J, dtype=np.int32)
     for j in range(1, J):
         depth[j] = depth[parents[j]] + 1
+    # rest skeleton: a y-up stick figure
     jrest = np.zeros((J, 3), dtype=np.float64)
     dirs = rng.normal(size=(J, 3))
     dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
-    # hips go sideways (joint 1 = left hip +x, joint 2 = right hip -x) so the canonical frame is defined
-    dirs[1] = [1.0, -0.3, 0.0]; dirs[2] = [-1.0, -0.3, 0.0]; dirs[3] = [0.0, 1.0, 0.0]
+    dirs[1] = [1.0, -0.3, 0.0]; dirs[2] = [-1.0, -0.3, 0.0]; dirs[3] = [0.0, 1.0, 0.0]   # hips sideways
     for j in (4, 5, 7, 8):
-        dirs[j] = [0.0, -1.0, 0.05 * (j % 2)]
+        dirs[j] = [0.0, -1.0, 0.02]
+    dirs[10] = dirs[11] = [0.0, -0.3, 1.0]
     for j in (6, 9, 12, 15):
         dirs[j] = [0.0, 1.0, 0.0]
-    dirs[23] = [0.3, 0.2, 0.9]; dirs[24] = [-0.3, 0.2, 0.9]   # eyeball joints: left (+x) / right (-x)
+    dirs[13] = [0.6, 0.8, 0.0]; dirs[14] = [-0.6, 0.8, 0.0]
+    dirs[16] = dirs[18] = dirs[20] = [1.0, -0.2, 0.0]
+    dirs[17] = dirs[19] = dirs[21] = [-1.0, -0.2, 0.0]
+    dirs[22] = [0.0, -0.3, 1.0]
+    dirs[23] = [0.3, 0.2, 0.9]; dirs[24] = [-0.3, 0.2, 0.9]      # eyeball joints: left (+x) / right (-x)
+    for j in range(25, 40):
+        dirs[j] = [1.0, -0.1, 0.1 * ((j - 25) // 3 - 2)]
+    for j in range(40, 55):
+        dirs[j] = [-1.0, -0.1, 0.1 * ((j - 40) // 3 - 2)]
     dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
-    seg_len = np.where(depth <= 1, 0.12, np.where(depth <= 4, 0.38, 0.12))
-    seg_len = np.where(parents >= 25 - 5, 0.03, seg_len)        # fingers
-    seg_len[[23, 24]] = 0.08
+    seg_len = np.full(J, 0.12)
+    seg_len[[4, 5, 7, 8]] = 0.40; seg_len[[16, 17, 18, 19]] = 0.26; seg_len[[10, 11]] = 0.12
+    seg_len[[6, 9]] = 0.15; seg_len[[13, 14]] = 0.14; seg_len[[20, 21]] = 0.08
+    seg_len[[22, 23, 24]] = 0.08
+    seg_len[25:] = 0.03
     for j in range(1, J):
         jrest[j] = jrest[parents[j]] + seg_len[j] * dirs[j]
     jrest[:, 1] -= 0.35                                          # pelvis slightly below origin like SMPL-X
-    assign = rng.integers(0, J, size=V)
-    fv = np.array(feet_vids())
-    assign[fv] = np.where(rng.random(len(fv)) < 0.5, 10, 11)     # feet vertices hang off the foot joints
-    v_template = jrest[assign] + rng.normal(scale=0.04, size=(V, 3))
+    # vertex -> joint from the real part labels; the two hand-finger parts are spread over the 15 finger joints
+    part = vertex_parts()
+    assign = np.zeros(V, dtype=np.int64)
+    rank = np.zeros(V, dtype=np.float64)                          # position of the vertex inside its part, in [0,1)
+    for pi, pj in enumerate(_PART_JOINT):
+        ids = np.nonzero(part == pi)[0]
+        if len(ids) == 0:
+            continue
+        r = np.arange(len(ids)) / len(ids)
+        if pj >= 0:
+            assign[ids] = pj
+            rank[ids] = r
+        else:                                                     # fingers: 15 joints, contiguous id blocks each
+            base = 25 if pj == -1 else 40
+            blk = np.minimum((r * 15).astype(np.int64), 14)
+            assign[ids] = base + blk
+            rank[ids] = r * 15 - blk
+    # geometry: spiral around the bone from the joint towards its (first) child / along its own direction
+    radius = np.where(depth <= 3, 0.11, 0.05)
+    radius[15] = 0.10; radius[[23, 24]] = 0.012; radius[25:] = 0.008; radius[[7, 8, 10, 11]] = 0.04
+    axis = dirs.copy()
+    length = np.array([seg_len[children[j][0]] if children[j] else seg_len[j] for j in range(J)])
+    length[15] = 0.22
+    ref = np.where(np.abs(axis[:, [1]]) < 0.9, [[0.0, 1.0, 0.0]], [[1.0, 0.0, 0.0]])
+    e1 = np.cross(axis, ref); e1 /= np.linalg.norm(e1, axis=1, keepdims=True)
+    e2 = np.cross(axis, e1)
+    a, t = assign, rank
+    turns = 14.0
+    ang = 2 * np.pi * turns * t
+    v_template = (jrest[a] + (t * length[a])[:, None] * axis[a]
+                  + (radius[a] * np.cos(ang))[:, None] * e1[a] + (radius[a] * np.sin(ang))[:, None] * e2[a]
+                  + rng.normal(scale=0.002, size=(V, 3)))
     # eye-surface vertices used as joints 56/57 sit in front of the eyeball joints
     v_template[SMPLX_EXTRA_JOINT_VIDS[1]] = jrest[24] + [0.0, 0.0, 0.02]
     v_template[SMPLX_EXTRA_JOINT_VIDS[2]] = jrest[23] + [0.0, 0.0, 0.02]
     shapedirs = rng.normal(scale=0.01, size=(V, 3, N_SHAPE))
     posedirs = rng.normal(scale=1e-3, size=(N_POSE_BASIS, V * 3))
-    # joint regressor: each row a softmax over 32 vertices assigned to (or near) that joint
+    # joint regressor: each row a softmax over 32 vertices of (or near) that joint
     J_regressor = np.zeros((J, V))
     for j in range(J):
         own = np.nonzero(assign == j)[0]
         if len(own) < 32:
-            own = np.concatenate([own, rng.integers(0, V, size=32 - len(own))])
+            near = np.argsort(np.linalg.norm(v_template - jrest[j], axis=1))[:64]
+            own = np.unique(np.concatenate([own, near]))
         pick = rng.choice(own, size=32, replace=False)
         w = np.exp(rng.normal(size=32)); w /= w.sum()
         J_regressor[j, pick] = w
-    # skinning weights: nnz_per_vertex non-zeros (own joint, parent, random others), Dirichlet(1)
+    # skinning: own joint, parent, child (else grand-parent), grand-parent / sibling; smooth along the bone
+    par = np.maximum(parents, 0)
+    child = np.array([children[j][0] if children[j] else par[par[j]] for j in range(J)])
+    gpar = par[par]
+    cand = np.stack([a, par[a], child[a], gpar[a]], axis=1)[:, :max(nnz_per_vertex, 1)]
+    wraw = np.stack([np.full(V, 1.0), 0.6 * (1 - t), 0.6 * t, np.full(V, 0.08)], axis=1)[:, :cand.shape[1]]
+    wraw = wraw * np.exp(rng.normal(scale=0.05, size=wraw.shape))
+    wraw /= wraw.sum(axis=1, keepdims=True)
     lbs_weights = np.zeros((V, J))
-    others = rng.integers(0, J, size=(V, nnz_per_vertex))
-    others[:, 0] = assign
-    if nnz_per_vertex > 1:
-        others[:, 1] = np.maximum(parents[assign], 0)
-    w = rng.dirichlet(np.ones(nnz_per_vertex), size=V)
-    for k in range(nnz_per_vertex):
-        np.add.at(lbs_weights, (np.arange(V), others[:, k]), w[:, k])
+    for k in range(cand.shape[1]):
+        np.add.at(lbs_weights, (np.arange(V), cand[:, k]), wraw[:, k])
     hand_comp_l = rng.normal(scale=0.1, size=(N_HAND_PCA, 45))
     hand_comp_r = rng.normal(scale=0.1, size=(N_HAND_PCA, 45))
     pose_mean = np.zeros(J * 3)

@@ -76,7 +76,15 @@ struct SdfGrid {
   int D0, D1, D2;
   const float* center;  // device [3]
   const float* scale;   // device [1]
+  // optional conservative coarse grid (eg_sdf_prepare): coarse[c] = min of (-grid) over every fine corner a
+  // trilinear sample inside the 8^3-cell c can touch; > 0 means no sample in the cell can be negative
+  const float* coarse = nullptr;
+  int C0 = 0, C1 = 0, C2 = 0;
 };
+constexpr int kCoarseShift = 3;
+
+// host-side lookup of the coarse grid registered for `grid` by eg_sdf_prepare (fills g.coarse / C*)
+void sdf_attach_coarse(SdfGrid& g);
 
 // un-normalise with align_corners=False then clamp to [0, D-1] (padding_mode='border').
 // Written with explicit round-to-nearest intrinsics so ptxas cannot contract the sequence into
@@ -121,6 +129,22 @@ __device__ __forceinline__ float sdf_sample_point(const SdfGrid& g, float cx, fl
     if (y1ok && z1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(b + sx + sy + 1), __fmul_rn(__fmul_rn(wz1, wy1), wx1)));
   }
   return -acc;
+}
+
+// sign-only query used by the fused penetration count: identical to sdf_sample_point(...) < 0 (the trilinear
+// sample is a non-negative combination of the cell's corners, so a positive coarse minimum proves "not negative"
+// without touching the fine grid); falls back to the exact sample otherwise.
+__device__ __forceinline__ bool sdf_is_negative(const SdfGrid& g, float cx, float cy, float cz, float s, float x,
+                                                float y, float z) {
+  if (g.coarse != nullptr) {
+    const float ix = sdf_unnormalize(__fmul_rn(__fsub_rn(x, cx), s), g.D0);
+    const float iy = sdf_unnormalize(__fmul_rn(__fsub_rn(y, cy), s), g.D1);
+    const float iz = sdf_unnormalize(__fmul_rn(__fsub_rn(z, cz), s), g.D2);
+    const int c0 = (int)ix >> kCoarseShift, c1 = (int)iy >> kCoarseShift, c2 = (int)iz >> kCoarseShift;
+    if (__ldg(g.coarse + ((int64_t)c0 * g.C1 + c1) * g.C2 + c2) > 0.0f) return false;
+  }
+  int ox, oy, oz;
+  return sdf_sample_point(g, cx, cy, cz, s, x, y, z, ox, oy, oz) < 0.0f;
 }
 
 }  // namespace eg

@@ -420,7 +420,7 @@ extern "C" int eg_env_set_scene(EgEnv* h, const float* grid, int D0, int D1, int
   EG_REQUIRE(D0 > 0 && D1 > 0 && D2 > 0 && n_segments > 0, "bad sizes");
   h->grid = grid; h->D0 = D0; h->D1 = D1; h->D2 = D2; h->center = center_dev; h->scale = scale_dev;
   h->skip = skip_mask; h->segs = segments_dev; h->S = n_segments;
-  return EG_OK;
+  return eg_sdf_prepare(grid, D0, D1, D2, nullptr);   // conservative coarse grid for the fused sign query
 }
 
 #define EG_TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)

@@ -311,8 +311,7 @@ __device__ __forceinline__ bool vertex_epilogue(const VertArgs& a, int v, bool v
     const float wx = __ldg(Rw + 0) * ox + __ldg(Rw + 1) * oy + __ldg(Rw + 2) * oz + __ldg(Tw + 0);
     const float wy = __ldg(Rw + 3) * ox + __ldg(Rw + 4) * oy + __ldg(Rw + 5) * oz + __ldg(Tw + 1);
     const float wz = __ldg(Rw + 6) * ox + __ldg(Rw + 7) * oy + __ldg(Rw + 8) * oz + __ldg(Tw + 2);
-    int ix, iy, iz;
-    if (!skip) neg = sdf_sample_point(a.sdf, cx, cy, cz, sc, wx, wy, wz, ix, iy, iz) < 0.0f;
+    if (!skip) neg = sdf_is_negative(a.sdf, cx, cy, cz, sc, wx, wy, wz);
   }
   return neg;
 }
@@ -569,9 +568,8 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
           float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
           if (FUSE_SDF) {                                // transforms are world-composed: (ox,oy,oz) is the world point
-            int ix, iy, iz;
             bool neg = false;
-            if (!skip) neg = sdf_sample_point(a.sdf, cx, cy, cz, sc, ox, oy, oz, ix, iy, iz) < 0.0f;
+            if (!skip) neg = sdf_is_negative(a.sdf, cx, cy, cz, sc, ox, oy, oz);
             const unsigned m = __ballot_sync(0xffffffffu, neg);
             if (lane == 0 && m) atomicAdd(a.counts + n, __popc(m));
           } else {
@@ -987,6 +985,7 @@ extern "C" int eg_lbs_forward_sdf(EgLbs* h, const float* xb, const float* betas,
   EG_REQUIRE(frames_per_env > 0 && N % frames_per_env == 0, "N must be a multiple of frames_per_env");
   EG_REQUIRE(markers == nullptr || h->n_markers > 0, "markers requested but none set");
   SdfGrid g{grid, D0, D1, D2, center_dev, scale_dev};
+  sdf_attach_coarse(g);     // sign-only early-out grid, if eg_sdf_prepare was called for this grid
   return run_forward(h, xb, betas, betas_rows, N, nullptr, joints, markers, true, frames_per_env, R0,
                      T0, g, skip_mask, counts, as_stream(stream));
 }

@@ -81,6 +81,22 @@ ego_depth_kernel(SdfGrid g, const float* __restrict__ cam, int A, int H, int W, 
   }
 }
 
+// coarse[c] = min over fine indices [8c, min(8c+8, D-1)]^3 of (-grid): one thread per coarse cell
+__global__ void __launch_bounds__(128)
+sdf_coarse_kernel(const float* __restrict__ grid, int D0, int D1, int D2, int C0, int C1, int C2,
+                  float* __restrict__ coarse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C0 * C1 * C2) return;
+  const int c2 = i % C2, c1 = (i / C2) % C1, c0 = i / (C1 * C2);
+  const int cs = 1 << kCoarseShift;
+  float mn = INFINITY;
+  for (int x = c0 * cs; x <= min(c0 * cs + cs, D0 - 1); ++x)
+    for (int y = c1 * cs; y <= min(c1 * cs + cs, D1 - 1); ++y)
+      for (int z = c2 * cs; z <= min(c2 * cs + cs, D2 - 1); ++z)
+        mn = fminf(mn, -grid[((int64_t)x * D1 + y) * D2 + z]);
+  coarse[i] = mn;
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t b = (n + block - 1) / block;
   const int64_t cap = (int64_t)kNumSMs * 16;  // multiple of the SM count, grid-stride beyond
@@ -91,7 +107,46 @@ static inline int grid_for(int64_t n, int block) {
 
 }  // namespace eg
 
+#include <map>
+#include <mutex>
+namespace eg {
+struct CoarseEntry { float* coarse; int D0, D1, D2, C0, C1, C2; };
+static std::map<const float*, CoarseEntry> g_coarse;
+static std::mutex g_coarse_mu;
+void sdf_attach_coarse(SdfGrid& g) {
+  std::lock_guard<std::mutex> lk(g_coarse_mu);
+  auto it = g_coarse.find(g.grid);
+  if (it == g_coarse.end() || it->second.D0 != g.D0 || it->second.D1 != g.D1 || it->second.D2 != g.D2) return;
+  g.coarse = it->second.coarse; g.C0 = it->second.C0; g.C1 = it->second.C1; g.C2 = it->second.C2;
+}
+}  // namespace eg
+
 using namespace eg;
+
+extern "C" int eg_sdf_prepare(const float* grid, int D0, int D1, int D2, void* stream) {
+  EG_REQUIRE(grid && D0 > 0 && D1 > 0 && D2 > 0, "bad arguments");
+  const int cs = 1 << kCoarseShift;
+  CoarseEntry e{nullptr, D0, D1, D2, (D0 + cs - 1) / cs, (D1 + cs - 1) / cs, (D2 + cs - 1) / cs};
+  {
+    std::lock_guard<std::mutex> lk(g_coarse_mu);
+    auto it = g_coarse.find(grid);
+    if (it != g_coarse.end()) { cudaFree(it->second.coarse); g_coarse.erase(it); }
+  }
+  const int n = e.C0 * e.C1 * e.C2;
+  EG_CUDA_CHECK(cudaMalloc((void**)&e.coarse, (size_t)n * sizeof(float)));
+  EG_LAUNCH(sdf_coarse_kernel, (n + 127) / 128, 128, 0, as_stream(stream), grid, D0, D1, D2, e.C0, e.C1, e.C2, e.coarse);
+  EG_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
+  std::lock_guard<std::mutex> lk(g_coarse_mu);
+  g_coarse[grid] = e;
+  return EG_OK;
+}
+
+extern "C" int eg_sdf_release(const float* grid) {
+  std::lock_guard<std::mutex> lk(g_coarse_mu);
+  auto it = g_coarse.find(grid);
+  if (it != g_coarse.end()) { cudaFree(it->second.coarse); g_coarse.erase(it); }
+  return EG_OK;
+}
 
 extern "C" int eg_sdf_sample(const float* grid, int D0, int D1, int D2, const float* center_dev,
                              const float* scale_dev, const float* pts, int64_t P, float* val,

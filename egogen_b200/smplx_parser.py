@@ -85,6 +85,12 @@ class LbsModel:
         if R0.shape[0] * frames_per_env != N or T0.shape[0] != R0.shape[0]:
             raise _lib.EgError("R0/T0 must have N/frames_per_env rows")
         grid = _grid3(sdf_dict)
+        if sdf_dict.get("_prepared_ptr") != grid.data_ptr():     # one-time conservative coarse grid (exact early-out)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().eg_sdf_prepare(_lib.ptr(grid), grid.shape[0], grid.shape[1], grid.shape[2],
+                                                     _lib.stream_ptr(self.device)))
+            sdf_dict["_prepared_ptr"] = grid.data_ptr()
+            sdf_dict["_prepared_grid"] = grid                     # keep the exact tensor alive
         center = sdf_dict["center"].to(torch.float32).reshape(-1).contiguous()
         scale = sdf_dict["scale"].to(torch.float32).reshape(-1).contiguous()
         counts = torch.empty(N, dtype=torch.int32, device=self.device)

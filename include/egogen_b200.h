@@ -59,6 +59,13 @@ int eg_sdf_sample(const float* grid, int D0, int D1, int D2, const float* center
                   const float* scale_dev, const float* pts, int64_t P, float* val,
                   int32_t* base_idx, void* stream);
 
+/* Optional: register a conservative 8^3-cell coarse grid for `grid` (kept inside the library, keyed by the
+ * pointer). The fused penetration count (eg_lbs_forward_sdf / eg_env_step) then answers "sdf < 0 ?" for vertices
+ * whose whole cell is positive without touching the fine grid; results are identical to the full sample.
+ * Call again after mutating the grid in place; eg_sdf_release drops the entry. Synchronises `stream`. */
+int eg_sdf_prepare(const float* grid, int D0, int D1, int D2, void* stream);
+int eg_sdf_release(const float* grid);
+
 /* crowd_env_2f.py:170-176: per-body count of vertices with sdf < 0, skipping vertices whose
  * skip_mask byte is non-zero (feet). sdf_vals [N,V]; counts int32 [N]. */
 int eg_penetration_count(const float* sdf_vals, int N, int V, const uint8_t* skip_mask,

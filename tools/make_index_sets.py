@@ -19,6 +19,26 @@ for part in seg:
     if part in ("leftToeBase", "rightToeBase", "leftFoot", "rightFoot"):
         feet.extend(seg[part])
 out["feet_vids"] = sorted(set(int(v) for v in feet))
+# per-vertex body-part label (index into PARTS) - gives the surrogate SMPL-X the real id -> part coherence
+PARTS = ["hips", "leftUpLeg", "rightUpLeg", "spine", "leftLeg", "rightLeg", "spine1", "leftFoot", "rightFoot", "spine2",
+         "leftToeBase", "rightToeBase", "neck", "leftShoulder", "rightShoulder", "head", "leftArm", "rightArm",
+         "leftForeArm", "rightForeArm", "leftHand", "rightHand", "leftHandIndex1", "rightHandIndex1", "leftEye",
+         "rightEye"]
+nv = 1 + max(max(v) for v in seg.values())
+label = [15] * nv                      # default: head
+for pi, part in enumerate(PARTS):      # later parts override earlier ones where the segmentation overlaps
+    for v in seg[part]:
+        label[v] = pi
+out["parts"] = PARTS
+# run-length encoded labels keep the JSON small
+rle, prev, cnt = [], label[0], 0
+for l in label:
+    if l == prev:
+        cnt += 1
+    else:
+        rle.append([prev, cnt]); prev, cnt = l, 1
+rle.append([prev, cnt])
+out["part_rle"] = rle
 out["feet_markers"] = ["RHEE", "RTOE", "RRSTBEEF", "LHEE", "LTOE", "LRSTBEEF"]  # main_ppo.py:298
 dst = os.path.join(os.path.dirname(__file__), "..", "egogen_b200", "data", "index_sets.json")
 json.dump(out, open(dst, "w"))
