@@ -59,6 +59,8 @@ PROTOTYPES = {
     "eg_last_error": (C.c_char_p, []),
     "eg_launch_count": (_L, []),
     "eg_profile_enable": (_I, [_I]),
+    "eg_stage_profile_enable": (_I, [_I]),
+    "eg_stage_profile_read": (_I, [C.POINTER(C.c_double), _I]),
     "eg_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "eg_sdf_sample": (_I, [_P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P]),
     "eg_sdf_prepare": (_I, [_P, _I, _I, _I, _P]),
@@ -73,6 +75,8 @@ PROTOTYPES = {
     "eg_lbs_rest_pelvis": (_I, [_P, _P, _I, _I, _P, _P]),
     "eg_motion_create": (_I, [C.POINTER(EgMotionDims), _P, _I, _I, C.POINTER(_P)]),
     "eg_motion_destroy": (None, [_P]),
+    "eg_motion_refresh": (_I, [_P, _P]),
+    "eg_motion_set_fused": (_I, [_P, _I]),
     "eg_motion_sample_prior": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
     "eg_vposer_create": (_I, [_P, _I, _I, C.POINTER(_P)]),
     "eg_vposer_destroy": (None, [_P]),

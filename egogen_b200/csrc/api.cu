@@ -36,6 +36,43 @@ void prof_end(cudaStream_t st) {
 }
 }  // namespace eg
 
+// ---- env-step stage timing: events between the stages of eg_env_step when enabled ---------------
+namespace eg {
+static bool g_stage_on = false;
+static std::vector<cudaEvent_t> g_stage_ev;
+static std::vector<int> g_stage_id;
+void stage_mark(cudaStream_t st, int id) {
+  if (!g_stage_on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_stage_ev.push_back(e);
+  g_stage_id.push_back(id);
+}
+}  // namespace eg
+
+extern "C" int eg_stage_profile_enable(int on) {
+  for (auto e : eg::g_stage_ev) cudaEventDestroy(e);
+  eg::g_stage_ev.clear(); eg::g_stage_id.clear();
+  eg::g_stage_on = on != 0;
+  return EG_OK;
+}
+
+// ms_out[16]: time attributed to stage id k = sum over consecutive marks (prev -> mark with id k)
+extern "C" int eg_stage_profile_read(double* ms_out, int n) {
+  EG_REQUIRE(ms_out && n > 0, "bad arguments");
+  for (int i = 0; i < n; ++i) ms_out[i] = 0.0;
+  for (size_t i = 1; i < eg::g_stage_ev.size(); ++i) {
+    const int id = eg::g_stage_id[i];
+    if (id <= 0 || id >= n) continue;              // id 0 marks the start of a step
+    EG_CUDA_CHECK(cudaEventSynchronize(eg::g_stage_ev[i]));
+    float ms = 0.f;
+    EG_CUDA_CHECK(cudaEventElapsedTime(&ms, eg::g_stage_ev[i - 1], eg::g_stage_ev[i]));
+    ms_out[id] += ms;
+  }
+  return eg_stage_profile_enable(eg::g_stage_on ? 1 : 0);
+}
+
 extern "C" int eg_profile_enable(int on) {
   eg::g_prof_on = on != 0;
   eg::g_prof_used = 0;

@@ -52,6 +52,7 @@ inline int set_error(int code, const char* fmt, const char* a = "", const char* 
 struct ProfSlot { cudaEvent_t a, b; int64_t units; };
 void prof_begin(cudaStream_t st, int64_t units);
 void prof_end(cudaStream_t st);
+void stage_mark(cudaStream_t st, int id);   // env-step stage boundaries (eg_stage_profile_*)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -434,22 +434,30 @@ extern "C" int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int 
   EG_CUDA_CHECK(cudaSetDevice(h->device));
   EG_TRY(env_ws(h, E));
   cudaStream_t st = as_stream(stream);
+  stage_mark(st, 0);
   // b: C-VAE rollout + body regressor (:109)
   EG_TRY(eg_motion_sample_prior(h->motion, b->state, 2 * 402, 402, z, b->betas, E, h->Y, h->params, stream));
+  stage_mark(st, 1);
   // c: history frames + parameter blending (:116-120)
   EG_LAUNCH(env_prepare_params_kernel, E, 128, 0, st, b->seed, h->params, E);
+  stage_mark(st, 2);
   // d,e: SMPL-X on 20 bodies per env fused with the SDF penetration query (:133-177)
   EG_TRY(eg_lbs_forward_sdf(h->lbs, h->params, b->betas, E, E * NT, NT, b->R0, b->T0, h->grid, h->D0, h->D1,
                             h->D2, h->center, h->scale, h->skip, h->counts, h->joints, h->mproj, stream));
+  stage_mark(st, 3);
   // f: VPoser latent of every frame's body pose (:197-200)
   EG_TRY(eg_vposer_encode(h->vposer, h->params + 6, 93, E * NT, h->vp, stream));
+  stage_mark(st, 4);
   EG_TRY(eg_lbs_rest_pelvis(h->lbs, b->betas, E, E, h->prest, stream));
   StepArgs a{h->cfg, *b, h->Y, h->params, h->counts, h->joints, h->mproj, h->vp, h->prest};
   EG_LAUNCH(env_reward_recanon_kernel, E, 256, 0, st, a);
+  stage_mark(st, 5);
   // i: all joints of the re-canonicalised seed for ego-sensing (:290-296)
   EG_TRY(eg_lbs_forward(h->lbs, b->seed, b->betas, E, E * 2, nullptr, h->joints2, nullptr, stream));
+  stage_mark(st, 6);
   EG_LAUNCH(env_egosensing_kernel, E, 64, 0, st, h->joints2, b->R0, b->T0, nullptr, nullptr, h->segs, h->S,
             (double)h->cfg.ray_len, b->ego);
+  stage_mark(st, 7);
   return EG_OK;
 }
 

@@ -238,6 +238,281 @@ regressor_tail_kernel(const float* __restrict__ xb_cont, int M, int frames, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused row-tile kernels for the two long sequential chains of the motion model. Weights are read from
+// TRANSPOSED, 4-padded copies ([K][N4]) so a warp's float4 loads of one k-row are contiguous.
+// ------------------------------------------------------------------------------------------
+__global__ void transpose_pad_kernel(const float* __restrict__ src, int ld_src, int N, int K, float* __restrict__ dst,
+                                     int ld_dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // dst[k][n] = src[n][k]
+  if (i >= K * ld_dst) return;
+  const int k = i / ld_dst, n = i % ld_dst;
+  dst[i] = n < N ? src[(int64_t)n * ld_src + k] : 0.0f;
+}
+
+// partial[ks][r][n] = sum over this thread's k-slice of x[r][k] * Wt[k][n]; threads = TN (float4 columns) x KS
+template <int R>
+__device__ __forceinline__ void tile_gemm_splitk(const float* __restrict__ Wt, int ldw, int K, int N,
+                                                 const float* xs, int ldx, float* part, int ldp, int tid,
+                                                 int nthreads, int& KS) {
+  const int TN = (N + 3) >> 2;
+  KS = nthreads / TN;
+  if (KS > 8) KS = 8;
+  if (KS < 1) KS = 1;
+  if (tid < TN * KS) {
+    const int n4 = tid % TN, ks = tid / TN;
+    const int Kc = (K + KS - 1) / KS;
+    const int k0 = ks * Kc, k1 = min(K, k0 + Kc);
+    float acc[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+    const float4* wp = reinterpret_cast<const float4*>(Wt + 4 * n4);
+    const int ldw4 = ldw >> 2;
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+      const float4 w0 = __ldg(wp + (int64_t)(k + 0) * ldw4), w1 = __ldg(wp + (int64_t)(k + 1) * ldw4);
+      const float4 w2 = __ldg(wp + (int64_t)(k + 2) * ldw4), w3 = __ldg(wp + (int64_t)(k + 3) * ldw4);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float x0 = xs[r * ldx + k], x1 = xs[r * ldx + k + 1], x2 = xs[r * ldx + k + 2], x3 = xs[r * ldx + k + 3];
+        acc[r][0] += x0 * w0.x; acc[r][1] += x0 * w0.y; acc[r][2] += x0 * w0.z; acc[r][3] += x0 * w0.w;
+        acc[r][0] += x1 * w1.x; acc[r][1] += x1 * w1.y; acc[r][2] += x1 * w1.z; acc[r][3] += x1 * w1.w;
+        acc[r][0] += x2 * w2.x; acc[r][1] += x2 * w2.y; acc[r][2] += x2 * w2.z; acc[r][3] += x2 * w2.w;
+        acc[r][0] += x3 * w3.x; acc[r][1] += x3 * w3.y; acc[r][2] += x3 * w3.z; acc[r][3] += x3 * w3.w;
+      }
+    }
+    for (; k < k1; ++k) {
+      const float4 w0 = __ldg(wp + (int64_t)k * ldw4);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float x0 = xs[r * ldx + k];
+        acc[r][0] += x0 * w0.x; acc[r][1] += x0 * w0.y; acc[r][2] += x0 * w0.z; acc[r][3] += x0 * w0.w;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      *reinterpret_cast<float4*>(part + (ks * R + r) * ldp + 4 * n4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  }
+}
+
+struct DecodeW {            // transposed weights of the 18-step decode loop
+  const float *WyT, *WhhT, *W1T, *W2T, *WoT;      // [201][768] [256][768] [256][512] [512][256] [256][204]
+  const float *bhh, *b1, *b2, *bo;
+};
+
+// 18 GRUCell + MLP steps for DR rows per CTA (models_GAMMA_primitive.py:91-99). h0 = drnn_mlp(hx) and the
+// step-invariant input term c = [hx,z] W_ih[:, :384]^T + b_ih are computed beforehand by the layer kernels.
+constexpr int DR = 2;
+constexpr int DEC_THREADS = 256;
+__global__ void __launch_bounds__(DEC_THREADS)
+fused_decode_kernel(DecodeW w, const float* __restrict__ c_in, const float* __restrict__ h_in, float* __restrict__ Y,
+                    int B, int D, int H, int Hm) {
+  extern __shared__ __align__(16) float sm[];
+  const int H3 = 3 * H, D4 = (D + 3) & ~3;
+  float* cs = sm;                       // [DR][H3]
+  float* hs = cs + DR * H3;             // [DR][H]
+  float* ys = hs + DR * H;              // [DR][D4]
+  float* t1 = ys + DR * D4;             // [DR][Hm]
+  float* t2 = t1 + DR * Hm;             // [DR][H]
+  float* part = t2 + DR * H;            // [8][DR][H3] split-k partials (gi)
+  float* part2 = part + 8 * DR * H3;    // [8][DR][H3] (gh)
+  const int tid = threadIdx.x, b0 = blockIdx.x * DR;
+  const int ldY = 20 * D;
+  for (int i = tid; i < DR * H3; i += DEC_THREADS) { const int r = i / H3, b = min(b0 + r, B - 1); cs[i] = c_in[(int64_t)b * H3 + i % H3]; }
+  for (int i = tid; i < DR * H; i += DEC_THREADS) { const int r = i / H, b = min(b0 + r, B - 1); hs[i] = h_in[(int64_t)b * H + i % H]; }
+  for (int i = tid; i < DR * D4; i += DEC_THREADS) {
+    const int r = i / D4, d = i % D4, b = min(b0 + r, B - 1);
+    ys[i] = d < D ? Y[(int64_t)b * ldY + D + d] : 0.0f;          // history frame 1
+  }
+  __syncthreads();
+  for (int step = 0; step < 18; ++step) {
+    int KS1, KS2;
+    tile_gemm_splitk<DR>(w.WyT, H3, D, H3, ys, D4, part, H3, tid, DEC_THREADS, KS1);
+    tile_gemm_splitk<DR>(w.WhhT, H3, H, H3, hs, H, part2, H3, tid, DEC_THREADS, KS2);
+    __syncthreads();
+    // GRUCell gates (PyTorch order r,z,n)
+    for (int i = tid; i < DR * H; i += DEC_THREADS) {
+      const int r = i / H, j = i % H;
+      float gi[3], gh[3];
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        float a = cs[r * H3 + g * H + j], bq = __ldg(w.bhh + g * H + j);
+        for (int ks = 0; ks < KS1; ++ks) a += part[(ks * DR + r) * H3 + g * H + j];
+        for (int ks = 0; ks < KS2; ++ks) bq += part2[(ks * DR + r) * H3 + g * H + j];
+        gi[g] = a; gh[g] = bq;
+      }
+      const float rr = 1.0f / (1.0f + expf(-(gi[0] + gh[0])));
+      const float zz = 1.0f / (1.0f + expf(-(gi[1] + gh[1])));
+      const float nn = tanhf(gi[2] + rr * gh[2]);
+      t2[i] = (1.0f - zz) * nn + zz * hs[i];                  // new h, staged
+    }
+    __syncthreads();
+    for (int i = tid; i < DR * H; i += DEC_THREADS) hs[i] = t2[i];
+    __syncthreads();
+    int KS;
+    tile_gemm_splitk<DR>(w.W1T, Hm, H, Hm, hs, H, part, Hm, tid, DEC_THREADS, KS);
+    __syncthreads();
+    for (int i = tid; i < DR * Hm; i += DEC_THREADS) {
+      const int r = i / Hm, j = i % Hm;
+      float a = __ldg(w.b1 + j);
+      for (int ks = 0; ks < KS; ++ks) a += part[(ks * DR + r) * Hm + j];
+      t1[i] = tanhf(a);
+    }
+    __syncthreads();
+    tile_gemm_splitk<DR>(w.W2T, H, Hm, H, t1, Hm, part, H, tid, DEC_THREADS, KS);
+    __syncthreads();
+    for (int i = tid; i < DR * H; i += DEC_THREADS) {
+      const int r = i / H, j = i % H;
+      float a = __ldg(w.b2 + j);
+      for (int ks = 0; ks < KS; ++ks) a += part[(ks * DR + r) * H + j];
+      t2[i] = tanhf(a);
+    }
+    __syncthreads();
+    tile_gemm_splitk<DR>(w.WoT, D4, H, D, t2, H, part, D4, tid, DEC_THREADS, KS);
+    __syncthreads();
+    for (int i = tid; i < DR * D; i += DEC_THREADS) {
+      const int r = i / D, j = i % D;
+      float a = __ldg(w.bo + j);
+      for (int ks = 0; ks < KS; ++ks) a += part[(ks * DR + r) * D4 + j];
+      a += ys[r * D4 + j];                                      // residual: y_i = d_out(..) + y_{i-1}
+      ys[r * D4 + j] = a;
+      if (b0 + r < B) Y[(int64_t)(b0 + r) * ldY + (2 + step) * D + j] = a;
+    }
+    __syncthreads();
+  }
+}
+
+struct RegW {               // transposed regressor weights
+  const float *WaT, *WbT, *WcT;     // in_fc split: markers [201][128], xb [159][128], betas [10][128]
+  const float* b_in;
+  const float* blkT;                // n_blocks x 2 x [128][128]
+  const float* blk_b;               // n_blocks x 2 x [128]
+  const float *WoT, *b_out;         // [128][160], [159]
+};
+
+// y[r][n] for a warp's RW rows: lanes own float4 column groups (n4 = lane, lane+32, ...)
+template <int RW>
+__device__ __forceinline__ void warp_rows_gemm(const float* __restrict__ Wt, int ldw, int K, int n4,
+                                               const float* xs, int ldx, float acc[RW][4]) {
+  const float4* wp = reinterpret_cast<const float4*>(Wt + 4 * n4);
+  const int ldw4 = ldw >> 2;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 wv = __ldg(wp + (int64_t)k * ldw4);
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      const float x = xs[r * ldx + k];
+      acc[r][0] += x * wv.x; acc[r][1] += x * wv.y; acc[r][2] += x * wv.z; acc[r][3] += x * wv.w;
+    }
+  }
+}
+
+// Whole MoshRegressor._forward (3 recurrences x (in_fc + 10 residual blocks + out_fc)) for RR rows per CTA,
+// activations resident in shared memory (models_GAMMA_primitive.py:222-259, ResNetBlock :160-175).
+constexpr int RR = 36, RWARPS = 9, RW = 4;
+__global__ void __launch_bounds__(RWARPS * 32)
+fused_regressor_kernel(RegW w, const float* __restrict__ Yin, const float* __restrict__ betas, int betas_div, int M,
+                       int n_blocks, int n_recur, float* __restrict__ xb_out) {
+  constexpr int HR = 128, D = 201, BD = 159, BD4 = 160, LDX = 204;
+  extern __shared__ __align__(16) float sm[];
+  float* xr = sm;                   // [RR][LDX] markers
+  float* be = xr + RR * LDX;        // [RR][12]
+  float* base = be + RR * 12;       // [RR][HR]
+  float* h = base + RR * HR;        // [RR][HR]
+  float* t = h + RR * HR;           // [RR][HR]
+  float* xb = t + RR * HR;          // [RR][BD4]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * RR;
+  for (int i = tid; i < RR * LDX; i += RWARPS * 32) {
+    const int r = i / LDX, d = i % LDX, m = min(m0 + r, M - 1);
+    xr[i] = d < D ? Yin[(int64_t)m * D + d] : 0.0f;
+  }
+  for (int i = tid; i < RR * 12; i += RWARPS * 32) {
+    const int r = i / 12, d = i % 12, m = min(m0 + r, M - 1);
+    be[i] = d < 10 ? betas[(int64_t)(m / betas_div) * 10 + d] : 0.0f;
+  }
+  for (int i = tid; i < RR * BD4; i += RWARPS * 32) xb[i] = 0.0f;
+  __syncthreads();
+  const int r0 = warp * RW;
+  // base = markers Wa^T + betas Wc^T + b_in   (constant over the recurrences)
+  {
+    float acc[RW][4];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+    warp_rows_gemm<RW>(w.WaT, HR, D, lane, xr + r0 * LDX, LDX, acc);
+    warp_rows_gemm<RW>(w.WcT, HR, 10, lane, be + r0 * 12, 12, acc);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(w.b_in) + lane);
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+      *reinterpret_cast<float4*>(base + (r0 + r) * HR + 4 * lane) =
+          make_float4(acc[r][0] + bb.x, acc[r][1] + bb.y, acc[r][2] + bb.z, acc[r][3] + bb.w);
+  }
+  __syncwarp();     // every warp only ever touches its own RW rows: no block-level barriers below
+  for (int rec = 0; rec < n_recur; ++rec) {
+    {   // h = base (+ xb Wb^T)
+      float acc[RW][4];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+      if (rec > 0) warp_rows_gemm<RW>(w.WbT, HR, BD, lane, xb + r0 * BD4, BD4, acc);
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        const float4 bv = *reinterpret_cast<const float4*>(base + (r0 + r) * HR + 4 * lane);
+        *reinterpret_cast<float4*>(h + (r0 + r) * HR + 4 * lane) =
+            make_float4(acc[r][0] + bv.x, acc[r][1] + bv.y, acc[r][2] + bv.z, acc[r][3] + bv.w);
+      }
+      __syncwarp();
+    }
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      const float* W0 = w.blkT + (int64_t)(blk * 2) * HR * HR;
+      const float* W1 = W0 + HR * HR;
+      const float* B0 = w.blk_b + (blk * 2) * HR;
+      float acc[RW][4];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+      warp_rows_gemm<RW>(W0, HR, HR, lane, h + r0 * HR, HR, acc);
+      float4 bb = __ldg(reinterpret_cast<const float4*>(B0) + lane);
+#pragma unroll
+      for (int r = 0; r < RW; ++r)
+        *reinterpret_cast<float4*>(t + (r0 + r) * HR + 4 * lane) =
+            make_float4(fmaxf(acc[r][0] + bb.x, 0.f), fmaxf(acc[r][1] + bb.y, 0.f), fmaxf(acc[r][2] + bb.z, 0.f),
+                        fmaxf(acc[r][3] + bb.w, 0.f));
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+      warp_rows_gemm<RW>(W1, HR, HR, lane, t + r0 * HR, HR, acc);
+      bb = __ldg(reinterpret_cast<const float4*>(B0 + HR) + lane);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        float4* hp = reinterpret_cast<float4*>(h + (r0 + r) * HR + 4 * lane);
+        const float4 hv = *hp;
+        *hp = make_float4(fmaxf(acc[r][0] + bb.x, 0.f) + hv.x, fmaxf(acc[r][1] + bb.y, 0.f) + hv.y,
+                          fmaxf(acc[r][2] + bb.z, 0.f) + hv.z, fmaxf(acc[r][3] + bb.w, 0.f) + hv.w);
+      }
+      __syncwarp();
+    }
+    // xb += h Wout^T + b_out  (159 outputs = 40 float4 groups: lanes 0..31 then 0..7)
+    for (int n4 = lane; n4 < BD4 / 4; n4 += 32) {
+      float acc[RW][4];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+      warp_rows_gemm<RW>(w.WoT, BD4, HR, n4, h + r0 * HR, HR, acc);
+#pragma unroll
+      for (int r = 0; r < RW; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = 4 * n4 + j;
+          if (n < BD) xb[(r0 + r) * BD4 + n] += acc[r][j] + __ldg(w.b_out + n);
+        }
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < RW * BD; i += 32) {
+    const int r = r0 + i / BD, n = i % BD;
+    if (m0 + r < M) xb_out[(int64_t)(m0 + r) * BD + n] = xb[r * BD4 + n];
+  }
+}
+
 static inline int ew_grid(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, kNumSMs * 8); }
 
 }  // namespace eg
@@ -254,6 +529,10 @@ struct EgMotion {
   int cap_B = 0;
   float *gi = nullptr, *gh = nullptr, *h = nullptr, *hx = nullptr, *c = nullptr, *t1 = nullptr, *t2 = nullptr;
   float *rh = nullptr, *rbase = nullptr, *rt = nullptr, *xbc = nullptr;
+  float* wt = nullptr;        // transposed, 4-padded weight copies for the fused kernels
+  DecodeW dw{};
+  RegW rw{};
+  int fused = 1;
 };
 
 namespace {
@@ -290,6 +569,57 @@ int motion_ws(EgMotion* h, int B) {
 }
 }  // namespace
 
+static int motion_build_transposed(EgMotion* h, cudaStream_t st) {
+  const EgMotionDims& d = h->d;
+  const int D = d.in_dim, H = d.h_dim, Z = d.z_dim, Hm = d.mlp_dim, H3 = 3 * H, D4 = (D + 3) & ~3;
+  const int Hr = d.reg_h, BD = d.body_dim, BD4 = (BD + 3) & ~3, Kr = D + BD + 10, nb = d.reg_blocks;
+  const float* const* w = h->w.data();
+  const size_t n_dec = (size_t)D * H3 + (size_t)H * H3 + (size_t)H * Hm + (size_t)Hm * H + (size_t)H * D4;
+  const size_t n_reg = (size_t)D * Hr + (size_t)BD * Hr + (size_t)10 * Hr + (size_t)nb * 2 * Hr * Hr + (size_t)nb * 2 * Hr +
+                       (size_t)Hr * BD4;
+  if (!h->wt) EG_CUDA_CHECK(cudaMalloc((void**)&h->wt, (n_dec + n_reg) * sizeof(float)));
+  float* p = h->wt;
+  auto tr = [&](const float* src, int ld_src, int N, int K, int ld_dst) -> const float* {
+    float* dst = p;
+    const int total = K * ld_dst;
+    transpose_pad_kernel<<<(total + 255) / 256, 256, 0, st>>>(src, ld_src, N, K, dst, ld_dst);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    p += total;
+    return dst;
+  };
+  const int Kin = H + Z + D;
+  h->dw.WyT = tr(w[P_DRNN_WIH] + H + Z, Kin, H3, D, H3);
+  h->dw.WhhT = tr(w[P_DRNN_WHH], H, H3, H, H3);
+  h->dw.W1T = tr(w[P_DMLP_W0], H, Hm, H, Hm);
+  h->dw.W2T = tr(w[P_DMLP_W1], Hm, H, Hm, H);
+  h->dw.WoT = tr(w[P_DOUT_W], H, D, H, D4);
+  h->dw.bhh = w[P_DRNN_BHH]; h->dw.b1 = w[P_DMLP_B0]; h->dw.b2 = w[P_DMLP_B1]; h->dw.bo = w[P_DOUT_B];
+  const float* Win = w[R_IN_W];
+  h->rw.WaT = tr(Win, Kr, Hr, D, Hr);
+  h->rw.WbT = tr(Win + D, Kr, Hr, BD, Hr);
+  h->rw.WcT = tr(Win + D + BD, Kr, Hr, 10, Hr);
+  h->rw.b_in = w[R_IN_B];
+  const float* const* wb = w + R_BLOCKS;
+  h->rw.blkT = p;
+  for (int k = 0; k < nb; ++k) { tr(wb[k * 4], Hr, Hr, Hr, Hr); tr(wb[k * 4 + 2], Hr, Hr, Hr, Hr); }
+  float* bb = p;
+  for (int k = 0; k < nb; ++k) {
+    EG_CUDA_CHECK(cudaMemcpyAsync(p, wb[k * 4 + 1], Hr * sizeof(float), cudaMemcpyDeviceToDevice, st)); p += Hr;
+    EG_CUDA_CHECK(cudaMemcpyAsync(p, wb[k * 4 + 3], Hr * sizeof(float), cudaMemcpyDeviceToDevice, st)); p += Hr;
+  }
+  h->rw.blk_b = bb;
+  h->rw.WoT = tr(wb[nb * 4], Hr, BD, Hr, BD4);
+  h->rw.b_out = wb[nb * 4 + 1];
+  EG_CUDA_CHECK(cudaGetLastError());
+  return EG_OK;
+}
+
+static size_t decode_smem(const EgMotionDims& d) {
+  const int H = d.h_dim, H3 = 3 * H, D4 = (d.in_dim + 3) & ~3, Hm = d.mlp_dim;
+  return sizeof(float) * ((size_t)DR * (H3 + H + D4 + Hm + H) + (size_t)2 * 8 * DR * H3);
+}
+constexpr size_t kRegSmem = sizeof(float) * RR * (204 + 12 + 128 * 3 + 160);
+
 extern "C" int eg_motion_create(const EgMotionDims* dims, const void* const* weights_host, int n_weights,
                                 int device, EgMotion** out) {
   EG_REQUIRE(dims && weights_host && out, "null pointer");
@@ -300,13 +630,37 @@ extern "C" int eg_motion_create(const EgMotionDims* dims, const void* const* wei
   EgMotion* h = new EgMotion();
   h->device = device; h->d = *dims;
   h->w.assign((const float* const*)weights_host, (const float* const*)weights_host + n_weights);
+  EG_CUDA_CHECK(cudaSetDevice(device));
+  h->fused = (dims->reg_h == 128 && dims->mlp_dim <= 3 * dims->h_dim) ? 1 : 0;   // fused kernels' static assumptions
+  if (h->fused) {
+    EG_CUDA_CHECK(cudaFuncSetAttribute(fused_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem(*dims)));
+    EG_CUDA_CHECK(cudaFuncSetAttribute(fused_regressor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRegSmem));
+    int rc = motion_build_transposed(h, nullptr);
+    if (rc) { delete h; return rc; }
+    EG_CUDA_CHECK(cudaDeviceSynchronize());
+  }
   *out = h;
+  return EG_OK;
+}
+
+extern "C" int eg_motion_refresh(EgMotion* h, void* stream) {
+  EG_REQUIRE(h != nullptr, "null handle");
+  if (!h->fused) return EG_OK;
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  return motion_build_transposed(h, as_stream(stream));
+}
+
+extern "C" int eg_motion_set_fused(EgMotion* h, int fused) {
+  EG_REQUIRE(h != nullptr, "null handle");
+  EG_REQUIRE(!fused || h->wt != nullptr, "fused kernels unavailable for these dimensions");
+  h->fused = fused ? 1 : 0;
   return EG_OK;
 }
 
 extern "C" void eg_motion_destroy(EgMotion* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  cudaFree(h->wt);
   float* bufs[] = {h->gi, h->gh, h->h, h->hx, h->c, h->t1, h->t2, h->rh, h->rbase, h->rt, h->xbc};
   for (auto p : bufs) cudaFree(p);
   delete h;
@@ -342,6 +696,9 @@ extern "C" int eg_motion_sample_prior(EgMotion* hd, const float* X, int ldx_env,
   const int Kin = H + Z + D;
   EG_TRY(linear(st, hd->hx, H, B, w[P_DRNN_WIH], Kin, w[P_DRNN_BIH], H, H3, hd->c, H3));
   EG_TRY(linear(st, z, Z, B, w[P_DRNN_WIH] + H, Kin, nullptr, Z, H3, hd->c, H3, ACT_NONE, 0.f, nullptr, 0, 1));
+  if (hd->fused) {
+    EG_LAUNCH(fused_decode_kernel, (B + DR - 1) / DR, DEC_THREADS, decode_smem(d), st, hd->dw, hd->c, hd->h, Y, B, D, H, Hm);
+  } else
   for (int i = 0; i < 18; ++i) {
     const float* yp = Y + (1 + i) * D;     // previous frame (history frame 1 for i == 0)
     float* yo = Y + (2 + i) * D;
@@ -354,6 +711,12 @@ extern "C" int eg_motion_sample_prior(EgMotion* hd, const float* X, int ldx_env,
   }
   // ---- regressor over all B*20 marker frames (frames 0,1 are computed and discarded) ----
   const int M = B * 20, Hr = d.reg_h, BD = d.body_dim, Kr = D + BD + 10;
+  if (hd->fused) {
+    EG_LAUNCH(fused_regressor_kernel, (M + RR - 1) / RR, RWARPS * 32, kRegSmem, st, hd->rw, Y, betas, 20, M, d.reg_blocks,
+              d.reg_recur, hd->xbc);
+    EG_LAUNCH(regressor_tail_kernel, (M * 32 + 127) / 128, 128, 0, st, hd->xbc, M, 20, 2, Yb);
+    return EG_OK;
+  }
   const float* Win = w[R_IN_W];
   EG_TRY(linear(st, Y, D, M, Win, Kr, w[R_IN_B], D, Hr, hd->rbase, Hr));
   EG_TRY(linear(st, betas, 10, M, Win + D + BD, Kr, nullptr, 10, Hr, hd->rbase, Hr, ACT_NONE, 0.f, nullptr, 0, 1, 20));

@@ -123,6 +123,20 @@ class GAMMAPrimitiveCombo(nn.Module):
             self._h, self._wkeep = h, key
         return self._h
 
+    def refresh_weights(self):
+        """Re-derive the library's transposed weight copies after an in-place weight change."""
+        if self._h is not None:
+            _lib.check(_lib.lib().eg_motion_refresh(self._h, None))
+            torch.cuda.synchronize()
+
+    def set_fused(self, fused: bool):
+        _lib.check(_lib.lib().eg_motion_set_fused(self.handle(), int(bool(fused))))
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.refresh_weights()
+        return r
+
     def release(self):
         if getattr(self, "_h", None) is not None:
             _lib.lib().eg_motion_destroy(self._h)

@@ -46,6 +46,10 @@ int64_t eg_launch_count(void);
  * number of timed launches, and clears the counters. */
 int eg_profile_enable(int on);
 int eg_profile_read(double* total_ms, int64_t* launches, int64_t* units /* bodies processed */);
+/* per-stage device time of eg_env_step (ids: 1 C-VAE decode + regressor, 2 param blend, 3 fused LBS+SDF,
+ * 4 VPoser, 5 rewards + re-canonicalisation, 6 seed-joint LBS, 7 ego-sensing); ms_out[n >= 8] */
+int eg_stage_profile_enable(int on);
+int eg_stage_profile_read(double* ms_out, int n);
 
 /* ------------------------------------------------------------------------------------------
  * calc_sdf  - replaces motion/crowd_ppo/utils.py:54-84 (F.grid_sample 5-D trilinear,
@@ -163,6 +167,10 @@ typedef struct EgMotionDims {
 int eg_motion_create(const EgMotionDims* dims, const void* const* weights_host, int n_weights,
                      int device, EgMotion** out);
 void eg_motion_destroy(EgMotion* h);
+/* the fused decode / regressor kernels read transposed copies of the weights: call after changing weights in place */
+int eg_motion_refresh(EgMotion* h, void* stream);
+/* 1 (default): fused row-tile kernels for the 18-step decode loop and the 3x22-layer regressor; 0: layer-by-layer */
+int eg_motion_set_fused(EgMotion* h, int fused);
 /* X: marker history, frame t of env b at X + b*ldx_env + t*ldx_frame (201 floats); z [B,128];
  * betas [B,10]. Y [B,20,201] receives the 2 history frames + 18 predicted frames;
  * Yb [B,20,93]: frames 2..19 are written (axis-angle body params), frames 0..1 are left untouched. */

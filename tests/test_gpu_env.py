@@ -64,6 +64,24 @@ def test_sample_prior_matches_oracle(dev, world):
     assert torch.allclose(Yb.cpu()[..., 3:69], Ybo[..., 3:69], atol=2e-4, rtol=1e-3)
 
 
+def test_fused_motion_kernels_match_layerwise(dev, world):
+    """The fused decode / regressor kernels against the layer-by-layer path (same weights, same inputs), at a
+    batch that spans several row tiles and is not a multiple of the tile sizes."""
+    g = torch.Generator().manual_seed(3)
+    b = 37
+    X = (torch.randn(2, b, 201, generator=g) * 0.3).to(dev)
+    z = torch.randn(b, 128, generator=g).to(dev)
+    betas = (torch.randn(b, 10, generator=g) * 0.5).to(dev)
+    m = world["genop"].model
+    m.set_fused(True)
+    Y1, Yb1 = m.sample_prior(X, betas, z)
+    m.set_fused(False)
+    Y0, Yb0 = m.sample_prior(X, betas, z)
+    m.set_fused(True)
+    assert torch.allclose(Y1, Y0, atol=2e-5, rtol=1e-4)
+    assert torch.allclose(Yb1, Yb0, atol=2e-4, rtol=1e-3)
+
+
 def test_vposer_matches_oracle(dev, world):
     g = torch.Generator().manual_seed(2)
     x = torch.randn(40, 63, generator=g) * 0.4
