@@ -164,7 +164,6 @@ def run_ours(args):
     tot_ms, n_l, n_units = C.c_double(), C.c_int64(), C.c_int64()
     _lib.check(lib.eg_profile_read(C.byref(tot_ms), C.byref(n_l), C.byref(n_units)))
     lib.eg_profile_enable(0)
-    clocks = sampler.stop() if sampler else None
     # the flush kernel is torch's, not ours; do not count it. launches counts only this library's kernels.
     total_ms = float(sum(ms))
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -184,6 +183,7 @@ def run_ours(args):
     if world_size > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = STEP_PER_COLLECT * world_size * args.steps / (float(t2.item()) / 1e3)
+    clocks = sampler.stop() if sampler else None
     e2e = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": col2.h2d_bytes // args.steps,
            "d2h_bytes_per_step": (col2.d2h_bytes + 5 * 8 * 4) // args.steps}
 
@@ -195,14 +195,23 @@ def run_ours(args):
     peak, how = peaks()
     k_ms = tot_ms.value / max(n_l.value, 1)
     bodies_per_launch = n_units.value / max(n_l.value, 1)
-    achieved = bodies_per_launch * B_BODY / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": how, "kernel": "lbs_verts_kernel<FUSE_SDF>",
+    hbm_achieved = bodies_per_launch * B_BODY / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    # the fused LBS kernel is a TF32 tensor-core contraction [bodies,576] x [576, 3*10496] + skinning/SDF epilogue
+    tc_flops = bodies_per_launch * 2.0 * 576 * 3 * 10496
+    tf_achieved = tc_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf_peak = float(pk.get("bf16_tflops", 1590.0)) / 2.0
+    roofline = {"bound": "tensor", "achieved": tf_achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf_achieved / tf_peak,
+                "traffic": None, "peak_source": how + " bf16 cuBLAS burst / 2 (TF32 runs at half the bf16 rate)",
+                "kernel": "lbs_verts_tc_kernel<FUSE_SDF> (tcgen05 kind::tf32)",
                 "avg_launch_ms": k_ms, "bodies_per_launch": bodies_per_launch, "launches_timed": n_l.value,
-                "frac_of_nominal_8TBs": achieved / 8000.0,
                 "kernel_share_of_step": tot_ms.value / float(sum(ms)),
-                "fp32_tflops_reference_flops": bodies_per_launch * FLOP_BODY / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
-                "note": "LBS is fp32-FMA bound (385 FLOP/B, SURVEY 8d); algorithmic bytes = bodies x 127636 B"}
+                "flops_per_body": 2.0 * 576 * 3 * 10496,
+                "hbm_contract": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+                                 "frac_of_nominal_8TBs": hbm_achieved / 8000.0,
+                                 "note": "SURVEY 8(d) contract figure: bodies x 127636 B (what an unfused LBS must move); "
+                                         "the fused kernel itself writes only the per-body counts"},
+                "reference_dense_tflops": bodies_per_launch * FLOP_BODY / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0}
     # ---- CPU baseline: the oracle port on a bounded sample, host cores of this box --------------
     from oracle import harness
     cores = os.cpu_count() or 1
@@ -222,13 +231,75 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_ego_depth(args):
+    """BASELINE config 5: ego-depth ray-march sweep, 8192 agents x 64x64 rays per GPU against a resident 256^3 SDF
+    (agents sharded over ranks, grid replicated, no collective). Secondary workload: prints its own JSON line."""
+    import torch
+    import torch.distributed as dist
+    from egogen_b200 import _lib, assets, ego_depth
+    world_size = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    A, H, W = 8192, 64, 64
+    scene = assets.make_box_scene(rank, n_boxes=4)
+    sdf = {k: v.to(dev) for k, v in assets.rasterize_scene_sdf(scene, D=256, device=str(dev)).items()}
+    g = torch.Generator(device=dev); g.manual_seed(rank)
+    eye = torch.cat([(torch.rand(A, 2, device=dev, generator=g) * 2 - 1) * 3.0, torch.full((A, 1), 1.6, device=dev)], 1)
+    yaw = torch.rand(A, device=dev, generator=g) * 6.2831853
+    fwd = torch.stack([yaw.cos(), yaw.sin(), torch.full((A,), -0.05, device=dev)], 1)
+    fwd = fwd / fwd.norm(dim=1, keepdim=True)
+    right = torch.cross(fwd, torch.tensor([0.0, 0.0, 1.0], device=dev).expand(A, 3), dim=1)
+    right = right / right.norm(dim=1, keepdim=True)
+    cam = torch.cat([eye, right, torch.cross(right, fwd, dim=1), fwd], 1).contiguous()
+    fx = fy = 64 * (200.0 / 320.0)
+    for _ in range(max(args.warmup, 3)):
+        ego_depth(sdf, cam, H, W, fx, fy)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); depth, steps = ego_depth(sdf, cam, H, W, fx, fy, return_steps=True); e1.record()
+        torch.cuda.synchronize(dev)
+        ms.append(e0.elapsed_time(e1))
+    t = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mean_steps = float(steps.float().mean().item()) + 1.0       # samples per ray (the terminating sample included)
+    if rank == 0:
+        peak, how = peaks()
+        rays = A * H * W * world_size * args.steps
+        secs = float(t.item()) / 1e3
+        gathered = A * H * W * mean_steps * 32.0 / (sum(ms) / args.steps / 1e3) / 1e9     # bytes gathered / s, this rank
+        print(json.dumps({"metric": "ego-depth rays/sec", "value": rays / secs, "unit": "rays/s", "n_gpus": world_size,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(t.item()) / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "ego-depth sweep: 8192 agents x 64x64 rays per GPU, 256^3 SDF, <=64 sphere-trace steps, 7 m range"},
+                          "roofline": {"bound": "hbm", "achieved": gathered, "peak": peak, "unit": "GB/s", "frac": gathered / peak,
+                                       "traffic": None, "peak_source": how, "kernel": "ego_depth_kernel",
+                                       "mean_samples_per_ray": mean_steps,
+                                       "note": "achieved = rays x samples x 32 B of corner gathers (L2-served; grid 67 MB resident)"},
+                          "gpu_launches": args.steps}))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "ego_depth"],
+                    help="ppo = headline (BASELINE config 2); ego_depth = secondary config-5 sweep")
     args = ap.parse_args()
+    if args.workload == "ego_depth" and args.impl == "ours":
+        return run_ego_depth(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -716,9 +716,10 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
                        float* verts, float* joints, float* markers, bool fuse, int frames_per_env,
                        const float* R0, const float* T0, SdfGrid sdf, const uint8_t* skip,
                        int32_t* counts, cudaStream_t st) {
-  EG_REQUIRE(h && xb && betas, "null pointer");
+  EG_REQUIRE(h != nullptr, "null handle");
   EG_REQUIRE(N >= 0, "negative N");
   if (N == 0) return EG_OK;
+  EG_REQUIRE(xb && betas, "null pointer");
   EG_REQUIRE(betas_rows >= 1 && N % betas_rows == 0, "betas_rows must divide N (row = body / (N / betas_rows))");
   const int betas_div = N / betas_rows;
   EG_CUDA_CHECK(cudaSetDevice(h->device));

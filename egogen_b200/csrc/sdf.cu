@@ -161,8 +161,9 @@ extern "C" int eg_sdf_sample(const float* grid, int D0, int D1, int D2, const fl
 
 extern "C" int eg_penetration_count(const float* sdf_vals, int N, int V, const uint8_t* skip_mask,
                                     int32_t* counts, void* stream) {
-  EG_REQUIRE(sdf_vals && counts && N >= 0 && V > 0, "bad arguments");
+  EG_REQUIRE(N >= 0 && V > 0, "bad sizes");
   if (N == 0) return EG_OK;
+  EG_REQUIRE(sdf_vals && counts, "null pointer");
   EG_LAUNCH(penetration_count_kernel, N, 256, 0, as_stream(stream), sdf_vals, V, skip_mask, counts);
   return EG_OK;
 }
@@ -171,9 +172,9 @@ extern "C" int eg_ego_depth(const float* grid, int D0, int D1, int D2, const flo
                             const float* scale_dev, const float* cam, int A, int H, int W, float fx,
                             float fy, float max_range, int max_steps, float hit_eps, float* depth,
                             int32_t* steps_out, void* stream) {
-  EG_REQUIRE(grid && center_dev && scale_dev && cam && depth, "null pointer");
   EG_REQUIRE(A >= 0 && H > 0 && W > 0 && max_steps > 0, "bad sizes");
-  if (A == 0) return EG_OK;
+  if (A == 0) return EG_OK;       // empty batch (torch hands out NULL data pointers for empty tensors)
+  EG_REQUIRE(grid && center_dev && scale_dev && cam && depth, "null pointer");
   SdfGrid g{grid, D0, D1, D2, center_dev, scale_dev};
   EG_LAUNCH(ego_depth_kernel, grid_for((int64_t)A * H * W, 256), 256, 0, as_stream(stream), g, cam, A,
             H, W, fx, fy, max_range, max_steps, hit_eps, depth, steps_out);
