@@ -36,6 +36,10 @@ class EgPolicyDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("in_dim", "ego_dim", "h_dim", "pe_L", "n_blocks", "z_dim")]
 
 
+class EgCvaeDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("in_dim", "h_dim", "z_dim", "mlp_dim")]
+
+
 class EgEnvConfig(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("finetuning", C.c_int32), ("pene_terminate_count", C.c_int32),
                 ("feet_marker_idx", C.c_int32 * 6), ("reproj_factor", C.c_float), ("goal_thresh", C.c_float)] + \
@@ -98,6 +102,13 @@ PROTOTYPES = {
     "eg_adv_normalize": (_I, [_P, _I, _P, _F, _P, _P]),
     "eg_clip_adamw_step": (_I, [_P, _P, _P, _F, _F, _F, _F, _F, _F, _I, _P]),
     "eg_gae": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_double, C.c_double, _P, _P, _P]),
+    "eg_cvae_param_count": (_L, [C.POINTER(EgCvaeDims)]),
+    "eg_cvae_create": (_I, [C.POINTER(EgCvaeDims), _P, _P, _I, C.POINTER(_P)]),
+    "eg_cvae_destroy": (None, [_P]),
+    "eg_cvae_loss_backward": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _I, _F, _P, _P, _P]),
+    "eg_adam_step_flat": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
+    "eg_new_coordinate": (_I, [_P, _I, _I, _P, _P, _P]),
+    "eg_rigid_points": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "eg_lbs_forward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "eg_lbs_forward_sdf": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
 }

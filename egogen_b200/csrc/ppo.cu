@@ -564,3 +564,416 @@ extern "C" int eg_gae(const float* v_s, const float* v_next, const float* rew, c
             gae_lambda, adv, ret);
   return EG_OK;
 }
+
+// ==========================================================================================================
+// C-VAE marker-predictor TRAINING (BASELINE config 3) - replaces GAMMAPrimitiveVAE.forward (encode + reparameterise
+// + decode, reference motion/models/models_GAMMA_primitive.py:75-110) and GAMMAPrimitiveVAETrainOP._calc_loss_rec /
+// calc_loss / one primitive of calc_loss_rollout (:400-432, :476-490) with a hand-written backward (BPTT through the
+// 18-step GRUCell decoder and the 18-step encoder GRU). Parameters / gradients are flat buffers in
+// GAMMAPrimitiveVAE.parameters() order: x_enc, e_rnn (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0), e_mlp.layers.{0,1},
+// e_mu, e_logvar, drnn_mlp.layers.{0,1,2}, d_rnn (weight_ih, weight_hh, bias_ih, bias_hh), d_mlp.layers.{0,1}, d_out.
+// ==========================================================================================================
+namespace eg {
+
+struct CvaeLayout {
+  int64_t x_wih, x_whh, x_bih, x_bhh, e_wih, e_whh, e_bih, e_bhh;
+  Lin e_mlp0, e_mlp1, e_mu, e_lv, dr0, dr1, dr2;
+  int64_t d_wih, d_whh, d_bih, d_bhh;
+  Lin d_mlp0, d_mlp1, d_out;
+  int64_t n_total;
+};
+
+static CvaeLayout make_cvae_layout(const EgCvaeDims& d) {
+  CvaeLayout L{};
+  const int D = d.in_dim, H = d.h_dim, Z = d.z_dim, Hm = d.mlp_dim, H3 = 3 * H;
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off += n; return o; };
+  auto lin = [&](int in, int out) { Lin l{off, off + (int64_t)in * out, in, out}; off += (int64_t)in * out + out; return l; };
+  L.x_wih = take((int64_t)H3 * D); L.x_whh = take((int64_t)H3 * H); L.x_bih = take(H3); L.x_bhh = take(H3);
+  L.e_wih = take((int64_t)H3 * D); L.e_whh = take((int64_t)H3 * H); L.e_bih = take(H3); L.e_bhh = take(H3);
+  L.e_mlp0 = lin(2 * H, Hm); L.e_mlp1 = lin(Hm, H); L.e_mu = lin(H, Z); L.e_lv = lin(H, Z);
+  L.dr0 = lin(H, Hm); L.dr1 = lin(Hm, H); L.dr2 = lin(H, H);
+  L.d_wih = take((int64_t)H3 * (D + Z + H)); L.d_whh = take((int64_t)H3 * H); L.d_bih = take(H3); L.d_bhh = take(H3);
+  L.d_mlp0 = lin(H, Hm); L.d_mlp1 = lin(Hm, H); L.d_out = lin(H, D);
+  L.n_total = off;
+  return L;
+}
+
+__global__ void __launch_bounds__(256)
+tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n, float* __restrict__ dx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * (1.0f - y[i] * y[i]);
+}
+
+// z = mu + eps * exp(0.5 logvar); also accumulates sum(-1 - lv + mu^2 + e^lv) into kl_sum (double)
+__global__ void __launch_bounds__(256)
+reparam_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps, int64_t n,
+               float* __restrict__ z, double* __restrict__ kl_sum) {
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float m = mu[i], l = lv[i];
+    z[i] = m + eps[i] * expf(0.5f * l);
+    s += (double)(-1.0f - l + m * m + expf(l));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(kl_sum, s);
+}
+
+// dmu = dz + c mu / n ; dlv = dz * eps * 0.5 e^{lv/2} + c * 0.5 (e^lv - 1) / n, c = w_kld * scale * d robust / d kld
+__global__ void __launch_bounds__(256)
+reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ lv,
+                   const float* __restrict__ eps, int64_t n, const double* __restrict__ kl_sum, float w_kld, int robust,
+                   float scale, float* __restrict__ dmu, float* __restrict__ dlv, float* __restrict__ stats) {
+  const double k = 0.5 * kl_sum[0] / (double)n;
+  const float c = w_kld * scale * (robust ? (float)(k / sqrt(1.0 + k * k)) : 1.0f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float m = mu[i], l = lv[i];
+    dmu[i] = dz[i] + c * m / (float)n;
+    dlv[i] = dz[i] * eps[i] * 0.5f * expf(0.5f * l) + c * 0.5f * (expf(l) - 1.0f) / (float)n;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && stats) {
+    const float kk = robust ? (float)(sqrt(1.0 + k * k) - 1.0) : (float)k;
+    atomicAdd(stats + 2, kk * scale);
+    atomicAdd(stats + 0, w_kld * kk * scale);
+  }
+}
+
+__device__ __forceinline__ float sgnf(float x) { return (x > 0.0f) - (x < 0.0f); }
+
+// dL/dY_rec for w_rec * mean|Y - Yrec| + w_td * mean|(Yrec[t+1]-Yrec[t]) - (Y[t+1]-Y[t])| ; Y, Yrec [T,B,D] t-major
+__global__ void __launch_bounds__(256)
+rec_loss_grad_kernel(const float* __restrict__ Y, const float* __restrict__ Yr, int T, int64_t BD, float w_rec,
+                     float w_td, float scale, float* __restrict__ dYr, double* __restrict__ sums) {
+  double s_rec = 0.0, s_td = 0.0;
+  const int64_t n = (int64_t)T * BD;
+  const float c_rec = w_rec * scale / (float)n, c_td = w_td * scale / (float)((int64_t)(T - 1) * BD);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i / BD);
+    const float e = Yr[i] - Y[i];
+    float g = c_rec * sgnf(e);
+    s_rec += fabsf(e);
+    if (t + 1 < T) {
+      const float d = (Yr[i + BD] - Yr[i]) - (Y[i + BD] - Y[i]);
+      g -= c_td * sgnf(d);
+      s_td += fabsf(d);
+    }
+    if (t > 0) {
+      const float d = (Yr[i] - Yr[i - BD]) - (Y[i] - Y[i - BD]);
+      g += c_td * sgnf(d);
+    }
+    dYr[i] = g;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s_rec += __shfl_xor_sync(0xffffffffu, s_rec, o); s_td += __shfl_xor_sync(0xffffffffu, s_td, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(sums, s_rec); atomicAdd(sums + 1, s_td); }
+}
+
+__global__ void cvae_stats_kernel(const double* __restrict__ sums, int T, int64_t BD, float w_rec, float w_td, float scale,
+                                  float* __restrict__ stats) {
+  const float rec = w_rec * (float)(sums[0] / (double)((int64_t)T * BD)) + w_td * (float)(sums[1] / (double)((int64_t)(T - 1) * BD));
+  atomicAdd(stats + 1, rec * scale);
+  atomicAdd(stats + 0, rec * scale);
+}
+
+__global__ void __launch_bounds__(256)
+adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float wd_decoupled, float bc1, float bc2_sqrt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    float pi = p[i] * (1.0f - lr * wd_decoupled);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    pi -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    p[i] = pi;
+  }
+}
+
+// new frame from joints (CanonicalCoordinateExtractor, baseops.py:214-225): jts [B,J,3] -> R [B,9], T [B,3]
+__global__ void new_coordinate_kernel(const float* __restrict__ jts, int ld, int B, float* __restrict__ R, float* __restrict__ T) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* j = jts + (int64_t)b * ld;
+  const float x0r = j[6] - j[3], x1r = j[7] - j[4];
+  const float nx = sqrtf(x0r * x0r + x1r * x1r + 0.0f);
+  const float x0 = x0r / nx, x1 = x1r / nx;
+  float y0 = -x1, y1 = x0;
+  const float ny = sqrtf(y0 * y0 + y1 * y1 + 0.0f);
+  y0 /= ny; y1 /= ny;
+  float* r = R + (int64_t)b * 9;
+  r[0] = x0; r[1] = y0; r[2] = 0.f; r[3] = x1; r[4] = y1; r[5] = 0.f; r[6] = 0.f; r[7] = 0.f; r[8] = 1.f;
+  T[b * 3] = j[0]; T[b * 3 + 1] = j[1]; T[b * 3 + 2] = j[2];
+}
+
+// pts [t,B,P,3]: inverse==0: out = R p + T ; inverse==1: out = R^T (p - T)   (einsum patterns of :462-466)
+__global__ void __launch_bounds__(256)
+rigid_points_kernel(const float* __restrict__ R, const float* __restrict__ T, const float* __restrict__ pts, int nt, int B,
+                    int P, int inverse, float* __restrict__ out) {
+  const int64_t n = (int64_t)nt * B * P;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)((i / P) % B);
+    const float* r = R + (int64_t)b * 9;
+    const float* t = T + (int64_t)b * 3;
+    const float* p = pts + i * 3;
+    float* o = out + i * 3;
+    if (inverse) {
+      const float d0 = p[0] - t[0], d1 = p[1] - t[1], d2 = p[2] - t[2];
+      for (int q = 0; q < 3; ++q) o[q] = r[0 * 3 + q] * d0 + r[1 * 3 + q] * d1 + r[2 * 3 + q] * d2;
+    } else {
+      for (int q = 0; q < 3; ++q) o[q] = (r[q * 3 + 0] * p[0] + r[q * 3 + 1] * p[1] + r[q * 3 + 2] * p[2]) + t[q];
+    }
+  }
+}
+
+}  // namespace eg
+
+struct EgCvae {
+  int device = 0;
+  EgCvaeDims d;
+  CvaeLayout L;
+  float *P = nullptr, *G = nullptr;
+  int cap = 0;
+  std::vector<float*> owned;
+  // saved activations
+  float *gi = nullptr, *gh = nullptr;
+  float *xr[2], *xz[2], *xn[2], *xg[2], *xh[2];            // x_enc steps (xh[t] = h after step t)
+  float *er[18], *ez[18], *en[18], *eg_[18], *eh[18];       // e_rnn steps
+  float *hcat = nullptr, *ea1 = nullptr, *ea2 = nullptr, *mu = nullptr, *lv = nullptr, *z = nullptr, *hz = nullptr;
+  float *dr_a0 = nullptr, *dr_a1 = nullptr, *h0 = nullptr, *c = nullptr;
+  float *dr_[18], *dz_[18], *dn_[18], *dg_[18], *dh_[18], *f1[18], *f2[18];
+  // backward scratch
+  float *dY = nullptr, *dy = nullptr, *dh = nullptr, *dhp = nullptr, *da = nullptr, *db = nullptr, *dgi = nullptr,
+        *dgh = nullptr, *dc = nullptr, *dhz = nullptr, *dmu = nullptr, *dlv = nullptr, *dhcat = nullptr, *dhx = nullptr;
+  double* sums = nullptr;       // [0] |rec| sum, [1] |td| sum, [2] kl sum
+};
+
+#undef EG_TRY
+#define EG_TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+static int cvae_ws(EgCvae* h, int B) {
+  if (B <= h->cap) return EG_OK;
+  for (float* p : h->owned) cudaFree(p);
+  h->owned.clear(); h->cap = 0;
+  const EgCvaeDims& d = h->d;
+  const size_t b = (size_t)B, H = d.h_dim, H3 = 3 * H, D = d.in_dim, Z = d.z_dim, Hm = d.mlp_dim;
+  auto A = [&](float** p, size_t n) -> int {
+    EG_CUDA_CHECK(cudaMalloc((void**)p, n * sizeof(float)));
+    h->owned.push_back(*p);
+    return EG_OK;
+  };
+  EG_TRY(A(&h->gi, b * H3)); EG_TRY(A(&h->gh, b * H3));
+  for (int t = 0; t < 2; ++t) { EG_TRY(A(&h->xr[t], b * H)); EG_TRY(A(&h->xz[t], b * H)); EG_TRY(A(&h->xn[t], b * H)); EG_TRY(A(&h->xg[t], b * H)); EG_TRY(A(&h->xh[t], b * H)); }
+  for (int t = 0; t < 18; ++t) {
+    EG_TRY(A(&h->er[t], b * H)); EG_TRY(A(&h->ez[t], b * H)); EG_TRY(A(&h->en[t], b * H)); EG_TRY(A(&h->eg_[t], b * H)); EG_TRY(A(&h->eh[t], b * H));
+    EG_TRY(A(&h->dr_[t], b * H)); EG_TRY(A(&h->dz_[t], b * H)); EG_TRY(A(&h->dn_[t], b * H)); EG_TRY(A(&h->dg_[t], b * H)); EG_TRY(A(&h->dh_[t], b * H));
+    EG_TRY(A(&h->f1[t], b * Hm)); EG_TRY(A(&h->f2[t], b * H));
+  }
+  EG_TRY(A(&h->hcat, b * 2 * H)); EG_TRY(A(&h->ea1, b * Hm)); EG_TRY(A(&h->ea2, b * H)); EG_TRY(A(&h->mu, b * Z)); EG_TRY(A(&h->lv, b * Z));
+  EG_TRY(A(&h->z, b * Z)); EG_TRY(A(&h->hz, b * (H + Z))); EG_TRY(A(&h->dr_a0, b * Hm)); EG_TRY(A(&h->dr_a1, b * H)); EG_TRY(A(&h->h0, b * H));
+  EG_TRY(A(&h->c, b * H3));
+  EG_TRY(A(&h->dY, 18 * b * D)); EG_TRY(A(&h->dy, b * D)); EG_TRY(A(&h->dh, b * H)); EG_TRY(A(&h->dhp, b * H)); EG_TRY(A(&h->da, b * Hm));
+  EG_TRY(A(&h->db, b * Hm)); EG_TRY(A(&h->dgi, b * H3)); EG_TRY(A(&h->dgh, b * H3)); EG_TRY(A(&h->dc, b * H3)); EG_TRY(A(&h->dhz, b * (H + Z)));
+  EG_TRY(A(&h->dmu, b * Z)); EG_TRY(A(&h->dlv, b * Z)); EG_TRY(A(&h->dhcat, b * 2 * H)); EG_TRY(A(&h->dhx, b * H));
+  h->cap = B;
+  return EG_OK;
+}
+
+extern "C" int64_t eg_cvae_param_count(const EgCvaeDims* d) { return d ? make_cvae_layout(*d).n_total : -1; }
+
+extern "C" int eg_cvae_create(const EgCvaeDims* dims, float* params_flat, float* grads_flat, int device, EgCvae** out) {
+  EG_REQUIRE(dims && params_flat && grads_flat && out, "null pointer");
+  EG_CUDA_CHECK(cudaSetDevice(device));
+  EgCvae* h = new EgCvae();
+  h->device = device; h->d = *dims; h->L = make_cvae_layout(*dims); h->P = params_flat; h->G = grads_flat;
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->sums, 4 * sizeof(double)));
+  *out = h;
+  return EG_OK;
+}
+
+extern "C" void eg_cvae_destroy(EgCvae* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (float* p : h->owned) cudaFree(p);
+  cudaFree(h->sums);
+  delete h;
+}
+
+namespace {
+// dY [B,out] -> dW += dY^T X, db += colsum(dY), optional dX (= or +=) dY W, for a Linear at flat offsets (w, b)
+int lin_bwd(EgCvae* h, cudaStream_t st, const float* dY, int ld_dy, const float* X, int ldx, int B, int64_t w, int64_t b,
+            int in, int out, int ldw, float* dX, int ld_dx, int dx_beta) {
+  GemmArgs gw{dY, ld_dy, 1, X, ldx, h->G + w, ldw, nullptr, nullptr, 0, out, in, B, ACT_NONE, 0.f, 1, 1.0f};
+  EG_TRY(launch_gemm(gw, true, false, st));
+  if (b >= 0) EG_LAUNCH(colsum_kernel, (out + 31) / 32, 256, 0, st, dY, ld_dy, B, out, h->G + b);
+  if (dX) {
+    GemmArgs gx{dY, ld_dy, 1, h->P + w, ldw, dX, ld_dx, nullptr, nullptr, 0, B, in, out, ACT_NONE, 0.f, dx_beta, 1.0f};
+    EG_TRY(launch_gemm(gx, false, false, st));
+  }
+  return EG_OK;
+}
+}  // namespace
+
+// One primitive: forward (encode, reparameterise, decode), losses, full backward. X [2,B,D] and Y [18,B,D] are
+// time-major like the reference tensors. Gradients are ACCUMULATED into the flat buffer scaled by loss_scale
+// (1 / #primitives of a rollout, calc_loss_rollout :500). Y_rec [18,B,D] is returned for the next rollout seed.
+// stats (device float[4], accumulated): 0 total loss, 1 rec loss (weighted), 2 kld term.
+extern "C" int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float w_rec,
+                                     float w_td, float w_kld, int robust_kld, float loss_scale, float* Y_rec, float* stats,
+                                     void* stream) {
+  EG_REQUIRE(h && X && Y && eps && Y_rec && stats && B > 0, "bad arguments");
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  EG_TRY(cvae_ws(h, B));
+  cudaStream_t st = as_stream(stream);
+  const EgCvaeDims& d = h->d;
+  const CvaeLayout& L = h->L;
+  const int D = d.in_dim, H = d.h_dim, Z = d.z_dim, Hm = d.mlp_dim, H3 = 3 * H, T = 18, Kin = H + Z + D;
+  const float* P = h->P;
+  float* G = h->G;
+  const int64_t BD = (int64_t)B * D;
+  const int64_t nBH = (int64_t)B * H;
+  // ---------------- forward: encoder ----------------
+  for (int t = 0; t < 2; ++t) {   // x_enc
+    EG_TRY(linear(st, X + t * BD, D, B, P + L.x_wih, D, P + L.x_bih, D, H3, h->gi, H3));
+    if (t > 0) EG_TRY(linear(st, h->xh[t - 1], H, B, P + L.x_whh, H, P + L.x_bhh, H, H3, h->gh, H3));
+    EG_TRY(launch_gru_gate(st, h->gi, t ? h->gh : nullptr, P + L.x_bhh, t ? h->xh[t - 1] : nullptr, h->xh[t], B, H, H,
+                           h->xr[t], h->xz[t], h->xn[t], h->xg[t]));
+  }
+  for (int t = 0; t < T; ++t) {   // e_rnn over the 18 target frames
+    EG_TRY(linear(st, Y + t * BD, D, B, P + L.e_wih, D, P + L.e_bih, D, H3, h->gi, H3));
+    if (t > 0) EG_TRY(linear(st, h->eh[t - 1], H, B, P + L.e_whh, H, P + L.e_bhh, H, H3, h->gh, H3));
+    EG_TRY(launch_gru_gate(st, h->gi, t ? h->gh : nullptr, P + L.e_bhh, t ? h->eh[t - 1] : nullptr, h->eh[t], B, H, H,
+                           h->er[t], h->ez[t], h->en[t], h->eg_[t]));
+  }
+  const float* hx = h->xh[1];
+  EG_CUDA_CHECK(cudaMemcpy2DAsync(h->hcat, 2 * H * 4, hx, H * 4, H * 4, B, cudaMemcpyDeviceToDevice, st));
+  EG_CUDA_CHECK(cudaMemcpy2DAsync(h->hcat + H, 2 * H * 4, h->eh[T - 1], H * 4, H * 4, B, cudaMemcpyDeviceToDevice, st));
+  EG_TRY(linear(st, h->hcat, 2 * H, B, P + L.e_mlp0.w, 2 * H, P + L.e_mlp0.b, 2 * H, Hm, h->ea1, Hm, ACT_TANH));
+  EG_TRY(linear(st, h->ea1, Hm, B, P + L.e_mlp1.w, Hm, P + L.e_mlp1.b, Hm, H, h->ea2, H, ACT_TANH));
+  EG_TRY(linear(st, h->ea2, H, B, P + L.e_mu.w, H, P + L.e_mu.b, H, Z, h->mu, Z));
+  EG_TRY(linear(st, h->ea2, H, B, P + L.e_lv.w, H, P + L.e_lv.b, H, Z, h->lv, Z));
+  EG_CUDA_CHECK(cudaMemsetAsync(h->sums, 0, 4 * sizeof(double), st));
+  EG_LAUNCH(reparam_kernel, ew_grid((int64_t)B * Z), 256, 0, st, h->mu, h->lv, eps, (int64_t)B * Z, h->z, h->sums + 2);
+  // ---------------- forward: decoder ----------------
+  EG_TRY(linear(st, hx, H, B, P + L.dr0.w, H, P + L.dr0.b, H, Hm, h->dr_a0, Hm, ACT_TANH));
+  EG_TRY(linear(st, h->dr_a0, Hm, B, P + L.dr1.w, Hm, P + L.dr1.b, Hm, H, h->dr_a1, H, ACT_TANH));
+  EG_TRY(linear(st, h->dr_a1, H, B, P + L.dr2.w, H, P + L.dr2.b, H, H, h->h0, H, ACT_TANH));
+  EG_CUDA_CHECK(cudaMemcpy2DAsync(h->hz, (H + Z) * 4, hx, H * 4, H * 4, B, cudaMemcpyDeviceToDevice, st));
+  EG_CUDA_CHECK(cudaMemcpy2DAsync(h->hz + H, (H + Z) * 4, h->z, Z * 4, Z * 4, B, cudaMemcpyDeviceToDevice, st));
+  EG_TRY(linear(st, h->hz, H + Z, B, P + L.d_wih, Kin, P + L.d_bih, H + Z, H3, h->c, H3));
+  for (int i = 0; i < T; ++i) {
+    const float* yp = i ? Y_rec + (int64_t)(i - 1) * BD : X + BD;
+    const float* hp = i ? h->dh_[i - 1] : h->h0;
+    EG_TRY(linear(st, yp, D, B, P + L.d_wih + H + Z, Kin, nullptr, D, H3, h->gi, H3, ACT_NONE, 0.f, h->c, H3));
+    EG_TRY(linear(st, hp, H, B, P + L.d_whh, H, P + L.d_bhh, H, H3, h->gh, H3));
+    EG_TRY(launch_gru_gate(st, h->gi, h->gh, nullptr, hp, h->dh_[i], B, H, H, h->dr_[i], h->dz_[i], h->dn_[i], h->dg_[i]));
+    EG_TRY(linear(st, h->dh_[i], H, B, P + L.d_mlp0.w, H, P + L.d_mlp0.b, H, Hm, h->f1[i], Hm, ACT_TANH));
+    EG_TRY(linear(st, h->f1[i], Hm, B, P + L.d_mlp1.w, Hm, P + L.d_mlp1.b, Hm, H, h->f2[i], H, ACT_TANH));
+    EG_TRY(linear(st, h->f2[i], H, B, P + L.d_out.w, H, P + L.d_out.b, H, D, Y_rec + (int64_t)i * BD, D, ACT_NONE, 0.f, yp, D));
+  }
+  // ---------------- losses ----------------
+  EG_LAUNCH(rec_loss_grad_kernel, ew_grid((int64_t)T * BD), 256, 0, st, Y, Y_rec, T, BD, w_rec, w_td, loss_scale, h->dY, h->sums);
+  EG_LAUNCH(cvae_stats_kernel, 1, 1, 0, st, h->sums, T, BD, w_rec, w_td, loss_scale, stats);
+  // ---------------- backward: decoder BPTT ----------------
+  EG_CUDA_CHECK(cudaMemsetAsync(h->dh, 0, nBH * 4, st));
+  EG_CUDA_CHECK(cudaMemsetAsync(h->dc, 0, (size_t)B * H3 * 4, st));
+  EG_CUDA_CHECK(cudaMemsetAsync(h->dy, 0, (size_t)BD * 4, st));
+  for (int i = T - 1; i >= 0; --i) {
+    const float* yp = i ? Y_rec + (int64_t)(i - 1) * BD : X + BD;
+    const float* hp = i ? h->dh_[i - 1] : h->h0;
+    // dy_i = dL/dY_rec[i] + carried gradient w.r.t. y_p of step i+1
+    EG_LAUNCH(add_kernel, ew_grid(BD), 256, 0, st, h->dY + (int64_t)i * BD, h->dy, BD, h->dy);
+    // y_i = d_out(f2) + y_p
+    EG_TRY(lin_bwd(h, st, h->dy, D, h->f2[i], H, B, L.d_out.w, L.d_out.b, H, D, H, h->db, H, 0));
+    EG_LAUNCH(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->db, h->f2[i], nBH, h->db);
+    EG_TRY(lin_bwd(h, st, h->db, H, h->f1[i], Hm, B, L.d_mlp1.w, L.d_mlp1.b, Hm, H, Hm, h->da, Hm, 0));
+    EG_LAUNCH(tanh_bwd_kernel, ew_grid((int64_t)B * Hm), 256, 0, st, h->da, h->f1[i], (int64_t)B * Hm, h->da);
+    EG_TRY(lin_bwd(h, st, h->da, Hm, h->dh_[i], H, B, L.d_mlp0.w, L.d_mlp0.b, H, Hm, H, h->dh, H, 1));   // dh_i += ...
+    // GRUCell backward
+    EG_LAUNCH(gru_bwd_kernel, ew_grid(nBH), 256, 0, st, h->dh, H, h->dr_[i], h->dz_[i], h->dn_[i], h->dg_[i], hp, B, H,
+              h->dgi, h->dgh, h->dhp);
+    EG_TRY(lin_bwd(h, st, h->dgh, H3, hp, H, B, L.d_whh, L.d_bhh, H, H3, H, h->dhp, H, 1));              // dh_{i-1}
+    // gi = c + y_p Wy^T : weight slice of d_rnn.weight_ih (columns H+Z..), bias lives in c
+    EG_TRY(lin_bwd(h, st, h->dgi, H3, yp, D, B, L.d_wih + H + Z, -1, D, H3, Kin, h->db, D, 0));           // d y_p (GRU path)
+    EG_LAUNCH(add_kernel, ew_grid((int64_t)B * H3), 256, 0, st, h->dc, h->dgi, (int64_t)B * H3, h->dc);
+    // carry: dy_{i-1} = dy_i (residual) + dgi Wy
+    EG_LAUNCH(add_kernel, ew_grid(BD), 256, 0, st, h->dy, h->db, BD, h->dy);
+    std::swap(h->dh, h->dhp);
+  }
+  // h->dh now holds dL/dh0 ; c = [hx,z] W_ih[:, :H+Z]^T + b_ih
+  EG_TRY(lin_bwd(h, st, h->dc, H3, h->hz, H + Z, B, L.d_wih, L.d_bih, H + Z, H3, Kin, h->dhz, H + Z, 0));
+  // drnn_mlp backward: h0 = tanh(W2 tanh(W1 tanh(W0 hx)))
+  EG_LAUNCH(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->dh, h->h0, nBH, h->dh);
+  EG_TRY(lin_bwd(h, st, h->dh, H, h->dr_a1, H, B, L.dr2.w, L.dr2.b, H, H, H, h->db, H, 0));
+  EG_LAUNCH(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->db, h->dr_a1, nBH, h->db);
+  EG_TRY(lin_bwd(h, st, h->db, H, h->dr_a0, Hm, B, L.dr1.w, L.dr1.b, Hm, H, Hm, h->da, Hm, 0));
+  EG_LAUNCH(tanh_bwd_kernel, ew_grid((int64_t)B * Hm), 256, 0, st, h->da, h->dr_a0, (int64_t)B * Hm, h->da);
+  EG_TRY(lin_bwd(h, st, h->da, Hm, hx, H, B, L.dr0.w, L.dr0.b, H, Hm, H, h->dhx, H, 0));                 // dhx (1)
+  // ---------------- backward: latent + encoder ----------------
+  // dz = dhz[:, H:], dhx (2) = dhz[:, :H]; gather dz contiguous through a strided copy
+  EG_CUDA_CHECK(cudaMemcpy2DAsync(h->z, Z * 4, h->dhz + H, (H + Z) * 4, Z * 4, B, cudaMemcpyDeviceToDevice, st));   // reuse z as dz
+  EG_LAUNCH(reparam_bwd_kernel, ew_grid((int64_t)B * Z), 256, 0, st, h->z, h->mu, h->lv, eps, (int64_t)B * Z, h->sums + 2,
+            w_kld, robust_kld, loss_scale, h->dmu, h->dlv, stats);
+  EG_TRY(lin_bwd(h, st, h->dmu, Z, h->ea2, H, B, L.e_mu.w, L.e_mu.b, H, Z, H, h->db, H, 0));
+  EG_TRY(lin_bwd(h, st, h->dlv, Z, h->ea2, H, B, L.e_lv.w, L.e_lv.b, H, Z, H, h->db, H, 1));
+  EG_LAUNCH(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->db, h->ea2, nBH, h->db);
+  EG_TRY(lin_bwd(h, st, h->db, H, h->ea1, Hm, B, L.e_mlp1.w, L.e_mlp1.b, Hm, H, Hm, h->da, Hm, 0));
+  EG_LAUNCH(tanh_bwd_kernel, ew_grid((int64_t)B * Hm), 256, 0, st, h->da, h->ea1, (int64_t)B * Hm, h->da);
+  EG_TRY(lin_bwd(h, st, h->da, Hm, h->hcat, 2 * H, B, L.e_mlp0.w, L.e_mlp0.b, 2 * H, Hm, 2 * H, h->dhcat, 2 * H, 0));
+  // dhx total = drnn path + c path + encoder path
+  // dhx += dhz[:, :H] + dhcat[:, :H]  (strided adds via 2-D copies into scratch then add)
+  EG_CUDA_CHECK(cudaMemcpy2DAsync(h->db, H * 4, h->dhz, (H + Z) * 4, H * 4, B, cudaMemcpyDeviceToDevice, st));
+  EG_LAUNCH(add_kernel, ew_grid(nBH), 256, 0, st, h->dhx, h->db, nBH, h->dhx);
+  EG_CUDA_CHECK(cudaMemcpy2DAsync(h->db, H * 4, h->dhcat, 2 * H * 4, H * 4, B, cudaMemcpyDeviceToDevice, st));
+  EG_LAUNCH(add_kernel, ew_grid(nBH), 256, 0, st, h->dhx, h->db, nBH, h->dhx);
+  // x_enc BPTT (2 steps)
+  {
+    float* dcur = h->dhx;
+    for (int t = 1; t >= 0; --t) {
+      const float* hp = t ? h->xh[t - 1] : nullptr;
+      EG_LAUNCH(gru_bwd_kernel, ew_grid(nBH), 256, 0, st, dcur, H, h->xr[t], h->xz[t], h->xn[t], h->xg[t], hp, B, H, h->dgi,
+                h->dgh, h->dhp);
+      EG_TRY(lin_bwd(h, st, h->dgi, H3, X + t * BD, D, B, L.x_wih, L.x_bih, D, H3, D, nullptr, 0, 0));
+      if (t > 0) EG_TRY(lin_bwd(h, st, h->dgh, H3, hp, H, B, L.x_whh, L.x_bhh, H, H3, H, h->dhp, H, 1));
+      else EG_LAUNCH(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + L.x_bhh);
+      dcur = h->dhp;
+    }
+  }
+  // e_rnn BPTT (18 steps); dh_T = dhcat[:, H:]
+  EG_CUDA_CHECK(cudaMemcpy2DAsync(h->dh, H * 4, h->dhcat + H, 2 * H * 4, H * 4, B, cudaMemcpyDeviceToDevice, st));
+  for (int t = T - 1; t >= 0; --t) {
+    const float* hp = t ? h->eh[t - 1] : nullptr;
+    EG_LAUNCH(gru_bwd_kernel, ew_grid(nBH), 256, 0, st, h->dh, H, h->er[t], h->ez[t], h->en[t], h->eg_[t], hp, B, H, h->dgi,
+              h->dgh, h->dhp);
+    EG_TRY(lin_bwd(h, st, h->dgi, H3, Y + t * BD, D, B, L.e_wih, L.e_bih, D, H3, D, nullptr, 0, 0));
+    if (t > 0) EG_TRY(lin_bwd(h, st, h->dgh, H3, hp, H, B, L.e_whh, L.e_bhh, H, H3, H, h->dhp, H, 1));
+    else EG_LAUNCH(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + L.e_bhh);
+    std::swap(h->dh, h->dhp);
+  }
+  return EG_OK;
+}
+
+extern "C" int eg_adam_step_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                 float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+  EG_REQUIRE(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "bad arguments");
+  if (n == 0) return EG_OK;
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2s = sqrtf(1.0f - powf(beta2, (float)step));
+  EG_LAUNCH(adam_flat_kernel, kNumSMs * 8, 256, 0, as_stream(stream), params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+            eps, weight_decay, bc1, bc2s);
+  return EG_OK;
+}
+
+extern "C" int eg_new_coordinate(const float* joints, int ld_body, int B, float* R, float* T, void* stream) {
+  EG_REQUIRE(joints && R && T && B >= 0 && ld_body >= 9, "bad arguments");
+  if (B == 0) return EG_OK;
+  EG_LAUNCH(new_coordinate_kernel, (B + 127) / 128, 128, 0, as_stream(stream), joints, ld_body, B, R, T);
+  return EG_OK;
+}
+
+extern "C" int eg_rigid_points(const float* R, const float* T, const float* pts, int nt, int B, int P, int inverse, float* out,
+                               void* stream) {
+  EG_REQUIRE(R && T && pts && out && nt >= 0 && B >= 0 && P >= 0, "bad arguments");
+  if ((int64_t)nt * B * P == 0) return EG_OK;
+  EG_LAUNCH(rigid_points_kernel, ew_grid((int64_t)nt * B * P), 256, 0, as_stream(stream), R, T, pts, nt, B, P, inverse, out);
+  return EG_OK;
+}

@@ -293,6 +293,30 @@ int eg_gae(const float* v_s, const float* v_next, const float* rew, const uint8_
            const uint8_t* end_flag, int T, int E, double gamma, double gae_lambda, float* adv, float* ret,
            void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * C-VAE marker-predictor training (BASELINE config 3) - replaces GAMMAPrimitiveVAE.forward + the loss of
+ * GAMMAPrimitiveVAETrainOP.calc_loss / one primitive of calc_loss_rollout
+ * (motion/models/models_GAMMA_primitive.py:75-110, 400-432, 476-490) with a hand-written backward.
+ * Flat parameter / gradient buffers in GAMMAPrimitiveVAE.parameters() order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EgCvae EgCvae;
+typedef struct EgCvaeDims { int32_t in_dim /*201*/, h_dim /*256*/, z_dim /*128*/, mlp_dim /*512*/; } EgCvaeDims;
+int64_t eg_cvae_param_count(const EgCvaeDims* dims);
+int eg_cvae_create(const EgCvaeDims* dims, float* params_flat, float* grads_flat, int device, EgCvae** out);
+void eg_cvae_destroy(EgCvae* h);
+/* X [2,B,201], Y [18,B,201] time-major, eps [B,128] the reparameterisation noise. Gradients are accumulated
+ * (scaled by loss_scale); Y_rec [18,B,201] out; stats (device float[4], accumulated): loss, rec, kld. */
+int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float w_rec, float w_td,
+                          float w_kld, int robust_kld, float loss_scale, float* Y_rec, float* stats, void* stream);
+/* torch.optim.Adam / AdamW step on flat buffers (weight_decay is the decoupled AdamW form; 0 for Adam) */
+int eg_adam_step_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+/* CanonicalCoordinateExtractor.get_new_coordinate_torch (baseops.py:214-225): joints of body b at joints + b*ld_body */
+int eg_new_coordinate(const float* joints, int ld_body, int B, float* R, float* T, void* stream);
+/* pts [nt,B,P,3]: inverse=0 -> R p + T, inverse=1 -> R^T (p - T)  (models_GAMMA_primitive.py:462-466) */
+int eg_rigid_points(const float* R, const float* T, const float* pts, int nt, int B, int P, int inverse, float* out,
+                    void* stream);
+
 /* y[M,out] = act(x W^T + b) + residual, W [out,in] row-major (nn.Linear; baseops.py:615-641 MLP layers).
  * act: 0 none, 1 tanh, 2 relu, 3 leaky-relu(slope). */
 int eg_linear_forward(const float* x, int ldx, int M, const float* W, const float* b, int in_dim,
