@@ -3,6 +3,7 @@
 //   * GAMMAPrimitiveCombo.sample_prior  (reference motion/models/models_GAMMA_primitive.py:334-360,
 //     predictor decode :83-101, regressor :222-301, 6-D -> axis-angle :208-219 + baseops.py:120-162)
 //   * VPoser v1 encoder `.loc`         (reference call site crowd_env_2f.py:197-200)
+#include <cooperative_groups.h>
 #include <vector>
 
 #include "geom.cuh"
@@ -21,17 +22,21 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   }
 }
 
-// fp32 SIMT GEMM, BM x BN x 16 tiles, TM x TN outputs per thread, 256 threads, double-buffered shared
-// memory with register prefetch of the next k-tile (one __syncthreads per k-tile). Three tile shapes are
-// instantiated; launch_gemm picks the largest one that still fills the 148 SMs.
-template <int BM, int BN, int TM, int TN, bool TA, bool TB>
+// fp32 SIMT GEMM, BM x BN x BKT tiles, TM x TN outputs per thread, 256 threads, double-buffered shared
+// memory with register prefetch of the next k-tile (one __syncthreads per k-tile). Operands whose K dimension is
+// contiguous and 16-byte aligned are fetched with 128-bit loads (VEC). launch_gemm picks the largest tile shape
+// that still fills the 148 SMs.
+template <int BM, int BN, int BKT, int TM, int TN, bool TA, bool TB, bool VEC, int SPLIT = 1>
 __global__ void __launch_bounds__(256)
 gemm_kernel(const GemmArgs g) {
   constexpr int NT = 256;
   static_assert((BM / TM) * (BN / TN) == NT, "tile / thread mismatch");
-  constexpr int LA = BM * BK / NT, LB = BN * BK / NT;      // elements each thread loads per tile
-  __shared__ __align__(16) float As[2][BK][BM + 4];
-  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  constexpr bool VA = VEC && !TA, VB = VEC && TB;           // K-contiguous operands only
+  constexpr int LA = BM * BKT / NT, LB = BN * BKT / NT;      // elements each thread loads per tile
+  static_assert(LA % 4 == 0 || !VA, "vector A load needs 4 elements per thread");
+  static_assert(LB % 4 == 0 || !VB, "vector B load needs 4 elements per thread");
+  __shared__ __align__(16) float As[2][BKT][BM + 4];
+  __shared__ __align__(16) float Bs[2][BKT][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -43,55 +48,102 @@ gemm_kernel(const GemmArgs g) {
   float ra[LA], rb[LB];
 
   auto load_global = [&](int k0) {
+    if (VA) {
 #pragma unroll
-    for (int i = 0; i < LA; ++i) {
-      const int idx = tid + i * NT;
-      int m, k;
-      if (TA) { k = idx / BM; m = idx % BM; } else { m = idx / BK; k = idx % BK; }
-      const int gm = m0 + m, gk = k0 + k;
-      float v = 0.0f;
-      if (gm < g.M && gk < g.K)
-        v = TA ? __ldg(g.A + (int64_t)gk * g.lda + gm) : __ldg(g.A + (int64_t)(gm / g.a_div) * g.lda + gk);
-      ra[i] = v;
+      for (int i = 0; i < LA / 4; ++i) {
+        const int idx = tid + i * NT;                         // one float4 = 4 consecutive k of one row
+        const int m = idx / (BKT / 4), k = (idx % (BKT / 4)) * 4;
+        const int gm = m0 + m, gk = k0 + k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gm < g.M && gk < g.K) v = __ldg(reinterpret_cast<const float4*>(g.A + (int64_t)(gm / g.a_div) * g.lda + gk));
+        ra[4 * i] = v.x; ra[4 * i + 1] = v.y; ra[4 * i + 2] = v.z; ra[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < LA; ++i) {
+        const int idx = tid + i * NT;
+        int m, k;
+        if (TA) { k = idx / BM; m = idx % BM; } else { m = idx / BKT; k = idx % BKT; }
+        const int gm = m0 + m, gk = k0 + k;
+        float v = 0.0f;
+        if (gm < g.M && gk < g.K)
+          v = TA ? __ldg(g.A + (int64_t)gk * g.lda + gm) : __ldg(g.A + (int64_t)(gm / g.a_div) * g.lda + gk);
+        ra[i] = v;
+      }
     }
+    if (VB) {
 #pragma unroll
-    for (int i = 0; i < LB; ++i) {
-      const int idx = tid + i * NT;
-      int n, k;
-      if (TB) { n = idx / BK; k = idx % BK; } else { k = idx / BN; n = idx % BN; }
-      const int gn = n0 + n, gk = k0 + k;
-      float v = 0.0f;
-      if (gn < g.N && gk < g.K)
-        v = TB ? __ldg(g.B + (int64_t)gn * g.ldb + gk) : __ldg(g.B + (int64_t)gk * g.ldb + gn);
-      rb[i] = v;
+      for (int i = 0; i < LB / 4; ++i) {
+        const int idx = tid + i * NT;
+        const int n = idx / (BKT / 4), k = (idx % (BKT / 4)) * 4;
+        const int gn = n0 + n, gk = k0 + k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gn < g.N && gk < g.K) v = __ldg(reinterpret_cast<const float4*>(g.B + (int64_t)gn * g.ldb + gk));
+        rb[4 * i] = v.x; rb[4 * i + 1] = v.y; rb[4 * i + 2] = v.z; rb[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < LB; ++i) {
+        const int idx = tid + i * NT;
+        int n, k;
+        if (TB) { n = idx / BKT; k = idx % BKT; } else { k = idx / BN; n = idx % BN; }
+        const int gn = n0 + n, gk = k0 + k;
+        float v = 0.0f;
+        if (gn < g.N && gk < g.K)
+          v = TB ? __ldg(g.B + (int64_t)gn * g.ldb + gk) : __ldg(g.B + (int64_t)gk * g.ldb + gn);
+        rb[i] = v;
+      }
     }
   };
   auto store_smem = [&](int buf) {
+    if (VA) {
 #pragma unroll
-    for (int i = 0; i < LA; ++i) {
-      const int idx = tid + i * NT;
-      int m, k;
-      if (TA) { k = idx / BM; m = idx % BM; } else { m = idx / BK; k = idx % BK; }
-      As[buf][k][m] = ra[i];
+      for (int i = 0; i < LA / 4; ++i) {
+        const int idx = tid + i * NT;
+        const int m = idx / (BKT / 4), k = (idx % (BKT / 4)) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) As[buf][k + q][m] = ra[4 * i + q];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < LA; ++i) {
+        const int idx = tid + i * NT;
+        int m, k;
+        if (TA) { k = idx / BM; m = idx % BM; } else { m = idx / BKT; k = idx % BKT; }
+        As[buf][k][m] = ra[i];
+      }
     }
+    if (VB) {
 #pragma unroll
-    for (int i = 0; i < LB; ++i) {
-      const int idx = tid + i * NT;
-      int n, k;
-      if (TB) { n = idx / BK; k = idx % BK; } else { k = idx / BN; n = idx % BN; }
-      Bs[buf][k][n] = rb[i];
+      for (int i = 0; i < LB / 4; ++i) {
+        const int idx = tid + i * NT;
+        const int n = idx / (BKT / 4), k = (idx % (BKT / 4)) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Bs[buf][k + q][n] = rb[4 * i + q];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < LB; ++i) {
+        const int idx = tid + i * NT;
+        int n, k;
+        if (TB) { n = idx / BKT; k = idx % BKT; } else { k = idx / BN; n = idx % BN; }
+        Bs[buf][k][n] = rb[i];
+      }
     }
   };
 
-  const int nk = (g.K + BK - 1) / BK;
-  load_global(0);
-  store_smem(0);
+  const int nk_all = (g.K + BKT - 1) / BKT;
+  // SPLIT == 2: the two CTAs of a (1,1,2) cluster each take half of the k-tiles; rank 0 reduces through DSMEM
+  const int kt_begin = SPLIT == 1 ? 0 : (int)blockIdx.z * ((nk_all + 1) / 2);
+  const int kt_end = SPLIT == 1 ? nk_all : min(nk_all, kt_begin + (nk_all + 1) / 2);
+  const int nk = kt_end - kt_begin;
+  if (nk > 0) { load_global(kt_begin * BKT); store_smem(0); }
   __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
     const int cur = kt & 1;
-    if (kt + 1 < nk) load_global((kt + 1) * BK);
+    if (kt + 1 < nk) load_global((kt_begin + kt + 1) * BKT);
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
+    for (int k = 0; k < BKT; ++k) {
       float av[TM], bv[TN];
 #pragma unroll
       for (int i = 0; i < TM; i += (TM >= 4 ? 4 : TM)) {
@@ -121,6 +173,28 @@ gemm_kernel(const GemmArgs g) {
     if (kt + 1 < nk) store_smem(cur ^ 1);
     __syncthreads();
   }
+  if (SPLIT == 2) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    static_assert(SPLIT == 1 || sizeof(As) >= sizeof(float) * BM * BN, "reduction buffer does not fit in As");
+    float* red = &As[0][0][0];
+    if (blockIdx.z == 1) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) red[(ty * TM + i) * BN + tx * TN + j] = acc[i][j];
+    }
+    cluster.sync();
+    if (blockIdx.z == 0) {
+      const float* remote = cluster.map_shared_rank(red, 1);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += remote[(ty * TM + i) * BN + tx * TN + j];
+    }
+    cluster.sync();                    // rank 1's shared memory must outlive rank 0's reads
+    if (blockIdx.z != 0) return;
+  }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * TM + i;
@@ -139,22 +213,56 @@ gemm_kernel(const GemmArgs g) {
   }
 }
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int BKT, int TM, int TN>
 static int launch_gemm_cfg(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
-  if (!TA && TB) EG_LAUNCH((gemm_kernel<BM, BN, TM, TN, false, true>), grid, 256, 0, st, g);
-  else if (!TA && !TB) EG_LAUNCH((gemm_kernel<BM, BN, TM, TN, false, false>), grid, 256, 0, st, g);
-  else if (TA && !TB) EG_LAUNCH((gemm_kernel<BM, BN, TM, TN, true, false>), grid, 256, 0, st, g);
-  else EG_LAUNCH((gemm_kernel<BM, BN, TM, TN, true, true>), grid, 256, 0, st, g);
+  // 128-bit loads need K-contiguous storage (A: !TA, B: TB), 16-byte aligned rows and K % 4 == 0
+  auto al = [](const float* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0; };
+  const bool vec = (g.K & 3) == 0 && (TA || al(g.A, g.lda)) && (!TB || al(g.B, g.ldb)) && (!TA || TB);
+  if (!TA && TB) {
+    if (vec) EG_LAUNCH((gemm_kernel<BM, BN, BKT, TM, TN, false, true, true>), grid, 256, 0, st, g);
+    else EG_LAUNCH((gemm_kernel<BM, BN, BKT, TM, TN, false, true, false>), grid, 256, 0, st, g);
+  } else if (!TA && !TB) {
+    if (vec) EG_LAUNCH((gemm_kernel<BM, BN, BKT, TM, TN, false, false, true>), grid, 256, 0, st, g);
+    else EG_LAUNCH((gemm_kernel<BM, BN, BKT, TM, TN, false, false, false>), grid, 256, 0, st, g);
+  } else if (TA && !TB) {
+    EG_LAUNCH((gemm_kernel<BM, BN, BKT, TM, TN, true, false, false>), grid, 256, 0, st, g);
+  } else {
+    EG_LAUNCH((gemm_kernel<BM, BN, BKT, TM, TN, true, true, false>), grid, 256, 0, st, g);
+  }
+  return EG_OK;
+}
+
+// 64x64x32 tiles with the k range split over a 2-CTA cluster (DSMEM reduction): for M <= 256 layers whose 64x64
+// tiling alone would leave half of the SMs idle. nn.Linear forward layout only (A row-major, W [out,in]).
+static int launch_gemm_splitk2(const GemmArgs& g, cudaStream_t st) {
+  auto al = [](const float* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0; };
+  const bool vec = (g.K & 3) == 0 && al(g.A, g.lda) && al(g.B, g.ldb);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((g.N + 63) / 64, (g.M + 63) / 64, 2);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 2;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = vec ? cudaLaunchKernelEx(&cfg, gemm_kernel<64, 64, 32, 4, 4, false, true, true, 2>, g)
+                      : cudaLaunchKernelEx(&cfg, gemm_kernel<64, 64, 32, 4, 4, false, true, false, 2>, g);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  EG_CUDA_CHECK(e);
   return EG_OK;
 }
 
 int launch_gemm(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return EG_OK;
   auto ctas = [&](int bm, int bn) { return (int64_t)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn); };
-  if (ctas(128, 64) >= kNumSMs) return launch_gemm_cfg<128, 64, 8, 4>(g, TA, TB, st);
-  if (ctas(64, 64) >= kNumSMs) return launch_gemm_cfg<64, 64, 4, 4>(g, TA, TB, st);
-  return launch_gemm_cfg<32, 32, 2, 2>(g, TA, TB, st);
+  if (!TA && TB && g.a_div == 1 && g.K >= 512 && ctas(64, 64) < kNumSMs * 3 / 4 && 2 * ctas(64, 64) >= kNumSMs / 2)
+    return launch_gemm_splitk2(g, st);
+  if (ctas(128, 64) >= kNumSMs) return launch_gemm_cfg<128, 64, 16, 8, 4>(g, TA, TB, st);
+  if (ctas(64, 64) >= kNumSMs) return launch_gemm_cfg<64, 64, 32, 4, 4>(g, TA, TB, st);
+  if (ctas(32, 64) >= kNumSMs * 3 / 4) return launch_gemm_cfg<32, 64, 32, 2, 4>(g, TA, TB, st);
+  return launch_gemm_cfg<32, 32, 32, 2, 2>(g, TA, TB, st);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -295,6 +403,11 @@ __device__ __forceinline__ void tile_gemm_splitk(const float* __restrict__ Wt, i
   }
 }
 
+__device__ __forceinline__ void cp_async16_nn(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+
 struct DecodeW {            // transposed weights of the 18-step decode loop
   const float *WyT, *WhhT, *W1T, *W2T, *WoT;      // [201][768] [256][768] [256][512] [512][256] [256][204]
   const float *bhh, *b1, *b2, *bo;
@@ -390,17 +503,43 @@ struct RegW {               // transposed regressor weights
   const float *WoT, *b_out;         // [128][160], [159]
 };
 
-// y[r][n] for a warp's RW rows: lanes own float4 column groups (n4 = lane, lane+32, ...)
-template <int RW>
-__device__ __forceinline__ void warp_rows_gemm(const float* __restrict__ Wt, int ldw, int K, int n4,
-                                               const float* xs, int ldx, float acc[RW][4]) {
-  const float4* wp = reinterpret_cast<const float4*>(Wt + 4 * n4);
+// ---- weight-chunk pipeline shared by the fused kernels: the whole ordered stream of weight chunks of a kernel is
+// described by a table in shared memory; chunk c+1 is fetched with cp.async (all threads) while chunk c is consumed.
+struct WChunk { const float* p; int rows; int ld; int pad; };
+
+struct ChunkPipe {
+  const WChunk* table; int n; float* buf; int buf_floats; int tid, nthreads; int next;
+  __device__ __forceinline__ void issue(int c) {
+    if (c < n) {
+      const WChunk ch = table[c];
+      const float4* src = reinterpret_cast<const float4*>(ch.p);
+      float4* dst = reinterpret_cast<float4*>(buf + (c & 1) * buf_floats);
+      const int n4 = ch.rows * ch.ld / 4;
+      for (int i = tid; i < n4; i += nthreads) cp_async16_nn(dst + i, src + i);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  // returns the shared-memory address of chunk c (rows x ld floats); call release() when done reading it
+  __device__ __forceinline__ const float* acquire(int c) {
+    issue(c + 1);
+    asm volatile("cp.async.wait_group 1;\n" ::);
+    __syncthreads();
+    return buf + (c & 1) * buf_floats;
+  }
+  __device__ __forceinline__ void release() { __syncthreads(); }
+};
+
+// acc[r][0..3] += sum_k x[r][k] * W[k][4 n4 .. 4 n4+3] for a warp's RW rows, weights from a shared-memory chunk
+template <int RW_>
+__device__ __forceinline__ void warp_rows_gemm_smem(const float* ws, int ldw, int K, int n4, const float* xs, int ldx,
+                                                    float acc[RW_][4]) {
+  const float4* wp = reinterpret_cast<const float4*>(ws) + n4;
   const int ldw4 = ldw >> 2;
-#pragma unroll 4
+#pragma unroll 8
   for (int k = 0; k < K; ++k) {
-    const float4 wv = __ldg(wp + (int64_t)k * ldw4);
+    const float4 wv = wp[k * ldw4];
 #pragma unroll
-    for (int r = 0; r < RW; ++r) {
+    for (int r = 0; r < RW_; ++r) {
       const float x = xs[r * ldx + k];
       acc[r][0] += x * wv.x; acc[r][1] += x * wv.y; acc[r][2] += x * wv.z; acc[r][3] += x * wv.w;
     }
@@ -408,12 +547,14 @@ __device__ __forceinline__ void warp_rows_gemm(const float* __restrict__ Wt, int
 }
 
 // Whole MoshRegressor._forward (3 recurrences x (in_fc + 10 residual blocks + out_fc)) for RR rows per CTA,
-// activations resident in shared memory (models_GAMMA_primitive.py:222-259, ResNetBlock :160-175).
+// activations resident in shared memory, weights streamed through a double-buffered shared-memory chunk pipeline
+// (models_GAMMA_primitive.py:222-259, ResNetBlock :160-175).
 constexpr int RR = 36, RWARPS = 9, RW = 4;
+constexpr int RCHUNK_ROWS = 64, RCHUNK_FLOATS = RCHUNK_ROWS * 160, RTABLE = 192;
 __global__ void __launch_bounds__(RWARPS * 32)
 fused_regressor_kernel(RegW w, const float* __restrict__ Yin, const float* __restrict__ betas, int betas_div, int M,
                        int n_blocks, int n_recur, float* __restrict__ xb_out) {
-  constexpr int HR = 128, D = 201, BD = 159, BD4 = 160, LDX = 204;
+  constexpr int HR = 128, D = 201, BD = 159, BD4 = 160, LDX = 204, NTH = RWARPS * 32;
   extern __shared__ __align__(16) float sm[];
   float* xr = sm;                   // [RR][LDX] markers
   float* be = xr + RR * LDX;        // [RR][12]
@@ -421,67 +562,84 @@ fused_regressor_kernel(RegW w, const float* __restrict__ Yin, const float* __res
   float* h = base + RR * HR;        // [RR][HR]
   float* t = h + RR * HR;           // [RR][HR]
   float* xb = t + RR * HR;          // [RR][BD4]
+  float* wbuf = xb + RR * BD4;      // 2 x RCHUNK_FLOATS
+  WChunk* table = reinterpret_cast<WChunk*>(wbuf + 2 * RCHUNK_FLOATS);
+  __shared__ int n_chunks_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * RR;
-  for (int i = tid; i < RR * LDX; i += RWARPS * 32) {
+  if (tid == 0) {                   // ordered stream of weight chunks for the whole forward pass
+    int n = 0;
+    auto add = [&](const float* p, int K, int ld) {
+      for (int k0 = 0; k0 < K; k0 += RCHUNK_ROWS) { table[n].p = p + (int64_t)k0 * ld; table[n].rows = min(RCHUNK_ROWS, K - k0); table[n].ld = ld; ++n; }
+    };
+    add(w.WaT, D, HR); add(w.WcT, 10, HR);
+    for (int rec = 0; rec < n_recur; ++rec) {
+      if (rec > 0) add(w.WbT, BD, HR);
+      for (int b = 0; b < n_blocks * 2; ++b) add(w.blkT + (int64_t)b * HR * HR, HR, HR);
+      add(w.WoT, HR, BD4);
+    }
+    n_chunks_s = n;
+  }
+  for (int i = tid; i < RR * LDX; i += NTH) {
     const int r = i / LDX, d = i % LDX, m = min(m0 + r, M - 1);
     xr[i] = d < D ? Yin[(int64_t)m * D + d] : 0.0f;
   }
-  for (int i = tid; i < RR * 12; i += RWARPS * 32) {
+  for (int i = tid; i < RR * 12; i += NTH) {
     const int r = i / 12, d = i % 12, m = min(m0 + r, M - 1);
     be[i] = d < 10 ? betas[(int64_t)(m / betas_div) * 10 + d] : 0.0f;
   }
-  for (int i = tid; i < RR * BD4; i += RWARPS * 32) xb[i] = 0.0f;
+  for (int i = tid; i < RR * BD4; i += NTH) xb[i] = 0.0f;
   __syncthreads();
+  ChunkPipe pipe{table, n_chunks_s, wbuf, RCHUNK_FLOATS, tid, NTH, 0};
+  pipe.issue(0);
+  int c = 0;
   const int r0 = warp * RW;
-  // base = markers Wa^T + betas Wc^T + b_in   (constant over the recurrences)
-  {
-    float acc[RW][4];
+  float acc[RW][4];
+  auto zero = [&]() {
 #pragma unroll
     for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
-    warp_rows_gemm<RW>(w.WaT, HR, D, lane, xr + r0 * LDX, LDX, acc);
-    warp_rows_gemm<RW>(w.WcT, HR, 10, lane, be + r0 * 12, 12, acc);
+  };
+  // acc += X[r0.., :K] W  with W streamed in chunks (N = 128 columns, lane owns 4)
+  auto stream_gemm = [&](const float* xs, int ldx, int K) {
+    for (int k0 = 0; k0 < K; k0 += RCHUNK_ROWS) {
+      const float* ws = pipe.acquire(c++);
+      warp_rows_gemm_smem<RW>(ws, HR, min(RCHUNK_ROWS, K - k0), lane, xs + r0 * ldx + k0, ldx, acc);
+      pipe.release();
+    }
+  };
+  // base = markers Wa^T + betas Wc^T + b_in   (constant over the recurrences)
+  zero();
+  stream_gemm(xr, LDX, D);
+  stream_gemm(be, 12, 10);
+  {
     const float4 bb = __ldg(reinterpret_cast<const float4*>(w.b_in) + lane);
 #pragma unroll
     for (int r = 0; r < RW; ++r)
       *reinterpret_cast<float4*>(base + (r0 + r) * HR + 4 * lane) =
           make_float4(acc[r][0] + bb.x, acc[r][1] + bb.y, acc[r][2] + bb.z, acc[r][3] + bb.w);
   }
-  __syncwarp();     // every warp only ever touches its own RW rows: no block-level barriers below
   for (int rec = 0; rec < n_recur; ++rec) {
-    {   // h = base (+ xb Wb^T)
-      float acc[RW][4];
+    zero();
+    if (rec > 0) stream_gemm(xb, BD4, BD);            // h = base + xb Wb^T
 #pragma unroll
-      for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
-      if (rec > 0) warp_rows_gemm<RW>(w.WbT, HR, BD, lane, xb + r0 * BD4, BD4, acc);
-#pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        const float4 bv = *reinterpret_cast<const float4*>(base + (r0 + r) * HR + 4 * lane);
-        *reinterpret_cast<float4*>(h + (r0 + r) * HR + 4 * lane) =
-            make_float4(acc[r][0] + bv.x, acc[r][1] + bv.y, acc[r][2] + bv.z, acc[r][3] + bv.w);
-      }
-      __syncwarp();
+    for (int r = 0; r < RW; ++r) {
+      const float4 bv = *reinterpret_cast<const float4*>(base + (r0 + r) * HR + 4 * lane);
+      *reinterpret_cast<float4*>(h + (r0 + r) * HR + 4 * lane) =
+          make_float4(acc[r][0] + bv.x, acc[r][1] + bv.y, acc[r][2] + bv.z, acc[r][3] + bv.w);
     }
     for (int blk = 0; blk < n_blocks; ++blk) {
-      const float* W0 = w.blkT + (int64_t)(blk * 2) * HR * HR;
-      const float* W1 = W0 + HR * HR;
       const float* B0 = w.blk_b + (blk * 2) * HR;
-      float acc[RW][4];
-#pragma unroll
-      for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
-      warp_rows_gemm<RW>(W0, HR, HR, lane, h + r0 * HR, HR, acc);
+      zero();
+      stream_gemm(h, HR, HR);                          // (the barriers inside order the smem hand-offs)
       float4 bb = __ldg(reinterpret_cast<const float4*>(B0) + lane);
 #pragma unroll
       for (int r = 0; r < RW; ++r)
         *reinterpret_cast<float4*>(t + (r0 + r) * HR + 4 * lane) =
             make_float4(fmaxf(acc[r][0] + bb.x, 0.f), fmaxf(acc[r][1] + bb.y, 0.f), fmaxf(acc[r][2] + bb.z, 0.f),
                         fmaxf(acc[r][3] + bb.w, 0.f));
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
-      warp_rows_gemm<RW>(W1, HR, HR, lane, t + r0 * HR, HR, acc);
+      zero();
+      stream_gemm(t, HR, HR);
       bb = __ldg(reinterpret_cast<const float4*>(B0 + HR) + lane);
-      __syncwarp();
 #pragma unroll
       for (int r = 0; r < RW; ++r) {
         float4* hp = reinterpret_cast<float4*>(h + (r0 + r) * HR + 4 * lane);
@@ -489,22 +647,28 @@ fused_regressor_kernel(RegW w, const float* __restrict__ Yin, const float* __res
         *hp = make_float4(fmaxf(acc[r][0] + bb.x, 0.f) + hv.x, fmaxf(acc[r][1] + bb.y, 0.f) + hv.y,
                           fmaxf(acc[r][2] + bb.z, 0.f) + hv.z, fmaxf(acc[r][3] + bb.w, 0.f) + hv.w);
       }
-      __syncwarp();
     }
-    // xb += h Wout^T + b_out  (159 outputs = 40 float4 groups: lanes 0..31 then 0..7)
-    for (int n4 = lane; n4 < BD4 / 4; n4 += 32) {
-      float acc[RW][4];
+    // xb += h Wout^T + b_out  (159 outputs = 40 float4 groups: lanes 0..31, then lanes 0..7 again)
+    float acc2[RW][4];
+    zero();
 #pragma unroll
-      for (int r = 0; r < RW; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
-      warp_rows_gemm<RW>(w.WoT, BD4, HR, n4, h + r0 * HR, HR, acc);
-#pragma unroll
-      for (int r = 0; r < RW; ++r)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = 4 * n4 + j;
-          if (n < BD) xb[(r0 + r) * BD4 + n] += acc[r][j] + __ldg(w.b_out + n);
-        }
+    for (int r = 0; r < RW; ++r) acc2[r][0] = acc2[r][1] = acc2[r][2] = acc2[r][3] = 0.0f;
+    for (int k0 = 0; k0 < HR; k0 += RCHUNK_ROWS) {
+      const float* ws = pipe.acquire(c++);
+      warp_rows_gemm_smem<RW>(ws, BD4, min(RCHUNK_ROWS, HR - k0), lane, h + r0 * HR + k0, HR, acc);
+      if (lane < BD4 / 4 - 32)
+        warp_rows_gemm_smem<RW>(ws, BD4, min(RCHUNK_ROWS, HR - k0), lane + 32, h + r0 * HR + k0, HR, acc2);
+      pipe.release();
     }
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = 4 * lane + j;
+        xb[(r0 + r) * BD4 + n] += acc[r][j] + __ldg(w.b_out + n);
+        const int n2 = 4 * (lane + 32) + j;
+        if (lane < BD4 / 4 - 32 && n2 < BD) xb[(r0 + r) * BD4 + n2] += acc2[r][j] + __ldg(w.b_out + n2);
+      }
     __syncwarp();
   }
   for (int i = lane; i < RW * BD; i += 32) {
@@ -618,7 +782,7 @@ static size_t decode_smem(const EgMotionDims& d) {
   const int H = d.h_dim, H3 = 3 * H, D4 = (d.in_dim + 3) & ~3, Hm = d.mlp_dim;
   return sizeof(float) * ((size_t)DR * (H3 + H + D4 + Hm + H) + (size_t)2 * 8 * DR * H3);
 }
-constexpr size_t kRegSmem = sizeof(float) * RR * (204 + 12 + 128 * 3 + 160);
+constexpr size_t kRegSmem = sizeof(float) * (RR * (204 + 12 + 128 * 3 + 160) + 2 * RCHUNK_FLOATS) + sizeof(WChunk) * RTABLE;
 
 extern "C" int eg_motion_create(const EgMotionDims* dims, const void* const* weights_host, int n_weights,
                                 int device, EgMotion** out) {
