@@ -377,16 +377,17 @@ __device__ __forceinline__ void tile_gemm_splitk(const float* __restrict__ Wt, i
     const float4* wp = reinterpret_cast<const float4*>(Wt + 4 * n4);
     const int ldw4 = ldw >> 2;
     int k = k0;
-    for (; k + 4 <= k1; k += 4) {
-      const float4 w0 = __ldg(wp + (int64_t)(k + 0) * ldw4), w1 = __ldg(wp + (int64_t)(k + 1) * ldw4);
-      const float4 w2 = __ldg(wp + (int64_t)(k + 2) * ldw4), w3 = __ldg(wp + (int64_t)(k + 3) * ldw4);
+    for (; k + 8 <= k1; k += 8) {                      // 8 independent 128-bit weight loads in flight per thread
+      float4 wv[8];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float x0 = xs[r * ldx + k], x1 = xs[r * ldx + k + 1], x2 = xs[r * ldx + k + 2], x3 = xs[r * ldx + k + 3];
-        acc[r][0] += x0 * w0.x; acc[r][1] += x0 * w0.y; acc[r][2] += x0 * w0.z; acc[r][3] += x0 * w0.w;
-        acc[r][0] += x1 * w1.x; acc[r][1] += x1 * w1.y; acc[r][2] += x1 * w1.z; acc[r][3] += x1 * w1.w;
-        acc[r][0] += x2 * w2.x; acc[r][1] += x2 * w2.y; acc[r][2] += x2 * w2.z; acc[r][3] += x2 * w2.w;
-        acc[r][0] += x3 * w3.x; acc[r][1] += x3 * w3.y; acc[r][2] += x3 * w3.z; acc[r][3] += x3 * w3.w;
+      for (int u = 0; u < 8; ++u) wv[u] = __ldg(wp + (int64_t)(k + u) * ldw4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float x = xs[r * ldx + k + u];
+          acc[r][0] += x * wv[u].x; acc[r][1] += x * wv[u].y; acc[r][2] += x * wv[u].z; acc[r][3] += x * wv[u].w;
+        }
       }
     }
     for (; k < k1; ++k) {
@@ -416,7 +417,7 @@ struct DecodeW {            // transposed weights of the 18-step decode loop
 // 18 GRUCell + MLP steps for DR rows per CTA (models_GAMMA_primitive.py:91-99). h0 = drnn_mlp(hx) and the
 // step-invariant input term c = [hx,z] W_ih[:, :384]^T + b_ih are computed beforehand by the layer kernels.
 constexpr int DR = 2;
-constexpr int DEC_THREADS = 256;
+constexpr int DEC_THREADS = 384;
 __global__ void __launch_bounds__(DEC_THREADS)
 fused_decode_kernel(DecodeW w, const float* __restrict__ c_in, const float* __restrict__ h_in, float* __restrict__ Y,
                     int B, int D, int H, int Hm) {
