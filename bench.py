@@ -129,8 +129,11 @@ def run_ours(args):
     col.reset()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    last = {}
+
     def iteration(c):
         batch, _ = c.collect(STEP_PER_COLLECT)
+        last["batch"] = batch
         return pol.learn(batch, BATCH, 1)
 
     def timed(c, k, profile):
@@ -187,6 +190,9 @@ def run_ours(args):
     e2e = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": col2.h2d_bytes // args.steps,
            "d2h_bytes_per_step": (col2.d2h_bytes + 5 * 8 * 4) // args.steps}
 
+    # sanity (outside every timed region): the rollouts and the updated policy are finite
+    assert bool(torch.isfinite(last["batch"].returns).all()) and bool(torch.isfinite(pol.flat_params).all()), \
+        "non-finite values after the timed iterations"
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()

@@ -64,35 +64,36 @@ class BoxSceneSampler:
 
     def seed(self, s: int):
         self.gen.manual_seed(int(s))
+        self._pool = None
 
     def _free_xy(self, n):
-        """n points whose column above the floor is at least 0.5 m from any obstacle."""
+        """n points whose column above the floor is at least 0.6 m from any obstacle (one host sync per call)."""
         out = torch.empty(0, 2, device=self.dev)
         while out.shape[0] < n:
-            xy = (torch.rand(4 * n + 64, 2, device=self.dev, generator=self.gen) * 2 - 1) * (self.fh - 0.8)
+            xy = (torch.rand(2 * n + 64, 2, device=self.dev, generator=self.gen) * 2 - 1) * (self.fh - 0.8)
             pts = torch.cat([xy, torch.full((xy.shape[0], 1), 0.9, device=self.dev)], dim=1)
             d = calc_sdf(pts.unsqueeze(0), self.sdf)[0]
             out = torch.cat([out, xy[d > 0.6]], dim=0)
         return out[:n]
 
-    def next_body(self, n: int):
+    def _refill(self, n):
+        """Pre-generate a pool of n candidates entirely on the device so that next_body() is sync-free slicing."""
         dev = self.dev
-        start = self._free_xy(n)
-        goal = self._free_xy(n)
+        start, goal = self._free_xy(n), self._free_xy(n)
         for _ in range(8):
             bad = (goal - start).norm(dim=1) < self.min_goal
-            if not bad.any():
+            nb = int(bad.sum())
+            if nb == 0:
                 break
-            goal[bad] = self._free_xy(int(bad.sum()))
+            goal[bad] = self._free_xy(nb)
         yaw = torch.rand(n, device=dev, generator=self.gen) * (2 * np.pi)
-        # global_orient = Rz(yaw) Rx(pi/2) as axis-angle
+        # global_orient = Rz(yaw) Rx(pi/2) as axis-angle via the quaternion product qz(yaw) * qx(pi/2)
+        # (w = cos(yaw/2) / sqrt 2 stays away from +-1, so the log map is well conditioned)
+        ch, sh, r = torch.cos(yaw / 2), torch.sin(yaw / 2), 0.5 ** 0.5
+        q = torch.stack([ch * r, ch * r, sh * r, sh * r], dim=1)          # (w, x, y, z)
+        ang = 2 * torch.acos(q[:, 0].clamp(-1, 1))
+        aa = q[:, 1:] / torch.sin(ang / 2).unsqueeze(1) * ang.unsqueeze(1)
         cy, sy = torch.cos(yaw), torch.sin(yaw)
-        R = torch.zeros(n, 3, 3, device=dev)
-        R[:, 0, 0] = cy; R[:, 0, 2] = sy
-        R[:, 1, 0] = sy; R[:, 1, 2] = -cy
-        R[:, 2, 1] = 1.0
-        from scipy.spatial.transform import Rotation
-        aa = torch.as_tensor(Rotation.from_matrix(R.cpu().numpy()).as_rotvec(), dtype=torch.float32, device=dev)
         wp = torch.zeros(n, 2, 93, device=dev)
         pose = torch.randn(n, 63, device=dev, generator=self.gen) * self.pose_noise
         fwd = torch.stack([sy, -cy], dim=1)                       # template forward (+z) after the rotation
@@ -102,7 +103,16 @@ class BoxSceneSampler:
             wp[:, t, 3:6] = aa
             wp[:, t, 6:69] = pose
         goals = torch.cat([goal, torch.full((n, 1), self.pelvis_h, device=dev)], dim=1)
-        return dict(world_params=wp, goals=goals, betas=torch.zeros(n, 10, device=dev), gender="male")
+        self._pool = dict(world_params=wp, goals=goals, betas=torch.zeros(n, 10, device=dev))
+        self._ptr = 0
+
+    def next_body(self, n: int):
+        if getattr(self, "_pool", None) is None or self._ptr + n > self._pool["goals"].shape[0]:
+            self._refill(max(4096, 4 * n))
+        a, b = self._ptr, self._ptr + n
+        self._ptr = b
+        return dict(world_params=self._pool["world_params"][a:b], goals=self._pool["goals"][a:b],
+                    betas=self._pool["betas"][a:b], gender="male")
 
 
 class CrowdVectorEnv:

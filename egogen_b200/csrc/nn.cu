@@ -235,9 +235,9 @@ static int launch_gemm_cfg(const GemmArgs& g, bool TA, bool TB, cudaStream_t st)
 
 // 64x64x32 tiles with the k range split over a 2-CTA cluster (DSMEM reduction): for M <= 256 layers whose 64x64
 // tiling alone would leave half of the SMs idle. nn.Linear forward layout only (A row-major, W [out,in]).
-static int launch_gemm_splitk2(const GemmArgs& g, cudaStream_t st) {
+static int launch_gemm_splitk2(const GemmArgs& g, bool TB, cudaStream_t st) {
   auto al = [](const float* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0; };
-  const bool vec = (g.K & 3) == 0 && al(g.A, g.lda) && al(g.B, g.ldb);
+  const bool vec = (g.K & 3) == 0 && al(g.A, g.lda) && (!TB || al(g.B, g.ldb));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((g.N + 63) / 64, (g.M + 63) / 64, 2);
   cfg.blockDim = dim3(256);
@@ -247,8 +247,11 @@ static int launch_gemm_splitk2(const GemmArgs& g, cudaStream_t st) {
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 2;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = vec ? cudaLaunchKernelEx(&cfg, gemm_kernel<64, 64, 32, 4, 4, false, true, true, 2>, g)
-                      : cudaLaunchKernelEx(&cfg, gemm_kernel<64, 64, 32, 4, 4, false, true, false, 2>, g);
+  cudaError_t e;
+  if (TB) e = vec ? cudaLaunchKernelEx(&cfg, gemm_kernel<64, 64, 32, 4, 4, false, true, true, 2>, g)
+                  : cudaLaunchKernelEx(&cfg, gemm_kernel<64, 64, 32, 4, 4, false, true, false, 2>, g);
+  else e = vec ? cudaLaunchKernelEx(&cfg, gemm_kernel<64, 64, 32, 4, 4, false, false, true, 2>, g)
+               : cudaLaunchKernelEx(&cfg, gemm_kernel<64, 64, 32, 4, 4, false, false, false, 2>, g);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   EG_CUDA_CHECK(e);
   return EG_OK;
@@ -257,9 +260,11 @@ static int launch_gemm_splitk2(const GemmArgs& g, cudaStream_t st) {
 int launch_gemm(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return EG_OK;
   auto ctas = [&](int bm, int bn) { return (int64_t)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn); };
-  if (!TA && TB && g.a_div == 1 && g.K >= 512 && ctas(64, 64) < kNumSMs * 3 / 4 && 2 * ctas(64, 64) >= kNumSMs / 2)
-    return launch_gemm_splitk2(g, st);
-  if (ctas(128, 64) >= kNumSMs) return launch_gemm_cfg<128, 64, 16, 8, 4>(g, TA, TB, st);
+  if (!TA && g.a_div == 1 && g.K >= 512 && ctas(64, 64) < kNumSMs * 3 / 4 && 2 * ctas(64, 64) >= kNumSMs / 2)
+    return launch_gemm_splitk2(g, TB, st);
+  // wave quantisation: a grid of 149..236 big tiles runs a nearly empty second wave; prefer the smaller tile then
+  auto wave_eff = [&](int64_t c) { return (double)c / (double)(((c + kNumSMs - 1) / kNumSMs) * kNumSMs); };
+  if (ctas(128, 64) >= kNumSMs && wave_eff(ctas(128, 64)) >= 0.8) return launch_gemm_cfg<128, 64, 16, 8, 4>(g, TA, TB, st);
   if (ctas(64, 64) >= kNumSMs) return launch_gemm_cfg<64, 64, 32, 4, 4>(g, TA, TB, st);
   if (ctas(32, 64) >= kNumSMs * 3 / 4) return launch_gemm_cfg<32, 64, 32, 2, 4>(g, TA, TB, st);
   return launch_gemm_cfg<32, 32, 32, 2, 2>(g, TA, TB, st);
