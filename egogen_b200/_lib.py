@@ -44,7 +44,8 @@ class EgEnvConfig(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("finetuning", C.c_int32), ("pene_terminate_count", C.c_int32),
                 ("feet_marker_idx", C.c_int32 * 6), ("reproj_factor", C.c_float), ("goal_thresh", C.c_float)] + \
                [(n, C.c_float) for n in ("w_skate", "w_floor", "w_face", "w_look", "w_success", "w_dist",
-                                         "w_vp", "w_pene", "ray_len")]
+                                         "w_vp", "w_pene", "ray_len")] + \
+               [("pene_mode", C.c_int32), ("map_res", C.c_int32), ("map_extent", C.c_float), ("pene_thres", C.c_float)]
 
 
 ENV_BUFFER_FIELDS = ("state", "seed", "R0", "T0", "betas", "dist", "steps", "goal", "ego", "obs_dist",
@@ -90,6 +91,7 @@ PROTOTYPES = {
     "eg_env_destroy": (None, [_P]),
     "eg_env_set_config": (_I, [_P, C.POINTER(EgEnvConfig)]),
     "eg_env_set_scene": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _I]),
+    "eg_env_set_navmesh": (_I, [_P, _P, _I]),
     "eg_env_step": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P]),
     "eg_env_reset": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
     "eg_policy_param_count": (_L, [C.POINTER(EgPolicyDims), C.POINTER(C.c_int64)]),

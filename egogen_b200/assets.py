@@ -300,6 +300,27 @@ def scene_polygon(scene: dict):
     return rings
 
 
+def scene_navmesh_triangles(scene: dict) -> np.ndarray:
+    """Walkable-floor triangles [F,3,2] of a box scene - the role of the reference's navmesh_tight.ply /
+    per-scene navmesh (`navmesh.vertices[navmesh.faces, :2]`, batch_gen_amass.py:948-950): the floor square is cut along
+    every box edge and each cell that no box footprint covers becomes two triangles."""
+    fh = scene["floor_half"]
+    xs, ys = {-fh, fh}, {-fh, fh}
+    for b in scene["boxes"]:
+        xs.update([float(np.clip(b[0], -fh, fh)), float(np.clip(b[3], -fh, fh))])
+        ys.update([float(np.clip(b[1], -fh, fh)), float(np.clip(b[4], -fh, fh))])
+    xs, ys = sorted(xs), sorted(ys)
+    tris = []
+    for x0, x1 in zip(xs[:-1], xs[1:]):
+        for y0, y1 in zip(ys[:-1], ys[1:]):
+            cx, cy = 0.5 * (x0 + x1), 0.5 * (y0 + y1)
+            if any(b[0] < cx < b[3] and b[1] < cy < b[4] for b in scene["boxes"]):
+                continue
+            tris.append([[x0, y0], [x1, y0], [x1, y1]])
+            tris.append([[x0, y0], [x1, y1], [x0, y1]])
+    return np.asarray(tris, np.float32)
+
+
 def rings_to_segments(rings):
     """Flatten closed rings to a [S,4] float64 array of boundary segments (x0,y0,x1,y1)."""
     segs = []

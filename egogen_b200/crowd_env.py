@@ -34,6 +34,16 @@ def default_cfg(finetuning: bool = False):
         args=SimpleNamespace(gpu_index=0, random_seed=0))
 
 
+def default_cfg_box():
+    """MPVAEPolicy_samp_collision_2.yaml (box-scene env): look-target weight 0.1, max_depth 11, map 16 x 16 @ 0.8 m."""
+    c = default_cfg()
+    c.lossconfig.weight_look_target = 0.1
+    c.lossconfig.pene_type = "body"
+    c.trainconfig.max_depth = 11
+    c.modelconfig.map_res, c.modelconfig.map_extent = 16, 0.8
+    return c
+
+
 def load_cfg(path: str):
     """Read the reference's policy yaml (OmegaConf in the reference, primitive_model.py:78-82)."""
     import yaml
@@ -121,8 +131,11 @@ class CrowdVectorEnv:
 
     def __init__(self, cfg, motion_model, lbs_model, vposer, scene_sdf: dict, scene_rings, sampler,
                  n_envs: int, device, feet_marker_idx=None, finetuning: bool = False,
-                 capture_rollout: bool = False, debug_terms: bool = False):
+                 capture_rollout: bool = False, debug_terms: bool = False, box_mode: bool = False, navmesh_tris=None):
+        """box_mode=True selects the reference's crowd_env_2f_box.CrowdEnv semantics (2-D walkability-map penetration over
+        ``navmesh_tris`` [F,3,2], penetration always terminates, weight_pene from the cfg); default is crowd_env_2f.CrowdEnv."""
         self.cfg, self.E, self.dev = cfg, int(n_envs), torch.device(device)
+        self.box_mode = bool(box_mode)
         self.motion, self.lbs, self.vposer, self.sampler = motion_model, lbs_model, vposer, sampler
         self.finetuning = bool(finetuning)
         self.feet_marker_idx = list(feet_marker_idx if feet_marker_idx is not None else assets.feet_marker_idx())
@@ -144,16 +157,24 @@ class CrowdVectorEnv:
         _lib.check(_lib.lib().eg_env_create(C.byref(self._config()), lbs_model._h, motion_model.handle(),
                                             vposer.handle(), idx, C.byref(self._h)))
         self.set_scene(scene_sdf, scene_rings)
+        if self.box_mode:
+            if navmesh_tris is None:
+                raise _lib.EgError("box_mode needs navmesh_tris [F,3,2]")
+            self._tris = torch.as_tensor(np.asarray(navmesh_tris), dtype=torch.float32, device=self.dev).contiguous()
+            _lib.check(_lib.lib().eg_env_set_navmesh(self._h, _lib.ptr(self._tris), self._tris.shape[0]))
         self.action_dim = 128
 
     def _config(self):
         c, l, t = self.cfg.modelconfig, self.cfg.lossconfig, self.cfg.trainconfig
         w_pene = 0.1 if self.finetuning else 1.0                    # crowd_env_2f.py:268-271
+        if self.box_mode:
+            w_pene = float(l.weight_pene)                           # crowd_env_2f_box.py:226
         return _lib.EgEnvConfig(int(t.max_depth), int(self.finetuning), 40, (C.c_int32 * 6)(*self.feet_marker_idx),
                                 float(c.reproj_factor), float(t.goal_thresh), float(l.weight_skate),
                                 float(l.weight_floor), float(l.weight_face_target), float(l.weight_look_target),
                                 float(l.weight_success), float(l.weight_target_dist), float(l.weight_vp),
-                                w_pene, 7.0)
+                                w_pene, 7.0, int(self.box_mode), int(getattr(c, "map_res", 16)),
+                                float(getattr(c, "map_extent", 0.8)), float(getattr(t, "pene_thres", 3)))
 
     def set_scene(self, scene_sdf, scene_rings):
         dev = self.dev

@@ -28,6 +28,8 @@ struct StepArgs {
   const float* mproj;      // [E,20,67,3]
   const float* vp_loc;     // [E,20,32]
   const float* pelvis_rest;// [E,3]
+  const float* tris;       // [n_tris,3,2] navmesh (pene_mode 1)
+  int n_tris;
 };
 
 __device__ __forceinline__ float norm3_clip(float x, float y, float z) {
@@ -78,12 +80,70 @@ __device__ __forceinline__ void write_state_marker(float* st, int p, const float
   st[201 + p * 3 + 0] = fx / d; st[201 + p * 3 + 1] = fy / d; st[201 + p * 3 + 2] = fz / d;
 }
 
+// torch.linspace(-extent, extent, res)[i] in fp32 (symmetric evaluation like ATen's kernel)
+__device__ __forceinline__ float linspace_sym(float extent, int res, int i) {
+  const float step = (extent - (-extent)) / (float)(res - 1);
+  return i < res / 2 ? -extent + step * (float)i : extent - step * (float)(res - 1 - i);
+}
+
+// 2-D penetration of crowd_env_2f_box.py:279-295 + get_map (batch_gen_amass.py:934-968) for one env; called by all
+// threads of the CTA. ms_xy: the markers of the 2-frame seed in the (new) local frame, [n_pts][2] in shared memory.
+// Returns the number of local-map cells inside the markers' bounding box that no navmesh triangle covers.
+__device__ float map_penetration(const float* Rl, const float* Tl, const float* ms_xy, int n_pts, const float* tris,
+                                 int n_tris, int res, float extent, float* red /* shared, >= 8 floats */) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = tid; i < n_pts; i += nth) {
+    mnx = fminf(mnx, ms_xy[2 * i]); mxx = fmaxf(mxx, ms_xy[2 * i]);
+    mny = fminf(mny, ms_xy[2 * i + 1]); mxy = fmaxf(mxy, ms_xy[2 * i + 1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  __shared__ float bb[8][4];
+  if ((tid & 31) == 0) { bb[tid >> 5][0] = mnx; bb[tid >> 5][1] = mny; bb[tid >> 5][2] = mxx; bb[tid >> 5][3] = mxy; }
+  __syncthreads();
+  mnx = mny = INFINITY; mxx = mxy = -INFINITY;
+  for (int w = 0; w < (nth >> 5); ++w) {
+    mnx = fminf(mnx, bb[w][0]); mny = fminf(mny, bb[w][1]); mxx = fmaxf(mxx, bb[w][2]); mxy = fmaxf(mxy, bb[w][3]);
+  }
+  float cnt = 0.0f;
+  for (int p = tid; p < res * res; p += nth) {
+    const float lx = linspace_sym(extent, res, p / res), ly = linspace_sym(extent, res, p % res);   // meshgrid 'ij'
+    const bool in_box = lx >= mnx && ly >= mny && lx <= mxx && ly <= mxy;
+    if (!in_box) continue;
+    const float wx = (Rl[0] * lx + Rl[1] * ly + Rl[2] * 0.0f) + Tl[0];
+    const float wy = (Rl[3] * lx + Rl[4] * ly + Rl[5] * 0.0f) + Tl[1];
+    bool walkable = false;
+    for (int f = 0; f < n_tris && !walkable; ++f) {
+      const float* t = tris + f * 6;
+      const float d1 = (wx - t[2]) * (t[1] - t[3]) - (t[0] - t[2]) * (wy - t[3]);
+      const float d2 = (wx - t[4]) * (t[3] - t[5]) - (t[2] - t[4]) * (wy - t[5]);
+      const float d3 = (wx - t[0]) * (t[5] - t[1]) - (t[4] - t[0]) * (wy - t[1]);
+      const bool has_neg = d1 < 0.f || d2 < 0.f || d3 < 0.f, has_pos = d1 > 0.f || d2 > 0.f || d3 > 0.f;
+      walkable = !(has_neg && has_pos);
+    }
+    cnt += walkable ? 0.0f : 1.0f;              // inside * (1 - map) * 0.5 with map = +1 / -1
+  }
+  cnt = warp_sum(cnt);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = cnt;
+  __syncthreads();
+  float total = 0.0f;
+  for (int w = 0; w < (nth >> 5); ++w) total += red[w];
+  __syncthreads();
+  return total;
+}
+
 __global__ void __launch_bounds__(256)
 env_reward_recanon_kernel(const StepArgs a) {
   const int e = blockIdx.x, tid = threadIdx.x;
   __shared__ float mb[NT * NM * 3];
   __shared__ float s_skate[18], s_floor[NT], s_vp[NT];
   __shared__ float Rn[9], Tn[3], R0n[9], T0n[3], goal_l2[3], delta[3];
+  __shared__ float sc[12], ms_xy[2 * NM * 2], red[8];
   const EgEnvConfig& c = a.cfg;
   const float* R0 = a.b.R0 + (int64_t)e * 9;
   const float* T0 = a.b.T0 + (int64_t)e * 3;
@@ -131,7 +191,8 @@ env_reward_recanon_kernel(const StepArgs a) {
 
   if (tid == 0) {
     int total = 0, mx = 0;
-    for (int t = 0; t < NT; ++t) { const int v = a.counts[e * NT + t]; total += v; mx = max(mx, v); }
+    if (c.pene_mode == 0)
+      for (int t = 0; t < NT; ++t) { const int v = a.counts[e * NT + t]; total += v; mx = max(mx, v); }
     const float num_inside = (float)total / (float)NT / 10.0f;
     const float r_pene = expf(-num_inside);
     const bool penetration = mx >= c.pene_terminate_count;
@@ -166,23 +227,11 @@ env_reward_recanon_kernel(const StepArgs a) {
     const float dist2 = norm3_clip(tl[0] - je[0], tl[1] - je[1], tl[2] - je[2]);
     const float r_dist = a.b.dist[e] - dist2;
     const float r_goal = dist2 < c.goal_thresh ? 1.0f : 0.0f;
-    float reward = r_skate * c.w_skate + r_floor * c.w_floor;
-    reward += r_face * c.w_face;
-    reward += r_look * c.w_look;
-    reward += r_goal * c.w_success;
-    reward += r_dist * c.w_dist;
-    reward += r_pene * c.w_pene;
-    reward += r_vp * c.w_vp;
+    // reward sum / termination are finalised after the re-canonicalisation (the box-scene penetration model
+    // needs the seed markers in the NEW frame); stash the terms
+    sc[0] = r_skate; sc[1] = r_floor; sc[2] = r_face; sc[3] = r_look; sc[4] = r_goal; sc[5] = r_dist; sc[6] = r_pene;
+    sc[7] = r_vp; sc[8] = penetration ? 1.0f : 0.0f;
     const int steps = a.b.steps[e] + 1;
-    const bool term = (r_goal > 0.0f) || (steps == c.max_depth) || (c.finetuning && penetration);
-    a.b.reward[e] = reward;
-    a.b.terminated[e] = term ? 1 : 0;
-    if (a.b.goal_reached) a.b.goal_reached[e] = r_goal > 0.0f ? 1 : 0;
-    if (a.b.reward_terms) {
-      float* rt = a.b.reward_terms + (int64_t)e * 8;
-      rt[0] = r_skate; rt[1] = r_floor; rt[2] = r_face; rt[3] = r_look; rt[4] = r_goal; rt[5] = r_dist;
-      rt[6] = r_pene; rt[7] = r_vp;
-    }
     a.b.dist[e] = dist2;
     a.b.steps[e] = steps;
     a.b.obs_dist[e] = 1.0f / (dist2 + 1.0f);
@@ -222,6 +271,35 @@ env_reward_recanon_kernel(const StepArgs a) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) ml[q] = Rn[0 * 3 + q] * d0 + Rn[1 * 3 + q] * d1 + Rn[2 * 3 + q] * d2;
     write_state_marker(a.b.state + ((int64_t)e * 2 + k) * 402, p, ml, goal_l2);
+    ms_xy[2 * i] = ml[0]; ms_xy[2 * i + 1] = ml[1];
+  }
+  __syncthreads();
+  float num_pene = 0.0f;
+  if (c.pene_mode == 1) num_pene = map_penetration(R0n, T0n, ms_xy, 2 * NM, a.tris, a.n_tris, c.map_res, c.map_extent, red);
+  if (tid == 0) {
+    float r_pene = sc[6];
+    bool penetration = sc[8] != 0.0f;
+    if (c.pene_mode == 1) {                     // crowd_env_2f_box.py:292-295
+      penetration = num_pene > c.pene_thres;
+      r_pene = penetration ? 0.0f : 0.05f;
+    }
+    float reward = sc[0] * c.w_skate + sc[1] * c.w_floor;
+    reward += sc[2] * c.w_face;
+    reward += sc[3] * c.w_look;
+    reward += sc[4] * c.w_success;
+    reward += sc[5] * c.w_dist;
+    reward += r_pene * c.w_pene;
+    reward += sc[7] * c.w_vp;
+    const int steps = a.b.steps[e];             // already incremented above
+    const bool term = (sc[4] > 0.0f) || (steps == c.max_depth) ||
+                      ((c.finetuning || c.pene_mode == 1) && penetration);   // box env always terminates on penetration (:325)
+    a.b.reward[e] = reward;
+    a.b.terminated[e] = term ? 1 : 0;
+    if (a.b.goal_reached) a.b.goal_reached[e] = sc[4] > 0.0f ? 1 : 0;
+    if (a.b.reward_terms) {
+      float* rt = a.b.reward_terms + (int64_t)e * 8;
+      rt[0] = sc[0]; rt[1] = sc[1]; rt[2] = sc[2]; rt[3] = sc[3]; rt[4] = sc[4]; rt[5] = sc[5]; rt[6] = r_pene; rt[7] = sc[7];
+    }
   }
 }
 
@@ -252,9 +330,21 @@ env_reset_commit_kernel(EgEnvBuffers b, const int32_t* __restrict__ env_ids, int
                         const float* __restrict__ T0c, const float* __restrict__ seedc,
                         const float* __restrict__ joints_c, const float* __restrict__ markers_c,
                         const float* __restrict__ goals, const float* __restrict__ betas_c,
-                        int32_t* __restrict__ accept) {
+                        int32_t* __restrict__ accept, EgEnvConfig cfg, const float* __restrict__ tris, int n_tris) {
   const int i = blockIdx.x, tid = threadIdx.x;
-  const bool ok = (counts[i * 2] + counts[i * 2 + 1]) == 0;
+  __shared__ float ms_xy[2 * NM * 2], red[8];
+  bool ok;
+  if (cfg.pene_mode == 1) {                     // crowd_env_2f_box.py reset: start pose must not cover unwalkable cells
+    for (int q = tid; q < 2 * NM; q += blockDim.x) {
+      ms_xy[2 * q] = markers_c[((int64_t)i * 2 * NM + q) * 3];
+      ms_xy[2 * q + 1] = markers_c[((int64_t)i * 2 * NM + q) * 3 + 1];
+    }
+    __syncthreads();
+    ok = map_penetration(R0c + (int64_t)i * 9, T0c + (int64_t)i * 3, ms_xy, 2 * NM, tris, n_tris, cfg.map_res,
+                         cfg.map_extent, red) == 0.0f;
+  } else {
+    ok = (counts[i * 2] + counts[i * 2 + 1]) == 0;
+  }
   if (tid == 0) accept[i] = ok ? 1 : 0;
   if (!ok) return;
   const int e = env_ids[i];
@@ -359,6 +449,7 @@ struct EgEnv {
   const float *center = nullptr, *scale = nullptr;
   const uint8_t* skip = nullptr;
   const double* segs = nullptr; int S = 0;
+  const float* tris = nullptr; int n_tris = 0;
   // workspace
   int cap = 0;
   float *Y = nullptr, *params = nullptr, *joints = nullptr, *mproj = nullptr, *vp = nullptr, *prest = nullptr;
@@ -423,6 +514,12 @@ extern "C" int eg_env_set_scene(EgEnv* h, const float* grid, int D0, int D1, int
   return eg_sdf_prepare(grid, D0, D1, D2, nullptr);   // conservative coarse grid for the fused sign query
 }
 
+extern "C" int eg_env_set_navmesh(EgEnv* h, const float* tris_dev, int n_tris) {
+  EG_REQUIRE(h && tris_dev && n_tris > 0, "bad arguments");
+  h->tris = tris_dev; h->n_tris = n_tris;
+  return EG_OK;
+}
+
 #define EG_TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 extern "C" int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int E, void* stream) {
@@ -441,15 +538,21 @@ extern "C" int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int 
   // c: history frames + parameter blending (:116-120)
   EG_LAUNCH(env_prepare_params_kernel, E, 128, 0, st, b->seed, h->params, E);
   stage_mark(st, 2);
-  // d,e: SMPL-X on 20 bodies per env fused with the SDF penetration query (:133-177)
-  EG_TRY(eg_lbs_forward_sdf(h->lbs, h->params, b->betas, E, E * NT, NT, b->R0, b->T0, h->grid, h->D0, h->D1,
-                            h->D2, h->center, h->scale, h->skip, h->counts, h->joints, h->mproj, stream));
+  if (h->cfg.pene_mode == 1) {
+    // box-scene env (crowd_env_2f_box.py): no vertex-level SDF query - joints and markers only
+    EG_REQUIRE(h->tris != nullptr, "navmesh not set (eg_env_set_navmesh)");
+    EG_TRY(eg_lbs_forward(h->lbs, h->params, b->betas, E, E * NT, nullptr, h->joints, h->mproj, stream));
+  } else {
+    // d,e: SMPL-X on 20 bodies per env fused with the SDF penetration query (:133-177)
+    EG_TRY(eg_lbs_forward_sdf(h->lbs, h->params, b->betas, E, E * NT, NT, b->R0, b->T0, h->grid, h->D0, h->D1,
+                              h->D2, h->center, h->scale, h->skip, h->counts, h->joints, h->mproj, stream));
+  }
   stage_mark(st, 3);
   // f: VPoser latent of every frame's body pose (:197-200)
   EG_TRY(eg_vposer_encode(h->vposer, h->params + 6, 93, E * NT, h->vp, stream));
   stage_mark(st, 4);
   EG_TRY(eg_lbs_rest_pelvis(h->lbs, b->betas, E, E, h->prest, stream));
-  StepArgs a{h->cfg, *b, h->Y, h->params, h->counts, h->joints, h->mproj, h->vp, h->prest};
+  StepArgs a{h->cfg, *b, h->Y, h->params, h->counts, h->joints, h->mproj, h->vp, h->prest, h->tris, h->n_tris};
   EG_LAUNCH(env_reward_recanon_kernel, E, 256, 0, st, a);
   stage_mark(st, 5);
   // i: all joints of the re-canonicalised seed for ego-sensing (:290-296)
@@ -473,10 +576,15 @@ extern "C" int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_
   EG_TRY(eg_lbs_rest_pelvis(h->lbs, betas_cand, n, n, h->prest, stream));
   EG_TRY(eg_lbs_forward(h->lbs, world_params, betas_cand, n, n * 2, nullptr, h->joints, nullptr, stream));
   EG_LAUNCH(env_reset_canon_kernel, n, 32, 0, st, world_params, h->joints, h->prest, n, h->R0c, h->T0c, h->seedc);
-  EG_TRY(eg_lbs_forward_sdf(h->lbs, h->seedc, betas_cand, n, n * 2, 2, h->R0c, h->T0c, h->grid, h->D0, h->D1, h->D2,
-                            h->center, h->scale, h->skip, h->counts, h->joints2, h->mproj, stream));
+  if (h->cfg.pene_mode == 1) {
+    EG_REQUIRE(h->tris != nullptr, "navmesh not set (eg_env_set_navmesh)");
+    EG_TRY(eg_lbs_forward(h->lbs, h->seedc, betas_cand, n, n * 2, nullptr, h->joints2, h->mproj, stream));
+  } else {
+    EG_TRY(eg_lbs_forward_sdf(h->lbs, h->seedc, betas_cand, n, n * 2, 2, h->R0c, h->T0c, h->grid, h->D0, h->D1, h->D2,
+                              h->center, h->scale, h->skip, h->counts, h->joints2, h->mproj, stream));
+  }
   EG_LAUNCH(env_reset_commit_kernel, n, 256, 0, st, *b, env_ids, n, h->counts, h->R0c, h->T0c, h->seedc,
-            h->joints2, h->mproj, goals, betas_cand, accept);
+            h->joints2, h->mproj, goals, betas_cand, accept, h->cfg, h->tris, h->n_tris);
   EG_LAUNCH(env_egosensing_kernel, n, 64, 0, st, h->joints2, h->R0c, h->T0c, env_ids, accept, h->segs, h->S,
             (double)h->cfg.ray_len, b->ego);
   return EG_OK;

@@ -97,13 +97,15 @@ def main(args=None):
     n_collect = shard(args.step_per_collect, world, rank, "step-per-collect")
     n_batch = shard(args.batch_size, world, rank, "batch-size")
     w = build_world(dev, n_train, seed=args.seed + rank, sdf_res=args.sdf_res, finetuning=args.finetune,
-                    body_model_path=args.body_model_path, scene_sdf=scene_sdf, scene_rings=scene_rings, args=args)
+                    body_model_path=args.body_model_path, scene_sdf=scene_sdf, scene_rings=scene_rings, args=args,
+                    box_mode=getattr(args, "box_mode", False))
     policy, optim, train_collector = w["policy"], w["optim"], w["collector"]
     if world > 1:                                  # identical initial weights on every rank
         dist.broadcast(policy.flat_params, src=0)
     tw = build_world(dev, args.test_num, seed=args.seed + 1000 + rank, sdf_res=args.sdf_res, finetuning=args.finetune,
-                     body_model_path=args.body_model_path, scene_sdf=w["scene_sdf"], scene_rings=w["scene_rings"],
-                     with_policy=False)
+                     body_model_path=args.body_model_path, scene_sdf=None if getattr(args, "box_mode", False) else w["scene_sdf"],
+                     scene_rings=None if getattr(args, "box_mode", False) else w["scene_rings"], with_policy=False,
+                     box_mode=getattr(args, "box_mode", False))
     test_collector = Collector(policy, tw["venv"])
     w["venv"].seed(args.seed + rank)
     tw["venv"].seed(args.seed + rank)

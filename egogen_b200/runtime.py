@@ -8,7 +8,7 @@ import torch
 
 from . import assets
 from .collector import Collector
-from .crowd_env import BoxSceneSampler, CrowdVectorEnv, default_cfg
+from .crowd_env import BoxSceneSampler, CrowdVectorEnv, default_cfg, default_cfg_box
 from .models_gamma_primitive import GAMMAPrimitiveComboGenOP, load_vposer
 from .models_policy_ppo import ActorCritic, GAMMAActor, GAMMACritic, GAMMAPolicyBase
 from .ppo_policy import GAMMAPPOPolicy
@@ -44,9 +44,10 @@ def build_policy(cfg, device, args=None, process_group=None):
 
 def build_world(device, n_envs: int, seed: int = 0, sdf_res: int = 256, n_boxes: int = 1, finetuning: bool = False,
                 body_model_path=None, scene_sdf=None, scene_rings=None, args=None, with_policy: bool = True,
-                host_boundary: bool = False, process_group=None, cfg=None):
+                host_boundary: bool = False, process_group=None, cfg=None, box_mode: bool = False):
     dev = torch.device(device)
-    cfg = cfg or default_cfg()
+    cfg = cfg or (default_cfg_box() if box_mode else default_cfg())
+    scene = None
     markers = assets.marker_ids()
     lbs = get_lbs_model("male", dev, body_model_path=body_model_path, marker_vids=markers)
     genop = GAMMAPrimitiveComboGenOP(testconfig={"gpu_index": dev.index or 0})
@@ -59,8 +60,13 @@ def build_world(device, n_envs: int, seed: int = 0, sdf_res: int = 256, n_boxes:
     scene_sdf = {k: torch.as_tensor(v, dtype=torch.float32).to(dev) for k, v in scene_sdf.items()}
     sampler = BoxSceneSampler(scene_sdf, lbs, dev, seed=seed)
     sampler.scene_rings = scene_rings
+    tris = None
+    if box_mode:
+        if scene is None:
+            raise ValueError("box_mode needs a synthetic box scene (or pass navmesh triangles through CrowdVectorEnv)")
+        tris = assets.scene_navmesh_triangles(scene)
     venv = CrowdVectorEnv(cfg, genop.model, lbs, vposer, scene_sdf, scene_rings, sampler, n_envs, dev,
-                          finetuning=finetuning)
+                          finetuning=finetuning, box_mode=box_mode, navmesh_tris=tris)
     out = dict(cfg=cfg, lbs=lbs, genop=genop, vposer=vposer, scene_sdf=scene_sdf, scene_rings=scene_rings,
                sampler=sampler, venv=venv)
     if with_policy:

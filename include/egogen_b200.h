@@ -201,6 +201,14 @@ typedef struct EgEnvConfig {
   float goal_thresh;             /* 0.1 */
   float w_skate, w_floor, w_face, w_look, w_success, w_dist, w_vp, w_pene;
   float ray_len;                 /* 7 */
+  /* penetration model: 0 = SDF vertex count of crowd_env_2f.py:162-177 (Replica room0 env);
+   * 1 = 2-D walkability map of crowd_env_2f_box.py:279-295 (random_box_obstacle_new env): cells of the local
+   * map_res x map_res grid (get_map, batch_gen_amass.py:934-968) that lie inside the markers' xy bounding box and
+   * outside every navmesh triangle are counted; count > pene_thres => r_pene = 0 and the episode terminates */
+  int32_t pene_mode;
+  int32_t map_res;               /* 16 */
+  float map_extent;              /* 0.8 */
+  float pene_thres;              /* 3 */
 } EgEnvConfig;
 
 typedef struct EgEnvBuffers {    /* device pointers; (n) = nullable */
@@ -233,6 +241,8 @@ int eg_env_set_config(EgEnv* h, const EgEnvConfig* cfg);
 int eg_env_set_scene(EgEnv* h, const float* grid, int D0, int D1, int D2, const float* center_dev,
                      const float* scale_dev, const uint8_t* skip_mask, const double* segments_dev,
                      int n_segments);
+/* navmesh triangles (xy) for pene_mode 1: tris_dev float [n_tris,3,2] (navmesh.vertices[faces, :2]) */
+int eg_env_set_navmesh(EgEnv* h, const float* tris_dev, int n_tris);
 /* one transition of all E envs with actions z [E,128] */
 int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int E, void* stream);
 /* try to (re)start the envs env_ids [n] from sampled world-frame 2-frame seeds world_params [n,2,93],

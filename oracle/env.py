@@ -70,6 +70,40 @@ def get_feature(Y_l, pel, R0, T0, pt_wpath):
     return dist_xy, dist_xyz, (fea_marker / dist_m_3d).reshape(nb, nt, -1)
 
 
+def get_map(tris, R, T, res=16, extent=0.8):
+    """get_map (exp_GAMMAPrimitive/utils/batch_gen_amass.py:934-968): tris [F,3,2] = navmesh.vertices[faces, :2].
+    Returns (points_local [b,res*res,3], local_map [b,res*res] with +1 walkable / -1 not, crowd_env_2f_box.py:769-770)."""
+    b = R.shape[0]
+    x = torch.linspace(-extent, extent, res)
+    xv, yv = torch.meshgrid(x, x, indexing="ij")
+    points = torch.stack([xv, yv, torch.zeros_like(xv)], dim=2).reshape(1, -1, 3).repeat(b, 1, 1)
+    points_scene = torch.einsum("bij,bpj->bpi", R, points) + T
+    p2 = points_scene[:, :, :2].reshape(b * res * res, 1, 2)
+    tri = torch.as_tensor(tris, dtype=torch.float32)[None]            # [1,F,3,2]
+
+    def sign(p1, p2_, p3):
+        return (p1[:, :, 0] - p3[:, :, 0]) * (p2_[:, :, 1] - p3[:, :, 1]) - (p2_[:, :, 0] - p3[:, :, 0]) * (p1[:, :, 1] - p3[:, :, 1])
+    d1 = sign(p2, tri[:, :, 0, :], tri[:, :, 1, :])
+    d2 = sign(p2, tri[:, :, 1, :], tri[:, :, 2, :])
+    d3 = sign(p2, tri[:, :, 2, :], tri[:, :, 0, :])
+    has_neg = (d1 < 0) | (d2 < 0) | (d3 < 0)
+    has_pos = (d1 > 0) | (d2 > 0) | (d3 > 0)
+    inside = (~(has_neg & has_pos)).any(-1).reshape(b, res * res)
+    local_map = inside.float()
+    local_map[~inside] = -1
+    return points, local_map
+
+
+def map_penetration(marker_seed, points_local, local_map):
+    """crowd_env_2f_box.py:279-292 (pene_type 'body'): marker_seed [b,t,67,3] local."""
+    nb = marker_seed.shape[0]
+    xy = marker_seed[:, :, :, :2]
+    box_min = xy.amin(dim=[1, 2]).reshape(nb, 1, 2)
+    box_max = xy.amax(dim=[1, 2]).reshape(nb, 1, 2)
+    inside = ((points_local[:, :, :2] >= box_min).all(-1) & (points_local[:, :, :2] <= box_max).all(-1)).float()
+    return (inside * (1 - local_map) * 0.5).sum(dim=1)
+
+
 def blend_params(body_params, t_his=2):
     """_blend_params (:729-739) on [t,b,93], in place."""
     s = 6
@@ -85,11 +119,15 @@ class CrowdEnvOracle:
     W = dict(skate=0.3, floor=0.1, face=0.1, look=0.3, success=0.5, dist=1.0, vp=0.1)   # yaml :41-53
 
     def __init__(self, parser, combo, vposer, scene_sdf, segments, marker_ids, feet_marker_idx, feet_vids,
-                 finetuning=False, max_depth=13, goal_thresh=0.1, reproj_factor=0.5):
+                 finetuning=False, max_depth=13, goal_thresh=0.1, reproj_factor=0.5, box_mode=False, navmesh_tris=None,
+                 pene_thres=3, weight_pene_box=0.1, weight_look=None):
         self.parser, self.combo, self.vposer = parser, combo, vposer
         self.sdf, self.segments = scene_sdf, segments
         self.marker, self.feet_marker_idx, self.feet_vids = marker_ids, feet_marker_idx, feet_vids
         self.finetuning, self.max_depth, self.goal_thresh, self.rf = finetuning, max_depth, goal_thresh, reproj_factor
+        self.box_mode, self.tris, self.pene_thres, self.w_pene_box = box_mode, navmesh_tris, pene_thres, weight_pene_box
+        if weight_look is not None:
+            self.W = dict(self.W, look=weight_look)
 
     def set_state(self, **kw):
         for k, v in kw.items():
@@ -139,11 +177,14 @@ class CrowdEnvOracle:
         markers_proj = out.vertices[:, self.marker, :].reshape(E, nt, -1, 3)
         marker_b = self.rf * markers_proj + (1 - self.rf) * pred_markers
         # sdf penetration (:162-177)
-        verts = out.vertices.reshape(E, nt, -1, 3)
-        verts_w = torch.einsum("bij,btpj->btpi", self.R0, verts) + self.T0[:, None, :, :]
-        sdf_values = osdf.calc_sdf(verts_w.reshape(E * nt, -1, 3), self.sdf).reshape(E, nt, -1)
-        sdf_values[:, :, self.feet_vids] = 0.0
-        counts = sdf_values.lt(0.0).sum(dim=-1)
+        if self.box_mode:
+            counts = torch.zeros(E, nt, dtype=torch.int64)
+        else:
+            verts = out.vertices.reshape(E, nt, -1, 3)
+            verts_w = torch.einsum("bij,btpj->btpi", self.R0, verts) + self.T0[:, None, :, :]
+            sdf_values = osdf.calc_sdf(verts_w.reshape(E * nt, -1, 3), self.sdf).reshape(E, nt, -1)
+            sdf_values[:, :, self.feet_vids] = 0.0
+            counts = sdf_values.lt(0.0).sum(dim=-1)
         num_inside = counts.sum(dim=1) / nt / 10
         num_inside_max = counts.max(dim=-1).values
         penetration = num_inside_max >= 40
@@ -199,6 +240,12 @@ class CrowdEnvOracle:
         self.state = torch.cat([marker_seed.reshape(E, t_his, -1), fea_marker], dim=-1)
         self.seed = seed_new
         w_pene = 0.1 if self.finetuning else 1.0
+        if self.box_mode:      # 2-D walkability-map penetration in the NEW frame (crowd_env_2f_box.py:279-295)
+            pts_l, lmap = get_map(self.tris, self.R0, self.T0)
+            num_pene = map_penetration(marker_seed, pts_l, lmap)
+            penetration = num_pene > self.pene_thres
+            r_pene = torch.where(penetration, torch.tensor(0.0), torch.tensor(0.05))
+            w_pene = self.w_pene_box
         W = self.W
         reward = r_skate * W["skate"] + r_floor * W["floor"] + r_face * W["face"] + r_look * W["look"] + \
             r_goal * W["success"] + r_dist * W["dist"] + r_pene * w_pene + r_vp * W["vp"]
@@ -207,7 +254,7 @@ class CrowdEnvOracle:
         ja_w = torch.einsum("bij,btpj->btpi", self.R0, ja.reshape(E, t_his, -1, 3)) + self.T0[:, None, :, :]
         self.ego = egosensing(ja_w, self.segments)
         at_max = self.steps == self.max_depth
-        terminated = (r_goal > 0) | at_max | (penetration if self.finetuning else torch.zeros(E, dtype=torch.bool))
+        terminated = (r_goal > 0) | at_max | (penetration if (self.finetuning or self.box_mode) else torch.zeros(E, dtype=torch.bool))
         return dict(state=self.state, egosensing=self.ego, dist=1 / (dist2target + 1),
                     time=torch.as_tensor([1 - s / self.max_depth for s in self.steps.tolist()], dtype=torch.float32),
                     reward=reward, terminated=terminated, counts=counts, seed=self.seed, R0=self.R0, T0=self.T0,
@@ -234,6 +281,9 @@ class CrowdEnvOracle:
         sdf_values[:, :, self.feet_vids] = 0.0
         counts = sdf_values.lt(0.0).sum(dim=-1)
         accept = counts.sum(dim=1) == 0
+        if self.box_mode:
+            pts_l, lmap = get_map(self.tris, R0, T0)
+            accept = map_penetration(marker_seed.reshape(n, 2, -1, 3), pts_l, lmap) == 0
         ja_w = torch.einsum("bij,btpj->btpi", R0, joints_all) + T0[:, None, :, :]
         ego = egosensing(ja_w, self.segments)
         state = torch.cat([marker_seed, fea_marker], dim=-1)

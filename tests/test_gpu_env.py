@@ -168,3 +168,45 @@ def test_single_env_gym_surface(dev, world, smplx_model):
         assert isinstance(rew, float) and isinstance(term, bool) and trunc is False
         n += 1
     assert 1 <= n <= 13 and len(env.outmps) == n
+
+
+def test_box_scene_env_matches_oracle(dev, world, smplx_model):
+    """f-1: the random_box_obstacle_new env (crowd_env_2f_box.py): 2-D walkability-map penetration, always-terminating."""
+    from egogen_b200.crowd_env import BoxSceneSampler, CrowdVectorEnv, default_cfg_box
+    from oracle.env import CrowdEnvOracle, get_map
+    from oracle.smplx_lbs import SMPLXParserOracle
+    scene = assets.make_box_scene(7, n_boxes=3)
+    sdf_cpu = assets.rasterize_scene_sdf(scene, D=64)
+    sdf = {k: v.to(dev) for k, v in sdf_cpu.items()}
+    rings, tris = assets.scene_polygon(scene), assets.scene_navmesh_triangles(scene)
+    E = 8
+    sampler = BoxSceneSampler(sdf, world["lbs"], dev, seed=5)
+    venv = CrowdVectorEnv(default_cfg_box(), world["genop"].model, world["lbs"], world["vposer"], sdf, rings, sampler, E, dev,
+                          debug_terms=True, capture_rollout=True, box_mode=True, navmesh_tris=tris)
+    markers = assets.marker_ids()
+    orc = CrowdEnvOracle(SMPLXParserOracle(smplx_model, marker=markers), world["combo"].eval(), world["vp_o"].eval(), sdf_cpu,
+                         assets.rings_to_segments(rings), markers, assets.feet_marker_idx(), assets.feet_vids(), max_depth=11,
+                         box_mode=True, navmesh_tris=tris, weight_look=0.1)
+    # reset parity incl. a candidate standing inside a box (must be rejected by both)
+    s = sampler.next_body(E)
+    bx = scene["boxes"][0]
+    s["world_params"][0, :, 0] = float(bx[0] + bx[3]) / 2; s["world_params"][0, :, 1] = float(bx[1] + bx[4]) / 2
+    acc = venv.reset_from(torch.arange(E), s["world_params"], s["goals"], s["betas"])
+    ref = orc.reset_from(s["world_params"].cpu(), s["goals"].cpu(), s["betas"].cpu())
+    assert torch.equal(acc.cpu().bool(), ref["accept"]) and not bool(acc[0]) and acc.sum() > 0
+    venv.reset()
+    g = torch.Generator().manual_seed(8)
+    for it in range(3):
+        _sync_oracle(orc, venv)
+        z = torch.randn(E, 128, generator=g)
+        obs, rew, term, _, _ = venv.step(z.to(dev))
+        r = orc.step(z)
+        b = venv.buf
+        assert torch.allclose(b["reward_terms"].cpu(), r["terms"], atol=2e-4), (b["reward_terms"].cpu() - r["terms"]).abs().max(0)
+        assert torch.allclose(rew.cpu(), r["reward"], atol=5e-4)
+        assert torch.equal(term.cpu().bool(), r["terminated"])
+        assert torch.allclose(obs["state"].cpu(), r["state"], atol=2e-4)
+    # the walkability map itself: every grid cell classification matches get_map for random frames
+    R = torch.eye(3).repeat(4, 1, 1); T = torch.rand(4, 1, 3) * 4 - 2
+    _, lmap = get_map(tris, R, T)
+    assert (lmap == -1).any() and (lmap == 1).any()
