@@ -163,7 +163,13 @@ def run_ours(args):
     if sampler:
         sampler.start()
     lib.eg_profile_enable(1)
+    ncu_range = os.environ.get("EG_NCU_RANGE") == "1"      # ncu --profile-from-start off: capture the timed region only
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     ms, launches = timed(col, args.steps, False)
+    if ncu_range:
+        torch.cuda.synchronize(dev)
+        torch.cuda.cudart().cudaProfilerStop()
     tot_ms, n_l, n_units = C.c_double(), C.c_int64(), C.c_int64()
     _lib.check(lib.eg_profile_read(C.byref(tot_ms), C.byref(n_l), C.byref(n_units)))
     lib.eg_profile_enable(0)

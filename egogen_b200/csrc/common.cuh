@@ -132,6 +132,18 @@ __device__ __forceinline__ float sdf_sample_point(const SdfGrid& g, float cx, fl
   return -acc;
 }
 
+// value of the conservative coarse cell containing the world point (<= 0: the cell may hold a negative sample);
+// -1 when no coarse grid is attached, so callers fall through to the exact sample.
+__device__ __forceinline__ float sdf_coarse_value(const SdfGrid& g, float cx, float cy, float cz, float s, float x,
+                                                  float y, float z) {
+  if (g.coarse == nullptr) return -1.0f;
+  const float ix = sdf_unnormalize(__fmul_rn(__fsub_rn(x, cx), s), g.D0);
+  const float iy = sdf_unnormalize(__fmul_rn(__fsub_rn(y, cy), s), g.D1);
+  const float iz = sdf_unnormalize(__fmul_rn(__fsub_rn(z, cz), s), g.D2);
+  const int c0 = (int)ix >> kCoarseShift, c1 = (int)iy >> kCoarseShift, c2 = (int)iz >> kCoarseShift;
+  return __ldg(g.coarse + (c0 * g.C1 + c1) * g.C2 + c2);
+}
+
 // sign-only query used by the fused penetration count: identical to sdf_sample_point(...) < 0 (the trilinear
 // sample is a non-negative combination of the cell's corners, so a positive coarse minimum proves "not negative"
 // without touching the fine grid); falls back to the exact sample otherwise.

@@ -219,26 +219,37 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
       a_out[a * 4 + 3] = g3 - (g0 * Jr[t][0] + g1 * Jr[t][1] + g2 * Jr[t][2]);
       jp[a] = g3;
     }
-    // world-composed copy for the fused tensor-core path: R0 (A [v;1] + transl) + T0 folded into A
-    // (skinning weights sum to 1, so the translation part can ride inside every A_j)
+    // copy for the tensor-core epilogue (Aw): world-composed R0 (A [v;1] + transl) + T0 when R0w is given (skinning
+    // weights sum to 1, so the translation part can ride inside every A_j), the local A_j otherwise. Stored in the
+    // epilogue's packed-FMA order {m00,m10,m01,m11 | m02,m12,m03,m13 | m20,m21,m22,m23}.
     if (Aw != nullptr) {
-      const int e = n / frames_per_env;
-      const float* Rw = R0w + (int64_t)e * 9;
-      const float* Tw = T0w + (int64_t)e * 3;
-      float* w_out = Aw + ((int64_t)n * J + t) * 12;
-      float col[4][3];
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int a = 0; a < 3; ++a) col[b][a] = a_out[a * 4 + b];
-      col[3][0] += x[0]; col[3][1] += x[1]; col[3][2] += x[2];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
+      float M[3][4];
+      if (R0w != nullptr) {
+        const int e = n / frames_per_env;
+        const float* Rw = R0w + (int64_t)e * 9;
+        const float* Tw = T0w + (int64_t)e * 3;
+        float col[4][3];
 #pragma unroll
         for (int b = 0; b < 4; ++b)
-          w_out[a * 4 + b] = Rw[a * 3 + 0] * col[b][0] + Rw[a * 3 + 1] * col[b][1] + Rw[a * 3 + 2] * col[b][2] +
-                             (b == 3 ? Tw[a] : 0.0f);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) col[b][a] = a_out[a * 4 + b];
+        col[3][0] += x[0]; col[3][1] += x[1]; col[3][2] += x[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            M[a][b] = Rw[a * 3 + 0] * col[b][0] + Rw[a * 3 + 1] * col[b][1] + Rw[a * 3 + 2] * col[b][2] +
+                      (b == 3 ? Tw[a] : 0.0f);
+      } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) M[a][b] = a_out[a * 4 + b];
       }
+      float4* w_out = reinterpret_cast<float4*>(Aw + ((int64_t)n * J + t) * 12);
+      w_out[0] = make_float4(M[0][0], M[1][0], M[0][1], M[1][1]);
+      w_out[1] = make_float4(M[0][2], M[1][2], M[0][3], M[1][3]);
+      w_out[2] = make_float4(M[2][0], M[2][1], M[2][2], M[2][3]);
     }
   }
 }
@@ -453,7 +464,8 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int vt = tile % n_vt, bt = tile / n_vt;
+        int vt, bt;
+        tile_coords(tile, n_vt, n_bt, vt, bt);
         for (int ch = 0; ch < NCHUNK; ++ch) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* st = smem + stage * STAGE_BYTES;
@@ -495,7 +507,8 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else if (warp >= 4) {
     // ===== epilogue: TMEM lane quarter q (= 32 vertices), body slot cg within each 16-body chunk =====
     // The joint transforms of a 16-body chunk are staged in shared memory by all 512 epilogue threads
-    // (cp.async, double-buffered) so the per-(vertex, body) skinning gathers hit smem instead of L2.
+    // (cp.async, double-buffered) so the per-(vertex, body) skinning gathers are ld.shared.v4, and the blend
+    // T = sum_k w_k A[n][j_k] runs on packed fp32 FMAs (FFMA2) in the {m00,m10,m01,m11 | m02,m12,m03,m13 | m2*} order.
     const int q = warp & 3, cg = (warp - 4) >> 2, eidx = tid - 128;
     float cx = 0.f, cy = 0.f, cz = 0.f, sc = 0.f;
     if (FUSE_SDF) {
@@ -503,23 +516,26 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       sc = __ldg(a.sdf.scale);
     }
     const int chunk_f4 = CHUNK_B * a.J * 3;            // float4 per staged chunk
+    const uint32_t jstride = (uint32_t)a.J * 48u;       // bytes per body in the staged chunk
+    const uint32_t smemA_u32 = smem_u32(smemA);
     auto stage_chunk = [&](int buf, int n0) {
       const float4* src = reinterpret_cast<const float4*>(a.A + (int64_t)n0 * a.J * 12);
-      float4* dst = reinterpret_cast<float4*>(smemA + buf * ASTAGE_BYTES);
-      for (int i = eidx; i < chunk_f4; i += EPI_WARPS * 32) cp_async16(dst + i, src + i);
+      const uint32_t dst = smemA_u32 + (uint32_t)buf * ASTAGE_BYTES;
+      for (int i = eidx; i < chunk_f4; i += EPI_WARPS * 32) cp_async16_u32(dst + (uint32_t)i * 16u, src + i);
       cp_async_commit();
     };
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int vt = tile % n_vt, bt = tile / n_vt;
+      int vt, bt;
+      tile_coords(tile, n_vt, n_bt, vt, bt);
       const int v = vt * TV + q * 32 + lane;
       const bool v_ok = v < a.n_real;
       const float t0 = a.vt[v * 3 + 0], t1 = a.vt[v * 3 + 1], t2 = a.vt[v * 3 + 2];
       const bool skip = FUSE_SDF ? (v_ok ? (a.skip != nullptr && a.skip[v] != 0) : true) : false;
-      int sj[4]; float sw[4];                          // first 4 skinning entries live in registers
+      uint32_t joff[4]; float sw[4];                   // first 4 skinning entries live in registers
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        sj[k] = k < a.nnz ? a.skin_idx[k * a.n_pad + v] : 0;
+        joff[k] = k < a.nnz ? (uint32_t)a.skin_idx[k * a.n_pad + v] * 48u : 0u;
         sw[k] = k < a.nnz ? a.skin_w[k * a.n_pad + v] : 0.0f;
       }
       stage_chunk(0, bt * TB);                         // overlaps this tile's MMA
@@ -537,47 +553,67 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         tmem_ld4(trow + TB + col, ay);
         tmem_ld4(trow + 2 * TB + col, az);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float4* Ac = reinterpret_cast<const float4*>(smemA + (c & 1) * ASTAGE_BYTES);
+        const uint32_t abase = smemA_u32 + (uint32_t)(c & 1) * ASTAGE_BYTES + (uint32_t)(cg * 4) * jstride;
+        const int n_first = bt * TB + c * CHUNK_B + cg * 4;
+        float ox[4], oy[4], oz[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const int bl = cg * 4 + b;
-          const int n = bt * TB + c * CHUNK_B + bl;
-          if (n >= a.N) continue;                       // warp-uniform
-          const float px = t0 + ax[b], py = t1 + ay[b], pz = t2 + az[b];
-          const float4* An = Ac + bl * a.J * 3;
-          float T[12];
-#pragma unroll
-          for (int e = 0; e < 12; ++e) T[e] = 0.0f;
+          const uint32_t ab = abase + (uint32_t)b * jstride;
+          float2 c0, c1, c2, c3, z0, z1;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float w = sw[k];
-            const float4 r0 = An[sj[k] * 3 + 0], r1 = An[sj[k] * 3 + 1], r2 = An[sj[k] * 3 + 2];
-            T[0] += w * r0.x; T[1] += w * r0.y; T[2] += w * r0.z; T[3] += w * r0.w;
-            T[4] += w * r1.x; T[5] += w * r1.y; T[6] += w * r1.z; T[7] += w * r1.w;
-            T[8] += w * r2.x; T[9] += w * r2.y; T[10] += w * r2.z; T[11] += w * r2.w;
+            const float4 q0 = lds128(ab + joff[k]), q1 = lds128(ab + joff[k] + 16u), q2 = lds128(ab + joff[k] + 32u);
+            const float2 w2 = make_float2(sw[k], sw[k]);
+            if (k == 0) {
+              c0 = __fmul2_rn(w2, make_float2(q0.x, q0.y)); c1 = __fmul2_rn(w2, make_float2(q0.z, q0.w));
+              c2 = __fmul2_rn(w2, make_float2(q1.x, q1.y)); c3 = __fmul2_rn(w2, make_float2(q1.z, q1.w));
+              z0 = __fmul2_rn(w2, make_float2(q2.x, q2.y)); z1 = __fmul2_rn(w2, make_float2(q2.z, q2.w));
+            } else {
+              c0 = __ffma2_rn(w2, make_float2(q0.x, q0.y), c0); c1 = __ffma2_rn(w2, make_float2(q0.z, q0.w), c1);
+              c2 = __ffma2_rn(w2, make_float2(q1.x, q1.y), c2); c3 = __ffma2_rn(w2, make_float2(q1.z, q1.w), c3);
+              z0 = __ffma2_rn(w2, make_float2(q2.x, q2.y), z0); z1 = __ffma2_rn(w2, make_float2(q2.z, q2.w), z1);
+            }
           }
           for (int k = 4; k < a.nnz; ++k) {             // rare: more than 4 non-zero weights
-            const int jj = a.skin_idx[k * a.n_pad + v];
+            const uint32_t jo = (uint32_t)a.skin_idx[k * a.n_pad + v] * 48u;
             const float w = a.skin_w[k * a.n_pad + v];
-            const float4 r0 = An[jj * 3 + 0], r1 = An[jj * 3 + 1], r2 = An[jj * 3 + 2];
-            T[0] += w * r0.x; T[1] += w * r0.y; T[2] += w * r0.z; T[3] += w * r0.w;
-            T[4] += w * r1.x; T[5] += w * r1.y; T[6] += w * r1.z; T[7] += w * r1.w;
-            T[8] += w * r2.x; T[9] += w * r2.y; T[10] += w * r2.z; T[11] += w * r2.w;
+            const float4 q0 = lds128(ab + jo), q1 = lds128(ab + jo + 16u), q2 = lds128(ab + jo + 32u);
+            const float2 w2 = make_float2(w, w);
+            c0 = __ffma2_rn(w2, make_float2(q0.x, q0.y), c0); c1 = __ffma2_rn(w2, make_float2(q0.z, q0.w), c1);
+            c2 = __ffma2_rn(w2, make_float2(q1.x, q1.y), c2); c3 = __ffma2_rn(w2, make_float2(q1.z, q1.w), c3);
+            z0 = __ffma2_rn(w2, make_float2(q2.x, q2.y), z0); z1 = __ffma2_rn(w2, make_float2(q2.z, q2.w), z1);
           }
-          float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
-          float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
-          float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-          if (FUSE_SDF) {                                // transforms are world-composed: (ox,oy,oz) is the world point
+          const float px = t0 + ax[b], py = t1 + ay[b], pz = t2 + az[b];
+          float2 xy = __ffma2_rn(c0, make_float2(px, px), c3);
+          xy = __ffma2_rn(c1, make_float2(py, py), xy);
+          xy = __ffma2_rn(c2, make_float2(pz, pz), xy);
+          ox[b] = xy.x; oy[b] = xy.y;
+          oz[b] = fmaf(z1.x, pz, fmaf(z0.y, py, fmaf(z0.x, px, z1.y)));
+        }
+        if (FUSE_SDF) {                                  // transforms are world-composed: (ox,oy,oz) is the world point
+          // conservative coarse-cell sign test for the 4 bodies first (4 independent loads), exact sample only
+          // where the cell can hold a negative value
+          float cv[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) cv[b] = sdf_coarse_value(a.sdf, cx, cy, cz, sc, ox[b], oy[b], oz[b]);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
             bool neg = false;
-            if (!skip) neg = sdf_is_negative(a.sdf, cx, cy, cz, sc, ox, oy, oz);
+            if (!skip && cv[b] <= 0.0f) {
+              int i0, i1, i2;
+              neg = sdf_sample_point(a.sdf, cx, cy, cz, sc, ox[b], oy[b], oz[b], i0, i1, i2) < 0.0f;
+            }
             const unsigned m = __ballot_sync(0xffffffffu, neg);
-            if (lane == 0 && m) atomicAdd(a.counts + n, __popc(m));
-          } else {
-            const float* x = a.xb + (int64_t)n * EG_XB_DIM;
-            ox = __fadd_rn(ox, __ldg(x)); oy = __fadd_rn(oy, __ldg(x + 1)); oz = __fadd_rn(oz, __ldg(x + 2));
-            if (a.out != nullptr && v_ok) {
+            if (lane == 0 && m && n_first + b < a.N) atomicAdd(a.counts + n_first + b, __popc(m));
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int n = n_first + b;
+            if (n < a.N && a.out != nullptr && v_ok) {
+              const float* x = a.xb + (int64_t)n * EG_XB_DIM;
               float* o = a.out + ((int64_t)n * a.n_real + v) * 3;
-              o[0] = ox; o[1] = oy; o[2] = oz;
+              o[0] = __fadd_rn(ox[b], __ldg(x)); o[1] = __fadd_rn(oy[b], __ldg(x + 1)); o[2] = __fadd_rn(oz[b], __ldg(x + 2));
             }
           }
         }
@@ -730,7 +766,7 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
   EG_LAUNCH(lbs_pose_prep_kernel, N, 64, 0, st, xb, betas, betas_div, N, Npad, h->J, h->S,
             h->n_levels, h->hand_l, h->hand_r, h->pose_mean, h->Jt, h->Js, h->parents,
             h->level_joints, h->level_start, h->Ft, want_tc ? h->Ftc : nullptr, h->A, h->Jp, R0, T0,
-            frames_per_env, (want_tc && fuse) ? h->Aw : nullptr);
+            frames_per_env, want_tc ? h->Aw : nullptr);
   VertArgs a{};
   a.Ft = h->Ft; a.A = h->A; a.xb = xb; a.N = N; a.Npad = Npad; a.J = h->J;
   const int by = (N + TILE_B - 1) / TILE_B;
@@ -750,7 +786,7 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
       int rc2 = encode_map(h, &mapB, h->Ftc, (uint64_t)h->cap_Ntc, tc::TB);
       if (rc2) return rc2;
       const int n_vt = s.n_pad / tc::TV, n_bt = (N + tc::TB - 1) / tc::TB;
-      if (fuse) a.A = h->Aw;        // world-composed transforms: the epilogue goes straight to the SDF sample
+      a.A = h->Aw;      // pair-layout transforms (world-composed when fused: the epilogue goes straight to the SDF sample)
       const int grid_tc = std::min(n_vt * n_bt, kNumSMs);
       prof_begin(st, N);
       if (fuse) EG_LAUNCH(lbs_verts_tc_kernel<true>, grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);

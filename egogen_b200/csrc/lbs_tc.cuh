@@ -105,5 +105,27 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void cp_async16_u32(uint32_t smem_addr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem));
+}
+
+// Tile order: vertex tiles are walked in bands of BAND_V tiles (BAND_V x 884 KB of basis ~ 25 MB) with every body
+// tile visited inside a band before the next band starts, so the basis band stays L2-resident while it is reused
+// by all body tiles (the full 72.5 MB basis plus features/transforms does not survive a full sweep in L2).
+constexpr int BAND_V = 28;
+__device__ __forceinline__ void tile_coords(int tile, int n_vt, int n_bt, int& vt, int& bt) {
+  const int full = BAND_V * n_bt;
+  const int band = tile / full;
+  const int rem = tile - band * full;
+  const int w = min(BAND_V, n_vt - band * BAND_V);
+  bt = rem / w;
+  vt = band * BAND_V + (rem - bt * w);
+}
+
 }  // namespace tc
 }  // namespace eg
