@@ -81,6 +81,9 @@ struct SdfGrid {
   // trilinear sample inside the 8^3-cell c can touch; > 0 means no sample in the cell can be negative
   const float* coarse = nullptr;
   int C0 = 0, C1 = 0, C2 = 0;
+  const uint32_t* coarse_bits = nullptr;   // 1 bit per coarse cell (coarse <= 0), n_bit_words words
+  int n_bit_words = 0;
+  const uint32_t* fine_bits = nullptr;     // same for 2^3 cells ([ceil(D/2)]^3 bits, dilated), global memory
 };
 constexpr int kCoarseShift = 3;
 
@@ -142,6 +145,16 @@ __device__ __forceinline__ float sdf_coarse_value(const SdfGrid& g, float cx, fl
   const float iz = sdf_unnormalize(__fmul_rn(__fsub_rn(z, cz), s), g.D2);
   const int c0 = (int)ix >> kCoarseShift, c1 = (int)iy >> kCoarseShift, c2 = (int)iz >> kCoarseShift;
   return __ldg(g.coarse + (c0 * g.C1 + c1) * g.C2 + c2);
+}
+
+// linear index of the conservative coarse cell containing the world point
+__device__ __forceinline__ int sdf_coarse_index(const SdfGrid& g, float cx, float cy, float cz, float s, float x,
+                                                float y, float z) {
+  const float ix = sdf_unnormalize(__fmul_rn(__fsub_rn(x, cx), s), g.D0);
+  const float iy = sdf_unnormalize(__fmul_rn(__fsub_rn(y, cy), s), g.D1);
+  const float iz = sdf_unnormalize(__fmul_rn(__fsub_rn(z, cz), s), g.D2);
+  const int c0 = (int)ix >> kCoarseShift, c1 = (int)iy >> kCoarseShift, c2 = (int)iz >> kCoarseShift;
+  return (c0 * g.C1 + c1) * g.C2 + c2;
 }
 
 // sign-only query used by the fused penetration count: identical to sdf_sample_point(...) < 0 (the trilinear

@@ -41,7 +41,14 @@ constexpr int VERT_SMEM = sizeof(float) * 2 * KC * (TILE_V * 3 + TILE_B) + sizeo
 struct VertexSet {
   int n = 0, n_pad = 0, nnz = 0;
   float* basis = nullptr;
-  float* basisT = nullptr;   // [3][n_pad][tc::KT] planar K-major TF32-rounded copy for the tcgen05 mainloop (full set only)
+  // tcgen05 path (full set only): joint-coherent vertex order, see build_tc_layout()
+  float* basisT = nullptr;   // [3][n_pad_tc][tc::KT] planar K-major TF32-rounded copy of the basis, rows in tc order
+  float4* tc_rec = nullptr;  // [n_pad_tc][3] per-vertex records
+  int32_t* tc_jl = nullptr;  // [n_vt_tc][NJ_MAX]
+  int32_t* tc_nj = nullptr;  // [n_vt_tc]
+  uint32_t* tc_xoff = nullptr;
+  float* tc_xw = nullptr;
+  int n_pad_tc = 0, n_vt_tc = 0;
   float* vt = nullptr;
   int32_t* skin_idx = nullptr;
   float* skin_w = nullptr;
@@ -64,7 +71,8 @@ struct EgLbs {
   int cap_N = 0;
   float *Ft = nullptr, *A = nullptr, *Jp = nullptr, *cout_ = nullptr;
   float* Ftc = nullptr;       // [cap_N rounded up to 128][tc::KT] features for the tcgen05 mainloop
-  float* Aw = nullptr;        // [cap_Ntc][J][12] world-composed transforms (fused tensor-core path)
+  float* Aw = nullptr;        // [J][cap_Ntc][12] joint-major transforms in the tensor-core epilogue's pair layout
+  float4* rec_call = nullptr; // [n_pad_tc][3] per-call vertex records with the skip mask folded in
   int cap_Ntc = 0;
   int use_tc = 1;             // 1: tcgen05/TMEM/TMA mainloop for the full mesh, 0: SIMT mainloop
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
@@ -91,7 +99,7 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
                      const int32_t* __restrict__ level_joints, const int32_t* __restrict__ level_start,
                      float* __restrict__ Ft, float* __restrict__ Ftc, float* __restrict__ A,
                      float* __restrict__ Jp, const float* __restrict__ R0w, const float* __restrict__ T0w,
-                     int frames_per_env, float* __restrict__ Aw) {
+                     int frames_per_env, float* __restrict__ Aw, int AwRows) {
   const int n = blockIdx.x;
   const int t = threadIdx.x;
   __shared__ float pose[MAXJ * 3];
@@ -246,7 +254,7 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
 #pragma unroll
           for (int b = 0; b < 4; ++b) M[a][b] = a_out[a * 4 + b];
       }
-      float4* w_out = reinterpret_cast<float4*>(Aw + ((int64_t)n * J + t) * 12);
+      float4* w_out = reinterpret_cast<float4*>(Aw + ((int64_t)t * AwRows + n) * 12);   // joint-major [J][AwRows][12]
       w_out[0] = make_float4(M[0][0], M[1][0], M[0][1], M[1][1]);
       w_out[1] = make_float4(M[0][2], M[1][2], M[0][3], M[1][3]);
       w_out[2] = make_float4(M[2][0], M[2][1], M[2][2], M[2][3]);
@@ -284,6 +292,14 @@ struct VertArgs {
   int frames_per_env;
   const uint8_t* skip;
   int32_t* counts;        // [N]
+  // tensor-core layout (joint-coherent vertex order; see lbs_tc.cuh)
+  const float4* tc_rec;   // [n_pad_tc][3]: {vt.xyz, original id}, {w0..w3}, {slot byte offsets 0..3}
+  const int32_t* tc_jl;   // [n_vt][NJ_MAX] joints of each vertex tile
+  const int32_t* tc_nj;   // [n_vt]
+  const uint32_t* tc_xoff;  // [(nnz-4)][n_pad_tc] slot byte offsets of the skinning entries beyond the 4th
+  const float* tc_xw;
+  int n_pad_tc;
+  int A_rows;             // tc path: A is joint-major [J][A_rows][12]
 };
 
 // One (vertex, body) of the epilogue shared by the SIMT and tcgen05 kernels: skinning T = sum_k w_k A[n][j_k],
@@ -431,13 +447,15 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   using namespace tc;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+  uint64_t* full_bar = bars;                 // [STAGES] operand ring
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* tmem_empty = bars + 2 * STAGES + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
-  unsigned char* smemA = smem + STAGES * STAGE_BYTES + 256;     // 2 x ASTAGE_BYTES joint-transform staging
+  uint64_t* tmem_full = bars + 2 * STAGES;   // [2] accumulator sets
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint64_t* tab_full = tmem_empty + 2;       // [2] joint-transform table + vertex records
+  uint64_t* tab_empty = tab_full + 2;        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tab_empty + 2);
+  const uint32_t smem_base = smem_u32(smem);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = n_vt * n_bt;
@@ -445,8 +463,10 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(tmem_full, 1);
-      mbar_init(tmem_empty, EPI_WARPS);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS);
+        mbar_init(&tab_full[b], 1); mbar_init(&tab_empty[b], EPI_WARPS);
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -460,10 +480,10 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== operand producer: TMA ring =====
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int stage = 0; uint32_t phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         int vt, bt;
         tile_coords(tile, n_vt, n_bt, vt, bt);
         for (int ch = 0; ch < NCHUNK; ++ch) {
@@ -472,156 +492,205 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            tma_load_2d(st + c * A_TILE_BYTES, &mapA, &full_bar[stage], ch * BKT, c * a.n_pad + vt * TV);
-          tma_load_2d(st + 3 * A_TILE_BYTES, &mapB, &full_bar[stage], ch * BKT, bt * TB);
+            tma_load_2d(st + c * V_TILE_BYTES, &mapA, &full_bar[stage], ch * BKT, c * a.n_pad_tc + vt * TV);
+          tma_load_2d(st + 3 * V_TILE_BYTES, &mapB, &full_bar[stage], ch * BKT, bt * TB);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
+  } else if (warp == 2) {
+    // ===== table producer: joint-transform table + vertex records of each tile (bulk copies), decoupled from the ring =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        int vt, bt;
+        tile_coords(tile, n_vt, n_bt, vt, bt);
+        const uint32_t tb = it % NTAB, tph = (it / NTAB) & 1u;
+        mbar_wait(&tab_empty[tb], tph ^ 1u);                       // epilogue of tile it-NTAB is done with this buffer
+        const int nj = __ldg(a.tc_nj + vt);
+        mbar_expect_tx(&tab_full[tb], (uint32_t)nj * SLOT_BYTES + REC_BYTES);
+        for (int s = 0; s < nj; ++s) {
+          const int j = __ldg(a.tc_jl + vt * NJ_MAX + s);
+          bulk_load(smem_base + OFF_TAB + tb * TAB_BYTES + s * SLOT_BYTES,
+                    a.A + ((int64_t)j * a.A_rows + (int64_t)bt * TB) * 12, SLOT_BYTES, &tab_full[tb]);
+        }
+        bulk_load(smem_base + OFF_REC + tb * REC_BYTES, a.tc_rec + (int64_t)vt * TV * 3, REC_BYTES, &tab_full[tb]);
+      }
+    }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: A = feature tile (bodies -> TMEM lanes), B = basis tile of component c (vertices -> columns) =====
     int stage = 0; uint32_t phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      mbar_wait(tmem_empty, (it & 1) ^ 1);                 // epilogue has drained the accumulators
+      const uint32_t buf = it & 1u;
+      mbar_wait(&tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);         // epilogue of tile it-2 has drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int ch = 0; ch < NCHUNK; ++ch) {
         mbar_wait(&full_bar[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
-          const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t db = make_desc(sbase + 3 * A_TILE_BYTES);
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+          const uint64_t df = make_desc(sbase + 3 * V_TILE_BYTES);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const uint64_t da = make_desc(sbase + c * A_TILE_BYTES);
+            const uint64_t dbs = make_desc(sbase + c * V_TILE_BYTES);
 #pragma unroll
             for (int kk = 0; kk < BKT / 8; ++kk)          // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
-              umma_tf32(tmem_base + c * TB, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), (ch | kk) ? 1u : 0u);
+              umma_tf32(tmem_base + buf * ACC_COLS + c * TV, df + (uint64_t)(kk * 2), dbs + (uint64_t)(kk * 2), (ch | kk) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
-          if (ch == NCHUNK - 1) umma_commit(tmem_full);    // accumulators complete
+          if (ch == NCHUNK - 1) umma_commit(&tmem_full[buf]);   // accumulators complete
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM lane quarter q (= 32 vertices), body slot cg within each 16-body chunk =====
-    // The joint transforms of a 16-body chunk are staged in shared memory by all 512 epilogue threads
-    // (cp.async, double-buffered) so the per-(vertex, body) skinning gathers are ld.shared.v4, and the blend
-    // T = sum_k w_k A[n][j_k] runs on packed fp32 FMAs (FFMA2) in the {m00,m10,m01,m11 | m02,m12,m03,m13 | m2*} order.
-    const int q = warp & 3, cg = (warp - 4) >> 2, eidx = tid - 128;
-    float cx = 0.f, cy = 0.f, cz = 0.f, sc = 0.f;
+    // ===== epilogue: thread = body (TMEM lane q*32+lane), warp `sub` of the quarter walks vertices [sub*VPW, +VPW) =====
+    const int q = warp & 3, sub = (warp - 4) >> 2, eidx = tid - 128;
+    constexpr int NEPI = EPI_WARPS * 32;
+    // SDF: coarse-cell sign bits in shared memory (a body-per-lane warp scatters its lookups over the whole grid;
+    // 1 bit per cell keeps them on chip) addressed with one FMA per axis; the bit grid is dilated by one fine
+    // corner (eg_sdf_prepare), which covers the rounding difference to the exact index sequence.
+    float cx = 0.f, cy = 0.f, cz = 0.f, sc = 0.f, gax = 0.f, gay = 0.f, gaz = 0.f, gbx = 0.f, gby = 0.f, gbz = 0.f;
+    const uint32_t mask_u32 = smem_base + OFF_MASK;
+    const bool smem_mask = FUSE_SDF && a.sdf.coarse_bits != nullptr && a.sdf.fine_bits != nullptr && a.sdf.n_bit_words <= MASK_WORDS;
+    const uint32_t fd1 = (uint32_t)((a.sdf.D1 + 1) / 2), fd2 = (uint32_t)((a.sdf.D2 + 1) / 2);
     if (FUSE_SDF) {
       cx = __ldg(a.sdf.center); cy = __ldg(a.sdf.center + 1); cz = __ldg(a.sdf.center + 2);
       sc = __ldg(a.sdf.scale);
+      gax = sc * (float)a.sdf.D0 * 0.5f; gbx = ((1.0f - cx * sc) * (float)a.sdf.D0 - 1.0f) * 0.5f;
+      gay = sc * (float)a.sdf.D1 * 0.5f; gby = ((1.0f - cy * sc) * (float)a.sdf.D1 - 1.0f) * 0.5f;
+      gaz = sc * (float)a.sdf.D2 * 0.5f; gbz = ((1.0f - cz * sc) * (float)a.sdf.D2 - 1.0f) * 0.5f;
+      if (smem_mask) {
+        uint32_t* mk = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
+        for (int i = eidx; i < a.sdf.n_bit_words; i += NEPI) mk[i] = __ldg(a.sdf.coarse_bits + i);
+      }
     }
-    const int chunk_f4 = CHUNK_B * a.J * 3;            // float4 per staged chunk
-    const uint32_t jstride = (uint32_t)a.J * 48u;       // bytes per body in the staged chunk
-    const uint32_t smemA_u32 = smem_u32(smemA);
-    auto stage_chunk = [&](int buf, int n0) {
-      const float4* src = reinterpret_cast<const float4*>(a.A + (int64_t)n0 * a.J * 12);
-      const uint32_t dst = smemA_u32 + (uint32_t)buf * ASTAGE_BYTES;
-      for (int i = eidx; i < chunk_f4; i += EPI_WARPS * 32) cp_async16_u32(dst + (uint32_t)i * 16u, src + i);
-      cp_async_commit();
-    };
+    asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");         // sign bits visible to every epilogue warp
+    const uint32_t dmax0 = (uint32_t)(a.sdf.D0 - 1), dmax1 = (uint32_t)(a.sdf.D1 - 1), dmax2 = (uint32_t)(a.sdf.D2 - 1);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       int vt, bt;
       tile_coords(tile, n_vt, n_bt, vt, bt);
-      const int v = vt * TV + q * 32 + lane;
-      const bool v_ok = v < a.n_real;
-      const float t0 = a.vt[v * 3 + 0], t1 = a.vt[v * 3 + 1], t2 = a.vt[v * 3 + 2];
-      const bool skip = FUSE_SDF ? (v_ok ? (a.skip != nullptr && a.skip[v] != 0) : true) : false;
-      uint32_t joff[4]; float sw[4];                   // first 4 skinning entries live in registers
+      const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+      const uint32_t tb = it % NTAB, tph = (it / NTAB) & 1u;
+      const uint32_t my_tab = smem_base + OFF_TAB + tb * TAB_BYTES + (uint32_t)(q * 32 + lane) * 48u;
+      const uint32_t my_rec = smem_base + OFF_REC + tb * REC_BYTES + (uint32_t)(sub * VPW) * 48u;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(sub * VPW);
+      const int n = bt * TB + q * 32 + lane;
+      const bool n_ok = n < a.N;
+      float trx = 0.f, try_ = 0.f, trz = 0.f;
+      if (!FUSE_SDF && n_ok) { const float* x = a.xb + (int64_t)n * EG_XB_DIM; trx = __ldg(x); try_ = __ldg(x + 1); trz = __ldg(x + 2); }
+      int cnt = 0;
+      float2 C[4][6];                                               // register cache: slot k -> transform of MY body
+      uint32_t cur[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        joff[k] = k < a.nnz ? (uint32_t)a.skin_idx[k * a.n_pad + v] * 48u : 0u;
-        sw[k] = k < a.nnz ? a.skin_w[k * a.n_pad + v] : 0.0f;
-      }
-      stage_chunk(0, bt * TB);                         // overlaps this tile's MMA
-      mbar_wait(tmem_full, it & 1);
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) C[k][e] = make_float2(0.f, 0.f);
+      const int vbase = vt * TV + sub * VPW;
+      mbar_wait(&tab_full[tb], tph);                                // table + records landed
+      mbar_wait(&tmem_full[buf], ph);                               // accumulators complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < TB / CHUNK_B; ++c) {
-        if (c + 1 < TB / CHUNK_B) { stage_chunk((c + 1) & 1, bt * TB + (c + 1) * CHUNK_B); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");     // chunk c staged by everyone
+      for (int g = 0; g < VPW / 4; ++g) {
         float ax[4], ay[4], az[4];
-        const uint32_t col = (uint32_t)(c * CHUNK_B + cg * 4);
-        tmem_ld4(trow + col, ax);
-        tmem_ld4(trow + TB + col, ay);
-        tmem_ld4(trow + 2 * TB + col, az);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const uint32_t abase = smemA_u32 + (uint32_t)(c & 1) * ASTAGE_BYTES + (uint32_t)(cg * 4) * jstride;
-        const int n_first = bt * TB + c * CHUNK_B + cg * 4;
-        float ox[4], oy[4], oz[4];
+        tmem_ld4(trow + (uint32_t)(g * 4), ax);
+        tmem_ld4(trow + TV + (uint32_t)(g * 4), ay);
+        tmem_ld4(trow + 2 * TV + (uint32_t)(g * 4), az);
+        float4 R0[4], R1[4], R2[4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t ab = abase + (uint32_t)b * jstride;
-          float2 c0, c1, c2, c3, z0, z1;
+        for (int u = 0; u < 4; ++u) {                               // warp-uniform addresses: broadcast loads
+          const uint32_t ra = my_rec + (uint32_t)(g * 4 + u) * 48u;
+          R0[u] = lds128(ra); R1[u] = lds128(ra + 16u); R2[u] = lds128(ra + 32u);
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float ox[4], oy[4], oz[4];
+        int pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 r0 = R0[u], r1 = R1[u], r2 = R2[u];
+          const uint32_t off[4] = {__float_as_uint(r2.x), __float_as_uint(r2.y), __float_as_uint(r2.z), __float_as_uint(r2.w)};
+          const float w[4] = {r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float4 q0 = lds128(ab + joff[k]), q1 = lds128(ab + joff[k] + 16u), q2 = lds128(ab + joff[k] + 32u);
-            const float2 w2 = make_float2(sw[k], sw[k]);
-            if (k == 0) {
-              c0 = __fmul2_rn(w2, make_float2(q0.x, q0.y)); c1 = __fmul2_rn(w2, make_float2(q0.z, q0.w));
-              c2 = __fmul2_rn(w2, make_float2(q1.x, q1.y)); c3 = __fmul2_rn(w2, make_float2(q1.z, q1.w));
-              z0 = __fmul2_rn(w2, make_float2(q2.x, q2.y)); z1 = __fmul2_rn(w2, make_float2(q2.z, q2.w));
-            } else {
-              c0 = __ffma2_rn(w2, make_float2(q0.x, q0.y), c0); c1 = __ffma2_rn(w2, make_float2(q0.z, q0.w), c1);
-              c2 = __ffma2_rn(w2, make_float2(q1.x, q1.y), c2); c3 = __ffma2_rn(w2, make_float2(q1.z, q1.w), c3);
-              z0 = __ffma2_rn(w2, make_float2(q2.x, q2.y), z0); z1 = __ffma2_rn(w2, make_float2(q2.z, q2.w), z1);
+            if (off[k] != cur[k]) {                                 // warp-uniform: the record is per vertex
+              cur[k] = off[k];
+              const float4 q0 = lds128(my_tab + off[k]), q1 = lds128(my_tab + off[k] + 16u), q2 = lds128(my_tab + off[k] + 32u);
+              C[k][0] = make_float2(q0.x, q0.y); C[k][1] = make_float2(q0.z, q0.w);
+              C[k][2] = make_float2(q1.x, q1.y); C[k][3] = make_float2(q1.z, q1.w);
+              C[k][4] = make_float2(q2.x, q2.y); C[k][5] = make_float2(q2.z, q2.w);
             }
           }
-          for (int k = 4; k < a.nnz; ++k) {             // rare: more than 4 non-zero weights
-            const uint32_t jo = (uint32_t)a.skin_idx[k * a.n_pad + v] * 48u;
-            const float w = a.skin_w[k * a.n_pad + v];
-            const float4 q0 = lds128(ab + jo), q1 = lds128(ab + jo + 16u), q2 = lds128(ab + jo + 32u);
-            const float2 w2 = make_float2(w, w);
+          float2 w2 = make_float2(w[0], w[0]);
+          float2 c0 = __fmul2_rn(w2, C[0][0]), c1 = __fmul2_rn(w2, C[0][1]), c2 = __fmul2_rn(w2, C[0][2]);
+          float2 c3 = __fmul2_rn(w2, C[0][3]), z0 = __fmul2_rn(w2, C[0][4]), z1 = __fmul2_rn(w2, C[0][5]);
+#pragma unroll
+          for (int k = 1; k < 4; ++k) {
+            w2 = make_float2(w[k], w[k]);
+            c0 = __ffma2_rn(w2, C[k][0], c0); c1 = __ffma2_rn(w2, C[k][1], c1); c2 = __ffma2_rn(w2, C[k][2], c2);
+            c3 = __ffma2_rn(w2, C[k][3], c3); z0 = __ffma2_rn(w2, C[k][4], z0); z1 = __ffma2_rn(w2, C[k][5], z1);
+          }
+          for (int k = 4; k < a.nnz; ++k) {                         // rare: more than 4 non-zero weights (uncached)
+            const int64_t xi = (int64_t)(k - 4) * a.n_pad_tc + vbase + g * 4 + u;
+            const uint32_t xo = __ldg(a.tc_xoff + xi);
+            const float xw = __ldg(a.tc_xw + xi);
+            const float4 q0 = lds128(my_tab + xo), q1 = lds128(my_tab + xo + 16u), q2 = lds128(my_tab + xo + 32u);
+            w2 = make_float2(xw, xw);
             c0 = __ffma2_rn(w2, make_float2(q0.x, q0.y), c0); c1 = __ffma2_rn(w2, make_float2(q0.z, q0.w), c1);
             c2 = __ffma2_rn(w2, make_float2(q1.x, q1.y), c2); c3 = __ffma2_rn(w2, make_float2(q1.z, q1.w), c3);
             z0 = __ffma2_rn(w2, make_float2(q2.x, q2.y), z0); z1 = __ffma2_rn(w2, make_float2(q2.z, q2.w), z1);
           }
-          const float px = t0 + ax[b], py = t1 + ay[b], pz = t2 + az[b];
+          const float px = r0.x + ax[u], py = r0.y + ay[u], pz = r0.z + az[u];
           float2 xy = __ffma2_rn(c0, make_float2(px, px), c3);
           xy = __ffma2_rn(c1, make_float2(py, py), xy);
           xy = __ffma2_rn(c2, make_float2(pz, pz), xy);
-          ox[b] = xy.x; oy[b] = xy.y;
-          oz[b] = fmaf(z1.x, pz, fmaf(z0.y, py, fmaf(z0.x, px, z1.y)));
+          ox[u] = xy.x; oy[u] = xy.y;
+          oz[u] = fmaf(z1.x, pz, fmaf(z0.y, py, fmaf(z0.x, px, z1.y)));
+          pv[u] = __float_as_int(r0.w);                             // original vertex id, -1 = padding / skipped vertex
         }
         if (FUSE_SDF) {                                  // transforms are world-composed: (ox,oy,oz) is the world point
-          // conservative coarse-cell sign test for the 4 bodies first (4 independent loads), exact sample only
-          // where the cell can hold a negative value
-          float cv[4];
+          bool maybe[4];
+          uint32_t fi[4];
 #pragma unroll
-          for (int b = 0; b < 4; ++b) cv[b] = sdf_coarse_value(a.sdf, cx, cy, cz, sc, ox[b], oy[b], oz[b]);
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            bool neg = false;
-            if (!skip && cv[b] <= 0.0f) {
-              int i0, i1, i2;
-              neg = sdf_sample_point(a.sdf, cx, cy, cz, sc, ox[b], oy[b], oz[b], i0, i1, i2) < 0.0f;
+          for (int u = 0; u < 4; ++u) {
+            if (smem_mask) {
+              const uint32_t f0 = min(__float2uint_rz(fmaf(ox[u], gax, gbx)), dmax0);
+              const uint32_t f1 = min(__float2uint_rz(fmaf(oy[u], gay, gby)), dmax1);
+              const uint32_t f2 = min(__float2uint_rz(fmaf(oz[u], gaz, gbz)), dmax2);
+              const uint32_t ci = ((f0 >> kCoarseShift) * (uint32_t)a.sdf.C1 + (f1 >> kCoarseShift)) * (uint32_t)a.sdf.C2 + (f2 >> kCoarseShift);
+              maybe[u] = pv[u] >= 0 && ((lds32(mask_u32 + (ci >> 5) * 4u) >> (ci & 31u)) & 1u);
+              fi[u] = ((f0 >> 1) * fd1 + (f1 >> 1)) * fd2 + (f2 >> 1);
+            } else {
+              maybe[u] = pv[u] >= 0 && sdf_coarse_value(a.sdf, cx, cy, cz, sc, ox[u], oy[u], oz[u]) <= 0.0f;
+              fi[u] = 0;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, neg);
-            if (lane == 0 && m && n_first + b < a.N) atomicAdd(a.counts + n_first + b, __popc(m));
+          }
+          // level 2 (2^3-cell bits, global) only where level 1 is set; the exact trilinear sample only where both are
+          uint32_t w2v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) w2v[u] = (maybe[u] && smem_mask) ? __ldg(a.sdf.fine_bits + (fi[u] >> 5)) : 0xffffffffu;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (maybe[u] && ((w2v[u] >> (fi[u] & 31u)) & 1u)) {
+              int i0, i1, i2;
+              cnt += sdf_sample_point(a.sdf, cx, cy, cz, sc, ox[u], oy[u], oz[u], i0, i1, i2) < 0.0f ? 1 : 0;
+            }
           }
         } else {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int n = n_first + b;
-            if (n < a.N && a.out != nullptr && v_ok) {
-              const float* x = a.xb + (int64_t)n * EG_XB_DIM;
-              float* o = a.out + ((int64_t)n * a.n_real + v) * 3;
-              o[0] = __fadd_rn(ox[b], __ldg(x)); o[1] = __fadd_rn(oy[b], __ldg(x + 1)); o[2] = __fadd_rn(oz[b], __ldg(x + 2));
+          for (int u = 0; u < 4; ++u) {
+            if (n_ok && a.out != nullptr && pv[u] >= 0) {
+              float* o = a.out + ((int64_t)n * a.n_real + pv[u]) * 3;
+              o[0] = __fadd_rn(ox[u], trx); o[1] = __fadd_rn(oy[u], try_); o[2] = __fadd_rn(oz[u], trz);
             }
           }
         }
-        asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory");     // buffer (c&1) free for chunk c+2
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
+      if (lane == 0) { mbar_arrive(&tmem_empty[buf]); mbar_arrive(&tab_empty[tb]); }   // both buffers of this tile are free
+      if (FUSE_SDF && n_ok && cnt > 0) atomicAdd(a.counts + n, cnt);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -630,6 +699,17 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+// per-call copy of the tc vertex records with the caller's skip mask folded into the id field (-1 = do not count)
+__global__ void tc_fold_skip_kernel(const float4* __restrict__ rec, const uint8_t* __restrict__ skip, int n_pad,
+                                    float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  float4 r0 = rec[i * 3];
+  const int id = __float_as_int(r0.w);
+  if (id >= 0 && skip != nullptr && skip[id] != 0) r0.w = __int_as_float(-1);
+  out[i * 3] = r0; out[i * 3 + 1] = rec[i * 3 + 1]; out[i * 3 + 2] = rec[i * 3 + 2];
 }
 
 // joints [N,127,3] = posed joints ++ vertex joints ++ landmarks (+transl); markers [N,M,3]
@@ -703,6 +783,7 @@ __global__ void rest_pelvis_kernel(const float* __restrict__ betas, int betas_di
 
 static void free_vertex_set(VertexSet& s) {
   cudaFree(s.basis); cudaFree(s.basisT); cudaFree(s.vt); cudaFree(s.skin_idx); cudaFree(s.skin_w);
+  cudaFree(s.tc_rec); cudaFree(s.tc_jl); cudaFree(s.tc_nj); cudaFree(s.tc_xoff); cudaFree(s.tc_xw);
   s = VertexSet();
 }
 
@@ -766,7 +847,7 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
   EG_LAUNCH(lbs_pose_prep_kernel, N, 64, 0, st, xb, betas, betas_div, N, Npad, h->J, h->S,
             h->n_levels, h->hand_l, h->hand_r, h->pose_mean, h->Jt, h->Js, h->parents,
             h->level_joints, h->level_start, h->Ft, want_tc ? h->Ftc : nullptr, h->A, h->Jp, R0, T0,
-            frames_per_env, want_tc ? h->Aw : nullptr);
+            frames_per_env, want_tc ? h->Aw : nullptr, h->cap_Ntc);
   VertArgs a{};
   a.Ft = h->Ft; a.A = h->A; a.xb = xb; a.N = N; a.Npad = Npad; a.J = h->J;
   const int by = (N + TILE_B - 1) / TILE_B;
@@ -785,7 +866,13 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
       CUtensorMap mapB;
       int rc2 = encode_map(h, &mapB, h->Ftc, (uint64_t)h->cap_Ntc, tc::TB);
       if (rc2) return rc2;
-      const int n_vt = s.n_pad / tc::TV, n_bt = (N + tc::TB - 1) / tc::TB;
+      const int n_vt = s.n_vt_tc, n_bt = (N + tc::TB - 1) / tc::TB;
+      a.tc_rec = s.tc_rec; a.tc_jl = s.tc_jl; a.tc_nj = s.tc_nj; a.tc_xoff = s.tc_xoff; a.tc_xw = s.tc_xw;
+      a.n_pad_tc = s.n_pad_tc; a.A_rows = h->cap_Ntc;
+      if (fuse && skip != nullptr) {               // fold the caller's skip mask into a per-call copy of the records
+        EG_LAUNCH(tc_fold_skip_kernel, (s.n_pad_tc + 127) / 128, 128, 0, st, s.tc_rec, skip, s.n_pad_tc, h->rec_call);
+        a.tc_rec = h->rec_call;
+      }
       a.A = h->Aw;      // pair-layout transforms (world-composed when fused: the epilogue goes straight to the SDF sample)
       const int grid_tc = std::min(n_vt * n_bt, kNumSMs);
       prof_begin(st, N);
@@ -814,6 +901,135 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
               h->n_markers, h->n_extra, h->n_lmk, s.n, joints, markers);
   }
   return EG_OK;
+}
+
+// Joint-coherent layout of the full mesh for the tcgen05 kernel (lbs_tc.cuh): vertices sorted by their tuple of
+// skinning joints, cut into tiles of <= 128 vertices touching <= NJ_MAX distinct joints; inside a tile every vertex
+// keeps as many of its (up to 4) register slots as possible on the joint the previous vertex had there, so the
+// epilogue's per-body register cache is reloaded only where the joint really changes.
+static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int32_t>& sidx, const std::vector<float>& sw) {
+  VertexSet& s = h->full;
+  const int V = s.n, nnz = s.nnz, P = h->P, S = h->S;
+  auto jw = [&](int v, int k, int& j, float& w) { j = sidx[(size_t)k * s.n_pad + v]; w = sw[(size_t)k * s.n_pad + v]; };
+  auto cnt = [&](int v) { int c = 0; for (int k = 0; k < nnz; ++k) c += sw[(size_t)k * s.n_pad + v] != 0.0f; return c; };
+  std::vector<int> order(V);
+  for (int v = 0; v < V; ++v) order[v] = v;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    for (int k = 0; k < nnz; ++k) {
+      int jx, jy; float wx, wy;
+      jw(x, k, jx, wx); jw(y, k, jy, wy);
+      if (wx == 0.0f) jx = 1 << 20;
+      if (wy == 0.0f) jy = 1 << 20;
+      if (jx != jy) return jx < jy;
+    }
+    return false;
+  });
+  // tiles
+  std::vector<std::vector<int>> tiles, tile_joints;
+  {
+    std::vector<int> cur, joints;
+    for (int v : order) {
+      std::vector<int> add;
+      for (int k = 0; k < cnt(v); ++k) {
+        int j; float w; jw(v, k, j, w);
+        if (std::find(joints.begin(), joints.end(), j) == joints.end()) add.push_back(j);
+      }
+      if ((int)cur.size() == tc::TV || (int)(joints.size() + add.size()) > tc::NJ_MAX) {
+        tiles.push_back(cur); tile_joints.push_back(joints);
+        cur.clear(); joints.clear(); add.clear();
+        for (int k = 0; k < cnt(v); ++k) { int j; float w; jw(v, k, j, w); add.push_back(j); }
+      }
+      if ((int)add.size() > tc::NJ_MAX) return set_error(EG_ERR_INVALID_ARG, "a vertex has more skinning joints than the tensor-core tile table holds (10)");
+      joints.insert(joints.end(), add.begin(), add.end());
+      cur.push_back(v);
+    }
+    if (!cur.empty()) { tiles.push_back(cur); tile_joints.push_back(joints); }
+  }
+  const int n_vt = (int)tiles.size();
+  const int n_pad = n_vt * tc::TV;
+  const int nx = std::max(nnz - 4, 0);
+  std::vector<float> rec((size_t)n_pad * 12, 0.0f);
+  std::vector<int32_t> jl((size_t)n_vt * tc::NJ_MAX, 0), nj(n_vt, 0);
+  std::vector<uint32_t> xoff((size_t)std::max(nx, 1) * n_pad, 0u);
+  std::vector<float> xw((size_t)std::max(nx, 1) * n_pad, 0.0f);
+  std::vector<int> perm(n_pad, -1);
+  for (int t = 0; t < n_vt; ++t) {
+    const std::vector<int>& J = tile_joints[t];
+    nj[t] = (int)J.size();
+    for (size_t i = 0; i < J.size(); ++i) jl[(size_t)t * tc::NJ_MAX + i] = J[i];
+    auto local = [&](int j) { return (uint32_t)(std::find(J.begin(), J.end(), j) - J.begin()); };
+    int prev[4] = {J.empty() ? 0 : J[0], J.empty() ? 0 : J[0], J.empty() ? 0 : J[0], J.empty() ? 0 : J[0]};
+    for (int i = 0; i < tc::TV; ++i) {
+      float* r = &rec[((size_t)t * tc::TV + i) * 12];
+      int slot_j[4] = {prev[0], prev[1], prev[2], prev[3]};
+      float slot_w[4] = {0.f, 0.f, 0.f, 0.f};
+      int id = -1;
+      if (i < (int)tiles[t].size()) {
+        const int v = id = tiles[t][i];
+        perm[(size_t)t * tc::TV + i] = v;
+        const int c = cnt(v);
+        bool taken[4] = {false, false, false, false};
+        std::vector<std::pair<int, float>> rest;
+        for (int k = 0; k < c; ++k) {
+          int j; float w; jw(v, k, j, w);
+          int hit = -1;
+          for (int q = 0; q < 4; ++q) if (!taken[q] && prev[q] == j) { hit = q; break; }
+          if (hit >= 0) { taken[hit] = true; slot_j[hit] = j; slot_w[hit] = w; }
+          else rest.push_back({j, w});
+        }
+        int xk = 0;
+        for (auto& jwv : rest) {
+          int q = 0;
+          while (q < 4 && taken[q]) ++q;
+          if (q < 4) { taken[q] = true; slot_j[q] = jwv.first; slot_w[q] = jwv.second; }
+          else {                                   // beyond 4 entries: uncached extras
+            xoff[(size_t)xk * n_pad + (size_t)t * tc::TV + i] = local(jwv.first) * (uint32_t)tc::SLOT_BYTES;
+            xw[(size_t)xk * n_pad + (size_t)t * tc::TV + i] = jwv.second;
+            ++xk;
+          }
+        }
+        r[0] = m->v_template[(size_t)v * 3 + 0]; r[1] = m->v_template[(size_t)v * 3 + 1]; r[2] = m->v_template[(size_t)v * 3 + 2];
+      }
+      memcpy(&r[3], &id, 4);
+      for (int q = 0; q < 4; ++q) {
+        r[4 + q] = slot_w[q];
+        const uint32_t o = local(slot_j[q]) * (uint32_t)tc::SLOT_BYTES;
+        memcpy(&r[8 + q], &o, 4);
+        prev[q] = slot_j[q];
+      }
+    }
+  }
+  // planar K-major TF32 copy of the basis in tc order: basisT[c][row][k]; shape rows in hi/hi, hi(again), lo form
+  auto rnd = [](float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    u += 0xFFFu + ((u >> 13) & 1u); u &= ~0x1FFFu;
+    float y; memcpy(&y, &u, 4); return y;
+  };
+  std::vector<float> bt((size_t)3 * n_pad * tc::KT, 0.0f);
+  for (int c = 0; c < 3; ++c)
+    for (int row = 0; row < n_pad; ++row) {
+      const int v = perm[row];
+      if (v < 0) continue;
+      float* dst = &bt[((size_t)c * n_pad + row) * tc::KT];
+      for (int k = 0; k < P; ++k) dst[k] = rnd(m->posedirs[(size_t)k * V * 3 + (size_t)v * 3 + c]);
+      for (int k = 0; k < S; ++k) {
+        const float p = m->shapedirs[((size_t)v * 3 + c) * S + k];
+        const float hi = rnd(p), lo = rnd(p - hi);
+        dst[P + k] = hi;            // x shape_hi
+        dst[P + S + k] = hi;        // x shape_lo
+        dst[P + 2 * S + k] = lo;    // x shape_hi
+      }
+    }
+  s.n_pad_tc = n_pad; s.n_vt_tc = n_vt;
+  int rc = dev_alloc_copy(&s.basisT, bt.data(), bt.size());
+  rc |= dev_alloc_copy(reinterpret_cast<float**>(&s.tc_rec), rec.data(), rec.size());
+  rc |= dev_alloc_copy(reinterpret_cast<float**>(&h->rec_call), rec.data(), rec.size());
+  rc |= dev_alloc_copy(&s.tc_jl, jl.data(), jl.size());
+  rc |= dev_alloc_copy(&s.tc_nj, nj.data(), nj.size());
+  rc |= dev_alloc_copy(&s.tc_xoff, xoff.data(), xoff.size());
+  rc |= dev_alloc_copy(&s.tc_xw, xw.data(), xw.size());
+  if (!rc && h->encode_fn) rc |= encode_map(h, &h->mapA, s.basisT, (uint64_t)3 * n_pad, tc::TV);
+  return rc;
 }
 
 static int build_compact(EgLbs* h, const int32_t* marker_vids, int n_markers) {
@@ -942,29 +1158,7 @@ extern "C" int eg_lbs_create(const EgLbsModel* m, int device, EgLbs** out) {
   ls.push_back((int32_t)lj.size());
   h->n_levels = maxd + 1;
   int rc = 0;
-  {
-    // planar K-major TF32 copy for the tcgen05 mainloop: basisT[c][v][k]; shape rows in hi/hi, hi(again), lo form
-    auto rnd = [](float x) {
-      uint32_t u; memcpy(&u, &x, 4);
-      u += 0xFFFu + ((u >> 13) & 1u); u &= ~0x1FFFu;
-      float y; memcpy(&y, &u, 4); return y;
-    };
-    std::vector<float> bt((size_t)3 * s.n_pad * tc::KT, 0.0f);
-    for (int c = 0; c < 3; ++c)
-      for (int v = 0; v < V; ++v) {
-        float* dst = &bt[((size_t)c * s.n_pad + v) * tc::KT];
-        for (int k = 0; k < P; ++k) dst[k] = rnd(m->posedirs[(size_t)k * V * 3 + (size_t)v * 3 + c]);
-        for (int k = 0; k < S; ++k) {
-          const float p = m->shapedirs[((size_t)v * 3 + c) * S + k];
-          const float hi = rnd(p), lo = rnd(p - hi);
-          dst[P + k] = hi;            // x shape_hi
-          dst[P + S + k] = hi;        // x shape_lo
-          dst[P + 2 * S + k] = lo;    // x shape_hi
-        }
-      }
-    rc |= dev_alloc_copy(&s.basisT, bt.data(), bt.size());
-    if (!rc && h->encode_fn) rc |= encode_map(h, &h->mapA, s.basisT, (uint64_t)3 * s.n_pad, tc::TV);
-  }
+  rc |= build_tc_layout(h, m, sidx, sw);
   rc |= dev_alloc_copy(&s.basis, basis.data(), basis.size());
   rc |= dev_alloc_copy(&s.vt, vt.data(), vt.size());
   rc |= dev_alloc_copy(&s.skin_idx, sidx.data(), sidx.size());
@@ -992,7 +1186,7 @@ extern "C" void eg_lbs_destroy(EgLbs* h) {
   free_vertex_set(h->compact);
   cudaFree(h->Jt); cudaFree(h->Js); cudaFree(h->hand_l); cudaFree(h->hand_r); cudaFree(h->pose_mean);
   cudaFree(h->parents); cudaFree(h->level_joints); cudaFree(h->level_start); cudaFree(h->lmk_bary);
-  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc); cudaFree(h->Aw);
+  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc); cudaFree(h->Aw); cudaFree(h->rec_call);
   delete h;
 }
 

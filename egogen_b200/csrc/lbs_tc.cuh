@@ -1,16 +1,25 @@
 // tcgen05 / TMEM / TMA mainloop of the full-mesh LBS vertex kernel (sm_100a).
 //
-//   D_c[v, n] = sum_k basisT_c[v, k] * F[n, k]      c in {x,y,z}, v = 128 vertices, n = 128 bodies, k = 576
+//   D_c[n, v] = sum_k F[n, k] * basisT_c[v, k]      c in {x,y,z}, n = 128 bodies (UMMA M, TMEM lanes),
+//                                                   v = 80 vertices (UMMA N, TMEM columns), k = 576
 //
-// A operand: basisT [3][n_pad][KT] fp32 (planar x/y/z rows, K-major), pre-rounded to TF32 on the host.
-// B operand: F [N_pad][KT] fp32 written by the prep kernel (TF32-rounded pose features; the shape
+// A operand: F [N_pad][KT] fp32 written by the prep kernel (TF32-rounded pose features; the shape
 //            coefficients are split hi/lo against hi/lo shape rows of the basis so the shape blend keeps
 //            ~fp32 accuracy - see build in lbs.cu).
-// Per CTA (persistent, 1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..19 =
-// epilogue. smem: ring of 2 stages x (3 A tiles 128x32 + 1 B tile 128x32, SWIZZLE_128B) = 128 KB, plus
-// 2 x 48 KB staging of per-body joint transforms for the skinning epilogue.
-// Accumulators: 3 x 128 fp32 columns of TMEM; the epilogue reads its lane (= vertex) with tcgen05.ld,
-// applies skinning (+transl, optional store, optional world transform + SDF sample + penetration count).
+// B operand: basisT [3][n_pad_tc][KT] fp32 (planar x/y/z rows, K-major), pre-rounded to TF32 on the host, rows in
+//            the JOINT-COHERENT vertex order built by eg_lbs_create (vertices sorted by their skinning-joint
+//            tuple, tiles closed at 80 vertices or NJ_MAX distinct joints).
+// Per CTA (persistent, 1 per SM): warp 0 = producer (TMA operand ring + bulk copies of the tile's joint-transform
+// table and vertex records), warp 1 = MMA issuer (+TMEM alloc), warps 4..11 = epilogue.
+// TMEM: TWO accumulator sets of 3 x 80 fp32 columns, so the MMA of tile i+1 runs under the epilogue of tile i.
+// smem: ring of 2 stages x (3 basis tiles 80x32 + 1 feature tile 128x32, SWIZZLE_128B) = 92 KB, two 60 KB tables
+// with the transforms of the tile's <= 10 joints for its 128 bodies (joint-major in HBM, so one 6 KB bulk copy per
+// joint), two 3.75 KB record buffers, 4 KB of SDF coarse-cell sign bits.
+// Epilogue thread = one BODY (its TMEM lane): it walks the tile's vertices, keeps the four skinning-slot transforms
+// of ITS body in registers and reloads a slot from the table only when the (warp-uniform) joint of that slot
+// changes between consecutive vertices - runs of vertices that share joints cost no shared-memory traffic at all,
+// where the vertex-per-lane form needed 12 ld.shared.v4 per (vertex, body). Penetration counts accumulate in a
+// register per body (one atomic per thread and tile).
 #pragma once
 #include <cuda.h>
 
@@ -22,18 +31,32 @@ namespace tc {
 constexpr int KT = 576;            // padded contraction: 486 pose + 3 x 20 shape (hi*hi, lo*hi, hi*lo) + 30 zero
 constexpr int BKT = 32;            // k-chunk per stage: 32 tf32 = 128 B = one swizzle atom row
 constexpr int NCHUNK = KT / BKT;   // 18
-constexpr int TV = 128;            // vertices per tile (UMMA M)
-constexpr int TB = 128;            // bodies per tile (UMMA N)
+constexpr int TV = 80;             // vertices per tile (UMMA N)
+constexpr int TB = 128;            // bodies per tile (UMMA M)
 constexpr int STAGES = 2;
-constexpr int A_TILE_BYTES = TV * BKT * 4;   // 16 KB
-constexpr int B_TILE_BYTES = TB * BKT * 4;   // 16 KB
-constexpr int STAGE_BYTES = 3 * A_TILE_BYTES + B_TILE_BYTES;   // 64 KB
-constexpr int EPI_WARPS = 16;
-constexpr int THREADS = 128 + EPI_WARPS * 32;   // 640
+constexpr int V_TILE_BYTES = TV * BKT * 4;   // 10 KB (basis, one component)
+constexpr int F_TILE_BYTES = TB * BKT * 4;   // 16 KB (features)
+constexpr int STAGE_BYTES = 3 * V_TILE_BYTES + F_TILE_BYTES;   // 46 KB
+constexpr int ACC_COLS = 3 * TV;                 // one accumulator set
 constexpr int TMEM_COLS = 512;
-constexpr int CHUNK_B = 16;                           // bodies per staged joint-transform chunk
-constexpr int ASTAGE_BYTES = CHUNK_B * 64 * 48;        // up to 64 joints x 12 floats per body = 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers, tmem ptr*/ + 2 * ASTAGE_BYTES;
+constexpr int EPI_SUB = 2;                       // epilogue warps per TMEM lane quarter (each takes TV / EPI_SUB vertices)
+constexpr int EPI_WARPS = 4 * EPI_SUB;
+constexpr int THREADS = 128 + EPI_WARPS * 32;   // 384
+constexpr int VPW = TV / EPI_SUB;                // vertices per epilogue warp and tile
+constexpr int NJ_MAX = 10;                       // distinct skinning joints per vertex tile (tiles are closed earlier otherwise)
+constexpr int SLOT_BYTES = TB * 48;              // one joint's transforms for the tile's 128 bodies
+constexpr int TAB_BYTES = NJ_MAX * SLOT_BYTES;   // 60 KB
+constexpr int REC_BYTES = TV * 48;               // the tile's per-vertex records
+constexpr int NTAB = 2;                          // table / record buffers
+constexpr int MASK_WORDS = 1024;                 // coarse-cell sign bits of the SDF grid (32^3 cells for a 256^3 grid)
+constexpr int BAR_BYTES = 256;
+constexpr int OFF_BARS = STAGES * STAGE_BYTES;
+constexpr int OFF_TAB = OFF_BARS + BAR_BYTES;
+constexpr int OFF_REC = OFF_TAB + NTAB * TAB_BYTES;
+constexpr int OFF_MASK = OFF_REC + NTAB * REC_BYTES;
+constexpr int SMEM_BYTES = OFF_MASK + MASK_WORDS * 4 + 1024 /*align slack*/;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(VPW % 4 == 0 && STAGE_BYTES % 1024 == 0 && V_TILE_BYTES % 1024 == 0, "tile geometry");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,6 +84,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// 1-D bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -78,7 +106,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 // cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, K-major A and B, M=128, N=TB
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TB >> 3) << 17) | ((uint32_t)(TV >> 4) << 24);
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TV >> 3) << 17) | ((uint32_t)(TB >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
   asm volatile(
@@ -110,14 +138,22 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
   return r;
 }
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
 __device__ __forceinline__ void cp_async16_u32(uint32_t smem_addr, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem));
 }
 
-// Tile order: vertex tiles are walked in bands of BAND_V tiles (BAND_V x 884 KB of basis ~ 25 MB) with every body
+// Tile order: vertex tiles are walked in bands of BAND_V tiles (BAND_V x 553 KB of basis ~ 24 MB) with every body
 // tile visited inside a band before the next band starts, so the basis band stays L2-resident while it is reused
 // by all body tiles (the full 72.5 MB basis plus features/transforms does not survive a full sweep in L2).
-constexpr int BAND_V = 28;
+constexpr int BAND_V = 44;
 __device__ __forceinline__ void tile_coords(int tile, int n_vt, int n_bt, int& vt, int& bt) {
   const int full = BAND_V * n_bt;
   const int band = tile / full;

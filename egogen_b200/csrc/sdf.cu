@@ -97,6 +97,33 @@ sdf_coarse_kernel(const float* __restrict__ grid, int D0, int D1, int D2, int C0
   coarse[i] = mn;
 }
 
+// dilated by one fine corner per side: min over [8c-1, 8c+9]^3. The tcgen05 LBS epilogue addresses this grid with an
+// FMA-rounded index that can sit one fine cell off the exact grid_sample index right at a coarse-cell boundary; the
+// extra corner keeps "bit clear => the exact sample cannot be negative" true for those points too.
+__global__ void __launch_bounds__(128)
+sdf_coarse_dilated_kernel(const float* __restrict__ grid, int D0, int D1, int D2, int C0, int C1, int C2, int shift,
+                          float* __restrict__ coarse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C0 * C1 * C2) return;
+  const int c2 = i % C2, c1 = (i / C2) % C1, c0 = i / (C1 * C2);
+  const int cs = 1 << shift;
+  float mn = INFINITY;
+  for (int x = max(c0 * cs - 1, 0); x <= min(c0 * cs + cs + 1, D0 - 1); ++x)
+    for (int y = max(c1 * cs - 1, 0); y <= min(c1 * cs + cs + 1, D1 - 1); ++y)
+      for (int z = max(c2 * cs - 1, 0); z <= min(c2 * cs + cs + 1, D2 - 1); ++z)
+        mn = fminf(mn, -grid[((int64_t)x * D1 + y) * D2 + z]);
+  coarse[i] = mn;
+}
+
+// 1 bit per coarse cell: set when the cell may hold a negative sample (coarse <= 0). 4 KB for a 256^3 grid, small
+// enough to sit in shared memory next to the tcgen05 LBS kernel's operand ring.
+__global__ void sdf_coarse_bits_kernel(const float* __restrict__ coarse, int n, uint32_t* __restrict__ bits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool f = i < n && coarse[i] <= 0.0f;
+  const unsigned m = __ballot_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && i < ((n + 31) / 32) * 32) bits[i >> 5] = m;
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t b = (n + block - 1) / block;
   const int64_t cap = (int64_t)kNumSMs * 16;  // multiple of the SM count, grid-stride beyond
@@ -107,10 +134,11 @@ static inline int grid_for(int64_t n, int block) {
 
 }  // namespace eg
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 namespace eg {
-struct CoarseEntry { float* coarse; int D0, D1, D2, C0, C1, C2; };
+struct CoarseEntry { float* coarse; int D0, D1, D2, C0, C1, C2; uint32_t* fine_bits = nullptr; };
 static std::map<const float*, CoarseEntry> g_coarse;
 static std::mutex g_coarse_mu;
 void sdf_attach_coarse(SdfGrid& g) {
@@ -118,6 +146,10 @@ void sdf_attach_coarse(SdfGrid& g) {
   auto it = g_coarse.find(g.grid);
   if (it == g_coarse.end() || it->second.D0 != g.D0 || it->second.D1 != g.D1 || it->second.D2 != g.D2) return;
   g.coarse = it->second.coarse; g.C0 = it->second.C0; g.C1 = it->second.C1; g.C2 = it->second.C2;
+  const int n = g.C0 * g.C1 * g.C2;
+  g.coarse_bits = reinterpret_cast<const uint32_t*>(it->second.coarse + (n + 31) / 32 * 32);
+  g.n_bit_words = (n + 31) / 32;
+  g.fine_bits = it->second.fine_bits;
 }
 }  // namespace eg
 
@@ -130,11 +162,29 @@ extern "C" int eg_sdf_prepare(const float* grid, int D0, int D1, int D2, void* s
   {
     std::lock_guard<std::mutex> lk(g_coarse_mu);
     auto it = g_coarse.find(grid);
-    if (it != g_coarse.end()) { cudaFree(it->second.coarse); g_coarse.erase(it); }
+    if (it != g_coarse.end()) { cudaFree(it->second.coarse); cudaFree(it->second.fine_bits); g_coarse.erase(it); }
   }
   const int n = e.C0 * e.C1 * e.C2;
-  EG_CUDA_CHECK(cudaMalloc((void**)&e.coarse, (size_t)n * sizeof(float)));
+  const int n32 = (n + 31) / 32 * 32;                     // floats, then one bit per cell
+  EG_CUDA_CHECK(cudaMalloc((void**)&e.coarse, (size_t)(n32 + n32 / 32) * sizeof(float)));
   EG_LAUNCH(sdf_coarse_kernel, (n + 127) / 128, 128, 0, as_stream(stream), grid, D0, D1, D2, e.C0, e.C1, e.C2, e.coarse);
+  {
+    // sign bits come from the dilated minimum; level 1 = 8^3 cells (shared-memory resident in the LBS kernel),
+    // level 2 = 2^3 cells (global, consulted only where level 1 is set)
+    const int f0 = (D0 + 1) / 2, f1 = (D1 + 1) / 2, f2 = (D2 + 1) / 2;
+    const int64_t nf = (int64_t)f0 * f1 * f2, nf32 = (nf + 31) / 32 * 32;
+    float* dil = nullptr;
+    EG_CUDA_CHECK(cudaMalloc((void**)&dil, (size_t)std::max<int64_t>(n32, nf32) * sizeof(float)));
+    EG_CUDA_CHECK(cudaMalloc((void**)&e.fine_bits, (size_t)(nf32 / 32) * sizeof(uint32_t)));
+    EG_LAUNCH(sdf_coarse_dilated_kernel, (n + 127) / 128, 128, 0, as_stream(stream), grid, D0, D1, D2, e.C0, e.C1, e.C2,
+              kCoarseShift, dil);
+    EG_LAUNCH(sdf_coarse_bits_kernel, n32 / 128 + 1, 128, 0, as_stream(stream), dil, n,
+              reinterpret_cast<uint32_t*>(e.coarse + n32));
+    EG_LAUNCH(sdf_coarse_dilated_kernel, (int)((nf + 127) / 128), 128, 0, as_stream(stream), grid, D0, D1, D2, f0, f1, f2, 1, dil);
+    EG_LAUNCH(sdf_coarse_bits_kernel, (int)(nf32 / 128 + 1), 128, 0, as_stream(stream), dil, (int)nf, e.fine_bits);
+    EG_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
+    cudaFree(dil);
+  }
   EG_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
   std::lock_guard<std::mutex> lk(g_coarse_mu);
   g_coarse[grid] = e;
@@ -144,7 +194,7 @@ extern "C" int eg_sdf_prepare(const float* grid, int D0, int D1, int D2, void* s
 extern "C" int eg_sdf_release(const float* grid) {
   std::lock_guard<std::mutex> lk(g_coarse_mu);
   auto it = g_coarse.find(grid);
-  if (it != g_coarse.end()) { cudaFree(it->second.coarse); g_coarse.erase(it); }
+  if (it != g_coarse.end()) { cudaFree(it->second.coarse); cudaFree(it->second.fine_bits); g_coarse.erase(it); }
   return EG_OK;
 }
 
