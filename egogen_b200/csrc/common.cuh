@@ -135,6 +135,14 @@ __device__ __forceinline__ float sdf_sample_point(const SdfGrid& g, float cx, fl
   return -acc;
 }
 
+// out-of-line exact sign query for rare paths (one copy of the 8-corner sample instead of one per call site)
+static __device__ __noinline__ bool sdf_exact_negative(const float* grid, int D0, int D1, int D2, float cx, float cy, float cz,
+                                                float s, float x, float y, float z) {
+  SdfGrid g{grid, D0, D1, D2, nullptr, nullptr};
+  int i0, i1, i2;
+  return sdf_sample_point(g, cx, cy, cz, s, x, y, z, i0, i1, i2) < 0.0f;
+}
+
 // value of the conservative coarse cell containing the world point (<= 0: the cell may hold a negative sample);
 // -1 when no coarse grid is attached, so callers fall through to the exact sample.
 __device__ __forceinline__ float sdf_coarse_value(const SdfGrid& g, float cx, float cy, float cz, float s, float x,

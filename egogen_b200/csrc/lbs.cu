@@ -75,6 +75,7 @@ struct EgLbs {
   float4* rec_call = nullptr; // [n_pad_tc][3] per-call vertex records with the skip mask folded in
   int cap_Ntc = 0;
   int use_tc = 1;             // 1: tcgen05/TMEM/TMA mainloop for the full mesh, 0: SIMT mainloop
+  int max_clusters = 64;      // co-resident 2-CTA clusters of the tcgen05 kernel (cudaOccupancyMaxActiveClusters)
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
   CUtensorMap mapA;
 };
@@ -441,7 +442,7 @@ lbs_verts_kernel(const VertArgs a) {
 // tcgen05 vertex kernel (full mesh): persistent, warp-specialised; see lbs_tc.cuh for the tile plan
 // --------------------------------------------------------------------------------------------
 template <bool FUSE_SDF>
-__global__ void __launch_bounds__(tc::THREADS, 1)
+__global__ void __cluster_dims__(tc::CLUSTER, 1, 1) __launch_bounds__(tc::THREADS, 1)
 lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const VertArgs a, int n_vt, int n_bt) {
   using namespace tc;
@@ -458,11 +459,15 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const uint32_t smem_base = smem_u32(smem);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = n_vt * n_bt;
+  // work unit = (vertex tile, PAIR of body tiles); CTA `rank` of the cluster takes body tile 2*pair + rank
+  const int rank = (int)cluster_ctarank();
+  const int n_btp = (n_bt + CLUSTER - 1) / CLUSTER;
+  const int n_tiles = n_vt * n_btp;
+  const int tile0 = blockIdx.x / CLUSTER, tile_step = gridDim.x / CLUSTER;
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER); }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS);
         mbar_init(&tab_full[b], 1); mbar_init(&tab_empty[b], EPI_WARPS);
@@ -475,7 +480,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  cluster_sync_all();                     // barriers of BOTH CTAs are initialised before any remote arrive / multicast
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -483,16 +488,18 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // ===== operand producer: TMA ring =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
         int vt, bt;
-        tile_coords(tile, n_vt, n_bt, vt, bt);
+        tile_coords(tile, n_vt, n_btp, vt, bt);
+        bt = bt * CLUSTER + rank;
         for (int ch = 0; ch < NCHUNK; ++ch) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* st = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-            tma_load_2d(st + c * V_TILE_BYTES, &mapA, &full_bar[stage], ch * BKT, c * a.n_pad_tc + vt * TV);
+          for (int c = 0; c < 3; ++c)       // my half of the basis tile, multicast to both CTAs of the pair
+            tma_load_2d_mc(smem_base + stage * STAGE_BYTES + c * V_TILE_BYTES + rank * HALF_BYTES, &mapA, &full_bar[stage],
+                           ch * BKT, c * a.n_pad_tc + vt * TV + rank * HALF_ROWS, (uint16_t)((1u << CLUSTER) - 1u));
           tma_load_2d(st + 3 * V_TILE_BYTES, &mapB, &full_bar[stage], ch * BKT, bt * TB);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -502,9 +509,10 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // ===== table producer: joint-transform table + vertex records of each tile (bulk copies), decoupled from the ring =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
         int vt, bt;
-        tile_coords(tile, n_vt, n_bt, vt, bt);
+        tile_coords(tile, n_vt, n_btp, vt, bt);
+        bt = bt * CLUSTER + rank;
         const uint32_t tb = it % NTAB, tph = (it / NTAB) & 1u;
         mbar_wait(&tab_empty[tb], tph ^ 1u);                       // epilogue of tile it-NTAB is done with this buffer
         const int nj = __ldg(a.tc_nj + vt);
@@ -520,7 +528,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer: A = feature tile (bodies -> TMEM lanes), B = basis tile of component c (vertices -> columns) =====
     int stage = 0; uint32_t phase = 0, it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
       const uint32_t buf = it & 1u;
       mbar_wait(&tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);         // epilogue of tile it-2 has drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -537,7 +545,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int kk = 0; kk < BKT / 8; ++kk)          // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
               umma_tf32(tmem_base + buf * ACC_COLS + c * TV, df + (uint64_t)(kk * 2), dbs + (uint64_t)(kk * 2), (ch | kk) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
+          umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CLUSTER) - 1u));   // frees the slot in BOTH CTAs' rings
           if (ch == NCHUNK - 1) umma_commit(&tmem_full[buf]);   // accumulators complete
         }
         __syncwarp();
@@ -558,9 +566,11 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (FUSE_SDF) {
       cx = __ldg(a.sdf.center); cy = __ldg(a.sdf.center + 1); cz = __ldg(a.sdf.center + 2);
       sc = __ldg(a.sdf.scale);
-      gax = sc * (float)a.sdf.D0 * 0.5f; gbx = ((1.0f - cx * sc) * (float)a.sdf.D0 - 1.0f) * 0.5f;
-      gay = sc * (float)a.sdf.D1 * 0.5f; gby = ((1.0f - cy * sc) * (float)a.sdf.D1 - 1.0f) * 0.5f;
-      gaz = sc * (float)a.sdf.D2 * 0.5f; gbz = ((1.0f - cz * sc) * (float)a.sdf.D2 - 1.0f) * 0.5f;
+      // fine index = x * (s D / 2) + ((1 - c s) D - 1) / 2; the epilogue wants the 8^3-cell index, so both are / 8
+      const float inv = 1.0f / (float)(1 << kCoarseShift);
+      gax = sc * (float)a.sdf.D0 * 0.5f * inv; gbx = ((1.0f - cx * sc) * (float)a.sdf.D0 - 1.0f) * 0.5f * inv;
+      gay = sc * (float)a.sdf.D1 * 0.5f * inv; gby = ((1.0f - cy * sc) * (float)a.sdf.D1 - 1.0f) * 0.5f * inv;
+      gaz = sc * (float)a.sdf.D2 * 0.5f * inv; gbz = ((1.0f - cz * sc) * (float)a.sdf.D2 - 1.0f) * 0.5f * inv;
       if (smem_mask) {
         uint32_t* mk = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
         for (int i = eidx; i < a.sdf.n_bit_words; i += NEPI) mk[i] = __ldg(a.sdf.coarse_bits + i);
@@ -568,10 +578,12 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");         // sign bits visible to every epilogue warp
     const uint32_t dmax0 = (uint32_t)(a.sdf.D0 - 1), dmax1 = (uint32_t)(a.sdf.D1 - 1), dmax2 = (uint32_t)(a.sdf.D2 - 1);
+    const uint32_t cmax0 = (uint32_t)(a.sdf.C0 - 1), cmax1 = (uint32_t)(a.sdf.C1 - 1), cmax2 = (uint32_t)(a.sdf.C2 - 1);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
       int vt, bt;
-      tile_coords(tile, n_vt, n_bt, vt, bt);
+      tile_coords(tile, n_vt, n_btp, vt, bt);
+        bt = bt * CLUSTER + rank;
       const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
       const uint32_t tb = it % NTAB, tph = (it / NTAB) & 1u;
       const uint32_t my_tab = smem_base + OFF_TAB + tb * TAB_BYTES + (uint32_t)(q * 32 + lane) * 48u;
@@ -583,7 +595,6 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (!FUSE_SDF && n_ok) { const float* x = a.xb + (int64_t)n * EG_XB_DIM; trx = __ldg(x); try_ = __ldg(x + 1); trz = __ldg(x + 2); }
       int cnt = 0;
       float2 C[4][6];                                               // register cache: slot k -> transform of MY body
-      uint32_t cur[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -607,30 +618,20 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float ox[4], oy[4], oz[4];
         int pv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 r0 = R0[u], r1 = R1[u], r2 = R2[u];
-          const uint32_t off[4] = {__float_as_uint(r2.x), __float_as_uint(r2.y), __float_as_uint(r2.z), __float_as_uint(r2.w)};
-          const float w[4] = {r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (off[k] != cur[k]) {                                 // warp-uniform: the record is per vertex
-              cur[k] = off[k];
-              const float4 q0 = lds128(my_tab + off[k]), q1 = lds128(my_tab + off[k] + 16u), q2 = lds128(my_tab + off[k] + 32u);
-              C[k][0] = make_float2(q0.x, q0.y); C[k][1] = make_float2(q0.z, q0.w);
-              C[k][2] = make_float2(q1.x, q1.y); C[k][3] = make_float2(q1.z, q1.w);
-              C[k][4] = make_float2(q2.x, q2.y); C[k][5] = make_float2(q2.z, q2.w);
-            }
-          }
-          float2 w2 = make_float2(w[0], w[0]);
+        // blend T = sum_k w_k C[k] (packed FMAs) and apply it to the posed-blend vertex
+        auto blend_apply = [&](int u, const float4& r0, const float4& r1) {
+          float2 w2 = make_float2(r1.x, r1.x);
           float2 c0 = __fmul2_rn(w2, C[0][0]), c1 = __fmul2_rn(w2, C[0][1]), c2 = __fmul2_rn(w2, C[0][2]);
           float2 c3 = __fmul2_rn(w2, C[0][3]), z0 = __fmul2_rn(w2, C[0][4]), z1 = __fmul2_rn(w2, C[0][5]);
-#pragma unroll
-          for (int k = 1; k < 4; ++k) {
-            w2 = make_float2(w[k], w[k]);
-            c0 = __ffma2_rn(w2, C[k][0], c0); c1 = __ffma2_rn(w2, C[k][1], c1); c2 = __ffma2_rn(w2, C[k][2], c2);
-            c3 = __ffma2_rn(w2, C[k][3], c3); z0 = __ffma2_rn(w2, C[k][4], z0); z1 = __ffma2_rn(w2, C[k][5], z1);
-          }
+          w2 = make_float2(r1.y, r1.y);
+          c0 = __ffma2_rn(w2, C[1][0], c0); c1 = __ffma2_rn(w2, C[1][1], c1); c2 = __ffma2_rn(w2, C[1][2], c2);
+          c3 = __ffma2_rn(w2, C[1][3], c3); z0 = __ffma2_rn(w2, C[1][4], z0); z1 = __ffma2_rn(w2, C[1][5], z1);
+          w2 = make_float2(r1.z, r1.z);
+          c0 = __ffma2_rn(w2, C[2][0], c0); c1 = __ffma2_rn(w2, C[2][1], c1); c2 = __ffma2_rn(w2, C[2][2], c2);
+          c3 = __ffma2_rn(w2, C[2][3], c3); z0 = __ffma2_rn(w2, C[2][4], z0); z1 = __ffma2_rn(w2, C[2][5], z1);
+          w2 = make_float2(r1.w, r1.w);
+          c0 = __ffma2_rn(w2, C[3][0], c0); c1 = __ffma2_rn(w2, C[3][1], c1); c2 = __ffma2_rn(w2, C[3][2], c2);
+          c3 = __ffma2_rn(w2, C[3][3], c3); z0 = __ffma2_rn(w2, C[3][4], z0); z1 = __ffma2_rn(w2, C[3][5], z1);
           for (int k = 4; k < a.nnz; ++k) {                         // rare: more than 4 non-zero weights (uncached)
             const int64_t xi = (int64_t)(k - 4) * a.n_pad_tc + vbase + g * 4 + u;
             const uint32_t xo = __ldg(a.tc_xoff + xi);
@@ -648,33 +649,64 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           ox[u] = xy.x; oy[u] = xy.y;
           oz[u] = fmaf(z1.x, pz, fmaf(z0.y, py, fmaf(z0.x, px, z1.y)));
           pv[u] = __float_as_int(r0.w);                             // original vertex id, -1 = padding / skipped vertex
+        };
+        const uint32_t gchg = (__float_as_uint(R2[0].x) | __float_as_uint(R2[1].x) | __float_as_uint(R2[2].x) |
+                               __float_as_uint(R2[3].x)) >> 24;
+        if (gchg == 0) {                                            // common: the 4 vertices keep all four cached slots
+#pragma unroll
+          for (int u = 0; u < 4; ++u) blend_apply(u, R0[u], R1[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 r2 = R2[u];
+            const uint32_t chg = __float_as_uint(r2.x) >> 24;       // warp-uniform: the record is per vertex
+            const uint32_t off[4] = {__float_as_uint(r2.x) & 0xffffffu, __float_as_uint(r2.y), __float_as_uint(r2.z), __float_as_uint(r2.w)};
+            if (chg) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (chg & (1u << k)) {
+                  const float4 q0 = lds128(my_tab + off[k]), q1 = lds128(my_tab + off[k] + 16u), q2 = lds128(my_tab + off[k] + 32u);
+                  C[k][0] = make_float2(q0.x, q0.y); C[k][1] = make_float2(q0.z, q0.w);
+                  C[k][2] = make_float2(q1.x, q1.y); C[k][3] = make_float2(q1.z, q1.w);
+                  C[k][4] = make_float2(q2.x, q2.y); C[k][5] = make_float2(q2.z, q2.w);
+                }
+              }
+            }
+            blend_apply(u, R0[u], R1[u]);
+          }
         }
         if (FUSE_SDF) {                                  // transforms are world-composed: (ox,oy,oz) is the world point
-          bool maybe[4];
-          uint32_t fi[4];
+          if (smem_mask) {
+            // level 1: one FMA + one saturating convert per axis straight to the 8^3-cell index, sign bit from smem
+            uint32_t m1 = 0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (smem_mask) {
-              const uint32_t f0 = min(__float2uint_rz(fmaf(ox[u], gax, gbx)), dmax0);
-              const uint32_t f1 = min(__float2uint_rz(fmaf(oy[u], gay, gby)), dmax1);
-              const uint32_t f2 = min(__float2uint_rz(fmaf(oz[u], gaz, gbz)), dmax2);
-              const uint32_t ci = ((f0 >> kCoarseShift) * (uint32_t)a.sdf.C1 + (f1 >> kCoarseShift)) * (uint32_t)a.sdf.C2 + (f2 >> kCoarseShift);
-              maybe[u] = pv[u] >= 0 && ((lds32(mask_u32 + (ci >> 5) * 4u) >> (ci & 31u)) & 1u);
-              fi[u] = ((f0 >> 1) * fd1 + (f1 >> 1)) * fd2 + (f2 >> 1);
-            } else {
-              maybe[u] = pv[u] >= 0 && sdf_coarse_value(a.sdf, cx, cy, cz, sc, ox[u], oy[u], oz[u]) <= 0.0f;
-              fi[u] = 0;
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t u0 = min(__float2uint_rz(fmaf(ox[u], gax, gbx)), cmax0);
+              const uint32_t u1 = min(__float2uint_rz(fmaf(oy[u], gay, gby)), cmax1);
+              const uint32_t u2 = min(__float2uint_rz(fmaf(oz[u], gaz, gbz)), cmax2);
+              const uint32_t ci = (u0 * (uint32_t)a.sdf.C1 + u1) * (uint32_t)a.sdf.C2 + u2;
+              const uint32_t bit = (lds32(mask_u32 + (ci >> 5) * 4u) >> (ci & 31u)) & 1u;
+              m1 |= (pv[u] >= 0 ? bit : 0u) << u;
             }
-          }
-          // level 2 (2^3-cell bits, global) only where level 1 is set; the exact trilinear sample only where both are
-          uint32_t w2v[4];
+            if (m1) {                                    // rare: level 2 (2^3-cell bits, global), then the exact sample
 #pragma unroll
-          for (int u = 0; u < 4; ++u) w2v[u] = (maybe[u] && smem_mask) ? __ldg(a.sdf.fine_bits + (fi[u] >> 5)) : 0xffffffffu;
+              for (int u = 0; u < 4; ++u) {
+                if (m1 & (1u << u)) {
+                  const float s8 = (float)(1 << (kCoarseShift - 1));
+                  const uint32_t f0 = min(__float2uint_rz(fmaf(ox[u], gax, gbx) * s8), (dmax0 >> 1));
+                  const uint32_t f1 = min(__float2uint_rz(fmaf(oy[u], gay, gby) * s8), (dmax1 >> 1));
+                  const uint32_t f2 = min(__float2uint_rz(fmaf(oz[u], gaz, gbz) * s8), (dmax2 >> 1));
+                  const uint32_t fi = (f0 * fd1 + f1) * fd2 + f2;
+                  if ((__ldg(a.sdf.fine_bits + (fi >> 5)) >> (fi & 31u)) & 1u)
+                    cnt += sdf_exact_negative(a.sdf.grid, a.sdf.D0, a.sdf.D1, a.sdf.D2, cx, cy, cz, sc, ox[u], oy[u], oz[u]) ? 1 : 0;
+                }
+              }
+            }
+          } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (maybe[u] && ((w2v[u] >> (fi[u] & 31u)) & 1u)) {
-              int i0, i1, i2;
-              cnt += sdf_sample_point(a.sdf, cx, cy, cz, sc, ox[u], oy[u], oz[u], i0, i1, i2) < 0.0f ? 1 : 0;
+            for (int u = 0; u < 4; ++u) {
+              if (pv[u] >= 0 && sdf_coarse_value(a.sdf, cx, cy, cz, sc, ox[u], oy[u], oz[u]) <= 0.0f)
+                cnt += sdf_exact_negative(a.sdf.grid, a.sdf.D0, a.sdf.D1, a.sdf.D2, cx, cy, cz, sc, ox[u], oy[u], oz[u]) ? 1 : 0;
             }
           }
         } else {
@@ -694,7 +726,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  cluster_sync_all();                     // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -796,14 +828,14 @@ static int ensure_workspace(EgLbs* h, int N) {
   h->cap_N = 0;
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Ft, (size_t)KPAD * cap * sizeof(float)));
   EG_CUDA_CHECK(cudaMemset(h->Ft, 0, (size_t)KPAD * cap * sizeof(float)));
-  const size_t cap128 = ((size_t)cap + tc::TB - 1) / tc::TB * tc::TB;   // the tc epilogue stages whole 16-body chunks
+  const size_t cap128 = ((size_t)cap + tc::CLUSTER * tc::TB - 1) / (tc::CLUSTER * tc::TB) * (tc::CLUSTER * tc::TB);   // whole body-tile pairs
   EG_CUDA_CHECK(cudaMalloc((void**)&h->A, cap128 * h->J * 12 * sizeof(float)));
   EG_CUDA_CHECK(cudaMemset(h->A, 0, cap128 * h->J * 12 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Aw, cap128 * h->J * 12 * sizeof(float)));
   EG_CUDA_CHECK(cudaMemset(h->Aw, 0, cap128 * h->J * 12 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Jp, (size_t)cap * h->J * 3 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->cout_, (size_t)cap * 512 * 3 * sizeof(float)));
-  h->cap_Ntc = (cap + tc::TB - 1) / tc::TB * tc::TB;
+  h->cap_Ntc = (int)cap128;
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Ftc, (size_t)h->cap_Ntc * tc::KT * sizeof(float)));
   EG_CUDA_CHECK(cudaMemset(h->Ftc, 0, (size_t)h->cap_Ntc * tc::KT * sizeof(float)));
   h->cap_N = cap;
@@ -874,7 +906,8 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
         a.tc_rec = h->rec_call;
       }
       a.A = h->Aw;      // pair-layout transforms (world-composed when fused: the epilogue goes straight to the SDF sample)
-      const int grid_tc = std::min(n_vt * n_bt, kNumSMs);
+      const int n_btp = (n_bt + tc::CLUSTER - 1) / tc::CLUSTER;
+      const int grid_tc = tc::CLUSTER * std::min(n_vt * n_btp, h->max_clusters);
       prof_begin(st, N);
       if (fuse) EG_LAUNCH(lbs_verts_tc_kernel<true>, grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
       else EG_LAUNCH(lbs_verts_tc_kernel<false>, grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
@@ -991,11 +1024,18 @@ static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int3
         r[0] = m->v_template[(size_t)v * 3 + 0]; r[1] = m->v_template[(size_t)v * 3 + 1]; r[2] = m->v_template[(size_t)v * 3 + 2];
       }
       memcpy(&r[3], &id, 4);
+      // bit 24+q of the first offset word: slot q differs from the previous vertex of the same epilogue warp's
+      // range (every range of VPW vertices starts with all four set) -> the epilogue reloads exactly those slots
+      uint32_t chg = (i % tc::VPW == 0) ? 0xFu : 0u;
       for (int q = 0; q < 4; ++q) {
         r[4 + q] = slot_w[q];
-        const uint32_t o = local(slot_j[q]) * (uint32_t)tc::SLOT_BYTES;
-        memcpy(&r[8 + q], &o, 4);
+        if (slot_j[q] != prev[q]) chg |= 1u << q;
         prev[q] = slot_j[q];
+      }
+      for (int q = 0; q < 4; ++q) {
+        uint32_t o = local(slot_j[q]) * (uint32_t)tc::SLOT_BYTES;
+        if (q == 0) o |= chg << 24;
+        memcpy(&r[8 + q], &o, 4);
       }
     }
   }
@@ -1028,7 +1068,7 @@ static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int3
   rc |= dev_alloc_copy(&s.tc_nj, nj.data(), nj.size());
   rc |= dev_alloc_copy(&s.tc_xoff, xoff.data(), xoff.size());
   rc |= dev_alloc_copy(&s.tc_xw, xw.data(), xw.size());
-  if (!rc && h->encode_fn) rc |= encode_map(h, &h->mapA, s.basisT, (uint64_t)3 * n_pad, tc::TV);
+  if (!rc && h->encode_fn) rc |= encode_map(h, &h->mapA, s.basisT, (uint64_t)3 * n_pad, tc::HALF_ROWS);
   return rc;
 }
 
@@ -1082,6 +1122,19 @@ extern "C" int eg_lbs_create(const EgLbsModel* m, int device, EgLbs** out) {
   EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
   EgLbs* h = new EgLbs();
   h->device = device;
+  {
+    // persistent kernel: the grid must not exceed what is co-resident (a GPC with an odd SM count strands one SM)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs / tc::CLUSTER * tc::CLUSTER); cfg.blockDim = dim3(tc::THREADS); cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = tc::CLUSTER; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, lbs_verts_tc_kernel<true>, &cfg) == cudaSuccess && nc > 0)
+      h->max_clusters = std::min(nc, kNumSMs / tc::CLUSTER);
+    else
+      cudaGetLastError();
+  }
   {
     cudaDriverEntryPointQueryResult qres;
     void* fn = nullptr;

@@ -9,8 +9,10 @@
 // B operand: basisT [3][n_pad_tc][KT] fp32 (planar x/y/z rows, K-major), pre-rounded to TF32 on the host, rows in
 //            the JOINT-COHERENT vertex order built by eg_lbs_create (vertices sorted by their skinning-joint
 //            tuple, tiles closed at 80 vertices or NJ_MAX distinct joints).
-// Per CTA (persistent, 1 per SM): warp 0 = producer (TMA operand ring + bulk copies of the tile's joint-transform
-// table and vertex records), warp 1 = MMA issuer (+TMEM alloc), warps 4..11 = epilogue.
+// Per CTA (persistent, 1 per SM): warp 0 = operand producer (TMA ring), warp 1 = MMA issuer (+TMEM alloc), warp 2 =
+// table producer (bulk copies of the tile's joint-transform table and vertex records), warps 4..11 = epilogue.
+// CTAs run as CLUSTERS OF 2 on the same vertex tile and adjacent body tiles: each CTA loads half of every basis tile
+// and multicasts it to both, so the basis (the bulk of the L2->SM traffic) crosses the fabric once per pair.
 // TMEM: TWO accumulator sets of 3 x 80 fp32 columns, so the MMA of tile i+1 runs under the epilogue of tile i.
 // smem: ring of 2 stages x (3 basis tiles 80x32 + 1 feature tile 128x32, SWIZZLE_128B) = 92 KB, two 60 KB tables
 // with the transforms of the tile's <= 10 joints for its 128 bodies (joint-major in HBM, so one 6 KB bulk copy per
@@ -34,7 +36,10 @@ constexpr int NCHUNK = KT / BKT;   // 18
 constexpr int TV = 80;             // vertices per tile (UMMA N)
 constexpr int TB = 128;            // bodies per tile (UMMA M)
 constexpr int STAGES = 2;
+constexpr int CLUSTER = 1;          // CTAs per cluster: same vertex tile, adjacent body tiles; basis tiles are multicast
+constexpr int HALF_ROWS = 80 / CLUSTER;   // basis rows each CTA of the pair loads (and multicasts) per component
 constexpr int V_TILE_BYTES = TV * BKT * 4;   // 10 KB (basis, one component)
+constexpr int HALF_BYTES = HALF_ROWS * BKT * 4;
 constexpr int F_TILE_BYTES = TB * BKT * 4;   // 16 KB (features)
 constexpr int STAGE_BYTES = 3 * V_TILE_BYTES + F_TILE_BYTES;   // 46 KB
 constexpr int ACC_COLS = 3 * TV;                 // one accumulator set
@@ -56,6 +61,7 @@ constexpr int OFF_REC = OFF_TAB + NTAB * TAB_BYTES;
 constexpr int OFF_MASK = OFF_REC + NTAB * REC_BYTES;
 constexpr int SMEM_BYTES = OFF_MASK + MASK_WORDS * 4 + 1024 /*align slack*/;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(HALF_ROWS * CLUSTER == TV && HALF_BYTES % 1024 == 0, "multicast split");
 static_assert(VPW % 4 == 0 && STAGE_BYTES % 1024 == 0 && V_TILE_BYTES % 1024 == 0, "tile geometry");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,6 +89,27 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// multicast variant: the box lands at the same CTA-relative offset (and signals the same-offset mbarrier) in every
+// CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // 1-D bulk copy global -> shared, completion counted on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gmem, uint32_t bytes, uint64_t* bar) {
