@@ -23,6 +23,8 @@
 #include <vector>
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "lbs_tc.cuh"
 
@@ -42,7 +44,7 @@ struct VertexSet {
   int n = 0, n_pad = 0, nnz = 0;
   float* basis = nullptr;
   // tcgen05 path (full set only): joint-coherent vertex order, see build_tc_layout()
-  float* basisT = nullptr;   // [3][n_pad_tc][tc::KT] planar K-major TF32-rounded copy of the basis, rows in tc order
+  __half* basisT = nullptr;  // [3][n_pad_tc][tc::KT] planar K-major fp16 copy of the basis, rows in tc order
   float4* tc_rec = nullptr;  // [n_pad_tc][3] per-vertex records
   int32_t* tc_jl = nullptr;  // [n_vt_tc][NJ_MAX]
   int32_t* tc_nj = nullptr;  // [n_vt_tc]
@@ -70,7 +72,7 @@ struct EgLbs {
   // workspace
   int cap_N = 0;
   float *Ft = nullptr, *A = nullptr, *Jp = nullptr, *cout_ = nullptr;
-  float* Ftc = nullptr;       // [cap_N rounded up to 128][tc::KT] features for the tcgen05 mainloop
+  __half* Ftc = nullptr;      // [cap_Ntc][tc::KT] fp16 features for the tcgen05 mainloop
   float* Aw = nullptr;        // [J][cap_Ntc][12] joint-major transforms in the tensor-core epilogue's pair layout
   float4* rec_call = nullptr; // [n_pad_tc][3] per-call vertex records with the skip mask folded in
   int cap_Ntc = 0;
@@ -98,7 +100,7 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
                      const float* __restrict__ pose_mean, const float* __restrict__ Jt,
                      const float* __restrict__ Js, const int32_t* __restrict__ parents,
                      const int32_t* __restrict__ level_joints, const int32_t* __restrict__ level_start,
-                     float* __restrict__ Ft, float* __restrict__ Ftc, float* __restrict__ A,
+                     float* __restrict__ Ft, __half* __restrict__ Ftc, float* __restrict__ A,
                      float* __restrict__ Jp, const float* __restrict__ R0w, const float* __restrict__ T0w,
                      int frames_per_env, float* __restrict__ Aw, int AwRows) {
   const int n = blockIdx.x;
@@ -168,7 +170,7 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
     }
     Ft[(int64_t)k * Npad + n] = v;
   }
-  // same features for the tensor-core mainloop: row-major [n][KT], pose part rounded to TF32 (rna), shape
+  // same features for the tensor-core mainloop: row-major [n][KT] fp16 (round-to-nearest), shape
   // coefficients split hi/lo and laid against the hi/hi, lo/hi, hi/lo shape rows of basisT
   if (Ftc != nullptr) {
     const int npose = (J - 1) * 9;
@@ -176,13 +178,13 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
       float v = 0.0f;
       if (k < npose) {
         const int j = 1 + k / 9, e = k % 9;
-        v = tf32_rna(R[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f));
+        v = R[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
       } else if (k < npose + 3 * S) {
         const int seg = (k - npose) / S, q = (k - npose) % S;
-        const float hi = tf32_rna(shape[q]);
-        v = seg == 1 ? tf32_rna(shape[q] - hi) : hi;
+        const float hi = __half2float(__float2half_rn(shape[q]));
+        v = seg == 1 ? shape[q] - hi : hi;
       }
-      Ftc[(int64_t)n * tc::KT + k] = v;
+      Ftc[(int64_t)n * tc::KT + k] = __float2half_rn(v);
     }
   }
 
@@ -542,8 +544,8 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           for (int c = 0; c < 3; ++c) {
             const uint64_t dbs = make_desc(sbase + c * V_TILE_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < BKT / 8; ++kk)          // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
-              umma_tf32(tmem_base + buf * ACC_COLS + c * TV, df + (uint64_t)(kk * 2), dbs + (uint64_t)(kk * 2), (ch | kk) ? 1u : 0u);
+            for (int kk = 0; kk < BKT / UMMA_K; ++kk)     // UMMA_K = 16 fp16: advance 32 B inside the swizzle atom
+              umma_f16(tmem_base + buf * ACC_COLS + c * TV, df + (uint64_t)(kk * 2), dbs + (uint64_t)(kk * 2), (ch | kk) ? 1u : 0u);
           }
           umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CLUSTER) - 1u));   // frees the slot in BOTH CTAs' rings
           if (ch == NCHUNK - 1) umma_commit(&tmem_full[buf]);   // accumulators complete
@@ -824,7 +826,8 @@ static int ensure_workspace(EgLbs* h, int N) {
   int cap = std::max(N, 64);
   cap = (cap + 31) / 32 * 32;
   cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc); cudaFree(h->Aw);
-  h->Ft = h->A = h->Jp = h->cout_ = h->Ftc = h->Aw = nullptr;
+  h->Ft = h->A = h->Jp = h->cout_ = h->Aw = nullptr;
+  h->Ftc = nullptr;
   h->cap_N = 0;
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Ft, (size_t)KPAD * cap * sizeof(float)));
   EG_CUDA_CHECK(cudaMemset(h->Ft, 0, (size_t)KPAD * cap * sizeof(float)));
@@ -836,8 +839,8 @@ static int ensure_workspace(EgLbs* h, int N) {
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Jp, (size_t)cap * h->J * 3 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->cout_, (size_t)cap * 512 * 3 * sizeof(float)));
   h->cap_Ntc = (int)cap128;
-  EG_CUDA_CHECK(cudaMalloc((void**)&h->Ftc, (size_t)h->cap_Ntc * tc::KT * sizeof(float)));
-  EG_CUDA_CHECK(cudaMemset(h->Ftc, 0, (size_t)h->cap_Ntc * tc::KT * sizeof(float)));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->Ftc, (size_t)h->cap_Ntc * tc::KT * sizeof(__half)));
+  EG_CUDA_CHECK(cudaMemset(h->Ftc, 0, (size_t)h->cap_Ntc * tc::KT * sizeof(__half)));
   h->cap_N = cap;
   return EG_OK;
 }
@@ -846,14 +849,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// 2-D fp32 tensor [rows][tc::KT] (K contiguous), box = [32 k][box_rows], SWIZZLE_128B
-static int encode_map(EgLbs* h, CUtensorMap* map, const float* base, uint64_t rows, uint32_t box_rows) {
+// 2-D fp16 tensor [rows][tc::KT] (K contiguous), box = [64 k][box_rows], SWIZZLE_128B
+static int encode_map(EgLbs* h, CUtensorMap* map, const __half* base, uint64_t rows, uint32_t box_rows) {
   if (!h->encode_fn) return set_error(EG_ERR_STATE, "cuTensorMapEncodeTiled unavailable");
   const cuuint64_t dims[2] = {(cuuint64_t)tc::KT, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)tc::KT * sizeof(float)};
+  const cuuint64_t strides[1] = {(cuuint64_t)tc::KT * sizeof(__half)};
   const cuuint32_t box[2] = {(cuuint32_t)tc::BKT, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = ((EncodeTiledFn)h->encode_fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims,
+  CUresult r = ((EncodeTiledFn)h->encode_fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims,
                                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1039,25 +1042,21 @@ static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int3
       }
     }
   }
-  // planar K-major TF32 copy of the basis in tc order: basisT[c][row][k]; shape rows in hi/hi, hi(again), lo form
-  auto rnd = [](float x) {
-    uint32_t u; memcpy(&u, &x, 4);
-    u += 0xFFFu + ((u >> 13) & 1u); u &= ~0x1FFFu;
-    float y; memcpy(&y, &u, 4); return y;
-  };
-  std::vector<float> bt((size_t)3 * n_pad * tc::KT, 0.0f);
+  // planar K-major fp16 copy of the basis in tc order: basisT[c][row][k]; shape rows in hi/hi, hi(again), lo form
+  auto rnd = [](float x) { return __half2float(__float2half_rn(x)); };
+  std::vector<__half> bt((size_t)3 * n_pad * tc::KT, __float2half_rn(0.0f));
   for (int c = 0; c < 3; ++c)
     for (int row = 0; row < n_pad; ++row) {
       const int v = perm[row];
       if (v < 0) continue;
-      float* dst = &bt[((size_t)c * n_pad + row) * tc::KT];
-      for (int k = 0; k < P; ++k) dst[k] = rnd(m->posedirs[(size_t)k * V * 3 + (size_t)v * 3 + c]);
+      __half* dst = &bt[((size_t)c * n_pad + row) * tc::KT];
+      for (int k = 0; k < P; ++k) dst[k] = __float2half_rn(m->posedirs[(size_t)k * V * 3 + (size_t)v * 3 + c]);
       for (int k = 0; k < S; ++k) {
         const float p = m->shapedirs[((size_t)v * 3 + c) * S + k];
-        const float hi = rnd(p), lo = rnd(p - hi);
-        dst[P + k] = hi;            // x shape_hi
-        dst[P + S + k] = hi;        // x shape_lo
-        dst[P + 2 * S + k] = lo;    // x shape_hi
+        const float hi = rnd(p);
+        dst[P + k] = __float2half_rn(hi);            // x shape_hi
+        dst[P + S + k] = __float2half_rn(hi);        // x shape_lo
+        dst[P + 2 * S + k] = __float2half_rn(p - hi);   // x shape_hi
       }
     }
   s.n_pad_tc = n_pad; s.n_vt_tc = n_vt;

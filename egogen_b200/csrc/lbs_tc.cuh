@@ -3,10 +3,12 @@
 //   D_c[n, v] = sum_k F[n, k] * basisT_c[v, k]      c in {x,y,z}, n = 128 bodies (UMMA M, TMEM lanes),
 //                                                   v = 80 vertices (UMMA N, TMEM columns), k = 576
 //
-// A operand: F [N_pad][KT] fp32 written by the prep kernel (TF32-rounded pose features; the shape
-//            coefficients are split hi/lo against hi/lo shape rows of the basis so the shape blend keeps
-//            ~fp32 accuracy - see build in lbs.cu).
-// B operand: basisT [3][n_pad_tc][KT] fp32 (planar x/y/z rows, K-major), pre-rounded to TF32 on the host, rows in
+// Operands are FP16 (kind::f16, fp32 accumulation in TMEM): fp16 carries the same 10-bit mantissa as TF32, so for
+// every value in fp16's normal range the products are the ones the TF32 form produced, at half the operand bytes
+// (the mainloop is bound by the L2->SM operand feed) and twice the tensor rate.
+// A operand: F [N_pad][KT] fp16 written by the prep kernel (pose features; the shape coefficients are split hi/lo
+//            against hi/lo shape rows of the basis so the shape blend keeps ~fp32 accuracy - see build in lbs.cu).
+// B operand: basisT [3][n_pad_tc][KT] fp16 (planar x/y/z rows, K-major), rounded on the host, rows in
 //            the JOINT-COHERENT vertex order built by eg_lbs_create (vertices sorted by their skinning-joint
 //            tuple, tiles closed at 80 vertices or NJ_MAX distinct joints).
 // Per CTA (persistent, 1 per SM): warp 0 = operand producer (TMA ring), warp 1 = MMA issuer (+TMEM alloc), warp 2 =
@@ -14,7 +16,7 @@
 // CTAs run as CLUSTERS OF 2 on the same vertex tile and adjacent body tiles: each CTA loads half of every basis tile
 // and multicasts it to both, so the basis (the bulk of the L2->SM traffic) crosses the fabric once per pair.
 // TMEM: TWO accumulator sets of 3 x 80 fp32 columns, so the MMA of tile i+1 runs under the epilogue of tile i.
-// smem: ring of 2 stages x (3 basis tiles 80x32 + 1 feature tile 128x32, SWIZZLE_128B) = 92 KB, two 60 KB tables
+// smem: ring of 2 stages x (3 basis tiles 80x64 + 1 feature tile 128x64 fp16, SWIZZLE_128B) = 92 KB, two 60 KB tables
 // with the transforms of the tile's <= 10 joints for its 128 bodies (joint-major in HBM, so one 6 KB bulk copy per
 // joint), two 3.75 KB record buffers, 4 KB of SDF coarse-cell sign bits.
 // Epilogue thread = one BODY (its TMEM lane): it walks the tile's vertices, keeps the four skinning-slot transforms
@@ -31,16 +33,17 @@ namespace eg {
 namespace tc {
 
 constexpr int KT = 576;            // padded contraction: 486 pose + 3 x 20 shape (hi*hi, lo*hi, hi*lo) + 30 zero
-constexpr int BKT = 32;            // k-chunk per stage: 32 tf32 = 128 B = one swizzle atom row
-constexpr int NCHUNK = KT / BKT;   // 18
+constexpr int BKT = 64;            // k-chunk per stage: 64 fp16 = 128 B = one swizzle atom row
+constexpr int NCHUNK = KT / BKT;   // 9
+constexpr int UMMA_K = 16;         // kind::f16
 constexpr int TV = 80;             // vertices per tile (UMMA N)
 constexpr int TB = 128;            // bodies per tile (UMMA M)
 constexpr int STAGES = 2;
 constexpr int CLUSTER = 1;          // CTAs per cluster: same vertex tile, adjacent body tiles; basis tiles are multicast
 constexpr int HALF_ROWS = 80 / CLUSTER;   // basis rows each CTA of the pair loads (and multicasts) per component
-constexpr int V_TILE_BYTES = TV * BKT * 4;   // 10 KB (basis, one component)
-constexpr int HALF_BYTES = HALF_ROWS * BKT * 4;
-constexpr int F_TILE_BYTES = TB * BKT * 4;   // 16 KB (features)
+constexpr int V_TILE_BYTES = TV * BKT * 2;   // 10 KB (basis, one component)
+constexpr int HALF_BYTES = HALF_ROWS * BKT * 2;
+constexpr int F_TILE_BYTES = TB * BKT * 2;   // 16 KB (features)
 constexpr int STAGE_BYTES = 3 * V_TILE_BYTES + F_TILE_BYTES;   // 46 KB
 constexpr int ACC_COLS = 3 * TV;                 // one accumulator set
 constexpr int TMEM_COLS = 512;
@@ -132,15 +135,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
-// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, K-major A and B, M=128, N=TB
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TV >> 3) << 17) | ((uint32_t)(TB >> 4) << 24);
+// cute::UMMA::InstrDescriptor for kind::f16 with fp16 A and B (a_format = b_format = 0), fp32 accumulate (c_format = 1),
+// K-major A and B, M = TB, N = TV
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TV >> 3) << 17) | ((uint32_t)(TB >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
