@@ -214,8 +214,17 @@ def run_ours(args):
     tf_achieved = tc_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     tf_peak = float(pk.get("bf16_tflops", 1590.0))
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/), scaled to this run's
+    # bodies per launch (the kernel's HBM traffic is the basis + features + transforms, linear in bodies apart from
+    # the 36 MB fp16 basis that is read once per launch)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_lbs_tc_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * bodies_per_launch / tj["bodies"]
+        traffic_src = tj["source"]
     roofline = {"bound": "tensor", "achieved": tf_achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf_achieved / tf_peak,
-                "traffic": None, "peak_source": how + " dense bf16/fp16 cuBLAS burst (kind::f16 operands, fp32 accumulation)",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": how + " dense bf16/fp16 cuBLAS burst (kind::f16 operands, fp32 accumulation)",
                 "kernel": "lbs_verts_tc_kernel<FUSE_SDF> (tcgen05 kind::f16, fp32 accumulate in TMEM)",
                 "avg_launch_ms": k_ms, "bodies_per_launch": bodies_per_launch, "launches_timed": n_l.value,
                 "kernel_share_of_step": tot_ms.value / float(sum(ms)),
