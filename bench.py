@@ -311,6 +311,57 @@ def run_ego_depth(args):
         dist.destroy_process_group()
 
 
+def run_crowd_eval(args):
+    """BASELINE config 4: 4-human crowd evaluation, 256 agents (64 scenes x 4) per GPU, scenes sharded over ranks with
+    no collective. One step = one vector step of every agent (policy forward + 4 agent-by-agent env sub-steps in the
+    reference's update order). Secondary workload: prints its own JSON line."""
+    import torch
+    import torch.distributed as dist
+    from egogen_b200.main_crowd_eval import build_crowd_world, crowd_start_data
+    from egogen_b200.ppo_policy import Batch
+    world_size = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, A = 64, 4
+    w = build_crowd_world(dev, S, A, sequential=True, seed=rank)
+    w["policy"].eval()
+    wp, goals, betas = crowd_start_data(w["sampler"], S, A, dev, seed=rank)
+    venv, pol = w["venv"], w["policy"]
+
+    def vector_step():
+        with torch.no_grad():
+            out = pol.forward(Batch(obs=venv.observation()))
+            venv.step(out.act)
+
+    venv.reset_from(torch.arange(S * A), wp, goals, betas)
+    for _ in range(max(args.warmup, 3)):
+        vector_step()
+    venv.reset_from(torch.arange(S * A), wp, goals, betas)
+    if world_size > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        vector_step()
+    e1.record(); torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t.item())
+        print(json.dumps({"metric": "crowd eval agent-steps/sec", "value": S * A * world_size * args.steps / (ms / 1e3),
+                          "unit": "env-steps/s", "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+                          "data": "synthetic",
+                          "config": {"workload": "4-human crowd eval (main_crowd_eval.py): 64 scenes x 4 agents per GPU, agents see "
+                                                 "each other as holes of the floor polygon, agent-by-agent update order"}}))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
 def run_cvae_train(args):
     """BASELINE config 3: C-VAE marker-predictor training on synthetic canonicalised primitives, batch 4096, 200-frame
     sequences, max_rollout 8 (8 chained primitives per optimiser step), Adam 5e-4. Secondary workload."""
@@ -344,13 +395,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "ego_depth", "cvae_train"],
+    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "ego_depth", "cvae_train", "crowd_eval"],
                     help="ppo = headline (BASELINE config 2); ego_depth = secondary config-5 sweep")
     args = ap.parse_args()
     if args.workload == "ego_depth" and args.impl == "ours":
         return run_ego_depth(args)
     if args.workload == "cvae_train" and args.impl == "ours":
         return run_cvae_train(args)
+    if args.workload == "crowd_eval" and args.impl == "ours":
+        return run_crowd_eval(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "eg_env_set_config": (_I, [_P, C.POINTER(EgEnvConfig)]),
     "eg_env_set_scene": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _I]),
     "eg_env_set_navmesh": (_I, [_P, _P, _I]),
+    "eg_env_set_crowd": (_I, [_P, _P, _I, _P, _I]),
     "eg_env_step": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P]),
     "eg_env_reset": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
     "eg_policy_param_count": (_L, [C.POINTER(EgPolicyDims), C.POINTER(C.c_int64)]),

@@ -258,6 +258,88 @@ class CrowdVectorEnv:
             pass
 
 
+class CrowdSceneVectorEnv(CrowdVectorEnv):
+    """Multi-agent crowd dynamics: ``n_scenes`` scenes x ``n_agents`` agents, the batched form of
+    ``DummyCrowdVectorEnv([CrowdEnv(init_env), CrowdEnv(init_env2), ...])`` (motion/crowd_ppo/dummy_vector_env.py:29-128,
+    main_crowd_eval.py:47) over ``crowd_env_crowd_eval.CrowdEnv`` (box-env arithmetic + the other agents' marker
+    bounding boxes as holes of the floor polygon, :66-75,345-352,796-822; termination on goal / max_depth only, :367;
+    fixed start data, no rejection, :391-405).
+
+    Env index = agent * n_scenes + scene (agent-major), so the agents that step together are one contiguous slice.
+    ``sequential=True`` reproduces the reference's update order exactly: ``update_holes_for_each_agent()`` runs before
+    every worker's step (:78-82) and DummyVectorEnv workers step synchronously, so agent a already sees the NEW
+    boxes of agents < a of the same vector step. ``sequential=False`` steps all agents against the boxes of the
+    previous vector step in one launch sequence (4x fewer launches; a documented deviation)."""
+
+    FLOOR = [[4.0, 4.0], [4.0, -4.0], [-4.0, -4.0], [-4.0, 4.0], [4.0, 4.0]]       # crowd_env_crowd_eval.py:398
+
+    def __init__(self, cfg, motion_model, lbs_model, vposer, scene_sdf: dict, n_scenes: int, device, n_agents: int = 4,
+                 sequential: bool = True, feet_marker_idx=None, debug_terms: bool = False, capture_rollout: bool = False):
+        self.S, self.A, self.sequential = int(n_scenes), int(n_agents), bool(sequential)
+        fl = np.asarray(self.FLOOR, np.float32)
+        tris = np.stack([fl[[0, 1, 2]], fl[[2, 3, 0]]])                              # floor square as two triangles
+        super().__init__(cfg, motion_model, lbs_model, vposer, scene_sdf, [np.asarray(self.FLOOR, np.float64)], None,
+                         self.S * self.A, device, feet_marker_idx, False, capture_rollout, debug_terms,
+                         box_mode=True, navmesh_tris=tris)
+        E, dev = self.E, self.dev
+        self.bbox = torch.zeros(E, 4, dtype=torch.float32, device=dev)
+        self.holes = torch.zeros(E, max(self.A - 1, 1), 4, dtype=torch.float32, device=dev)
+        # one EgEnvBuffers view per agent slot (rows [a*S, (a+1)*S) of every buffer)
+        self._slices = []
+        for a in range(self.A):
+            sl = slice(a * self.S, (a + 1) * self.S)
+            self._slices.append(_lib.EgEnvBuffers(**{k: (C.c_void_p(v[sl].data_ptr()) if v is not None else None)
+                                                     for k, v in self.buf.items()}))
+
+    def _set_crowd(self, a=None, with_holes=True):
+        lo = 0 if a is None else a * self.S
+        n_h = self.A - 1 if (with_holes and self.A > 1) else 0
+        _lib.check(_lib.lib().eg_env_set_crowd(self._h, _lib.ptr(self.holes[lo:]) if n_h else None, n_h,
+                                               _lib.ptr(self.bbox[lo:]), 0))
+
+    def update_holes_for_each_agent(self):
+        """dummy_vector_env.py:33-39: holes of agent a = the current boxes of every other agent of its scene (ascending)."""
+        if self.A < 2:
+            return
+        bb = self.bbox.view(self.A, self.S, 4)
+        hv = self.holes.view(self.A, self.S, self.A - 1, 4)
+        for a in range(self.A):
+            others = [o for o in range(self.A) if o != a]
+            hv[a].copy_(bb[others].permute(1, 0, 2))
+
+    def reset_from(self, env_ids, world_params, goals, betas):
+        """Start data is fixed per agent (crowd_env_crowd_eval.py:55-78): first pass computes every agent's box
+        (CrowdEnv.__init__), then the holes are distributed (DummyCrowdVectorEnv.__init__) and the observation is
+        built against them (reset -> _get_feature / _calc_egosensing)."""
+        self._set_crowd(None, with_holes=False)
+        super().reset_from(env_ids, world_params, goals, betas)
+        self.update_holes_for_each_agent()
+        self._set_crowd(None, with_holes=True)
+        return super().reset_from(env_ids, world_params, goals, betas)
+
+    def reset(self, env_ids=None, max_tries: int = 50):
+        raise _lib.EgError("CrowdSceneVectorEnv starts from explicit per-agent data: use reset_from (main_crowd_eval.py:47)")
+
+    def step(self, action_z: torch.Tensor):
+        z = _lib.f32c(action_z, self.dev)
+        if z.shape != (self.E, 128):
+            raise _lib.EgError(f"action must be [{self.E},128]")
+        lib = _lib.lib()
+        with torch.cuda.device(self.dev):
+            if self.sequential:
+                for a in range(self.A):
+                    self.update_holes_for_each_agent()              # before every worker's step (:78-82)
+                    self._set_crowd(a)
+                    _lib.check(lib.eg_env_step(self._h, C.byref(self._slices[a]), _lib.ptr(z[a * self.S:]), self.S,
+                                               _lib.stream_ptr(self.dev)))
+            else:
+                self.update_holes_for_each_agent()
+                self._set_crowd(None)
+                _lib.check(lib.eg_env_step(self._h, C.byref(self._cbuf), _lib.ptr(z), self.E, _lib.stream_ptr(self.dev)))
+        b = self.buf
+        return self.observation(), b["reward"], b["terminated"], torch.zeros_like(b["terminated"]), {}
+
+
 class CrowdEnv:
     """Single-agent environment with the reference constructor and gymnasium surface
     (crowd_env_2f.py:34-51,78,320,519). ``init_env`` is the reference's 12-element list

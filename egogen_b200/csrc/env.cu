@@ -30,7 +30,23 @@ struct StepArgs {
   const float* pelvis_rest;// [E,3]
   const float* tris;       // [n_tris,3,2] navmesh (pene_mode 1)
   int n_tris;
+  // crowd dynamics (crowd_env_crowd_eval.py / dummy_vector_env.py): the other agents of the scene as axis-aligned
+  // hole rectangles (xmin, ymin, xmax, ymax), this agent's own rectangle as output
+  const float* holes;      // [E,n_holes,4] or null
+  int n_holes;
+  float* bbox_out;         // [E,4] or null
+  int pene_terminates;     // 0: crowd eval (:367) never terminates on penetration
 };
+
+// the union of the other agents' marker bounding boxes is cut out of the floor polygon (crowd_env_crowd_eval.py:796-822);
+// a point is off the walkable polygon when any closed rectangle holds it
+__device__ __forceinline__ bool in_any_hole(const float* holes, int H, float x, float y) {
+  for (int k = 0; k < H; ++k) {
+    const float* r = holes + 4 * k;
+    if (x >= r[0] && y >= r[1] && x <= r[2] && y <= r[3]) return true;
+  }
+  return false;
+}
 
 __device__ __forceinline__ float norm3_clip(float x, float y, float z) {
   return fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
@@ -90,7 +106,8 @@ __device__ __forceinline__ float linspace_sym(float extent, int res, int i) {
 // threads of the CTA. ms_xy: the markers of the 2-frame seed in the (new) local frame, [n_pts][2] in shared memory.
 // Returns the number of local-map cells inside the markers' bounding box that no navmesh triangle covers.
 __device__ float map_penetration(const float* Rl, const float* Tl, const float* ms_xy, int n_pts, const float* tris,
-                                 int n_tris, int res, float extent, float* red /* shared, >= 8 floats */) {
+                                 int n_tris, int res, float extent, float* red /* shared, >= 8 floats */,
+                                 const float* holes = nullptr, int n_holes = 0) {
   const int tid = threadIdx.x, nth = blockDim.x;
   float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
   for (int i = tid; i < n_pts; i += nth) {
@@ -125,6 +142,7 @@ __device__ float map_penetration(const float* Rl, const float* Tl, const float* 
       const bool has_neg = d1 < 0.f || d2 < 0.f || d3 < 0.f, has_pos = d1 > 0.f || d2 > 0.f || d3 > 0.f;
       walkable = !(has_neg && has_pos);
     }
+    if (walkable && holes != nullptr && in_any_hole(holes, n_holes, wx, wy)) walkable = false;
     cnt += walkable ? 0.0f : 1.0f;              // inside * (1 - map) * 0.5 with map = +1 / -1
   }
   cnt = warp_sum(cnt);
@@ -275,7 +293,21 @@ env_reward_recanon_kernel(const StepArgs a) {
   }
   __syncthreads();
   float num_pene = 0.0f;
-  if (c.pene_mode == 1) num_pene = map_penetration(R0n, T0n, ms_xy, 2 * NM, a.tris, a.n_tris, c.map_res, c.map_extent, red);
+  if (c.pene_mode == 1)
+    num_pene = map_penetration(R0n, T0n, ms_xy, 2 * NM, a.tris, a.n_tris, c.map_res, c.map_extent, red,
+                               a.holes ? a.holes + (int64_t)e * a.n_holes * 4 : nullptr, a.n_holes);
+  if (tid == 0 && a.bbox_out != nullptr) {
+    // bbox of the new 2-frame seed's markers on the world xy plane (crowd_env_crowd_eval.py:345-352)
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = 0; i < 2 * NM; ++i) {
+      const float* st = a.b.state + ((int64_t)e * 2 + i / NM) * 402 + (i % NM) * 3;
+      const float wx = (R0n[0] * st[0] + R0n[1] * st[1] + R0n[2] * st[2]) + T0n[0];
+      const float wy = (R0n[3] * st[0] + R0n[4] * st[1] + R0n[5] * st[2]) + T0n[1];
+      mnx = fminf(mnx, wx); mxx = fmaxf(mxx, wx); mny = fminf(mny, wy); mxy = fmaxf(mxy, wy);
+    }
+    float* bb = a.bbox_out + (int64_t)e * 4;
+    bb[0] = mnx; bb[1] = mny; bb[2] = mxx; bb[3] = mxy;
+  }
   if (tid == 0) {
     float r_pene = sc[6];
     bool penetration = sc[8] != 0.0f;
@@ -292,7 +324,7 @@ env_reward_recanon_kernel(const StepArgs a) {
     reward += sc[7] * c.w_vp;
     const int steps = a.b.steps[e];             // already incremented above
     const bool term = (sc[4] > 0.0f) || (steps == c.max_depth) ||
-                      ((c.finetuning || c.pene_mode == 1) && penetration);   // box env always terminates on penetration (:325)
+                      ((c.finetuning || c.pene_mode == 1) && penetration && a.pene_terminates);   // box env always terminates on penetration (:325)
     a.b.reward[e] = reward;
     a.b.terminated[e] = term ? 1 : 0;
     if (a.b.goal_reached) a.b.goal_reached[e] = sc[4] > 0.0f ? 1 : 0;
@@ -330,11 +362,14 @@ env_reset_commit_kernel(EgEnvBuffers b, const int32_t* __restrict__ env_ids, int
                         const float* __restrict__ T0c, const float* __restrict__ seedc,
                         const float* __restrict__ joints_c, const float* __restrict__ markers_c,
                         const float* __restrict__ goals, const float* __restrict__ betas_c,
-                        int32_t* __restrict__ accept, EgEnvConfig cfg, const float* __restrict__ tris, int n_tris) {
+                        int32_t* __restrict__ accept, EgEnvConfig cfg, const float* __restrict__ tris, int n_tris,
+                        int check_start, float* __restrict__ bbox_out) {
   const int i = blockIdx.x, tid = threadIdx.x;
   __shared__ float ms_xy[2 * NM * 2], red[8];
   bool ok;
-  if (cfg.pene_mode == 1) {                     // crowd_env_2f_box.py reset: start pose must not cover unwalkable cells
+  if (!check_start) {                           // crowd eval: fixed start data, no rejection (crowd_env_crowd_eval.py:391-405)
+    ok = true;
+  } else if (cfg.pene_mode == 1) {                     // crowd_env_2f_box.py reset: start pose must not cover unwalkable cells
     for (int q = tid; q < 2 * NM; q += blockDim.x) {
       ms_xy[2 * q] = markers_c[((int64_t)i * 2 * NM + q) * 3];
       ms_xy[2 * q + 1] = markers_c[((int64_t)i * 2 * NM + q) * 3 + 1];
@@ -367,6 +402,17 @@ env_reset_commit_kernel(EgEnvBuffers b, const int32_t* __restrict__ env_ids, int
   __syncthreads();
   if (tid < 9) b.R0[(int64_t)e * 9 + tid] = R0[tid];
   if (tid < 3) b.T0[(int64_t)e * 3 + tid] = T0[tid];
+  if (tid == 0 && bbox_out != nullptr) {        // crowd_env_crowd_eval.py:66-75
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int q = 0; q < 2 * NM; ++q) {
+      const float* m = markers_c + ((int64_t)i * 2 * NM + q) * 3;
+      const float wx = (R0[0] * m[0] + R0[1] * m[1] + R0[2] * m[2]) + T0[0];
+      const float wy = (R0[3] * m[0] + R0[4] * m[1] + R0[5] * m[2]) + T0[1];
+      mnx = fminf(mnx, wx); mxx = fmaxf(mxx, wx); mny = fminf(mny, wy); mxy = fmaxf(mxy, wy);
+    }
+    float* bb = bbox_out + (int64_t)e * 4;
+    bb[0] = mnx; bb[1] = mny; bb[2] = mxx; bb[3] = mxy;
+  }
   for (int q = tid; q < 2 * 93; q += blockDim.x) b.seed[(int64_t)e * 2 * 93 + q] = seedc[(int64_t)i * 2 * 93 + q];
   for (int q = tid; q < 2 * NM; q += blockDim.x) {
     const int k = q / NM, p = q % NM;
@@ -381,7 +427,7 @@ __global__ void __launch_bounds__(64)
 env_egosensing_kernel(const float* __restrict__ joints, const float* __restrict__ R0a,
                       const float* __restrict__ T0a, const int32_t* __restrict__ slot_ids,
                       const int32_t* __restrict__ accept, const double* __restrict__ segs, int S,
-                      double ray_len, float* __restrict__ ego) {
+                      double ray_len, float* __restrict__ ego, const float* __restrict__ holes_all, int n_holes) {
   const int i = blockIdx.x;
   if (accept && !accept[i]) return;
   const int t = threadIdx.x >> 5, ray = threadIdx.x & 31;
@@ -425,9 +471,30 @@ env_egosensing_kernel(const float* __restrict__ joints, const float* __restrict_
       if (tt >= 0.0 && u >= 0.0 && u <= 1.0 && tt < tmin) tmin = tt;
     }
   }
+  // crowd dynamics: the other agents' rectangles are holes of the scene polygon (their union's boundary is hit
+  // first on an edge of one of them as long as the eye is outside all of them; inside one => off the polygon => 0)
+  bool in_hole = false;
+  if (holes_all != nullptr) {
+    const float* holes = holes_all + (int64_t)slot * n_holes * 4;
+    for (int k = 0; k < n_holes; ++k) {
+      const double x0 = (double)holes[4 * k], y0 = (double)holes[4 * k + 1], x1 = (double)holes[4 * k + 2], y1 = (double)holes[4 * k + 3];
+      if (ex >= x0 && ex <= x1 && ey >= y0 && ey <= y1) in_hole = true;
+      const double cxs[5] = {x0, x1, x1, x0, x0}, cys[5] = {y0, y0, y1, y1, y0};
+      for (int q = 0; q < 4; ++q) {
+        const double ax = cxs[q], ay = cys[q], sx = cxs[q + 1] - ax, sy = cys[q + 1] - ay;
+        const double den = dx * sy - dy * sx;
+        if (den != 0.0) {
+          const double qx = ax - ex, qy = ay - ey;
+          const double tt = (qx * sy - qy * sx) / den;
+          const double u = (qx * dy - qy * dx) / den;
+          if (tt >= 0.0 && u >= 0.0 && u <= 1.0 && tt < tmin) tmin = tt;
+        }
+      }
+    }
+  }
   // the hit point is reconstructed like shapely's end coordinate and its distance re-measured
   double d = 0.0;
-  if (crossings & 1) {
+  if ((crossings & 1) && !in_hole) {
     const double hx = ex + tmin * dx, hy = ey + tmin * dy;
     d = sqrt((hx - ex) * (hx - ex) + (hy - ey) * (hy - ey));
   }
@@ -450,6 +517,8 @@ struct EgEnv {
   const uint8_t* skip = nullptr;
   const double* segs = nullptr; int S = 0;
   const float* tris = nullptr; int n_tris = 0;
+  // crowd dynamics (eg_env_set_crowd)
+  const float* holes = nullptr; int n_holes = 0; float* bbox_out = nullptr; int pene_terminates = 1;
   // workspace
   int cap = 0;
   float *Y = nullptr, *params = nullptr, *joints = nullptr, *mproj = nullptr, *vp = nullptr, *prest = nullptr;
@@ -520,6 +589,15 @@ extern "C" int eg_env_set_navmesh(EgEnv* h, const float* tris_dev, int n_tris) {
   return EG_OK;
 }
 
+extern "C" int eg_env_set_crowd(EgEnv* h, const float* holes_dev, int n_holes, float* bbox_out_dev,
+                                int penetration_terminates) {
+  EG_REQUIRE(h != nullptr, "null handle");
+  EG_REQUIRE(n_holes >= 0 && (holes_dev != nullptr || n_holes == 0), "holes pointer / count mismatch");
+  h->holes = n_holes > 0 ? holes_dev : nullptr; h->n_holes = n_holes; h->bbox_out = bbox_out_dev;
+  h->pene_terminates = penetration_terminates ? 1 : 0;
+  return EG_OK;
+}
+
 #define EG_TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 extern "C" int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int E, void* stream) {
@@ -552,14 +630,15 @@ extern "C" int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int 
   EG_TRY(eg_vposer_encode(h->vposer, h->params + 6, 93, E * NT, h->vp, stream));
   stage_mark(st, 4);
   EG_TRY(eg_lbs_rest_pelvis(h->lbs, b->betas, E, E, h->prest, stream));
-  StepArgs a{h->cfg, *b, h->Y, h->params, h->counts, h->joints, h->mproj, h->vp, h->prest, h->tris, h->n_tris};
+  StepArgs a{h->cfg, *b, h->Y, h->params, h->counts, h->joints, h->mproj, h->vp, h->prest, h->tris, h->n_tris,
+             h->holes, h->n_holes, h->bbox_out, h->pene_terminates};
   EG_LAUNCH(env_reward_recanon_kernel, E, 256, 0, st, a);
   stage_mark(st, 5);
   // i: all joints of the re-canonicalised seed for ego-sensing (:290-296)
   EG_TRY(eg_lbs_forward(h->lbs, b->seed, b->betas, E, E * 2, nullptr, h->joints2, nullptr, stream));
   stage_mark(st, 6);
   EG_LAUNCH(env_egosensing_kernel, E, 64, 0, st, h->joints2, b->R0, b->T0, nullptr, nullptr, h->segs, h->S,
-            (double)h->cfg.ray_len, b->ego);
+            (double)h->cfg.ray_len, b->ego, h->holes, h->n_holes);
   stage_mark(st, 7);
   return EG_OK;
 }
@@ -584,8 +663,8 @@ extern "C" int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_
                               h->center, h->scale, h->skip, h->counts, h->joints2, h->mproj, stream));
   }
   EG_LAUNCH(env_reset_commit_kernel, n, 256, 0, st, *b, env_ids, n, h->counts, h->R0c, h->T0c, h->seedc,
-            h->joints2, h->mproj, goals, betas_cand, accept, h->cfg, h->tris, h->n_tris);
+            h->joints2, h->mproj, goals, betas_cand, accept, h->cfg, h->tris, h->n_tris, h->pene_terminates, h->bbox_out);
   EG_LAUNCH(env_egosensing_kernel, n, 64, 0, st, h->joints2, h->R0c, h->T0c, env_ids, accept, h->segs, h->S,
-            (double)h->cfg.ray_len, b->ego);
+            (double)h->cfg.ray_len, b->ego, h->holes, h->n_holes);
   return EG_OK;
 }

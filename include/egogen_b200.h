@@ -243,6 +243,15 @@ int eg_env_set_scene(EgEnv* h, const float* grid, int D0, int D1, int D2, const 
                      int n_segments);
 /* navmesh triangles (xy) for pene_mode 1: tris_dev float [n_tris,3,2] (navmesh.vertices[faces, :2]) */
 int eg_env_set_navmesh(EgEnv* h, const float* tris_dev, int n_tris);
+/* crowd dynamics - replaces DummyCrowdVectorEnv.update_holes_for_each_agent (motion/crowd_ppo/dummy_vector_env.py:33-39)
+ * and the bbox / hole handling of crowd_env_crowd_eval.CrowdEnv (crowd_env_crowd_eval.py:66-75,345-352,796-822):
+ * holes_dev float [E,n_holes,4] = (xmin,ymin,xmax,ymax) of the OTHER agents of each env's scene (read by the next
+ * eg_env_step / eg_env_reset: cut out of the walkability map and hit by the ego rays), bbox_out_dev float [E,4]
+ * (nullable) receives each env's own marker bounding box after the step / reset; penetration_terminates = 0 selects
+ * the crowd-eval termination (goal or max_depth only, :367) and the reset without start-pose rejection (:391-405).
+ * Both pointers are indexed by the env index of the CALL, so a caller stepping a contiguous slice of envs passes
+ * offset pointers. n_holes = 0 / NULL restores the single-agent behaviour. */
+int eg_env_set_crowd(EgEnv* h, const float* holes_dev, int n_holes, float* bbox_out_dev, int penetration_terminates);
 /* one transition of all E envs with actions z [E,128] */
 int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int E, void* stream);
 /* try to (re)start the envs env_ids [n] from sampled world-frame 2-frame seeds world_params [n,2,93],

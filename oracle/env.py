@@ -13,15 +13,34 @@ import torch
 from . import sdf as osdf
 
 
-def egosensing(joints_w: torch.Tensor, segments: np.ndarray, ray_len: float = 7.0) -> torch.Tensor:
-    """joints_w [E,2,127,3] float32 world joints -> [E,2,32] float32 in [-1,1] (crowd_env_2f.py:524-613)."""
+def rect_segments(rects) -> np.ndarray:
+    """[H,4] (xmin,ymin,xmax,ymax) -> [4H,4] boundary segments in the order of the reference's bbox ring
+    (crowd_env_crowd_eval.py:74-75)."""
+    out = []
+    for x0, y0, x1, y1 in np.asarray(rects, np.float64).reshape(-1, 4):
+        c = [(x0, y0), (x1, y0), (x1, y1), (x0, y1), (x0, y0)]
+        out += [[c[q][0], c[q][1], c[q + 1][0], c[q + 1][1]] for q in range(4)]
+    return np.asarray(out, np.float64).reshape(-1, 4)
+
+
+def egosensing(joints_w: torch.Tensor, segments: np.ndarray, ray_len: float = 7.0, holes=None) -> torch.Tensor:
+    """joints_w [E,2,127,3] float32 world joints -> [E,2,32] float32 in [-1,1] (crowd_env_2f.py:524-613).
+    holes [E,H,4] (optional): the other agents' rectangles cut out of the scene polygon
+    (crowd_env_crowd_eval.py:796-822, Polygon(floor, holes=union of the rectangles)): an eye inside any rectangle is
+    off the polygon (distance 0), and the first crossing of the union's boundary along a ray that starts outside
+    every rectangle lies on an edge of one of them."""
     joint = joints_w.detach().cpu().numpy()
     E = joint.shape[0]
     out = np.zeros((E, 2, 32), np.float64)
     angle_grids = np.linspace(-np.pi / 2, np.pi / 2, 32)
-    seg = np.asarray(segments, np.float64)
-    ax, ay, bx, by = seg[:, 0], seg[:, 1], seg[:, 2], seg[:, 3]
+    seg0 = np.asarray(segments, np.float64)
     for e in range(E):
+        seg, hole_e = seg0, None
+        if holes is not None:
+            hole_e = np.asarray(holes[e], np.float64).reshape(-1, 4)
+            seg = np.concatenate([seg0, rect_segments(hole_e)], axis=0)
+        ax, ay, bx, by = seg[:, 0], seg[:, 1], seg[:, 2], seg[:, 3]
+        ax0, ay0, bx0, by0 = seg0[:, 0], seg0[:, 1], seg0[:, 2], seg0[:, 3]
         j = joint[e]
         look_at = j[:, 57] - j[:, 23] + j[:, 56] - j[:, 24]
         look_at = look_at.astype(np.float64)
@@ -32,10 +51,12 @@ def egosensing(joints_w: torch.Tensor, segments: np.ndarray, ray_len: float = 7.
         for t in range(2):
             ex, ey = float(eye_2d[t, 0]), float(eye_2d[t, 1])
             # polygon.contains(eye): even-odd rule over exterior + hole rings
-            cond = (ay > ey) != (by > ey)
+            cond = (ay0 > ey) != (by0 > ey)
             with np.errstate(divide="ignore", invalid="ignore"):
-                xi = ax + (ey - ay) * (bx - ax) / (by - ay)
+                xi = ax0 + (ey - ay0) * (bx0 - ax0) / (by0 - ay0)
             inside = (np.count_nonzero(cond & (xi > ex)) % 2) == 1
+            if hole_e is not None and inside:
+                inside = not bool(((ex >= hole_e[:, 0]) & (ex <= hole_e[:, 2]) & (ey >= hole_e[:, 1]) & (ey <= hole_e[:, 3])).any())
             if not inside:
                 continue                                  # end points = eye => distance 0
             l0, l1 = look_at[t, 0], look_at[t, 1]
@@ -70,9 +91,11 @@ def get_feature(Y_l, pel, R0, T0, pt_wpath):
     return dist_xy, dist_xyz, (fea_marker / dist_m_3d).reshape(nb, nt, -1)
 
 
-def get_map(tris, R, T, res=16, extent=0.8):
+def get_map(tris, R, T, res=16, extent=0.8, holes=None):
     """get_map (exp_GAMMAPrimitive/utils/batch_gen_amass.py:934-968): tris [F,3,2] = navmesh.vertices[faces, :2].
-    Returns (points_local [b,res*res,3], local_map [b,res*res] with +1 walkable / -1 not, crowd_env_2f_box.py:769-770)."""
+    Returns (points_local [b,res*res,3], local_map [b,res*res] with +1 walkable / -1 not, crowd_env_2f_box.py:769-770).
+    holes [b,H,4] (optional) = _get_dynamic_map of crowd_env_crowd_eval.py:742-765: a grid point is walkable when the
+    floor polygon contains it and no (closed) rectangle of another agent does."""
     b = R.shape[0]
     x = torch.linspace(-extent, extent, res)
     xv, yv = torch.meshgrid(x, x, indexing="ij")
@@ -89,6 +112,11 @@ def get_map(tris, R, T, res=16, extent=0.8):
     has_neg = (d1 < 0) | (d2 < 0) | (d3 < 0)
     has_pos = (d1 > 0) | (d2 > 0) | (d3 > 0)
     inside = (~(has_neg & has_pos)).any(-1).reshape(b, res * res)
+    if holes is not None:
+        h = torch.as_tensor(holes, dtype=torch.float32).reshape(b, 1, -1, 4)
+        px, py = points_scene[:, :, 0:1], points_scene[:, :, 1:2]
+        in_hole = ((px >= h[..., 0]) & (py >= h[..., 1]) & (px <= h[..., 2]) & (py <= h[..., 3])).any(-1)
+        inside = inside & ~in_hole
     local_map = inside.float()
     local_map[~inside] = -1
     return points, local_map
@@ -128,6 +156,17 @@ class CrowdEnvOracle:
         self.box_mode, self.tris, self.pene_thres, self.w_pene_box = box_mode, navmesh_tris, pene_thres, weight_pene_box
         if weight_look is not None:
             self.W = dict(self.W, look=weight_look)
+        # crowd dynamics (crowd_env_crowd_eval.py): holes [E,H,4] of the other agents, set by the vector env before every
+        # step; crowd=True drops the penetration termination (:367) and the start-pose rejection (:391-405)
+        self.holes, self.crowd, self.bbox = None, False, None
+
+    @staticmethod
+    def marker_bbox(marker_seed, R0, T0):
+        """crowd_env_crowd_eval.py:345-352: xy bounding box of the 2-frame seed's markers in the world frame -> [E,4]."""
+        E = marker_seed.shape[0]
+        mw = torch.einsum("bij,btpj->btpi", R0, marker_seed.reshape(E, 2, -1, 3)) + T0[:, None, :, :]
+        xy = mw[:, :, :, :2]
+        return torch.cat([xy.amin(dim=[1, 2]), xy.amax(dim=[1, 2])], dim=1)
 
     def set_state(self, **kw):
         for k, v in kw.items():
@@ -241,9 +280,10 @@ class CrowdEnvOracle:
         self.seed = seed_new
         w_pene = 0.1 if self.finetuning else 1.0
         if self.box_mode:      # 2-D walkability-map penetration in the NEW frame (crowd_env_2f_box.py:279-295)
-            pts_l, lmap = get_map(self.tris, self.R0, self.T0)
+            pts_l, lmap = get_map(self.tris, self.R0, self.T0, holes=self.holes)
             num_pene = map_penetration(marker_seed, pts_l, lmap)
             penetration = num_pene > self.pene_thres
+            self.bbox = self.marker_bbox(marker_seed, self.R0, self.T0)
             r_pene = torch.where(penetration, torch.tensor(0.0), torch.tensor(0.05))
             w_pene = self.w_pene_box
         W = self.W
@@ -252,9 +292,10 @@ class CrowdEnvOracle:
         # ego-sensing on the new seed (:290-296)
         ja = self._lbs(self.seed.reshape(E * t_his, -1), self.betas.repeat_interleave(t_his, 0)).joints
         ja_w = torch.einsum("bij,btpj->btpi", self.R0, ja.reshape(E, t_his, -1, 3)) + self.T0[:, None, :, :]
-        self.ego = egosensing(ja_w, self.segments)
+        self.ego = egosensing(ja_w, self.segments, holes=self.holes)
         at_max = self.steps == self.max_depth
-        terminated = (r_goal > 0) | at_max | (penetration if (self.finetuning or self.box_mode) else torch.zeros(E, dtype=torch.bool))
+        terminated = (r_goal > 0) | at_max | (penetration if ((self.finetuning or self.box_mode) and not self.crowd)
+                                              else torch.zeros(E, dtype=torch.bool))
         return dict(state=self.state, egosensing=self.ego, dist=1 / (dist2target + 1),
                     time=torch.as_tensor([1 - s / self.max_depth for s in self.steps.tolist()], dtype=torch.float32),
                     reward=reward, terminated=terminated, counts=counts, seed=self.seed, R0=self.R0, T0=self.T0,
@@ -282,10 +323,13 @@ class CrowdEnvOracle:
         counts = sdf_values.lt(0.0).sum(dim=-1)
         accept = counts.sum(dim=1) == 0
         if self.box_mode:
-            pts_l, lmap = get_map(self.tris, R0, T0)
+            pts_l, lmap = get_map(self.tris, R0, T0, holes=self.holes)
             accept = map_penetration(marker_seed.reshape(n, 2, -1, 3), pts_l, lmap) == 0
+        if self.crowd:
+            accept = torch.ones(n, dtype=torch.bool)
         ja_w = torch.einsum("bij,btpj->btpi", R0, joints_all) + T0[:, None, :, :]
-        ego = egosensing(ja_w, self.segments)
+        ego = egosensing(ja_w, self.segments, holes=self.holes)
         state = torch.cat([marker_seed, fea_marker], dim=-1)
         return dict(accept=accept, state=state, seed=seed, R0=R0, T0=T0, dist=dist[:, 0, 0], egosensing=ego,
+                    bbox=self.marker_bbox(marker_seed, R0, T0),
                     counts=counts, obs_dist=(1 / (dist + 1))[:, 0, 0])

@@ -210,3 +210,97 @@ def test_box_scene_env_matches_oracle(dev, world, smplx_model):
     R = torch.eye(3).repeat(4, 1, 1); T = torch.rand(4, 1, 3) * 4 - 2
     _, lmap = get_map(tris, R, T)
     assert (lmap == -1).any() and (lmap == 1).any()
+
+
+def test_crowd_scene_env_matches_oracle(dev, world, smplx_model):
+    """f-2: multi-agent crowd dynamics (dummy_vector_env.py:29-128 + crowd_env_crowd_eval.py): the other agents' marker
+    boxes are holes of the floor polygon for the walkability map and the ego rays, boxes are refreshed before every
+    agent's step (Gauss-Seidel order of the synchronous DummyVectorEnv workers), no penetration termination."""
+    from egogen_b200.crowd_env import BoxSceneSampler, CrowdSceneVectorEnv, default_cfg_box
+    from oracle.env import CrowdEnvOracle, egosensing
+    from oracle.smplx_lbs import SMPLXParserOracle
+    S, A = 3, 4
+    E = S * A
+    scene = assets.make_box_scene(3, n_boxes=0)
+    sdf_cpu = assets.rasterize_scene_sdf(scene, D=32)
+    sdf = {k: v.to(dev) for k, v in sdf_cpu.items()}
+    venv = CrowdSceneVectorEnv(default_cfg_box(), world["genop"].model, world["lbs"], world["vposer"], sdf, S, dev, n_agents=A,
+                               sequential=True, debug_terms=True)
+    markers = assets.marker_ids()
+    floor = [np.asarray(CrowdSceneVectorEnv.FLOOR, np.float64)]
+    fl = np.asarray(CrowdSceneVectorEnv.FLOOR, np.float32)
+    tris = np.stack([fl[[0, 1, 2]], fl[[2, 3, 0]]])
+    orcs = []
+    for a in range(A):
+        o = CrowdEnvOracle(SMPLXParserOracle(smplx_model, marker=markers), world["combo"].eval(), world["vp_o"].eval(), sdf_cpu,
+                           assets.rings_to_segments(floor), markers, assets.feet_marker_idx(), assets.feet_vids(), max_depth=11,
+                           box_mode=True, navmesh_tris=tris, weight_look=0.1)
+        o.crowd = True
+        orcs.append(o)
+    # start data: agents of a scene on a 0.7 m circle, agent 1 almost on top of agent 0 (overlapping boxes)
+    sampler = BoxSceneSampler(sdf, world["lbs"], dev, seed=11)
+    s = sampler.next_body(E)
+    wp, goals, betas = s["world_params"].clone(), s["goals"].clone(), s["betas"].clone()
+    for a in range(A):
+        for sc in range(S):
+            e = a * S + sc
+            ang = 2 * np.pi * a / A + 0.3 * sc
+            pos = np.array([0.7 * np.cos(ang), 0.7 * np.sin(ang)]) if a != 1 else np.array([0.7 + 0.25, 0.05 * sc])
+            d = wp[e, 1, :2] - wp[e, 0, :2]
+            wp[e, 0, :2] = torch.tensor(pos, dtype=torch.float32)
+            wp[e, 1, :2] = wp[e, 0, :2] + d
+            goals[e, :2] = torch.tensor(-3.0 * pos / np.linalg.norm(pos), dtype=torch.float32)
+    sl = lambda a: slice(a * S, (a + 1) * S)
+
+    def holes_for(bbox_list, a):
+        return torch.stack([bbox_list[o] for o in range(A) if o != a], dim=1)       # [S,A-1,4]
+
+    # ---- reset: boxes first, then the observation against the distributed holes -------------------------------
+    venv.reset_from(torch.arange(E), wp, goals, betas)
+    bb = []
+    for a in range(A):
+        orcs[a].holes = None
+        bb.append(orcs[a].reset_from(wp[sl(a)].cpu(), goals[sl(a)].cpu(), betas[sl(a)].cpu())["bbox"])
+    assert torch.allclose(venv.bbox.cpu(), torch.cat(bb), atol=1e-5)
+    ego_changed = 0.0
+    for a in range(A):
+        orcs[a].holes = holes_for(bb, a)
+        assert torch.allclose(venv.holes[sl(a)].cpu(), orcs[a].holes, atol=1e-5)
+        ref = orcs[a].reset_from(wp[sl(a)].cpu(), goals[sl(a)].cpu(), betas[sl(a)].cpu())
+        assert bool(ref["accept"].all())
+        assert torch.allclose(venv.buf["state"][sl(a)].cpu(), ref["state"], atol=2e-5)
+        assert torch.allclose(venv.buf["ego"][sl(a)].cpu(), ref["egosensing"], atol=1e-3)
+        orcs[a].holes = None
+        ego_changed += (orcs[a].reset_from(wp[sl(a)].cpu(), goals[sl(a)].cpu(), betas[sl(a)].cpu())["egosensing"]
+                        - ref["egosensing"]).abs().sum().item()
+    assert ego_changed > 1.0, "the other agents must be visible to the ego rays in this set-up"
+    # ---- steps in the reference's update order ------------------------------------------------------------------
+    g = torch.Generator().manual_seed(21)
+    pene_seen = False
+    for it in range(2):
+        b = venv.buf
+        for a in range(A):
+            orcs[a].set_state(state=b["state"][sl(a)].cpu(), seed=b["seed"][sl(a)].cpu(), R0=b["R0"][sl(a)].cpu(),
+                              T0=b["T0"][sl(a)].cpu().view(-1, 1, 3), betas=b["betas"][sl(a)].cpu(), dist=b["dist"][sl(a)].cpu(),
+                              steps=b["steps"][sl(a)].cpu().to(torch.int64), goal=b["goal"][sl(a)].cpu())
+        bb = [venv.bbox[sl(a)].cpu().clone() for a in range(A)]
+        z = torch.randn(E, 128, generator=g) * 0.5
+        obs, rew, term, _, _ = venv.step(z.to(dev))
+        for a in range(A):
+            orcs[a].holes = holes_for(bb, a)                   # update_holes_for_each_agent() before this worker's step
+            r = orcs[a].step(z[sl(a)])
+            bb[a] = orcs[a].bbox                                # agents > a see the new box in the same vector step
+            assert torch.allclose(b["reward_terms"][sl(a)].cpu(), r["terms"], atol=2e-4)
+            assert torch.allclose(rew[sl(a)].cpu(), r["reward"], atol=5e-4)
+            assert torch.equal(term[sl(a)].cpu().bool(), r["terminated"])
+            assert torch.allclose(obs["state"][sl(a)].cpu(), r["state"], atol=2e-4)
+            assert torch.allclose(obs["egosensing"][sl(a)].cpu(), r["egosensing"], atol=1e-3)
+            assert torch.allclose(venv.bbox[sl(a)].cpu(), bb[a], atol=2e-4)
+            pene_seen = pene_seen or bool((r["terms"][:, 6] == 0).any())
+        assert not bool(term.any()) or it > 0                   # no penetration termination in the crowd env
+    assert pene_seen, "agents 0/1 overlap: the map penetration of the dynamic holes must trigger at least once"
+    # Jacobi variant: one launch sequence for all agents against the previous step's boxes
+    venv.sequential = False
+    venv.step(torch.zeros(E, 128, device=dev))
+    assert bool(torch.isfinite(venv.buf["reward"]).all())
+    venv.close()
