@@ -1,0 +1,427 @@
+// tcgen05 dense layer for sm_100a: C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias (+ C)) + residual at fp32 accuracy.
+//
+// Replaces the fp32 SIMT tiles for the nn.Linear-forward shape (activations row-major, weight [out,in]: both operands
+// K-major) of the policy / C-VAE / VPoser layers (reference models_policy_ppo.py:24-39,287-350, models_GAMMA_primitive.py).
+// The parity bar on this path is 1e-4 relative through chains of tens of layers, so a single TF32 pass (2^-11 per
+// operand) is not enough; this kernel runs the 3xTF32 split
+//      A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo,   x_hi = x with the low 13 mantissa bits cleared, x_lo = x - x_hi
+// (relative error ~2^-21) on the tensor cores: TMA stages the raw fp32 tiles (SWIZZLE_128B), four transform warps
+// derive the lo copy of every staged tile (element-wise, so the swizzled layout is irrelevant; the raw tile IS the hi
+// operand because kind::tf32 ignores the low 13 mantissa bits - tests/test_gpu_gemm_tc.py would catch a rounding unit), one
+// thread issues 3 x 4 UMMAs (128x64x8, kind::tf32) per 32-wide k block into 64 fp32 TMEM columns.
+// Small-M layers (M = 256 is the whole PPO batch) would leave most SMs idle, so the k range is split over a
+// thread-block cluster of up to 8 CTAs whose partial tiles are reduced through distributed shared memory, and the
+// fused epilogue (alpha, bias, beta, activation, residual) runs on the reduced rows only.
+#include <cooperative_groups.h>
+#include <cuda.h>
+
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "nn.cuh"
+
+#ifndef EG_GEMM_TC_REWRITE_HI
+#define EG_GEMM_TC_REWRITE_HI 0
+#endif
+
+namespace eg {
+namespace gtc {
+
+constexpr int BM = 128, BN = 64, BK = 32;           // BK fp32 = 128 B = one swizzle row
+constexpr int STAGES = 2;                            // 2 x 48 KB: two CTAs per SM, so 4-CTA clusters of small-M layers are co-resident
+constexpr int A_BYTES = BM * BK * 4;                // 16 KB
+constexpr int B_BYTES = BN * BK * 4;                // 8 KB
+constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // raw(hi) A, raw(hi) B, lo A, lo B = 48 KB
+constexpr int TMEM_COLS = 64;
+constexpr int XF_WARPS = 8;                          // transform + epilogue warps
+constexpr int THREADS = 64 + XF_WARPS * 32;          // 320
+constexpr int XF_THREADS = XF_WARPS * 32;
+constexpr int EPI_COLS = BN / (XF_WARPS / 4);        // columns per epilogue thread (two warps share a TMEM lane quarter)
+constexpr int RED_LD = BN + 1;                       // padded row of the split-k reduction buffer
+constexpr int OFF_BARS = STAGES * STAGE_BYTES;
+constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
+static_assert(BM * RED_LD * 4 <= STAGES * STAGE_BYTES, "reduction buffer aliases the operand ring");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory descriptor: LBO = 1, SBO = 1024 B, version 1 (same form as lbs_tc.cuh)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::tf32, fp32 accumulate, K-major A and B, M = 128, N = 64
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float act_apply(float x, int act, float slope) {
+  switch (act) {
+    case ACT_TANH: return tanhf(x);
+    case ACT_RELU: return fmaxf(x, 0.0f);
+    case ACT_LRELU: return x > 0.0f ? x : x * slope;
+    default: return x;
+  }
+}
+
+struct Params {
+  float* C; int ldc;
+  const float* bias;
+  const float* residual; int ldr;
+  int M, N, K;
+  int act; float slope; int beta; float alpha;
+  int kb_per_split;      // 32-wide k blocks per cluster rank
+};
+
+__global__ void __launch_bounds__(THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+  namespace cg = cooperative_groups;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+  uint64_t* full_bar = bars;                  // [STAGES] TMA landed
+  uint64_t* ready_bar = bars + STAGES;        // [STAGES] hi / lo copies written
+  uint64_t* empty_bar = bars + 2 * STAGES;    // [STAGES] MMAs retired
+  uint64_t* acc_bar = bars + 3 * STAGES;      // accumulators complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int split = blockIdx.z, n_split = gridDim.z;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb0 = min(split * p.kb_per_split, kb_total);
+  const int nkb = min(kb0 + p.kb_per_split, kb_total) - kb0;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], XF_WARPS); mbar_init(&empty_bar[s], 1); }
+      mbar_init(acc_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES; const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        tma_load_2d(st, &mapA, &full_bar[s], (kb0 + i) * BK, m0);
+        tma_load_2d(st + A_BYTES, &mapB, &full_bar[s], (kb0 + i) * BK, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer: hi*hi + lo*hi + hi*lo per 8-wide k step =====
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES; const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+      mbar_wait(&ready_bar[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + A_BYTES);
+        const uint64_t a_lo = make_desc(st + A_BYTES + B_BYTES), b_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {
+          const uint64_t o = (uint64_t)(kk * 2);           // 32 B inside the swizzle atom
+          umma_tf32(tmem_base, a_lo + o, b_hi + o, (i | kk) ? 1u : 0u);
+          umma_tf32(tmem_base, a_hi + o, b_lo + o, 1u);
+          umma_tf32(tmem_base, a_hi + o, b_hi + o, 1u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (i == nkb - 1) umma_commit(acc_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== transform warps: split the staged tiles into hi (in place) and lo copies; then the epilogue =====
+    const int xt = tid - 64;                               // 0..XF_THREADS-1
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES; const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      const uint32_t raw = smem_base + s * STAGE_BYTES;                    // A then B, contiguous
+      const uint32_t lo = raw + A_BYTES + B_BYTES;
+      float4 xs[(A_BYTES + B_BYTES) / 16 / XF_THREADS];
+#pragma unroll
+      for (int q = 0; q < (A_BYTES + B_BYTES) / 16 / XF_THREADS; ++q) xs[q] = lds128(raw + (uint32_t)(xt + q * XF_THREADS) * 16u);
+#pragma unroll
+      for (int q = 0; q < (A_BYTES + B_BYTES) / 16 / XF_THREADS; ++q) {
+        const uint32_t off = (uint32_t)(xt + q * XF_THREADS) * 16u;
+        const float4 x = xs[q];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+#if EG_GEMM_TC_REWRITE_HI
+        sts128(raw + off, h);      // not needed: kind::tf32 reads the fp32 words and ignores the low 13 mantissa bits
+#endif
+        sts128(lo + off, l);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the UMMA reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready_bar[s]);
+    }
+    // ---- epilogue: TMEM lane quarter (warp & 3) -> row, column half ((warp - 2) >> 2) -> EPI_COLS columns per thread ----
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;                         // row of the tile this thread owns in TMEM
+    const int c0 = half * EPI_COLS;
+    float acc[EPI_COLS];
+    if (nkb > 0) {
+      mbar_wait(acc_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+#pragma unroll
+      for (int c = 0; c < EPI_COLS / 16; ++c) tmem_ld16(taddr + c * 16, acc + c * 16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    } else {
+#pragma unroll
+      for (int c = 0; c < EPI_COLS; ++c) acc[c] = 0.0f;
+    }
+    // partial tile -> shared memory (the operand ring is dead: acc_bar implies every MMA has retired); the fused
+    // epilogue then runs with consecutive threads on consecutive columns (coalesced stores)
+#pragma unroll
+    for (int c = 0; c < EPI_COLS; ++c) sts32(smem_base + (uint32_t)(row * RED_LD + c0 + c) * 4u, acc[c]);
+    if (n_split == 1) {
+      asm volatile("bar.sync 1, %0;" ::"n"(XF_THREADS) : "memory");
+      for (int e = xt; e < BM * BN; e += XF_THREADS) {
+        const int r = e / BN, c = e % BN;
+        const int m = m0 + r, n = n0 + c;
+        if (m < p.M && n < p.N) {
+          float v = p.alpha * lds32f(smem_base + (uint32_t)(r * RED_LD + c) * 4u);
+          if (p.bias) v += __ldg(p.bias + n);
+          if (p.beta) v += p.C[(int64_t)m * p.ldc + n];
+          v = act_apply(v, p.act, p.slope);
+          if (p.residual) v += p.residual[(int64_t)m * p.ldr + n];
+          p.C[(int64_t)m * p.ldc + n] = v;
+        }
+      }
+    }
+  }
+  if (n_split > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();                                         // every rank's partial tile is in its shared memory
+    if (warp >= 2) {
+      float* red = reinterpret_cast<float*>(smem);
+      const int rows_per = (BM + n_split - 1) / n_split;    // rows this rank reduces and writes
+      const int r_lo = split * rows_per, r_n = max(0, min(BM, r_lo + rows_per) - r_lo);
+      const int xt = tid - 64;
+      for (int e = xt; e < r_n * BN; e += XF_THREADS) {
+        const int r = r_lo + e / BN, c = e % BN;
+        float v = 0.0f;
+        for (int k = 0; k < n_split; ++k) v += cluster.map_shared_rank(red, k)[r * RED_LD + c];
+        const int m = m0 + r, n = n0 + c;
+        if (m < p.M && n < p.N) {
+          v *= p.alpha;
+          if (p.bias) v += __ldg(p.bias + n);
+          if (p.beta) v += p.C[(int64_t)m * p.ldc + n];
+          v = act_apply(v, p.act, p.slope);
+          if (p.residual) v += p.residual[(int64_t)m * p.ldr + n];
+          p.C[(int64_t)m * p.ldc + n] = v;
+        }
+      }
+    }
+    cluster.sync();                                         // remote shared memory must outlive the reads
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct MapKey {
+  const void* p; int rows, cols, ld, box;
+  bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.p);
+    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (size_t)k.ld * 0x165667B19E3779F9ull + (size_t)k.box;
+    return h;
+  }
+};
+
+static EncodeTiledFn g_encode = nullptr;
+static bool g_init_done = false, g_attr_done = false;
+static std::mutex g_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D fp32 tensor [rows][cols] with row pitch ld (elements), box = [BK cols][box_rows], SWIZZLE_128B, OOB -> 0
+static bool get_map(const float* base, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  MapKey key{base, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return true; }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  if (g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return true;
+}
+
+}  // namespace gtc
+
+static int g_gemm_tc_enabled = -1;          // -1: read EG_GEMM_TC (default on) at first use
+void gemm_tc_set_enabled(int on) { g_gemm_tc_enabled = on ? 1 : 0; }
+
+// Returns EG_OK when the layer was launched on the tensor-core path, 1 when the shape / layout is not eligible
+// (the caller then uses the SIMT tiles), a negative EG_ERR_* on a CUDA failure.
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+  using namespace gtc;
+  if (g_gemm_tc_enabled < 0) {
+    const char* e = getenv("EG_GEMM_TC");
+    g_gemm_tc_enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (!g_gemm_tc_enabled) return 1;
+  if (g.a_div != 1 || g.K < 64 || g.N < 32 || g.M < 1) return 1;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al(g.A) || !al(g.B) || (g.lda & 3) || (g.ldb & 3)) return 1;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_init_done) {
+      g_init_done = true;
+      cudaDriverEntryPointQueryResult qres;
+      void* fn = nullptr;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+          qres == cudaDriverEntryPointSuccess)
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+  }
+  if (!g_encode) return 1;
+  if (!g_attr_done) {
+    EG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    // two CTAs per SM need the full shared-memory carveout (the default picks the smallest one that fits ONE block)
+    EG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    g_attr_done = true;
+    if (getenv("EG_GEMM_TC_DEBUG")) {
+      int nb = -1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gemm_tc_kernel, THREADS, SMEM_BYTES);
+      cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, gemm_tc_kernel);
+      for (int kb = 16; kb <= 112; kb += 16) { int x = -1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&x, gemm_tc_kernel, THREADS, kb * 1024); fprintf(stderr, "[gemm_tc] %d KB -> %d blocks/SM\n", kb, x); }
+      fprintf(stderr, "[gemm_tc] blocks/SM %d, regs %d, static smem %zu, dyn max %d, carveout %d\n", nb, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
+    }
+  }
+  CUtensorMap mapA, mapB;
+  if (!get_map(g.A, g.M, g.K, g.lda, BM, &mapA) || !get_map(g.B, g.N, g.K, g.ldb, BN, &mapB)) return 1;
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  const int kb_total = (g.K + BK - 1) / BK;
+  // split-k factor: the largest cluster size whose clusters are all co-resident (a second wave of clusters would
+  // double the layer's latency) and that leaves >= 2 k blocks per rank
+  static int max_clusters[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};     // indexed by cluster size
+  int sk = 1;
+  for (int c = 8; c >= 2; --c) {
+    if (kb_total / c < 2) continue;
+    if (max_clusters[c] < 0) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(1, 1, c); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 1; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = c;
+      q.attrs = qa; q.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, gemm_tc_kernel, &q) != cudaSuccess) { cudaGetLastError(); nc = kNumSMs / c / 2; }
+      max_clusters[c] = nc;
+      if (getenv("EG_GEMM_TC_DEBUG")) fprintf(stderr, "[gemm_tc] max active clusters of %d CTAs: %d\n", c, nc);
+    }
+    if (tiles <= max_clusters[c]) { sk = c; break; }
+  }
+  if (getenv("EG_GEMM_TC_DEBUG")) fprintf(stderr, "[gemm_tc] M=%d N=%d K=%d tiles=%d sk=%d\n", g.M, g.N, g.K, tiles, sk);
+  Params p{g.C, g.ldc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, g.act, g.slope, g.beta, g.alpha, (kb_total + sk - 1) / sk};
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, sk);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = sk;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, mapA, mapB, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  EG_CUDA_CHECK(e);
+  return EG_OK;
+}
+
+}  // namespace eg

@@ -259,6 +259,10 @@ static int launch_gemm_splitk2(const GemmArgs& g, bool TB, cudaStream_t st) {
 
 int launch_gemm(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return EG_OK;
+  if (!TA && TB) {                       // nn.Linear forward shape: tcgen05 3xTF32 path (gemm_tc.cu) when eligible
+    const int rc = launch_gemm_tc(g, st);
+    if (rc <= 0) return rc;
+  }
   auto ctas = [&](int bm, int bn) { return (int64_t)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn); };
   if (!TA && g.a_div == 1 && g.K >= 512 && ctas(64, 64) < kNumSMs * 3 / 4 && 2 * ctas(64, 64) >= kNumSMs / 2)
     return launch_gemm_splitk2(g, TB, st);

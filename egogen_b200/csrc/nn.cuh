@@ -1,6 +1,6 @@
 // Dense-layer building blocks shared by the C-VAE / regressor / VPoser / policy operators.
-// fp32 SIMT on purpose: the batch x hidden contractions on this path are M<=5120 rows by 128..1152
-// wide with a 1e-4 relative parity bar through 60-layer chains, so tensor-core TF32 is not used here.
+// The parity bar is 1e-4 relative through 60-layer chains, so single-pass TF32 is not used: nn.Linear-forward layers
+// run the 3xTF32 split on tcgen05 (gemm_tc.cu, ~2^-21 relative), every other layout the fp32 SIMT tiles below.
 #pragma once
 #include "common.cuh"
 
@@ -26,6 +26,9 @@ struct GemmArgs {
 };
 
 int launch_gemm(const GemmArgs& g, bool TA, bool TB, cudaStream_t st);
+// tensor-core path for the !TA && TB layout (gemm_tc.cu): EG_OK = launched, 1 = not eligible, < 0 = error
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+void gemm_tc_set_enabled(int on);
 
 // y = act(x W^T + b) (+ residual) for an nn.Linear weight W[out,in]
 inline int linear(cudaStream_t st, const float* x, int ldx, int M, const float* W, int ldw,

@@ -98,3 +98,33 @@ def test_gloo_world2_gradient_and_moment_allreduce(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_crowd_holes_oracle_known_answers():
+    """f-2 oracle pieces on hand-checkable geometry (crowd_env_crowd_eval.py:742-822): a rectangle straight ahead is hit
+    at its near edge, an eye inside a rectangle reads 0, and map cells under a rectangle turn unwalkable."""
+    import numpy as np
+    import torch
+    from oracle.env import egosensing, get_map
+    floor = np.array([[4, 4, 4, -4], [4, -4, -4, -4], [-4, -4, -4, 4], [-4, 4, 4, 4]], np.float64)
+    j = torch.zeros(1, 2, 127, 3)
+    j[:, :, 23] = torch.tensor([0.0, 0.1, 1.6]); j[:, :, 24] = torch.tensor([0.0, -0.1, 1.6])       # eyes -> eye_2d = origin
+    j[:, :, 57] = torch.tensor([1.0, 0.1, 1.6]); j[:, :, 56] = torch.tensor([1.0, -0.1, 1.6])       # gaze = +x
+    free = egosensing(j, floor)
+    holes = torch.tensor([[[2.0, -1.0, 3.0, 1.0]]])
+    blocked = egosensing(j, floor, holes=holes)
+    ang = np.linspace(-np.pi / 2, np.pi / 2, 32)
+    mid = int(np.argmin(np.abs(ang)))                       # the ray closest to straight ahead
+    d_free = (free[0, 0, mid] + 1) / 2 * 7
+    d_hit = (blocked[0, 0, mid] + 1) / 2 * 7
+    assert abs(float(d_free) - 4.0 / np.cos(ang[mid])) < 1e-4
+    assert abs(float(d_hit) - 2.0 / np.cos(ang[mid])) < 1e-4
+    assert float(blocked[0, 0, 0]) == float(free[0, 0, 0])  # the sideways rays do not see the rectangle
+    inside = egosensing(j, floor, holes=torch.tensor([[[-0.5, -0.5, 0.5, 0.5]]]))
+    assert torch.all(inside == -1.0)                        # eye inside a hole: off the polygon, distance 0
+    fl = np.asarray([[4, 4], [4, -4], [-4, -4], [-4, 4]], np.float32)
+    tris = np.stack([fl[[0, 1, 2]], fl[[2, 3, 0]]])
+    R, T = torch.eye(3)[None], torch.zeros(1, 1, 3)
+    _, m0 = get_map(tris, R, T)
+    _, m1 = get_map(tris, R, T, holes=torch.tensor([[[0.0, 0.0, 0.5, 0.5]]]))
+    assert bool((m0 == 1).all()) and int((m1 == -1).sum()) == 25          # 5 x 5 grid points of the 16 x 16 @ 0.8 m map
