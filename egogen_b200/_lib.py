@@ -86,6 +86,7 @@ PROTOTYPES = {
     "eg_vposer_create": (_I, [_P, _I, _I, C.POINTER(_P)]),
     "eg_vposer_destroy": (None, [_P]),
     "eg_vposer_encode": (_I, [_P, _P, _I, _I, _P, _P]),
+    "eg_matmul": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     "eg_linear_forward": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _F, _P, _I, _P, _I, _P]),
     "eg_env_create": (_I, [C.POINTER(EgEnvConfig), _P, _P, _P, _I, C.POINTER(_P)]),
     "eg_env_destroy": (None, [_P]),

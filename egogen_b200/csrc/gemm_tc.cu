@@ -77,13 +77,28 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::tf32, fp32 accumulate, K-major A and B, M = 128, N = 64
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// MN-major descriptor for 32-bit operands (cute make_umma_desc<Major::MN>, Layout_MN_SW128_32B_Atom - the only MN-major
+// shared-memory layout tf32 accepts): the tile is stored as 32-element (128 B) chunks along M/N, each chunk a [k][32]
+// box of 128 B rows written by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32 B chunks swizzled over 4 rows);
+// layout type 1 = SWIZZLE_128B_BASE32B, LBO = stride between chunks, SBO = stride between 4-row k atoms (512 B)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t chunk_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((chunk_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// kind::tf32, fp32 accumulate, M = 128, N = 64; bit 15 / 16 = A / B is MN-major
+template <bool A_MN, bool B_MN>
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate) : "memory");
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -132,6 +147,9 @@ struct Params {
   int kb_per_split;      // 32-wide k blocks per cluster rank
 };
 
+// A_MN / B_MN: the operand is stored with its M / N index contiguous (dW = dY^T X has both, dX = dY W has B) instead of
+// its k index (nn.Linear forward). MN-major tiles are staged as 32-wide chunks, one TMA box [32 k][32 mn] each.
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
   namespace cg = cooperative_groups;
@@ -175,8 +193,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
         const uint32_t st = smem_base + s * STAGE_BYTES;
-        tma_load_2d(st, &mapA, &full_bar[s], (kb0 + i) * BK, m0);
-        tma_load_2d(st + A_BYTES, &mapB, &full_bar[s], (kb0 + i) * BK, n0);
+        if (A_MN) {
+#pragma unroll
+          for (int c = 0; c < BM / 32; ++c) tma_load_2d(st + c * (BK * 128), &mapA, &full_bar[s], m0 + c * 32, (kb0 + i) * BK);
+        } else {
+          tma_load_2d(st, &mapA, &full_bar[s], (kb0 + i) * BK, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) tma_load_2d(st + A_BYTES + c * (BK * 128), &mapB, &full_bar[s], n0 + c * 32, (kb0 + i) * BK);
+        } else {
+          tma_load_2d(st + A_BYTES, &mapB, &full_bar[s], (kb0 + i) * BK, n0);
+        }
       }
     }
     __syncwarp();
@@ -188,14 +216,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t st = smem_base + s * STAGE_BYTES;
-        const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + A_BYTES);
-        const uint64_t a_lo = make_desc(st + A_BYTES + B_BYTES), b_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
+        constexpr uint32_t CH = BK * 128;                  // bytes of one 32-wide MN chunk ([32 k][128 B])
+        const uint64_t a_hi = A_MN ? make_desc_mn(st, CH) : make_desc(st);
+        const uint64_t b_hi = B_MN ? make_desc_mn(st + A_BYTES, CH) : make_desc(st + A_BYTES);
+        const uint64_t a_lo = A_MN ? make_desc_mn(st + A_BYTES + B_BYTES, CH) : make_desc(st + A_BYTES + B_BYTES);
+        const uint64_t b_lo = B_MN ? make_desc_mn(st + 2 * A_BYTES + B_BYTES, CH) : make_desc(st + 2 * A_BYTES + B_BYTES);
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint64_t o = (uint64_t)(kk * 2);           // 32 B inside the swizzle atom
-          umma_tf32(tmem_base, a_lo + o, b_hi + o, (i | kk) ? 1u : 0u);
-          umma_tf32(tmem_base, a_hi + o, b_lo + o, 1u);
-          umma_tf32(tmem_base, a_hi + o, b_hi + o, 1u);
+          // one 8-wide k step: K-major advances 32 B inside the swizzle atom, MN-major one 8-row group (1024 B)
+          const uint64_t oa = (uint64_t)(A_MN ? kk * 64 : kk * 2), ob = (uint64_t)(B_MN ? kk * 64 : kk * 2);
+          umma_tf32<A_MN, B_MN>(tmem_base, a_lo + oa, b_hi + ob, (i | kk) ? 1u : 0u);
+          umma_tf32<A_MN, B_MN>(tmem_base, a_hi + oa, b_lo + ob, 1u);
+          umma_tf32<A_MN, B_MN>(tmem_base, a_hi + oa, b_hi + ob, 1u);
         }
         umma_commit(&empty_bar[s]);
         if (i == nkb - 1) umma_commit(acc_bar);
@@ -305,25 +337,27 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct MapKey {
-  const void* p; int rows, cols, ld, box;
-  bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+  const void* p; int rows, cols, ld, box, mn;
+  bool operator==(const MapKey& o) const {
+    return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box && mn == o.mn;
+  }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.p);
-    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (size_t)k.ld * 0x165667B19E3779F9ull + (size_t)k.box;
+    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (size_t)k.ld * 0x165667B19E3779F9ull + (size_t)k.box * 2 + (size_t)k.mn;
     return h;
   }
 };
 
 static EncodeTiledFn g_encode = nullptr;
-static bool g_init_done = false, g_attr_done = false;
+static bool g_init_done = false;
 static std::mutex g_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// 2-D fp32 tensor [rows][cols] with row pitch ld (elements), box = [BK cols][box_rows], SWIZZLE_128B, OOB -> 0
-static bool get_map(const float* base, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
-  MapKey key{base, rows, cols, ld, box_rows};
+// 2-D fp32 tensor [rows][cols] with row pitch ld (elements), box = [32 cols][box_rows], SWIZZLE_128B, OOB -> 0
+static bool get_map(const float* base, int rows, int cols, int ld, int box_rows, bool mn_major, CUtensorMap* out) {
+  MapKey key{base, rows, cols, ld, box_rows, mn_major ? 1 : 0};
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return true; }
@@ -333,7 +367,8 @@ static bool get_map(const float* base, int rows, int cols, int ld, int box_rows,
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   if (g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
   if (g_maps.size() > 4096) g_maps.clear();
@@ -347,15 +382,72 @@ static bool get_map(const float* base, int rows, int cols, int ld, int box_rows,
 static int g_gemm_tc_enabled = -1;          // -1: read EG_GEMM_TC (default on) at first use
 void gemm_tc_set_enabled(int on) { g_gemm_tc_enabled = on ? 1 : 0; }
 
+template <bool A_MN, bool B_MN>
+static int launch_variant(const GemmArgs& g, cudaStream_t st) {
+  using namespace gtc;
+  static bool attr_done = false;
+  static int max_clusters[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};     // indexed by cluster size
+  auto kernel = gemm_tc_kernel<A_MN, B_MN>;
+  if (!attr_done) {
+    EG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  CUtensorMap mapA, mapB;
+  // K-major operand: tensor [rows = M or N][cols = K], box [32 k][BM or BN rows]
+  // MN-major operand: tensor [rows = K][cols = M or N], box [32 mn][32 k]
+  const bool okA = A_MN ? get_map(g.A, g.K, g.M, g.lda, BK, true, &mapA) : get_map(g.A, g.M, g.K, g.lda, BM, false, &mapA);
+  const bool okB = B_MN ? get_map(g.B, g.K, g.N, g.ldb, BK, true, &mapB) : get_map(g.B, g.N, g.K, g.ldb, BN, false, &mapB);
+  if (!okA || !okB) return 1;
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  const int kb_total = (g.K + BK - 1) / BK;
+  // split-k factor: the largest cluster size whose clusters are all co-resident (a second wave of clusters would
+  // double the layer's latency) and that leaves >= 2 k blocks per rank
+  int sk = 1;
+  for (int c = 8; c >= 2; --c) {
+    if (kb_total / c < 2) continue;
+    if (max_clusters[c] < 0) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(1, 1, c); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 1; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = c;
+      q.attrs = qa; q.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, kernel, &q) != cudaSuccess) { cudaGetLastError(); nc = kNumSMs / c / 2; }
+      max_clusters[c] = nc;
+    }
+    if (tiles <= max_clusters[c]) { sk = c; break; }
+  }
+  if (getenv("EG_GEMM_TC_DEBUG")) fprintf(stderr, "[gemm_tc<%d,%d>] M=%d N=%d K=%d tiles=%d sk=%d\n", (int)A_MN, (int)B_MN, g.M, g.N, g.K, tiles, sk);
+  Params p{g.C, g.ldc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, g.act, g.slope, g.beta, g.alpha, (kb_total + sk - 1) / sk};
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, sk);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = sk;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, mapA, mapB, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  EG_CUDA_CHECK(e);
+  return EG_OK;
+}
+
 // Returns EG_OK when the layer was launched on the tensor-core path, 1 when the shape / layout is not eligible
 // (the caller then uses the SIMT tiles), a negative EG_ERR_* on a CUDA failure.
-int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+//   !TA &&  TB : y = x W^T            (nn.Linear forward)        A K-major,  B K-major
+//   !TA && !TB : dX = dY W            (input gradient)           A K-major,  B MN-major
+//    TA && !TB : dW = dY^T X          (weight gradient)          A MN-major, B MN-major
+int launch_gemm_tc(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
   using namespace gtc;
   if (g_gemm_tc_enabled < 0) {
     const char* e = getenv("EG_GEMM_TC");
     g_gemm_tc_enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   if (!g_gemm_tc_enabled) return 1;
+  if (TA && TB) return 1;
   if (g.a_div != 1 || g.K < 64 || g.N < 32 || g.M < 1) return 1;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al(g.A) || !al(g.B) || (g.lda & 3) || (g.ldb & 3)) return 1;
@@ -371,57 +463,9 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     }
   }
   if (!g_encode) return 1;
-  if (!g_attr_done) {
-    EG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    // two CTAs per SM need the full shared-memory carveout (the default picks the smallest one that fits ONE block)
-    EG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    g_attr_done = true;
-    if (getenv("EG_GEMM_TC_DEBUG")) {
-      int nb = -1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gemm_tc_kernel, THREADS, SMEM_BYTES);
-      cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, gemm_tc_kernel);
-      for (int kb = 16; kb <= 112; kb += 16) { int x = -1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&x, gemm_tc_kernel, THREADS, kb * 1024); fprintf(stderr, "[gemm_tc] %d KB -> %d blocks/SM\n", kb, x); }
-      fprintf(stderr, "[gemm_tc] blocks/SM %d, regs %d, static smem %zu, dyn max %d, carveout %d\n", nb, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
-    }
-  }
-  CUtensorMap mapA, mapB;
-  if (!get_map(g.A, g.M, g.K, g.lda, BM, &mapA) || !get_map(g.B, g.N, g.K, g.ldb, BN, &mapB)) return 1;
-  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
-  const int kb_total = (g.K + BK - 1) / BK;
-  // split-k factor: the largest cluster size whose clusters are all co-resident (a second wave of clusters would
-  // double the layer's latency) and that leaves >= 2 k blocks per rank
-  static int max_clusters[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};     // indexed by cluster size
-  int sk = 1;
-  for (int c = 8; c >= 2; --c) {
-    if (kb_total / c < 2) continue;
-    if (max_clusters[c] < 0) {
-      cudaLaunchConfig_t q{};
-      q.gridDim = dim3(1, 1, c); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = SMEM_BYTES;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = 1; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = c;
-      q.attrs = qa; q.numAttrs = 1;
-      int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, gemm_tc_kernel, &q) != cudaSuccess) { cudaGetLastError(); nc = kNumSMs / c / 2; }
-      max_clusters[c] = nc;
-      if (getenv("EG_GEMM_TC_DEBUG")) fprintf(stderr, "[gemm_tc] max active clusters of %d CTAs: %d\n", c, nc);
-    }
-    if (tiles <= max_clusters[c]) { sk = c; break; }
-  }
-  if (getenv("EG_GEMM_TC_DEBUG")) fprintf(stderr, "[gemm_tc] M=%d N=%d K=%d tiles=%d sk=%d\n", g.M, g.N, g.K, tiles, sk);
-  Params p{g.C, g.ldc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, g.act, g.slope, g.beta, g.alpha, (kb_total + sk - 1) / sk};
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, sk);
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = sk;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, mapA, mapB, p);
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  EG_CUDA_CHECK(e);
-  return EG_OK;
+  if (!TA && TB) return launch_variant<false, false>(g, st);
+  if (!TA && !TB) return launch_variant<false, true>(g, st);
+  return launch_variant<true, true>(g, st);
 }
 
 }  // namespace eg

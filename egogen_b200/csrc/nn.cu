@@ -259,8 +259,8 @@ static int launch_gemm_splitk2(const GemmArgs& g, bool TB, cudaStream_t st) {
 
 int launch_gemm(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return EG_OK;
-  if (!TA && TB) {                       // nn.Linear forward shape: tcgen05 3xTF32 path (gemm_tc.cu) when eligible
-    const int rc = launch_gemm_tc(g, st);
+  {                                      // tcgen05 3xTF32 path (gemm_tc.cu) when the shape / layout is eligible
+    const int rc = launch_gemm_tc(g, TA, TB, st);
     if (rc <= 0) return rc;
   }
   auto ctas = [&](int bm, int bn) { return (int64_t)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn); };
@@ -961,6 +961,15 @@ extern "C" int eg_vposer_encode(EgVposer* h, const float* x, int ldx, int M, flo
   if ((rc = linear(st, h->a, 512, M, w[10], 512, w[11], 512, 512, h->b, 512, ACT_LRELU, 0.2f))) return rc;
   if ((rc = linear(st, h->b, 512, M, w[12], 512, w[13], 512, 32, loc, 32))) return rc;
   return EG_OK;
+}
+
+// generic product C[M,N] = op(A) op(B) in the library's three backward / forward layouts (GemmArgs in nn.cuh), exposed for
+// tests: trans_a: A element (m,k) at A[k*lda+m]; trans_b: B element (k,n) at B[n*ldb+k] (nn.Linear weight)
+extern "C" int eg_matmul(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, int M, int N, int K,
+                         float* Cm, int ldc, int accumulate, void* stream) {
+  EG_REQUIRE(A && B && Cm && M >= 0 && N >= 0 && K > 0, "bad arguments");
+  GemmArgs g{A, lda, 1, B, ldb, Cm, ldc, nullptr, nullptr, 0, M, N, K, ACT_NONE, 0.0f, accumulate ? 1 : 0, 1.0f};
+  return launch_gemm(g, trans_a != 0, trans_b != 0, as_stream(stream));
 }
 
 // generic dense layer exposed for tests and host-side composition

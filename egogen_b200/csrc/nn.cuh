@@ -26,8 +26,8 @@ struct GemmArgs {
 };
 
 int launch_gemm(const GemmArgs& g, bool TA, bool TB, cudaStream_t st);
-// tensor-core path for the !TA && TB layout (gemm_tc.cu): EG_OK = launched, 1 = not eligible, < 0 = error
-int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+// tensor-core path (gemm_tc.cu) for every layout but TA && TB: EG_OK = launched, 1 = not eligible, < 0 = error
+int launch_gemm_tc(const GemmArgs& g, bool TA, bool TB, cudaStream_t st);
 void gemm_tc_set_enabled(int on);
 
 // y = act(x W^T + b) (+ residual) for an nn.Linear weight W[out,in]

@@ -338,6 +338,11 @@ int eg_rigid_points(const float* R, const float* T, const float* pts, int nt, in
 
 /* y[M,out] = act(x W^T + b) + residual, W [out,in] row-major (nn.Linear; baseops.py:615-641 MLP layers).
  * act: 0 none, 1 tanh, 2 relu, 3 leaky-relu(slope). */
+/* generic product C[M,N] (+)= op(A) op(B) in the layouts the layers' forward / backward passes use (tests):
+ * trans_a = 0: A[m*lda+k], 1: A[k*lda+m]; trans_b = 1: B[n*ldb+k] (nn.Linear weight), 0: B[k*ldb+n].
+ * y = x W^T is (0,1), dX = dY W is (0,0), dW = dY^T X is (1,0). */
+int eg_matmul(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, int M, int N, int K,
+              float* C, int ldc, int accumulate, void* stream);
 int eg_linear_forward(const float* x, int ldx, int M, const float* W, const float* b, int in_dim,
                       int out_dim, int act, float slope, const float* residual, int ldr, float* y,
                       int ldy, void* stream);

@@ -54,3 +54,30 @@ def test_gemm_tc_matches_float64(M, N, K, act, res):
         y32 = y32 + r
     err32 = (y32.double() - ref).abs().max().item()
     assert err <= 16 * err32 + 1e-6, (err, err32)
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [
+    (256, 1152, 1152, 0, 0),      # dX = dY W: A K-major, B (the weight [n_out, k_in] read along k_in) MN-major
+    (1152, 1152, 256, 1, 0),      # dW = dY^T X: both operands MN-major, contraction over the 256-row batch
+    (256, 1152, 256, 1, 0),       # dW of the actor head
+    (1536, 402 + 2, 256, 1, 0),   # GRU input weights (ragged N)
+    (300, 200, 136, 0, 0),        # ragged tails, B MN-major
+    (200, 136, 300, 1, 0),        # ragged tails, both MN-major
+    (4096, 512, 256, 0, 0),
+])
+def test_gemm_tc_backward_layouts(M, N, K, ta, tb):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + 3 * N + 5 * K + ta)
+    A = torch.randn(M, K, generator=g).to(dev)
+    B = (torch.randn(K, N, generator=g) / K ** 0.5).to(dev)
+    ref = A.double() @ B.double()
+    A_st = A.t().contiguous() if ta else A.contiguous()             # storage the layout flag describes
+    B_st = B.t().contiguous() if tb else B.contiguous()
+    C0 = torch.randn(M, N, generator=g).to(dev)
+    for acc in (0, 1):
+        Cm = C0.clone()
+        _lib.check(_lib.lib().eg_matmul(_lib.ptr(A_st), A_st.shape[1], ta, _lib.ptr(B_st), B_st.shape[1], tb, M, N, K,
+                                        _lib.ptr(Cm), N, acc, _lib.stream_ptr(dev)))
+        want = ref + (C0.double() if acc else 0.0)
+        err = (Cm.double() - want).abs().max().item()
+        assert err <= 1e-5 * max(want.abs().max().item(), 1.0), (acc, err)
