@@ -7,6 +7,8 @@
 #include <vector>
 
 #include "geom.cuh"
+#include <stdlib.h>
+
 #include "nn.cuh"
 
 namespace eg {
@@ -505,6 +507,245 @@ fused_decode_kernel(DecodeW w, const float* __restrict__ c_in, const float* __re
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Weight-stationary decode (B >= 64): fused_decode_kernel re-streams all 2.66 MB of step weights from L2 for every
+// pair of rows and every step (6.1 GB per 256-env call - the per-SM L2 ingest rate is its bound). Here the work is cut
+// in 2-D: a CTA owns a block of 32 rows and 1/18 of every layer's OUTPUT columns, keeps that weight slice (166 KB) in
+// shared memory for all 18 steps, and the 18 CTAs of a row block exchange each layer's activations through L2
+// (4 hand-offs per step over a per-row-block arrival counter). L2 traffic drops to ~1 GB per call.
+// Arithmetic per output element is the plain fp32 k-ascending dot product (same rounding class as the layer kernels).
+namespace dws {
+constexpr int RB = 32, CS = 18, THREADS = 256, KC = 128;
+constexpr int NG = 48, N1 = 32, N2 = 16, NO = 16;          // padded slice widths: GRU (3 gates x 16), W1, W2, Wo
+}
+
+struct DwsArgs {
+  DecodeW w;
+  const float* c_in;      // [B][3H]
+  const float* h_in;      // [B][H]
+  float* Y;               // [B][20][D]
+  float* Hx[2];           // [B][H] ping-pong hidden state
+  float* T1;              // [B][Hm]
+  float* T2;              // [B][H]
+  float* Yp[2];           // [B][D4] ping-pong padded previous frame
+  unsigned* cnt;          // [row blocks] arrival counters (zeroed before the launch)
+  int B, D, H, Hm;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all 18 CTAs of the row block have published phase `target / CS`
+__device__ __forceinline__ void rowblock_sync(unsigned* cnt, unsigned target) {
+  __syncthreads();                       // every thread's exchange-buffer writes happen-before thread 0 ...
+  if (threadIdx.x == 0) {
+    __threadfence();                     // ... whose cumulative gpu-scope fence orders them before the arrival
+    atomicAdd(cnt, 1u);
+    unsigned spins = 0;
+    while (ld_acquire_u32(cnt) < target) {
+      if (++spins > (1u << 24)) __trap();          // a peer CTA never arrived: fail loudly instead of hanging the GPU
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// acc[r][c] += sum_k in[row rg*4+r][k] * Ws[k][cl + 32 c]: the input rows stream from global through a double-buffered
+// shared-memory ring (cp.async.cg = L2, never a stale L1 line), the weight slice is resident in shared memory.
+template <int NC>     // columns per thread (1 or 2); second column only for lanes < ncols2
+__device__ __forceinline__ void dws_gemm(const float* __restrict__ in, int ld_in, int K, int b0, int B, const float* Ws, int ldw,
+                                         float* ring, int tid, float acc[4][NC], bool col2) {
+  using namespace dws;
+  const int rg = tid >> 5, cl = tid & 31;
+  const int nchunks = (K + KC - 1) / KC;
+  auto issue = [&](int c) {
+    if (c < nchunks) {
+      const int k0 = c * KC, kc = min(KC, K - k0);           // multiples of 4
+      float* dst = ring + (c & 1) * RB * KC;
+      const int n4 = kc >> 2;
+      for (int i = tid; i < RB * n4; i += THREADS) {
+        const int r = i / n4, q = i - r * n4;
+        const int b = min(b0 + r, B - 1);
+        cp_async16_nn(dst + r * KC + q * 4, in + (int64_t)b * ld_in + k0 + q * 4);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  issue(0);
+  for (int c = 0; c < nchunks; ++c) {
+    issue(c + 1);
+    asm volatile("cp.async.wait_group 1;\n" ::);
+    __syncthreads();
+    const int k0 = c * KC, kc = min(KC, K - k0);
+    const float* xs = ring + (c & 1) * RB * KC + rg * 4 * KC;
+    const float* wp = Ws + (int64_t)k0 * ldw + cl;
+#pragma unroll 2
+    for (int k = 0; k < kc; k += 4) {
+      float4 x[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) x[r] = *reinterpret_cast<const float4*>(xs + r * KC + k);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float w0 = wp[(k + kk) * ldw];
+        const float w1 = (NC > 1 && col2) ? wp[(k + kk) * ldw + 32] : 0.0f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float xv = kk == 0 ? x[r].x : kk == 1 ? x[r].y : kk == 2 ? x[r].z : x[r].w;
+          acc[r][0] = fmaf(xv, w0, acc[r][0]);
+          if (NC > 1) acc[r][1] = fmaf(xv, w1, acc[r][1]);
+        }
+      }
+    }
+    __syncthreads();                     // ring buffer (c & 1) may be refilled by issue(c + 2)
+  }
+}
+
+__global__ void __launch_bounds__(dws::THREADS, 1)
+decode_ws_kernel(const DwsArgs a) {
+  using namespace dws;
+  extern __shared__ __align__(16) float sm[];
+  const int D = a.D, H = a.H, Hm = a.Hm, H3 = 3 * H, D4 = (D + 3) & ~3, B = a.B;
+  float* Wy_s = sm;                          // [D4][NG]
+  float* Whh_s = Wy_s + D4 * NG;             // [H][NG]
+  float* W1_s = Whh_s + H * NG;              // [H][N1]
+  float* W2_s = W1_s + H * N1;               // [Hm][N2]
+  float* Wo_s = W2_s + Hm * N2;              // [H][NO]
+  float* c_s = Wo_s + H * NO;                // [RB][NG]
+  float* gin = c_s + RB * NG;                // [RB][NG] gi (all gates)
+  float* ghn = gin + RB * NG;                // [RB][NG] gh (all gates)
+  float* ring = ghn + RB * NG;               // [2][RB][KC]
+  const int tid = threadIdx.x, cs = blockIdx.x, rb = blockIdx.y, b0 = rb * RB;
+  const int rg = tid >> 5, cl = tid & 31;
+  const int j0 = cs * H / CS, nj = (cs + 1) * H / CS - j0;        // my hidden columns (h, t2)
+  const int m0 = cs * Hm / CS, nm = (cs + 1) * Hm / CS - m0;      // my mlp columns (t1)
+  const int d0 = cs * D / CS, nd = (cs + 1) * D / CS - d0;        // my output columns (y)
+  unsigned* cnt = a.cnt + rb;
+  unsigned phase = 0;
+
+  // ---- resident weight slices + the step-invariant input term ----
+  for (int i = tid; i < D4 * NG; i += THREADS) {
+    const int k = i / NG, c = i % NG, g = c >> 4, jj = c & 15;
+    Wy_s[i] = (k < D && jj < nj) ? __ldg(a.w.WyT + (int64_t)k * H3 + g * H + j0 + jj) : 0.0f;
+  }
+  for (int i = tid; i < H * NG; i += THREADS) {
+    const int k = i / NG, c = i % NG, g = c >> 4, jj = c & 15;
+    Whh_s[i] = jj < nj ? __ldg(a.w.WhhT + (int64_t)k * H3 + g * H + j0 + jj) : 0.0f;
+  }
+  for (int i = tid; i < H * N1; i += THREADS) { const int k = i / N1, c = i % N1; W1_s[i] = c < nm ? __ldg(a.w.W1T + (int64_t)k * Hm + m0 + c) : 0.0f; }
+  for (int i = tid; i < Hm * N2; i += THREADS) { const int k = i / N2, c = i % N2; W2_s[i] = c < nj ? __ldg(a.w.W2T + (int64_t)k * H + j0 + c) : 0.0f; }
+  for (int i = tid; i < H * NO; i += THREADS) { const int k = i / NO, c = i % NO; Wo_s[i] = c < nd ? __ldg(a.w.WoT + (int64_t)k * D4 + d0 + c) : 0.0f; }
+  for (int i = tid; i < RB * NG; i += THREADS) {
+    const int r = i / NG, c = i % NG, g = c >> 4, jj = c & 15, b = min(b0 + r, B - 1);
+    c_s[i] = jj < nj ? a.c_in[(int64_t)b * H3 + g * H + j0 + jj] : 0.0f;
+  }
+  // ---- phase 0: publish my slice of h0 and of the last history frame ----
+  for (int i = tid; i < RB * nj; i += THREADS) {
+    const int r = i / nj, jj = i % nj, b = b0 + r;
+    if (b < B) a.Hx[0][(int64_t)b * H + j0 + jj] = a.h_in[(int64_t)b * H + j0 + jj];
+  }
+  for (int i = tid; i < RB * nd; i += THREADS) {
+    const int r = i / nd, dd = i % nd, b = b0 + r;
+    if (b < B) a.Yp[0][(int64_t)b * D4 + d0 + dd] = a.Y[(int64_t)b * 20 * D + D + d0 + dd];
+  }
+  if (cs == CS - 1)                                     // zero padding columns of both ping-pong frames
+    for (int i = tid; i < RB * (D4 - D) * 2; i += THREADS) {
+      const int r = (i >> 1) / (D4 - D), dd = (i >> 1) % (D4 - D), b = b0 + r;
+      if (b < B) a.Yp[i & 1][(int64_t)b * D4 + D + dd] = 0.0f;
+    }
+  rowblock_sync(cnt, ++phase * CS);
+
+  for (int step = 0; step < 18; ++step) {
+    const int cur = step & 1, nxt = cur ^ 1;
+    // ---- GRUCell: gi = c + y_prev Wy, gh = b_hh + h Whh for my 3 x nj gate columns ----
+    {
+      float gi[4][2], gh[4][2];
+      const bool col2 = cl < 16;                        // columns cl (gates r / z) and 32 + cl (gate n)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { gi[r][0] = gi[r][1] = 0.0f; gh[r][0] = gh[r][1] = 0.0f; }
+      dws_gemm<2>(a.Yp[cur], D4, D4, b0, B, Wy_s, NG, ring, tid, gi, col2);
+      dws_gemm<2>(a.Hx[cur], H, H, b0, B, Whh_s, NG, ring, tid, gh, col2);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int row = rg * 4 + r;
+        gin[row * NG + cl] = gi[r][0]; ghn[row * NG + cl] = gh[r][0];
+        if (col2) { gin[row * NG + 32 + cl] = gi[r][1]; ghn[row * NG + 32 + cl] = gh[r][1]; }
+      }
+      __syncthreads();
+      for (int i = tid; i < RB * nj; i += THREADS) {
+        const int r = i / nj, jj = i % nj, b = b0 + r, j = j0 + jj;
+        const float gir = c_s[r * NG + jj] + gin[r * NG + jj], giz = c_s[r * NG + 16 + jj] + gin[r * NG + 16 + jj];
+        const float gin_ = c_s[r * NG + 32 + jj] + gin[r * NG + 32 + jj];
+        const float ghr = __ldg(a.w.bhh + j) + ghn[r * NG + jj], ghz = __ldg(a.w.bhh + H + j) + ghn[r * NG + 16 + jj];
+        const float ghn_ = __ldg(a.w.bhh + 2 * H + j) + ghn[r * NG + 32 + jj];
+        const float rr = 1.0f / (1.0f + expf(-(gir + ghr)));
+        const float zz = 1.0f / (1.0f + expf(-(giz + ghz)));
+        const float nn = tanhf(gin_ + rr * ghn_);
+        if (b < B) {
+          const float hp = __ldcg(a.Hx[cur] + (int64_t)b * H + j);
+          a.Hx[nxt][(int64_t)b * H + j] = (1.0f - zz) * nn + zz * hp;
+        }
+      }
+    }
+    rowblock_sync(cnt, ++phase * CS);
+    // ---- t1 = tanh(b1 + h W1) ----
+    {
+      float acc[4][1];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r][0] = 0.0f;
+      dws_gemm<1>(a.Hx[nxt], H, H, b0, B, W1_s, N1, ring, tid, acc, false);
+      if (cl < nm) {
+        const float bb = __ldg(a.w.b1 + m0 + cl);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int b = b0 + rg * 4 + r;
+          if (b < B) a.T1[(int64_t)b * Hm + m0 + cl] = tanhf(bb + acc[r][0]);
+        }
+      }
+    }
+    rowblock_sync(cnt, ++phase * CS);
+    // ---- t2 = tanh(b2 + t1 W2) ----
+    {
+      float acc[4][1];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r][0] = 0.0f;
+      // lanes beyond the slice width keep the ring / barrier protocol and read W2_s[0] (one call site: no divergent barrier)
+      dws_gemm<1>(a.T1, Hm, Hm, b0, B, cl < N2 ? W2_s : W2_s - cl, cl < N2 ? N2 : 0, ring, tid, acc, false);
+      if (cl < nj) {
+        const float bb = __ldg(a.w.b2 + j0 + cl);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int b = b0 + rg * 4 + r;
+          if (b < B) a.T2[(int64_t)b * H + j0 + cl] = tanhf(bb + acc[r][0]);
+        }
+      }
+    }
+    rowblock_sync(cnt, ++phase * CS);
+    // ---- y = bo + t2 Wo + y_prev ----
+    {
+      float acc[4][1];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r][0] = 0.0f;
+      dws_gemm<1>(a.T2, H, H, b0, B, cl < NO ? Wo_s : Wo_s - cl, cl < NO ? NO : 0, ring, tid, acc, false);
+      if (cl < nd) {
+        const float bb = __ldg(a.w.bo + d0 + cl);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int b = b0 + rg * 4 + r;
+          if (b < B) {
+            const float y = bb + acc[r][0] + __ldcg(a.Yp[cur] + (int64_t)b * D4 + d0 + cl);
+            a.Yp[nxt][(int64_t)b * D4 + d0 + cl] = y;
+            a.Y[(int64_t)b * 20 * D + (2 + step) * D + d0 + cl] = y;
+          }
+        }
+      }
+    }
+    rowblock_sync(cnt, ++phase * CS);
+  }
+}
+
 struct RegW {               // transposed regressor weights
   const float *WaT, *WbT, *WcT;     // in_fc split: markers [201][128], xb [159][128], betas [10][128]
   const float* b_in;
@@ -703,6 +944,9 @@ struct EgMotion {
   int cap_B = 0;
   float *gi = nullptr, *gh = nullptr, *h = nullptr, *hx = nullptr, *c = nullptr, *t1 = nullptr, *t2 = nullptr;
   float *rh = nullptr, *rbase = nullptr, *rt = nullptr, *xbc = nullptr;
+  float *hx2 = nullptr, *yp2 = nullptr;   // decode_ws exchange buffers: [2][B][H], [2][B][D4]
+  unsigned* dcnt = nullptr;               // decode_ws per-row-block arrival counters
+  int decode_ws = -1;                     // -1: read EG_DECODE_WS (default on) at first use
   float* wt = nullptr;        // transposed, 4-padded weight copies for the fused kernels
   DecodeW dw{};
   RegW rw{};
@@ -723,8 +967,9 @@ enum {  // weight table order (state_dict names in comments)
 int motion_ws(EgMotion* h, int B) {
   if (B <= h->cap_B) return EG_OK;
   const EgMotionDims& d = h->d;
-  float** bufs[] = {&h->gi, &h->gh, &h->h, &h->hx, &h->c, &h->t1, &h->t2, &h->rh, &h->rbase, &h->rt, &h->xbc};
+  float** bufs[] = {&h->gi, &h->gh, &h->h, &h->hx, &h->c, &h->t1, &h->t2, &h->rh, &h->rbase, &h->rt, &h->xbc, &h->hx2, &h->yp2};
   for (auto p : bufs) { cudaFree(*p); *p = nullptr; }
+  cudaFree(h->dcnt); h->dcnt = nullptr;
   h->cap_B = 0;
   const size_t b = (size_t)B, M = b * 20;
   EG_CUDA_CHECK(cudaMalloc((void**)&h->gi, b * 3 * d.h_dim * 4));
@@ -738,6 +983,9 @@ int motion_ws(EgMotion* h, int B) {
   EG_CUDA_CHECK(cudaMalloc((void**)&h->rbase, M * d.reg_h * 4));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->rt, M * d.reg_h * 4));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->xbc, M * 159 * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->hx2, 2 * b * d.h_dim * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->yp2, 2 * b * (size_t)((d.in_dim + 3) & ~3) * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->dcnt, ((b + dws::RB - 1) / dws::RB) * sizeof(unsigned)));
   h->cap_B = B;
   return EG_OK;
 }
@@ -792,6 +1040,11 @@ static size_t decode_smem(const EgMotionDims& d) {
   const int H = d.h_dim, H3 = 3 * H, D4 = (d.in_dim + 3) & ~3, Hm = d.mlp_dim;
   return sizeof(float) * ((size_t)DR * (H3 + H + D4 + Hm + H) + (size_t)2 * 8 * DR * H3);
 }
+static size_t decode_ws_smem(const EgMotionDims& d) {
+  const int H = d.h_dim, D4 = (d.in_dim + 3) & ~3, Hm = d.mlp_dim;
+  return sizeof(float) * ((size_t)D4 * dws::NG + (size_t)H * dws::NG + (size_t)H * dws::N1 + (size_t)Hm * dws::N2 +
+                          (size_t)H * dws::NO + (size_t)3 * dws::RB * dws::NG + (size_t)2 * dws::RB * dws::KC);
+}
 constexpr size_t kRegSmem = sizeof(float) * (RR * (204 + 12 + 128 * 3 + 160) + 2 * RCHUNK_FLOATS) + sizeof(WChunk) * RTABLE;
 
 extern "C" int eg_motion_create(const EgMotionDims* dims, const void* const* weights_host, int n_weights,
@@ -808,6 +1061,8 @@ extern "C" int eg_motion_create(const EgMotionDims* dims, const void* const* wei
   h->fused = (dims->reg_h == 128 && dims->mlp_dim <= 3 * dims->h_dim) ? 1 : 0;   // fused kernels' static assumptions
   if (h->fused) {
     EG_CUDA_CHECK(cudaFuncSetAttribute(fused_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem(*dims)));
+    if (decode_ws_smem(*dims) <= 232448)
+      EG_CUDA_CHECK(cudaFuncSetAttribute(decode_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_ws_smem(*dims)));
     EG_CUDA_CHECK(cudaFuncSetAttribute(fused_regressor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRegSmem));
     int rc = motion_build_transposed(h, nullptr);
     if (rc) { delete h; return rc; }
@@ -835,8 +1090,9 @@ extern "C" void eg_motion_destroy(EgMotion* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->wt);
-  float* bufs[] = {h->gi, h->gh, h->h, h->hx, h->c, h->t1, h->t2, h->rh, h->rbase, h->rt, h->xbc};
+  float* bufs[] = {h->gi, h->gh, h->h, h->hx, h->c, h->t1, h->t2, h->rh, h->rbase, h->rt, h->xbc, h->hx2, h->yp2};
   for (auto p : bufs) cudaFree(p);
+  cudaFree(h->dcnt);
   delete h;
 }
 
@@ -870,7 +1126,18 @@ extern "C" int eg_motion_sample_prior(EgMotion* hd, const float* X, int ldx_env,
   const int Kin = H + Z + D;
   EG_TRY(linear(st, hd->hx, H, B, w[P_DRNN_WIH], Kin, w[P_DRNN_BIH], H, H3, hd->c, H3));
   EG_TRY(linear(st, z, Z, B, w[P_DRNN_WIH] + H, Kin, nullptr, Z, H3, hd->c, H3, ACT_NONE, 0.f, nullptr, 0, 1));
-  if (hd->fused) {
+  if (hd->decode_ws < 0) {
+    const char* e = getenv("EG_DECODE_WS");
+    hd->decode_ws = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (hd->fused && hd->decode_ws && B >= 64 && H == 256 && Hm == 512 && D == 201) {
+    // weight-stationary 2-D decode: 18 column-slice CTAs per 32-row block (see decode_ws_kernel)
+    const int n_rb = (B + dws::RB - 1) / dws::RB, D4 = (D + 3) & ~3;
+    EG_CUDA_CHECK(cudaMemsetAsync(hd->dcnt, 0, n_rb * sizeof(unsigned), st));
+    DwsArgs da{hd->dw, hd->c, hd->h, Y, {hd->hx2, hd->hx2 + (size_t)B * H}, hd->t1, hd->t2,
+               {hd->yp2, hd->yp2 + (size_t)B * D4}, hd->dcnt, B, D, H, Hm};
+    EG_LAUNCH(decode_ws_kernel, dim3(dws::CS, n_rb), dws::THREADS, decode_ws_smem(d), st, da);
+  } else if (hd->fused) {
     EG_LAUNCH(fused_decode_kernel, (B + DR - 1) / DR, DEC_THREADS, decode_smem(d), st, hd->dw, hd->c, hd->h, Y, B, D, H, Hm);
   } else
   for (int i = 0; i < 18; ++i) {

@@ -91,6 +91,24 @@ def test_vposer_matches_oracle(dev, world):
     assert torch.allclose(loc.cpu(), ref, atol=1e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("b", [96, 70, 256])
+def test_sample_prior_large_batch_matches_oracle(dev, world, b):
+    """B >= 64 takes the weight-stationary 2-D decode kernel (18 column-slice CTAs per 32-row block exchanging
+    activations through L2); 70 exercises the ragged last row block, 256 the bench shape."""
+    g = torch.Generator().manual_seed(100 + b)
+    X = torch.randn(2, b, 201, generator=g) * 0.3
+    z = torch.randn(b, 128, generator=g)
+    betas = torch.randn(b, 10, generator=g) * 0.5
+    Y, Yb = world["genop"].model.sample_prior(X.to(dev), betas.unsqueeze(0).repeat(18, 1, 1).to(dev), z.to(dev))
+    with torch.no_grad():
+        Yo, Ybo = world["combo"].sample_prior(X, betas.unsqueeze(0).repeat(18, 1, 1), z)
+    assert torch.allclose(Y.cpu(), Yo, atol=2e-5, rtol=1e-4), (Y.cpu() - Yo).abs().max()
+    assert torch.allclose(Yb.cpu(), Ybo, atol=1e-4, rtol=1e-4), (Yb.cpu() - Ybo).abs().max()
+    # and twice in a row (the arrival counters are re-armed per launch)
+    Y2, _ = world["genop"].model.sample_prior(X.to(dev), betas.unsqueeze(0).repeat(18, 1, 1).to(dev), z.to(dev))
+    assert torch.equal(Y, Y2)
+
+
 def _sync_oracle(orc, venv):
     b = venv.buf
     orc.set_state(state=b["state"].cpu(), seed=b["seed"].cpu(), R0=b["R0"].cpu(), T0=b["T0"].cpu().view(-1, 1, 3),
