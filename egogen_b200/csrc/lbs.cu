@@ -1131,8 +1131,10 @@ extern "C" int eg_lbs_create(const EgLbsModel* m, int device, EgLbs** out) {
     int nc = 0;
     if (cudaOccupancyMaxActiveClusters(&nc, lbs_verts_tc_kernel<true>, &cfg) == cudaSuccess && nc > 0)
       h->max_clusters = std::min(nc, kNumSMs / tc::CLUSTER);
-    else
+    else {
       cudaGetLastError();
+      h->max_clusters = tc::CLUSTER == 1 ? kNumSMs : 64;
+    }
   }
   {
     cudaDriverEntryPointQueryResult qres;
