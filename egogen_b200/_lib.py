@@ -96,6 +96,7 @@ PROTOTYPES = {
     "eg_env_set_crowd": (_I, [_P, _P, _I, _P, _I]),
     "eg_env_step": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P]),
     "eg_env_reset": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
+    "eg_env_reset_masked": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
     "eg_policy_param_count": (_L, [C.POINTER(EgPolicyDims), C.POINTER(C.c_int64)]),
     "eg_policy_create": (_I, [C.POINTER(EgPolicyDims), _P, _P, _I, C.POINTER(_P)]),
     "eg_policy_destroy": (None, [_P]),

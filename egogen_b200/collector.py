@@ -22,6 +22,40 @@ class RolloutBuffer:
         self.v_next = f()
 
 
+class LazyStats(dict):
+    """Collector statistics whose episode entries ('n/ep', 'rew', 'len', 'rews', 'lens') are read back from the device
+    on first access, so a training loop that only logs every few collects never synchronises for them."""
+
+    _LAZY = ("n/ep", "rew", "len", "rews", "lens")
+
+    def _materialise(self):
+        if "_term" in self:
+            m = dict.pop(self, "_term").bool()
+            r, l = dict.pop(self, "_ret_hist")[m], dict.pop(self, "_len_hist")[m]
+            dict.__setitem__(self, "n/ep", int(r.numel()))
+            col = dict.pop(self, "_collector", None)
+            if col is not None:
+                col.collect_episode += int(r.numel())
+            if r.numel():
+                dict.update(self, {"rew": float(r.mean()), "len": float(l.float().mean()), "rews": r.cpu().numpy(),
+                                   "lens": l.cpu().numpy()})
+
+    def __getitem__(self, k):
+        if k in self._LAZY:
+            self._materialise()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        if k in self._LAZY:
+            self._materialise()
+        return dict.get(self, k, default)
+
+    def __contains__(self, k):
+        if k in self._LAZY:
+            self._materialise()
+        return dict.__contains__(self, k)
+
+
 class Collector:
     def __init__(self, policy, venv, host_boundary: bool = False):
         """host_boundary=True reproduces the reference's host-side data path (tianshou moves actions to numpy and
@@ -78,6 +112,8 @@ class Collector:
             self.buf = RolloutBuffer(T, E, self.dev)
         b, pol, venv = self.buf, self.policy, self.venv
         rets, lens = [], []
+        if not self.host_boundary and hasattr(venv, "reset_masked") and getattr(venv, "sampler", None) is not None:
+            return self._collect_sync_free(T)
         for t in range(T):
             obs = self._policy_obs()
             out = pol.forward(Batch(obs=obs), want_value=True)
@@ -117,6 +153,44 @@ class Collector:
             stats.update({"n/ep": int(r.numel()), "rew": float(r.mean()), "len": float(l.float().mean()),
                           "rews": r.cpu().numpy(), "lens": l.cpu().numpy()})
         return batch, stats
+
+    @torch.no_grad()
+    def _collect_sync_free(self, T: int):
+        """Same transitions as collect(), with no host synchronisation inside the T vector steps: finished envs are
+        restarted on the device from the step's `terminated` buffer (CrowdVectorEnv.reset_masked), episode statistics
+        are snapshotted per step and read back once at the end."""
+        E = self.E
+        b, pol, venv = self.buf, self.policy, self.venv
+        if getattr(self, "_ret_hist", None) is None or self._ret_hist.shape[0] != T:
+            self._ret_hist = torch.zeros(T, E, device=self.dev)
+            self._len_hist = torch.zeros(T, E, dtype=torch.int32, device=self.dev)
+        for t in range(T):
+            obs = venv.observation()
+            out = pol.forward(Batch(obs=obs), want_value=True)
+            b.state[t].copy_(obs["state"]); b.ego[t].copy_(obs["egosensing"])
+            b.dist[t].copy_(obs["dist"].view(-1)); b.time[t].copy_(obs["time"].view(-1))
+            b.act[t].copy_(out.act); b.logp[t].copy_(out.logp); b.v_s[t].copy_(out.value)
+            _, rew, term, _, _ = venv.step(out.act)
+            b.rew[t].copy_(rew); b.term[t].copy_(term)
+            self.ep_ret += rew; self.ep_len += 1
+            self._ret_hist[t].copy_(self.ep_ret); self._len_hist[t].copy_(self.ep_len)
+            keep = (b.term[t] == 0)
+            self.ep_ret *= keep; self.ep_len *= keep.to(torch.int32)
+            venv.reset_masked(b.term[t])
+        _, v_last = pol.net_forward(venv.observation(), want_actor=False, want_critic=True)
+        if T > 1:
+            b.v_next[:-1].copy_(b.v_s[1:])
+        b.v_next[-1].copy_(v_last)
+        end = b.term.clone()
+        end[-1] = 1
+        ret, adv = pol.compute_returns(b.v_s, b.v_next, b.rew, b.term, end)
+        fl = lambda x: x.transpose(0, 1).reshape(T * E, *x.shape[2:]).contiguous()
+        batch = Batch(obs={"state": fl(b.state), "egosensing": fl(b.ego), "dist": fl(b.dist), "time": fl(b.time)},
+                      act=fl(b.act), logp_old=fl(b.logp), adv=fl(adv), returns=fl(ret), v_s=fl(b.v_s))
+        self.collect_step += T * E
+        stats = {"n/st": T * E, "n/ep": 0, "_term": b.term.clone(), "_ret_hist": self._ret_hist.clone(),
+                 "_len_hist": self._len_hist.clone(), "_collector": self}
+        return batch, LazyStats(stats)
 
     @torch.no_grad()
     def collect_episodes(self, n_episode: int, max_steps: int = 10000):

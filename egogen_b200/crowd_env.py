@@ -224,6 +224,58 @@ class CrowdVectorEnv:
             tries += 1
         return self.observation(), {}
 
+    # ---- sync-free restart of finished episodes ------------------------------------------------------------
+    def _validated_candidates(self, n: int, pool: int = 2048):
+        """n start candidates that eg_env_reset is known to accept: the sampler's candidates are run through the reset
+        pipeline once on scratch slots (same accept test as reset(), :379-380 / crowd_env_2f_box.py reset) and only the
+        accepted ones are kept, so reset_masked() never has to read an accept mask back. One host sync per `pool`
+        candidates instead of one per vector step."""
+        dev = self.dev
+        vp = getattr(self, "_vpool", None)
+        if vp is None or self._vptr + n > vp["goals"].shape[0]:
+            if getattr(self, "_scratch", None) is None:
+                f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+                P = pool
+                sb = dict(state=f(P, 2, 402), seed=f(P, 2, 93), R0=f(P, 3, 3), T0=f(P, 3), betas=f(P, 10), dist=f(P),
+                          steps=torch.zeros(P, dtype=torch.int32, device=dev), goal=f(P, 3), ego=f(P, 2, 32),
+                          obs_dist=f(P), obs_time=f(P), reward=f(P), terminated=torch.zeros(P, dtype=torch.uint8, device=dev),
+                          goal_reached=None, reward_terms=None, out_markers=None, out_params=None, out_pelvis=None)
+                self._scratch = sb
+                self._scratch_c = _lib.EgEnvBuffers(**{k: (C.c_void_p(v.data_ptr()) if v is not None else None)
+                                                       for k, v in sb.items()})
+                self._scratch_ids = torch.arange(P, dtype=torch.int32, device=dev)
+            parts, have = [], 0
+            while have < max(n, pool // 2):
+                s = self.sampler.next_body(pool)
+                accept = torch.zeros(pool, dtype=torch.int32, device=dev)
+                with torch.cuda.device(dev):
+                    _lib.check(_lib.lib().eg_env_reset(self._h, C.byref(self._scratch_c), _lib.ptr(self._scratch_ids), pool,
+                                                       _lib.ptr(s["world_params"].contiguous()), _lib.ptr(s["goals"].contiguous()),
+                                                       _lib.ptr(s["betas"].contiguous()), _lib.ptr(accept), _lib.stream_ptr(dev)))
+                ok = accept != 0                                         # the one host sync of the refill
+                parts.append({k: s[k][ok].clone() for k in ("world_params", "goals", "betas")})
+                have += int(ok.sum())
+            self._vpool = {k: torch.cat([p_[k] for p_ in parts]) for k in ("world_params", "goals", "betas")}
+            self._vptr = 0
+        a, b = self._vptr, self._vptr + n
+        self._vptr = b
+        return {k: v[a:b] for k, v in self._vpool.items()}
+
+    def reset_masked(self, mask: torch.Tensor):
+        """Restart the envs whose mask entry is non-zero (device uint8 [E], e.g. the `terminated` buffer) without any
+        host synchronisation: every slot gets a pre-validated candidate, eg_env_reset_masked commits it where asked."""
+        dev = self.dev
+        s = self._validated_candidates(self.E)
+        if getattr(self, "_accept_all", None) is None:
+            self._accept_all = torch.zeros(self.E, dtype=torch.int32, device=dev)
+        m = mask if mask.dtype == torch.uint8 else mask.to(torch.uint8)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().eg_env_reset_masked(self._h, C.byref(self._cbuf), _lib.ptr(m.contiguous()), self.E,
+                                                      _lib.ptr(s["world_params"].contiguous()), _lib.ptr(s["goals"].contiguous()),
+                                                      _lib.ptr(s["betas"].contiguous()), _lib.ptr(self._accept_all),
+                                                      _lib.stream_ptr(dev)))
+        return self._accept_all
+
     def reset_from(self, env_ids, world_params, goals, betas):
         """Deterministic reset from explicit candidates (tests / parity); returns the accept mask."""
         dev = self.dev

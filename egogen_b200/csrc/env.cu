@@ -363,9 +363,13 @@ env_reset_commit_kernel(EgEnvBuffers b, const int32_t* __restrict__ env_ids, int
                         const float* __restrict__ joints_c, const float* __restrict__ markers_c,
                         const float* __restrict__ goals, const float* __restrict__ betas_c,
                         int32_t* __restrict__ accept, EgEnvConfig cfg, const float* __restrict__ tris, int n_tris,
-                        int check_start, float* __restrict__ bbox_out) {
+                        int check_start, float* __restrict__ bbox_out, const uint8_t* __restrict__ mask) {
   const int i = blockIdx.x, tid = threadIdx.x;
   __shared__ float ms_xy[2 * NM * 2], red[8];
+  if (mask != nullptr && mask[i] == 0) {        // masked reset: this slot keeps running its episode
+    if (tid == 0) accept[i] = 0;
+    return;
+  }
   bool ok;
   if (!check_start) {                           // crowd eval: fixed start data, no rejection (crowd_env_crowd_eval.py:391-405)
     ok = true;
@@ -382,7 +386,7 @@ env_reset_commit_kernel(EgEnvBuffers b, const int32_t* __restrict__ env_ids, int
   }
   if (tid == 0) accept[i] = ok ? 1 : 0;
   if (!ok) return;
-  const int e = env_ids[i];
+  const int e = env_ids ? env_ids[i] : i;
   __shared__ float goal_l[3];
   const float* R0 = R0c + (int64_t)i * 9;
   const float* T0 = T0c + (int64_t)i * 3;
@@ -643,10 +647,28 @@ extern "C" int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int 
   return EG_OK;
 }
 
+static int env_reset_impl(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_ids, const uint8_t* mask, int n,
+                          const float* world_params, const float* goals, const float* betas_cand,
+                          int32_t* accept, void* stream);
+
 extern "C" int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_ids, int n,
                             const float* world_params, const float* goals, const float* betas_cand,
                             int32_t* accept, void* stream) {
-  EG_REQUIRE(h && b && env_ids && world_params && goals && betas_cand && accept, "null pointer");
+  EG_REQUIRE(env_ids != nullptr, "null pointer");
+  return env_reset_impl(h, b, env_ids, nullptr, n, world_params, goals, betas_cand, accept, stream);
+}
+
+extern "C" int eg_env_reset_masked(EgEnv* h, const EgEnvBuffers* b, const uint8_t* mask, int E,
+                                   const float* world_params, const float* goals, const float* betas_cand,
+                                   int32_t* accept, void* stream) {
+  EG_REQUIRE(mask != nullptr, "null pointer");
+  return env_reset_impl(h, b, nullptr, mask, E, world_params, goals, betas_cand, accept, stream);
+}
+
+static int env_reset_impl(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_ids, const uint8_t* mask, int n,
+                          const float* world_params, const float* goals, const float* betas_cand,
+                          int32_t* accept, void* stream) {
+  EG_REQUIRE(h && b && world_params && goals && betas_cand && accept, "null pointer");
   EG_REQUIRE(h->grid != nullptr, "scene not set (eg_env_set_scene)");
   if (n <= 0) return EG_OK;
   EG_CUDA_CHECK(cudaSetDevice(h->device));
@@ -663,7 +685,7 @@ extern "C" int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_
                               h->center, h->scale, h->skip, h->counts, h->joints2, h->mproj, stream));
   }
   EG_LAUNCH(env_reset_commit_kernel, n, 256, 0, st, *b, env_ids, n, h->counts, h->R0c, h->T0c, h->seedc,
-            h->joints2, h->mproj, goals, betas_cand, accept, h->cfg, h->tris, h->n_tris, h->pene_terminates, h->bbox_out);
+            h->joints2, h->mproj, goals, betas_cand, accept, h->cfg, h->tris, h->n_tris, h->pene_terminates, h->bbox_out, mask);
   EG_LAUNCH(env_egosensing_kernel, n, 64, 0, st, h->joints2, h->R0c, h->T0c, env_ids, accept, h->segs, h->S,
             (double)h->cfg.ray_len, b->ego, h->holes, h->n_holes);
   return EG_OK;

@@ -259,6 +259,12 @@ int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int E, void* st
  * slot was initialised, 0 where the caller must resample. */
 int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_ids, int n, const float* world_params,
                  const float* goals, const float* betas_cand, int32_t* accept, void* stream);
+/* same for ALL E slots at once, committed only where mask[e] != 0 (device uint8 [E], typically the `terminated` flags of
+ * the step that just ran): candidate e is for slot e. Lets a collector restart finished episodes (tianshou
+ * Collector.collect: finished envs are reset immediately, crowd_env_2f.py:320) without reading the mask back to the
+ * host. accept [E] = 1 where a slot was restarted. */
+int eg_env_reset_masked(EgEnv* h, const EgEnvBuffers* b, const uint8_t* mask, int E, const float* world_params,
+                        const float* goals, const float* betas_cand, int32_t* accept, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * PPO policy - replaces GAMMAPolicyBase / GAMMAActor / GAMMACritic forward

@@ -322,3 +322,35 @@ def test_crowd_scene_env_matches_oracle(dev, world, smplx_model):
     venv.step(torch.zeros(E, 128, device=dev))
     assert bool(torch.isfinite(venv.buf["reward"]).all())
     venv.close()
+
+
+def test_sync_free_collect_restarts_finished_envs(dev):
+    """The device-side restart path (eg_env_reset_masked + pre-validated start candidates): every env flagged
+    `terminated` in step t starts step t+1 from a fresh episode (time observation 1, distance reset), every other env
+    continues, and the lazily read statistics count exactly the terminated transitions."""
+    from egogen_b200.runtime import build_world
+    w = build_world(dev, 32, seed=3, sdf_res=64)
+    col, venv = w["collector"], w["venv"]
+    w["policy"].train()
+    col.reset()
+    # validated candidates are accepted by construction
+    s = venv._validated_candidates(32)
+    acc = venv.reset_from(torch.arange(32), s["world_params"], s["goals"], s["betas"])
+    assert bool((acc != 0).all())
+    total_term = 0
+    for it in range(5):                       # 13-step episodes: 20 vector steps see every env finish at least once
+        batch, st = col.collect(32 * 4)
+        b = col.buf
+        term = b.term.bool()
+        total_term += int(term.sum())
+        assert st["n/ep"] == int(term.sum())
+        assert bool(torch.isfinite(batch.returns).all()) and bool(torch.isfinite(batch.adv).all())
+        for t in range(3):
+            nxt_time = b.time[t + 1]
+            assert torch.allclose(nxt_time[term[t]], torch.ones_like(nxt_time[term[t]]))          # restarted: 1 - 0/max_depth
+            assert bool((nxt_time[~term[t]] < b.time[t][~term[t]]).all())                        # running: time decreases
+        if term[3].any():
+            assert torch.allclose(venv.buf["obs_time"][term[3]], torch.ones_like(venv.buf["obs_time"][term[3]]))
+            assert bool((venv.buf["steps"][term[3]] == 0).all())
+    assert total_term >= 32
+    assert col.collect_episode == total_term
