@@ -418,7 +418,8 @@ static int launch_variant(const GemmArgs& g, cudaStream_t st) {
     }
     if (tiles <= max_clusters[c]) { sk = c; break; }
   }
-  if (getenv("EG_GEMM_TC_DEBUG")) fprintf(stderr, "[gemm_tc<%d,%d>] M=%d N=%d K=%d tiles=%d sk=%d\n", (int)A_MN, (int)B_MN, g.M, g.N, g.K, tiles, sk);
+  static const bool debug = getenv("EG_GEMM_TC_DEBUG") != nullptr;
+  if (debug) fprintf(stderr, "[gemm_tc<%d,%d>] M=%d N=%d K=%d tiles=%d sk=%d\n", (int)A_MN, (int)B_MN, g.M, g.N, g.K, tiles, sk);
   Params p{g.C, g.ldc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, g.act, g.slope, g.beta, g.alpha, (kb_total + sk - 1) / sk};
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, sk);
