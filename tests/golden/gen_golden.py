@@ -108,3 +108,14 @@ sub = np.load(os.path.join(REF, "motion/data/locomotion/subseq_00343.npz"))
 jl = torch.as_tensor(sub["joints"][:1], dtype=torch.float32)
 R2, T2 = ce.get_new_coordinate_torch(jl.clone())
 save("coord_golden.npz", jts=jts, R=R, T=T, jts_loco=jl, R_loco=R2, T_loco=T2)
+
+
+def gen_locomotion_seed():
+    """tests/golden/locomotion_seed_00343.npz: the reference's motion seed fixture motion/data/locomotion/subseq_00343.npz
+    trimmed to the keys the start-body samplers read (environments.py:1048-1066)."""
+    d = np.load(os.path.join(REF, "motion", "data", "locomotion", "subseq_00343.npz"), allow_pickle=True)
+    np.savez_compressed(os.path.join(HERE, "locomotion_seed_00343.npz"), poses=d["poses"][:, :66].astype(np.float32),
+                        trans=d["trans"].astype(np.float32), betas=d["betas"].astype(np.float32))
+
+
+gen_locomotion_seed()

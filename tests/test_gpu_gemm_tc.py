@@ -81,3 +81,21 @@ def test_gemm_tc_backward_layouts(M, N, K, ta, tb):
         want = ref + (C0.double() if acc else 0.0)
         err = (Cm.double() - want).abs().max().item()
         assert err <= 1e-5 * max(want.abs().max().item(), 1.0), (acc, err)
+
+
+def test_matmul_edge_cases_and_fallback_layouts():
+    """Empty products are no-ops, null pointers are rejected with EG_ERR_INVALID_ARG, and shapes the tensor-core path
+    does not take (unaligned pitch, tiny K) still give the right answer through the SIMT tiles."""
+    dev = torch.device("cuda:0")
+    lib = _lib.lib()
+    A = torch.randn(8, 70, device=dev); B = torch.randn(70, 40, device=dev); Cm = torch.full((8, 40), 7.0, device=dev)
+    assert lib.eg_matmul(_lib.ptr(A), 70, 0, _lib.ptr(B), 40, 0, 0, 40, 70, _lib.ptr(Cm), 40, 0, _lib.stream_ptr(dev)) == 0
+    assert bool((Cm == 7.0).all())                                    # M = 0: untouched
+    assert lib.eg_matmul(None, 70, 0, _lib.ptr(B), 40, 0, 8, 40, 70, _lib.ptr(Cm), 40, 0, _lib.stream_ptr(dev)) < 0
+    assert b"invalid argument" in lib.eg_last_error()
+    # pitch 70 is not 16-byte aligned and K = 6 is below the tensor-core threshold: SIMT fallback
+    for (M, N, K) in [(8, 40, 70), (33, 65, 6), (256, 130, 402)]:
+        A = torch.randn(M, K, device=dev); B = torch.randn(K, N, device=dev); Cm = torch.empty(M, N, device=dev)
+        _lib.check(lib.eg_matmul(_lib.ptr(A), K, 0, _lib.ptr(B), N, 0, M, N, K, _lib.ptr(Cm), N, 0, _lib.stream_ptr(dev)))
+        ref = A.double() @ B.double()
+        assert (Cm.double() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1.0)

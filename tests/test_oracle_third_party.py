@@ -96,3 +96,29 @@ def test_gae_matches_closed_form():
             w *= 0.99 * 0.95
         exp[i] = acc
     assert np.allclose(adv, exp)
+
+
+def test_start_body_oracle_invariants():
+    """f-3 oracle (oracle/sampler.py, environments.py:1041-1131) on the reference's own motion seed fixture: after
+    gen_init_body the body's forward axis points from start to target, the pelvis stands over the start point, the lowest
+    joint of frame 0 touches the floor and wpath is snapped to the pelvis height."""
+    import os
+    import numpy as np
+    import torch
+    from egogen_b200 import assets
+    from oracle.sampler import gen_init_body
+    from oracle.smplx_lbs import SMPLXParserOracle
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "locomotion_seed_00343.npz"))
+    parser = SMPLXParserOracle(assets.make_surrogate_smplx(seed=0), marker=assets.marker_ids())
+    start, target = np.array([1.0, -2.0, 0.0], np.float32), np.array([-2.5, 1.5, 0.0], np.float32)
+    r = gen_init_body(parser, start, target, d["betas"], d["poses"][3:5, 3:66], d["poses"][3:5, :3], d["trans"][3:5], yaw=0.0)
+    j = r["joints"]
+    x_axis = j[0, 2] - j[0, 1]; x_axis[2] = 0
+    fwd = torch.cross(torch.tensor([0.0, 0.0, 1.0]), x_axis / x_axis.norm(), dim=0)
+    t = torch.as_tensor(target - start); t = t / t.norm()
+    assert torch.allclose(fwd / fwd.norm(), t, atol=1e-4)                     # faces the target (yaw jitter 0)
+    assert torch.allclose(j[0, 0, :2], torch.as_tensor(start[:2]), atol=1e-5)  # pelvis over the start point
+    assert abs(float(j[0, :, 2].min())) < 1e-5                                 # lowest joint on the floor
+    assert torch.allclose(r["wpath"][0], j[0, 0]) and float(r["wpath"][1, 2]) == float(r["wpath"][0, 2])
+    R = r["global_orient_matrix"]
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(2, 3, 3), atol=1e-5)
