@@ -158,3 +158,36 @@ def test_fused_lbs_sdf_counts(dev, parser, smplx_model):
     rc, _, _ = osdf.penetration_counts(rs, assets.feet_vids(), T)
     near_o = (rs.abs() < 1e-4).sum(dim=-1)
     assert ((counts.cpu().view(E, T) - rc).abs() <= near_o).all()
+
+
+def test_fused_counts_at_bench_size(dev, parser):
+    """BASELINE config-2 size (256 envs x 20 frames = 5120 bodies, 256^3 SDF, bodies standing on the floor next to a
+    box): the fused tcgen05 kernel's per-body penetration counts (2-level conservative sign bits + exact sample) equal
+    the unfused operator chain (materialised vertices -> calc_sdf -> count) on the same GPU vertices, body for body,
+    up to vertices within 1e-5 of the zero level."""
+    from egogen_b200 import calc_sdf, penetration_count
+    E, T = 256, 20
+    g = torch.Generator().manual_seed(17)
+    xb = torch.randn(E * T, 93, generator=g) * 0.15
+    xb[:, 3] += 3.14159265 / 2                                  # y-up template -> z-up
+    xb[:, :3] = 0.0
+    betas = torch.randn(E, 10, generator=g) * 0.5
+    scene = assets.rasterize_scene_sdf(assets.make_box_scene(5, n_boxes=2), D=256, device=str(dev))
+    sd = {k: v.to(dev) for k, v in scene.items()}
+    ang = torch.rand(E, generator=g) * 6.28
+    R0 = torch.zeros(E, 3, 3); R0[:, 0, 0] = ang.cos(); R0[:, 0, 1] = -ang.sin()
+    R0[:, 1, 0] = ang.sin(); R0[:, 1, 1] = ang.cos(); R0[:, 2, 2] = 1
+    T0 = torch.cat([torch.rand(E, 1, 2, generator=g) * 5 - 2.5, torch.full((E, 1, 1), 1.05)], dim=2)
+    skip = torch.zeros(assets.V_SMPLX, dtype=torch.uint8)
+    skip[assets.feet_vids()] = 1
+    bm = parser.bm_male
+    brow = betas.repeat_interleave(T, 0)
+    counts, _, _ = bm.forward_sdf(xb.to(dev), brow.to(dev), T, R0.to(dev), T0.to(dev), sd, skip.to(dev))
+    verts = bm.forward(xb.to(dev), brow.to(dev), want_verts=True)[0]
+    vw = torch.einsum("bij,btpj->btpi", R0.to(dev), verts.view(E, T, -1, 3)) + T0.to(dev)[:, None]
+    sv = calc_sdf(vw.reshape(E * T, -1, 3), sd)
+    c2 = penetration_count(sv, skip.to(dev))
+    near = (sv.abs() < 1e-5).sum(dim=1)
+    assert bool(((counts - c2).abs() <= near).all()), (counts - c2).abs().max()
+    assert int((counts > 0).sum()) > E * T // 20, "bodies intersecting the floor / boxes must be present"
+    assert int((counts == 0).sum()) > 0
