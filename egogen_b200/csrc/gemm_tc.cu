@@ -29,20 +29,25 @@
 namespace eg {
 namespace gtc {
 
-constexpr int BM = 128, BN = 64, BK = 32;           // BK fp32 = 128 B = one swizzle row
-constexpr int STAGES = 2;                            // 2 x 48 KB: two CTAs per SM, so 4-CTA clusters of small-M layers are co-resident
+constexpr int BM = 128, BK = 32;                     // BK fp32 = 128 B = one swizzle row; BN (64 or 128) is a template parameter
+constexpr int STAGES = 2;
 constexpr int A_BYTES = BM * BK * 4;                // 16 KB
-constexpr int B_BYTES = BN * BK * 4;                // 8 KB
-constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // raw(hi) A, raw(hi) B, lo A, lo B = 48 KB
-constexpr int TMEM_COLS = 64;
 constexpr int XF_WARPS = 8;                          // transform + epilogue warps
 constexpr int THREADS = 64 + XF_WARPS * 32;          // 320
 constexpr int XF_THREADS = XF_WARPS * 32;
-constexpr int EPI_COLS = BN / (XF_WARPS / 4);        // columns per epilogue thread (two warps share a TMEM lane quarter)
-constexpr int RED_LD = BN + 1;                       // padded row of the split-k reduction buffer
-constexpr int OFF_BARS = STAGES * STAGE_BYTES;
-constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
-static_assert(BM * RED_LD * 4 <= STAGES * STAGE_BYTES, "reduction buffer aliases the operand ring");
+// geometry that depends on the tile width
+template <int BN>
+struct Geo {
+  static constexpr int B_BYTES = BN * BK * 4;                   // 8 / 16 KB
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // raw(hi) A, raw(hi) B, lo A, lo B = 48 / 64 KB
+  static constexpr int TMEM_COLS = BN;
+  static constexpr int EPI_COLS = BN / (XF_WARPS / 4);          // columns per epilogue thread (two warps share a TMEM lane quarter)
+  static constexpr int RED_LD = BN + 1;                         // padded row of the split-k reduction buffer
+  static constexpr int OFF_BARS = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
+  static_assert(BM * RED_LD * 4 <= STAGES * STAGE_BYTES, "reduction buffer aliases the operand ring");
+  static_assert((A_BYTES + B_BYTES) / 16 % XF_THREADS == 0, "transform work split");
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -91,7 +96,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t ch
   return d;
 }
 // kind::tf32, fp32 accumulate, M = 128, N = 64; bit 15 / 16 = A / B is MN-major
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
   constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -149,10 +154,13 @@ struct Params {
 
 // A_MN / B_MN: the operand is stored with its M / N index contiguous (dW = dY^T X has both, dX = dY W has B) instead of
 // its k index (nn.Linear forward). MN-major tiles are staged as 32-wide chunks, one TMA box [32 k][32 mn] each.
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(THREADS, 2)
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
   namespace cg = cooperative_groups;
+  using G = Geo<BN>;
+  constexpr int B_BYTES = G::B_BYTES, STAGE_BYTES = G::STAGE_BYTES, TMEM_COLS = G::TMEM_COLS, EPI_COLS = G::EPI_COLS,
+                RED_LD = G::RED_LD, OFF_BARS = G::OFF_BARS;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
@@ -225,9 +233,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kk = 0; kk < BK / 8; ++kk) {
           // one 8-wide k step: K-major advances 32 B inside the swizzle atom, MN-major one 8-row group (1024 B)
           const uint64_t oa = (uint64_t)(A_MN ? kk * 64 : kk * 2), ob = (uint64_t)(B_MN ? kk * 64 : kk * 2);
-          umma_tf32<A_MN, B_MN>(tmem_base, a_lo + oa, b_hi + ob, (i | kk) ? 1u : 0u);
-          umma_tf32<A_MN, B_MN>(tmem_base, a_hi + oa, b_lo + ob, 1u);
-          umma_tf32<A_MN, B_MN>(tmem_base, a_hi + oa, b_hi + ob, 1u);
+          umma_tf32<A_MN, B_MN, BN>(tmem_base, a_lo + oa, b_hi + ob, (i | kk) ? 1u : 0u);
+          umma_tf32<A_MN, B_MN, BN>(tmem_base, a_hi + oa, b_lo + ob, 1u);
+          umma_tf32<A_MN, B_MN, BN>(tmem_base, a_hi + oa, b_hi + ob, 1u);
         }
         umma_commit(&empty_bar[s]);
         if (i == nkb - 1) umma_commit(acc_bar);
@@ -382,12 +390,13 @@ static bool get_map(const float* base, int rows, int cols, int ld, int box_rows,
 static int g_gemm_tc_enabled = -1;          // -1: read EG_GEMM_TC (default on) at first use
 void gemm_tc_set_enabled(int on) { g_gemm_tc_enabled = on ? 1 : 0; }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 static int launch_variant(const GemmArgs& g, cudaStream_t st) {
   using namespace gtc;
+  constexpr int SMEM_BYTES = Geo<BN>::SMEM_BYTES;
   static bool attr_done = false;
   static int max_clusters[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};     // indexed by cluster size
-  auto kernel = gemm_tc_kernel<A_MN, B_MN>;
+  auto kernel = gemm_tc_kernel<A_MN, B_MN, BN>;
   if (!attr_done) {
     EG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
@@ -419,7 +428,7 @@ static int launch_variant(const GemmArgs& g, cudaStream_t st) {
     if (tiles <= max_clusters[c]) { sk = c; break; }
   }
   static const bool debug = getenv("EG_GEMM_TC_DEBUG") != nullptr;
-  if (debug) fprintf(stderr, "[gemm_tc<%d,%d>] M=%d N=%d K=%d tiles=%d sk=%d\n", (int)A_MN, (int)B_MN, g.M, g.N, g.K, tiles, sk);
+  if (debug) fprintf(stderr, "[gemm_tc<%d,%d,%d>] M=%d N=%d K=%d tiles=%d sk=%d\n", (int)A_MN, (int)B_MN, BN, g.M, g.N, g.K, tiles, sk);
   Params p{g.C, g.ldc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, g.act, g.slope, g.beta, g.alpha, (kb_total + sk - 1) / sk};
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, sk);
@@ -464,9 +473,13 @@ int launch_gemm_tc(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
     }
   }
   if (!g_encode) return 1;
-  if (!TA && TB) return launch_variant<false, false>(g, st);
-  if (!TA && !TB) return launch_variant<false, true>(g, st);
-  return launch_variant<true, true>(g, st);
+  // 128-wide tiles (EG_GEMM_TC_BN128=1) cut the operand traffic per flop but halve the CTA count; measured on the path's
+  // shapes they are no faster for M = 256 (18.8 us) and slower for M >= 4096 (53.7 vs 41.9 us), so 64 is the default
+  static const bool wide_ok = getenv("EG_GEMM_TC_BN128") != nullptr;
+  const bool wide = wide_ok && g.N >= 512;
+  if (!TA && TB) return wide ? launch_variant<false, false, 128>(g, st) : launch_variant<false, false, 64>(g, st);
+  if (!TA && !TB) return wide ? launch_variant<false, true, 128>(g, st) : launch_variant<false, true, 64>(g, st);
+  return wide ? launch_variant<true, true, 128>(g, st) : launch_variant<true, true, 64>(g, st);
 }
 
 }  // namespace eg
