@@ -473,10 +473,12 @@ int launch_gemm_tc(const GemmArgs& g, bool TA, bool TB, cudaStream_t st) {
     }
   }
   if (!g_encode) return 1;
-  // 128-wide tiles (EG_GEMM_TC_BN128=1) cut the operand traffic per flop but halve the CTA count; measured on the path's
-  // shapes they are no faster for M = 256 (18.8 us) and slower for M >= 4096 (53.7 vs 41.9 us), so 64 is the default
-  static const bool wide_ok = getenv("EG_GEMM_TC_BN128") != nullptr;
-  const bool wide = wide_ok && g.N >= 512;
+  // 128-wide tiles (EG_GEMM_TC_BN128=1) cut the operand traffic per flop but halve the CTA count. Measured on the path's
+  // shapes: no faster for M = 256 (18.8 us), slower for M >= 4096 (53.7 vs 41.9 us), and using them only where the
+  // 64-wide tiling spills into a second wave (dW of the 1152 x 1152 layers, 162 vs 81 tiles) cost 2 % of the whole
+  // iteration in an A/B on one box (50.35 k vs 51.3 k env-steps/s) - so 64 is the default everywhere.
+  static const char* wide_env = getenv("EG_GEMM_TC_BN128");
+  const bool wide = wide_env != nullptr && wide_env[0] == '1' && g.N >= 512;
   if (!TA && TB) return wide ? launch_variant<false, false, 128>(g, st) : launch_variant<false, false, 64>(g, st);
   if (!TA && !TB) return wide ? launch_variant<false, true, 128>(g, st) : launch_variant<false, true, 64>(g, st);
   return wide ? launch_variant<true, true, 128>(g, st) : launch_variant<true, true, 64>(g, st);
