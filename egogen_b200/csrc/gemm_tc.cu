@@ -192,6 +192,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
+  // programmatic dependent launch: the next kernel of the stream may start its own prologue (barrier init, TMEM
+  // allocation, descriptor fetch) now; this kernel touches global memory only after its predecessor has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -435,10 +439,13 @@ static int launch_variant(const GemmArgs& g, cudaStream_t st) {
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  static const bool pdl = !(getenv("EG_GEMM_TC_PDL") != nullptr && getenv("EG_GEMM_TC_PDL")[0] == '0');
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = sk;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, mapA, mapB, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   EG_CUDA_CHECK(e);
