@@ -47,6 +47,28 @@ inline int set_error(int code, const char* fmt, const char* a = "", const char* 
     EG_CUDA_CHECK(cudaGetLastError());                                                   \
   } while (0)
 
+// Programmatic dependent launch for the short kernels that sit between the dense layers: the kernel may be scheduled
+// while its predecessor drains; eg_pdl_enter() (FIRST statement of such a kernel) releases this kernel's own dependents and
+// then blocks until the predecessor grid has completed and its writes are visible. A kernel launched this way without
+// eg_pdl_enter() would race with its producer - only kernels that call it may use EG_LAUNCH_PDL.
+__device__ __forceinline__ void eg_pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#define EG_LAUNCH_PDL(kernel, grid_, block_, smem_, stream_, ...)                          \
+  do {                                                                                   \
+    cudaLaunchConfig_t _cfg{};                                                           \
+    _cfg.gridDim = dim3(grid_); _cfg.blockDim = dim3(block_);                            \
+    _cfg.dynamicSmemBytes = (smem_); _cfg.stream = (stream_);                            \
+    cudaLaunchAttribute _at[1];                                                          \
+    _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                      \
+    _at[0].val.programmaticStreamSerializationAllowed = 1;                               \
+    _cfg.attrs = _at; _cfg.numAttrs = 1;                                                 \
+    cudaError_t _le = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                    \
+    eg::g_launch_count.fetch_add(1, std::memory_order_relaxed);                          \
+    EG_CUDA_CHECK(_le);                                                                  \
+  } while (0)
+
 // Optional device-side timing of one named kernel class (bench.py roofline): CUDA events recorded on the
 // launching stream around the kernel; eg_profile_read() synchronises and sums them.
 struct ProfSlot { cudaEvent_t a, b; int64_t units; };

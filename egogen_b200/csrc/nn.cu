@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(256)
 gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ b_hh,
                 const float* __restrict__ h_in, float* __restrict__ h_out, int M, int H, int ld_h_out,
                 float* r_save, float* z_save, float* n_save, float* ghn_save) {
+  eg_pdl_enter();
   const int64_t total = (int64_t)M * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / H), j = (int)(i % H);
@@ -308,7 +309,7 @@ int launch_gru_gate(cudaStream_t st, const float* gi, const float* gh, const flo
                     float* z_save, float* n_save, float* ghn_save) {
   const int64_t total = (int64_t)M * H;
   const int grid = (int)std::min<int64_t>((total + 255) / 256, kNumSMs * 8);
-  EG_LAUNCH(gru_gate_kernel, grid, 256, 0, st, gi, gh, b_hh, h_in, h_out, M, H, ld_h_out, r_save, z_save,
+  EG_LAUNCH_PDL(gru_gate_kernel, grid, 256, 0, st, gi, gh, b_hh, h_in, h_out, M, H, ld_h_out, r_save, z_save,
             n_save, ghn_save);
   return EG_OK;
 }

@@ -66,12 +66,14 @@ pe_kernel(const float* __restrict__ dist, const float* __restrict__ time, int B,
 __global__ void __launch_bounds__(256)
 lrelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float slope, int64_t n,
                  float* __restrict__ dx) {
+  eg_pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dx[i] = y[i] > 0.0f ? dy[i] : dy[i] * slope;
 }
 
 __global__ void __launch_bounds__(256)
 add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ c) {
+  eg_pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     c[i] = a[i] + b[i];
 }
@@ -80,6 +82,7 @@ add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, 
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dY, int ld, int M, int N, float* __restrict__ db) {
   __shared__ float part[8][33];
+  eg_pdl_enter();
   const int col = blockIdx.x * 32 + threadIdx.x % 32, rl = threadIdx.x / 32;
   float s = 0.0f;
   if (col < N)
@@ -99,6 +102,7 @@ __global__ void __launch_bounds__(256)
 gru_bwd_kernel(const float* __restrict__ dh, int ld_dh, const float* __restrict__ r, const float* __restrict__ z,
                const float* __restrict__ n, const float* __restrict__ ghn, const float* __restrict__ h_prev,
                int M, int H, float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dh_prev) {
+  eg_pdl_enter();
   const int64_t total = (int64_t)M * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / H), j = (int)(i % H);
@@ -397,7 +401,7 @@ static int mlp_block_forward(EgPolicy* h, cudaStream_t st, const Lin blk[][2], c
   for (int k = 0; k < h->d.n_blocks; ++k) {
     EG_TRY(linear(st, in[k], D, B, P + blk[k][0].w, D, P + blk[k][0].b, D, D, t[k], D, ACT_LRELU, 0.01f));
     EG_TRY(linear(st, t[k], D, B, P + blk[k][1].w, D, P + blk[k][1].b, D, D, u[k], D, ACT_LRELU, 0.01f));
-    EG_LAUNCH(add_kernel, ew_grid((int64_t)B * D), 256, 0, st, u[k], in[k], (int64_t)B * D, in[k + 1]);
+    EG_LAUNCH_PDL(add_kernel, ew_grid((int64_t)B * D), 256, 0, st, u[k], in[k], (int64_t)B * D, in[k + 1]);
   }
   EG_TRY(linear(st, in[h->d.n_blocks], D, B, P + outl.w, D, P + outl.b, D, outl.out, out, outl.out));
   return EG_OK;
@@ -447,7 +451,7 @@ static int linear_backward(EgPolicy* h, cudaStream_t st, const float* dY, int ld
   float* G = h->G;
   GemmArgs gw{dY, ld_dy, 1, X, ldx, G + l.w, l.in, nullptr, nullptr, 0, l.out, l.in, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(gw, true, false, st));
-  EG_LAUNCH(colsum_kernel, (l.out + 31) / 32, 256, 0, st, dY, ld_dy, B, l.out, G + l.b);
+  EG_LAUNCH_PDL(colsum_kernel, (l.out + 31) / 32, 256, 0, st, dY, ld_dy, B, l.out, G + l.b);
   if (dX) {
     GemmArgs gx{dY, ld_dy, 1, P + l.w, l.in, dX, ld_dx, nullptr, nullptr, 0, B, l.in, l.out, ACT_NONE, 0.f, dx_beta, 1.0f};
     EG_TRY(launch_gemm(gx, false, false, st));
@@ -463,13 +467,13 @@ static int mlp_block_backward(EgPolicy* h, cudaStream_t st, const Lin blk[][2], 
   EG_TRY(linear_backward(h, st, d_out, outl.out, in[h->d.n_blocks], D, B, outl, h->dh, D, 0));
   for (int k = h->d.n_blocks - 1; k >= 0; --k) {
     // in[k+1] = u + in[k];  u = lrelu(t W2^T + b2);  t = lrelu(in[k] W1^T + b1)
-    EG_LAUNCH(lrelu_bwd_kernel, ew_grid(n), 256, 0, st, h->dh, u[k], 0.01f, n, h->da);
+    EG_LAUNCH_PDL(lrelu_bwd_kernel, ew_grid(n), 256, 0, st, h->dh, u[k], 0.01f, n, h->da);
     EG_TRY(linear_backward(h, st, h->da, D, t[k], D, B, blk[k][1], h->dt, D, 0));
-    EG_LAUNCH(lrelu_bwd_kernel, ew_grid(n), 256, 0, st, h->dt, t[k], 0.01f, n, h->da);
+    EG_LAUNCH_PDL(lrelu_bwd_kernel, ew_grid(n), 256, 0, st, h->dt, t[k], 0.01f, n, h->da);
     // d in[k] = da1 W1 + dh (residual): accumulate straight into dh
     EG_TRY(linear_backward(h, st, h->da, D, in[k], D, B, blk[k][0], h->dh, D, 1));
   }
-  if (dhx_beta) EG_LAUNCH(add_kernel, ew_grid(n), 256, 0, st, dhx, h->dh, n, dhx);
+  if (dhx_beta) EG_LAUNCH_PDL(add_kernel, ew_grid(n), 256, 0, st, dhx, h->dh, n, dhx);
   else EG_CUDA_CHECK(cudaMemcpyAsync(dhx, h->dh, n * 4, cudaMemcpyDeviceToDevice, st));
   return EG_OK;
 }
@@ -481,24 +485,24 @@ static int gru2_backward(EgPolicy* h, cudaStream_t st, const float* x, int ld_en
   const float* P = h->P;
   float* G = h->G;
   // step 2
-  EG_LAUNCH(gru_bwd_kernel, ew_grid((int64_t)B * H), 256, 0, st, dh2, ld_dh2, r[1], z[1], n[1], g[1], h1, B, H, h->dgi,
+  EG_LAUNCH_PDL(gru_bwd_kernel, ew_grid((int64_t)B * H), 256, 0, st, dh2, ld_dh2, r[1], z[1], n[1], g[1], h1, B, H, h->dgi,
             h->dgh, h->dh1);
   GemmArgs w1{h->dgi, H3, 1, x + ld_frame, ld_env, G + wih, in_dim, nullptr, nullptr, 0, H3, in_dim, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(w1, true, false, st));
-  EG_LAUNCH(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgi, H3, B, H3, G + bih);
+  EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgi, H3, B, H3, G + bih);
   GemmArgs w2{h->dgh, H3, 1, h1, H, G + whh, H, nullptr, nullptr, 0, H3, H, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(w2, true, false, st));
-  EG_LAUNCH(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + bhh);
+  EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + bhh);
   // dh1 = dh2 * z + dgh W_hh
   GemmArgs x2{h->dgh, H3, 1, P + whh, H, h->dh1, H, nullptr, nullptr, 0, B, H, H3, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(x2, false, false, st));
   // step 1 (h0 = 0: no W_hh gradient, b_hh still receives dgh)
-  EG_LAUNCH(gru_bwd_kernel, ew_grid((int64_t)B * H), 256, 0, st, h->dh1, H, r[0], z[0], n[0], g[0], nullptr, B, H,
+  EG_LAUNCH_PDL(gru_bwd_kernel, ew_grid((int64_t)B * H), 256, 0, st, h->dh1, H, r[0], z[0], n[0], g[0], nullptr, B, H,
             h->dgi, h->dgh, nullptr);
   GemmArgs w3{h->dgi, H3, 1, x, ld_env, G + wih, in_dim, nullptr, nullptr, 0, H3, in_dim, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(w3, true, false, st));
-  EG_LAUNCH(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgi, H3, B, H3, G + bih);
-  EG_LAUNCH(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + bhh);
+  EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgi, H3, B, H3, G + bih);
+  EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + bhh);
   return EG_OK;
 }
 
@@ -601,6 +605,7 @@ static CvaeLayout make_cvae_layout(const EgCvaeDims& d) {
 
 __global__ void __launch_bounds__(256)
 tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n, float* __restrict__ dx) {
+  eg_pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dx[i] = dy[i] * (1.0f - y[i] * y[i]);
 }
@@ -805,7 +810,7 @@ int lin_bwd(EgCvae* h, cudaStream_t st, const float* dY, int ld_dy, const float*
             int in, int out, int ldw, float* dX, int ld_dx, int dx_beta) {
   GemmArgs gw{dY, ld_dy, 1, X, ldx, h->G + w, ldw, nullptr, nullptr, 0, out, in, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(gw, true, false, st));
-  if (b >= 0) EG_LAUNCH(colsum_kernel, (out + 31) / 32, 256, 0, st, dY, ld_dy, B, out, h->G + b);
+  if (b >= 0) EG_LAUNCH_PDL(colsum_kernel, (out + 31) / 32, 256, 0, st, dY, ld_dy, B, out, h->G + b);
   if (dX) {
     GemmArgs gx{dY, ld_dy, 1, h->P + w, ldw, dX, ld_dx, nullptr, nullptr, 0, B, in, out, ACT_NONE, 0.f, dx_beta, 1.0f};
     EG_TRY(launch_gemm(gx, false, false, st));
@@ -882,32 +887,32 @@ extern "C" int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, 
     const float* yp = i ? Y_rec + (int64_t)(i - 1) * BD : X + BD;
     const float* hp = i ? h->dh_[i - 1] : h->h0;
     // dy_i = dL/dY_rec[i] + carried gradient w.r.t. y_p of step i+1
-    EG_LAUNCH(add_kernel, ew_grid(BD), 256, 0, st, h->dY + (int64_t)i * BD, h->dy, BD, h->dy);
+    EG_LAUNCH_PDL(add_kernel, ew_grid(BD), 256, 0, st, h->dY + (int64_t)i * BD, h->dy, BD, h->dy);
     // y_i = d_out(f2) + y_p
     EG_TRY(lin_bwd(h, st, h->dy, D, h->f2[i], H, B, L.d_out.w, L.d_out.b, H, D, H, h->db, H, 0));
-    EG_LAUNCH(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->db, h->f2[i], nBH, h->db);
+    EG_LAUNCH_PDL(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->db, h->f2[i], nBH, h->db);
     EG_TRY(lin_bwd(h, st, h->db, H, h->f1[i], Hm, B, L.d_mlp1.w, L.d_mlp1.b, Hm, H, Hm, h->da, Hm, 0));
-    EG_LAUNCH(tanh_bwd_kernel, ew_grid((int64_t)B * Hm), 256, 0, st, h->da, h->f1[i], (int64_t)B * Hm, h->da);
+    EG_LAUNCH_PDL(tanh_bwd_kernel, ew_grid((int64_t)B * Hm), 256, 0, st, h->da, h->f1[i], (int64_t)B * Hm, h->da);
     EG_TRY(lin_bwd(h, st, h->da, Hm, h->dh_[i], H, B, L.d_mlp0.w, L.d_mlp0.b, H, Hm, H, h->dh, H, 1));   // dh_i += ...
     // GRUCell backward
-    EG_LAUNCH(gru_bwd_kernel, ew_grid(nBH), 256, 0, st, h->dh, H, h->dr_[i], h->dz_[i], h->dn_[i], h->dg_[i], hp, B, H,
+    EG_LAUNCH_PDL(gru_bwd_kernel, ew_grid(nBH), 256, 0, st, h->dh, H, h->dr_[i], h->dz_[i], h->dn_[i], h->dg_[i], hp, B, H,
               h->dgi, h->dgh, h->dhp);
     EG_TRY(lin_bwd(h, st, h->dgh, H3, hp, H, B, L.d_whh, L.d_bhh, H, H3, H, h->dhp, H, 1));              // dh_{i-1}
     // gi = c + y_p Wy^T : weight slice of d_rnn.weight_ih (columns H+Z..), bias lives in c
     EG_TRY(lin_bwd(h, st, h->dgi, H3, yp, D, B, L.d_wih + H + Z, -1, D, H3, Kin, h->db, D, 0));           // d y_p (GRU path)
-    EG_LAUNCH(add_kernel, ew_grid((int64_t)B * H3), 256, 0, st, h->dc, h->dgi, (int64_t)B * H3, h->dc);
+    EG_LAUNCH_PDL(add_kernel, ew_grid((int64_t)B * H3), 256, 0, st, h->dc, h->dgi, (int64_t)B * H3, h->dc);
     // carry: dy_{i-1} = dy_i (residual) + dgi Wy
-    EG_LAUNCH(add_kernel, ew_grid(BD), 256, 0, st, h->dy, h->db, BD, h->dy);
+    EG_LAUNCH_PDL(add_kernel, ew_grid(BD), 256, 0, st, h->dy, h->db, BD, h->dy);
     std::swap(h->dh, h->dhp);
   }
   // h->dh now holds dL/dh0 ; c = [hx,z] W_ih[:, :H+Z]^T + b_ih
   EG_TRY(lin_bwd(h, st, h->dc, H3, h->hz, H + Z, B, L.d_wih, L.d_bih, H + Z, H3, Kin, h->dhz, H + Z, 0));
   // drnn_mlp backward: h0 = tanh(W2 tanh(W1 tanh(W0 hx)))
-  EG_LAUNCH(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->dh, h->h0, nBH, h->dh);
+  EG_LAUNCH_PDL(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->dh, h->h0, nBH, h->dh);
   EG_TRY(lin_bwd(h, st, h->dh, H, h->dr_a1, H, B, L.dr2.w, L.dr2.b, H, H, H, h->db, H, 0));
-  EG_LAUNCH(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->db, h->dr_a1, nBH, h->db);
+  EG_LAUNCH_PDL(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->db, h->dr_a1, nBH, h->db);
   EG_TRY(lin_bwd(h, st, h->db, H, h->dr_a0, Hm, B, L.dr1.w, L.dr1.b, Hm, H, Hm, h->da, Hm, 0));
-  EG_LAUNCH(tanh_bwd_kernel, ew_grid((int64_t)B * Hm), 256, 0, st, h->da, h->dr_a0, (int64_t)B * Hm, h->da);
+  EG_LAUNCH_PDL(tanh_bwd_kernel, ew_grid((int64_t)B * Hm), 256, 0, st, h->da, h->dr_a0, (int64_t)B * Hm, h->da);
   EG_TRY(lin_bwd(h, st, h->da, Hm, hx, H, B, L.dr0.w, L.dr0.b, H, Hm, H, h->dhx, H, 0));                 // dhx (1)
   // ---------------- backward: latent + encoder ----------------
   // dz = dhz[:, H:], dhx (2) = dhz[:, :H]; gather dz contiguous through a strided copy
@@ -916,26 +921,26 @@ extern "C" int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, 
             w_kld, robust_kld, loss_scale, h->dmu, h->dlv, stats);
   EG_TRY(lin_bwd(h, st, h->dmu, Z, h->ea2, H, B, L.e_mu.w, L.e_mu.b, H, Z, H, h->db, H, 0));
   EG_TRY(lin_bwd(h, st, h->dlv, Z, h->ea2, H, B, L.e_lv.w, L.e_lv.b, H, Z, H, h->db, H, 1));
-  EG_LAUNCH(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->db, h->ea2, nBH, h->db);
+  EG_LAUNCH_PDL(tanh_bwd_kernel, ew_grid(nBH), 256, 0, st, h->db, h->ea2, nBH, h->db);
   EG_TRY(lin_bwd(h, st, h->db, H, h->ea1, Hm, B, L.e_mlp1.w, L.e_mlp1.b, Hm, H, Hm, h->da, Hm, 0));
-  EG_LAUNCH(tanh_bwd_kernel, ew_grid((int64_t)B * Hm), 256, 0, st, h->da, h->ea1, (int64_t)B * Hm, h->da);
+  EG_LAUNCH_PDL(tanh_bwd_kernel, ew_grid((int64_t)B * Hm), 256, 0, st, h->da, h->ea1, (int64_t)B * Hm, h->da);
   EG_TRY(lin_bwd(h, st, h->da, Hm, h->hcat, 2 * H, B, L.e_mlp0.w, L.e_mlp0.b, 2 * H, Hm, 2 * H, h->dhcat, 2 * H, 0));
   // dhx total = drnn path + c path + encoder path
   // dhx += dhz[:, :H] + dhcat[:, :H]  (strided adds via 2-D copies into scratch then add)
   EG_CUDA_CHECK(cudaMemcpy2DAsync(h->db, H * 4, h->dhz, (H + Z) * 4, H * 4, B, cudaMemcpyDeviceToDevice, st));
-  EG_LAUNCH(add_kernel, ew_grid(nBH), 256, 0, st, h->dhx, h->db, nBH, h->dhx);
+  EG_LAUNCH_PDL(add_kernel, ew_grid(nBH), 256, 0, st, h->dhx, h->db, nBH, h->dhx);
   EG_CUDA_CHECK(cudaMemcpy2DAsync(h->db, H * 4, h->dhcat, 2 * H * 4, H * 4, B, cudaMemcpyDeviceToDevice, st));
-  EG_LAUNCH(add_kernel, ew_grid(nBH), 256, 0, st, h->dhx, h->db, nBH, h->dhx);
+  EG_LAUNCH_PDL(add_kernel, ew_grid(nBH), 256, 0, st, h->dhx, h->db, nBH, h->dhx);
   // x_enc BPTT (2 steps)
   {
     float* dcur = h->dhx;
     for (int t = 1; t >= 0; --t) {
       const float* hp = t ? h->xh[t - 1] : nullptr;
-      EG_LAUNCH(gru_bwd_kernel, ew_grid(nBH), 256, 0, st, dcur, H, h->xr[t], h->xz[t], h->xn[t], h->xg[t], hp, B, H, h->dgi,
+      EG_LAUNCH_PDL(gru_bwd_kernel, ew_grid(nBH), 256, 0, st, dcur, H, h->xr[t], h->xz[t], h->xn[t], h->xg[t], hp, B, H, h->dgi,
                 h->dgh, h->dhp);
       EG_TRY(lin_bwd(h, st, h->dgi, H3, X + t * BD, D, B, L.x_wih, L.x_bih, D, H3, D, nullptr, 0, 0));
       if (t > 0) EG_TRY(lin_bwd(h, st, h->dgh, H3, hp, H, B, L.x_whh, L.x_bhh, H, H3, H, h->dhp, H, 1));
-      else EG_LAUNCH(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + L.x_bhh);
+      else EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + L.x_bhh);
       dcur = h->dhp;
     }
   }
@@ -943,11 +948,11 @@ extern "C" int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, 
   EG_CUDA_CHECK(cudaMemcpy2DAsync(h->dh, H * 4, h->dhcat + H, 2 * H * 4, H * 4, B, cudaMemcpyDeviceToDevice, st));
   for (int t = T - 1; t >= 0; --t) {
     const float* hp = t ? h->eh[t - 1] : nullptr;
-    EG_LAUNCH(gru_bwd_kernel, ew_grid(nBH), 256, 0, st, h->dh, H, h->er[t], h->ez[t], h->en[t], h->eg_[t], hp, B, H, h->dgi,
+    EG_LAUNCH_PDL(gru_bwd_kernel, ew_grid(nBH), 256, 0, st, h->dh, H, h->er[t], h->ez[t], h->en[t], h->eg_[t], hp, B, H, h->dgi,
               h->dgh, h->dhp);
     EG_TRY(lin_bwd(h, st, h->dgi, H3, Y + t * BD, D, B, L.e_wih, L.e_bih, D, H3, D, nullptr, 0, 0));
     if (t > 0) EG_TRY(lin_bwd(h, st, h->dgh, H3, hp, H, B, L.e_whh, L.e_bhh, H, H3, H, h->dhp, H, 1));
-    else EG_LAUNCH(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + L.e_bhh);
+    else EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + L.e_bhh);
     std::swap(h->dh, h->dhp);
   }
   return EG_OK;
