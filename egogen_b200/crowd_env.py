@@ -225,14 +225,17 @@ class CrowdVectorEnv:
         return self.observation(), {}
 
     # ---- sync-free restart of finished episodes ------------------------------------------------------------
+    _POOL_FIELDS = ("state", "seed", "R0", "T0", "betas", "dist", "steps", "goal", "ego", "obs_dist", "obs_time")
+
     def _validated_candidates(self, n: int, pool: int = 2048):
-        """n start candidates that eg_env_reset is known to accept: the sampler's candidates are run through the reset
-        pipeline once on scratch slots (same accept test as reset(), :379-380 / crowd_env_2f_box.py reset) and only the
-        accepted ones are kept, so reset_masked() never has to read an accept mask back. One host sync per `pool`
-        candidates instead of one per vector step."""
+        """n start candidates that eg_env_reset is known to accept, TOGETHER WITH the initial env state the reset
+        computed for them: the sampler's candidates are run through the reset pipeline once on scratch slots (same accept
+        test as reset(), crowd_env_2f.py:379-380 / the box env's map test; same canonicalisation, features and
+        ego-sensing) and the accepted rows of every state buffer are kept. Restarting an episode is then a masked copy -
+        no SMPL-X pass, no accept mask to read back. One host sync per `pool` candidates instead of one per vector step."""
         dev = self.dev
         vp = getattr(self, "_vpool", None)
-        if vp is None or self._vptr + n > vp["goals"].shape[0]:
+        if vp is None or self._vptr + n > vp["goal"].shape[0]:
             if getattr(self, "_scratch", None) is None:
                 f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
                 P = pool
@@ -253,28 +256,28 @@ class CrowdVectorEnv:
                                                        _lib.ptr(s["world_params"].contiguous()), _lib.ptr(s["goals"].contiguous()),
                                                        _lib.ptr(s["betas"].contiguous()), _lib.ptr(accept), _lib.stream_ptr(dev)))
                 ok = accept != 0                                         # the one host sync of the refill
-                parts.append({k: s[k][ok].clone() for k in ("world_params", "goals", "betas")})
+                part = {k: self._scratch[k][ok].clone() for k in self._POOL_FIELDS}
+                part["world_params"] = s["world_params"][ok].clone()
+                parts.append(part)
                 have += int(ok.sum())
-            self._vpool = {k: torch.cat([p_[k] for p_ in parts]) for k in ("world_params", "goals", "betas")}
+            self._vpool = {k: torch.cat([p_[k] for p_ in parts]) for k in parts[0]}
             self._vptr = 0
         a, b = self._vptr, self._vptr + n
         self._vptr = b
-        return {k: v[a:b] for k, v in self._vpool.items()}
+        out = {k: v[a:b] for k, v in self._vpool.items()}
+        out["goals"] = out["goal"]
+        return out
 
     def reset_masked(self, mask: torch.Tensor):
-        """Restart the envs whose mask entry is non-zero (device uint8 [E], e.g. the `terminated` buffer) without any
-        host synchronisation: every slot gets a pre-validated candidate, eg_env_reset_masked commits it where asked."""
-        dev = self.dev
+        """Restart the envs whose mask entry is non-zero (device uint8 / bool [E], e.g. the `terminated` buffer) without
+        any host synchronisation: slot e takes the pre-computed initial state of the next pre-validated candidate e."""
         s = self._validated_candidates(self.E)
-        if getattr(self, "_accept_all", None) is None:
-            self._accept_all = torch.zeros(self.E, dtype=torch.int32, device=dev)
-        m = mask if mask.dtype == torch.uint8 else mask.to(torch.uint8)
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().eg_env_reset_masked(self._h, C.byref(self._cbuf), _lib.ptr(m.contiguous()), self.E,
-                                                      _lib.ptr(s["world_params"].contiguous()), _lib.ptr(s["goals"].contiguous()),
-                                                      _lib.ptr(s["betas"].contiguous()), _lib.ptr(self._accept_all),
-                                                      _lib.stream_ptr(dev)))
-        return self._accept_all
+        m = mask.bool()
+        for k in self._POOL_FIELDS:
+            dst = self.buf[k]
+            mk = m.view(-1, *([1] * (dst.dim() - 1)))
+            dst.copy_(torch.where(mk, s[k], dst))
+        return m
 
     def reset_from(self, env_ids, world_params, goals, betas):
         """Deterministic reset from explicit candidates (tests / parity); returns the accept mask."""

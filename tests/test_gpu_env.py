@@ -357,61 +357,39 @@ def test_sync_free_collect_restarts_finished_envs(dev):
 
 
 def test_masked_reset_edge_cases(dev, world):
-    """eg_env_reset_masked: an all-zero mask changes nothing, an all-one mask restarts every slot, a null mask is an
-    error; candidate e always lands in slot e."""
+    """reset_masked (masked copy of pre-computed initial states) and the C entry point eg_env_reset_masked: an all-zero
+    mask changes nothing, an all-one mask restarts every slot with candidate e in slot e, the pooled initial state is
+    what a direct reset of the same candidate produces, a null mask is an error."""
     import ctypes as C
     from egogen_b200 import _lib
     venv, E = world["venv"], world["E"]
     venv.reset()
     before = {k: venv.buf[k].clone() for k in ("state", "seed", "R0", "T0", "steps", "goal")}
-    acc = venv.reset_masked(torch.zeros(E, dtype=torch.uint8, device=dev)).clone()
-    assert int(acc.sum()) == 0
+    venv.reset_masked(torch.zeros(E, dtype=torch.uint8, device=dev))
     for k, v in before.items():
         assert torch.equal(venv.buf[k], v), k
     venv.step(torch.zeros(E, 128, device=dev))
     assert bool((venv.buf["steps"] == 1).all())
-    acc = venv.reset_masked(torch.ones(E, dtype=torch.uint8, device=dev)).clone()
-    assert int(acc.sum()) == E and bool((venv.buf["steps"] == 0).all())
-    used = venv._vpool["goals"][venv._vptr - E:venv._vptr]
-    assert torch.equal(venv.buf["goal"], used)                         # candidate e -> slot e
-    rc = _lib.lib().eg_env_reset_masked(venv._h, C.byref(venv._cbuf), None, E, _lib.ptr(venv._vpool["world_params"]),
-                                        _lib.ptr(venv._vpool["goals"]), _lib.ptr(venv._vpool["betas"]), _lib.ptr(acc),
-                                        _lib.stream_ptr(dev))
+    venv.reset_masked(torch.ones(E, dtype=torch.uint8, device=dev))
+    assert bool((venv.buf["steps"] == 0).all())
+    lo = venv._vptr - E
+    pooled = {k: venv._vpool[k][lo:lo + E].clone() for k in ("goal", "world_params", "betas", "state", "seed", "R0", "T0", "ego", "dist")}
+    assert torch.equal(venv.buf["goal"], pooled["goal"])                # candidate e -> slot e
+    after = {k: venv.buf[k].clone() for k in ("state", "seed", "R0", "T0", "ego", "dist")}
+    # a direct reset of the same candidates reproduces the pooled state bit for bit
+    acc = venv.reset_from(torch.arange(E), pooled["world_params"], pooled["goal"], pooled["betas"])
+    assert bool((acc != 0).all())
+    for k, v in after.items():
+        assert torch.equal(venv.buf[k], v), k
+    # C entry point: masked commit through the full reset pipeline gives the same state; null mask rejected
+    venv.step(torch.zeros(E, 128, device=dev))
+    mask = torch.zeros(E, dtype=torch.uint8, device=dev); mask[::2] = 1
+    acc32 = torch.zeros(E, dtype=torch.int32, device=dev)
+    wp, gl, be = pooled["world_params"].contiguous(), pooled["goal"].contiguous(), pooled["betas"].contiguous()
+    _lib.check(_lib.lib().eg_env_reset_masked(venv._h, C.byref(venv._cbuf), _lib.ptr(mask), E, _lib.ptr(wp), _lib.ptr(gl),
+                                              _lib.ptr(be), _lib.ptr(acc32), _lib.stream_ptr(dev)))
+    assert torch.equal(acc32.bool(), mask.bool())
+    assert torch.equal(venv.buf["state"][::2], after["state"][::2]) and bool((venv.buf["steps"][1::2] == 1).all())
+    rc = _lib.lib().eg_env_reset_masked(venv._h, C.byref(venv._cbuf), None, E, _lib.ptr(wp), _lib.ptr(gl), _lib.ptr(be),
+                                        _lib.ptr(acc32), _lib.stream_ptr(dev))
     assert rc < 0
-
-
-def test_start_body_sampler_matches_oracle(dev, world, smplx_model):
-    """f-3: CrowdMotionSampler.gen_init_bodies (batched, CUDA LBS joints) against the per-body oracle of
-    environments.py:1041-1131 on the reference's locomotion seed fixture; then the sampler-dict contract feeds reset."""
-    import os
-    from egogen_b200.scene_sampler import CrowdMotionSampler, axis_angle_to_matrix, batched_to_dicts, sampler_dicts_to_candidates
-    from oracle.sampler import gen_init_body
-    from oracle.smplx_lbs import SMPLXParserOracle
-    d = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "locomotion_seed_00343.npz")))
-    sampler = CrowdMotionSampler(world["lbs"], dev, d, seed=0)
-    parser = SMPLXParserOracle(smplx_model, marker=assets.marker_ids())
-    n = 5
-    g = torch.Generator().manual_seed(4)
-    start = torch.cat([torch.rand(n, 2, generator=g) * 6 - 3, torch.zeros(n, 1)], 1)
-    target = torch.cat([torch.rand(n, 2, generator=g) * 6 - 3, torch.zeros(n, 1)], 1)
-    frames = [0, 3, 7, 11, 18]
-    ms = (torch.as_tensor(d["betas"]).repeat(n, 1), torch.as_tensor(np.stack([d["poses"][f:f + 2, 3:66] for f in frames])),
-          torch.as_tensor(np.stack([d["poses"][f:f + 2, :3] for f in frames])), torch.as_tensor(np.stack([d["trans"][f:f + 2] for f in frames])))
-    yaw = torch.tensor([0.0, 0.4, -0.9, 1.2, -0.1])
-    b = sampler.gen_init_bodies(start, target, motion_seed=ms, yaw=yaw)
-    for i in range(n):
-        r = gen_init_body(parser, start[i].numpy(), target[i].numpy(), d["betas"], ms[1][i].numpy(), ms[2][i].numpy(),
-                          ms[3][i].numpy(), float(yaw[i]))
-        assert torch.allclose(b["transl"][i].cpu(), r["transl"], atol=2e-5), (b["transl"][i].cpu() - r["transl"]).abs().max()
-        assert torch.allclose(axis_angle_to_matrix(b["global_orient"][i]).cpu(), r["global_orient_matrix"], atol=2e-5)
-        assert torch.allclose(b["wpath"][i].cpu(), r["wpath"], atol=2e-5)
-    # the dict contract: reference-format dicts -> reset candidates -> a running env
-    dicts = batched_to_dicts(b)
-    assert set(dicts[0]) >= {"gender", "motion_seed", "betas", "wpath", "scene_path", "navmesh", "navmesh_path", "floor_height"}
-    assert dicts[0]["motion_seed"]["betas"].shape == (2, 10) and dicts[0]["motion_seed"]["transl"].shape == (2, 3)
-    wp, goals, betas = sampler_dicts_to_candidates(dicts, dev)
-    assert wp.shape == (n, 2, 93) and bool((wp[:, :, 69:] == 0).all())
-    assert torch.allclose(goals.cpu(), b["wpath"][:, 1].cpu())
-    one = sampler.next_body((start[0].numpy(), target[0].numpy()), fixed_seed=True, num_agents=1)
-    four = sampler.next_body([(start[i].numpy(), target[i].numpy()) for i in range(4)], fixed_seed=True, num_agents=4)
-    assert isinstance(one, dict) and len(four) == 4
