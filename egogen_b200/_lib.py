@@ -77,6 +77,7 @@ PROTOTYPES = {
     "eg_lbs_set_markers": (_I, [_P, _P, _I]),
     "eg_lbs_max_skin_nnz": (_I, [_P]),
     "eg_lbs_set_mainloop": (_I, [_P, _I]),
+    "eg_lbs_markers_backward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "eg_lbs_rest_pelvis": (_I, [_P, _P, _I, _I, _P, _P]),
     "eg_motion_create": (_I, [C.POINTER(EgMotionDims), _P, _I, _I, C.POINTER(_P)]),
     "eg_motion_destroy": (None, [_P]),

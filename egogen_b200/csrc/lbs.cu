@@ -746,6 +746,201 @@ __global__ void tc_fold_skip_kernel(const float4* __restrict__ rec, const uint8_
   out[i * 3] = r0; out[i * 3 + 1] = rec[i * 3 + 1]; out[i * 3 + 2] = rec[i * 3 + 2];
 }
 
+// --------------------------------------------------------------------------------------------
+// Backward of the marker positions w.r.t. the body parameters (the loss of the reference's
+// GAMMARegressorTrainOP / ComboTrainOP differentiates through SMPL-X, models_GAMMA_primitive.py:616-631):
+//   markers[n,m] = sum_k w_mk A_jk [p_m; 1] + transl,   p_m = t_m + S_m beta + P_m F(theta),   A_j from the kinematic chain
+// One CTA per body re-derives the forward quantities (rotations, chain, relative transforms) in shared memory, then
+//   dA_j += w g (x) [p;1],  dp = sum_k w_k R(A_jk)^T g,  dF = P^T dp  ->  dR_j (pose blend path),
+//   dG from dA, the chain walked from the leaves to the root,  dR_j -> dtheta_j through smplx's Rodrigues
+//   (angle = |theta + 1e-8|), hand PCA transposed, d transl = sum_m g.
+// betas are data in that loss (no gradient). Accumulation is fp32 with shared-memory atomics.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+lbs_markers_backward_kernel(const float* __restrict__ xb, const float* __restrict__ betas, int betas_div, int N, int J, int S,
+                            int n_levels, const float* __restrict__ hand_l, const float* __restrict__ hand_r,
+                            const float* __restrict__ pose_mean, const float* __restrict__ Jt, const float* __restrict__ Js,
+                            const int32_t* __restrict__ parents, const int32_t* __restrict__ level_joints,
+                            const int32_t* __restrict__ level_start,
+                            const float* __restrict__ basis /*[KPAD][3*n_pad]*/, const float* __restrict__ vt,
+                            const int32_t* __restrict__ skin_idx, const float* __restrict__ skin_w, int n_pad, int nnz,
+                            int n_markers, const float* __restrict__ d_markers, float* __restrict__ d_xb) {
+  const int n = blockIdx.x, t = threadIdx.x, NT = blockDim.x;
+  __shared__ float pose[MAXJ * 3], R[MAXJ][9], Jr[MAXJ][3], G[MAXJ][12], shape[32];
+  __shared__ float dA[MAXJ][12], dG[MAXJ][12], dR[MAXJ][9], dth[MAXJ * 3], dtr[3];
+  __shared__ float feat[KPAD], dF[KPAD];
+  extern __shared__ float dyn[];                 // dp [n_markers][3]
+  const float* x = xb + (int64_t)n * EG_XB_DIM;
+  const float* be = betas + (int64_t)(n / betas_div) * 10;
+  const int npose = (J - 1) * 9;
+  // ---- forward re-derivation (same arithmetic as lbs_pose_prep_kernel) ----
+  for (int i = t; i < J * 3; i += NT) {
+    float v = 0.0f;
+    if (i < 66) v = x[3 + i];
+    else if (i >= 75 && i < 120) { for (int k = 0; k < 12; ++k) v += x[69 + k] * __ldg(hand_l + k * 45 + (i - 75)); }
+    else if (i >= 120 && i < 165) { for (int k = 0; k < 12; ++k) v += x[81 + k] * __ldg(hand_r + k * 45 + (i - 120)); }
+    pose[i] = v + __ldg(pose_mean + i);
+  }
+  if (t < 32) shape[t] = (t < 10) ? be[t] : 0.0f;
+  for (int i = t; i < MAXJ * 12; i += NT) { (&dA[0][0])[i] = 0.0f; (&dG[0][0])[i] = 0.0f; }
+  for (int i = t; i < MAXJ * 9; i += NT) (&dR[0][0])[i] = 0.0f;
+  if (t < 3) dtr[t] = 0.0f;
+  __syncthreads();
+  if (t < J) {
+    const float rx = pose[3 * t], ry = pose[3 * t + 1], rz = pose[3 * t + 2];
+    const float ax = rx + 1e-8f, ay = ry + 1e-8f, az = rz + 1e-8f;
+    const float angle = sqrtf(ax * ax + ay * ay + az * az);
+    const float dx = rx / angle, dy = ry / angle, dz = rz / angle;
+    const float sn = sinf(angle), cs = cosf(angle), omc = 1.0f - cs;
+    const float K[9] = {0.f, -dz, dy, dz, 0.f, -dx, -dy, dx, 0.f};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        float kk = 0.f;
+        for (int m = 0; m < 3; ++m) kk += K[a * 3 + m] * K[m * 3 + b];
+        R[t][a * 3 + b] = (a == b ? 1.0f : 0.0f) + sn * K[a * 3 + b] + omc * kk;
+      }
+    for (int c = 0; c < 3; ++c) {
+      float v = __ldg(Jt + t * 3 + c);
+      for (int k = 0; k < S; ++k) v += __ldg(Js + (t * 3 + c) * S + k) * shape[k];
+      Jr[t][c] = v;
+    }
+  }
+  __syncthreads();
+  for (int k = t; k < KPAD; k += NT) {
+    float v = 0.0f;
+    if (k < npose) { const int j = 1 + k / 9, e = k % 9; v = R[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f); }
+    else if (k < npose + S) v = shape[k - npose];
+    feat[k] = v;
+  }
+  for (int lv = 0; lv < n_levels; ++lv) {
+    const int beg = __ldg(level_start + lv), end = __ldg(level_start + lv + 1);
+    for (int q = beg + t; q < end; q += NT) {
+      const int j = __ldg(level_joints + q), p = __ldg(parents + j);
+      if (p < 0) {
+        for (int a = 0; a < 3; ++a) { G[j][a * 4] = R[j][a * 3]; G[j][a * 4 + 1] = R[j][a * 3 + 1]; G[j][a * 4 + 2] = R[j][a * 3 + 2]; G[j][a * 4 + 3] = Jr[j][a]; }
+      } else {
+        const float r0 = Jr[j][0] - Jr[p][0], r1 = Jr[j][1] - Jr[p][1], r2 = Jr[j][2] - Jr[p][2];
+        for (int a = 0; a < 3; ++a) {
+          const float g0 = G[p][a * 4], g1 = G[p][a * 4 + 1], g2 = G[p][a * 4 + 2], g3 = G[p][a * 4 + 3];
+          for (int b = 0; b < 3; ++b) G[j][a * 4 + b] = g0 * R[j][b] + g1 * R[j][3 + b] + g2 * R[j][6 + b];
+          G[j][a * 4 + 3] = g0 * r0 + g1 * r1 + g2 * r2 + g3;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- markers: dA, dp ----
+  const int64_t brow = (int64_t)n_pad * 3;
+  for (int m = t; m < n_markers; m += NT) {
+    float p[3];
+    for (int c = 0; c < 3; ++c) {
+      float v = vt[m * 3 + c];
+      for (int k = 0; k < npose + S; ++k) v += basis[k * brow + m * 3 + c] * feat[k];
+      p[c] = v;
+    }
+    const float* g = d_markers + ((int64_t)n * n_markers + m) * 3;
+    const float g0 = g[0], g1 = g[1], g2 = g[2];
+    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+    for (int k = 0; k < nnz; ++k) {
+      const float w = skin_w[k * n_pad + m];
+      if (w == 0.0f) continue;
+      const int j = skin_idx[k * n_pad + m];
+      const float gv[3] = {w * g0, w * g1, w * g2};
+      for (int a = 0; a < 3; ++a) {
+        atomicAdd(&dA[j][a * 4 + 0], gv[a] * p[0]); atomicAdd(&dA[j][a * 4 + 1], gv[a] * p[1]);
+        atomicAdd(&dA[j][a * 4 + 2], gv[a] * p[2]); atomicAdd(&dA[j][a * 4 + 3], gv[a]);
+      }
+      // A_j rotation part = G_j rotation part
+      dp0 += G[j][0] * gv[0] + G[j][4] * gv[1] + G[j][8] * gv[2];
+      dp1 += G[j][1] * gv[0] + G[j][5] * gv[1] + G[j][9] * gv[2];
+      dp2 += G[j][2] * gv[0] + G[j][6] * gv[1] + G[j][10] * gv[2];
+    }
+    dyn[m * 3] = dp0; dyn[m * 3 + 1] = dp1; dyn[m * 3 + 2] = dp2;
+    atomicAdd(&dtr[0], g0); atomicAdd(&dtr[1], g1); atomicAdd(&dtr[2], g2);
+  }
+  __syncthreads();
+  // ---- pose blend path: dF[k] = sum_m P[k][m] . dp[m]  ->  dR_j ----
+  for (int k = t; k < npose; k += NT) {
+    float v = 0.0f;
+    for (int m = 0; m < n_markers; ++m)
+      v += basis[k * brow + m * 3] * dyn[m * 3] + basis[k * brow + m * 3 + 1] * dyn[m * 3 + 1] + basis[k * brow + m * 3 + 2] * dyn[m * 3 + 2];
+    dF[k] = v;
+  }
+  __syncthreads();
+  for (int k = t; k < npose; k += NT) dR[1 + k / 9][k % 9] = dF[k];
+  // ---- dA -> dG:  A_R = G_R,  A_t = G_t - G_R J ----
+  if (t < J) {
+    for (int a = 0; a < 3; ++a) {
+      const float dat = dA[t][a * 4 + 3];
+      for (int b = 0; b < 3; ++b) dG[t][a * 4 + b] = dA[t][a * 4 + b] - dat * Jr[t][b];
+      dG[t][a * 4 + 3] = dat;
+    }
+  }
+  __syncthreads();
+  // ---- chain, leaves to root:  G_j,R = G_p,R R_j,  G_j,t = G_p,R r_j + G_p,t ----
+  for (int lv = n_levels - 1; lv >= 0; --lv) {
+    const int beg = __ldg(level_start + lv), end = __ldg(level_start + lv + 1);
+    for (int q = beg + t; q < end; q += NT) {
+      const int j = __ldg(level_joints + q), p = __ldg(parents + j);
+      if (p < 0) {
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) atomicAdd(&dR[j][a * 3 + b], dG[j][a * 4 + b]);
+      } else {
+        const float r[3] = {Jr[j][0] - Jr[p][0], Jr[j][1] - Jr[p][1], Jr[j][2] - Jr[p][2]};
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) {
+            // dR_j[a][b] += sum_c G_p,R[c][a] dG_j,R[c][b]
+            float v = 0.0f;
+            for (int c = 0; c < 3; ++c) v += G[p][c * 4 + a] * dG[j][c * 4 + b];
+            atomicAdd(&dR[j][a * 3 + b], v);
+            // dG_p,R[a][b] += sum_c dG_j,R[a][c] R_j[b][c] + dG_j,t[a] r[b]
+            float u = dG[j][a * 4 + 3] * r[b];
+            for (int c = 0; c < 3; ++c) u += dG[j][a * 4 + c] * R[j][b * 3 + c];
+            atomicAdd(&dG[p][a * 4 + b], u);
+          }
+        for (int a = 0; a < 3; ++a) atomicAdd(&dG[p][a * 4 + 3], dG[j][a * 4 + 3]);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- Rodrigues backward (smplx batch_rodrigues: angle = |theta + 1e-8|, dir = theta / angle) ----
+  if (t < J) {
+    const float th[3] = {pose[3 * t], pose[3 * t + 1], pose[3 * t + 2]};
+    const float av[3] = {th[0] + 1e-8f, th[1] + 1e-8f, th[2] + 1e-8f};
+    const float angle = sqrtf(av[0] * av[0] + av[1] * av[1] + av[2] * av[2]);
+    const float d[3] = {th[0] / angle, th[1] / angle, th[2] / angle};
+    const float sn = sinf(angle), cs = cosf(angle), omc = 1.0f - cs;
+    const float K[9] = {0.f, -d[2], d[1], d[2], 0.f, -d[0], -d[1], d[0], 0.f};
+    float K2[9], dK[9];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { float v = 0.f; for (int m = 0; m < 3; ++m) v += K[a * 3 + m] * K[m * 3 + b]; K2[a * 3 + b] = v; }
+    float dLs = 0.f, dLc = 0.f;
+    for (int e = 0; e < 9; ++e) { dLs += dR[t][e] * K[e]; dLc -= dR[t][e] * K2[e]; }
+    // dL/dK = s dR + (1 - c) (dR K^T + K^T dR)
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        float v = sn * dR[t][a * 3 + b];
+        for (int m = 0; m < 3; ++m) v += omc * (dR[t][a * 3 + m] * K[b * 3 + m] + K[m * 3 + a] * dR[t][m * 3 + b]);
+        dK[a * 3 + b] = v;
+      }
+    const float dd[3] = {dK[7] - dK[5], dK[2] - dK[6], dK[3] - dK[1]};
+    const float dang = dLs * cs - dLc * sn;
+    const float inv = 1.0f / angle, inv3 = inv * inv * inv;
+    const float dth_dot = dd[0] * th[0] + dd[1] * th[1] + dd[2] * th[2];
+    for (int i = 0; i < 3; ++i) dth[3 * t + i] = dang * av[i] * inv + dd[i] * inv - dth_dot * av[i] * inv3;
+  }
+  __syncthreads();
+  // ---- d xb: transl, global_orient + body_pose, hand PCA (jaw / eyes are constants of the parser) ----
+  float* out = d_xb + (int64_t)n * EG_XB_DIM;
+  if (t < 3) out[t] = dtr[t];
+  for (int i = t; i < 66; i += NT) out[3 + i] = dth[i];
+  for (int k = t; k < 24; k += NT) {
+    const float* comp = k < 12 ? hand_l + k * 45 : hand_r + (k - 12) * 45;
+    const int base = k < 12 ? 75 : 120;
+    float v = 0.0f;
+    for (int c = 0; c < 45; ++c) v += dth[base + c] * __ldg(comp + c);
+    out[69 + k] = v;
+  }
+}
+
 // joints [N,127,3] = posed joints ++ vertex joints ++ landmarks (+transl); markers [N,M,3]
 __global__ void __launch_bounds__(128)
 lbs_finish_kernel(const float* __restrict__ Jp, const float* __restrict__ cverts,
@@ -1281,6 +1476,21 @@ extern "C" int eg_lbs_rest_pelvis(EgLbs* h, const float* betas, int betas_rows, 
   EG_REQUIRE(betas_rows >= 1 && N % betas_rows == 0, "betas_rows must divide N");
   EG_LAUNCH(rest_pelvis_kernel, (N * 3 + 127) / 128, 128, 0, as_stream(stream), betas, N / betas_rows, N, h->S,
             h->Jt, h->Js, out);
+  return EG_OK;
+}
+
+extern "C" int eg_lbs_markers_backward(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
+                                       const float* d_markers, float* d_xb, void* stream) {
+  EG_REQUIRE(h && xb && betas && d_markers && d_xb && N >= 0, "bad arguments");
+  if (N == 0) return EG_OK;
+  EG_REQUIRE(h->n_markers > 0, "no marker set (eg_lbs_set_markers)");
+  EG_REQUIRE(betas_rows >= 1 && N % betas_rows == 0, "betas_rows must divide N");
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  const VertexSet& s = h->compact;
+  EG_LAUNCH(lbs_markers_backward_kernel, N, 128, (size_t)h->n_markers * 3 * sizeof(float), as_stream(stream), xb, betas,
+            N / betas_rows, N, h->J, h->S, h->n_levels, h->hand_l, h->hand_r, h->pose_mean, h->Jt, h->Js, h->parents,
+            h->level_joints, h->level_start, s.basis, s.vt, s.skin_idx, s.skin_w, s.n_pad, s.nnz, h->n_markers, d_markers,
+            d_xb);
   return EG_OK;
 }
 

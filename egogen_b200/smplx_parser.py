@@ -74,6 +74,21 @@ class LbsModel:
                                                  _lib.stream_ptr(self.device)))
         return verts, joints, markers
 
+    def markers_backward(self, xb, betas, d_markers):
+        """Gradient of the marker output w.r.t. the body parameters: d_xb [N,93] for an upstream d_markers [N,M,3]
+        (the SMPL-X gradient of the reference's regressor / combo training losses, models_GAMMA_primitive.py:616-631)."""
+        xb = _lib.f32c(xb, self.device)
+        betas = _lib.f32c(betas, self.device).reshape(-1, 10)
+        g = _lib.f32c(d_markers, self.device)
+        N = xb.shape[0]
+        if xb.shape[1] != 93 or g.shape != (N, self.n_markers, 3) or betas.shape[0] not in (1, N):
+            raise _lib.EgError("markers_backward: xb [N,93], betas [1 or N,10], d_markers [N,n_markers,3] expected")
+        d_xb = torch.empty(N, 93, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().eg_lbs_markers_backward(self._h, _lib.ptr(xb), _lib.ptr(betas), betas.shape[0], N,
+                                                          _lib.ptr(g), _lib.ptr(d_xb), _lib.stream_ptr(self.device)))
+        return d_xb
+
     def forward_sdf(self, xb, betas, frames_per_env, R0, T0, sdf_dict, skip_mask, want_markers=True):
         """Fused LBS -> world transform -> calc_sdf -> feet skip -> per-body count (crowd_env_2f.py:133-177)."""
         from .sdf import _grid3

@@ -122,6 +122,12 @@ int eg_lbs_set_markers(EgLbs* h, const int32_t* marker_vids_host, int n_markers)
 int eg_lbs_max_skin_nnz(const EgLbs* h);
 /* full-mesh mainloop: 1 (default) = tcgen05/TMEM/TMA TF32 tiles, 0 = fp32 SIMT tiles (debug / comparison) */
 int eg_lbs_set_mainloop(EgLbs* h, int use_tcgen05);
+/* backward of the marker output of eg_lbs_forward w.r.t. the body parameters: d_xb [N,93] = (d markers / d xb)^T
+ * d_markers [N,n_markers,3] (transl, global_orient, body_pose, hand PCA; betas are data). This is the SMPL-X gradient the
+ * reference's regressor / combo training loss needs (bm(...).vertices[:, markers] inside calc_loss,
+ * motion/models/models_GAMMA_primitive.py:616-631). */
+int eg_lbs_markers_backward(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
+                            const float* d_markers, float* d_xb, void* stream);
 /* SMPLXParser.calc_calibrate_offset (baseops.py:494-534): pelvis of the zero-transl / zero-orient body,
  * i.e. the rest position of the root joint J_0(betas). out [N,3]. */
 int eg_lbs_rest_pelvis(EgLbs* h, const float* betas, int betas_rows, int N, float* out, void* stream);

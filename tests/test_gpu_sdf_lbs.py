@@ -191,3 +191,31 @@ def test_fused_counts_at_bench_size(dev, parser):
     assert bool(((counts - c2).abs() <= near).all()), (counts - c2).abs().max()
     assert int((counts > 0).sum()) > E * T // 20, "bodies intersecting the floor / boxes must be present"
     assert int((counts == 0).sum()) > 0
+
+
+def test_markers_backward_matches_autograd(dev, parser, smplx_model):
+    """f-4 building block: eg_lbs_markers_backward (pose blend shapes, kinematic chain, smplx Rodrigues, hand PCA,
+    translation) against torch autograd through the LBS oracle; including the
+    reference's all-zero pose (the Rodrigues 1e-8 quirk keeps the gradient finite there) and ragged betas rows."""
+    from oracle.smplx_lbs import SMPLXParserOracle
+    orc = SMPLXParserOracle(smplx_model, marker=assets.marker_ids())
+    g = torch.Generator().manual_seed(5)
+    for N, scale in [(6, 0.3), (4, 0.0), (3, 1.2)]:
+        xb = torch.randn(N, 93, generator=g) * scale
+        betas = torch.randn(N, 10, generator=g) * 0.7
+        w = torch.randn(N, 67, 3, generator=g)
+        xr = xb.clone().requires_grad_(True)
+        (orc.forward_smplx(betas, "male", xr, "markers") * w).sum().backward()
+        ref = xr.grad
+        got = parser.bm_male.markers_backward(xb.to(dev), betas.to(dev), w.to(dev)).cpu()
+        assert torch.isfinite(got).all()
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-4 * max(ref.abs().max().item(), 1.0), (N, scale, err, ref.abs().max().item())
+    # one shared betas row
+    xb = torch.randn(5, 93, generator=g) * 0.3
+    betas = torch.randn(1, 10, generator=g)
+    w = torch.randn(5, 67, 3, generator=g)
+    xr = xb.clone().requires_grad_(True)
+    (orc.forward_smplx(betas.repeat(5, 1), "male", xr, "markers") * w).sum().backward()
+    got = parser.bm_male.markers_backward(xb.to(dev), betas.to(dev), w.to(dev)).cpu()
+    assert (got - xr.grad).abs().max().item() <= 2e-4 * max(xr.grad.abs().max().item(), 1.0)
