@@ -40,6 +40,10 @@ class EgCvaeDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("in_dim", "h_dim", "z_dim", "mlp_dim")]
 
 
+class EgRegressorDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("in_dim", "h_dim", "n_blocks", "n_recur", "body_dim")]
+
+
 class EgEnvConfig(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("finetuning", C.c_int32), ("pene_terminate_count", C.c_int32),
                 ("feet_marker_idx", C.c_int32 * 6), ("reproj_factor", C.c_float), ("goal_thresh", C.c_float)] + \
@@ -78,6 +82,7 @@ PROTOTYPES = {
     "eg_lbs_max_skin_nnz": (_I, [_P]),
     "eg_lbs_set_mainloop": (_I, [_P, _I]),
     "eg_lbs_markers_backward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "eg_lbs_markers_backward_rot": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "eg_lbs_rest_pelvis": (_I, [_P, _P, _I, _I, _P, _P]),
     "eg_motion_create": (_I, [C.POINTER(EgMotionDims), _P, _I, _I, C.POINTER(_P)]),
     "eg_motion_destroy": (None, [_P]),
@@ -112,6 +117,10 @@ PROTOTYPES = {
     "eg_cvae_create": (_I, [C.POINTER(EgCvaeDims), _P, _P, _I, C.POINTER(_P)]),
     "eg_cvae_destroy": (None, [_P]),
     "eg_cvae_loss_backward": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _I, _F, _P, _P, _P]),
+    "eg_regressor_param_count": (_L, [C.POINTER(EgRegressorDims)]),
+    "eg_regressor_train_create": (_I, [C.POINTER(EgRegressorDims), _P, _P, _P, _I, C.POINTER(_P)]),
+    "eg_regressor_train_destroy": (None, [_P]),
+    "eg_regressor_loss_backward": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
     "eg_adam_step_flat": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
     "eg_new_coordinate": (_I, [_P, _I, _I, _P, _P, _P]),
     "eg_rigid_points": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),

@@ -764,7 +764,8 @@ lbs_markers_backward_kernel(const float* __restrict__ xb, const float* __restric
                             const int32_t* __restrict__ level_start,
                             const float* __restrict__ basis /*[KPAD][3*n_pad]*/, const float* __restrict__ vt,
                             const int32_t* __restrict__ skin_idx, const float* __restrict__ skin_w, int n_pad, int nnz,
-                            int n_markers, const float* __restrict__ d_markers, float* __restrict__ d_xb) {
+                            int n_markers, const float* __restrict__ d_markers, float* __restrict__ d_xb,
+                            float* __restrict__ d_rot /*[N,22,9] dL/dR of the global + body joints, or null*/) {
   const int n = blockIdx.x, t = threadIdx.x, NT = blockDim.x;
   __shared__ float pose[MAXJ * 3], R[MAXJ][9], Jr[MAXJ][3], G[MAXJ][12], shape[32];
   __shared__ float dA[MAXJ][12], dG[MAXJ][12], dR[MAXJ][9], dth[MAXJ * 3], dtr[3];
@@ -902,6 +903,9 @@ lbs_markers_backward_kernel(const float* __restrict__ xb, const float* __restric
     }
     __syncthreads();
   }
+  // rotation-matrix gradient of the 22 regressed joints, for callers whose pose parameterisation is not axis-angle
+  if (d_rot != nullptr)
+    for (int i = t; i < 22 * 9; i += NT) d_rot[(int64_t)n * 198 + i] = dR[i / 9][i % 9];
   // ---- Rodrigues backward (smplx batch_rodrigues: angle = |theta + 1e-8|, dir = theta / angle) ----
   if (t < J) {
     const float th[3] = {pose[3 * t], pose[3 * t + 1], pose[3 * t + 2]};
@@ -1481,6 +1485,11 @@ extern "C" int eg_lbs_rest_pelvis(EgLbs* h, const float* betas, int betas_rows, 
 
 extern "C" int eg_lbs_markers_backward(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
                                        const float* d_markers, float* d_xb, void* stream) {
+  return eg_lbs_markers_backward_rot(h, xb, betas, betas_rows, N, d_markers, d_xb, nullptr, stream);
+}
+
+extern "C" int eg_lbs_markers_backward_rot(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
+                                           const float* d_markers, float* d_xb, float* d_rot, void* stream) {
   EG_REQUIRE(h && xb && betas && d_markers && d_xb && N >= 0, "bad arguments");
   if (N == 0) return EG_OK;
   EG_REQUIRE(h->n_markers > 0, "no marker set (eg_lbs_set_markers)");
@@ -1490,7 +1499,7 @@ extern "C" int eg_lbs_markers_backward(EgLbs* h, const float* xb, const float* b
   EG_LAUNCH(lbs_markers_backward_kernel, N, 128, (size_t)h->n_markers * 3 * sizeof(float), as_stream(stream), xb, betas,
             N / betas_rows, N, h->J, h->S, h->n_levels, h->hand_l, h->hand_r, h->pose_mean, h->Jt, h->Js, h->parents,
             h->level_joints, h->level_start, s.basis, s.vt, s.skin_idx, s.skin_w, s.n_pad, s.nnz, h->n_markers, d_markers,
-            d_xb);
+            d_xb, d_rot);
   return EG_OK;
 }
 

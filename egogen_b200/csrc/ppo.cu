@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "nn.cuh"
+#include "geom.cuh"
 
 namespace eg {
 
@@ -980,5 +981,290 @@ extern "C" int eg_rigid_points(const float* R, const float* T, const float* pts,
   EG_REQUIRE(R && T && pts && out && nt >= 0 && B >= 0 && P >= 0, "bad arguments");
   if ((int64_t)nt * B * P == 0) return EG_OK;
   EG_LAUNCH(rigid_points_kernel, ew_grid((int64_t)nt * B * P), 256, 0, as_stream(stream), R, T, pts, nt, B, P, inverse, out);
+  return EG_OK;
+}
+
+// ============================================================================================
+// Body-regressor training: GAMMARegressorTrainOP.calc_loss + the step of its train loop
+// (motion/models/models_GAMMA_primitive.py:594-633, :664-682) for MoshRegressor (:178-301, use_cont + relu):
+//   xb_0 = 0;  xb_{r+1} = pnet([markers, xb_r, betas]) + xb_r  (n_recur times, ResNetBlock :160-175)
+//   yb = [transl, aa(GramSchmidt(6-D)) x 22, hand PCA]           (_cont2aa :208-219)
+//   loss = L1(markers, SMPL-X markers(yb, betas)) + w * mean(hand PCA^2)
+// The SMPL-X gradient arrives as dL/dR of the 22 regressed joints (eg_lbs_markers_backward_rot) and enters the 6-D
+// parameters through the Gram-Schmidt Jacobian: axis-angle is only an intermediate re-parameterisation of the same
+// rotation (exp(log R) = R, and the Gram-Schmidt image is tangent to SO(3)), so the chain rule through it cancels.
+// ============================================================================================
+namespace eg {
+
+struct RegLayout { int64_t in_w, in_b, blk, out_w, out_b, n_total; };
+static RegLayout make_reg_layout(const EgRegressorDims& d) {
+  RegLayout L;
+  const int64_t H = d.h_dim, K = d.in_dim + d.body_dim + 10;
+  int64_t off = 0;
+  L.in_w = off; off += H * K;
+  L.in_b = off; off += H;
+  L.blk = off; off += (int64_t)d.n_blocks * 2 * (H * H + H);
+  L.out_w = off; off += (int64_t)d.body_dim * H;
+  L.out_b = off; off += d.body_dim;
+  L.n_total = off;
+  return L;
+}
+
+// xin[m] = [markers[m] (D) | xb[m] (BD) | betas[m] (10)]
+__global__ void __launch_bounds__(256)
+reg_concat_kernel(const float* __restrict__ mk, const float* __restrict__ xb, const float* __restrict__ betas, int M, int D,
+                  int BD, float* __restrict__ xin) {
+  const int K = D + BD + 10;
+  const int64_t total = (int64_t)M * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / K), k = (int)(i % K);
+    xin[i] = k < D ? mk[(int64_t)m * D + k] : k < D + BD ? xb[(int64_t)m * BD + (k - D)] : betas[(int64_t)m * 10 + (k - D - BD)];
+  }
+}
+
+// MoshRegressor._cont2aa: same arithmetic as the inference tail (nn.cu regressor_tail_kernel)
+__global__ void __launch_bounds__(128)
+reg_cont2aa_kernel(const float* __restrict__ xb_cont, int M, float* __restrict__ yb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = i / 32, slot = i % 32;
+  if (row >= M) return;
+  const float* x = xb_cont + (int64_t)row * 159;
+  float* y = yb + (int64_t)row * 93;
+  if (slot < 22) {
+    float R[9], aa[3];
+    cont6d_to_rotmat(x + 3 + slot * 6, R);
+    tgm_rotmat_to_aa(R, aa);
+    y[3 + slot * 3 + 0] = aa[0]; y[3 + slot * 3 + 1] = aa[1]; y[3 + slot * 3 + 2] = aa[2];
+  } else if (slot == 22) {
+    y[0] = x[0]; y[1] = x[1]; y[2] = x[2];
+  } else if (slot == 23) {
+    for (int k = 0; k < 24; ++k) y[69 + k] = x[135 + k];
+  }
+}
+
+// F.l1_loss(ref, pred): sums[0] += sum |pred - ref|, d_pred = sign(pred - ref) / n
+__global__ void __launch_bounds__(256)
+reg_l1_kernel(const float* __restrict__ pred, const float* __restrict__ ref, int64_t n, float* __restrict__ d_pred,
+              double* __restrict__ sum) {
+  double s = 0.0;
+  const float inv = 1.0f / (float)n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = pred[i] - ref[i];
+    s += (double)fabsf(d);
+    d_pred[i] = d > 0.0f ? inv : d < 0.0f ? -inv : 0.0f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(sum, s);
+}
+
+// sum of the squared hand-PCA entries xb[:, 135:159]
+__global__ void __launch_bounds__(256)
+reg_hpose_kernel(const float* __restrict__ xb_cont, int M, double* __restrict__ sum) {
+  double s = 0.0;
+  const int64_t total = (int64_t)M * 24;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = xb_cont[(i / 24) * 159 + 135 + (i % 24)];
+    s += (double)(v * v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(sum, s);
+}
+
+__global__ void reg_stats_kernel(const double* __restrict__ sums, int64_t n_marker, int64_t n_hpose, float w_hpose,
+                                 float* __restrict__ stats) {
+  const float lm = (float)(sums[0] / (double)n_marker), lh = (float)(sums[1] / (double)n_hpose);
+  stats[0] = lm + w_hpose * lh; stats[1] = lm; stats[2] = lh;
+}
+
+// d xb_cont from (d yb, dL/dR): transl and hand PCA pass through (+ the hand regulariser), the 22 rotations go through
+// the Gram-Schmidt backward of cont6d_to_rotmat (geom.cuh): a' = a/|a|, u = c - (a'.c) a', b = u/|u|, d = a' x b,
+// R columns (a', b, d); a = x[0,2,4], c = x[1,3,5].
+__global__ void __launch_bounds__(128)
+reg_gs_bwd_kernel(const float* __restrict__ xb_cont, const float* __restrict__ d_rot, const float* __restrict__ d_yb, int M,
+                  float hpose_scale /* w * 2 / (M * 24) */, float* __restrict__ d_xb_cont) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = i / 32, slot = i % 32;
+  if (row >= M) return;
+  const float* x = xb_cont + (int64_t)row * 159;
+  const float* gy = d_yb + (int64_t)row * 93;
+  float* gx = d_xb_cont + (int64_t)row * 159;
+  if (slot < 22) {
+    const float* xs = x + 3 + slot * 6;
+    const float* gR = d_rot + (int64_t)row * 198 + slot * 9;
+    const float a[3] = {xs[0], xs[2], xs[4]}, c[3] = {xs[1], xs[3], xs[5]};
+    const float na = fmaxf(sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), 1e-12f);
+    const float an[3] = {a[0] / na, a[1] / na, a[2] / na};
+    const float dot = an[0] * c[0] + an[1] * c[1] + an[2] * c[2];
+    const float u[3] = {c[0] - dot * an[0], c[1] - dot * an[1], c[2] - dot * an[2]};
+    const float nu = fmaxf(sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), 1e-12f);
+    const float b[3] = {u[0] / nu, u[1] / nu, u[2] / nu};
+    float ga[3] = {gR[0], gR[3], gR[6]}, gb[3] = {gR[1], gR[4], gR[7]};
+    const float gd[3] = {gR[2], gR[5], gR[8]};
+    // d = a' x b
+    ga[0] += b[1] * gd[2] - b[2] * gd[1]; ga[1] += b[2] * gd[0] - b[0] * gd[2]; ga[2] += b[0] * gd[1] - b[1] * gd[0];
+    gb[0] += gd[1] * an[2] - gd[2] * an[1]; gb[1] += gd[2] * an[0] - gd[0] * an[2]; gb[2] += gd[0] * an[1] - gd[1] * an[0];
+    // b = u / |u|
+    const float bgb = b[0] * gb[0] + b[1] * gb[1] + b[2] * gb[2];
+    const float gu[3] = {(gb[0] - b[0] * bgb) / nu, (gb[1] - b[1] * bgb) / nu, (gb[2] - b[2] * bgb) / nu};
+    // u = c - (a'.c) a'
+    const float agu = an[0] * gu[0] + an[1] * gu[1] + an[2] * gu[2];
+    const float gc[3] = {gu[0] - an[0] * agu, gu[1] - an[1] * agu, gu[2] - an[2] * agu};
+    for (int k = 0; k < 3; ++k) ga[k] -= dot * gu[k] + agu * c[k];
+    // a' = a / |a|
+    const float aga = an[0] * ga[0] + an[1] * ga[1] + an[2] * ga[2];
+    float* o = gx + 3 + slot * 6;
+    for (int k = 0; k < 3; ++k) { o[2 * k] = (ga[k] - an[k] * aga) / na; o[2 * k + 1] = gc[k]; }
+  } else if (slot == 22) {
+    gx[0] = gy[0]; gx[1] = gy[1]; gx[2] = gy[2];
+  } else if (slot == 23) {
+    for (int k = 0; k < 24; ++k) gx[135 + k] = gy[69 + k] + hpose_scale * x[135 + k];
+  }
+}
+
+// d xb[m, :] += d xin[m, D : D + BD]   (the body-parameter slice of the next recurrence's input)
+__global__ void __launch_bounds__(256)
+reg_add_slice_kernel(const float* __restrict__ d_xin, int M, int K, int D, int BD, float* __restrict__ d_xb) {
+  const int64_t total = (int64_t)M * BD;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    d_xb[i] += d_xin[(i / BD) * K + D + (i % BD)];
+}
+
+}  // namespace eg
+
+struct EgRegTrain {
+  int device = 0;
+  EgRegressorDims d;
+  RegLayout L;
+  float *P = nullptr, *G = nullptr;
+  EgLbs* lbs = nullptr;
+  int cap = 0;
+  std::vector<float*> owned;
+  float *xin = nullptr, *hs = nullptr, *t1 = nullptr, *t2 = nullptr, *xbc = nullptr;   // saved per recurrence
+  float *yb = nullptr, *mk = nullptr, *dmk = nullptr, *dyb = nullptr, *drot = nullptr;
+  float *dxbc = nullptr, *dh = nullptr, *da = nullptr, *db = nullptr, *dc = nullptr, *din = nullptr;
+  double* sums = nullptr;
+};
+
+static int reg_ws(EgRegTrain* h, int M) {
+  if (M <= h->cap) return EG_OK;
+  for (float* p : h->owned) cudaFree(p);
+  h->owned.clear(); h->cap = 0;
+  const EgRegressorDims& d = h->d;
+  const size_t m = (size_t)M, H = d.h_dim, K = d.in_dim + d.body_dim + 10, NB = d.n_blocks, NR = d.n_recur, BD = d.body_dim;
+  auto A = [&](float** p, size_t n) -> int {
+    EG_CUDA_CHECK(cudaMalloc((void**)p, n * sizeof(float)));
+    h->owned.push_back(*p);
+    return EG_OK;
+  };
+  EG_TRY(A(&h->xin, NR * m * K)); EG_TRY(A(&h->hs, NR * (NB + 1) * m * H));
+  EG_TRY(A(&h->t1, NR * NB * m * H)); EG_TRY(A(&h->t2, NR * NB * m * H)); EG_TRY(A(&h->xbc, (NR + 1) * m * BD));
+  EG_TRY(A(&h->yb, m * 93)); EG_TRY(A(&h->mk, m * d.in_dim)); EG_TRY(A(&h->dmk, m * d.in_dim));
+  EG_TRY(A(&h->dyb, m * 93)); EG_TRY(A(&h->drot, m * 198)); EG_TRY(A(&h->dxbc, m * BD));
+  EG_TRY(A(&h->dh, m * H)); EG_TRY(A(&h->da, m * H)); EG_TRY(A(&h->db, m * H)); EG_TRY(A(&h->dc, m * H));
+  EG_TRY(A(&h->din, m * K));
+  h->cap = M;
+  return EG_OK;
+}
+
+extern "C" int64_t eg_regressor_param_count(const EgRegressorDims* d) { return d ? make_reg_layout(*d).n_total : -1; }
+
+extern "C" int eg_regressor_train_create(const EgRegressorDims* dims, float* params_flat, float* grads_flat, EgLbs* lbs,
+                                         int device, EgRegTrain** out) {
+  EG_REQUIRE(dims && params_flat && grads_flat && lbs && out, "null pointer");
+  EG_REQUIRE(dims->in_dim == 201 && dims->body_dim == 159, "ssm2_67 markers and the 6-D body vector (use_cont) expected");
+  EG_REQUIRE(dims->h_dim > 0 && dims->n_blocks > 0 && dims->n_recur > 0, "bad dims");
+  EG_CUDA_CHECK(cudaSetDevice(device));
+  EgRegTrain* h = new EgRegTrain();
+  h->device = device; h->d = *dims; h->L = make_reg_layout(*dims); h->P = params_flat; h->G = grads_flat; h->lbs = lbs;
+  if (cudaMalloc((void**)&h->sums, 2 * sizeof(double)) != cudaSuccess) { delete h; return set_error(EG_ERR_CUDA, "cudaMalloc failed"); }
+  *out = h;
+  return EG_OK;
+}
+
+extern "C" void eg_regressor_train_destroy(EgRegTrain* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (float* p : h->owned) cudaFree(p);
+  cudaFree(h->sums);
+  delete h;
+}
+
+namespace {
+int lin_bwd_pg(const float* P, float* G, cudaStream_t st, const float* dY, int ld_dy, const float* X, int ldx, int B, int64_t w,
+               int64_t b, int in, int out, int ldw, float* dX, int ld_dx, int dx_beta) {
+  GemmArgs gw{dY, ld_dy, 1, X, ldx, G + w, ldw, nullptr, nullptr, 0, out, in, B, ACT_NONE, 0.f, 1, 1.0f};
+  EG_TRY(launch_gemm(gw, true, false, st));
+  EG_LAUNCH_PDL(colsum_kernel, (out + 31) / 32, 256, 0, st, dY, ld_dy, B, out, G + b);
+  if (dX) {
+    GemmArgs gx{dY, ld_dy, 1, P + w, ldw, dX, ld_dx, nullptr, nullptr, 0, B, in, out, ACT_NONE, 0.f, dx_beta, 1.0f};
+    EG_TRY(launch_gemm(gx, false, false, st));
+  }
+  return EG_OK;
+}
+}  // namespace
+
+extern "C" int eg_regressor_loss_backward(EgRegTrain* h, const float* marker_ref, const float* betas, int M,
+                                          float w_hpose, float* xb_out, float* stats, void* stream) {
+  EG_REQUIRE(h && marker_ref && betas && stats && M > 0, "bad arguments");
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  EG_TRY(reg_ws(h, M));
+  cudaStream_t st = as_stream(stream);
+  const EgRegressorDims& d = h->d;
+  const RegLayout& L = h->L;
+  const int D = d.in_dim, BD = d.body_dim, H = d.h_dim, NB = d.n_blocks, NR = d.n_recur, K = D + BD + 10;
+  const float* P = h->P;
+  float* G = h->G;
+  const int64_t MH = (int64_t)M * H, MK = (int64_t)M * K, MB = (int64_t)M * BD;
+  const int64_t blk_sz = 2 * ((int64_t)H * H + H);
+  // ---------------- forward (activations kept per recurrence) ----------------
+  EG_CUDA_CHECK(cudaMemsetAsync(h->xbc, 0, MB * sizeof(float), st));
+  for (int r = 0; r < NR; ++r) {
+    float* xin = h->xin + r * MK;
+    float* hr = h->hs + (int64_t)r * (NB + 1) * MH;
+    const float* xb_r = h->xbc + r * MB;
+    EG_LAUNCH(reg_concat_kernel, ew_grid(MK), 256, 0, st, marker_ref, xb_r, betas, M, D, BD, xin);
+    EG_TRY(linear(st, xin, K, M, P + L.in_w, K, P + L.in_b, K, H, hr, H));
+    for (int b = 0; b < NB; ++b) {
+      const int64_t w1 = L.blk + b * blk_sz, b1 = w1 + (int64_t)H * H, w2 = b1 + H, b2 = w2 + (int64_t)H * H;
+      float* t1 = h->t1 + ((int64_t)r * NB + b) * MH;
+      float* t2 = h->t2 + ((int64_t)r * NB + b) * MH;
+      EG_TRY(linear(st, hr + b * MH, H, M, P + w1, H, P + b1, H, H, t1, H, ACT_RELU));
+      EG_TRY(linear(st, t1, H, M, P + w2, H, P + b2, H, H, t2, H, ACT_RELU));
+      EG_LAUNCH_PDL(add_kernel, ew_grid(MH), 256, 0, st, (const float*)t2, (const float*)(hr + b * MH), MH, hr + (b + 1) * MH);
+    }
+    EG_TRY(linear(st, hr + NB * MH, H, M, P + L.out_w, H, P + L.out_b, H, BD, h->xbc + (r + 1) * MB, BD, ACT_NONE, 0.f, xb_r, BD));
+  }
+  const float* xb_fin = h->xbc + NR * MB;
+  EG_LAUNCH(reg_cont2aa_kernel, (M * 32 + 127) / 128, 128, 0, st, xb_fin, M, h->yb);
+  EG_TRY(eg_lbs_forward(h->lbs, h->yb, betas, M, M, nullptr, nullptr, h->mk, stream));
+  if (xb_out) EG_CUDA_CHECK(cudaMemcpyAsync(xb_out, h->yb, (size_t)M * 93 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // ---------------- losses ----------------
+  EG_CUDA_CHECK(cudaMemsetAsync(h->sums, 0, 2 * sizeof(double), st));
+  EG_LAUNCH(reg_l1_kernel, ew_grid((int64_t)M * D), 256, 0, st, (const float*)h->mk, marker_ref, (int64_t)M * D, h->dmk, h->sums);
+  EG_LAUNCH(reg_hpose_kernel, ew_grid((int64_t)M * 24), 256, 0, st, xb_fin, M, h->sums + 1);
+  EG_LAUNCH(reg_stats_kernel, 1, 1, 0, st, (const double*)h->sums, (int64_t)M * D, (int64_t)M * 24, w_hpose, stats);
+  // ---------------- backward ----------------
+  EG_CUDA_CHECK(cudaMemsetAsync(G, 0, (size_t)L.n_total * sizeof(float), st));
+  EG_TRY(eg_lbs_markers_backward_rot(h->lbs, h->yb, betas, M, M, h->dmk, h->dyb, h->drot, stream));
+  EG_LAUNCH(reg_gs_bwd_kernel, (M * 32 + 127) / 128, 128, 0, st, xb_fin, (const float*)h->drot, (const float*)h->dyb, M,
+            w_hpose * 2.0f / (float)((int64_t)M * 24), h->dxbc);
+  for (int r = NR - 1; r >= 0; --r) {
+    const float* xin = h->xin + r * MK;
+    const float* hr = h->hs + (int64_t)r * (NB + 1) * MH;
+    EG_TRY(lin_bwd_pg(P, G, st, h->dxbc, BD, hr + NB * MH, H, M, L.out_w, L.out_b, H, BD, H, h->dh, H, 0));
+    for (int b = NB - 1; b >= 0; --b) {
+      const int64_t w1 = L.blk + b * blk_sz, b1 = w1 + (int64_t)H * H, w2 = b1 + H, b2 = w2 + (int64_t)H * H;
+      const float* t1 = h->t1 + ((int64_t)r * NB + b) * MH;
+      const float* t2 = h->t2 + ((int64_t)r * NB + b) * MH;
+      EG_LAUNCH_PDL(lrelu_bwd_kernel, ew_grid(MH), 256, 0, st, (const float*)h->dh, t2, 0.0f, MH, h->da);
+      EG_TRY(lin_bwd_pg(P, G, st, h->da, H, t1, H, M, w2, b2, H, H, H, h->db, H, 0));
+      EG_LAUNCH_PDL(lrelu_bwd_kernel, ew_grid(MH), 256, 0, st, (const float*)h->db, t1, 0.0f, MH, h->dc);
+      EG_TRY(lin_bwd_pg(P, G, st, h->dc, H, hr + b * MH, H, M, w1, b1, H, H, H, h->dh, H, 1));   // + the skip path
+    }
+    EG_TRY(lin_bwd_pg(P, G, st, h->dh, H, xin, K, M, L.in_w, L.in_b, K, H, K, r > 0 ? h->din : nullptr, K, 0));
+    if (r > 0) EG_LAUNCH(reg_add_slice_kernel, ew_grid(MB), 256, 0, st, (const float*)h->din, M, K, D, BD, h->dxbc);
+  }
   return EG_OK;
 }

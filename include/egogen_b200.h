@@ -128,6 +128,10 @@ int eg_lbs_set_mainloop(EgLbs* h, int use_tcgen05);
  * motion/models/models_GAMMA_primitive.py:616-631). */
 int eg_lbs_markers_backward(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
                             const float* d_markers, float* d_xb, void* stream);
+/* same, and also d_rot [N,22,9] = dL/dR_j (row-major) for the global + 21 body joints, for callers whose pose comes from
+ * another rotation parameterisation (the regressor's 6-D representation, baseops.py:120-130) */
+int eg_lbs_markers_backward_rot(EgLbs* h, const float* xb, const float* betas, int betas_rows, int N,
+                                const float* d_markers, float* d_xb, float* d_rot, void* stream);
 /* SMPLXParser.calc_calibrate_offset (baseops.py:494-534): pelvis of the zero-transl / zero-orient body,
  * i.e. the rest position of the root joint J_0(betas). out [N,3]. */
 int eg_lbs_rest_pelvis(EgLbs* h, const float* betas, int betas_rows, int N, float* out, void* stream);
@@ -342,6 +346,21 @@ int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, const float
 /* torch.optim.Adam / AdamW step on flat buffers (weight_decay is the decoupled AdamW form; 0 for Adam) */
 int eg_adam_step_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
+/* Body-regressor training step (GAMMARegressorTrainOP, motion/models/models_GAMMA_primitive.py:594-633 and the loop
+ * :664-682): MoshRegressor forward (use_cont, relu; :222-301) on marker_ref [M,201] / betas [M,10], 6-D -> axis-angle,
+ * SMPL-X markers of the regressed bodies, loss = L1(marker_ref, markers) + weight_reg_hpose * mean(hand_pca^2), and the
+ * full backward into the flat gradient buffer (ZEROED first, like optimizer.zero_grad()). Flat buffers are in
+ * MoshRegressor.parameters() order. xb_out [M,93] (axis-angle body parameters) may be null; stats = device float[3]:
+ * loss, loss_marker, loss_hpose (overwritten). The step itself is eg_adam_step_flat. */
+typedef struct EgRegTrain EgRegTrain;
+typedef struct EgRegressorDims { int32_t in_dim /*201*/, h_dim /*128*/, n_blocks /*10*/, n_recur /*3*/, body_dim /*159*/; } EgRegressorDims;
+int64_t eg_regressor_param_count(const EgRegressorDims* dims);
+int eg_regressor_train_create(const EgRegressorDims* dims, float* params_flat, float* grads_flat, EgLbs* lbs, int device,
+                              EgRegTrain** out);
+void eg_regressor_train_destroy(EgRegTrain* h);
+int eg_regressor_loss_backward(EgRegTrain* h, const float* marker_ref, const float* betas, int M, float weight_reg_hpose,
+                               float* xb_out, float* stats, void* stream);
 /* CanonicalCoordinateExtractor.get_new_coordinate_torch (baseops.py:214-225): joints of body b at joints + b*ld_body */
 int eg_new_coordinate(const float* joints, int ld_body, int B, float* R, float* T, void* stream);
 /* pts [nt,B,P,3]: inverse=0 -> R p + T, inverse=1 -> R^T (p - T)  (models_GAMMA_primitive.py:462-466) */
