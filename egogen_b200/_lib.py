@@ -122,6 +122,7 @@ PROTOTYPES = {
     "eg_regressor_train_destroy": (None, [_P]),
     "eg_regressor_loss_backward": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
     "eg_adam_step_flat": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
+    "eg_update_transl_glorot": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _P, _P]),
     "eg_new_coordinate": (_I, [_P, _I, _I, _P, _P, _P]),
     "eg_rigid_points": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "eg_lbs_forward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),

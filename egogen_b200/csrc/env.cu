@@ -658,6 +658,32 @@ extern "C" int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_
   return env_reset_impl(h, b, env_ids, nullptr, n, world_params, goals, betas_cand, accept, stream);
 }
 
+// standalone SMPLXParser.update_transl_glorot (baseops.py:537-598): one thread per body; rows 6..92 pass through
+__global__ void __launch_bounds__(128)
+update_transl_glorot_kernel(const float* __restrict__ R, const float* __restrict__ T, const float* __restrict__ delta,
+                            const float* xb, int N, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float o[6];
+  update_transl_glorot(R + (int64_t)i * 9, T + (int64_t)i * 3, delta + (int64_t)i * 3, xb + (int64_t)i * 93, o);
+  float* y = out + (int64_t)i * 93;
+  if (out != xb)
+    for (int k = 6; k < 93; ++k) y[k] = xb[(int64_t)i * 93 + k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) y[k] = o[k];
+}
+
+extern "C" int eg_update_transl_glorot(EgLbs* lbs, const float* transf_rotmat, const float* transf_transl, const float* betas,
+                                       int betas_rows, const float* xb, int N, float* delta_T, float* xb_out, void* stream) {
+  EG_REQUIRE(lbs && transf_rotmat && transf_transl && betas && xb && delta_T && xb_out && N >= 0, "bad arguments");
+  if (N == 0) return EG_OK;
+  int rc = eg_lbs_rest_pelvis(lbs, betas, betas_rows, N, delta_T, stream);
+  if (rc) return rc;
+  EG_LAUNCH(update_transl_glorot_kernel, (N + 127) / 128, 128, 0, as_stream(stream), transf_rotmat, transf_transl,
+            (const float*)delta_T, xb, N, xb_out);
+  return EG_OK;
+}
+
 extern "C" int eg_env_reset_masked(EgEnv* h, const EgEnvBuffers* b, const uint8_t* mask, int E,
                                    const float* world_params, const float* goals, const float* betas_cand,
                                    int32_t* accept, void* stream) {

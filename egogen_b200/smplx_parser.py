@@ -197,3 +197,61 @@ class SMPLXParser:
 
     def get_markers(self, betas, gender, xb, to_numpy=True):
         return self.forward_smplx(betas, gender, xb, to_numpy, "markers")
+
+    # ---- canonical-frame helpers (baseops.py:465-598) ------------------------------------------
+    def _out(self, t, to_numpy):
+        return t.detach().cpu().numpy() if to_numpy else t
+
+    def get_new_coordinate(self, betas, gender, xb, to_numpy=True):
+        """baseops.py:465-490: canonical frame of each body (x = left->right hip projected on the floor, z up, origin at
+        the pelvis). Returns (new_rotmat [b,3,3], new_transl [b,1,3])."""
+        jts = self.forward_smplx(betas, gender, xb, False, "joints").contiguous()       # [b,22,3] on the device
+        B = jts.shape[0]
+        R = torch.empty(B, 3, 3, device=self.device)
+        T = torch.empty(B, 3, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().eg_new_coordinate(_lib.ptr(jts), 22 * 3, B, _lib.ptr(R), _lib.ptr(T),
+                                                    _lib.stream_ptr(self.device)))
+        return self._out(R, to_numpy), self._out(T.view(B, 1, 3), to_numpy)
+
+    def calc_calibrate_offset(self, bm, betas, body_pose, to_numpy=True):
+        """baseops.py:494-534: pelvis of the body with zero transl / global_orient, one row per row of body_pose.
+        (The pelvis is the root of the kinematic chain, so the result depends on betas only.)"""
+        n = body_pose.shape[0]
+        be = self._t(betas).reshape(-1, 10).contiguous()
+        if be.shape[0] not in (1, n):
+            raise _lib.EgError("betas must have 1 or b rows")
+        out = torch.empty(n, 3, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().eg_lbs_rest_pelvis(bm._h, _lib.ptr(be), be.shape[0], n, _lib.ptr(out),
+                                                     _lib.stream_ptr(self.device)))
+        return self._out(out, to_numpy)
+
+    def update_transl_glorot(self, transf_rotmat, transf_transl, betas, gender, xb, to_numpy=True, inplace=True):
+        """baseops.py:537-598: the body parameters re-expressed in the frame (transf_rotmat [b,3,3], transf_transl [b,1,3]).
+        Device arithmetic follows the reference's torch branch (tgm conversions) for numpy inputs as well."""
+        bm = self._bm(gender)
+        xb_t = self._t(xb).contiguous()
+        n = xb_t.shape[0]
+        R = self._t(transf_rotmat).reshape(n, 9).contiguous()
+        T = self._t(transf_transl).reshape(n, 3).contiguous()
+        be = self._t(betas).reshape(-1, 10).contiguous()
+        if be.shape[0] not in (1, n):
+            raise _lib.EgError("betas must have 1 or b rows")
+        delta = torch.empty(n, 3, device=self.device)
+        same = torch.is_tensor(xb) and xb_t.data_ptr() == xb.data_ptr()
+        out = xb_t if (inplace and same) else torch.empty_like(xb_t)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().eg_update_transl_glorot(bm._h, _lib.ptr(R), _lib.ptr(T), _lib.ptr(be), be.shape[0],
+                                                          _lib.ptr(xb_t), n, _lib.ptr(delta), _lib.ptr(out),
+                                                          _lib.stream_ptr(self.device)))
+        if to_numpy:
+            res = out.detach().cpu().numpy()
+            if inplace and isinstance(xb, np.ndarray):
+                xb[:] = res
+                return xb
+            return res
+        if inplace and torch.is_tensor(xb) and not same:
+            xb.copy_(out)
+            return xb
+        return out

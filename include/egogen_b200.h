@@ -361,6 +361,11 @@ int eg_regressor_train_create(const EgRegressorDims* dims, float* params_flat, f
 void eg_regressor_train_destroy(EgRegTrain* h);
 int eg_regressor_loss_backward(EgRegTrain* h, const float* marker_ref, const float* betas, int M, float weight_reg_hpose,
                                float* xb_out, float* stats, void* stream);
+/* SMPLXParser.update_transl_glorot, torch branch (baseops.py:537-598): re-express transl / global_orient of xb [N,93] in
+ * the frame (transf_rotmat [N,3,3], transf_transl [N,3]) with the root-vs-pelvis offset compensation
+ * (calc_calibrate_offset :494-534). delta_T [N,3] receives that offset; xb_out may alias xb (inplace=True). */
+int eg_update_transl_glorot(EgLbs* lbs, const float* transf_rotmat, const float* transf_transl, const float* betas,
+                            int betas_rows, const float* xb, int N, float* delta_T, float* xb_out, void* stream);
 /* CanonicalCoordinateExtractor.get_new_coordinate_torch (baseops.py:214-225): joints of body b at joints + b*ld_body */
 int eg_new_coordinate(const float* joints, int ld_body, int B, float* R, float* T, void* stream);
 /* pts [nt,B,P,3]: inverse=0 -> R p + T, inverse=1 -> R^T (p - T)  (models_GAMMA_primitive.py:462-466) */
