@@ -121,6 +121,9 @@ PROTOTYPES = {
     "eg_regressor_train_create": (_I, [C.POINTER(EgRegressorDims), _P, _P, _P, _I, C.POINTER(_P)]),
     "eg_regressor_train_destroy": (None, [_P]),
     "eg_regressor_loss_backward": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
+    "eg_cvae_forward_train": (_I, [_P, _P, _P, _P, _I, _P, _P]),
+    "eg_cvae_backward": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _I, _F, _I, _P, _P, _P, _P]),
+    "eg_regressor_cycle_backward": (_I, [_P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
     "eg_adam_step_flat": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
     "eg_update_transl_glorot": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _P, _P]),
     "eg_new_coordinate": (_I, [_P, _I, _I, _P, _P, _P]),

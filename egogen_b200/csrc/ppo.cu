@@ -676,10 +676,10 @@ rec_loss_grad_kernel(const float* __restrict__ Y, const float* __restrict__ Yr, 
 }
 
 __global__ void cvae_stats_kernel(const double* __restrict__ sums, int T, int64_t BD, float w_rec, float w_td, float scale,
-                                  float* __restrict__ stats) {
+                                  int in_loss, float* __restrict__ stats) {
   const float rec = w_rec * (float)(sums[0] / (double)((int64_t)T * BD)) + w_td * (float)(sums[1] / (double)((int64_t)(T - 1) * BD));
   atomicAdd(stats + 1, rec * scale);
-  atomicAdd(stats + 0, rec * scale);
+  if (in_loss) atomicAdd(stats + 0, rec * scale);
 }
 
 __global__ void __launch_bounds__(256)
@@ -824,20 +824,19 @@ int lin_bwd(EgCvae* h, cudaStream_t st, const float* dY, int ld_dy, const float*
 // time-major like the reference tensors. Gradients are ACCUMULATED into the flat buffer scaled by loss_scale
 // (1 / #primitives of a rollout, calc_loss_rollout :500). Y_rec [18,B,D] is returned for the next rollout seed.
 // stats (device float[4], accumulated): 0 total loss, 1 rec loss (weighted), 2 kld term.
-extern "C" int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float w_rec,
-                                     float w_td, float w_kld, int robust_kld, float loss_scale, float* Y_rec, float* stats,
-                                     void* stream) {
-  EG_REQUIRE(h && X && Y && eps && Y_rec && stats && B > 0, "bad arguments");
-  EG_CUDA_CHECK(cudaSetDevice(h->device));
-  EG_TRY(cvae_ws(h, B));
-  cudaStream_t st = as_stream(stream);
-  const EgCvaeDims& d = h->d;
-  const CvaeLayout& L = h->L;
-  const int D = d.in_dim, H = d.h_dim, Z = d.z_dim, Hm = d.mlp_dim, H3 = 3 * H, T = 18, Kin = H + Z + D;
-  const float* P = h->P;
-  float* G = h->G;
-  const int64_t BD = (int64_t)B * D;
-  const int64_t nBH = (int64_t)B * H;
+#define EG_CVAE_LOCALS                                                                                              \
+  const EgCvaeDims& d = h->d;                                                                                      \
+  const CvaeLayout& L = h->L;                                                                                      \
+  const int D = d.in_dim, H = d.h_dim, Z = d.z_dim, Hm = d.mlp_dim, H3 = 3 * H, T = 18, Kin = H + Z + D;           \
+  const float* P = h->P;                                                                                           \
+  float* G = h->G;                                                                                                 \
+  const int64_t BD = (int64_t)B * D;                                                                               \
+  const int64_t nBH = (int64_t)B * H;                                                                              \
+  (void)G; (void)nBH; (void)Kin; (void)Hm; (void)Z; (void)P
+
+// forward of one primitive with every activation the backward needs kept in the handle's workspace
+static int cvae_forward(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float* Y_rec, cudaStream_t st) {
+  EG_CVAE_LOCALS;
   // ---------------- forward: encoder ----------------
   for (int t = 0; t < 2; ++t) {   // x_enc
     EG_TRY(linear(st, X + t * BD, D, B, P + L.x_wih, D, P + L.x_bih, D, H3, h->gi, H3));
@@ -877,9 +876,22 @@ extern "C" int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, 
     EG_TRY(linear(st, h->f1[i], Hm, B, P + L.d_mlp1.w, Hm, P + L.d_mlp1.b, Hm, H, h->f2[i], H, ACT_TANH));
     EG_TRY(linear(st, h->f2[i], H, B, P + L.d_out.w, H, P + L.d_out.b, H, D, Y_rec + (int64_t)i * BD, D, ACT_NONE, 0.f, yp, D));
   }
+  return EG_OK;
+}
+
+// losses + backward of the primitive cvae_forward just ran. rec_in_loss = 0 keeps the reconstruction term out of the
+// objective (it is still reported in stats[1]); dY_extra [18,B,D] (nullable) is an additional gradient w.r.t. Y_rec from
+// a downstream loss (the regressor cycle loss of the combo training op).
+static int cvae_backward(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float w_rec, float w_td,
+                         float w_kld, int robust_kld, float loss_scale, int rec_in_loss, const float* Y_rec,
+                         const float* dY_extra, float* stats, cudaStream_t st) {
+  EG_CVAE_LOCALS;
+  const float* hx = h->xh[1];
   // ---------------- losses ----------------
-  EG_LAUNCH(rec_loss_grad_kernel, ew_grid((int64_t)T * BD), 256, 0, st, Y, Y_rec, T, BD, w_rec, w_td, loss_scale, h->dY, h->sums);
-  EG_LAUNCH(cvae_stats_kernel, 1, 1, 0, st, h->sums, T, BD, w_rec, w_td, loss_scale, stats);
+  EG_LAUNCH(rec_loss_grad_kernel, ew_grid((int64_t)T * BD), 256, 0, st, Y, Y_rec, T, BD, w_rec, w_td,
+            rec_in_loss ? loss_scale : 0.0f, h->dY, h->sums);
+  EG_LAUNCH(cvae_stats_kernel, 1, 1, 0, st, h->sums, T, BD, w_rec, w_td, loss_scale, rec_in_loss, stats);
+  if (dY_extra) EG_LAUNCH_PDL(add_kernel, ew_grid((int64_t)T * BD), 256, 0, st, (const float*)h->dY, dY_extra, (int64_t)T * BD, h->dY);
   // ---------------- backward: decoder BPTT ----------------
   EG_CUDA_CHECK(cudaMemsetAsync(h->dh, 0, nBH * 4, st));
   EG_CUDA_CHECK(cudaMemsetAsync(h->dc, 0, (size_t)B * H3 * 4, st));
@@ -957,6 +969,35 @@ extern "C" int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, 
     std::swap(h->dh, h->dhp);
   }
   return EG_OK;
+}
+
+extern "C" int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float w_rec,
+                                     float w_td, float w_kld, int robust_kld, float loss_scale, float* Y_rec, float* stats,
+                                     void* stream) {
+  EG_REQUIRE(h && X && Y && eps && Y_rec && stats && B > 0, "bad arguments");
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  EG_TRY(cvae_ws(h, B));
+  cudaStream_t st = as_stream(stream);
+  EG_TRY(cvae_forward(h, X, Y, eps, B, Y_rec, st));
+  return cvae_backward(h, X, Y, eps, B, w_rec, w_td, w_kld, robust_kld, loss_scale, 1, Y_rec, nullptr, stats, st);
+}
+
+extern "C" int eg_cvae_forward_train(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float* Y_rec,
+                                     void* stream) {
+  EG_REQUIRE(h && X && Y && eps && Y_rec && B > 0, "bad arguments");
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  EG_TRY(cvae_ws(h, B));
+  return cvae_forward(h, X, Y, eps, B, Y_rec, as_stream(stream));
+}
+
+extern "C" int eg_cvae_backward(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float w_rec, float w_td,
+                                float w_kld, int robust_kld, float loss_scale, int rec_in_loss, const float* Y_rec,
+                                const float* dY_extra, float* stats, void* stream) {
+  EG_REQUIRE(h && X && Y && eps && Y_rec && stats && B > 0, "bad arguments");
+  EG_REQUIRE(B <= h->cap, "eg_cvae_forward_train must run first with the same batch");
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  return cvae_backward(h, X, Y, eps, B, w_rec, w_td, w_kld, robust_kld, loss_scale, rec_in_loss, Y_rec, dY_extra, stats,
+                       as_stream(stream));
 }
 
 extern "C" int eg_adam_step_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
@@ -1178,7 +1219,7 @@ extern "C" int eg_regressor_train_create(const EgRegressorDims* dims, float* par
   EG_CUDA_CHECK(cudaSetDevice(device));
   EgRegTrain* h = new EgRegTrain();
   h->device = device; h->d = *dims; h->L = make_reg_layout(*dims); h->P = params_flat; h->G = grads_flat; h->lbs = lbs;
-  if (cudaMalloc((void**)&h->sums, 2 * sizeof(double)) != cudaSuccess) { delete h; return set_error(EG_ERR_CUDA, "cudaMalloc failed"); }
+  if (cudaMalloc((void**)&h->sums, 4 * sizeof(double)) != cudaSuccess) { delete h; return set_error(EG_ERR_CUDA, "cudaMalloc failed"); }
   *out = h;
   return EG_OK;
 }
@@ -1193,38 +1234,34 @@ extern "C" void eg_regressor_train_destroy(EgRegTrain* h) {
 
 namespace {
 int lin_bwd_pg(const float* P, float* G, cudaStream_t st, const float* dY, int ld_dy, const float* X, int ldx, int B, int64_t w,
-               int64_t b, int in, int out, int ldw, float* dX, int ld_dx, int dx_beta) {
-  GemmArgs gw{dY, ld_dy, 1, X, ldx, G + w, ldw, nullptr, nullptr, 0, out, in, B, ACT_NONE, 0.f, 1, 1.0f};
-  EG_TRY(launch_gemm(gw, true, false, st));
-  EG_LAUNCH_PDL(colsum_kernel, (out + 31) / 32, 256, 0, st, dY, ld_dy, B, out, G + b);
+               int64_t b, int in, int out, int ldw, float* dX, int ld_dx, int dx_beta, bool wgrad = true) {
+  if (wgrad) {
+    GemmArgs gw{dY, ld_dy, 1, X, ldx, G + w, ldw, nullptr, nullptr, 0, out, in, B, ACT_NONE, 0.f, 1, 1.0f};
+    EG_TRY(launch_gemm(gw, true, false, st));
+    EG_LAUNCH_PDL(colsum_kernel, (out + 31) / 32, 256, 0, st, dY, ld_dy, B, out, G + b);
+  }
   if (dX) {
     GemmArgs gx{dY, ld_dy, 1, P + w, ldw, dX, ld_dx, nullptr, nullptr, 0, B, in, out, ACT_NONE, 0.f, dx_beta, 1.0f};
     EG_TRY(launch_gemm(gx, false, false, st));
   }
   return EG_OK;
 }
-}  // namespace
 
-extern "C" int eg_regressor_loss_backward(EgRegTrain* h, const float* marker_ref, const float* betas, int M,
-                                          float w_hpose, float* xb_out, float* stats, void* stream) {
-  EG_REQUIRE(h && marker_ref && betas && stats && M > 0, "bad arguments");
-  EG_CUDA_CHECK(cudaSetDevice(h->device));
-  EG_TRY(reg_ws(h, M));
+// regressor forward over its recurrences (activations kept), 6-D -> axis-angle (h->yb) and the SMPL-X markers (h->mk)
+int reg_forward(EgRegTrain* h, const float* markers, const float* betas, int M, void* stream) {
   cudaStream_t st = as_stream(stream);
   const EgRegressorDims& d = h->d;
   const RegLayout& L = h->L;
   const int D = d.in_dim, BD = d.body_dim, H = d.h_dim, NB = d.n_blocks, NR = d.n_recur, K = D + BD + 10;
   const float* P = h->P;
-  float* G = h->G;
   const int64_t MH = (int64_t)M * H, MK = (int64_t)M * K, MB = (int64_t)M * BD;
   const int64_t blk_sz = 2 * ((int64_t)H * H + H);
-  // ---------------- forward (activations kept per recurrence) ----------------
   EG_CUDA_CHECK(cudaMemsetAsync(h->xbc, 0, MB * sizeof(float), st));
   for (int r = 0; r < NR; ++r) {
     float* xin = h->xin + r * MK;
     float* hr = h->hs + (int64_t)r * (NB + 1) * MH;
     const float* xb_r = h->xbc + r * MB;
-    EG_LAUNCH(reg_concat_kernel, ew_grid(MK), 256, 0, st, marker_ref, xb_r, betas, M, D, BD, xin);
+    EG_LAUNCH(reg_concat_kernel, ew_grid(MK), 256, 0, st, markers, xb_r, betas, M, D, BD, xin);
     EG_TRY(linear(st, xin, K, M, P + L.in_w, K, P + L.in_b, K, H, hr, H));
     for (int b = 0; b < NB; ++b) {
       const int64_t w1 = L.blk + b * blk_sz, b1 = w1 + (int64_t)H * H, w2 = b1 + H, b2 = w2 + (int64_t)H * H;
@@ -1236,35 +1273,96 @@ extern "C" int eg_regressor_loss_backward(EgRegTrain* h, const float* marker_ref
     }
     EG_TRY(linear(st, hr + NB * MH, H, M, P + L.out_w, H, P + L.out_b, H, BD, h->xbc + (r + 1) * MB, BD, ACT_NONE, 0.f, xb_r, BD));
   }
+  EG_LAUNCH(reg_cont2aa_kernel, (M * 32 + 127) / 128, 128, 0, st, (const float*)(h->xbc + NR * MB), M, h->yb);
+  return eg_lbs_forward(h->lbs, h->yb, betas, M, M, nullptr, nullptr, h->mk, stream);
+}
+
+// backward from h->dmk (dL/d SMPL-X markers) and the hand regulariser to the parameters (wgrad) and / or to the marker
+// input of the regressor (d_in [M,D], overwritten)
+int reg_backward(EgRegTrain* h, const float* betas, int M, float hpose_scale, bool wgrad, float* d_in, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  const EgRegressorDims& d = h->d;
+  const RegLayout& L = h->L;
+  const int D = d.in_dim, BD = d.body_dim, H = d.h_dim, NB = d.n_blocks, NR = d.n_recur, K = D + BD + 10;
+  const float* P = h->P;
+  float* G = h->G;
+  const int64_t MH = (int64_t)M * H, MK = (int64_t)M * K, MB = (int64_t)M * BD;
+  const int64_t blk_sz = 2 * ((int64_t)H * H + H);
   const float* xb_fin = h->xbc + NR * MB;
-  EG_LAUNCH(reg_cont2aa_kernel, (M * 32 + 127) / 128, 128, 0, st, xb_fin, M, h->yb);
-  EG_TRY(eg_lbs_forward(h->lbs, h->yb, betas, M, M, nullptr, nullptr, h->mk, stream));
-  if (xb_out) EG_CUDA_CHECK(cudaMemcpyAsync(xb_out, h->yb, (size_t)M * 93 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  // ---------------- losses ----------------
-  EG_CUDA_CHECK(cudaMemsetAsync(h->sums, 0, 2 * sizeof(double), st));
-  EG_LAUNCH(reg_l1_kernel, ew_grid((int64_t)M * D), 256, 0, st, (const float*)h->mk, marker_ref, (int64_t)M * D, h->dmk, h->sums);
-  EG_LAUNCH(reg_hpose_kernel, ew_grid((int64_t)M * 24), 256, 0, st, xb_fin, M, h->sums + 1);
-  EG_LAUNCH(reg_stats_kernel, 1, 1, 0, st, (const double*)h->sums, (int64_t)M * D, (int64_t)M * 24, w_hpose, stats);
-  // ---------------- backward ----------------
-  EG_CUDA_CHECK(cudaMemsetAsync(G, 0, (size_t)L.n_total * sizeof(float), st));
+  if (wgrad) EG_CUDA_CHECK(cudaMemsetAsync(G, 0, (size_t)L.n_total * sizeof(float), st));
+  if (d_in) EG_CUDA_CHECK(cudaMemsetAsync(d_in, 0, (size_t)M * D * sizeof(float), st));
   EG_TRY(eg_lbs_markers_backward_rot(h->lbs, h->yb, betas, M, M, h->dmk, h->dyb, h->drot, stream));
   EG_LAUNCH(reg_gs_bwd_kernel, (M * 32 + 127) / 128, 128, 0, st, xb_fin, (const float*)h->drot, (const float*)h->dyb, M,
-            w_hpose * 2.0f / (float)((int64_t)M * 24), h->dxbc);
+            hpose_scale, h->dxbc);
   for (int r = NR - 1; r >= 0; --r) {
     const float* xin = h->xin + r * MK;
     const float* hr = h->hs + (int64_t)r * (NB + 1) * MH;
-    EG_TRY(lin_bwd_pg(P, G, st, h->dxbc, BD, hr + NB * MH, H, M, L.out_w, L.out_b, H, BD, H, h->dh, H, 0));
+    EG_TRY(lin_bwd_pg(P, G, st, h->dxbc, BD, hr + NB * MH, H, M, L.out_w, L.out_b, H, BD, H, h->dh, H, 0, wgrad));
     for (int b = NB - 1; b >= 0; --b) {
       const int64_t w1 = L.blk + b * blk_sz, b1 = w1 + (int64_t)H * H, w2 = b1 + H, b2 = w2 + (int64_t)H * H;
       const float* t1 = h->t1 + ((int64_t)r * NB + b) * MH;
       const float* t2 = h->t2 + ((int64_t)r * NB + b) * MH;
       EG_LAUNCH_PDL(lrelu_bwd_kernel, ew_grid(MH), 256, 0, st, (const float*)h->dh, t2, 0.0f, MH, h->da);
-      EG_TRY(lin_bwd_pg(P, G, st, h->da, H, t1, H, M, w2, b2, H, H, H, h->db, H, 0));
+      EG_TRY(lin_bwd_pg(P, G, st, h->da, H, t1, H, M, w2, b2, H, H, H, h->db, H, 0, wgrad));
       EG_LAUNCH_PDL(lrelu_bwd_kernel, ew_grid(MH), 256, 0, st, (const float*)h->db, t1, 0.0f, MH, h->dc);
-      EG_TRY(lin_bwd_pg(P, G, st, h->dc, H, hr + b * MH, H, M, w1, b1, H, H, H, h->dh, H, 1));   // + the skip path
+      EG_TRY(lin_bwd_pg(P, G, st, h->dc, H, hr + b * MH, H, M, w1, b1, H, H, H, h->dh, H, 1, wgrad));   // + the skip path
     }
-    EG_TRY(lin_bwd_pg(P, G, st, h->dh, H, xin, K, M, L.in_w, L.in_b, K, H, K, r > 0 ? h->din : nullptr, K, 0));
+    const bool need_din = r > 0 || d_in != nullptr;
+    EG_TRY(lin_bwd_pg(P, G, st, h->dh, H, xin, K, M, L.in_w, L.in_b, K, H, K, need_din ? h->din : nullptr, K, 0, wgrad));
     if (r > 0) EG_LAUNCH(reg_add_slice_kernel, ew_grid(MB), 256, 0, st, (const float*)h->din, M, K, D, BD, h->dxbc);
+    if (d_in) EG_LAUNCH(reg_add_slice_kernel, ew_grid((int64_t)M * D), 256, 0, st, (const float*)h->din, M, K, 0, D, d_in);
   }
   return EG_OK;
+}
+}  // namespace
+
+extern "C" int eg_regressor_loss_backward(EgRegTrain* h, const float* marker_ref, const float* betas, int M,
+                                          float w_hpose, float* xb_out, float* stats, void* stream) {
+  EG_REQUIRE(h && marker_ref && betas && stats && M > 0, "bad arguments");
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  EG_TRY(reg_ws(h, M));
+  cudaStream_t st = as_stream(stream);
+  const int D = h->d.in_dim;
+  EG_TRY(reg_forward(h, marker_ref, betas, M, stream));
+  if (xb_out) EG_CUDA_CHECK(cudaMemcpyAsync(xb_out, h->yb, (size_t)M * 93 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  EG_CUDA_CHECK(cudaMemsetAsync(h->sums, 0, 4 * sizeof(double), st));
+  EG_LAUNCH(reg_l1_kernel, ew_grid((int64_t)M * D), 256, 0, st, (const float*)h->mk, marker_ref, (int64_t)M * D, h->dmk, h->sums);
+  EG_LAUNCH(reg_hpose_kernel, ew_grid((int64_t)M * 24), 256, 0, st, (const float*)(h->xbc + (int64_t)h->d.n_recur * M * h->d.body_dim),
+            M, h->sums + 1);
+  EG_LAUNCH(reg_stats_kernel, 1, 1, 0, st, (const double*)h->sums, (int64_t)M * D, (int64_t)M * 24, w_hpose, stats);
+  return reg_backward(h, betas, M, w_hpose * 2.0f / (float)((int64_t)M * 24), true, nullptr, stream);
+}
+
+// Regressor part of the combo objective (GAMMAPrimitiveComboTrainOP.calc_loss_regressor, models_GAMMA_primitive.py:787-794):
+// markers_in [T*B,201] (t-major, the predictor's Y_rec) -> body parameters -> SMPL-X markers x_pred;
+//   loss = w_rec L1(Y_ref, x_pred) + w_td L1(dt x_pred, dt Y_ref) + w_hpose mean(hand^2)   (x loss_scale)
+// and its gradient w.r.t. markers_in (the regressor's weights are not trained by that op). want_grad = 0 only evaluates
+// the two loss terms (the torch.no_grad() branch). stats (device float[2], ACCUMULATED): marker term, hand term.
+__global__ void reg_cycle_stats_kernel(const double* __restrict__ sums, int T, int64_t BD, int64_t n_hpose, float w_rec,
+                                       float w_td, float scale, float* __restrict__ stats) {
+  const float rec = w_rec * (float)(sums[0] / (double)((int64_t)T * BD)) + w_td * (float)(sums[1] / (double)((int64_t)(T - 1) * BD));
+  atomicAdd(stats + 0, rec * scale);
+  atomicAdd(stats + 1, (float)(sums[2] / (double)n_hpose) * scale);
+}
+
+extern "C" int eg_regressor_cycle_backward(EgRegTrain* h, const float* markers_in, const float* betas, const float* Y_ref,
+                                           int T, int B, float w_rec, float w_td, float w_hpose, float loss_scale,
+                                           int want_grad, float* d_markers_in, float* xb_out, float* stats, void* stream) {
+  EG_REQUIRE(h && markers_in && betas && Y_ref && stats && T > 1 && B > 0, "bad arguments");
+  EG_REQUIRE(!want_grad || d_markers_in, "d_markers_in required when want_grad");
+  EG_CUDA_CHECK(cudaSetDevice(h->device));
+  const int M = T * B, D = h->d.in_dim;
+  EG_TRY(reg_ws(h, M));
+  cudaStream_t st = as_stream(stream);
+  EG_TRY(reg_forward(h, markers_in, betas, M, stream));
+  if (xb_out) EG_CUDA_CHECK(cudaMemcpyAsync(xb_out, h->yb, (size_t)M * 93 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  EG_CUDA_CHECK(cudaMemsetAsync(h->sums, 0, 4 * sizeof(double), st));
+  const int64_t BDm = (int64_t)B * D;
+  EG_LAUNCH(rec_loss_grad_kernel, ew_grid((int64_t)T * BDm), 256, 0, st, Y_ref, (const float*)h->mk, T, BDm, w_rec, w_td,
+            want_grad ? loss_scale : 0.0f, h->dmk, h->sums);
+  EG_LAUNCH(reg_hpose_kernel, ew_grid((int64_t)M * 24), 256, 0, st, (const float*)(h->xbc + (int64_t)h->d.n_recur * M * h->d.body_dim),
+            M, h->sums + 2);
+  EG_LAUNCH(reg_cycle_stats_kernel, 1, 1, 0, st, (const double*)h->sums, T, BDm, (int64_t)M * 24, w_rec, w_td, loss_scale, stats);
+  if (!want_grad) return EG_OK;
+  return reg_backward(h, betas, M, w_hpose * loss_scale * 2.0f / (float)((int64_t)M * 24), false, d_markers_in, stream);
 }

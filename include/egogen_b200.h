@@ -343,6 +343,15 @@ void eg_cvae_destroy(EgCvae* h);
  * (scaled by loss_scale); Y_rec [18,B,201] out; stats (device float[4], accumulated): loss, rec, kld. */
 int eg_cvae_loss_backward(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float w_rec, float w_td,
                           float w_kld, int robust_kld, float loss_scale, float* Y_rec, float* stats, void* stream);
+/* The same primitive in two calls, for objectives that add a downstream loss on Y_rec before the backward
+ * (GAMMAPrimitiveComboTrainOP.calc_loss_one, models_GAMMA_primitive.py:819-838): eg_cvae_forward_train keeps the activations;
+ * eg_cvae_backward evaluates the losses and back-propagates. rec_in_loss = 0 reports the reconstruction term in stats[1]
+ * but keeps it out of the objective (calc_loss_marker :797-815 without scheduled sampling); dY_extra [18,B,201] (nullable)
+ * is added to dL/dY_rec. */
+int eg_cvae_forward_train(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float* Y_rec, void* stream);
+int eg_cvae_backward(EgCvae* h, const float* X, const float* Y, const float* eps, int B, float w_rec, float w_td, float w_kld,
+                     int robust_kld, float loss_scale, int rec_in_loss, const float* Y_rec, const float* dY_extra,
+                     float* stats, void* stream);
 /* torch.optim.Adam / AdamW step on flat buffers (weight_decay is the decoupled AdamW form; 0 for Adam) */
 int eg_adam_step_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
@@ -361,6 +370,14 @@ int eg_regressor_train_create(const EgRegressorDims* dims, float* params_flat, f
 void eg_regressor_train_destroy(EgRegTrain* h);
 int eg_regressor_loss_backward(EgRegTrain* h, const float* marker_ref, const float* betas, int M, float weight_reg_hpose,
                                float* xb_out, float* stats, void* stream);
+/* Regressor part of the combo objective (calc_loss_regressor, models_GAMMA_primitive.py:787-794): markers_in [T*B,201]
+ * (t-major; the predictor's Y_rec) -> body parameters -> SMPL-X markers x_pred; loss_scale * (w_rec L1(Y_ref, x_pred) +
+ * w_td L1(dt x_pred, dt Y_ref) + w_hpose mean(hand_pca^2)) and its gradient w.r.t. markers_in (d_markers_in [T*B,201],
+ * overwritten; the regressor's weights are not trained by that op). want_grad = 0 only evaluates the terms (the no_grad
+ * branch). stats (device float[2], ACCUMULATED): marker term, hand term. xb_out [T*B,93] may be null. */
+int eg_regressor_cycle_backward(EgRegTrain* h, const float* markers_in, const float* betas, const float* Y_ref, int T, int B,
+                                float w_rec, float w_td, float w_hpose, float loss_scale, int want_grad, float* d_markers_in,
+                                float* xb_out, float* stats, void* stream);
 /* SMPLXParser.update_transl_glorot, torch branch (baseops.py:537-598): re-express transl / global_orient of xb [N,93] in
  * the frame (transf_rotmat [N,3,3], transf_transl [N,3]) with the root-vs-pelvis offset compensation
  * (calc_calibrate_offset :494-534). delta_T [N,3] receives that offset; xb_out may alias xb (inplace=True). */

@@ -54,3 +54,24 @@ def rollout_loss(pred, ref_markers, ref_jts, eps_list, max_rollout=8, t_his=2):
         if len(losses) >= max_rollout:
             break
     return torch.stack(losses).mean()
+
+
+def combo_loss_one(pred, reg, lbs, X, Y, betas_Y, eps, w_rec=1.0, w_td=3.0, w_kld=1.0, robust=True, w_hpose=0.01,
+                   scheduled_sampling=False):
+    """GAMMAPrimitiveComboTrainOP.calc_loss_one (models_GAMMA_primitive.py:819-838) with calc_loss_marker (:797-815) and
+    calc_loss_regressor (:787-794): the predictor's Y_rec goes through the regressor and SMPL-X (`lbs`, an
+    SMPLXParserOracle) and is compared with the ground-truth markers. Returns (loss, [rec, kld, reg, hpose], Yb_rec)."""
+    Y_rec, mu, logvar = forward(pred, X, Y, eps)
+    nt, nb = Y_rec.shape[:2]
+    rec_of = lambda a, b: w_rec * F.l1_loss(a, b) + w_td * F.l1_loss(b[1:] - b[:-1], a[1:] - a[:-1])
+    loss_rec = rec_of(Y, Y_rec)
+    kld = 0.5 * torch.mean(-1 - logvar + mu.pow(2) + logvar.exp())
+    if robust:
+        kld = torch.sqrt(1 + kld ** 2) - 1
+    loss_marker = loss_rec + w_kld * kld if scheduled_sampling else w_kld * kld
+    Yb = reg(Y_rec.contiguous().view(nt * nb, -1), betas_Y.contiguous().view(nt * nb, -1))
+    x_pred = lbs.forward_smplx(betas_Y.reshape(nt * nb, 10), "male", Yb, "markers").reshape(nt, nb, -1)
+    loss_reg = rec_of(Y, x_pred)
+    loss_h = torch.mean(Yb[:, 69:] ** 2)
+    loss = loss_marker + loss_reg + w_hpose * loss_h
+    return loss, [loss_rec, kld, loss_reg, loss_h], Yb.view(nt, nb, -1)
