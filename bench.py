@@ -389,13 +389,72 @@ def run_cvae_train(args):
                       "config": {"workload": "C-VAE predictor training, batch 4096 x 8-primitive rollout (200-frame sequences), Adam"}}))
 
 
+def run_regressor_train(args):
+    """Marker -> body regressor training (GAMMARegressorTrainOP, models_GAMMA_primitive.py:594-710): 512 sequences x 16
+    frames = 8192 bodies per optimiser step (forward over 3 recurrences, SMPL-X markers, backward through SMPL-X, Adam).
+    Secondary workload."""
+    import torch
+    from egogen_b200 import assets
+    from egogen_b200.smplx_parser import get_lbs_model
+    from egogen_b200.train_gamma_regressor import GAMMARegressorTrainOP, SyntheticBodyMarkerBatchGen
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    n_seq, n_frames = 512, 16
+    op = GAMMARegressorTrainOP(trainconfig={"batch_size": n_seq}, device=dev)
+    op.build_model(seed=0)
+    gen = SyntheticBodyMarkerBatchGen(get_lbs_model("male", dev, marker_vids=assets.marker_ids()), n_seq, n_frames, dev, seed=0)
+    betas, mk = gen.next_batch_genderselection(n_seq)
+    mk = mk.reshape(-1, 201).contiguous(); betas = betas.reshape(-1, 10).contiguous()
+    for _ in range(max(args.warmup, 3)):
+        op.forward_loss_backward(mk, betas); op.optimizer_step(3e-4)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        _, loss, _ = op.forward_loss_backward(mk, betas); op.optimizer_step(3e-4)
+    e1.record(); torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"metric": "regressor training bodies/sec", "value": mk.shape[0] * args.steps / (ms / 1e3), "unit": "bodies/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                      "higher_is_better": True, "dtype": "f32", "data": "synthetic", "loss": loss,
+                      "config": {"workload": "body-regressor training, 512 sequences x 16 frames per step, SMPL-X marker loss, Adam"}}))
+
+
+def run_combo_train(args):
+    """Joint predictor + regressor objective (GAMMAPrimitiveComboTrainOP.calc_loss_one, :819-838): 1024 primitives per
+    optimiser step (18 432 regressed bodies in the SMPL-X cycle loss). Secondary workload."""
+    import torch
+    from egogen_b200.train_gamma_combo import GAMMAPrimitiveComboTrainOP
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B = 1024
+    op = GAMMAPrimitiveComboTrainOP(trainconfig={"batch_size": B}, device=dev)
+    op.build_model(seed=0)
+    g = torch.Generator().manual_seed(0)
+    ref = (torch.cumsum(torch.randn(20, B, 201, generator=g) * 0.02, dim=0) + torch.randn(1, B, 201, generator=g) * 0.3).to(dev)
+    betas = (torch.randn(1, B, 10, generator=g) * 0.5).expand(20, B, 10).contiguous().to(dev)
+    for _ in range(max(args.warmup, 3)):
+        op.calc_loss_one([betas, ref], 0); op.optimizer_step(1e-4)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, _, _ = op.calc_loss_one([betas, ref], 0); op.optimizer_step(1e-4)
+    e1.record(); torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"metric": "combo training primitives/sec", "value": B * args.steps / (ms / 1e3), "unit": "primitives/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                      "higher_is_better": True, "dtype": "f32", "data": "synthetic", "loss": loss,
+                      "config": {"workload": "predictor + regressor combo objective, 1024 primitives per step (18432 bodies), Adam on the predictor"}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "ego_depth", "cvae_train", "crowd_eval"],
+    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "ego_depth", "cvae_train", "crowd_eval", "regressor_train", "combo_train"],
                     help="ppo = headline (BASELINE config 2); ego_depth = secondary config-5 sweep")
     args = ap.parse_args()
     if args.workload == "ego_depth" and args.impl == "ours":
@@ -404,6 +463,10 @@ def main():
         return run_cvae_train(args)
     if args.workload == "crowd_eval" and args.impl == "ours":
         return run_crowd_eval(args)
+    if args.workload == "regressor_train" and args.impl == "ours":
+        return run_regressor_train(args)
+    if args.workload == "combo_train" and args.impl == "ours":
+        return run_combo_train(args)
     if args.impl == "reference":
         run_reference(args)
     else:
