@@ -29,13 +29,12 @@ def _setup(dev, smplx_model, sched):
     return op, pred, reg, SMPLXParserOracle(smplx_model, marker=assets.marker_ids())
 
 
-@pytest.mark.parametrize("sched", [False, True])
-def test_combo_loss_one_and_predictor_grads(smplx_model, sched):
+@pytest.mark.parametrize("sched,B", [(False, 6), (True, 6), (True, 1)])
+def test_combo_loss_one_and_predictor_grads(smplx_model, sched, B):
     from oracle import cvae_train as oc
     dev = torch.device("cuda:0")
     op, pred, reg, lbs = _setup(dev, smplx_model, sched)
     g = torch.Generator().manual_seed(3)
-    B = 6
     ref = torch.cumsum(torch.randn(20, B, 201, generator=g) * 0.02, dim=0) + torch.randn(1, B, 201, generator=g) * 0.3
     betas = (torch.randn(1, B, 10, generator=g) * 0.5).expand(20, B, 10).contiguous()
     eps = torch.randn(B, 128, generator=g)
@@ -64,3 +63,38 @@ def test_combo_loss_one_and_predictor_grads(smplx_model, sched):
     op.optimizer_step(1e-4)
     assert torch.equal(op._rop.flat_params, r0) and not torch.equal(op._pop.flat_params, p0)
     assert set(op.model.state_dict()) == {"predictor." + k for k in pred.state_dict()} | {"regressor." + k for k in reg.state_dict()}
+
+
+def test_cycle_loss_without_grad_and_call_order(smplx_model):
+    """want_grad = 0 (the reference's torch.no_grad() evaluation of the regressor terms) reports the same terms and leaves
+    the gradient output alone; eg_cvae_backward refuses to run before eg_cvae_forward_train sized the workspace."""
+    import ctypes as C
+    from egogen_b200 import _lib
+    dev = torch.device("cuda:0")
+    op, _, _, _ = _setup(dev, smplx_model, True)
+    g = torch.Generator().manual_seed(8)
+    T, B = 18, 3
+    Yr = (torch.randn(T, B, 201, generator=g) * 0.3).to(dev)
+    Y = (Yr.cpu() + torch.randn(T, B, 201, generator=g) * 0.02).to(dev)
+    betas = (torch.randn(T, B, 10, generator=g) * 0.5).to(dev)
+    L, st = _lib.lib(), _lib.stream_ptr(dev)
+    outs = []
+    for want in (1, 0):
+        d = torch.full((T, B, 201), 7.0, device=dev)
+        stats = torch.zeros(2, device=dev)
+        _lib.check(L.eg_regressor_cycle_backward(op._rop._h, _lib.ptr(Yr), _lib.ptr(betas), _lib.ptr(Y), T, B, 1.0, 3.0, 0.01,
+                                                 0.5, want, _lib.ptr(d), None, _lib.ptr(stats), st))
+        outs.append((d.cpu(), stats.cpu()))
+    assert torch.equal(outs[0][1], outs[1][1]) and float(outs[0][1][0]) > 0
+    assert torch.isfinite(outs[0][0]).all() and float(outs[0][0].abs().max()) < 7.0        # overwritten with the gradient
+    assert torch.equal(outs[1][0], torch.full((T, B, 201), 7.0))                              # untouched
+    assert L.eg_regressor_cycle_backward(op._rop._h, _lib.ptr(Yr), _lib.ptr(betas), _lib.ptr(Y), T, B, 1.0, 3.0, 0.01, 1.0, 1,
+                                         None, None, _lib.ptr(stats), st) != 0              # gradient requested, no buffer
+    # a fresh predictor handle has no forward activations yet
+    from egogen_b200.train_gamma_predictor import GAMMAPrimitiveVAETrainOP
+    fresh = GAMMAPrimitiveVAETrainOP(device=dev)
+    fresh.build_model(seed=1)
+    X = torch.zeros(2, B, 201, device=dev); eps = torch.zeros(B, 128, device=dev); s4 = torch.zeros(4, device=dev)
+    rc = L.eg_cvae_backward(fresh._h, _lib.ptr(X), _lib.ptr(Y), _lib.ptr(eps), B, 1.0, 3.0, 1.0, 1, 1.0, 1, _lib.ptr(Yr), None,
+                            _lib.ptr(s4), st)
+    assert rc != 0 and b"forward" in L.eg_last_error()

@@ -47,7 +47,7 @@ def _oracle_loss(orc, lbs, mk, betas, w):
     return xb, lm + w * lh, lm, lh
 
 
-@pytest.mark.parametrize("M,seed", [(12, 3), (70, 4)])
+@pytest.mark.parametrize("M,seed", [(12, 3), (70, 4), (1, 6)])
 def test_regressor_loss_and_grads(smplx_model, M, seed):
     dev = torch.device("cuda:0")
     op, orc, lbs = _setup(dev, smplx_model, seed)
