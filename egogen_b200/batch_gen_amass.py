@@ -250,7 +250,7 @@ class BatchGeneratorAMASSCanonicalized:
         keys = ("betas", "transl", "glorot", "thetas", "feature", "jts")
         acc = {k: [] for k in keys}
         bb = 0
-        while self.index_rec < len(self.rec_list):
+        while self.has_next_rec():
             rec = self.rec_list[self.index_rec]
             if bb == batch_size:
                 break
@@ -271,7 +271,7 @@ class BatchGeneratorAMASSCanonicalized:
             acc["thetas"].append(pose[:, 3:]); acc["jts"].append(joints.reshape([-1, 22 * 3]))
             self.index_rec += 1
             bb += 1
-            if self.index_rec == len(self.rec_list):
+            if self.index_rec == len(self.data_list):
                 break
         if len(acc["betas"]) < batch_size:
             return None
