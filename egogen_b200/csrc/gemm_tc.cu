@@ -30,7 +30,9 @@ namespace eg {
 namespace gtc {
 
 constexpr int BM = 128, BK = 32;                     // BK fp32 = 128 B = one swizzle row; BN (64 or 128) is a template parameter
-constexpr int STAGES = 2;
+#ifndef EG_GEMM_TC_STAGES
+#define EG_GEMM_TC_STAGES 2                             // ring depth (48 KB per stage at BN = 64); see DESIGN 6b for the 3 / 4-stage A/B
+#endif
 constexpr int A_BYTES = BM * BK * 4;                // 16 KB
 constexpr int XF_WARPS = 8;                          // transform + epilogue warps
 constexpr int THREADS = 64 + XF_WARPS * 32;          // 320
@@ -39,6 +41,7 @@ constexpr int XF_THREADS = XF_WARPS * 32;
 template <int BN>
 struct Geo {
   static constexpr int B_BYTES = BN * BK * 4;                   // 8 / 16 KB
+  static constexpr int STAGES = (BN == 64 || EG_GEMM_TC_STAGES < 3) ? EG_GEMM_TC_STAGES : 3;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // raw(hi) A, raw(hi) B, lo A, lo B = 48 / 64 KB
   static constexpr int TMEM_COLS = BN;
   static constexpr int EPI_COLS = BN / (XF_WARPS / 4);          // columns per epilogue thread (two warps share a TMEM lane quarter)
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
   namespace cg = cooperative_groups;
   using G = Geo<BN>;
-  constexpr int B_BYTES = G::B_BYTES, STAGE_BYTES = G::STAGE_BYTES, TMEM_COLS = G::TMEM_COLS, EPI_COLS = G::EPI_COLS,
+  constexpr int STAGES = G::STAGES, B_BYTES = G::B_BYTES, STAGE_BYTES = G::STAGE_BYTES, TMEM_COLS = G::TMEM_COLS, EPI_COLS = G::EPI_COLS,
                 RED_LD = G::RED_LD, OFF_BARS = G::OFF_BARS;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);

@@ -13,3 +13,13 @@ e0.record()
 for _ in range(20): pol.net_forward(obs)
 e1.record(); torch.cuda.synchronize()
 print("policy forward (actor+critic) B=256:", e0.elapsed_time(e1) / 20, "ms")
+# one PPO minibatch update (forward + loss + backward + clip + AdamW), the unit the 4 updates of a bench iteration repeat
+from types import SimpleNamespace
+mb = SimpleNamespace(obs=obs, act=torch.randn(B, 128, device=dev), logp_old=torch.randn(B, device=dev) - 180.0,
+                     adv=torch.randn(B, device=dev), returns=torch.randn(B, device=dev))
+for _ in range(3): pol.learn_minibatch(mb)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(20): pol.learn_minibatch(mb)
+e1.record(); torch.cuda.synchronize()
+print("policy learn_minibatch B=256:", e0.elapsed_time(e1) / 20, "ms")
