@@ -103,102 +103,95 @@ def apply_rot_noise(rot, noise):
     return matrix_to_axis_angle(res).reshape(t, d)
 
 
+def _finite(*arrays):
+    return all(np.isfinite(a).all() for a in arrays)
+
+
+def read_primitive(path, stride=1, max_len=None, need_120fps=False, check_finite=True):
+    """One primitive file as a dict of strided (and optionally truncated) arrays, or None when it fails the filters the
+    reference applies while loading (:161-171: frame rate, NaN / inf in the body parameters)."""
+    with np.load(path) as f:
+        if need_120fps and f["mocap_framerate"] != 120:
+            return None
+        rec = {"pose": f["poses"][::stride, :66], "transl": f["trans"][::stride], "betas": f["betas"],
+               "gender": str(f["gender"].astype(str)), "cmu": f["marker_cmu_41"][::stride], "ssm": f["marker_ssm2_67"][::stride],
+               "joints": f["joints"][::stride].reshape([-1, 22, 3]), "R": f["transf_rotmat"], "T": f["transf_transl"]}
+    if check_finite and not _finite(rec["pose"], rec["transl"]):
+        return None
+    if max_len is not None:
+        for k in ("pose", "transl", "cmu", "ssm", "joints"):
+            rec[k] = rec[k][:max_len]
+    return rec
+
+
 class BatchGeneratorAMASSCanonicalized:
+    """Same constructor arguments, attributes and batch methods as the reference class; `device` / `parser` are the
+    only additions (where batches land, and the body model used by the noise-augmented batches)."""
+
+    _IN_MEMORY = ("data_all", "pose_all", "beta_all", "transl_all", "gender_all")
+
     def __init__(self, amass_data_path, amass_subset_name=None, sample_rate=3, body_repr="cmu_41", read_to_ram=True,
                  device="cuda:0", parser=None):
-        self.rec_list = []
+        self.amass_data_path, self.amass_subset_name = amass_data_path, amass_subset_name
+        self.sample_rate, self.body_repr, self.read_to_ram = sample_rate, body_repr, read_to_ram
+        self.rec_list, self.data_list, self.jts_list = [], [], []
         self.index_rec = 0
-        self.amass_data_path = amass_data_path
-        self.amass_subset_name = amass_subset_name
-        self.sample_rate = sample_rate
-        self.data_list = []
-        self.jts_list = []
-        self.body_repr = body_repr
-        self.read_to_ram = read_to_ram
         self.max_len = 200 if "x10" in amass_data_path else 20
         self.device = torch.device(device)
         self._parser = parser            # SMPLXParser (ssm2_67), built on first use by the noise-augmented batches
 
     # ---- iteration state ---------------------------------------------------------------------
-    def _permute(self, with_jts):
+    def _rewind(self, fields):
+        """index back to 0 and a fresh order: one permutation applied to the named in-memory arrays (the reference's
+        reset() leaves jts_all out, reset_with_jts() includes it), or a shuffle of the file list."""
+        self.index_rec = 0
+        if not self.read_to_ram:
+            random.shuffle(self.rec_list)
+            return
         random.shuffle(self.data_list)
-        idx = torch.randperm(self.data_all.shape[0])
-        names = ["data_all", "pose_all", "beta_all", "transl_all", "gender_all"] + (["jts_all"] if with_jts else [])
-        for n in names:
-            v = getattr(self, n)
-            setattr(self, n, v[idx.to(v.device)] if torch.is_tensor(v) else v[idx.numpy()])
+        order = torch.randperm(self.data_all.shape[0])
+        for name in fields:
+            v = getattr(self, name)
+            setattr(self, name, v[order.to(v.device)] if torch.is_tensor(v) else v[order.numpy()])
 
     def reset(self):
-        self.index_rec = 0
-        if self.read_to_ram:
-            self._permute(False)
-        else:
-            random.shuffle(self.rec_list)
+        self._rewind(self._IN_MEMORY)
 
     def reset_with_jts(self):
-        self.index_rec = 0
-        if self.read_to_ram:
-            self._permute(True)
-        else:
-            random.shuffle(self.rec_list)
+        self._rewind(self._IN_MEMORY + ("jts_all",))
 
     def has_next_rec(self):
-        return self.index_rec < (len(self.data_list) if self.read_to_ram else len(self.rec_list))
+        return self.index_rec < len(self.data_list if self.read_to_ram else self.rec_list)
 
     # ---- loading -------------------------------------------------------------------------------
+    def _feature(self, rec, frame_R=np.eye(3), frame_T=np.zeros((1, 3))):
+        _, _, to_target = get_target_feature(rec["joints"], rec["ssm"], frame_R, frame_T)
+        return body_feature(self.body_repr, rec["transl"], rec["pose"], rec["joints"], rec["cmu"], rec["ssm"], to_target)
+
     def get_rec_list(self, shuffle_seed=None, to_gpu=False):
-        if self.amass_subset_name is not None:
-            self.rec_list = []
-            for subset in self.amass_subset_name:
-                self.rec_list += sorted(glob.glob(os.path.join(self.amass_data_path, subset, "*.npz")))
-        else:
-            self.rec_list = sorted(glob.glob(os.path.join(self.amass_data_path, "*/*.npz")))
-        if shuffle_seed is not None:
-            random.Random(shuffle_seed).shuffle(self.rec_list)
-        else:
-            random.shuffle(self.rec_list)
+        root = self.amass_data_path
+        patterns = [os.path.join(root, "*/*.npz")] if self.amass_subset_name is None else \
+                   [os.path.join(root, sub, "*.npz") for sub in self.amass_subset_name]
+        self.rec_list = [p for pat in patterns for p in sorted(glob.glob(pat))]
+        (random.Random(shuffle_seed) if shuffle_seed is not None else random).shuffle(self.rec_list)
         if not self.read_to_ram:
             return
-        self.data_list, self.jts_list = [], []
-        self.pose_list, self.transl_list, self.beta_list, self.gender_list = [], [], [], []
-        for rec in self.rec_list:
-            with np.load(rec) as d:
-                if d["mocap_framerate"] != 120:
-                    continue
-                sr = self.sample_rate
-                pose = d["poses"][::sr, :66]
-                transl = d["trans"][::sr]
-                beta = d["betas"]
-                gender = d["gender"].astype(str)
-                if np.isnan(pose).any() or np.isinf(pose).any() or np.isnan(transl).any() or np.isinf(transl).any():
-                    continue
-                body_cmu_41 = d["marker_cmu_41"][::sr]
-                body_ssm2_67 = d["marker_ssm2_67"][::sr]
-                joints = d["joints"][::sr].reshape([-1, 22, 3])
-                transf_rotmat = d["transf_rotmat"]
-                transf_transl = d["transf_transl"]
-            m = self.max_len
-            transl, pose, body_cmu_41, body_ssm2_67, joints = transl[:m], pose[:m], body_cmu_41[:m], body_ssm2_67[:m], joints[:m]
-            _, _, marker2tarloc_n = get_target_feature(joints, body_ssm2_67, transf_rotmat, transf_transl)
-            self.data_list.append(body_feature(self.body_repr, transl, pose, joints, body_cmu_41, body_ssm2_67, marker2tarloc_n))
-            self.jts_list.append(joints)
-            self.pose_list.append(pose)
-            self.beta_list.append(beta)
-            self.transl_list.append(transl)
-            self.gender_list.append(gender)
-        if not self.data_list:
-            raise FileNotFoundError(f"no usable 120 fps primitives under {self.amass_data_path}")
+        kept = [r for r in (read_primitive(p, self.sample_rate, self.max_len, need_120fps=True) for p in self.rec_list)
+                if r is not None]
+        if not kept:
+            raise FileNotFoundError(f"no usable 120 fps primitives under {root}")
+        self.data_list = [self._feature(r, r["R"], r["T"]) for r in kept]          # also applies the pelvis quirk to joints
+        self.jts_list = [r["joints"] for r in kept]
+        stack = lambda key: np.stack([r[key] for r in kept], axis=0).astype(np.float32)
         self.data_all = np.stack(self.data_list, axis=0).astype(np.float32)        # [b,t,d]
-        self.jts_all = np.stack(self.jts_list, axis=0).astype(np.float32)          # [b,t,22,3]
+        self.jts_all = stack("joints")                                              # [b,t,22,3]
         # the reference stacks data_list here (:223), which feeds marker coordinates to the noise path as if they were
         # joint rotations; the rotations are what apply_rot_noise / the body model need
-        self.pose_all = np.stack(self.pose_list, axis=0).astype(np.float32)        # [b,t,66]
-        self.beta_all = np.stack(self.beta_list, axis=0).astype(np.float32)
-        self.transl_all = np.stack(self.transl_list, axis=0).astype(np.float32)
-        self.gender_all = np.array(self.gender_list)
+        self.pose_all, self.beta_all, self.transl_all = stack("pose"), stack("betas"), stack("transl")
+        self.gender_all = np.array([r["gender"] for r in kept])
         if to_gpu:
-            for n in ("data_all", "jts_all", "pose_all", "transl_all", "beta_all"):
-                setattr(self, n, torch.as_tensor(getattr(self, n)).to(self.device))
+            for name in ("data_all", "jts_all", "pose_all", "transl_all", "beta_all"):
+                setattr(self, name, torch.as_tensor(getattr(self, name)).to(self.device))
 
     # ---- batches ---------------------------------------------------------------------------------
     def _dev(self, x):
@@ -211,96 +204,66 @@ class BatchGeneratorAMASSCanonicalized:
             self._parser = SMPLXParser({"n_batch": self.max_len, "device": self.device, "marker_placement": "ssm2_67"})
         return self._parser
 
+    def _take(self, array, batch_size):
+        return self._dev(array[self.index_rec:self.index_rec + batch_size])
+
+    def _noisy_markers(self, i, noise):
+        """markers [t,201] of recording i after one random rotation per joint (std `noise`, constant over the frames)
+        has been composed onto its pose (:242-259)."""
+        transl, pose, betas = (self._dev(a[i]) for a in (self.transl_all, self.pose_all, self.beta_all))
+        jitter = torch.normal(mean=0.0, std=float(noise), size=pose[:1].shape, device=pose.device).expand(pose.shape)
+        pose = apply_rot_noise(pose, jitter)
+        xb = torch.cat([transl, pose, torch.zeros(pose.shape[0], 24, device=pose.device)], dim=1)
+        mk = self._get_parser().forward_smplx(betas[:10].reshape(1, 10), str(self.gender_all[i]), xb, to_numpy=False,
+                                              output_type="markers")
+        return mk.reshape(pose.shape[0], 67 * 3)
+
     def next_batch(self, batch_size=64, noise=None):
-        """[t,b,d]. With `noise` (std of a per-sequence axis-angle perturbation applied to every joint, constant over
-        the sequence) the markers are re-generated by the body model from the perturbed poses (:240-263)."""
+        """[t,b,d]. With `noise` the markers are re-generated by the body model from perturbed poses."""
         if noise is None:
-            batch = self.data_all[self.index_rec:self.index_rec + batch_size]
+            batch = self._take(self.data_all, batch_size)
             self.index_rec += batch_size
-            return self._dev(batch).permute(1, 0, 2)
-        parser = self._get_parser()
-        out, bb = [], 0
-        while self.has_next_rec():
-            if bb == batch_size:
-                break
-            i = self.index_rec
-            gender = str(self.gender_all[i])
-            transl, pose, betas = self._dev(self.transl_all[i]), self._dev(self.pose_all[i]), self._dev(self.beta_all[i])
-            rot_noise = torch.normal(mean=0.0, std=float(noise), size=pose[:1].shape, device=pose.device).expand(pose.shape)
-            pose = apply_rot_noise(pose, rot_noise)
-            t = pose.shape[0]
-            xb = torch.cat([transl, pose, torch.zeros(t, 24, device=pose.device)], dim=1)
-            mk = parser.forward_smplx(betas[:10].reshape(1, 10), gender, xb, to_numpy=False, output_type="markers")
-            out.append(mk.reshape(t, 67 * 3))
-            self.index_rec += 1
-            bb += 1
-            if self.index_rec == len(self.data_list):
-                break
-        return torch.stack(out).permute(1, 0, 2)
+            return batch.permute(1, 0, 2)
+        last = min(self.index_rec + batch_size, len(self.data_list))
+        seqs = [self._noisy_markers(i, noise) for i in range(self.index_rec, last)]
+        self.index_rec = last
+        return torch.stack(seqs).permute(1, 0, 2)
 
     def next_batch_with_jts(self, batch_size=64, noise=None):
-        d = self._dev(self.data_all[self.index_rec:self.index_rec + batch_size]).permute(1, 0, 2)
-        j = self._dev(self.jts_all[self.index_rec:self.index_rec + batch_size]).permute(1, 0, 2, 3)
+        d, j = self._take(self.data_all, batch_size), self._take(self.jts_all, batch_size)
         self.index_rec += batch_size
-        return d, j
+        return d.permute(1, 0, 2), j.permute(1, 0, 2, 3)
 
     def next_batch_genderselection(self, batch_size=64, gender="male", batch_first=True, noise=None):
         """Same-gender batch read from the files (:348-429): [betas, body_feature, transl, glorot, thetas, joints],
         each [b,t,d] (or [t,b,d]); None when fewer than batch_size sequences are left."""
-        keys = ("betas", "transl", "glorot", "thetas", "feature", "jts")
-        acc = {k: [] for k in keys}
-        bb = 0
-        while self.has_next_rec():
-            rec = self.rec_list[self.index_rec]
-            if bb == batch_size:
-                break
-            with np.load(rec) as d:
-                if str(d["gender"]) != gender:
-                    self.index_rec += 1
-                    continue
-                sr = self.sample_rate
-                transl = d["trans"][::sr]
-                pose = d["poses"][::sr, :66]
-                betas = np.tile(d["betas"][:10], (transl.shape[0], 1))
-                body_cmu_41 = d["marker_cmu_41"][::sr]
-                body_ssm2_67 = d["marker_ssm2_67"][::sr]
-                joints = d["joints"][::sr].reshape([-1, 22, 3])
-            _, _, marker2tarloc_n = get_target_feature(joints, body_ssm2_67)
-            acc["feature"].append(body_feature(self.body_repr, transl, pose, joints, body_cmu_41, body_ssm2_67, marker2tarloc_n))
-            acc["betas"].append(betas); acc["transl"].append(transl); acc["glorot"].append(pose[:, :3])
-            acc["thetas"].append(pose[:, 3:]); acc["jts"].append(joints.reshape([-1, 22 * 3]))
+        picked = []
+        while self.has_next_rec() and len(picked) < batch_size:
+            rec = read_primitive(self.rec_list[self.index_rec], self.sample_rate, check_finite=False)   # unfiltered, as :372-381
             self.index_rec += 1
-            bb += 1
-            if self.index_rec == len(self.data_list):
-                break
-        if len(acc["betas"]) < batch_size:
+            if rec["gender"] == gender:
+                picked.append(rec)
+        if len(picked) < batch_size:
             return None
-        ax = 0 if batch_first else 1
-        st = {k: self._dev(np.stack(v, axis=ax).astype(np.float32)) for k, v in acc.items()}
-        return [st["betas"], st["feature"], st["transl"], st["glorot"], st["thetas"], st["jts"]]
+        cols = {"betas": lambda r: np.tile(r["betas"][:10], (r["transl"].shape[0], 1)), "feature": self._feature,
+                "transl": lambda r: r["transl"], "glorot": lambda r: r["pose"][:, :3], "thetas": lambda r: r["pose"][:, 3:],
+                "jts": lambda r: r["joints"].reshape([-1, 22 * 3])}
+        axis = 0 if batch_first else 1
+        out = {k: self._dev(np.stack([f(r) for r in picked], axis=axis).astype(np.float32)) for k, f in cols.items()}
+        return [out[k] for k in ("betas", "feature", "transl", "glorot", "thetas", "jts")]
 
     def next_sequence(self):
         """One recording with its meta information (:287-345); None for recordings with NaN / inf parameters."""
-        rec = self.rec_list[self.index_rec]
-        with np.load(rec) as d:
-            sr = self.sample_rate
-            pose = d["poses"][::sr, :66]
-            transl = d["trans"][::sr]
-            gender = d["gender"]
-            if np.isnan(pose).any() or np.isinf(pose).any() or np.isnan(transl).any() or np.isinf(transl).any():
-                return None
-            betas = d["betas"][:10]
-            body_cmu_41 = d["marker_cmu_41"][::sr]
-            body_ssm2_67 = d["marker_ssm2_67"][::sr]
-            joints = d["joints"][::sr].reshape([-1, 22, 3])
-            transf_rotmat = d["transf_rotmat"]
-            transf_transl = d["transf_transl"]
-        _, _, marker2tarloc_n = get_target_feature(joints, body_ssm2_67)
-        feat = body_feature(self.body_repr, transl, pose, joints, body_cmu_41, body_ssm2_67, marker2tarloc_n)
+        path = self.rec_list[self.index_rec]
+        rec = read_primitive(path, self.sample_rate)
+        if rec is None:
+            return None
         self.index_rec += 1
-        return {"betas": betas, "gender": gender, "transl": transl, "glorot": pose[:, :3], "poses": pose[:, 3:],
-                "body_feature": feat, "transf_rotmat": transf_rotmat, "transf_transl": transf_transl,
-                "pelvis_loc": joints[:, 0, :]}
+        with np.load(path) as f:
+            gender = f["gender"]
+        return {"betas": rec["betas"][:10], "gender": gender, "transl": rec["transl"], "glorot": rec["pose"][:, :3],
+                "poses": rec["pose"][:, 3:], "body_feature": self._feature(rec), "transf_rotmat": rec["R"],
+                "transf_transl": rec["T"], "pelvis_loc": rec["joints"][:, 0, :]}
 
     def get_all_data(self):
         return torch.as_tensor(self.data_all, dtype=torch.float32).permute(1, 0, 2)

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from egogen_b200.batch_gen_amass import (PRIMITIVE_KEYS, BatchGeneratorAMASSCanonicalized, body_feature,
+from egogen_b200.primitive_batches import (PRIMITIVE_KEYS, BatchGeneratorAMASSCanonicalized, body_feature,
                                           get_target_feature, save_primitive)
 
 

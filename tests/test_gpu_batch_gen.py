@@ -66,7 +66,7 @@ def test_frame_helpers_match_oracle(dev, parsers, orc):
 
 
 def test_canonicalize_subsequence_matches_oracle(parsers, orc):
-    from egogen_b200.batch_gen_amass import PRIMITIVE_KEYS, canonicalize_subsequence
+    from egogen_b200.primitive_batches import PRIMITIVE_KEYS, canonicalize_subsequence
     transl, pose, betas = _motion(4, 200)
     assert canonicalize_subsequence(parsers, betas, transl, pose, 150, 210) is None      # recording too short
     out = canonicalize_subsequence(parsers, betas, transl, pose, 30, 90)
@@ -92,7 +92,7 @@ def test_canonicalize_subsequence_matches_oracle(parsers, orc):
 
 
 def test_noise_augmented_batches(dev, parsers, tmp_path):
-    from egogen_b200.batch_gen_amass import BatchGeneratorAMASSCanonicalized, canonicalize_subsequence, save_primitive
+    from egogen_b200.primitive_batches import BatchGeneratorAMASSCanonicalized, canonicalize_subsequence, save_primitive
     for i in range(5):
         transl, pose, betas = _motion(10 + i, 100)
         save_primitive(str(tmp_path / "canon" / "s" / f"subseq_{i:05d}.npz"), canonicalize_subsequence(parsers, betas, transl, pose, 0, 60))
