@@ -38,10 +38,11 @@ constexpr int XF_WARPS = 8;                          // transform + epilogue war
 constexpr int THREADS = 64 + XF_WARPS * 32;          // 320
 constexpr int XF_THREADS = XF_WARPS * 32;
 // geometry that depends on the tile width
-template <int BN>
+template <int BN, bool DEEP = false>
 struct Geo {
   static constexpr int B_BYTES = BN * BK * 4;                   // 8 / 16 KB
-  static constexpr int STAGES = (BN == 64 || EG_GEMM_TC_STAGES < 3) ? EG_GEMM_TC_STAGES : 3;
+  // DEEP: 4 (BN = 64) / 3 (BN = 128) stages, opt-in per launch through EG_GEMM_TC_DEEP
+  static constexpr int STAGES = DEEP ? (BN == 64 ? 4 : 3) : ((BN == 64 || EG_GEMM_TC_STAGES < 3) ? EG_GEMM_TC_STAGES : 3);
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // raw(hi) A, raw(hi) B, lo A, lo B = 48 / 64 KB
   static constexpr int TMEM_COLS = BN;
   static constexpr int EPI_COLS = BN / (XF_WARPS / 4);          // columns per epilogue thread (two warps share a TMEM lane quarter)
@@ -157,11 +158,11 @@ struct Params {
 
 // A_MN / B_MN: the operand is stored with its M / N index contiguous (dW = dY^T X has both, dX = dY W has B) instead of
 // its k index (nn.Linear forward). MN-major tiles are staged as 32-wide chunks, one TMA box [32 k][32 mn] each.
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, bool DEEP>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
   namespace cg = cooperative_groups;
-  using G = Geo<BN>;
+  using G = Geo<BN, DEEP>;
   constexpr int STAGES = G::STAGES, B_BYTES = G::B_BYTES, STAGE_BYTES = G::STAGE_BYTES, TMEM_COLS = G::TMEM_COLS, EPI_COLS = G::EPI_COLS,
                 RED_LD = G::RED_LD, OFF_BARS = G::OFF_BARS;
   extern __shared__ unsigned char smem_dyn[];
@@ -400,12 +401,14 @@ void gemm_tc_set_enabled(int on) { g_gemm_tc_enabled = on ? 1 : 0; }
 template <bool A_MN, bool B_MN, int BN>
 static int launch_variant(const GemmArgs& g, cudaStream_t st) {
   using namespace gtc;
-  constexpr int SMEM_BYTES = Geo<BN>::SMEM_BYTES;
+  constexpr int SMEM_BYTES = Geo<BN, false>::SMEM_BYTES, SMEM_DEEP = Geo<BN, true>::SMEM_BYTES;
   static bool attr_done = false;
   static int max_clusters[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};     // indexed by cluster size
-  auto kernel = gemm_tc_kernel<A_MN, B_MN, BN>;
+  auto kernel = gemm_tc_kernel<A_MN, B_MN, BN, false>;
+  auto kernel_deep = gemm_tc_kernel<A_MN, B_MN, BN, true>;
   if (!attr_done) {
     EG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EG_CUDA_CHECK(cudaFuncSetAttribute(kernel_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DEEP));
     attr_done = true;
   }
   CUtensorMap mapA, mapB;
@@ -440,7 +443,11 @@ static int launch_variant(const GemmArgs& g, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, sk);
   cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
+  // deeper operand ring per launch (EG_GEMM_TC_DEEP, default 0 = never): 1 = always, 2 = forward layout only,
+  // 3 = launches that leave at least half the SMs free for the next kernel's programmatic-dependent prologue
+  static const int deep_mode = getenv("EG_GEMM_TC_DEEP") ? atoi(getenv("EG_GEMM_TC_DEEP")) : 0;
+  const bool deep = deep_mode == 1 || (deep_mode == 2 && !A_MN && !B_MN) || (deep_mode == 3 && tiles * sk <= kNumSMs / 2);
+  cfg.dynamicSmemBytes = deep ? SMEM_DEEP : SMEM_BYTES;
   cfg.stream = st;
   static const bool pdl = !(getenv("EG_GEMM_TC_PDL") != nullptr && getenv("EG_GEMM_TC_PDL")[0] == '0');
   cudaLaunchAttribute at[2];
@@ -449,7 +456,7 @@ static int launch_variant(const GemmArgs& g, cudaStream_t st) {
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, mapA, mapB, p);
+  cudaError_t e = deep ? cudaLaunchKernelEx(&cfg, kernel_deep, mapA, mapB, p) : cudaLaunchKernelEx(&cfg, kernel, mapA, mapB, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   EG_CUDA_CHECK(e);
   return EG_OK;
