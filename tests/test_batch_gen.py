@@ -22,15 +22,22 @@ def _primitive(tag, T=30, gender="male", fps=120, nan=False):
     return d
 
 
+def build_dataset(tmp):
+    """10 usable recordings in two subsets (2 female), one 60 fps and one NaN recording; shared with
+    tests/golden/gen_primitive_batches_golden.py, which runs the reference's class on the same files."""
+    import os
+    root = os.path.join(str(tmp), "canon")
+    for i in range(10):
+        save_primitive(os.path.join(root, "setA" if i < 6 else "setB", f"subseq_{i:05d}.npz"),
+                       _primitive(i + 1, gender="female" if i in (2, 7) else "male"))
+    save_primitive(os.path.join(root, "setA", "subseq_slow.npz"), _primitive(50, fps=60))
+    save_primitive(os.path.join(root, "setA", "subseq_nan.npz"), _primitive(51, nan=True))
+    return root
+
+
 @pytest.fixture()
 def dataset(tmp_path):
-    root = tmp_path / "canon"
-    for i in range(10):
-        save_primitive(str(root / ("setA" if i < 6 else "setB") / f"subseq_{i:05d}.npz"),
-                       _primitive(i + 1, gender="female" if i in (2, 7) else "male"))
-    save_primitive(str(root / "setA" / "subseq_slow.npz"), _primitive(50, fps=60))
-    save_primitive(str(root / "setA" / "subseq_nan.npz"), _primitive(51, nan=True))
-    return str(root)
+    return build_dataset(tmp_path)
 
 
 def test_schema_roundtrip(tmp_path):
@@ -116,3 +123,68 @@ def test_genderselection_and_next_sequence(dataset):
     s = gen.next_sequence()
     assert set(s) == {"betas", "gender", "transl", "glorot", "poses", "body_feature", "transf_rotmat", "transf_transl", "pelvis_loc"}
     assert s["betas"].shape == (10,) and s["poses"].shape == (30, 63) and s["pelvis_loc"].shape == (30, 3) and gen.index_rec == 1
+
+
+# ---- parity with the reference's own class (tests/golden/primitive_batches_golden.npz) ------------------------------
+@pytest.fixture(scope="module")
+def ref_golden(golden_dir):
+    import os
+    return np.load(os.path.join(golden_dir, "primitive_batches_golden.npz"))
+
+
+def _by_tag(gen):
+    return np.argsort(np.asarray(gen.jts_all)[:, 0, 1, 1])
+
+
+def test_get_rec_list_matches_reference_class(dataset, ref_golden):
+    """Every array the reference's get_rec_list builds (all body_repr, incl. the in-place pelvis shift that leaks into
+    jts_all), record by record on the same files. cmu_41 is where the reference itself raises (:199)."""
+    g = ref_golden
+    for repr_ in ["ssm2_67", "joints", "smpl_params", "ssm2_67_marker2tarloc", "bone_transform"]:
+        gen = BatchGeneratorAMASSCanonicalized(dataset, sample_rate=1, body_repr=repr_, device="cpu")
+        gen.get_rec_list(shuffle_seed=11)                       # any order: records are matched by their tag
+        o = _by_tag(gen)
+        mine = gen.data_all[o]
+        if repr_ == "ssm2_67_marker2tarloc":
+            assert np.array_equal(mine[..., :201], g["data_ssm2_67"]) and int(g["tarloc_head_is_ssm2_67"]) == 1
+            mine = mine[..., 201:]
+        assert mine.shape == g[f"data_{repr_}"].shape, repr_
+        assert np.array_equal(mine, g[f"data_{repr_}"]), repr_
+        if repr_ == "ssm2_67":
+            assert np.array_equal(gen.jts_all[o][:, 0, 1, 1], g["tags"])
+            assert np.array_equal(gen.jts_all[o], g["jts_all"])
+            assert np.array_equal(gen.beta_all[o], g["beta_all"]) and np.array_equal(gen.transl_all[o], g["transl_all"])
+            assert gen.gender_all[o].tolist() == g["gender_all"].tolist()
+            assert np.array_equal(gen.get_all_data().numpy(), gen.data_all.transpose(1, 0, 2)) and int(g["all_data_is_data_all_tmajor"]) == 1
+    assert int(g["cmu_41_raises"]) == 1
+    gen3 = BatchGeneratorAMASSCanonicalized(dataset, amass_subset_name=["setB"], sample_rate=3, body_repr="ssm2_67", device="cpu")
+    gen3.get_rec_list(shuffle_seed=5)
+    assert np.array_equal(gen3.data_all[_by_tag(gen3)], g["data_stride3"])
+
+
+def test_genderselection_and_next_sequence_match_reference_class(dataset, ref_golden):
+    g = ref_golden
+    gen = BatchGeneratorAMASSCanonicalized(dataset, amass_subset_name=["setB"], sample_rate=1, body_repr="ssm2_67", device="cpu")
+    gen.get_rec_list(shuffle_seed=1)
+    gen.rec_list = sorted(gen.rec_list); gen.index_rec = 0      # the fixture was generated on the sorted file order
+    sel = gen.next_batch_genderselection(3, "male")
+    for k, t in zip(["betas", "feature", "transl", "glorot", "thetas", "jts"], sel):
+        assert np.array_equal(t.numpy(), g[f"sel_{k}"]), k
+    assert gen.index_rec == int(g["sel_index_after"])
+    assert (gen.next_batch_genderselection(3, "male") is None) == bool(g["sel_second_is_none"])
+    gen.index_rec = 0
+    tm = gen.next_batch_genderselection(2, "male", batch_first=False)[1].numpy()
+    assert np.array_equal(tm, g["sel_feature"][:2].transpose(1, 0, 2)) and int(g["sel_tmajor_is_transpose"]) == 1
+    gen.index_rec = 0
+    seq = gen.next_sequence()
+    for k in ["betas", "transl", "glorot", "poses", "body_feature", "transf_rotmat", "transf_transl", "pelvis_loc"]:
+        assert np.array_equal(np.asarray(seq[k]), g[f"seq_{k}"]), k
+    assert str(seq["gender"]) == str(g["seq_gender"])
+
+
+def test_target_feature_matches_reference_function(ref_golden):
+    g = ref_golden
+    J = g["tf_joints"].copy()
+    v, w, l = get_target_feature(J, g["tf_markers"], np.eye(3), g["tf_transl"])
+    assert np.array_equal(v, g["tf_vec"]) and np.array_equal(w, g["tf_wpath"]) and np.array_equal(l, g["tf_locn"])
+    assert np.array_equal(J, g["tf_joints_after"]) and not np.array_equal(J, g["tf_joints"])
