@@ -75,3 +75,13 @@ def combo_loss_one(pred, reg, lbs, X, Y, betas_Y, eps, w_rec=1.0, w_td=3.0, w_kl
     loss_h = torch.mean(Yb[:, 69:] ** 2)
     loss = loss_marker + loss_reg + w_hpose * loss_h
     return loss, [loss_rec, kld, loss_reg, loss_h], Yb.view(nt, nb, -1)
+
+
+def regressor_loss(reg, lbs, marker_ref, betas, w_hpose=0.01):
+    """GAMMARegressorTrainOP: xb = model(marker_ref, betas); calc_loss (models_GAMMA_primitive.py:617-633).
+    Returns (xb [M,93], loss, loss_marker, loss_hpose)."""
+    xb = reg(marker_ref, betas)
+    pred = lbs.forward_smplx(betas, "male", xb, "markers").reshape(marker_ref.shape)
+    loss_marker = F.l1_loss(marker_ref, pred)
+    loss_hpose = torch.mean(xb[:, 69:] ** 2)
+    return xb, loss_marker + w_hpose * loss_hpose, loss_marker, loss_hpose

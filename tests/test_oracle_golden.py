@@ -72,3 +72,78 @@ def test_coordinate_extractor_matches_reference(golden_dir):
     assert torch.allclose(R2, _t(g["R_loco"]), atol=1e-7)
     # model-free invariant of the reference fixture subseq_00343.npz:
     assert torch.allclose(R2[0], torch.eye(3), atol=1e-3) and T2.abs().max() < 1e-3
+
+
+# ---- training objectives: the reference's own train ops (tests/golden/gen_train_golden.py) -----------------------------
+def _gradnorms(module):
+    return np.array([p.grad.norm().item() if p.grad is not None else -1.0 for p in module.parameters()])
+
+
+def _regressor_weights(reg, seed):
+    from egogen_b200.assets import fill_params_
+    fill_params_(reg, seed=seed, w_gain=0.5)
+    with torch.no_grad():
+        gg = torch.Generator().manual_seed(seed)
+        reg.pnet.out_fc.bias[3:135] = torch.tensor([1.0, 0.0, 0.0, 1.0, 0.0, 0.0]).repeat(22) + torch.randn(132, generator=gg) * 0.3
+
+
+def _close(a, b, rtol):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), 1e-6) + 1e-9)
+
+
+def test_cvae_training_oracle_matches_reference_trainop(golden_dir):
+    """oracle.cvae_train.primitive_loss / rollout_loss vs GAMMAPrimitiveVAETrainOP.calc_loss / calc_loss_rollout run on
+    the reference's own class: loss, [loss, rec, kld], every parameter's gradient norm."""
+    from egogen_b200.assets import fill_params_
+    from oracle import cvae_train as oc, nets
+    g = np.load(os.path.join(golden_dir, "train_golden.npz"))
+    t = lambda k: torch.as_tensor(g[k])
+    pred = nets.PredictorOracle().train()
+    fill_params_(pred, seed=41)
+    loss, rec, kld, _ = oc.primitive_loss(pred, t("p_data")[:2], t("p_data")[2:], t("p_eps"))
+    loss.backward()
+    assert _close([loss.item(), rec.item(), kld.item()], g["p_info"], 1e-5) and _close(loss.item(), g["p_loss"], 1e-5)
+    assert _close(_gradnorms(pred), g["p_gradnorm"], 2e-4)
+    assert np.allclose(pred.d_out.bias.grad.numpy(), g["p_grad_dout_bias"], rtol=1e-4, atol=1e-7)
+    pred.zero_grad()
+    loss = oc.rollout_loss(pred, t("r_markers"), t("r_jts"), list(t("r_eps")))
+    loss.backward()
+    assert _close(loss.item(), g["r_loss"], 1e-5) and _close(loss.item(), g["r_info"][0], 1e-5)
+    assert _close(_gradnorms(pred), g["r_gradnorm"], 5e-4)
+
+
+def test_regressor_training_oracle_matches_reference_trainop(golden_dir, smplx_model):
+    from egogen_b200 import assets
+    from oracle import cvae_train as oc, nets
+    from oracle.smplx_lbs import SMPLXParserOracle
+    g = np.load(os.path.join(golden_dir, "train_golden.npz"))
+    reg = nets.RegressorOracle().train()
+    _regressor_weights(reg, 3)
+    lbs = SMPLXParserOracle(smplx_model, marker=assets.marker_ids())
+    xb, loss, lm, lh = oc.regressor_loss(reg, lbs, torch.as_tensor(g["g_marker_ref"]), torch.as_tensor(g["g_betas"]))
+    loss.backward()
+    assert np.allclose(xb.detach().numpy(), g["g_xb"], rtol=1e-5, atol=1e-6)
+    assert _close(loss.item(), g["g_loss"], 1e-5) and _close([lm.item(), lh.item()], g["g_items"], 1e-5)
+    assert _close(_gradnorms(reg), g["g_gradnorm"], 2e-4)
+    assert np.allclose(reg.pnet.out_fc.bias.grad.numpy(), g["g_grad_out_bias"], rtol=1e-4, atol=1e-8)
+
+
+def test_combo_oracle_matches_reference_trainop(golden_dir, smplx_model):
+    from egogen_b200 import assets
+    from egogen_b200.assets import fill_params_
+    from oracle import cvae_train as oc, nets
+    from oracle.smplx_lbs import SMPLXParserOracle
+    g = np.load(os.path.join(golden_dir, "train_golden.npz"))
+    lbs = SMPLXParserOracle(smplx_model, marker=assets.marker_ids())
+    data, betas, eps = torch.as_tensor(g["p_data"]), torch.as_tensor(g["c_betas"]), torch.as_tensor(g["c_eps"])
+    for sched in (0, 1):
+        pred, reg = nets.PredictorOracle().train(), nets.RegressorOracle().train()
+        fill_params_(pred, seed=41)
+        _regressor_weights(reg, 5)
+        loss, items, _ = oc.combo_loss_one(pred, reg, lbs, data[:2], data[2:], betas[2:], eps, scheduled_sampling=bool(sched))
+        loss.backward()
+        assert _close(loss.item(), g[f"c{sched}_loss"], 1e-5), sched
+        assert _close([x.item() for x in items], g[f"c{sched}_info"], 1e-5), sched
+        assert _close(_gradnorms(pred), g[f"c{sched}_gradnorm"], 5e-4), sched
+        assert int(g[f"c{sched}_reg_has_grad"]) == 1        # autograd reaches the regressor too; only the predictor is stepped
