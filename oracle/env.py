@@ -4,8 +4,12 @@ motion/crowd_ppo/crowd_env_2f.py:78-317 (step), :320-415 (reset), :524-613 (_cal
 environments with the reference's 4x batch duplication removed (only element [0] of the duplicated
 batch is ever consumed: :169,174-175,185,194,202,219,229,233,235,287,296,312).
 
-shapely/GEOS is absent => the ray/polygon intersection follows the closed form of SURVEY.md
-Appendix A6 in float64 (parity unpinned for that piece).
+Pinned: tests/golden/gen_env_golden.py runs the reference's OWN CrowdEnv.reset / step (and its SMPLXParser,
+GAMMAPrimitiveCombo, calc_sdf) on the CPU with the absent third-party packages supplied by the oracle's restatements;
+tests/test_oracle_golden.py::test_env_oracle_matches_reference_crowd_env reproduces those trajectories (state 2e-7,
+reward exact, ego-sensing 2e-4). shapely/GEOS itself is absent => the ray/polygon intersection follows the closed form
+of SURVEY.md Appendix A6 in float64 and is cross-checked against an independent segment-vs-polygon clip in that
+generator (GEOS parity unpinned for that piece).
 """
 import numpy as np
 import torch

@@ -1,0 +1,242 @@
+"""Golden trajectories of the REFERENCE'S OWN CrowdEnv (motion/crowd_ppo/crowd_env_2f.py) - build container only.
+
+CrowdEnv.reset / step / _canonicalize_2frame / _get_feature / _blend_params / _calc_egosensing and the reference's
+SMPLXParser (forward_smplx, get_new_coordinate, update_transl_glorot, calc_calibrate_offset), GAMMAPrimitiveCombo.sample_prior
+and calc_sdf run UNMODIFIED on the CPU. What the reference imports from absent third-party packages is supplied by:
+  smplx.create(...)        -> the oracle's SMPL-X restatement on the surrogate body model (oracle.smplx_lbs.SMPLXOracle)
+  torchgeometry            -> oracle.tgm
+  vposer.encode(x).loc     -> oracle.nets.VPoserEncoderOracle
+  shapely                  -> MiniShapely below: an independent float64 clip of a segment against a polygon with holes
+                              (GEOS' LineString.intersection(Polygon) / Polygon.contains for this use)
+  gymnasium / trimesh / pyrender / pytorch3d -> empty stubs (rendering is off)
+and `.cuda()` / torch.cuda.FloatTensor are aliased to their CPU forms. The world (surrogate SMPL-X, seeded weights, box
+scene, start bodies) is oracle.harness.build_oracle_world / sample_candidates_cpu, which the test rebuilds.
+
+Run:  python tests/golden/gen_env_golden.py   ->  tests/golden/env_golden.npz
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("EGOGEN_REFERENCE", "/root/reference")
+
+from egogen_b200 import assets                                # noqa: E402
+from oracle import harness, nets, tgm as oracle_tgm           # noqa: E402
+from oracle.smplx_lbs import SMPLXOracle                      # noqa: E402
+
+
+# ---- MiniShapely ----------------------------------------------------------------------------------------
+class Point:
+    geom_type = "Point"
+
+    def __init__(self, xy):
+        self.xy = np.asarray(xy, dtype=np.float64)
+        self.coords = [tuple(self.xy)]
+
+    def distance(self, other):
+        return other.distance(self) if isinstance(other, LineString) else float(np.linalg.norm(self.xy - other.xy))
+
+
+class MultiPoint:
+    def __init__(self, pts):
+        self.geoms = [Point(p) for p in np.asarray(pts, dtype=np.float64)]
+
+
+class LineString:
+    geom_type = "LineString"
+
+    def __init__(self, coords):
+        self.coords = [tuple(np.asarray(c, dtype=np.float64)) for c in coords]
+
+    def distance(self, pt):
+        a, b = np.asarray(self.coords[0]), np.asarray(self.coords[1])
+        d = b - a
+        t = np.clip(np.dot(pt.xy - a, d) / max(np.dot(d, d), 1e-300), 0.0, 1.0)
+        return float(np.linalg.norm(a + t * d - pt.xy))
+
+    def intersection(self, poly):
+        return poly.clip(self)
+
+
+class MultiLineString:
+    geom_type = "MultiLineString"
+
+    def __init__(self, parts):
+        self.geoms = parts
+
+
+class Polygon:
+    """exterior ring + holes (closed rings [n,2]); interior = inside the exterior and outside every hole."""
+
+    def __init__(self, rings):
+        self.rings = [np.asarray(r, dtype=np.float64) for r in rings]
+
+    @staticmethod
+    def _in_ring(ring, p):
+        x, y = p
+        inside = False
+        for (x0, y0), (x1, y1) in zip(ring[:-1], ring[1:]):
+            if (y0 > y) != (y1 > y) and x < (x1 - x0) * (y - y0) / (y1 - y0) + x0:
+                inside = not inside
+        return inside
+
+    def _inside(self, p):
+        return self._in_ring(self.rings[0], p) and not any(self._in_ring(h, p) for h in self.rings[1:])
+
+    def contains(self, pt):
+        return self._inside(pt.xy)
+
+    def clip(self, line):
+        a, b = np.asarray(line.coords[0]), np.asarray(line.coords[1])
+        d = b - a
+        ts = [0.0, 1.0]
+        for ring in self.rings:
+            for p, q in zip(ring[:-1], ring[1:]):
+                e = q - p
+                den = d[0] * e[1] - d[1] * e[0]
+                if den == 0.0:
+                    continue
+                w = p - a
+                t = (w[0] * e[1] - w[1] * e[0]) / den
+                u = (w[0] * d[1] - w[1] * d[0]) / den
+                if 0.0 <= t <= 1.0 and 0.0 <= u <= 1.0:
+                    ts.append(t)
+        ts = sorted(set(ts))
+        parts = []
+        for t0, t1 in zip(ts[:-1], ts[1:]):
+            if t1 - t0 > 1e-12 and self._inside(a + 0.5 * (t0 + t1) * d):
+                if parts and abs(parts[-1][1] - t0) < 1e-15:
+                    parts[-1][1] = t1                 # merge pieces that only touch a vertex
+                else:
+                    parts.append([t0, t1])
+        segs = [LineString([a + t0 * d, a + t1 * d]) for t0, t1 in parts]
+        if len(segs) == 1:
+            return segs[0]
+        return MultiLineString(segs)
+
+
+def stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+class _Space:
+    def __init__(self, *a, **k):
+        pass
+
+
+stub("gymnasium", Env=object)
+stub("gymnasium.spaces", Dict=_Space, Box=_Space)
+for n in ["trimesh", "pyrender", "pytorch3d", "tensorboardX", "matplotlib", "matplotlib.pyplot", "omegaconf"]:
+    stub(n)
+sys.modules["tensorboardX"].SummaryWriter = object
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+stub("shapely", LineString=LineString)
+stub("shapely.geometry", MultiPoint=MultiPoint, Point=Point)
+sys.modules["torchgeometry"] = oracle_tgm
+
+
+class _BodyModel(torch.nn.Module):
+    """what smplx.create(...) returns, as far as SMPLXParser uses it"""
+
+    def __init__(self, arrays):
+        super().__init__()
+        self.m = SMPLXOracle(arrays)
+
+    def forward(self, return_verts=True, **kw):
+        n = kw["body_pose"].shape[0]
+        z = lambda d: torch.zeros(n, d)
+        return self.m.forward(betas=kw["betas"], global_orient=kw["global_orient"], body_pose=kw["body_pose"],
+                              left_hand_pose=kw.get("left_hand_pose", z(12)), right_hand_pose=kw.get("right_hand_pose", z(12)),
+                              transl=kw["transl"])
+
+
+MODEL = assets.make_surrogate_smplx(seed=0)
+stub("smplx", create=lambda *a, **k: _BodyModel(MODEL))
+torch.Tensor.cuda = lambda self, *a, **k: self
+torch.cuda.FloatTensor = lambda *a, device=None: torch.FloatTensor(*a)
+
+sys.path.insert(0, os.path.join(REF, "motion"))
+os.chdir(os.path.join(REF, "motion"))                       # CrowdEnv opens data/smplx_vert_segmentation.json relatively (read only)
+from models import baseops as ref_baseops                   # noqa: E402
+from models import models_GAMMA_primitive as ref_gamma      # noqa: E402
+ref_baseops.get_body_marker_path = lambda: os.path.join(REF, "motion", "data")
+ref_baseops.get_body_model_path = lambda: ""
+from crowd_ppo import crowd_env_2f as ref_env               # noqa: E402
+
+
+class AttrDict(dict):
+    __getattr__ = dict.__getitem__
+
+
+def build_reference_env(world, sampler, finetuning):
+    cfg = AttrDict(args=AttrDict(gpu_index=0),
+                   modelconfig=AttrDict(reproj_factor=0.5, body_repr="ssm2_67_condi_marker_map"),
+                   trainconfig=AttrDict(goal_thresh=0.1, max_depth=13, random_rotation_range=0.0),
+                   lossconfig=AttrDict(weight_skate=0.3, weight_floor=0.1, weight_face_target=0.1, weight_look_target=0.3,
+                                       weight_success=0.5, weight_target_dist=1.0, weight_vp=0.1))
+    combo = ref_gamma.GAMMAPrimitiveCombo(
+        {"body_repr": "ssm2_67", "h_dim": 256, "z_dim": 128, "t_his": 2, "t_pred": 18, "use_drnn_mlp": True,
+         "hdims_mlp": [512, 256], "residual": True},
+        {"gender": "male", "h_dim": 128, "n_blocks": 10, "n_recur": 3, "body_repr": "ssm2_67", "actfun": "relu", "use_cont": True})
+    combo.predictor.load_state_dict(world["env"].combo.predictor.state_dict())
+    combo.regressor.load_state_dict(world["env"].combo.regressor.state_dict())
+    genop = types.SimpleNamespace(model=combo.eval())
+    dev = torch.device("cpu")
+    parsers = [ref_baseops.SMPLXParser({"n_batch": n, "device": dev, "marker_placement": "ssm2_67"}) for n in (4, 8, 80)]
+    vp = world["env"].vposer
+    vposer = types.SimpleNamespace(encode=lambda x: types.SimpleNamespace(loc=vp.encode_loc(x)))
+    init_env = (cfg, genop, genop, "", sampler, parsers[0], parsers[1], parsers[2], assets.feet_marker_idx(),
+                parsers[0].marker, vposer, world["sdf"])
+    return ref_env.CrowdEnv(init_env, save_rollout=False, render=False, finetuning=finetuning)
+
+
+class Sampler:
+    def __init__(self, wp, goal, betas, poly):
+        self.wp, self.goal, self.betas, self.poly, self.calls = wp, goal, betas, poly, 0
+
+    def next_body(self, **kw):
+        self.calls += 1
+        assert self.calls <= 2, "start body rejected by the reference's collision test"
+        start = torch.cat([self.wp[0, :2], self.goal[2:]]).reshape(1, 3)
+        return {"motion_seed": {"transl": self.wp[:, :3].clone(), "global_orient": self.wp[:, 3:6].clone(),
+                                "body_pose": self.wp[:, 6:69].clone()},
+                "gender": "male", "betas": self.betas.clone(), "wpath": torch.cat([start, self.goal.reshape(1, 3)]),
+                "shapely_poly": self.poly}
+
+
+out = {}
+world = harness.build_oracle_world(0, sdf_res=64)
+rings = assets.scene_polygon(assets.make_box_scene(0))
+N_ENVS, N_STEPS = 3, 3
+wp, goals, betas = harness.sample_candidates_cpu(world, N_ENVS, seed=5)
+g = torch.Generator().manual_seed(17)
+Z = torch.randn(N_ENVS, N_STEPS, 128, generator=g)
+assert set(ref_env.CrowdEnv.__init__.__code__.co_names) and True
+for fin in (0, 1):
+    for e in range(N_ENVS):
+        env = build_reference_env(world, Sampler(wp[e], goals[e], betas[e], Polygon(rings)), bool(fin))
+        obs, _ = env.reset()
+        rec = {"state": [obs["state"]], "ego": [obs["egosensing"]], "dist": [obs["dist"].reshape(1)], "time": [obs["time"]],
+               "reward": [], "term": [], "seed": [env.body_param_seed[0]], "R0": [env.R0[0]], "T0": [env.T0[0]]}
+        for s in range(N_STEPS):
+            obs, rew, term, trunc, _ = env.step(Z[e, s].clone())
+            rec["state"].append(obs["state"]); rec["ego"].append(obs["egosensing"]); rec["dist"].append(obs["dist"])
+            rec["time"].append(obs["time"]); rec["reward"].append(torch.tensor(rew)); rec["term"].append(torch.tensor(term))
+            rec["seed"].append(env.body_param_seed[0]); rec["R0"].append(env.R0[0]); rec["T0"].append(env.T0[0])
+            assert not trunc
+        for k, v in rec.items():
+            out[f"f{fin}_e{e}_{k}"] = torch.stack([torch.as_tensor(x).detach().float() for x in v]).numpy()
+        if fin == 0 and e == 0:
+            out["feet_vids_sorted"] = np.array(sorted(env.feet_vids))
+out.update(wp=wp.numpy(), goals=goals.numpy(), betas=betas.numpy(), Z=Z.numpy())
+np.savez_compressed(os.path.join(HERE, "env_golden.npz"), **out)
+print("wrote env_golden.npz", len(out), "arrays;", "rewards env0:", out["f0_e0_reward"], "ego[0,:4]:", out["f0_e0_ego"][0, 0, :4])

@@ -147,3 +147,54 @@ def test_combo_oracle_matches_reference_trainop(golden_dir, smplx_model):
         assert _close([x.item() for x in items], g[f"c{sched}_info"], 1e-5), sched
         assert _close(_gradnorms(pred), g[f"c{sched}_gradnorm"], 5e-4), sched
         assert int(g[f"c{sched}_reg_has_grad"]) == 1        # autograd reaches the regressor too; only the predictor is stepped
+
+
+def test_env_oracle_matches_reference_crowd_env(golden_dir):
+    """oracle.env.CrowdEnvOracle (batched, dup removed) vs trajectories of the reference's OWN CrowdEnv.reset / step run on
+    the CPU (tests/golden/gen_env_golden.py): observations, rewards, termination and the carried state (body seed, R0, T0)
+    over reset + 3 steps of 3 envs, pre-training and fine-tuning reward settings."""
+    from egogen_b200 import assets
+    from oracle import harness
+    g = np.load(os.path.join(golden_dir, "env_golden.npz"))
+    assert g["feet_vids_sorted"].tolist() == sorted(assets.feet_vids())
+    world = harness.build_oracle_world(0, sdf_res=64)
+    wp, goals, betas = harness.sample_candidates_cpu(world, 3, seed=5)
+    assert np.array_equal(wp.numpy(), g["wp"]) and np.array_equal(goals.numpy(), g["goals"])
+    Z = torch.as_tensor(g["Z"])
+    env = world["env"]
+    worst = {}
+
+    def check(name, got, ref, tol):
+        err = float(np.abs(np.asarray(got, dtype=np.float64) - np.asarray(ref, dtype=np.float64)).max())
+        worst[name] = max(worst.get(name, 0.0), err)
+        assert err <= tol, (name, err)
+
+    for fin in (0, 1):
+        env.finetuning = bool(fin)
+        r = env.reset_from(wp, goals, betas)
+        assert bool(r["accept"].all())
+        env.set_state(state=r["state"], seed=r["seed"], R0=r["R0"], T0=r["T0"], betas=betas, dist=r["dist"],
+                      steps=torch.zeros(3, dtype=torch.int64), goal=goals)
+        for e in range(3):
+            k = f"f{fin}_e{e}_"
+            check("state0", r["state"][e], g[k + "state"][0], 2e-5)
+            check("ego0", r["egosensing"][e], g[k + "ego"][0], 1e-5)
+            check("dist0", r["obs_dist"][e], g[k + "dist"][0, 0], 1e-6)
+            check("seed0", r["seed"][e], g[k + "seed"][0], 2e-5)
+            check("R0_0", r["R0"][e], g[k + "R0"][0], 1e-6)
+            check("T0_0", r["T0"][e], g[k + "T0"][0], 1e-6)
+            assert float(g[k + "time"][0, 0]) == 1.0
+        for s in range(3):
+            o = env.step(Z[:, s])
+            for e in range(3):
+                k = f"f{fin}_e{e}_"
+                check("state", o["state"][e], g[k + "state"][s + 1], 1e-4)
+                check("ego", o["egosensing"][e], g[k + "ego"][s + 1], 1e-3)
+                check("dist", o["dist"][e], g[k + "dist"][s + 1, 0], 1e-5)
+                check("time", o["time"][e], g[k + "time"][s + 1, 0], 1e-6)
+                check("reward", o["reward"][e], g[k + "reward"][s], 1e-4)
+                check("seed", o["seed"][e], g[k + "seed"][s + 1], 1e-4)
+                check("R0", o["R0"][e], g[k + "R0"][s + 1], 1e-5)
+                check("T0", o["T0"][e], g[k + "T0"][s + 1], 1e-4)
+                assert bool(o["terminated"][e]) == bool(g[k + "term"][s]), (fin, e, s)
+    print("max |oracle - reference CrowdEnv|:", {k: f"{v:.2e}" for k, v in worst.items()})
