@@ -1,6 +1,9 @@
 """PPO oracle (TEST INFRASTRUCTURE): tianshou 0.5.0 GAE restated in numpy float64 and one minibatch of
 GAMMAPPOPolicy.learn (motion/crowd_ppo/ppo_policy.py:189-252) with torch autograd on the oracle nets.
-tianshou is not vendored / not installed => parity unpinned for the GAE piece.
+tianshou is not vendored / not installed => parity unpinned for the GAE piece. The minibatch update
+IS pinned: tests/golden/gen_ppo_golden.py runs the reference's own GAMMAPPOPolicy.forward / learn over a tianshou shim and
+tests/test_oracle_golden.py::test_ppo_oracle_matches_reference_policy_learn reproduces its losses, clipped gradients and
+post-AdamW parameters.
 """
 import numpy as np
 import torch

@@ -198,3 +198,35 @@ def test_env_oracle_matches_reference_crowd_env(golden_dir):
                 check("T0", o["T0"][e], g[k + "T0"][s + 1], 1e-4)
                 assert bool(o["terminated"][e]) == bool(g[k + "term"][s]), (fin, e, s)
     print("max |oracle - reference CrowdEnv|:", {k: f"{v:.2e}" for k, v in worst.items()})
+
+
+def test_ppo_oracle_matches_reference_policy_learn(golden_dir):
+    """oracle.ppo.learn_minibatch + clip_and_adamw vs the reference's own GAMMAPPOPolicy.forward / learn (one minibatch:
+    clip / value / entropy terms, backward, gradient clip over actor+critic only, AdamW) run over a tianshou shim
+    (tests/golden/gen_ppo_golden.py)."""
+    from oracle import ppo as oppo
+    g = np.load(os.path.join(golden_dir, "ppo_golden.npz"))
+    actor = fill_params_(nets.ActorOracle(), seed=21)
+    critic = fill_params_(nets.CriticOracle(), seed=22)
+    shared = fill_params_(nets.PolicyBaseOracle(), seed=23)
+    with torch.no_grad():
+        for mod in actor.pnet.modules():
+            if isinstance(mod, torch.nn.Linear):
+                mod.weight.mul_(0.01)
+    obs = {k: _t(g[k]) for k in ("state", "egosensing", "dist", "time")}
+    optim = torch.optim.AdamW(list(actor.parameters()) + list(critic.parameters()) + list(shared.parameters()), lr=3e-4,
+                              weight_decay=0.01)
+    r = oppo.learn_minibatch(actor, critic, shared, obs, _t(g["act"]), _t(g["logp_old"]), _t(g["adv"]), _t(g["returns"]),
+                             eps_clip=0.1, vf_coef=1.0, ent_coef=0.01, norm_adv=True)
+    assert torch.allclose(r["mu"], _t(g["z_mu"]), atol=1e-6, rtol=1e-5) and torch.allclose(r["logvar"], _t(g["z_logvar"]), atol=1e-6, rtol=1e-5)
+    assert torch.allclose(r["logp"], _t(g["logp_fw"]), atol=1e-3, rtol=1e-6)
+    for k in ("loss", "clip", "vf", "ent", "kld"):
+        assert abs(r[k] - float(g[k])) <= 1e-5 * max(1.0, abs(float(g[k]))), (k, r[k], float(g[k]))
+    oppo.clip_and_adamw(actor, critic, shared, max_grad_norm=0.1, optim=optim)
+    gn = lambda m: np.array([p.grad.norm().item() for p in m.parameters()])     # as learn() leaves them: clipped in place
+    for name, m in (("actor", actor), ("critic", critic), ("shared", shared)):
+        assert np.allclose(gn(m), g[name + "_gradnorm"], rtol=5e-4, atol=1e-9), (name, gn(m), g[name + "_gradnorm"])
+    pn = lambda m: np.array([p.detach().norm().item() for p in m.parameters()])
+    for name, m in (("actor", actor), ("critic", critic), ("shared", shared)):
+        assert np.allclose(pn(m), g[name + "_after"], rtol=1e-6, atol=1e-9), name
+    assert np.allclose(actor.pnet.out_fc.weight.detach()[:8, :16].numpy(), g["actor_out_w_after"], rtol=1e-5, atol=1e-8)
