@@ -142,6 +142,10 @@ sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
 stub("shapely", LineString=LineString)
 stub("shapely.geometry", MultiPoint=MultiPoint, Point=Point)
 sys.modules["torchgeometry"] = oracle_tgm
+for n in ["pytorch3d.structures", "pytorch3d.transforms", "human_body_prior", "human_body_prior.tools"]:
+    stub(n)
+stub("human_body_prior.tools.model_loader", load_vposer=None)
+stub("exp_GAMMAPrimitive.utils.utils_canonicalize_babel", get_body_model=None, marker_ssm_67=list(range(67)))
 
 
 class _BodyModel(torch.nn.Module):
@@ -162,6 +166,17 @@ class _BodyModel(torch.nn.Module):
 MODEL = assets.make_surrogate_smplx(seed=0)
 stub("smplx", create=lambda *a, **k: _BodyModel(MODEL))
 torch.Tensor.cuda = lambda self, *a, **k: self
+_tensor_to = torch.Tensor.to
+
+
+def _to_without_cuda(self, *a, **k):                       # get_map moves its grid with .to(device='cuda')
+    if isinstance(k.get("device"), str) and k["device"].startswith("cuda"):
+        k.pop("device")
+    a = tuple(x for x in a if not (isinstance(x, str) and x.startswith("cuda")))
+    return _tensor_to(self, *a, **k) if (a or k) else self
+
+
+torch.Tensor.to = _to_without_cuda
 torch.cuda.FloatTensor = lambda *a, device=None: torch.FloatTensor(*a)
 
 sys.path.insert(0, os.path.join(REF, "motion"))
@@ -171,18 +186,21 @@ from models import models_GAMMA_primitive as ref_gamma      # noqa: E402
 ref_baseops.get_body_marker_path = lambda: os.path.join(REF, "motion", "data")
 ref_baseops.get_body_model_path = lambda: ""
 from crowd_ppo import crowd_env_2f as ref_env               # noqa: E402
+from crowd_ppo import crowd_env_2f_box as ref_env_box       # noqa: E402   (box scenes: 2-D walkability-map penetration)
 
 
 class AttrDict(dict):
     __getattr__ = dict.__getitem__
 
 
-def build_reference_env(world, sampler, finetuning):
+def build_reference_env(world, sampler, finetuning, box=False):
+    """cfg values: MPVAEPolicy_samp_collision.yaml (SDF env) / MPVAEPolicy_samp_collision_2.yaml (box env)"""
     cfg = AttrDict(args=AttrDict(gpu_index=0),
-                   modelconfig=AttrDict(reproj_factor=0.5, body_repr="ssm2_67_condi_marker_map"),
-                   trainconfig=AttrDict(goal_thresh=0.1, max_depth=13, random_rotation_range=0.0),
-                   lossconfig=AttrDict(weight_skate=0.3, weight_floor=0.1, weight_face_target=0.1, weight_look_target=0.3,
-                                       weight_success=0.5, weight_target_dist=1.0, weight_vp=0.1))
+                   modelconfig=AttrDict(reproj_factor=0.5, body_repr="ssm2_67_condi_marker_map", map_res=16, map_extent=0.8),
+                   trainconfig=AttrDict(goal_thresh=0.1, max_depth=13, random_rotation_range=0.0, pene_thres=3),
+                   lossconfig=AttrDict(weight_skate=0.3, weight_floor=0.1, weight_face_target=0.1,
+                                       weight_look_target=0.1 if box else 0.3, weight_success=0.5, weight_target_dist=1.0,
+                                       weight_vp=0.1, weight_pene=0.1, pene_type="body"))
     combo = ref_gamma.GAMMAPrimitiveCombo(
         {"body_repr": "ssm2_67", "h_dim": 256, "z_dim": 128, "t_his": 2, "t_pred": 18, "use_drnn_mlp": True,
          "hdims_mlp": [512, 256], "residual": True},
@@ -196,12 +214,14 @@ def build_reference_env(world, sampler, finetuning):
     vposer = types.SimpleNamespace(encode=lambda x: types.SimpleNamespace(loc=vp.encode_loc(x)))
     init_env = (cfg, genop, genop, "", sampler, parsers[0], parsers[1], parsers[2], assets.feet_marker_idx(),
                 parsers[0].marker, vposer, world["sdf"])
+    if box:
+        return ref_env_box.CrowdEnv(init_env[:-1], save_rollout=False, render=False)
     return ref_env.CrowdEnv(init_env, save_rollout=False, render=False, finetuning=finetuning)
 
 
 class Sampler:
-    def __init__(self, wp, goal, betas, poly):
-        self.wp, self.goal, self.betas, self.poly, self.calls = wp, goal, betas, poly, 0
+    def __init__(self, wp, goal, betas, poly, navmesh=None):
+        self.wp, self.goal, self.betas, self.poly, self.calls, self.navmesh = wp, goal, betas, poly, 0, navmesh
 
     def next_body(self, **kw):
         self.calls += 1
@@ -210,7 +230,7 @@ class Sampler:
         return {"motion_seed": {"transl": self.wp[:, :3].clone(), "global_orient": self.wp[:, 3:6].clone(),
                                 "body_pose": self.wp[:, 6:69].clone()},
                 "gender": "male", "betas": self.betas.clone(), "wpath": torch.cat([start, self.goal.reshape(1, 3)]),
-                "shapely_poly": self.poly}
+                "shapely_poly": self.poly, "navmesh": self.navmesh}
 
 
 out = {}
@@ -220,7 +240,6 @@ N_ENVS, N_STEPS = 3, 3
 wp, goals, betas = harness.sample_candidates_cpu(world, N_ENVS, seed=5)
 g = torch.Generator().manual_seed(17)
 Z = torch.randn(N_ENVS, N_STEPS, 128, generator=g)
-assert set(ref_env.CrowdEnv.__init__.__code__.co_names) and True
 for fin in (0, 1):
     for e in range(N_ENVS):
         env = build_reference_env(world, Sampler(wp[e], goals[e], betas[e], Polygon(rings)), bool(fin))
@@ -237,6 +256,24 @@ for fin in (0, 1):
             out[f"f{fin}_e{e}_{k}"] = torch.stack([torch.as_tensor(x).detach().float() for x in v]).numpy()
         if fin == 0 and e == 0:
             out["feet_vids_sorted"] = np.array(sorted(env.feet_vids))
+# ---- box-scene env (crowd_env_2f_box.py): walkability map from the navmesh triangles, bbox penetration count --------
+tris = assets.scene_navmesh_triangles(assets.make_box_scene(0))                      # [F,3,2]
+navmesh = types.SimpleNamespace(vertices=np.concatenate([tris.reshape(-1, 2), np.zeros((tris.shape[0] * 3, 1))], axis=1),
+                                faces=np.arange(tris.shape[0] * 3).reshape(-1, 3))
+for e in range(N_ENVS):
+    env = build_reference_env(world, Sampler(wp[e], goals[e], betas[e], Polygon(rings), navmesh), False, box=True)
+    obs, _ = env.reset()
+    rec = {"state": [obs["state"]], "ego": [obs["egosensing"]], "reward": [], "term": [], "seed": [env.body_param_seed[0]],
+           "R0": [env.R0[0]], "T0": [env.T0[0]]}
+    for s in range(N_STEPS):
+        obs, rew, term, trunc, _ = env.step(Z[e, s].clone())
+        rec["state"].append(obs["state"]); rec["ego"].append(obs["egosensing"])
+        rec["reward"].append(torch.tensor(rew)); rec["term"].append(torch.tensor(term))
+        rec["seed"].append(env.body_param_seed[0]); rec["R0"].append(env.R0[0]); rec["T0"].append(env.T0[0])
+        if term:
+            break
+    for k, v in rec.items():
+        out[f"box_e{e}_{k}"] = torch.stack([torch.as_tensor(x).detach().float() for x in v]).numpy()
 out.update(wp=wp.numpy(), goals=goals.numpy(), betas=betas.numpy(), Z=Z.numpy())
 np.savez_compressed(os.path.join(HERE, "env_golden.npz"), **out)
 print("wrote env_golden.npz", len(out), "arrays;", "rewards env0:", out["f0_e0_reward"], "ego[0,:4]:", out["f0_e0_ego"][0, 0, :4])

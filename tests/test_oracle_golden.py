@@ -230,3 +230,41 @@ def test_ppo_oracle_matches_reference_policy_learn(golden_dir):
     for name, m in (("actor", actor), ("critic", critic), ("shared", shared)):
         assert np.allclose(pn(m), g[name + "_after"], rtol=1e-6, atol=1e-9), name
     assert np.allclose(actor.pnet.out_fc.weight.detach()[:8, :16].numpy(), g["actor_out_w_after"], rtol=1e-5, atol=1e-8)
+
+
+def test_box_env_oracle_matches_reference_box_env(golden_dir):
+    """box_mode of the oracle env vs the reference's own crowd_env_2f_box.CrowdEnv (get_map walkability grid from the
+    navmesh triangles, marker-bbox penetration count, termination on penetration) on the same starts and actions."""
+    from egogen_b200 import assets
+    from oracle import harness
+    from oracle.env import CrowdEnvOracle
+    g = np.load(os.path.join(golden_dir, "env_golden.npz"))
+    world = harness.build_oracle_world(0, sdf_res=64)
+    base = world["env"]
+    tris = assets.scene_navmesh_triangles(assets.make_box_scene(0))
+    env = CrowdEnvOracle(base.parser, base.combo, base.vposer, base.sdf, base.segments, base.marker, base.feet_marker_idx,
+                         base.feet_vids, box_mode=True, navmesh_tris=tris, weight_look=0.1)
+    wp, goals, betas, Z = (torch.as_tensor(g[k]) for k in ("wp", "goals", "betas", "Z"))
+    r = env.reset_from(wp, goals, betas)
+    assert bool(r["accept"].all())
+    env.set_state(state=r["state"], seed=r["seed"], R0=r["R0"], T0=r["T0"], betas=betas, dist=r["dist"],
+                  steps=torch.zeros(3, dtype=torch.int64), goal=goals)
+    err = lambda a, b: float(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).max())
+    done = [False] * 3
+    for e in range(3):
+        assert err(r["state"][e], g[f"box_e{e}_state"][0]) < 2e-5 and err(r["egosensing"][e], g[f"box_e{e}_ego"][0]) < 1e-5
+    n_cmp = 0
+    for s in range(3):
+        o = env.step(Z[:, s])
+        for e in range(3):
+            k = f"box_e{e}_"
+            if done[e] or s >= len(g[k + "reward"]):
+                continue
+            assert err(o["state"][e], g[k + "state"][s + 1]) < 1e-4, (e, s)
+            assert err(o["egosensing"][e], g[k + "ego"][s + 1]) < 1e-3, (e, s)
+            assert err(o["reward"][e], g[k + "reward"][s]) < 1e-4, (e, s, float(o["reward"][e]), g[k + "reward"][s])
+            assert err(o["seed"][e], g[k + "seed"][s + 1]) < 1e-4 and err(o["T0"][e], g[k + "T0"][s + 1]) < 1e-4
+            assert bool(o["terminated"][e]) == bool(g[k + "term"][s]), (e, s)
+            done[e] = bool(g[k + "term"][s])
+            n_cmp += 1
+    assert n_cmp >= 3
