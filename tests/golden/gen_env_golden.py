@@ -74,8 +74,11 @@ class MultiLineString:
 class Polygon:
     """exterior ring + holes (closed rings [n,2]); interior = inside the exterior and outside every hole."""
 
-    def __init__(self, rings):
-        self.rings = [np.asarray(r, dtype=np.float64) for r in rings]
+    is_valid = True
+
+    def __init__(self, shell, holes=None):
+        self.rings = [np.asarray(r, dtype=np.float64) for r in [shell] + list(holes or [])]
+        self.exterior = types.SimpleNamespace(coords=[tuple(p) for p in self.rings[0]])
 
     @staticmethod
     def _in_ring(ring, p):
@@ -121,6 +124,14 @@ class Polygon:
         return MultiLineString(segs)
 
 
+class MultiPolygon:
+    """union_all of the other agents' boxes: kept as the list of boxes - for containment and for the first hit of a ray
+    the union of (possibly overlapping) holes and the set of holes are the same thing"""
+
+    def __init__(self, geoms):
+        self.geoms = list(geoms)
+
+
 def stub(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
@@ -139,8 +150,12 @@ for n in ["trimesh", "pyrender", "pytorch3d", "tensorboardX", "matplotlib", "mat
     stub(n)
 sys.modules["tensorboardX"].SummaryWriter = object
 sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-stub("shapely", LineString=LineString)
-stub("shapely.geometry", MultiPoint=MultiPoint, Point=Point)
+stub("shapely", LineString=LineString, union_all=lambda polys: MultiPolygon(polys), is_valid=lambda g: True)
+stub("shapely.geometry", MultiPoint=MultiPoint, Point=Point, Polygon=Polygon, MultiPolygon=MultiPolygon, mapping=None,
+     LinearRing=None, multipolygon=types.SimpleNamespace(MultiPolygon=MultiPolygon), polygon=types.SimpleNamespace(Polygon=Polygon))
+stub("shapely.plotting", plot_polygon=None)
+sys.modules["shapely"].geometry = sys.modules["shapely.geometry"]
+sys.modules["shapely"].plotting = sys.modules["shapely.plotting"]
 sys.modules["torchgeometry"] = oracle_tgm
 for n in ["pytorch3d.structures", "pytorch3d.transforms", "human_body_prior", "human_body_prior.tools"]:
     stub(n)
@@ -187,6 +202,7 @@ ref_baseops.get_body_marker_path = lambda: os.path.join(REF, "motion", "data")
 ref_baseops.get_body_model_path = lambda: ""
 from crowd_ppo import crowd_env_2f as ref_env               # noqa: E402
 from crowd_ppo import crowd_env_2f_box as ref_env_box       # noqa: E402   (box scenes: 2-D walkability-map penetration)
+from crowd_ppo import crowd_env_crowd_eval as ref_env_crowd  # noqa: E402   (multi-agent: other agents' boxes are holes)
 
 
 class AttrDict(dict):
@@ -214,6 +230,8 @@ def build_reference_env(world, sampler, finetuning, box=False):
     vposer = types.SimpleNamespace(encode=lambda x: types.SimpleNamespace(loc=vp.encode_loc(x)))
     init_env = (cfg, genop, genop, "", sampler, parsers[0], parsers[1], parsers[2], assets.feet_marker_idx(),
                 parsers[0].marker, vposer, world["sdf"])
+    if box == "crowd":      # sampler is the agent's start data here (crowd_env_crowd_eval.py:50-51)
+        return ref_env_crowd.CrowdEnv(init_env[:-1] + ("0", "golden"), save_rollout=False, render=False)
     if box:
         return ref_env_box.CrowdEnv(init_env[:-1], save_rollout=False, render=False)
     return ref_env.CrowdEnv(init_env, save_rollout=False, render=False, finetuning=finetuning)
@@ -242,7 +260,7 @@ g = torch.Generator().manual_seed(17)
 Z = torch.randn(N_ENVS, N_STEPS, 128, generator=g)
 for fin in (0, 1):
     for e in range(N_ENVS):
-        env = build_reference_env(world, Sampler(wp[e], goals[e], betas[e], Polygon(rings)), bool(fin))
+        env = build_reference_env(world, Sampler(wp[e], goals[e], betas[e], Polygon(rings[0], rings[1:])), bool(fin))
         obs, _ = env.reset()
         rec = {"state": [obs["state"]], "ego": [obs["egosensing"]], "dist": [obs["dist"].reshape(1)], "time": [obs["time"]],
                "reward": [], "term": [], "seed": [env.body_param_seed[0]], "R0": [env.R0[0]], "T0": [env.T0[0]]}
@@ -261,7 +279,7 @@ tris = assets.scene_navmesh_triangles(assets.make_box_scene(0))                 
 navmesh = types.SimpleNamespace(vertices=np.concatenate([tris.reshape(-1, 2), np.zeros((tris.shape[0] * 3, 1))], axis=1),
                                 faces=np.arange(tris.shape[0] * 3).reshape(-1, 3))
 for e in range(N_ENVS):
-    env = build_reference_env(world, Sampler(wp[e], goals[e], betas[e], Polygon(rings), navmesh), False, box=True)
+    env = build_reference_env(world, Sampler(wp[e], goals[e], betas[e], Polygon(rings[0], rings[1:]), navmesh), False, box=True)
     obs, _ = env.reset()
     rec = {"state": [obs["state"]], "ego": [obs["egosensing"]], "reward": [], "term": [], "seed": [env.body_param_seed[0]],
            "R0": [env.R0[0]], "T0": [env.T0[0]]}
@@ -274,6 +292,43 @@ for e in range(N_ENVS):
             break
     for k, v in rec.items():
         out[f"box_e{e}_{k}"] = torch.stack([torch.as_tensor(x).detach().float() for x in v]).numpy()
+# ---- 4-agent crowd scene (crowd_env_crowd_eval.py driven in the order of dummy_vector_env.py:29-128) -----------------
+# every agent's marker box is a hole of the floor polygon for the others; the boxes are redistributed before EACH
+# agent's step, so agent i already sees the new boxes of agents < i
+A = 4
+cw, cg, cb = harness.sample_candidates_cpu(world, A, seed=9)
+for a in range(A):                                            # on a 0.8 m circle, walking through the centre
+    ang = 2 * np.pi * a / A + 0.2
+    pos = torch.tensor([0.8 * np.cos(ang), 0.8 * np.sin(ang)], dtype=torch.float32)
+    cw[a, :, :2] = pos
+    cg[a, :2] = -3.0 * pos / pos.norm()
+envs = [build_reference_env(world, Sampler(cw[a], cg[a], cb[a], None).next_body(), False, box="crowd") for a in range(A)]
+
+
+def distribute_holes():
+    for i in range(A):
+        envs[i].holes = [envs[j].bbox for j in range(A) if j != i]
+
+
+distribute_holes()
+rec = {k: [] for k in ("state", "ego", "reward", "term", "bbox", "seed", "T0")}
+first = [e.reset()[0] for e in envs]
+rec["state"].append(torch.stack([o["state"] for o in first])); rec["ego"].append(torch.stack([o["egosensing"] for o in first]))
+rec["bbox"].append(torch.tensor(np.array([[e.bbox[0][0], e.bbox[0][1], e.bbox[2][0], e.bbox[2][1]] for e in envs], dtype=np.float32)))
+Zc = torch.randn(2, A, 128, generator=torch.Generator().manual_seed(23)) * 0.5
+for s in range(2):
+    st, eg, rw, tm, bb, sd, t0 = [], [], [], [], [], [], []
+    for a in range(A):
+        distribute_holes()
+        obs, rew, term, trunc, _ = envs[a].step(Zc[s, a].clone())
+        st.append(obs["state"]); eg.append(obs["egosensing"]); rw.append(torch.tensor(rew)); tm.append(torch.tensor(term))
+        bb.append(torch.tensor([envs[a].bbox[0][0], envs[a].bbox[0][1], envs[a].bbox[2][0], envs[a].bbox[2][1]], dtype=torch.float32))
+        sd.append(envs[a].body_param_seed[0]); t0.append(envs[a].T0[0])
+    for k, v in zip(("state", "ego", "reward", "term", "bbox", "seed", "T0"), (st, eg, rw, tm, bb, sd, t0)):
+        rec[k].append(torch.stack([x.float() for x in v]))
+for k, v in rec.items():
+    out[f"crowd_{k}"] = torch.stack(v).numpy()
+out.update(crowd_wp=cw.numpy(), crowd_goals=cg.numpy(), crowd_betas=cb.numpy(), crowd_Z=Zc.numpy())
 out.update(wp=wp.numpy(), goals=goals.numpy(), betas=betas.numpy(), Z=Z.numpy())
 np.savez_compressed(os.path.join(HERE, "env_golden.npz"), **out)
 print("wrote env_golden.npz", len(out), "arrays;", "rewards env0:", out["f0_e0_reward"], "ego[0,:4]:", out["f0_e0_ego"][0, 0, :4])

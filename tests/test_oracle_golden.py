@@ -268,3 +268,49 @@ def test_box_env_oracle_matches_reference_box_env(golden_dir):
             done[e] = bool(g[k + "term"][s])
             n_cmp += 1
     assert n_cmp >= 3
+
+
+def test_crowd_env_oracle_matches_reference_crowd_env(golden_dir):
+    """4-agent crowd dynamics vs the reference's own crowd_env_crowd_eval.CrowdEnv driven in DummyCrowdVectorEnv's order:
+    the other agents' marker boxes are holes of the floor polygon (walkability map + ego rays), redistributed before each
+    agent's step; no penetration termination."""
+    from egogen_b200 import assets
+    from oracle import harness
+    from oracle.env import CrowdEnvOracle
+    g = np.load(os.path.join(golden_dir, "env_golden.npz"))
+    world = harness.build_oracle_world(0, sdf_res=64)
+    base = world["env"]
+    A = 4
+    fl = np.array([[4, 4], [4, -4], [-4, -4], [-4, 4], [4, 4]], np.float64)          # crowd_env_crowd_eval.py:391
+    tris = np.stack([fl[[0, 1, 2]], fl[[2, 3, 0]]]).astype(np.float32)
+    wp, goals, betas, Z = (torch.as_tensor(g[k]) for k in ("crowd_wp", "crowd_goals", "crowd_betas", "crowd_Z"))
+    envs = []
+    for a in range(A):
+        e = CrowdEnvOracle(base.parser, base.combo, base.vposer, base.sdf, assets.rings_to_segments([fl]), base.marker,
+                           base.feet_marker_idx, base.feet_vids, box_mode=True, navmesh_tris=tris, weight_look=0.1)
+        e.crowd = True
+        envs.append(e)
+    sl = lambda a: slice(a, a + 1)
+    bb = [envs[a].reset_from(wp[sl(a)], goals[sl(a)], betas[sl(a)])["bbox"] for a in range(A)]       # [1,4] each
+    holes_for = lambda a: torch.stack([bb[o] for o in range(A) if o != a], dim=1)                      # [1,A-1,4]
+    err = lambda x, y: float(np.abs(np.asarray(x, dtype=np.float64) - np.asarray(y, dtype=np.float64)).max())
+    assert err(torch.cat(bb), g["crowd_bbox"][0]) < 1e-5
+    for a in range(A):
+        envs[a].holes = holes_for(a)
+        r = envs[a].reset_from(wp[sl(a)], goals[sl(a)], betas[sl(a)])
+        assert err(r["state"][0], g["crowd_state"][0, a]) < 2e-5 and err(r["egosensing"][0], g["crowd_ego"][0, a]) < 1e-4, a
+        envs[a].set_state(state=r["state"], seed=r["seed"], R0=r["R0"], T0=r["T0"], betas=betas[sl(a)], dist=r["dist"],
+                          steps=torch.zeros(1, dtype=torch.int64), goal=goals[sl(a)])
+    envs[0].holes = None                                        # the other agents must matter in this set-up
+    blind = envs[0].reset_from(wp[sl(0)], goals[sl(0)], betas[sl(0)])["egosensing"][0]
+    assert err(blind, g["crowd_ego"][0, 0]) > 0.05
+    for s in range(2):
+        for a in range(A):
+            envs[a].holes = holes_for(a)                        # update_holes_for_each_agent() before this worker's step
+            o = envs[a].step(Z[s, a:a + 1])
+            bb[a] = envs[a].bbox
+            assert err(o["state"][0], g["crowd_state"][s + 1, a]) < 1e-4, (s, a)
+            assert err(o["egosensing"][0], g["crowd_ego"][s + 1, a]) < 1e-3, (s, a)
+            assert err(o["reward"][0], g["crowd_reward"][s, a]) < 1e-4, (s, a, float(o["reward"][0]), g["crowd_reward"][s, a])
+            assert err(envs[a].bbox[0], g["crowd_bbox"][s + 1, a]) < 1e-4 and err(o["seed"][0], g["crowd_seed"][s, a]) < 1e-4
+            assert bool(o["terminated"][0]) == bool(g["crowd_term"][s, a])
