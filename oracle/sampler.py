@@ -1,7 +1,9 @@
 """Start-body generation oracle (TEST INFRASTRUCTURE): per-body CPU restatement of CrowdMotion.gen_init_body
 (exp_GAMMAPrimitive/utils/environments.py:1041-1131) on top of the LBS oracle. pytorch3d is absent, so its
 axis_angle_to_matrix / matrix_to_axis_angle are replaced by scipy's Rotation (same rotations; parity unpinned for the
-third-party conversion, compared as rotation matrices in the tests)."""
+third-party conversion, compared as rotation matrices in the tests). Pinned: tests/golden/gen_sampler_golden.py runs the
+reference's own gen_init_body on its subseq_00343 motion seed (body model / pytorch3d served by the oracle / scipy) and
+tests/test_oracle_golden.py::test_start_body_oracle_matches_reference_sampler reproduces its outputs."""
 import numpy as np
 import torch
 from scipy.spatial.transform import Rotation

@@ -314,3 +314,27 @@ def test_crowd_env_oracle_matches_reference_crowd_env(golden_dir):
             assert err(o["reward"][0], g["crowd_reward"][s, a]) < 1e-4, (s, a, float(o["reward"][0]), g["crowd_reward"][s, a])
             assert err(envs[a].bbox[0], g["crowd_bbox"][s + 1, a]) < 1e-4 and err(o["seed"][0], g["crowd_seed"][s, a]) < 1e-4
             assert bool(o["terminated"][0]) == bool(g["crowd_term"][s, a])
+
+
+def test_start_body_oracle_matches_reference_sampler(golden_dir, smplx_model):
+    """oracle.sampler.gen_init_body vs the reference's own CrowdMotion.gen_init_body (environments.py:1041-1131) run on
+    its motion seed subseq_00343 (tests/golden/gen_sampler_golden.py): face-the-goal rotation, yaw jitter, pelvis-over-
+    start / feet-on-floor translation, way-point heights; the motion-seed fixture carries the same frames."""
+    from scipy.spatial.transform import Rotation
+    from egogen_b200 import assets
+    from oracle import sampler as osampler
+    g = np.load(os.path.join(golden_dir, "sampler_golden.npz"))
+    seed = np.load(os.path.join(golden_dir, "locomotion_seed_00343.npz"))
+    parser = SMPLXParserOracle(smplx_model, marker=assets.marker_ids())
+    for i in range(3):
+        sf = int(g["start_frame"][i])
+        assert np.array_equal(seed["poses"][sf:sf + 2, 3:66], g["body_pose"][i]) and np.array_equal(seed["betas"][:10], g["betas"][i])
+        out = osampler.gen_init_body(parser, g["start"][i], g["target"][i], seed["betas"][:10], seed["poses"][sf:sf + 2, 3:66],
+                                     seed["poses"][sf:sf + 2, :3], seed["trans"][sf:sf + 2], float(g["yaw"][i]))
+        assert np.abs(out["transl"].numpy() - g["transl"][i]).max() < 2e-5, i
+        assert np.abs(out["wpath"].numpy() - g["wpath"][i]).max() < 2e-5, i
+        R_ref = Rotation.from_rotvec(g["global_orient"][i].astype(np.float64)).as_matrix()
+        assert np.abs(out["global_orient_matrix"].numpy() - R_ref).max() < 2e-5, i
+        # the body faces its goal up to the yaw jitter, pelvis above the start point, lowest joint on the floor
+        assert np.abs(out["joints"][0, 0, :2].numpy() - g["start"][i][:2]).max() < 1e-4
+        assert abs(float(out["joints"][0, :, 2].min())) < 1e-4
