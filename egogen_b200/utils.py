@@ -17,6 +17,10 @@ def save_rollout_results(scene, outmps, outfolder, man_id=None):
     wpath = scene["wpath"]
     node = {"motion": [], "wpath": wpath.detach().cpu().numpy() if hasattr(wpath, "detach") else wpath,
             "navmesh_path": scene.get("navmesh_path")}
+    if "obj_id" in scene:
+        node["obj_id"] = scene["obj_id"]
+    if "obj_transform" in scene:
+        node["obj_transform"] = (scene["obj_transform"],)      # 1-tuple, as the reference writes it (utils.py:27)
     if "scene_path" in scene:
         node["scene_path"] = scene["scene_path"]
     for mp in outmps:

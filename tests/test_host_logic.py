@@ -39,6 +39,40 @@ def test_rollout_writer_schema(tmp_path):
     assert m["pelvis_loc"].shape == (20, 3) and m["mp_type"] == "2-frame"
 
 
+def synthetic_rollout():
+    """deterministic (scene, outmps) in the layout CrowdEnv.step appends (crowd_env_2f.py:156), the 4x duplicated batch
+    included; shared with tests/golden/gen_rollout_golden.py, which feeds it to the reference's own writer"""
+    g = torch.Generator().manual_seed(12)
+    r = lambda *s: torch.randn(*s, generator=g)
+    outmps = [[r(4, 20, 67, 3), r(4, 20, 93), r(10), "male", r(3, 3), r(1, 3), r(4, 20, 3), "2-frame"] for _ in range(3)]
+    scene = {"wpath": r(2, 3), "navmesh_path": "scenes/room_0/navmesh_tight.ply", "scene_path": "scenes/room_0/mesh.ply",
+             "obj_id": 7, "obj_transform": np.eye(4)}
+    return scene, outmps
+
+
+def test_rollout_writer_matches_reference_writer(tmp_path, golden_dir):
+    """egogen_b200.utils.save_rollout_results vs the pickle the reference's own save_rollout_results wrote for the same
+    rollout (tests/golden/gen_rollout_golden.py): same keys in the same order, same values, same file name rule."""
+    import os
+    from egogen_b200.utils import save_rollout_results
+    scene, outmps = synthetic_rollout()
+    p = save_rollout_results(scene, outmps, str(tmp_path / "out"), man_id="golden7")
+    assert os.path.basename(p) == "motion_golden7.pkl"
+    mine = pickle.load(open(p, "rb"))
+    ref = pickle.load(open(os.path.join(golden_dir, "rollout_golden.pkl"), "rb"))
+
+    def same(a, b):
+        if isinstance(a, dict):
+            return isinstance(b, dict) and list(a) == list(b) and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, (list, tuple)):
+            return type(a) is type(b) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        if isinstance(a, np.ndarray):
+            return isinstance(b, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+        return a == b
+    assert same(ref, mine)
+    assert ref["motion"][0]["smplx_params"].shape == (1, 20, 93) and isinstance(ref["obj_transform"], tuple)
+
+
 def test_surrogate_assets_have_real_shapes(smplx_model):
     from egogen_b200 import assets
     m = smplx_model
