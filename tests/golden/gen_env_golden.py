@@ -329,6 +329,60 @@ for s in range(2):
 for k, v in rec.items():
     out[f"crowd_{k}"] = torch.stack(v).numpy()
 out.update(crowd_wp=cw.numpy(), crowd_goals=cg.numpy(), crowd_betas=cb.numpy(), crowd_Z=Zc.numpy())
+# ---- a start that walks into the box: penetration terminates the fine-tuning episode (and the box-scene episode) ----
+from scipy.spatial.transform import Rotation                 # noqa: E402
+bx = assets.make_box_scene(0)["boxes"][0]
+cxy = np.array([(bx[0] + bx[3]) / 2, (bx[1] + bx[4]) / 2])
+rad = float(np.hypot(bx[3] - bx[0], bx[4] - bx[1]) / 2 + 0.3)
+pw, pg, pb = harness.sample_candidates_cpu(world, 1, seed=33)
+found = None
+for k in range(12):
+    for yk in range(6):
+        ang, yaw = 2 * np.pi * k / 12, 2 * np.pi * yk / 6
+        pos = cxy + rad * np.array([np.cos(ang), np.sin(ang)])
+        if np.abs(pos).max() > 3.3:
+            continue
+        R = np.zeros((3, 3)); c_, s_ = np.cos(yaw), np.sin(yaw)
+        R[0, 0] = c_; R[0, 2] = s_; R[1, 0] = s_; R[1, 2] = -c_; R[2, 1] = 1
+        cand = pw[0].clone()
+        cand[:, :2] = torch.tensor(pos, dtype=torch.float32)
+        cand[:, 3:6] = torch.tensor(Rotation.from_matrix(R).as_rotvec(), dtype=torch.float32)
+        goal = torch.tensor([2 * cxy[0] - pos[0], 2 * cxy[1] - pos[1], float(pg[0, 2])], dtype=torch.float32)
+        try:
+            env = build_reference_env(world, Sampler(cand, goal, pb[0], Polygon(rings[0], rings[1:])), True)
+            obs, _ = env.reset()
+        except AssertionError:
+            continue
+        rec = {"state": [obs["state"]], "reward": [], "term": []}
+        for s in range(N_STEPS):
+            obs, rew, term, _, _ = env.step(Z[0, s].clone())
+            rec["state"].append(obs["state"]); rec["reward"].append(torch.tensor(rew)); rec["term"].append(torch.tensor(term))
+            if term:
+                break
+        if rec["term"][-1] and len(rec["term"]) < 13:
+            found = (cand, goal, rec)
+            break
+    if found:
+        break
+assert found is not None, "no start walks into the box within 3 steps"
+cand, goal, rec = found
+for k, v in rec.items():
+    out[f"pen_{k}"] = torch.stack([torch.as_tensor(x).detach().float() for x in v]).numpy()
+out.update(pen_wp=cand.numpy(), pen_goal=goal.numpy(), pen_betas=pb[0].numpy())
+env = build_reference_env(world, Sampler(cand, goal, pb[0], Polygon(rings[0], rings[1:]), navmesh), False, box=True)
+try:
+    obs, _ = env.reset()
+    rec = {"state": [obs["state"]], "reward": [], "term": []}
+    for s in range(N_STEPS):
+        obs, rew, term, _, _ = env.step(Z[0, s].clone())
+        rec["state"].append(obs["state"]); rec["reward"].append(torch.tensor(rew)); rec["term"].append(torch.tensor(term))
+        if term:
+            break
+    for k, v in rec.items():
+        out[f"penbox_{k}"] = torch.stack([torch.as_tensor(x).detach().float() for x in v]).numpy()
+except AssertionError:
+    pass                                                     # the 2-D map test rejects this start: nothing to record
+print("penetration case: steps", len(out["pen_term"]), "term", out["pen_term"], "box:", out.get("penbox_term"))
 out.update(wp=wp.numpy(), goals=goals.numpy(), betas=betas.numpy(), Z=Z.numpy())
 np.savez_compressed(os.path.join(HERE, "env_golden.npz"), **out)
 print("wrote env_golden.npz", len(out), "arrays;", "rewards env0:", out["f0_e0_reward"], "ego[0,:4]:", out["f0_e0_ego"][0, 0, :4])

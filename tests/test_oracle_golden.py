@@ -338,3 +338,28 @@ def test_start_body_oracle_matches_reference_sampler(golden_dir, smplx_model):
         # the body faces its goal up to the yaw jitter, pelvis above the start point, lowest joint on the floor
         assert np.abs(out["joints"][0, 0, :2].numpy() - g["start"][i][:2]).max() < 1e-4
         assert abs(float(out["joints"][0, :, 2].min())) < 1e-4
+
+
+def test_env_oracle_penetration_termination_matches_reference(golden_dir):
+    """A start that walks into the box: in the fine-tuning setting the reference terminates the episode on the per-frame
+    penetration count (crowd_env_2f.py:175-176,299-302); the oracle must end the same step with the same reward."""
+    from oracle import harness
+    g = np.load(os.path.join(golden_dir, "env_golden.npz"))
+    world = harness.build_oracle_world(0, sdf_res=64)
+    env = world["env"]
+    env.finetuning = True
+    wp, goal, betas = torch.as_tensor(g["pen_wp"])[None], torch.as_tensor(g["pen_goal"])[None], torch.as_tensor(g["pen_betas"])[None]
+    r = env.reset_from(wp, goal, betas)
+    assert bool(r["accept"][0]) and np.abs(r["state"][0].numpy() - g["pen_state"][0]).max() < 2e-5
+    env.set_state(state=r["state"], seed=r["seed"], R0=r["R0"], T0=r["T0"], betas=betas, dist=r["dist"],
+                  steps=torch.zeros(1, dtype=torch.int64), goal=goal)
+    Z = torch.as_tensor(g["Z"])
+    n = len(g["pen_term"])
+    assert bool(g["pen_term"][-1]) and n < 13
+    for s in range(n):
+        o = env.step(Z[0:1, s])
+        assert np.abs(o["state"][0].numpy() - g["pen_state"][s + 1]).max() < 1e-4
+        assert abs(float(o["reward"][0]) - float(g["pen_reward"][s])) < 1e-4
+        assert bool(o["terminated"][0]) == bool(g["pen_term"][s])
+    assert int(o["counts"][0].max()) >= 40 and float(o["dist"][0]) < 1.0       # ended by penetration, not by the goal / depth
+    env.finetuning = False
