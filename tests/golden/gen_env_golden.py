@@ -382,6 +382,41 @@ try:
         out[f"penbox_{k}"] = torch.stack([torch.as_tensor(x).detach().float() for x in v]).numpy()
 except AssertionError:
     pass                                                     # the 2-D map test rejects this start: nothing to record
+# the same search for the box-scene env, whose 2-D start test is stricter: a start it accepts that ends by penetration
+found = None
+for k in range(12):
+    for yk in range(6):
+        ang, yaw = 2 * np.pi * k / 12, 2 * np.pi * yk / 6
+        pos = cxy + (rad + 0.25) * np.array([np.cos(ang), np.sin(ang)])
+        if np.abs(pos).max() > 3.3:
+            continue
+        R = np.zeros((3, 3)); c_, s_ = np.cos(yaw), np.sin(yaw)
+        R[0, 0] = c_; R[0, 2] = s_; R[1, 0] = s_; R[1, 2] = -c_; R[2, 1] = 1
+        cand = pw[0].clone()
+        cand[:, :2] = torch.tensor(pos, dtype=torch.float32)
+        cand[:, 3:6] = torch.tensor(Rotation.from_matrix(R).as_rotvec(), dtype=torch.float32)
+        goal = torch.tensor([2 * cxy[0] - pos[0], 2 * cxy[1] - pos[1], float(pg[0, 2])], dtype=torch.float32)
+        try:
+            env = build_reference_env(world, Sampler(cand, goal, pb[0], Polygon(rings[0], rings[1:]), navmesh), False, box=True)
+            obs, _ = env.reset()
+        except AssertionError:
+            continue
+        rec = {"state": [obs["state"]], "reward": [], "term": []}
+        for s in range(N_STEPS):
+            obs, rew, term, _, _ = env.step(Z[0, s].clone())
+            rec["state"].append(obs["state"]); rec["reward"].append(torch.tensor(rew)); rec["term"].append(torch.tensor(term))
+            if term:
+                break
+        if rec["term"][-1]:
+            found = (cand, goal, rec)
+            break
+    if found:
+        break
+if found is not None:
+    cand, goal, rec = found
+    for k, v in rec.items():
+        out[f"penbox_{k}"] = torch.stack([torch.as_tensor(x).detach().float() for x in v]).numpy()
+    out.update(penbox_wp=cand.numpy(), penbox_goal=goal.numpy())
 print("penetration case: steps", len(out["pen_term"]), "term", out["pen_term"], "box:", out.get("penbox_term"))
 out.update(wp=wp.numpy(), goals=goals.numpy(), betas=betas.numpy(), Z=Z.numpy())
 np.savez_compressed(os.path.join(HERE, "env_golden.npz"), **out)

@@ -363,3 +363,32 @@ def test_env_oracle_penetration_termination_matches_reference(golden_dir):
         assert bool(o["terminated"][0]) == bool(g["pen_term"][s])
     assert int(o["counts"][0].max()) >= 40 and float(o["dist"][0]) < 1.0       # ended by penetration, not by the goal / depth
     env.finetuning = False
+
+
+def test_box_env_oracle_penetration_termination_matches_reference(golden_dir):
+    """box-scene env: a start the 2-D map test accepts that ends by the marker-bbox penetration count
+    (crowd_env_2f_box.py:279-295,325); same step, same reward (r_pene drops to 0)."""
+    from egogen_b200 import assets
+    from oracle import harness
+    from oracle.env import CrowdEnvOracle
+    g = np.load(os.path.join(golden_dir, "env_golden.npz"))
+    assert "penbox_wp" in g.files
+    world = harness.build_oracle_world(0, sdf_res=64)
+    base = world["env"]
+    tris = assets.scene_navmesh_triangles(assets.make_box_scene(0))
+    env = CrowdEnvOracle(base.parser, base.combo, base.vposer, base.sdf, base.segments, base.marker, base.feet_marker_idx,
+                         base.feet_vids, box_mode=True, navmesh_tris=tris, weight_look=0.1)
+    wp, goal, betas = torch.as_tensor(g["penbox_wp"])[None], torch.as_tensor(g["penbox_goal"])[None], torch.as_tensor(g["pen_betas"])[None]
+    r = env.reset_from(wp, goal, betas)
+    assert bool(r["accept"][0]) and np.abs(r["state"][0].numpy() - g["penbox_state"][0]).max() < 2e-5
+    env.set_state(state=r["state"], seed=r["seed"], R0=r["R0"], T0=r["T0"], betas=betas, dist=r["dist"],
+                  steps=torch.zeros(1, dtype=torch.int64), goal=goal)
+    Z = torch.as_tensor(g["Z"])
+    n = len(g["penbox_term"])
+    assert bool(g["penbox_term"][-1]) and n < 13
+    for s in range(n):
+        o = env.step(Z[0:1, s])
+        assert np.abs(o["state"][0].numpy() - g["penbox_state"][s + 1]).max() < 1e-4
+        assert abs(float(o["reward"][0]) - float(g["penbox_reward"][s])) < 1e-4
+        assert bool(o["terminated"][0]) == bool(g["penbox_term"][s])
+    assert float(o["terms"][0, 6]) == 0.0 and float(o["dist"][0]) < 1.0        # r_pene = 0: ended by penetration
