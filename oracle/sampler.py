@@ -50,3 +50,25 @@ def gen_init_body(parser, start, target, betas, body_pose, global_orient, transl
     wpath[0] = j[0, 0, :]
     wpath[1, 2] = wpath[0, 2]
     return dict(transl=tr, global_orient_matrix=rot, wpath=wpath, joints=j)
+
+
+def canonicalize_subsequence(parser, parser_cmu, betas, transl_all, pose_all, start_frame, end_frame, downsample_rate=3):
+    """utils_canonicalize_samp.py:123-187 on the LBS oracle (torch branch of update_transl_glorot for the frame change; the
+    reference script uses scipy's Rotation in float64 for the same rotation). parser / parser_cmu: SMPLXParserOracle with
+    the ssm2_67 / cmu_41 marker sets. Returns the primitive dict (numpy), or None when the recording is too short."""
+    if transl_all.shape[0] <= end_frame:
+        return None
+    f32 = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32)
+    tr = f32(transl_all[start_frame:end_frame:downsample_rate])
+    po = f32(pose_all[start_frame:end_frame:downsample_rate])
+    be = f32(betas[:10]).reshape(1, 10)
+    T = tr.shape[0]
+    xb = torch.cat([tr, po[:, :66], torch.zeros(T, 24)], dim=1)
+    R, Tt = parser.get_new_coordinate(be, "male", xb[:1])
+    xn = parser.update_transl_glorot(R.repeat(T, 1, 1), Tt.repeat(T, 1, 1), be, "male", xb)
+    poses = po.clone()
+    poses[:, :3] = xn[:, 3:6]
+    return {"transf_rotmat": R[0].numpy(), "transf_transl": Tt[0].numpy(), "trans": xn[:, :3].numpy(), "poses": poses.numpy(),
+            "joints": parser.get_jts(be, "male", xn).numpy(),
+            "marker_ssm2_67": parser.get_markers(be, "male", xn).reshape(T, -1, 3).numpy(),
+            "marker_cmu_41": parser_cmu.get_markers(be, "male", xn).reshape(T, -1, 3).numpy()}

@@ -392,3 +392,24 @@ def test_box_env_oracle_penetration_termination_matches_reference(golden_dir):
         assert abs(float(o["reward"][0]) - float(g["penbox_reward"][s])) < 1e-4
         assert bool(o["terminated"][0]) == bool(g["penbox_term"][s])
     assert float(o["terms"][0, 6]) == 0.0 and float(o["dist"][0]) < 1.0        # r_pene = 0: ended by penetration
+
+
+def test_canonicalisation_oracle_matches_reference_script(golden_dir, smplx_model):
+    """oracle.sampler.canonicalize_subsequence vs the primitive the reference's own canonicalize_subsequence produced for
+    the same synthetic recording (tests/golden/gen_canon_golden.py); the GPU test of egogen_b200.primitive_batches compares
+    the CUDA path with this same pipeline on this same recording."""
+    from scipy.spatial.transform import Rotation
+    from egogen_b200 import assets
+    from oracle import sampler as osampler
+    g = np.load(os.path.join(golden_dir, "canon_golden.npz"))
+    p67 = SMPLXParserOracle(smplx_model, marker=assets.marker_ids())
+    p41 = SMPLXParserOracle(smplx_model, marker=assets.marker_ids("cmu_41"))
+    assert osampler.canonicalize_subsequence(p67, p41, g["in_betas"], g["in_transl"], g["in_pose"], 150, 210) is None
+    out = osampler.canonicalize_subsequence(p67, p41, g["in_betas"], g["in_transl"], g["in_pose"], 30, 90)
+    assert np.abs(out["transf_rotmat"] - g["transf_rotmat"]).max() < 1e-6 and np.abs(out["transf_transl"] - g["transf_transl"]).max() < 1e-6
+    assert np.abs(out["trans"] - g["trans"]).max() < 2e-6
+    rot = lambda aa: Rotation.from_rotvec(np.asarray(aa, dtype=np.float64)).as_matrix()
+    assert np.abs(rot(out["poses"][:, :3]) - rot(g["poses"][:, :3])).max() < 2e-6       # same rotation (tgm vs scipy axis-angle)
+    assert np.array_equal(out["poses"][:, 3:], g["poses"][:, 3:].astype(np.float32))
+    for k in ("joints", "marker_ssm2_67", "marker_cmu_41"):
+        assert out[k].shape == g[k].shape and np.abs(out[k] - g[k]).max() < 5e-6, k
