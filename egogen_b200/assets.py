@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import json
 import os
-import pickle
 from typing import Dict, Optional
 
 import numpy as np

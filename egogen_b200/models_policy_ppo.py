@@ -4,7 +4,6 @@ ActorCritic :353-358). The modules hold parameters under the reference's state_d
 backward run in the CUDA library through GAMMAPPOPolicy (egogen_b200/ppo_policy.py)."""
 from __future__ import annotations
 
-import torch
 from torch import nn
 
 

@@ -16,7 +16,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib, assets
+from . import _lib
 from .models_gamma_primitive import PREDICTOR_CFG, GAMMAPrimitiveVAE
 
 DEFAULT_LOSSCFG = {"weight_rec": 1.0, "weight_td": 3.0, "weight_kld": 1.0, "annealing_kld": False, "robust_kld": True}

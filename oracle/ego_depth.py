@@ -4,7 +4,6 @@ rasterisations in experiments/gen_egobody_depth.py) => parity unpinned; this ora
 pinhole rays from the head camera (camera convention of experiments/gen_egobody_depth.py:163-199: eye at the mean of
 joints 23/24, gaze from joints 56/57), marched through the reference's calc_sdf field (motion/crowd_ppo/utils.py:54-84):
 t <- t + max(d, eps) until d < eps, t > max_range or max_steps."""
-import numpy as np
 import torch
 
 from .sdf import calc_sdf
