@@ -137,5 +137,16 @@ for sched in (0, 1):
                 f"c{sched}_reg_has_grad": np.array(int(any(p.grad is not None and p.grad.abs().sum() > 0 for p in op3.model.regressor.parameters())))})
     out.update(c_betas=cb, c_eps=eps_c)
 
+# ---- learning-rate rule of the train loops (baseops.get_scheduler 'lambda', stepped once per epoch :526-529,560) ------
+from models import baseops as ref_baseops                     # noqa: E402
+w = torch.nn.Parameter(torch.zeros(1))
+opt = torch.optim.Adam([w], lr=5e-4)
+sched = ref_baseops.get_scheduler(opt, policy="lambda", num_epochs_fix=100, num_epochs=400)
+lrs = []
+for epoch in range(400):
+    lrs.append(opt.param_groups[0]["lr"])                    # the rate the epoch's optimiser steps use
+    opt.step(); sched.step()
+out["sched_lr"] = np.array(lrs, dtype=np.float64)
+
 np.savez_compressed(os.path.join(HERE, "train_golden.npz"), **{k: np.asarray(v) for k, v in out.items()})
 print("wrote train_golden.npz", {k: np.asarray(v).shape for k, v in out.items()})

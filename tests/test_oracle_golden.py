@@ -413,3 +413,16 @@ def test_canonicalisation_oracle_matches_reference_script(golden_dir, smplx_mode
     assert np.array_equal(out["poses"][:, 3:], g["poses"][:, 3:].astype(np.float32))
     for k in ("joints", "marker_ssm2_67", "marker_cmu_41"):
         assert out[k].shape == g[k].shape and np.abs(out[k] - g[k]).max() < 5e-6, k
+
+
+def test_train_loop_lr_rule_matches_reference_scheduler(golden_dir):
+    """lr_at(epoch) of the train-op mirrors vs the reference's get_scheduler('lambda') stepped once per epoch."""
+    from egogen_b200.train_gamma_predictor import GAMMAPrimitiveVAETrainOP
+    from egogen_b200.train_gamma_regressor import GAMMARegressorTrainOP
+    g = np.load(os.path.join(golden_dir, "train_golden.npz"))
+    cfg = {"learning_rate": 5e-4, "num_epochs": 400, "num_epochs_fix": 100}
+    for cls in (GAMMAPrimitiveVAETrainOP, GAMMARegressorTrainOP):
+        op = cls(trainconfig=cfg, device="cpu")
+        mine = np.array([op.lr_at(e) for e in range(400)])
+        assert np.allclose(mine, g["sched_lr"], rtol=1e-12, atol=0), cls.__name__
+    assert g["sched_lr"][0] == 5e-4 and g["sched_lr"][100] == 5e-4 and g["sched_lr"][399] < 5e-6
