@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include "nn.cuh"
+#include "motion_tc.cuh"
 
 namespace eg {
 
@@ -952,6 +953,7 @@ struct EgMotion {
   DecodeW dw{};
   RegW rw{};
   int fused = 1;
+  mtc::MotionTc* tc = nullptr;            // tcgen05 decode / regressor (motion_tc.cu); nullptr or unavailable -> SIMT fused kernels
 };
 
 namespace {
@@ -1067,6 +1069,8 @@ extern "C" int eg_motion_create(const EgMotionDims* dims, const void* const* wei
     EG_CUDA_CHECK(cudaFuncSetAttribute(fused_regressor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRegSmem));
     int rc = motion_build_transposed(h, nullptr);
     if (rc) { delete h; return rc; }
+    rc = mtc::create(&h->tc, *dims, h->w.data(), nullptr);
+    if (rc) { mtc::destroy(h->tc); delete h; return rc; }
     EG_CUDA_CHECK(cudaDeviceSynchronize());
   }
   *out = h;
@@ -1077,7 +1081,9 @@ extern "C" int eg_motion_refresh(EgMotion* h, void* stream) {
   EG_REQUIRE(h != nullptr, "null handle");
   if (!h->fused) return EG_OK;
   EG_CUDA_CHECK(cudaSetDevice(h->device));
-  return motion_build_transposed(h, as_stream(stream));
+  int rc = motion_build_transposed(h, as_stream(stream));
+  if (rc) return rc;
+  return mtc::refresh(h->tc, h->w.data(), as_stream(stream));
 }
 
 extern "C" int eg_motion_set_fused(EgMotion* h, int fused) {
@@ -1094,6 +1100,7 @@ extern "C" void eg_motion_destroy(EgMotion* h) {
   float* bufs[] = {h->gi, h->gh, h->h, h->hx, h->c, h->t1, h->t2, h->rh, h->rbase, h->rt, h->xbc, h->hx2, h->yp2};
   for (auto p : bufs) cudaFree(p);
   cudaFree(h->dcnt);
+  mtc::destroy(h->tc);
   delete h;
 }
 
@@ -1131,7 +1138,11 @@ extern "C" int eg_motion_sample_prior(EgMotion* hd, const float* X, int ldx_env,
     const char* e = getenv("EG_DECODE_WS");
     hd->decode_ws = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  if (hd->fused && hd->decode_ws && B >= 64 && H == 256 && Hm == 512 && D == 201) {
+  if (hd->fused && mtc::decode_available(hd->tc)) {
+    // tcgen05 decode (motion_tc.cu): first-step input term gi_1 = c + y_0 Wy^T, then one 16-CTA cluster per 128 rows
+    EG_TRY(linear(st, Y + D, ldY, B, w[P_DRNN_WIH] + H + Z, Kin, nullptr, D, H3, hd->c, H3, ACT_NONE, 0.f, nullptr, 0, 1));
+    EG_TRY(mtc::decode(hd->tc, hd->c, hd->h, Y, B, st));
+  } else if (hd->fused && hd->decode_ws && B >= 64 && H == 256 && Hm == 512 && D == 201) {
     // weight-stationary 2-D decode: 18 column-slice CTAs per 32-row block (see decode_ws_kernel)
     const int n_rb = (B + dws::RB - 1) / dws::RB, D4 = (D + 3) & ~3;
     EG_CUDA_CHECK(cudaMemsetAsync(hd->dcnt, 0, n_rb * sizeof(unsigned), st));
@@ -1153,6 +1164,11 @@ extern "C" int eg_motion_sample_prior(EgMotion* hd, const float* X, int ldx_env,
   }
   // ---- regressor over all B*20 marker frames (frames 0,1 are computed and discarded) ----
   const int M = B * 20, Hr = d.reg_h, BD = d.body_dim, Kr = D + BD + 10;
+  if (hd->fused && mtc::regress_available(hd->tc)) {
+    EG_TRY(mtc::regress(hd->tc, Y, betas, B, hd->xbc, st));
+    EG_LAUNCH(regressor_tail_kernel, (M * 32 + 127) / 128, 128, 0, st, hd->xbc, M, 20, 2, Yb);
+    return EG_OK;
+  }
   if (hd->fused) {
     EG_LAUNCH(fused_regressor_kernel, (M + RR - 1) / RR, RWARPS * 32, kRegSmem, st, hd->rw, Y, betas, 20, M, d.reg_blocks,
               d.reg_recur, hd->xbc);

@@ -47,6 +47,38 @@ def world(dev, smplx_model):
     return dict(venv=venv, orc=orc, genop=genop, vposer=vposer, combo=combo, vp_o=vp_o, sampler=sampler, E=E, lbs=lbs)
 
 
+def _assert_sample_prior_close(world, X, betas, z, Y, Yb):
+    """GPU sample_prior against the oracle nets evaluated in FLOAT64 (the fp32 oracle is itself ~1e-4 off in the axis-angle
+    columns of ill-conditioned joints, so it cannot referee between two fp32-class implementations).
+    * markers Y and the body-parameter columns the regressor emits directly (transl, hand PCA): tight absolute bounds;
+    * axis-angle columns: 1e-4 wherever the 6-D -> rotation conversion is well conditioned. Gram-Schmidt divides by the norm
+      of the (orthogonalised) 6-D columns, and the synthetic regressor emits some joints with norms down to 2e-3, where an
+      input error of 5e-7 becomes 2.5e-4; those joints - counted and required to be few - get 1e-5 x the amplification."""
+    import copy
+    c64 = copy.deepcopy(world["combo"]).double().eval()
+    b = X.shape[1]
+    b18 = betas.double().unsqueeze(0).repeat(18, 1, 1)
+    with torch.no_grad():
+        Yo = c64.predictor.sample_prior(X.double(), z.double())
+        xb = c64.regressor.forward_cont(Yo.reshape(18 * b, 201), b18.reshape(18 * b, 10))
+        Ybo = c64.regressor.cont2aa(xb).view(18, b, 93)
+    Y, Yb = Y.cpu().double(), Yb.cpu().double()
+    assert Y.shape == (18, b, 201) and Yb.shape == (18, b, 93)
+    assert torch.allclose(Y, Yo, atol=2e-5, rtol=1e-4), (Y - Yo).abs().max()
+    assert torch.allclose(Yb[..., :3], Ybo[..., :3], atol=5e-6, rtol=1e-5), (Yb[..., :3] - Ybo[..., :3]).abs().max()
+    assert torch.allclose(Yb[..., 69:], Ybo[..., 69:], atol=5e-6, rtol=1e-5), (Yb[..., 69:] - Ybo[..., 69:]).abs().max()
+    x6 = xb[:, 3:135].reshape(-1, 22, 3, 2)
+    a1, a2 = x6[..., 0], x6[..., 1]
+    b1 = a1 / a1.norm(dim=-1, keepdim=True)
+    a2o = a2 - (b1 * a2).sum(-1, keepdim=True) * b1
+    amp = (1.0 / torch.minimum(a1.norm(dim=-1), a2o.norm(dim=-1))).clamp_min(1.0).view(18, b, 22, 1)
+    tol = torch.maximum(torch.full_like(amp, 1e-4), 1e-5 * amp)
+    err = (Yb[..., 3:69] - Ybo[..., 3:69]).abs().view(18, b, 22, 3)
+    assert (amp > 10.0).double().mean().item() < 0.1, "the test model must keep most joints well conditioned"
+    bad = err > tol + 1e-4 * Ybo[..., 3:69].abs().view(18, b, 22, 3)
+    assert not bad.any(), (err.max(), int(bad.sum()))
+
+
 def test_sample_prior_matches_oracle(dev, world):
     g = torch.Generator().manual_seed(1)
     b = 5
@@ -54,14 +86,7 @@ def test_sample_prior_matches_oracle(dev, world):
     z = torch.randn(b, 128, generator=g)
     betas = torch.randn(b, 10, generator=g) * 0.5
     Y, Yb = world["genop"].model.sample_prior(X.to(dev), betas.unsqueeze(0).repeat(18, 1, 1).to(dev), z.to(dev))
-    with torch.no_grad():
-        Yo, Ybo = world["combo"].sample_prior(X, betas.unsqueeze(0).repeat(18, 1, 1), z)
-    assert Y.shape == (18, b, 201) and Yb.shape == (18, b, 93)
-    assert torch.allclose(Y.cpu(), Yo, atol=2e-5, rtol=1e-4)
-    # rotation entries go through 6-D -> rotmat -> quaternion -> axis-angle; compare as rotations
-    assert torch.allclose(Yb.cpu()[..., :3], Ybo[..., :3], atol=5e-5, rtol=1e-4)
-    assert torch.allclose(Yb.cpu()[..., 69:], Ybo[..., 69:], atol=5e-5, rtol=1e-4)
-    assert torch.allclose(Yb.cpu()[..., 3:69], Ybo[..., 3:69], atol=2e-4, rtol=1e-3)
+    _assert_sample_prior_close(world, X, betas, z, Y, Yb)
 
 
 def test_fused_motion_kernels_match_layerwise(dev, world):
@@ -93,18 +118,15 @@ def test_vposer_matches_oracle(dev, world):
 
 @pytest.mark.parametrize("b", [96, 70, 256])
 def test_sample_prior_large_batch_matches_oracle(dev, world, b):
-    """B >= 64 takes the weight-stationary 2-D decode kernel (18 column-slice CTAs per 32-row block exchanging
-    activations through L2); 70 exercises the ragged last row block, 256 the bench shape."""
+    """The tcgen05 decode (one 16-CTA cluster per 128 rows) and regressor (128 marker frames per CTA): 70 and 96 exercise
+    ragged last tiles, 256 is the bench shape."""
     g = torch.Generator().manual_seed(100 + b)
     X = torch.randn(2, b, 201, generator=g) * 0.3
     z = torch.randn(b, 128, generator=g)
     betas = torch.randn(b, 10, generator=g) * 0.5
     Y, Yb = world["genop"].model.sample_prior(X.to(dev), betas.unsqueeze(0).repeat(18, 1, 1).to(dev), z.to(dev))
-    with torch.no_grad():
-        Yo, Ybo = world["combo"].sample_prior(X, betas.unsqueeze(0).repeat(18, 1, 1), z)
-    assert torch.allclose(Y.cpu(), Yo, atol=2e-5, rtol=1e-4), (Y.cpu() - Yo).abs().max()
-    assert torch.allclose(Yb.cpu(), Ybo, atol=1e-4, rtol=1e-4), (Yb.cpu() - Ybo).abs().max()
-    # and twice in a row (the arrival counters are re-armed per launch)
+    _assert_sample_prior_close(world, X, betas, z, Y, Yb)
+    # and twice in a row (bit-identical: fixed MMA order, no atomics)
     Y2, _ = world["genop"].model.sample_prior(X.to(dev), betas.unsqueeze(0).repeat(18, 1, 1).to(dev), z.to(dev))
     assert torch.equal(Y, Y2)
 
