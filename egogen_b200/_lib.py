@@ -103,6 +103,7 @@ PROTOTYPES = {
     "eg_env_step": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P]),
     "eg_env_reset": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
     "eg_env_reset_masked": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
+    "eg_env_restart_from_pool": (_I, [C.POINTER(EgEnvBuffers), C.POINTER(EgEnvBuffers), _I, _P, _I, _P, _P]),
     "eg_policy_param_count": (_L, [C.POINTER(EgPolicyDims), C.POINTER(C.c_int64)]),
     "eg_policy_create": (_I, [C.POINTER(EgPolicyDims), _P, _P, _I, C.POINTER(_P)]),
     "eg_policy_destroy": (None, [_P]),
@@ -112,6 +113,8 @@ PROTOTYPES = {
     "eg_moments": (_I, [_P, _L, _P, _P]),
     "eg_adv_normalize": (_I, [_P, _I, _P, _F, _P, _P]),
     "eg_clip_adamw_step": (_I, [_P, _P, _P, _F, _F, _F, _F, _F, _F, _I, _P]),
+    "eg_dp_reduce_norm": (_I, [_P, _P, _I, _I, _L, _L, _P, _P, _P, _P]),
+    "eg_dp_adamw_gather": (_I, [_P, _P, _I, _I, _L, _L, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I, _P]),
     "eg_gae": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_double, C.c_double, _P, _P, _P]),
     "eg_cvae_param_count": (_L, [C.POINTER(EgCvaeDims)]),
     "eg_cvae_create": (_I, [C.POINTER(EgCvaeDims), _P, _P, _I, C.POINTER(_P)]),

@@ -227,56 +227,91 @@ class CrowdVectorEnv:
     # ---- sync-free restart of finished episodes ------------------------------------------------------------
     _POOL_FIELDS = ("state", "seed", "R0", "T0", "betas", "dist", "steps", "goal", "ego", "obs_dist", "obs_time")
 
-    def _validated_candidates(self, n: int, pool: int = 2048):
-        """n start candidates that eg_env_reset is known to accept, TOGETHER WITH the initial env state the reset
-        computed for them: the sampler's candidates are run through the reset pipeline once on scratch slots (same accept
-        test as reset(), crowd_env_2f.py:379-380 / the box env's map test; same canonicalisation, features and
-        ego-sensing) and the accepted rows of every state buffer are kept. Restarting an episode is then a masked copy -
-        no SMPL-X pass, no accept mask to read back. One host sync per `pool` candidates instead of one per vector step."""
+    def _refill_pool(self, pool: int = 2048, min_rows: int = 0):
+        """(Re)build the pool of start candidates that eg_env_reset is known to accept, TOGETHER WITH the initial env state
+        the reset computed for them: the sampler's candidates are run through the reset pipeline once on scratch slots (same
+        accept test as reset(), crowd_env_2f.py:379-380 / the box env's map test; same canonicalisation, features and
+        ego-sensing) and the accepted rows of every state buffer are kept. Restarting an episode is then a copy of one pool
+        row - no SMPL-X pass, no accept mask to read back. One host sync per `pool` candidates."""
         dev = self.dev
-        vp = getattr(self, "_vpool", None)
-        if vp is None or self._vptr + n > vp["goal"].shape[0]:
-            if getattr(self, "_scratch", None) is None:
-                f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-                P = pool
-                sb = dict(state=f(P, 2, 402), seed=f(P, 2, 93), R0=f(P, 3, 3), T0=f(P, 3), betas=f(P, 10), dist=f(P),
-                          steps=torch.zeros(P, dtype=torch.int32, device=dev), goal=f(P, 3), ego=f(P, 2, 32),
-                          obs_dist=f(P), obs_time=f(P), reward=f(P), terminated=torch.zeros(P, dtype=torch.uint8, device=dev),
-                          goal_reached=None, reward_terms=None, out_markers=None, out_params=None, out_pelvis=None)
-                self._scratch = sb
-                self._scratch_c = _lib.EgEnvBuffers(**{k: (C.c_void_p(v.data_ptr()) if v is not None else None)
-                                                       for k, v in sb.items()})
-                self._scratch_ids = torch.arange(P, dtype=torch.int32, device=dev)
-            parts, have = [], 0
-            while have < max(n, pool // 2):
-                s = self.sampler.next_body(pool)
-                accept = torch.zeros(pool, dtype=torch.int32, device=dev)
-                with torch.cuda.device(dev):
-                    _lib.check(_lib.lib().eg_env_reset(self._h, C.byref(self._scratch_c), _lib.ptr(self._scratch_ids), pool,
-                                                       _lib.ptr(s["world_params"].contiguous()), _lib.ptr(s["goals"].contiguous()),
-                                                       _lib.ptr(s["betas"].contiguous()), _lib.ptr(accept), _lib.stream_ptr(dev)))
-                ok = accept != 0                                         # the one host sync of the refill
-                part = {k: self._scratch[k][ok].clone() for k in self._POOL_FIELDS}
-                part["world_params"] = s["world_params"][ok].clone()
-                parts.append(part)
-                have += int(ok.sum())
-            self._vpool = {k: torch.cat([p_[k] for p_ in parts]) for k in parts[0]}
-            self._vptr = 0
-        a, b = self._vptr, self._vptr + n
-        self._vptr = b
-        out = {k: v[a:b] for k, v in self._vpool.items()}
+        if getattr(self, "_scratch", None) is None:
+            f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+            P = pool
+            sb = dict(state=f(P, 2, 402), seed=f(P, 2, 93), R0=f(P, 3, 3), T0=f(P, 3), betas=f(P, 10), dist=f(P),
+                      steps=torch.zeros(P, dtype=torch.int32, device=dev), goal=f(P, 3), ego=f(P, 2, 32),
+                      obs_dist=f(P), obs_time=f(P), reward=f(P), terminated=torch.zeros(P, dtype=torch.uint8, device=dev),
+                      goal_reached=None, reward_terms=None, out_markers=None, out_params=None, out_pelvis=None)
+            self._scratch = sb
+            self._scratch_c = _lib.EgEnvBuffers(**{k: (C.c_void_p(v.data_ptr()) if v is not None else None)
+                                                   for k, v in sb.items()})
+            self._scratch_ids = torch.arange(P, dtype=torch.int32, device=dev)
+            self._cursor = torch.zeros(2, dtype=torch.int64, device=dev)      # {int64 cursor, uint32 ticket + pad}
+            self._cursor_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        parts, have = [], 0
+        while have < max(min_rows, pool // 2):
+            s = self.sampler.next_body(pool)
+            accept = torch.zeros(pool, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().eg_env_reset(self._h, C.byref(self._scratch_c), _lib.ptr(self._scratch_ids), pool,
+                                                   _lib.ptr(s["world_params"].contiguous()), _lib.ptr(s["goals"].contiguous()),
+                                                   _lib.ptr(s["betas"].contiguous()), _lib.ptr(accept), _lib.stream_ptr(dev)))
+            ok = accept != 0                                         # the one host sync of the refill
+            part = {k: self._scratch[k][ok].clone() for k in self._POOL_FIELDS}
+            part["world_params"] = s["world_params"][ok].clone()
+            parts.append(part)
+            have += int(ok.sum())
+        self._vpool = {k: torch.cat([p_[k] for p_ in parts]).contiguous() for k in parts[0]}
+        self._pool_rows = int(self._vpool["goal"].shape[0])
+        bufs = {k: None for k in self.buf}
+        bufs.update({k: self._vpool[k] for k in self._POOL_FIELDS})
+        self._pool_c = _lib.EgEnvBuffers(**{k: (C.c_void_p(v.data_ptr()) if v is not None else None) for k, v in bufs.items()})
+        self._cursor.zero_()
+        self._used_bound, self._cursor_ev = 0, None
+        self.pool_refills = getattr(self, "pool_refills", 0) + 1
+
+    def _pool_reserve(self, n_max: int):
+        """Make sure the next restart (which consumes at most n_max rows) cannot run past the pool. The exact consumption
+        lives in the device cursor; the host keeps an upper bound (n_max per call since the last value it has SEEN) and
+        tightens it from an asynchronous cursor snapshot when one has landed, or with one blocking read when the bound
+        says the pool might be exhausted. Only a pool that is really used up is rebuilt."""
+        if getattr(self, "_vpool", None) is None:
+            self._refill_pool(min_rows=n_max)
+        if self._cursor_ev is not None and self._cursor_ev[0].query():
+            ev, bound_then = self._cursor_ev                         # true cursor after the call whose bound was bound_then
+            self._used_bound = int(self._cursor_host[0]) + (self._used_bound - bound_then)
+            self._cursor_ev = None
+        if self._used_bound + n_max > self._pool_rows:
+            self._used_bound = int(self._cursor[0].item())           # blocking read: rare (see docstring)
+            self._cursor_ev = None
+            if self._used_bound + n_max > self._pool_rows:
+                self._refill_pool(min_rows=n_max)
+
+    def _validated_candidates(self, n: int):
+        """n pre-validated start candidates (pool rows at the cursor, which advances by n): tests / direct resets."""
+        self._pool_reserve(n)
+        a = int(self._cursor[0].item())
+        self._cursor[0] += n
+        self._used_bound, self._cursor_ev = a + n, None
+        out = {k: v[a:a + n] for k, v in self._vpool.items()}
         out["goals"] = out["goal"]
         return out
 
     def reset_masked(self, mask: torch.Tensor):
         """Restart the envs whose mask entry is non-zero (device uint8 / bool [E], e.g. the `terminated` buffer) without
-        any host synchronisation: slot e takes the pre-computed initial state of the next pre-validated candidate e."""
-        s = self._validated_candidates(self.E)
-        m = mask.bool()
-        for k in self._POOL_FIELDS:
-            dst = self.buf[k]
-            mk = m.view(-1, *([1] * (dst.dim() - 1)))
-            dst.copy_(torch.where(mk, s[k], dst))
+        any host synchronisation: the k-th flagged env takes the k-th unused row of the pre-validated pool
+        (eg_env_restart_from_pool: device-side rank + cursor), so only finished episodes consume candidates."""
+        self._pool_reserve(self.E)
+        m = mask if mask.dtype == torch.uint8 else mask.to(torch.uint8)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().eg_env_restart_from_pool(C.byref(self._cbuf), C.byref(self._pool_c), self._pool_rows,
+                                                           _lib.ptr(m.contiguous()), self.E, _lib.ptr(self._cursor),
+                                                           _lib.stream_ptr(self.dev)))
+        self._used_bound += self.E
+        if self._cursor_ev is None:                                  # asynchronous snapshot of the true consumption
+            self._cursor_host.copy_(self._cursor[:1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.dev))
+            self._cursor_ev = (ev, self._used_bound)
         return m
 
     def reset_from(self, env_ids, world_params, goals, betas):

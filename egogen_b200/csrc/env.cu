@@ -684,6 +684,68 @@ extern "C" int eg_update_transl_glorot(EgLbs* lbs, const float* transf_rotmat, c
   return EG_OK;
 }
 
+// ---- episode restart from a pool of pre-computed initial states (no host synchronisation) ------------------------
+// block e: if mask[e], rank(e) = number of set entries below e, pool row = (cursor + rank) mod pool_rows, copy every
+// state field of that row into slot e. The LAST block to finish (ticket counter) advances the cursor by the number of set
+// entries - every block read the cursor before it took its ticket, so all of them used the old value.
+struct PoolCursor { long long cursor; unsigned ticket; unsigned pad; };
+__global__ void __launch_bounds__(128)
+env_restart_pool_kernel(const EgEnvBuffers dst, const EgEnvBuffers pool, int pool_rows, const uint8_t* __restrict__ mask, int E,
+                        PoolCursor* pc) {
+  __shared__ int red[4];
+  __shared__ int is_last;
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const long long cur = *reinterpret_cast<volatile long long*>(&pc->cursor);
+  auto count_below = [&](int n) {
+    int c = 0;
+    for (int i = tid; i < n; i += 128) c += mask[i] != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0) red[tid >> 5] = c;
+    __syncthreads();
+    const int tot = red[0] + red[1] + red[2] + red[3];
+    __syncthreads();
+    return tot;
+  };
+  if (mask[e] != 0) {
+    const int rank = count_below(e);
+    const int64_t r = (int64_t)((cur + rank) % pool_rows);
+    auto cp = [&](float* d, const float* s_, int n) {
+      for (int i = tid; i < n; i += 128) d[(int64_t)e * n + i] = s_[r * n + i];
+    };
+    cp(dst.state, pool.state, 2 * 402); cp(dst.seed, pool.seed, 2 * 93); cp(dst.R0, pool.R0, 9); cp(dst.T0, pool.T0, 3);
+    cp(dst.betas, pool.betas, 10); cp(dst.goal, pool.goal, 3); cp(dst.ego, pool.ego, 64);
+    if (tid == 0) {
+      dst.dist[e] = pool.dist[r]; dst.steps[e] = pool.steps[r];
+      dst.obs_dist[e] = pool.obs_dist[r]; dst.obs_time[e] = pool.obs_time[r];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    is_last = atomicAdd(&pc->ticket, 1u) == (unsigned)(E - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    const int tot = count_below(E);
+    if (tid == 0) { pc->cursor = cur + tot; pc->ticket = 0; __threadfence(); }
+  }
+}
+
+extern "C" int eg_env_restart_from_pool(const EgEnvBuffers* dst, const EgEnvBuffers* pool, int pool_rows, const uint8_t* mask,
+                                        int E, void* cursor_dev, void* stream) {
+  EG_REQUIRE(dst && pool && mask && cursor_dev, "null pointer");
+  EG_REQUIRE(pool_rows > 0 && E >= 0, "bad sizes");
+  EG_REQUIRE(dst->state && dst->seed && dst->R0 && dst->T0 && dst->betas && dst->dist && dst->steps && dst->goal && dst->ego &&
+             dst->obs_dist && dst->obs_time, "destination buffers incomplete");
+  EG_REQUIRE(pool->state && pool->seed && pool->R0 && pool->T0 && pool->betas && pool->dist && pool->steps && pool->goal &&
+             pool->ego && pool->obs_dist && pool->obs_time, "pool buffers incomplete");
+  if (E == 0) return EG_OK;
+  EG_LAUNCH(env_restart_pool_kernel, E, 128, 0, as_stream(stream), *dst, *pool, pool_rows, mask, E,
+            reinterpret_cast<PoolCursor*>(cursor_dev));
+  return EG_OK;
+}
+
 extern "C" int eg_env_reset_masked(EgEnv* h, const EgEnvBuffers* b, const uint8_t* mask, int E,
                                    const float* world_params, const float* goals, const float* betas_cand,
                                    int32_t* accept, void* stream) {

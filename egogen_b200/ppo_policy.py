@@ -69,10 +69,20 @@ class GAMMAPPOPolicy(nn.Module):
         if expect != n:
             raise _lib.EgError(f"parameter count {n} does not match the library layout {expect}")
         self.n_actor_critic = nac.value
-        self.flat_params = torch.empty(n, dtype=torch.float32, device=dev)
-        self.flat_grads = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.n_params = n
+        self._dp = None
+        if self._world() > 1:
+            self._dp = self._setup_nvlink_optimizer(n, dev)
+        if self._dp is not None:
+            self.flat_params, self.flat_grads = self._dp["params"][:n], self._dp["grads"][:n]
+            chunk = self._dp["n_pad"] // self._dp["world"]
+            self.exp_avg = torch.zeros(chunk, dtype=torch.float32, device=dev)        # this rank's moment slices
+            self.exp_avg_sq = torch.zeros(chunk, dtype=torch.float32, device=dev)
+        else:
+            self.flat_params = torch.empty(n, dtype=torch.float32, device=dev)
+            self.flat_grads = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         for p in ps:
             k = p.numel()
@@ -83,6 +93,55 @@ class GAMMAPPOPolicy(nn.Module):
         self._stats = torch.zeros(8, dtype=torch.float32, device=dev)
         self._mom = torch.zeros(3, dtype=torch.float64, device=dev)
         self.dev = dev
+        if self._world() > 1:                                      # every replica starts from rank 0's initialisation
+            import torch.distributed as dist
+            dist.broadcast(self.flat_params, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+
+    def _setup_nvlink_optimizer(self, n, dev):
+        """Flat parameter / gradient vectors in torch symmetric memory (peer-mapped over NVLink, multicast-mapped through
+        the NVSwitch when the fabric offers it) for the sharded optimiser step of csrc/dp_optim.cu. Returns None - and the
+        policy falls back to one NCCL all_reduce of the gradient per step - when symmetric memory cannot be set up
+        (EG_DP_OPTIM=0, a non-NCCL group such as the gloo CPU tests, or no peer access)."""
+        import os
+        import torch.distributed as dist
+        if os.environ.get("EG_DP_OPTIM", "1") == "0":
+            return None
+        try:
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            if dist.get_backend(group) != "nccl":
+                return None
+            import torch.distributed._symmetric_memory as symm_mem
+            try:
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    symm_mem.enable_symm_mem_for_group(group.group_name)      # required by older torch, a no-op since
+            except Exception:                                     # noqa: BLE001
+                pass
+            W, rank = dist.get_world_size(group), dist.get_rank(group)
+            if W > 16:
+                return None
+            n_pad = -(-n // (4 * W)) * 4 * W
+            bufs = {"params": symm_mem.empty(n_pad, dtype=torch.float32, device=dev),
+                    "grads": symm_mem.empty(n_pad, dtype=torch.float32, device=dev),
+                    "scratch": symm_mem.empty(max(W, 2), dtype=torch.float64, device=dev)}
+            hdl = {}
+            for k, t in bufs.items():
+                t.zero_()
+                hdl[k] = symm_mem.rendezvous(t, group.group_name)
+            use_mc = os.environ.get("EG_DP_MULTICAST", "1") != "0"
+            mc = {k: (int(getattr(hdl[k], "multicast_ptr", 0) or 0) if use_mc else 0) for k in ("params", "grads")}
+            ptrs = {k: (C.c_void_p * W)(*[int(x) for x in hdl[k].buffer_ptrs]) for k in bufs}
+            dp = dict(bufs, hdl=hdl, mc=mc, ptrs=ptrs, world=W, rank=rank, n_pad=n_pad,
+                      gred=torch.zeros(n_pad // W, dtype=torch.float32, device=dev),
+                      work=torch.zeros(2, dtype=torch.float64, device=dev))
+            torch.cuda.synchronize(dev)
+            hdl["grads"].barrier(channel=0)
+            return dp
+        except Exception as e:                                     # noqa: BLE001 - any failure means "no symmetric memory here"
+            import warnings
+            warnings.warn(f"NVLink sharded optimiser unavailable ({type(e).__name__}: {e}); using NCCL all_reduce")
+            return None
 
     def handle(self):
         if self._h is None:
@@ -158,19 +217,28 @@ class GAMMAPPOPolicy(nn.Module):
         import torch.distributed as dist
         return dist.get_world_size(self.pg) if (dist.is_available() and dist.is_initialized()) else 1
 
-    def normalize_adv(self, adv):
-        """per-minibatch (mean, unbiased std) normalisation (:192-195); global over ranks when distributed."""
-        lib = _lib.lib()
-        n = adv.numel()
+    def adv_moments(self, adv, out=None):
+        """{sum, sum of squares, count} of one minibatch's advantages as device doubles (local to this rank)."""
+        mom = self._mom if out is None else out
         with torch.cuda.device(self.dev):
-            _lib.check(lib.eg_moments(_lib.ptr(adv), n, _lib.ptr(self._mom), _lib.stream_ptr(self.dev)))
-            self._mom[2] = float(n)
+            _lib.check(_lib.lib().eg_moments(_lib.ptr(adv), adv.numel(), _lib.ptr(mom), _lib.stream_ptr(self.dev)))
+        mom[2] = float(adv.numel())
+        return mom
+
+    def normalize_adv(self, adv, moments=None):
+        """per-minibatch (mean, unbiased std) normalisation (:192-195); global over ranks when distributed.
+        `moments`: already rank-summed {sum, sumsq, count} (learn() reduces the moments of ALL its minibatches in one
+        collective up front); None computes and reduces them here."""
+        n = adv.numel()
+        if moments is None:
+            moments = self.adv_moments(adv)
             if self._world() > 1:
                 import torch.distributed as dist
-                dist.all_reduce(self._mom, group=self.pg)
-            out = torch.empty_like(adv)
-            _lib.check(lib.eg_adv_normalize(_lib.ptr(adv), n, _lib.ptr(self._mom), self._eps, _lib.ptr(out),
-                                            _lib.stream_ptr(self.dev)))
+                dist.all_reduce(moments, group=self.pg)
+        out = torch.empty_like(adv)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().eg_adv_normalize(_lib.ptr(adv), n, _lib.ptr(moments), self._eps, _lib.ptr(out),
+                                                   _lib.stream_ptr(self.dev)))
         return out
 
     def _opt_hparams(self):
@@ -178,11 +246,11 @@ class GAMMAPPOPolicy(nn.Module):
         b1, b2 = g.get("betas", (0.9, 0.999))
         return float(g["lr"]), float(b1), float(b2), float(g.get("eps", 1e-8)), float(g.get("weight_decay", 0.01))
 
-    def loss_backward(self, mb, global_batch: Optional[int] = None):
+    def loss_backward(self, mb, global_batch: Optional[int] = None, moments=None):
         """forward + PPO loss + backward of one minibatch into flat_grads; stats land in self._stats."""
         B = mb.act.shape[0]
         gb = global_batch if global_batch is not None else B * self._world()
-        adv = self.normalize_adv(mb.adv.contiguous()) if self._norm_adv else mb.adv.contiguous()
+        adv = self.normalize_adv(mb.adv.contiguous(), moments) if self._norm_adv else mb.adv.contiguous()
         st, eg, di, ti = self._obs_ptrs(mb.obs)
         self._stats.zero_()
         with torch.cuda.device(self.dev):
@@ -193,22 +261,43 @@ class GAMMAPPOPolicy(nn.Module):
                 float(self.actor.max_logvar), 1, _lib.ptr(self._stats), _lib.stream_ptr(self.dev)))
 
     def optimizer_step(self):
+        """clip_grad_norm_(actor + critic) + AdamW (:241-247). With N > 1 ranks the gradient is first summed over the
+        ranks: by the sharded NVLink step (eg_dp_reduce_norm -> eg_dp_adamw_gather, each rank updates 1/N of the
+        parameters and broadcasts them) when symmetric memory is set up, else by one NCCL all_reduce."""
         lr, b1, b2, eps, wd = self._opt_hparams()
         self._opt_step += 1
+        lib, st = _lib.lib(), _lib.stream_ptr(self.dev)
+        dp = self._dp
         with torch.cuda.device(self.dev):
-            _lib.check(_lib.lib().eg_clip_adamw_step(self.handle(), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
-                                                     float(self._grad_norm or 0.0), lr, b1, b2, eps, wd, self._opt_step,
-                                                     _lib.stream_ptr(self.dev)))
+            if dp is not None:
+                W, rank, n_pad = dp["world"], dp["rank"], dp["n_pad"]
+                bar = dp["hdl"]["grads"].barrier
+                bar(channel=0)                                       # every rank's backward has written its gradient
+                _lib.check(lib.eg_dp_reduce_norm(dp["ptrs"]["grads"], C.c_void_p(dp["mc"]["grads"] or None), W, rank, n_pad,
+                                                 self.n_actor_critic, _lib.ptr(dp["gred"]), dp["ptrs"]["scratch"],
+                                                 _lib.ptr(dp["work"]), st))
+                bar(channel=0)                                       # all norm shares published, all slices read
+                _lib.check(lib.eg_dp_adamw_gather(dp["ptrs"]["params"], C.c_void_p(dp["mc"]["params"] or None), W, rank, n_pad,
+                                                  self.n_actor_critic, _lib.ptr(dp["gred"]), _lib.ptr(dp["scratch"]),
+                                                  _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                                  float(self._grad_norm or 0.0), lr, b1, b2, eps, wd, self._opt_step, st))
+                bar(channel=0)                                       # every rank's slice of the new parameters has landed
+                return
+            if self._world() > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.flat_grads, group=self.pg)      # fallback: ONE allreduce of the whole gradient
+            _lib.check(lib.eg_clip_adamw_step(self.handle(), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                              float(self._grad_norm or 0.0), lr, b1, b2, eps, wd, self._opt_step, st))
 
-    def learn_minibatch(self, mb, global_batch: Optional[int] = None):
+    def learn_minibatch(self, mb, global_batch: Optional[int] = None, moments=None, reduce_stats: bool = True):
         """One iteration of the inner loop of learn (:189-252). mb: Batch(obs, act, logp_old, adv, returns)
-        with CUDA tensors. Returns a clone of the device stats tensor."""
-        self.loss_backward(mb, global_batch)
-        if self._world() > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_grads, group=self.pg)          # ONE allreduce of the whole gradient
-            dist.all_reduce(self._stats, group=self.pg)
+        with CUDA tensors. Returns a clone of the device stats tensor (rank-summed unless reduce_stats is False:
+        learn() sums the statistics of all its minibatches in one collective at the end)."""
+        self.loss_backward(mb, global_batch, moments)
         self.optimizer_step()
+        if reduce_stats and self._world() > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._stats, group=self.pg)
         return self._stats.clone()
 
     def learn(self, batch, batch_size: int, repeat: int, **kwargs):
@@ -218,21 +307,37 @@ class GAMMAPPOPolicy(nn.Module):
         N = batch.act.shape[0]
         out = {k: [] for k in ("loss", "loss/clip", "loss/vf", "loss/ent", "loss/kld")}
         all_stats = []
+        multi = self._world() > 1
+        if multi:
+            import torch.distributed as dist
         for step in range(repeat):
             perm = np.random.permutation(N)
             starts = list(range(0, N, batch_size))
             if len(starts) > 1 and N - starts[-1] < batch_size:
                 starts = starts[:-1]                                   # merge_last
-            stats = None
-            for i, s in enumerate(starts):
-                e = N if i == len(starts) - 1 else s + batch_size
-                idx = torch.as_tensor(perm[s:e], device=self.dev)
-                mb = Batch(obs={k: v.index_select(0, idx) for k, v in batch.obs.items()},
-                           act=batch.act.index_select(0, idx), logp_old=batch.logp_old.index_select(0, idx),
-                           adv=batch.adv.index_select(0, idx), returns=batch.returns.index_select(0, idx))
-                stats = self.learn_minibatch(mb)
-                all_stats.append(stats)
-            if repeat > 1 and stats is not None and float(stats[4].item()) >= 0.02:
+            bounds = [(s, N if i == len(starts) - 1 else s + batch_size) for i, s in enumerate(starts)]
+            perm_dev = torch.as_tensor(perm, device=self.dev)          # one H2D copy of the permutation per repeat
+            mbs = []
+            for s0, e0 in bounds:
+                idx = perm_dev[s0:e0]
+                mbs.append(Batch(obs={k: v.index_select(0, idx) for k, v in batch.obs.items()},
+                                 act=batch.act.index_select(0, idx), logp_old=batch.logp_old.index_select(0, idx),
+                                 adv=batch.adv.index_select(0, idx), returns=batch.returns.index_select(0, idx)))
+            moms = None
+            if self._norm_adv:                                         # advantage moments of every minibatch, ONE collective
+                moms = torch.zeros(len(mbs), 3, dtype=torch.float64, device=self.dev)
+                for i, mb in enumerate(mbs):
+                    self.adv_moments(mb.adv.contiguous(), out=moms[i])
+                if multi:
+                    dist.all_reduce(moms, group=self.pg)
+            rep_stats = [self.learn_minibatch(mb, moments=None if moms is None else moms[i], reduce_stats=False)
+                         for i, mb in enumerate(mbs)]
+            if rep_stats:
+                S_rep = torch.stack(rep_stats)
+                if multi:
+                    dist.all_reduce(S_rep, group=self.pg)              # loss statistics of the repeat, ONE collective
+                all_stats.extend(S_rep.unbind(0))
+            if repeat > 1 and rep_stats and float(all_stats[-1][4].item()) >= 0.02:
                 break                                                  # KL early stop on the last minibatch (:254-257)
         if all_stats:
             S = torch.stack(all_stats).cpu().numpy()                   # one D2H read per learn() call
@@ -244,12 +349,23 @@ class GAMMAPPOPolicy(nn.Module):
         return out
 
     # ---- optimiser state in torch.optim.AdamW format (checkpoint "optim" entry, main_ppo.py:207-213) ----
+    def _full_moments(self):
+        """(exp_avg, exp_avg_sq) as full-length vectors: the sharded optimiser keeps only this rank's slice."""
+        if self._dp is None:
+            return self.exp_avg, self.exp_avg_sq
+        import torch.distributed as dist
+        full = [torch.empty(self._dp["n_pad"], dtype=torch.float32, device=self.dev) for _ in range(2)]
+        dist.all_gather_into_tensor(full[0], self.exp_avg, group=self.pg)
+        dist.all_gather_into_tensor(full[1], self.exp_avg_sq, group=self.pg)
+        return full[0][:self.n_params], full[1][:self.n_params]
+
     def export_optim_state(self):
+        exp_avg, exp_avg_sq = self._full_moments()
         off = 0
         for p in self._ordered_params():
             k = p.numel()
             self.optim.state[p] = {"step": torch.tensor(float(self._opt_step)),
-                                   "exp_avg": self.exp_avg[off:off + k].view_as(p),
-                                   "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p)}
+                                   "exp_avg": exp_avg[off:off + k].view_as(p),
+                                   "exp_avg_sq": exp_avg_sq[off:off + k].view_as(p)}
             off += k
         return self.optim.state_dict()

@@ -275,6 +275,13 @@ int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_ids, int n,
  * host. accept [E] = 1 where a slot was restarted. */
 int eg_env_reset_masked(EgEnv* h, const EgEnvBuffers* b, const uint8_t* mask, int E, const float* world_params,
                         const float* goals, const float* betas_cand, int32_t* accept, void* stream);
+/* Restart from a POOL of pre-computed initial states (rows of `pool`, the state fields of EgEnvBuffers as written by
+ * eg_env_reset for accepted candidates): slot e with mask[e] != 0 takes pool row (cursor + rank(e)) mod pool_rows, rank(e) =
+ * number of set mask entries below e, and the device cursor advances by the number of set entries - only finished
+ * episodes consume candidates, and nothing is read back to the host. cursor_dev: 16 zero-initialised device bytes
+ * (int64 cursor, uint32 ticket, pad) owned by the caller. Same reference behaviour as above (crowd_env_2f.py:320). */
+int eg_env_restart_from_pool(const EgEnvBuffers* dst, const EgEnvBuffers* pool, int pool_rows, const uint8_t* mask,
+                             int E, void* cursor_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * PPO policy - replaces GAMMAPolicyBase / GAMMAActor / GAMMACritic forward
@@ -322,6 +329,25 @@ int eg_adv_normalize(const float* adv, int n, const double* moments3, float eps,
 /* clip_grad_norm_ over the actor+critic prefix (max_grad_norm <= 0 disables) fused with one AdamW step */
 int eg_clip_adamw_step(EgPolicy* h, float* exp_avg, float* exp_avg_sq, float max_grad_norm, float lr, float beta1,
                        float beta2, float eps, float weight_decay, int step, void* stream);
+/* Data-parallel form of  all_reduce(gradients) ; eg_clip_adamw_step  for `world` ranks of one NVLink domain, one process
+ * per GPU (csrc/dp_optim.cu; same reference step, ppo_policy.py:241-247). The flat gradient and parameter vectors of every
+ * rank live in peer-mapped (symmetric) memory, padded to n_pad = multiple of 4 * world floats; rank r owns elements
+ * [r * n_pad / world, (r + 1) * n_pad / world).
+ *   eg_dp_reduce_norm : gred [n_pad / world] = sum over ranks of the own gradient slice (grads_mc: multicast address of the
+ *     gradient buffers -> in-switch reduction; NULL -> peer loads through grads_ptrs, summed in rank order), and this rank's
+ *     share of the squared norm over the first n_clip elements is written to slot `rank` of EVERY rank's scratch
+ *     (scratch_ptrs: `world` device pointers, each to double[world]). work: 16 zero-initialised device bytes.
+ *   -- the caller runs a cross-rank barrier before (all backwards done) and after eg_dp_reduce_norm --
+ *   eg_dp_adamw_gather: clip coefficient from the sum of the scratch slots, AdamW on the own slice (moment slices
+ *     [n_pad / world], local), updated parameters stored to every rank (params_mc multicast, or peer stores).
+ *   -- and a barrier after it, before any rank reads the parameters again.
+ * grads_ptrs / params_ptrs / scratch_ptrs are HOST arrays of `world` device pointers (index = rank). */
+int eg_dp_reduce_norm(const void* const* grads_ptrs, const void* grads_mc, int world, int rank, int64_t n_pad,
+                      int64_t n_clip, float* gred, const void* const* scratch_ptrs, void* work, void* stream);
+int eg_dp_adamw_gather(const void* const* params_ptrs, void* params_mc, int world, int rank, int64_t n_pad,
+                       int64_t n_clip, const float* gred, const double* scratch_local, float* exp_avg_slice,
+                       float* exp_avg_sq_slice, float max_grad_norm, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, void* stream);
 /* tianshou _gae_return on [T,E] time-major rollouts: v_next must already be critic(obs_next) unmasked;
  * terminated masks it, end_flag = terminated | truncated | last-stored-step. adv, ret [T,E]. */
 int eg_gae(const float* v_s, const float* v_next, const float* rew, const uint8_t* terminated,

@@ -379,22 +379,33 @@ def test_sync_free_collect_restarts_finished_envs(dev):
 
 
 def test_masked_reset_edge_cases(dev, world):
-    """reset_masked (masked copy of pre-computed initial states) and the C entry point eg_env_reset_masked: an all-zero
-    mask changes nothing, an all-one mask restarts every slot with candidate e in slot e, the pooled initial state is
-    what a direct reset of the same candidate produces, a null mask is an error."""
+    """reset_masked (eg_env_restart_from_pool: copy of pre-computed initial states) and the C entry point
+    eg_env_reset_masked: an all-zero mask changes nothing AND consumes no candidate, a sparse mask consumes exactly as many
+    pool rows as it has set entries (k-th flagged env <- k-th unused row), an all-one mask restarts every slot in order, the
+    pooled initial state is what a direct reset of the same candidate produces, a null mask is an error."""
     import ctypes as C
     from egogen_b200 import _lib
     venv, E = world["venv"], world["E"]
     venv.reset()
     before = {k: venv.buf[k].clone() for k in ("state", "seed", "R0", "T0", "steps", "goal")}
+    venv.reset_masked(torch.ones(E, dtype=torch.uint8, device=dev))       # builds the pool
+    venv.reset()
+    before = {k: venv.buf[k].clone() for k in ("state", "seed", "R0", "T0", "steps", "goal")}
+    c0 = int(venv._cursor[0].item())
     venv.reset_masked(torch.zeros(E, dtype=torch.uint8, device=dev))
     for k, v in before.items():
         assert torch.equal(venv.buf[k], v), k
+    assert int(venv._cursor[0].item()) == c0                              # nothing terminated -> no candidate consumed
+    sparse = torch.zeros(E, dtype=torch.uint8, device=dev); sparse[1] = 1; sparse[E - 1] = 1
+    venv.reset_masked(sparse)
+    assert int(venv._cursor[0].item()) == c0 + 2
+    assert torch.equal(venv.buf["goal"][1], venv._vpool["goal"][c0]) and torch.equal(venv.buf["goal"][E - 1], venv._vpool["goal"][c0 + 1])
+    assert torch.equal(venv.buf["state"][0], before["state"][0])          # unflagged slots untouched
     venv.step(torch.zeros(E, 128, device=dev))
     assert bool((venv.buf["steps"] == 1).all())
     venv.reset_masked(torch.ones(E, dtype=torch.uint8, device=dev))
     assert bool((venv.buf["steps"] == 0).all())
-    lo = venv._vptr - E
+    lo = int(venv._cursor[0].item()) - E
     pooled = {k: venv._vpool[k][lo:lo + E].clone() for k in ("goal", "world_params", "betas", "state", "seed", "R0", "T0", "ego", "dist")}
     assert torch.equal(venv.buf["goal"], pooled["goal"])                # candidate e -> slot e
     after = {k: venv.buf[k].clone() for k in ("state", "seed", "R0", "T0", "ego", "dist")}
