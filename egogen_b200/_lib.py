@@ -105,6 +105,7 @@ PROTOTYPES = {
     "eg_env_reset_masked": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
     "eg_env_restart_from_pool": (_I, [C.POINTER(EgEnvBuffers), C.POINTER(EgEnvBuffers), _I, _P, _I, _P, _P]),
     "eg_policy_param_count": (_L, [C.POINTER(EgPolicyDims), C.POINTER(C.c_int64)]),
+    "eg_policy_param_offsets": (_I, [C.POINTER(EgPolicyDims), C.POINTER(C.c_int64), _I]),
     "eg_policy_create": (_I, [C.POINTER(EgPolicyDims), _P, _P, _I, C.POINTER(_P)]),
     "eg_policy_destroy": (None, [_P]),
     "eg_policy_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

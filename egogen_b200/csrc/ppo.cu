@@ -9,6 +9,8 @@
 // the order of ActorCritic(actor, critic, shared_net).parameters(): one NCCL allreduce covers the whole
 // gradient, one kernel applies AdamW, and the clip-grad-norm range (actor + critic only - the
 // reference's `_actor_critic` quirk) is a prefix of the buffer.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "nn.cuh"
@@ -23,29 +25,37 @@ struct PolicyLayout {
   int64_t x_wih, x_whh, x_bih, x_bhh, e_wih, e_whh, e_bih, e_bhh;
   int64_t n_actor_critic, n_total;
   int hx_dim;
+  int n_tensors;
+  int64_t tensor_off[64];      // offset of every parameter tensor, in ActorCritic(actor, critic, shared_net).parameters() order
 };
 
+// Every tensor starts on a 16-byte boundary of the flat buffers (the critic's 1-element output bias would otherwise
+// leave every later matrix misaligned for TMA): the padding elements are zero parameters with zero gradients.
 static PolicyLayout make_layout(const EgPolicyDims& d) {
   PolicyLayout L{};
   const int D = 2 * d.h_dim + 4 * d.pe_L;    // 1152
   L.hx_dim = D;
   int64_t off = 0;
-  auto lin = [&](int in, int out) { Lin l{off, off + (int64_t)in * out, in, out}; off += (int64_t)in * out + out; return l; };
+  int nt = 0;
+  auto take = [&](int64_t n) { off = (off + 3) & ~(int64_t)3; const int64_t o = off; L.tensor_off[nt++] = o; off += n; return o; };
+  auto lin = [&](int in, int out) { Lin l{}; l.in = in; l.out = out; l.w = take((int64_t)in * out); l.b = take(out); return l; };
   for (int k = 0; k < d.n_blocks; ++k) { L.a_blk[k][0] = lin(D, D); L.a_blk[k][1] = lin(D, D); }
   L.a_out = lin(D, 2 * d.z_dim);
   for (int k = 0; k < d.n_blocks; ++k) { L.c_blk[k][0] = lin(D, D); L.c_blk[k][1] = lin(D, D); }
   L.c_out = lin(D, 1);
+  off = (off + 3) & ~(int64_t)3;
   L.n_actor_critic = off;
   const int H = d.h_dim, H3 = 3 * d.h_dim;
-  L.x_wih = off; off += (int64_t)H3 * d.in_dim;
-  L.x_whh = off; off += (int64_t)H3 * H;
-  L.x_bih = off; off += H3;
-  L.x_bhh = off; off += H3;
-  L.e_wih = off; off += (int64_t)H3 * d.ego_dim;
-  L.e_whh = off; off += (int64_t)H3 * H;
-  L.e_bih = off; off += H3;
-  L.e_bhh = off; off += H3;
-  L.n_total = off;
+  L.x_wih = take((int64_t)H3 * d.in_dim);
+  L.x_whh = take((int64_t)H3 * H);
+  L.x_bih = take(H3);
+  L.x_bhh = take(H3);
+  L.e_wih = take((int64_t)H3 * d.ego_dim);
+  L.e_whh = take((int64_t)H3 * H);
+  L.e_bih = take(H3);
+  L.e_bhh = take(H3);
+  L.n_total = (off + 3) & ~(int64_t)3;
+  L.n_tensors = nt;
   return L;
 }
 
@@ -95,6 +105,56 @@ colsum_kernel(const float* __restrict__ dY, int ld, int M, int N, float* __restr
 #pragma unroll
     for (int q = 0; q < 8; ++q) t += part[q][threadIdx.x];
     db[col] += t;
+  }
+}
+
+// dx = dy * lrelu'(y) and, in the same pass, db[n] += sum_m dx[m, n] (the bias gradient of the layer that produced y):
+// block = 16 columns x 16 row lanes, deterministic order
+__global__ void __launch_bounds__(256)
+lrelu_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y, float slope, int M, int N,
+                        float* __restrict__ dx, float* __restrict__ db) {
+  __shared__ float part[16][17];
+  eg_pdl_enter();
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int col = blockIdx.x * 16 + cl;
+  float s = 0.0f;
+  if (col < N)
+    for (int m = rl; m < M; m += 16) {
+      const int64_t i = (int64_t)m * N + col;
+      const float g = y[i] > 0.0f ? dy[i] : dy[i] * slope;
+      dx[i] = g;
+      s += g;
+    }
+  part[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && col < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) t += part[q][cl];
+    db[col] += t;
+  }
+}
+
+// y[m] = act(x[m, :] . w + b): the N = 1 layer (critic head) as one warp per row
+__global__ void __launch_bounds__(256)
+gemv_rows_kernel(const float* __restrict__ x, int ldx, int M, int K, const float* __restrict__ w, const float* __restrict__ b,
+                 float* __restrict__ y, int ldy) {
+  eg_pdl_enter();
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float s = 0.0f;
+  for (int k = lane; k < K; k += 32) s = fmaf(x[(int64_t)m * ldx + k], __ldg(w + k), s);
+  s = warp_sum(s);
+  if (lane == 0) y[(int64_t)m * ldy] = s + (b ? __ldg(b) : 0.0f);
+}
+
+// dst[r, 0..ld_dst) = src[r, 0..cols) zero-padded: 16-byte aligned row pitch for the TMA operands of the dense layers
+__global__ void __launch_bounds__(256)
+pad_rows_kernel(const float* __restrict__ src, int ld_src, int rows, int cols, float* __restrict__ dst, int ld_dst) {
+  const int64_t n = (int64_t)rows * ld_dst;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld_dst), c = (int)(i % ld_dst);
+    dst[i] = c < cols ? src[(int64_t)r * ld_src + c] : 0.0f;
   }
 }
 
@@ -317,6 +377,15 @@ struct EgPolicy {
         *dgi = nullptr, *dgh = nullptr, *dh1 = nullptr, *dh1b = nullptr;
   double* mom = nullptr;                                 // [4] device scalars
   std::vector<float*> owned;
+  // x_enc operands with a 16-byte row pitch (in_dim = 402 floats is not): padded copies so the products run on gemm_tc
+  int in_pad = 0;                                        // in_dim rounded up to 4
+  float *xpad = nullptr, *wih_pad = nullptr;             // [B,2,in_pad], [3H,in_pad]
+  // actor and critic chains are independent between the shared encoder and the GRU backward: the critic runs on a side
+  // stream so that two latency-bound layer chains share the SMs
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int two_streams = 1;
+  float *dh2 = nullptr, *da2 = nullptr, *dt2 = nullptr, *dhx2 = nullptr;   // critic-chain backward scratch
 };
 
 #define EG_TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
@@ -350,6 +419,8 @@ static int policy_ws(EgPolicy* h, int B) {
   EG_TRY(alloc(&h->d_out_a, b * Z2)); EG_TRY(alloc(&h->d_out_c, b));
   EG_TRY(alloc(&h->dh, b * D)); EG_TRY(alloc(&h->da, b * D)); EG_TRY(alloc(&h->dt, b * D)); EG_TRY(alloc(&h->dhx, b * D));
   EG_TRY(alloc(&h->dgi, b * H3)); EG_TRY(alloc(&h->dgh, b * H3)); EG_TRY(alloc(&h->dh1, b * H)); EG_TRY(alloc(&h->dh1b, b * H));
+  EG_TRY(alloc(&h->dh2, b * D)); EG_TRY(alloc(&h->da2, b * D)); EG_TRY(alloc(&h->dt2, b * D)); EG_TRY(alloc(&h->dhx2, b * D));
+  EG_TRY(alloc(&h->xpad, b * 2 * h->in_pad));
   h->cap = B;
   return EG_OK;
 }
@@ -361,6 +432,14 @@ extern "C" int64_t eg_policy_param_count(const EgPolicyDims* d, int64_t* n_actor
   return L.n_total;
 }
 
+extern "C" int eg_policy_param_offsets(const EgPolicyDims* d, int64_t* offsets, int n_max) {
+  if (!d || !offsets) return -1;
+  PolicyLayout L = make_layout(*d);
+  if (L.n_tensors > n_max) return -1;
+  for (int i = 0; i < L.n_tensors; ++i) offsets[i] = L.tensor_off[i];
+  return L.n_tensors;
+}
+
 extern "C" int eg_policy_create(const EgPolicyDims* dims, float* params_flat, float* grads_flat, int device,
                                 EgPolicy** out) {
   EG_REQUIRE(dims && params_flat && out, "null pointer");
@@ -369,6 +448,13 @@ extern "C" int eg_policy_create(const EgPolicyDims* dims, float* params_flat, fl
   EgPolicy* h = new EgPolicy();
   h->device = device; h->d = *dims; h->L = make_layout(*dims); h->P = params_flat; h->G = grads_flat;
   EG_CUDA_CHECK(cudaMalloc((void**)&h->mom, 4 * sizeof(double)));
+  h->in_pad = (dims->in_dim + 3) & ~3;
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->wih_pad, (size_t)3 * dims->h_dim * h->in_pad * sizeof(float)));
+  EG_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  EG_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  EG_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  const char* e = getenv("EG_POLICY_TWO_STREAMS");
+  h->two_streams = (e != nullptr && e[0] == '0') ? 0 : 1;
   *out = h;
   return EG_OK;
 }
@@ -378,18 +464,22 @@ extern "C" void eg_policy_destroy(EgPolicy* h) {
   cudaSetDevice(h->device);
   for (float* p : h->owned) cudaFree(p);
   cudaFree(h->mom);
+  cudaFree(h->wih_pad);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
 // one GRU encoder over the 2 observation frames (h0 = 0), saving gate activations for backward
 static int gru2_forward(EgPolicy* h, cudaStream_t st, const float* x, int ld_env, int ld_frame, int in_dim, int B,
-                        int64_t wih, int64_t whh, int64_t bih, int64_t bhh, float** r, float** z, float** n, float** g,
+                        const float* Wih, int ld_wih, int64_t whh, int64_t bih, int64_t bhh, float** r, float** z, float** n, float** g,
                         float* h1, float* out, int ld_out) {
   const int H = h->d.h_dim, H3 = 3 * H;
   const float* P = h->P;
-  EG_TRY(linear(st, x, ld_env, B, P + wih, in_dim, P + bih, in_dim, H3, h->gi, H3));
+  EG_TRY(linear(st, x, ld_env, B, Wih, ld_wih, P + bih, in_dim, H3, h->gi, H3));
   EG_TRY(launch_gru_gate(st, h->gi, nullptr, P + bhh, nullptr, h1, B, H, H, r[0], z[0], n[0], g[0]));
-  EG_TRY(linear(st, x + ld_frame, ld_env, B, P + wih, in_dim, P + bih, in_dim, H3, h->gi, H3));
+  EG_TRY(linear(st, x + ld_frame, ld_env, B, Wih, ld_wih, P + bih, in_dim, H3, h->gi, H3));
   EG_TRY(linear(st, h1, H, B, P + whh, H, P + bhh, H, H3, h->gh, H3));
   EG_TRY(launch_gru_gate(st, h->gi, h->gh, nullptr, h1, out, B, H, ld_out, r[1], z[1], n[1], g[1]));
   return EG_OK;
@@ -404,7 +494,8 @@ static int mlp_block_forward(EgPolicy* h, cudaStream_t st, const Lin blk[][2], c
     EG_TRY(linear(st, t[k], D, B, P + blk[k][1].w, D, P + blk[k][1].b, D, D, u[k], D, ACT_LRELU, 0.01f));
     EG_LAUNCH_PDL(add_kernel, ew_grid((int64_t)B * D), 256, 0, st, u[k], in[k], (int64_t)B * D, in[k + 1]);
   }
-  EG_TRY(linear(st, in[h->d.n_blocks], D, B, P + outl.w, D, P + outl.b, D, outl.out, out, outl.out));
+  if (outl.out == 1) EG_LAUNCH_PDL(gemv_rows_kernel, (B + 7) / 8, 256, 0, st, in[h->d.n_blocks], D, B, D, P + outl.w, P + outl.b, out, 1);
+  else EG_TRY(linear(st, in[h->d.n_blocks], D, B, P + outl.w, D, P + outl.b, D, outl.out, out, outl.out));
   return EG_OK;
 }
 
@@ -419,18 +510,32 @@ extern "C" int eg_policy_forward(EgPolicy* h, const float* state, const float* e
   const EgPolicyDims& d = h->d;
   const PolicyLayout& L = h->L;
   const int H = d.h_dim, D = L.hx_dim;
-  EG_TRY(gru2_forward(h, st, state, 2 * d.in_dim, d.in_dim, d.in_dim, B, L.x_wih, L.x_whh, L.x_bih, L.x_bhh, h->xr,
+  // x_enc: the 402-float frames and W_ih rows are re-pitched to 404 floats (16 B) so the products are TMA-eligible
+  const int IP = h->in_pad;
+  EG_LAUNCH(pad_rows_kernel, ew_grid((int64_t)B * 2 * IP), 256, 0, st, state, d.in_dim, B * 2, d.in_dim, h->xpad, IP);
+  EG_LAUNCH(pad_rows_kernel, ew_grid((int64_t)3 * H * IP), 256, 0, st, h->P + L.x_wih, d.in_dim, 3 * H, d.in_dim, h->wih_pad, IP);
+  EG_TRY(gru2_forward(h, st, h->xpad, 2 * IP, IP, d.in_dim, B, h->wih_pad, IP, L.x_whh, L.x_bih, L.x_bhh, h->xr,
                       h->xz, h->xn, h->xg, h->xh1, h->hx, D));
-  EG_TRY(gru2_forward(h, st, ego, 2 * d.ego_dim, d.ego_dim, d.ego_dim, B, L.e_wih, L.e_whh, L.e_bih, L.e_bhh, h->er,
+  EG_TRY(gru2_forward(h, st, ego, 2 * d.ego_dim, d.ego_dim, d.ego_dim, B, h->P + L.e_wih, d.ego_dim, L.e_whh, L.e_bih, L.e_bhh, h->er,
                       h->ez, h->en, h->eg_, h->eh1, h->hx + H, D));
   EG_LAUNCH(pe_kernel, (B * 2 * d.pe_L + 127) / 128, 128, 0, st, dist, time, B, d.pe_L, D, 2 * H, h->hx);
+  const bool fork = want_actor && want_critic && h->two_streams;
+  cudaStream_t sc = fork ? h->side : st;                 // critic chain
+  if (fork) {
+    EG_CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
+    EG_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  }
   if (want_actor) {
     EG_TRY(mlp_block_forward(h, st, L.a_blk, L.a_out, h->a_in, h->a_t, h->a_u, h->out_a, B));
     if (out_actor) EG_CUDA_CHECK(cudaMemcpyAsync(out_actor, h->out_a, (size_t)B * 2 * d.z_dim * 4, cudaMemcpyDeviceToDevice, st));
   }
   if (want_critic) {
-    EG_TRY(mlp_block_forward(h, st, L.c_blk, L.c_out, h->c_in, h->c_t, h->c_u, h->out_c, B));
-    if (value) EG_CUDA_CHECK(cudaMemcpyAsync(value, h->out_c, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    EG_TRY(mlp_block_forward(h, sc, L.c_blk, L.c_out, h->c_in, h->c_t, h->c_u, h->out_c, B));
+    if (value) EG_CUDA_CHECK(cudaMemcpyAsync(value, h->out_c, (size_t)B * 4, cudaMemcpyDeviceToDevice, sc));
+  }
+  if (fork) {
+    EG_CUDA_CHECK(cudaEventRecord(h->ev_join, h->side));
+    EG_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
   if (hx_out) EG_CUDA_CHECK(cudaMemcpyAsync(hx_out, h->hx, (size_t)B * D * 4, cudaMemcpyDeviceToDevice, st));
   return EG_OK;
@@ -445,14 +550,14 @@ extern "C" int eg_gauss_sample(const float* out_actor, const float* eps, int B, 
   return EG_OK;
 }
 
-// dY [B,out] -> dW += dY^T X, db += colsum(dY), dX = dY W (+ optional accumulate into dX)
+// dY [B,out] -> dW += dY^T X, db += colsum(dY) (unless the producer of dY already added it), dX = dY W (+ optional accumulate)
 static int linear_backward(EgPolicy* h, cudaStream_t st, const float* dY, int ld_dy, const float* X, int ldx, int B,
-                           const Lin& l, float* dX, int ld_dx, int dx_beta) {
+                           const Lin& l, float* dX, int ld_dx, int dx_beta, bool bias_done = false) {
   const float* P = h->P;
   float* G = h->G;
   GemmArgs gw{dY, ld_dy, 1, X, ldx, G + l.w, l.in, nullptr, nullptr, 0, l.out, l.in, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(gw, true, false, st));
-  EG_LAUNCH_PDL(colsum_kernel, (l.out + 31) / 32, 256, 0, st, dY, ld_dy, B, l.out, G + l.b);
+  if (!bias_done) EG_LAUNCH_PDL(colsum_kernel, (l.out + 31) / 32, 256, 0, st, dY, ld_dy, B, l.out, G + l.b);
   if (dX) {
     GemmArgs gx{dY, ld_dy, 1, P + l.w, l.in, dX, ld_dx, nullptr, nullptr, 0, B, l.in, l.out, ACT_NONE, 0.f, dx_beta, 1.0f};
     EG_TRY(launch_gemm(gx, false, false, st));
@@ -460,22 +565,21 @@ static int linear_backward(EgPolicy* h, cudaStream_t st, const float* dY, int ld
   return EG_OK;
 }
 
+// dh / da / dt: the chain's scratch set [B, D]; the gradient w.r.t. hx is left in dh
 static int mlp_block_backward(EgPolicy* h, cudaStream_t st, const Lin blk[][2], const Lin& outl, float** in, float** t,
-                              float** u, const float* d_out, int B, float* dhx, int dhx_beta) {
+                              float** u, const float* d_out, int B, float* dh, float* da, float* dt) {
   const int D = h->L.hx_dim;
-  const int64_t n = (int64_t)B * D;
+  float* G = h->G;
   // out = in[nb] W_o^T + b_o
-  EG_TRY(linear_backward(h, st, d_out, outl.out, in[h->d.n_blocks], D, B, outl, h->dh, D, 0));
+  EG_TRY(linear_backward(h, st, d_out, outl.out, in[h->d.n_blocks], D, B, outl, dh, D, 0));
   for (int k = h->d.n_blocks - 1; k >= 0; --k) {
-    // in[k+1] = u + in[k];  u = lrelu(t W2^T + b2);  t = lrelu(in[k] W1^T + b1)
-    EG_LAUNCH_PDL(lrelu_bwd_kernel, ew_grid(n), 256, 0, st, h->dh, u[k], 0.01f, n, h->da);
-    EG_TRY(linear_backward(h, st, h->da, D, t[k], D, B, blk[k][1], h->dt, D, 0));
-    EG_LAUNCH_PDL(lrelu_bwd_kernel, ew_grid(n), 256, 0, st, h->dt, t[k], 0.01f, n, h->da);
+    // in[k+1] = u + in[k];  u = lrelu(t W2^T + b2);  t = lrelu(in[k] W1^T + b1)   (bias gradients fused into the lrelu backward)
+    EG_LAUNCH_PDL(lrelu_bwd_colsum_kernel, (D + 15) / 16, 256, 0, st, dh, u[k], 0.01f, B, D, da, G + blk[k][1].b);
+    EG_TRY(linear_backward(h, st, da, D, t[k], D, B, blk[k][1], dt, D, 0, true));
+    EG_LAUNCH_PDL(lrelu_bwd_colsum_kernel, (D + 15) / 16, 256, 0, st, dt, t[k], 0.01f, B, D, da, G + blk[k][0].b);
     // d in[k] = da1 W1 + dh (residual): accumulate straight into dh
-    EG_TRY(linear_backward(h, st, h->da, D, in[k], D, B, blk[k][0], h->dh, D, 1));
+    EG_TRY(linear_backward(h, st, da, D, in[k], D, B, blk[k][0], dh, D, 1, true));
   }
-  if (dhx_beta) EG_LAUNCH_PDL(add_kernel, ew_grid(n), 256, 0, st, dhx, h->dh, n, dhx);
-  else EG_CUDA_CHECK(cudaMemcpyAsync(dhx, h->dh, n * 4, cudaMemcpyDeviceToDevice, st));
   return EG_OK;
 }
 
@@ -522,9 +626,22 @@ extern "C" int eg_ppo_loss_backward(EgPolicy* h, const float* state, const float
   if (zero_grads) EG_CUDA_CHECK(cudaMemsetAsync(h->G, 0, (size_t)L.n_total * 4, st));
   EG_LAUNCH(ppo_head_kernel, B, 128, 0, st, h->out_a, h->out_c, act, logp_old, adv_norm, returns, B, d.z_dim, inv_B,
             eps_clip, vf_coef, ent_coef, min_logvar, max_logvar, h->d_out_a, h->d_out_c, stats);
-  EG_TRY(mlp_block_backward(h, st, L.a_blk, L.a_out, h->a_in, h->a_t, h->a_u, h->d_out_a, B, h->dhx, 0));
-  EG_TRY(mlp_block_backward(h, st, L.c_blk, L.c_out, h->c_in, h->c_t, h->c_u, h->d_out_c, B, h->dhx, 1));
-  EG_TRY(gru2_backward(h, st, state, 2 * d.in_dim, d.in_dim, d.in_dim, B, L.x_wih, L.x_whh, L.x_bih, L.x_bhh, h->xr,
+  const int64_t nD = (int64_t)B * D;
+  const bool fork = h->two_streams != 0;
+  cudaStream_t sc = fork ? h->side : st;
+  if (fork) {
+    EG_CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
+    EG_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  }
+  EG_TRY(mlp_block_backward(h, st, L.a_blk, L.a_out, h->a_in, h->a_t, h->a_u, h->d_out_a, B, h->dh, h->da, h->dt));
+  EG_TRY(mlp_block_backward(h, sc, L.c_blk, L.c_out, h->c_in, h->c_t, h->c_u, h->d_out_c, B, h->dh2, h->da2, h->dt2));
+  if (fork) {
+    EG_CUDA_CHECK(cudaEventRecord(h->ev_join, h->side));
+    EG_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join, 0));
+  }
+  EG_LAUNCH_PDL(add_kernel, ew_grid(nD), 256, 0, st, h->dh, h->dh2, nD, h->dhx);      // d hx = actor path + critic path
+  const int IP = h->in_pad;
+  EG_TRY(gru2_backward(h, st, h->xpad, 2 * IP, IP, d.in_dim, B, L.x_wih, L.x_whh, L.x_bih, L.x_bhh, h->xr,
                        h->xz, h->xn, h->xg, h->xh1, h->dhx, D));
   EG_TRY(gru2_backward(h, st, ego, 2 * d.ego_dim, d.ego_dim, d.ego_dim, B, L.e_wih, L.e_whh, L.e_bih, L.e_bhh, h->er,
                        h->ez, h->en, h->eg_, h->eh1, h->dhx + H, D));

@@ -61,13 +61,19 @@ class GAMMAPPOPolicy(nn.Module):
         dev = ps[0].device
         if dev.type != "cuda":
             raise _lib.EgError("policy parameters must live on a CUDA device (no CPU path)")
-        n = sum(p.numel() for p in ps)
         self.dims = _lib.EgPolicyDims(self.shared_net.in_dim, 32, self.shared_net.h_dim, 32, self.actor.n_blocks,
                                       self.actor.z_dim)
         nac = C.c_int64()
-        expect = _lib.lib().eg_policy_param_count(C.byref(self.dims), C.byref(nac))
-        if expect != n:
-            raise _lib.EgError(f"parameter count {n} does not match the library layout {expect}")
+        n = _lib.lib().eg_policy_param_count(C.byref(self.dims), C.byref(nac))       # flat length incl. alignment padding
+        offs = (C.c_int64 * 64)()
+        nt = _lib.lib().eg_policy_param_offsets(C.byref(self.dims), offs, 64)
+        if nt != len(ps):
+            raise _lib.EgError(f"{len(ps)} parameter tensors do not match the library layout ({nt})")
+        self._offsets = [int(offs[i]) for i in range(nt)]
+        for i, p in enumerate(ps):                                               # the layout must hold every tensor
+            end = self._offsets[i + 1] if i + 1 < nt else n
+            if self._offsets[i] + p.numel() > end:
+                raise _lib.EgError(f"parameter tensor {i} ({tuple(p.shape)}) does not fit the library layout")
         self.n_actor_critic = nac.value
         self.n_params = n
         self._dp = None
@@ -79,17 +85,15 @@ class GAMMAPPOPolicy(nn.Module):
             self.exp_avg = torch.zeros(chunk, dtype=torch.float32, device=dev)        # this rank's moment slices
             self.exp_avg_sq = torch.zeros(chunk, dtype=torch.float32, device=dev)
         else:
-            self.flat_params = torch.empty(n, dtype=torch.float32, device=dev)
+            self.flat_params = torch.zeros(n, dtype=torch.float32, device=dev)
             self.flat_grads = torch.zeros(n, dtype=torch.float32, device=dev)
             self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
             self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        for p in ps:
+        for off, p in zip(self._offsets, ps):
             k = p.numel()
             self.flat_params[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_params[off:off + k].view_as(p)
             p.grad = self.flat_grads[off:off + k].view_as(p)
-            off += k
         self._stats = torch.zeros(8, dtype=torch.float32, device=dev)
         self._mom = torch.zeros(3, dtype=torch.float64, device=dev)
         self.dev = dev
@@ -361,8 +365,7 @@ class GAMMAPPOPolicy(nn.Module):
 
     def export_optim_state(self):
         exp_avg, exp_avg_sq = self._full_moments()
-        off = 0
-        for p in self._ordered_params():
+        for off, p in zip(self._offsets, self._ordered_params()):
             k = p.numel()
             self.optim.state[p] = {"step": torch.tensor(float(self._opt_step)),
                                    "exp_avg": exp_avg[off:off + k].view_as(p),

@@ -304,6 +304,10 @@ typedef struct EgPolicyDims {
 } EgPolicyDims;
 
 int64_t eg_policy_param_count(const EgPolicyDims* dims, int64_t* n_actor_critic);
+/* offset (in floats) of every parameter tensor inside the flat buffers, in ActorCritic(actor, critic,
+ * shared_net).parameters() order; every tensor starts on a 16-byte boundary (padding elements are zero parameters).
+ * Returns the number of tensors written, -1 when n_max is too small. */
+int eg_policy_param_offsets(const EgPolicyDims* dims, int64_t* offsets, int n_max);
 int eg_policy_create(const EgPolicyDims* dims, float* params_flat, float* grads_flat, int device, EgPolicy** out);
 void eg_policy_destroy(EgPolicy* h);
 /* obs batch: state [B,2,402], ego [B,2,32], dist [B], time [B]. out_actor [B,256] = raw [mu | logvar]
