@@ -10,6 +10,8 @@ rewards -> re-canonicalisation -> ego-sensing) followed by GAE and one learn pas
 forward + backward + grad-clip + AdamW, one NCCL gradient allreduce per optimiser step when N > 1).
 value = env transitions of all ranks / time, with every input resident in HBM; e2e = the same iteration with the
 reference's host-side data path (obs / actions / rewards cross pinned host memory every vector step).
+The default (ppo) line also carries `secondary`: BASELINE configs 1, 3, 4 and 5 measured on the same GPUs, each with its
+own clocks / roofline / cpu_baseline (`--workload X` runs one of them alone; `--no-secondary` skips them).
 """
 import argparse
 import ctypes as C
@@ -26,7 +28,10 @@ N_ENVS = 256            # per GPU (main_ppo.py --training-num)
 STEP_PER_COLLECT = 1024  # per GPU (main_ppo.py --step-per-collect)
 BATCH = 256             # per-GPU minibatch (main_ppo.py --batch-size)
 B_BODY = 127636         # algorithmic bytes per materialised body
+B_LBS_ENV_STEP = 20 * B_BODY   # LBS bytes per env step (20 bodies)
 FLOP_BODY = 49.1e6      # dense-reference FLOPs per body
+FLOP_BLEND_BODY = 2.0 * (486 + 20) * 3 * 10475     # useful pose + shape blend contraction per body (31.8 MFLOP)
+DTYPE = "f32 (tensor-core products on fp16 / tf32 split operands, f32 accumulate)"
 
 
 def peaks():
@@ -78,19 +83,25 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     world = harness.build_oracle_world(0, sdf_res=256)
-    n_envs, n_steps = 4, 2          # bounded sample of the 256-env x 4-step collect
+    # bounded sample with the GPU arm's definition of a step: a collect of n_steps vector steps followed by GAE and one
+    # learn pass of FOUR minibatches (one optimiser step each), scaled from 256 envs to 16
+    n_envs, n_steps, n_mb = 16, 4, 4
     for i in range(args.warmup):
-        harness.run_iteration(world, n_envs, 1, True, seed=100 + i)
+        harness.run_iteration(world, 2, 1, True, seed=100 + i, n_minibatch=1)
     tot_s, tot_n = 0.0, 0
     for i in range(args.steps):
-        s, n = harness.run_iteration(world, n_envs, n_steps, True, seed=i)
+        s, n = harness.run_iteration(world, n_envs, n_steps, True, seed=i, n_minibatch=n_mb)
         tot_s += s; tot_n += n
     v = tot_n / tot_s
-    sample = f"{n_envs} envs x {n_steps} vector steps per step (of 256 x 4), sequential per-env loop with 4x duplicated batch"
+    sample = (f"{n_envs} envs x {n_steps} vector steps + GAE + {n_mb} minibatch updates of {n_envs * n_steps // n_mb} rows per step "
+              f"(the GPU arm: 256 envs x 4 vector steps + 4 x 256 rows), sequential per-env loop with the 4x duplicated batch")
+    cfg = config_dict(args.gpus)
+    cfg["reference_sample"] = {"envs": n_envs, "vector_steps": n_steps, "minibatches": n_mb,
+                               "rows_per_minibatch": n_envs * n_steps // n_mb, "warmup_sample": "2 envs x 1 vector step"}
     line = {"impl": "reference", "metric": "crowd_ppo env-steps/sec", "value": v, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args.gpus),
+            "config": cfg,
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -104,30 +115,99 @@ def config_dict(n):
             "cache": "L2 flushed (256 MiB write) between timed iterations; working set ~250 MB > 126 MB L2"}
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from egogen_b200 import _lib
-    from egogen_b200.runtime import build_world
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(1234 + rank)
+class Ctx:
+    """One process per GPU: rank / device / process group, set up once per bench.py run."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world_size > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self._flush = None
+
+    def flush_l2(self):
+        if self._flush is None:
+            self._flush = self.torch.empty(256 << 20, dtype=self.torch.uint8, device=self.dev)
+        self._flush.zero_()
+
+    def barrier(self):
+        if self.world_size > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([float(ms)], device=self.dev, dtype=self.torch.float64)
+        if self.world_size > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_steps(self, fn, steps, flush=True):
+        """EXACTLY `steps` calls of fn, each bracketed by (L2 flush,) barrier + synchronize and CUDA events on the current
+        stream; returns (sum of ms, max over ranks; this rank's per-step list)."""
+        torch = self.torch
+        ms = []
+        for _ in range(steps):
+            if flush:
+                self.flush_l2()
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize(self.dev)
+            ms.append(e0.elapsed_time(e1))
+        return self.max_over_ranks(sum(ms)), ms
+
+    def close(self):
+        if self.world_size > 1:
+            self.dist.destroy_process_group()
+
+
+class clocked:
+    """`with clocked(ctx) as c: ...` -> c.result = nvidia-smi clock record of rank 0's GPU during the block."""
+
+    def __init__(self, ctx):
+        self.s = ClockSampler(ctx.local) if ctx.rank == 0 else None
+        self.result = None
+
+    def __enter__(self):
+        if self.s:
+            self.s.start()
+        return self
+
+    def __exit__(self, *a):
+        if self.s:
+            self.result = self.s.stop()
+        return False
+
+
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p)).get("bf16_tflops", 1590.0)), "measured"
+    return 1590.0, "fallback"
+
+
+def measure_ppo(ctx, args):
+    """Headline workload (BASELINE config 2). Returns the JSON line (rank 0) or None."""
     import numpy as np
+    torch, dist = ctx.torch, ctx.dist
+    from egogen_b200 import _lib
+    from egogen_b200.collector import Collector
+    from egogen_b200.runtime import build_world
+    world_size, rank, dev = ctx.world_size, ctx.rank, ctx.dev
+    torch.manual_seed(1234 + rank)
     np.random.seed(1234 + rank)
     lib = _lib.lib()
-
     w = build_world(dev, N_ENVS, seed=rank, sdf_res=256)
     col, pol = w["collector"], w["policy"]
     pol.train()
     col.reset()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
     last = {}
 
     def iteration(c):
@@ -135,134 +215,267 @@ def run_ours(args):
         last["batch"] = batch
         return pol.learn(batch, BATCH, 1)
 
-    def timed(c, k, profile):
-        ms = []
-        launches0 = lib.eg_launch_count()
-        for _ in range(k):
-            flush.zero_()
-            if world_size > 1:
-                dist.barrier()
-            torch.cuda.synchronize(dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if profile:
-                lib.eg_profile_enable(1)
-            launches_before = lib.eg_launch_count()
-            e0.record()
-            iteration(c)
-            e1.record()
-            torch.cuda.synchronize(dev)
-            ms.append(e0.elapsed_time(e1))
-        return ms, lib.eg_launch_count() - launches0 - 0
-
     for _ in range(max(args.warmup, 3)):
         iteration(col)
     torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    lib.eg_profile_enable(1)
     ncu_range = os.environ.get("EG_NCU_RANGE") == "1"      # ncu --profile-from-start off: capture the timed region only
-    if ncu_range:
-        torch.cuda.cudart().cudaProfilerStart()
-    ms, launches = timed(col, args.steps, False)
-    if ncu_range:
-        torch.cuda.synchronize(dev)
-        torch.cuda.cudart().cudaProfilerStop()
-    tot_ms, n_l, n_units = C.c_double(), C.c_int64(), C.c_int64()
-    _lib.check(lib.eg_profile_read(C.byref(tot_ms), C.byref(n_l), C.byref(n_units)))
-    lib.eg_profile_enable(0)
-    # the flush kernel is torch's, not ours; do not count it. launches counts only this library's kernels.
-    total_ms = float(sum(ms))
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = STEP_PER_COLLECT * world_size * args.steps / (total_ms / 1e3)
-
-    # ---- e2e: same iteration with the reference's host-side data path -------------------------
-    from egogen_b200.collector import Collector
-    col2 = Collector(pol, w["venv"], host_boundary=True)
-    col2.reset()
-    iteration(col2)
-    col2.h2d_bytes = col2.d2h_bytes = 0
-    ms2, _ = timed(col2, args.steps, False)
-    t2 = torch.tensor([float(sum(ms2))], device=dev, dtype=torch.float64)
-    if world_size > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = STEP_PER_COLLECT * world_size * args.steps / (float(t2.item()) / 1e3)
-    clocks = sampler.stop() if sampler else None
-    e2e = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": col2.h2d_bytes // args.steps,
-           "d2h_bytes_per_step": (col2.d2h_bytes + 5 * 8 * 4) // args.steps}
-
+    with clocked(ctx) as ck:
+        lib.eg_profile_enable(1)
+        launches0 = lib.eg_launch_count()
+        if ncu_range:
+            torch.cuda.cudart().cudaProfilerStart()
+        total_ms, ms = ctx.time_steps(lambda: iteration(col), args.steps)
+        if ncu_range:
+            torch.cuda.synchronize(dev)
+            torch.cuda.cudart().cudaProfilerStop()
+        launches = lib.eg_launch_count() - launches0
+        tot_ms, n_l, n_units = C.c_double(), C.c_int64(), C.c_int64()
+        _lib.check(lib.eg_profile_read(C.byref(tot_ms), C.byref(n_l), C.byref(n_units)))
+        lib.eg_profile_enable(0)
+        value = STEP_PER_COLLECT * world_size * args.steps / (total_ms / 1e3)
+        # ---- e2e: same iteration with the reference's host-side data path ---------------------
+        col2 = Collector(pol, w["venv"], host_boundary=True)
+        col2.reset()
+        iteration(col2)
+        col2.h2d_bytes = col2.d2h_bytes = 0
+        e2e_ms, _ = ctx.time_steps(lambda: iteration(col2), args.steps)
+    e2e = {"value": STEP_PER_COLLECT * world_size * args.steps / (e2e_ms / 1e3), "unit": "env-steps/s",
+           "h2d_bytes_per_step": col2.h2d_bytes // args.steps, "d2h_bytes_per_step": (col2.d2h_bytes + 5 * 8 * 4) // args.steps}
     # sanity (outside every timed region): the rollouts and the updated policy are finite
     assert bool(torch.isfinite(last["batch"].returns).all()) and bool(torch.isfinite(pol.flat_params).all()), \
         "non-finite values after the timed iterations"
+    # ---- where the step goes (untimed extra iterations with the env-stage profiler on) -----------
+    # two untimed passes: collect / learn split without any instrumentation, then the env stages with the stage profiler on
+    # (its per-stage events cost launch overlap, so its figures are shares of the env step, not of the timed iteration)
+    stage = None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    K = 2
+    tc = tl = 0.0
+    for _ in range(K):
+        torch.cuda.synchronize(dev)
+        ev[0].record(); b_, _ = col.collect(STEP_PER_COLLECT); ev[1].record(); pol.learn(b_, BATCH, 1); ev[2].record()
+        torch.cuda.synchronize(dev)
+        tc += ev[0].elapsed_time(ev[1]); tl += ev[1].elapsed_time(ev[2])
+    if rank == 0:
+        lib.eg_stage_profile_enable(1)
+    for _ in range(K):
+        b_, _ = col.collect(STEP_PER_COLLECT); pol.learn(b_, BATCH, 1)
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        sm = (C.c_double * 16)()
+        _lib.check(lib.eg_stage_profile_read(sm, 16))
+        lib.eg_stage_profile_enable(0)
+        names = {1: "cvae_decode_regressor", 2: "param_blend", 3: "lbs_sdf", 4: "vposer", 5: "rewards_recanon",
+                 6: "seed_joint_lbs", 7: "ego_sensing"}
+        stage = {"collect_ms": tc / K, "learn_ms": tl / K, "env_stage_ms_instrumented": {n: sm[k] / K for k, n in names.items()}}
     if rank != 0:
-        if world_size > 1:
-            dist.destroy_process_group()
-        return
-    # ---- roofline of the dominant kernel (fused LBS + SDF vertex kernel) -----------------------
+        return None
+    # ---- roofline of the path's headline kernel (fused LBS + SDF vertex kernel) ------------------
     peak, how = peaks()
     k_ms = tot_ms.value / max(n_l.value, 1)
     bodies_per_launch = n_units.value / max(n_l.value, 1)
     hbm_achieved = bodies_per_launch * B_BODY / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    # the fused LBS kernel is an fp16-operand / fp32-accumulate tensor-core contraction [bodies,576] x [576, 3*V]
-    # (V = 10475 real vertices; tile padding is not counted) + skinning/SDF epilogue
-    tc_flops = bodies_per_launch * 2.0 * 576 * 3 * 10475
-    tf_achieved = tc_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    tf_peak = float(pk.get("bf16_tflops", 1590.0))
-    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/), scaled to this run's
-    # bodies per launch (the kernel's HBM traffic is the basis + features + transforms, linear in bodies apart from
-    # the 36 MB fp16 basis that is read once per launch)
+    # useful blend FLOPs: [bodies, 486 pose + 20 shape] x [506, 3 V]; the kernel issues K = 576 (hi/lo shape columns + padding)
+    tf_achieved = bodies_per_launch * FLOP_BLEND_BODY / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    tf_issued = bodies_per_launch * 2.0 * 576 * 3 * 10475 / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    tf_peak, tf_how = tensor_peak()
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_lbs_tc_traffic.json")
-    if os.path.exists(tp):
-        tj = json.load(open(tp))
-        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * bodies_per_launch / tj["bodies"]
-        traffic_src = tj["source"]
+    for name in ("r2_lbs_tc_traffic.json", "r1_lbs_tc_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * bodies_per_launch / tj["bodies"]
+            traffic_src = tj["source"]
+            break
+    step_gbs = value / world_size * B_LBS_ENV_STEP / 1e9
     roofline = {"bound": "tensor", "achieved": tf_achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf_achieved / tf_peak,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": how + " dense bf16/fp16 cuBLAS burst (kind::f16 operands, fp32 accumulation)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": tf_how + " dense bf16/fp16 cuBLAS burst (kind::f16 operands, fp32 accumulation)",
                 "kernel": "lbs_verts_tc_kernel<FUSE_SDF> (tcgen05 kind::f16, fp32 accumulate in TMEM)",
                 "avg_launch_ms": k_ms, "bodies_per_launch": bodies_per_launch, "launches_timed": n_l.value,
                 "kernel_share_of_step": tot_ms.value / float(sum(ms)),
-                "flops_per_body": 2.0 * 576 * 3 * 10475,
+                "flops_per_body": FLOP_BLEND_BODY, "issued_tflops_incl_k_padding": tf_issued,
                 "hbm_contract": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
-                                 "frac_of_nominal_8TBs": hbm_achieved / 8000.0,
                                  "note": "SURVEY 8(d) contract figure: bodies x 127636 B (what an unfused LBS must move); "
                                          "the fused kernel itself writes only the per-body counts"},
-                "reference_dense_tflops": bodies_per_launch * FLOP_BODY / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0}
+                "step": {"lbs_bytes_per_env_step": B_LBS_ENV_STEP, "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0,
+                         "note": "whole-iteration LBS-bytes roofline per GPU: env-steps/s x 2 552 720 B; the iteration is a chain of "
+                                 "latency-bound dense layers and a tensor-bound LBS kernel, not an HBM stream", "where": stage}}
     # ---- CPU baseline: the oracle port on a bounded sample, host cores of this box --------------
-    from oracle import harness
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    ow = harness.build_oracle_world(0, sdf_res=256)
-    harness.run_iteration(ow, 8, 1, False, seed=99)                       # warm-up
-    s, n = harness.run_iteration(ow, 16, 2, False, seed=0)
-    cpu = {"value": n / s, "unit": "env-steps/s", "cores": cores, "kind": "port",
-           "sample": "oracle (batched, dup removed): 16 envs x 2 vector steps + GAE + 1 learn pass, torch-CPU all threads"}
-    line = {"metric": "crowd_ppo env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world_size,
+    cpu = None
+    if world_size == 1:
+        from oracle import harness
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ow = harness.build_oracle_world(0, sdf_res=256)
+        harness.run_iteration(ow, 8, 1, False, seed=99)                       # warm-up
+        s_, n_ = harness.run_iteration(ow, 16, 2, False, seed=0, n_minibatch=4)
+        cpu = {"value": n_ / s_, "unit": "env-steps/s", "cores": cores, "kind": "port",
+               "sample": "oracle (batched, dup removed): 16 envs x 2 vector steps + GAE + 4 minibatch updates, torch-CPU all threads"}
+    return {"metric": "crowd_ppo env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(world_size), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": config_dict(world_size), "e2e": e2e, "gpu_launches": int(launches), "clocks": ck.result,
             "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
-    if world_size > 1:
-        dist.destroy_process_group()
 
 
-def run_ego_depth(args):
+# ---------------------------------------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE configs 1, 3, 4, 5): each returns one dict with its own clocks / roofline / cpu_baseline
+# ---------------------------------------------------------------------------------------------------------------------------
+def measure_single_env(ctx, steps, warmup):
+    """BASELINE config 1: single-agent evaluation, 1 env, deterministic policy (main_ppo.py --watch): latency per env step.
+    Every rank runs its own env (replicas, no collective); value = env-steps/s of all ranks."""
+    torch = ctx.torch
+    from egogen_b200.ppo_policy import Batch
+    from egogen_b200.runtime import build_world
+    w = build_world(ctx.dev, 1, seed=100 + ctx.rank, sdf_res=256)
+    venv, pol = w["venv"], w["policy"]
+    pol.eval()
+    pol._deterministic_eval = True
+    venv.reset()
+
+    def step():
+        with torch.no_grad():
+            out = pol.forward(Batch(obs=venv.observation()))
+            _, _, term, _, _ = venv.step(out.act)
+            venv.reset_masked(term)
+    for _ in range(max(warmup, 3)):
+        step()
+    n_inner = 16
+    with clocked(ctx) as ck:
+        launches0 = _launches()
+        total_ms, _ = ctx.time_steps(lambda: [step() for _ in range(n_inner)], steps)
+        launches = _launches() - launches0
+    ms_step = total_ms / (steps * n_inner)
+    peak, how = peaks()
+    gbs = B_LBS_ENV_STEP / (ms_step * 1e-3) / 1e9
+    out = {"config_id": 1, "metric": "single-env eval env-steps/sec", "value": ctx.world_size * 1e3 / ms_step, "unit": "env-steps/s",
+           "latency_ms_per_env_step": ms_step, "n_gpus": ctx.world_size, "steps": steps * n_inner, "scaling": "replicas",
+           "higher_is_better": True, "dtype": DTYPE, "data": "synthetic", "gpu_launches": int(launches), "clocks": ck.result,
+           "config": {"workload": "single-agent evaluation (main_ppo.py --watch), 1 env per GPU, deterministic policy, 256^3 SDF; "
+                                  "16 env steps per timed call, L2 flushed between calls"},
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                        "peak_source": how, "kernel": "whole env step (LBS-bytes contract figure, 20 bodies x 127636 B)",
+                        "note": "latency-bound by construction: one env is a chain of ~70 dependent launches on 20 bodies"}}
+    if ctx.rank == 0 and ctx.world_size == 1:
+        from oracle import harness
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ow = harness.build_oracle_world(0, sdf_res=256)
+        harness.run_eval_steps(ow, 1, 1, True, seed=9)
+        s_, n_ = harness.run_eval_steps(ow, 1, 8, True, seed=0)
+        out["cpu_baseline"] = {"value": n_ / s_, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                               "sample": "oracle in the reference's shape (1 env, 4x duplicated batch), 8 env steps"}
+    return out if ctx.rank == 0 else None
+
+
+def _launches():
+    from egogen_b200 import _lib
+    return _lib.lib().eg_launch_count()
+
+
+def measure_cvae_train(ctx, steps, warmup):
+    """BASELINE config 3: C-VAE marker-predictor training on synthetic canonicalised primitives, batch 4096, 200-frame
+    sequences, max_rollout 8 (8 chained primitives per optimiser step), Adam 5e-4. Replicas (the reference trains on one GPU)."""
+    torch = ctx.torch
+    from egogen_b200.train_gamma_predictor import GAMMAPrimitiveVAETrainOP, SyntheticPrimitiveBatchGen
+    dev = ctx.dev
+    B = 4096
+    op = GAMMAPrimitiveVAETrainOP(trainconfig={"batch_size": B, "max_rollout": 8}, device=dev)
+    op.build_model(seed=0)
+    gen = SyntheticPrimitiveBatchGen(B, 200, dev, seed=ctx.rank)
+    data = gen.next_batch_with_jts(B)
+    loss = [None]
+
+    def step():
+        loss[0], _ = op.calc_loss_rollout(data, 0); op.optimizer_step(5e-4)
+    for _ in range(max(warmup, 3)):
+        step()
+    with clocked(ctx) as ck:
+        launches0 = _launches()
+        total_ms, _ = ctx.time_steps(step, steps)
+        launches = _launches() - launches0
+    prim = B * 8 * steps * ctx.world_size
+    # algorithmic MACs per primitive, forward: x_enc 2 x 351k, e_rnn 18 x 351k, e_mlp 393k, mu/logvar 66k, drnn_mlp 328k,
+    # decode 18 x (841 x 768 + 256 x 512 + 512 x 256 + 256 x 201) = 18 x 960k  -> 25.1 M; forward + backward = 3x
+    flop_prim = 2.0 * 3.0 * 25.1e6
+    tf = prim / ctx.world_size * flop_prim / (total_ms / 1e3) / 1e12
+    tf_peak, tf_how = tensor_peak()
+    out = {"config_id": 3, "metric": "C-VAE training primitives/sec", "value": prim / (total_ms / 1e3), "unit": "primitives/s",
+           "n_gpus": ctx.world_size, "steps": steps, "ms_per_step": total_ms / steps, "scaling": "replicas", "higher_is_better": True,
+           "dtype": DTYPE, "data": "synthetic", "loss": loss[0], "gpu_launches": int(launches), "clocks": ck.result,
+           "config": {"workload": "C-VAE predictor training, batch 4096 x 8-primitive rollout (200-frame sequences), Adam; "
+                                  "working set > L2, L2 flushed between steps"},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
+                        "peak_source": tf_how + " dense bf16 burst; the layers run 3xTF32 (3 tensor passes per useful FLOP, tf32 rate = 1/2)",
+                        "kernel": "gemm_tc_kernel family (forward / dX / dW of the GRU + MLP layers)",
+                        "flops_per_primitive": flop_prim}}
+    if ctx.rank == 0 and ctx.world_size == 1:
+        from oracle import harness
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        harness.run_cvae_train_steps(16, 200, 8, 1)
+        s_, n_ = harness.run_cvae_train_steps(128, 200, 8, 2)
+        out["cpu_baseline"] = {"value": n_ / s_, "unit": "primitives/s", "cores": cores, "kind": "port",
+                               "sample": "oracle predictor + torch autograd + Adam: batch 128 x 8-primitive rollout, 2 steps"}
+    return out if ctx.rank == 0 else None
+
+
+def measure_crowd_eval(ctx, steps, warmup):
+    """BASELINE config 4: 4-human crowd evaluation, 256 agents (64 scenes x 4) per GPU (2048 rollouts on 8 GPUs), scenes
+    sharded over ranks with no collective. One step = one vector step of every agent (policy forward + 4 agent-by-agent
+    env sub-steps in the reference's update order)."""
+    torch = ctx.torch
+    from egogen_b200.main_crowd_eval import build_crowd_world, crowd_start_data
+    from egogen_b200.ppo_policy import Batch
+    dev = ctx.dev
+    S, A = 64, 4
+    w = build_crowd_world(dev, S, A, sequential=True, seed=ctx.rank)
+    w["policy"].eval()
+    wp, goals, betas = crowd_start_data(w["sampler"], S, A, dev, seed=ctx.rank)
+    venv, pol = w["venv"], w["policy"]
+
+    def vector_step():
+        with torch.no_grad():
+            out = pol.forward(Batch(obs=venv.observation()))
+            venv.step(out.act)
+    venv.reset_from(torch.arange(S * A), wp, goals, betas)
+    for _ in range(max(warmup, 3)):
+        vector_step()
+    venv.reset_from(torch.arange(S * A), wp, goals, betas)
+    with clocked(ctx) as ck:
+        launches0 = _launches()
+        total_ms, _ = ctx.time_steps(vector_step, steps)
+        launches = _launches() - launches0
+    value = S * A * ctx.world_size * steps / (total_ms / 1e3)
+    peak, how = peaks()
+    gbs = value / ctx.world_size * B_LBS_ENV_STEP / 1e9
+    out = {"config_id": 4, "metric": "crowd eval agent-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": ctx.world_size,
+           "steps": steps, "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "dtype": DTYPE,
+           "data": "synthetic", "gpu_launches": int(launches), "clocks": ck.result,
+           "config": {"workload": "4-human crowd eval (main_crowd_eval.py): 64 scenes x 4 agents per GPU, agents see each other as "
+                                  "holes of the floor polygon, agent-by-agent update order; L2 flushed between vector steps"},
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                        "peak_source": how, "kernel": "whole vector step (LBS-bytes contract figure, 20 bodies x 127636 B per agent step)",
+                        "note": "4 sequential sub-steps of 64 agents each: launch / latency bound"}}
+    if ctx.rank == 0 and ctx.world_size == 1:
+        from oracle import harness
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        harness.run_crowd_steps(1, 4, 1, seed=1)
+        s_, n_ = harness.run_crowd_steps(2, 4, 3, seed=0)
+        out["cpu_baseline"] = {"value": n_ / s_, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                               "sample": "oracle crowd env: 2 scenes x 4 agents x 3 vector steps, reference update order"}
+    return out if ctx.rank == 0 else None
+
+
+def measure_ego_depth(ctx, steps, warmup):
     """BASELINE config 5: ego-depth ray-march sweep, 8192 agents x 64x64 rays per GPU against a resident 256^3 SDF
-    (agents sharded over ranks, grid replicated, no collective). Secondary workload: prints its own JSON line."""
-    import torch
-    import torch.distributed as dist
-    from egogen_b200 import _lib, assets, ego_depth
-    world_size = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local); dev = torch.device("cuda", local)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    (agents sharded over ranks, grid replicated, no collective)."""
+    torch = ctx.torch
+    from egogen_b200 import assets, ego_depth
+    dev, rank = ctx.dev, ctx.rank
     A, H, W = 8192, 64, 64
     scene = assets.make_box_scene(rank, n_boxes=4)
     sdf = {k: v.to(dev) for k, v in assets.rasterize_scene_sdf(scene, D=256, device=str(dev)).items()}
@@ -275,117 +488,68 @@ def run_ego_depth(args):
     right = right / right.norm(dim=1, keepdim=True)
     cam = torch.cat([eye, right, torch.cross(right, fwd, dim=1), fwd], 1).contiguous()
     fx = fy = 64 * (200.0 / 320.0)
-    for _ in range(max(args.warmup, 3)):
-        ego_depth(sdf, cam, H, W, fx, fy)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ms = []
-    for _ in range(args.steps):
-        flush.zero_()
-        if world_size > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); depth, steps = ego_depth(sdf, cam, H, W, fx, fy, return_steps=True); e1.record()
-        torch.cuda.synchronize(dev)
-        ms.append(e0.elapsed_time(e1))
-    t = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    mean_steps = float(steps.float().mean().item()) + 1.0       # samples per ray (the terminating sample included)
-    if rank == 0:
-        peak, how = peaks()
-        rays = A * H * W * world_size * args.steps
-        secs = float(t.item()) / 1e3
-        gathered = A * H * W * mean_steps * 32.0 / (sum(ms) / args.steps / 1e3) / 1e9     # bytes gathered / s, this rank
-        print(json.dumps({"metric": "ego-depth rays/sec", "value": rays / secs, "unit": "rays/s", "n_gpus": world_size,
-                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(t.item()) / args.steps,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "ego-depth sweep: 8192 agents x 64x64 rays per GPU, 256^3 SDF, <=64 sphere-trace steps, 7 m range"},
-                          "roofline": {"bound": "hbm", "achieved": gathered, "peak": peak, "unit": "GB/s", "frac": gathered / peak,
-                                       "traffic": None, "peak_source": how, "kernel": "ego_depth_kernel",
-                                       "mean_samples_per_ray": mean_steps,
-                                       "note": "achieved = rays x samples x 32 B of corner gathers (L2-served; grid 67 MB resident)"},
-                          "gpu_launches": args.steps}))
-    if world_size > 1:
-        dist.destroy_process_group()
+    res = [None]
+
+    def step():
+        res[0] = ego_depth(sdf, cam, H, W, fx, fy, return_steps=True)
+    for _ in range(max(warmup, 3)):
+        step()
+    with clocked(ctx) as ck:
+        total_ms, ms = ctx.time_steps(step, steps)
+    mean_steps = float(res[0][1].float().mean().item()) + 1.0       # samples per ray (the terminating sample included)
+    peak, how = peaks()
+    rays = A * H * W * ctx.world_size * steps
+    gathered = A * H * W * mean_steps * 32.0 / (sum(ms) / steps / 1e3) / 1e9     # bytes gathered / s, this rank
+    out = {"config_id": 5, "metric": "ego-depth rays/sec", "value": rays / (total_ms / 1e3), "unit": "rays/s", "n_gpus": ctx.world_size,
+           "steps": steps, "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+           "data": "synthetic", "gpu_launches": steps, "clocks": ck.result,
+           "config": {"workload": "ego-depth sweep: 8192 agents x 64x64 rays per GPU, 256^3 SDF, <=64 sphere-trace steps, 7 m range; "
+                                  "L2 flushed between sweeps"},
+           "roofline": {"bound": "hbm", "achieved": gathered, "peak": peak, "unit": "GB/s", "frac": gathered / peak, "traffic": None,
+                        "peak_source": how, "kernel": "ego_depth_kernel", "mean_samples_per_ray": mean_steps,
+                        "note": "achieved = rays x samples x 32 B of corner gathers (L2-served; grid 67 MB resident)"}}
+    if ctx.rank == 0 and ctx.world_size == 1:
+        from oracle import harness
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sdf_cpu = {k: v.cpu() for k, v in sdf.items()}
+        harness.run_ego_depth_cpu(sdf_cpu, cam[:4].cpu(), H, W, fx, fy)
+        s_, n_ = harness.run_ego_depth_cpu(sdf_cpu, cam[:256].cpu(), H, W, fx, fy)
+        out["cpu_baseline"] = {"value": n_ / s_, "unit": "rays/s", "cores": cores, "kind": "port",
+                               "sample": "defining oracle (torch-CPU, all threads): 256 agents x 64x64 rays"}
+    return out if ctx.rank == 0 else None
 
 
-def run_crowd_eval(args):
-    """BASELINE config 4: 4-human crowd evaluation, 256 agents (64 scenes x 4) per GPU, scenes sharded over ranks with
-    no collective. One step = one vector step of every agent (policy forward + 4 agent-by-agent env sub-steps in the
-    reference's update order). Secondary workload: prints its own JSON line."""
-    import torch
-    import torch.distributed as dist
-    from egogen_b200.main_crowd_eval import build_crowd_world, crowd_start_data
-    from egogen_b200.ppo_policy import Batch
-    world_size = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local); dev = torch.device("cuda", local)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    S, A = 64, 4
-    w = build_crowd_world(dev, S, A, sequential=True, seed=rank)
-    w["policy"].eval()
-    wp, goals, betas = crowd_start_data(w["sampler"], S, A, dev, seed=rank)
-    venv, pol = w["venv"], w["policy"]
-
-    def vector_step():
-        with torch.no_grad():
-            out = pol.forward(Batch(obs=venv.observation()))
-            venv.step(out.act)
-
-    venv.reset_from(torch.arange(S * A), wp, goals, betas)
-    for _ in range(max(args.warmup, 3)):
-        vector_step()
-    venv.reset_from(torch.arange(S * A), wp, goals, betas)
-    if world_size > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        vector_step()
-    e1.record(); torch.cuda.synchronize(dev)
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        ms = float(t.item())
-        print(json.dumps({"metric": "crowd eval agent-steps/sec", "value": S * A * world_size * args.steps / (ms / 1e3),
-                          "unit": "env-steps/s", "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
-                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
-                          "data": "synthetic",
-                          "config": {"workload": "4-human crowd eval (main_crowd_eval.py): 64 scenes x 4 agents per GPU, agents see "
-                                                 "each other as holes of the floor polygon, agent-by-agent update order"}}))
-    if world_size > 1:
-        dist.destroy_process_group()
+SECONDARY = {"single_env": measure_single_env, "cvae_train": measure_cvae_train, "crowd_eval": measure_crowd_eval,
+             "ego_depth": measure_ego_depth}
 
 
-def run_cvae_train(args):
-    """BASELINE config 3: C-VAE marker-predictor training on synthetic canonicalised primitives, batch 4096, 200-frame
-    sequences, max_rollout 8 (8 chained primitives per optimiser step), Adam 5e-4. Secondary workload."""
-    import torch
-    from egogen_b200.train_gamma_predictor import GAMMAPrimitiveVAETrainOP, SyntheticPrimitiveBatchGen
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
-    B = 4096
-    op = GAMMAPrimitiveVAETrainOP(trainconfig={"batch_size": B, "max_rollout": 8}, device=dev)
-    op.build_model(seed=0)
-    gen = SyntheticPrimitiveBatchGen(B, 200, dev, seed=0)
-    data = gen.next_batch_with_jts(B)
-    for _ in range(max(args.warmup, 3)):
-        op.calc_loss_rollout(data, 0); op.optimizer_step(5e-4)
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss, _ = op.calc_loss_rollout(data, 0); op.optimizer_step(5e-4)
-    e1.record(); torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
-    print(json.dumps({"metric": "C-VAE training primitives/sec", "value": B * 8 * args.steps / (ms / 1e3), "unit": "primitives/s",
-                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-                      "higher_is_better": True, "dtype": "f32", "data": "synthetic", "loss": loss,
-                      "config": {"workload": "C-VAE predictor training, batch 4096 x 8-primitive rollout (200-frame sequences), Adam"}}))
+def run_ours(args):
+    ctx = Ctx()
+    line = measure_ppo(ctx, args)
+    if not args.no_secondary:
+        sec = []
+        for name, fn in SECONDARY.items():
+            try:
+                r = fn(ctx, max(2, min(args.steps, 5)), args.warmup)
+            except Exception as e:                       # noqa: BLE001 - a secondary workload must not take the headline line down
+                r = {"workload": name, "error": f"{type(e).__name__}: {e}"} if ctx.rank == 0 else None
+            ctx.torch.cuda.empty_cache()
+            if r is not None:
+                sec.append(r)
+        if line is not None:
+            line["secondary"] = sec
+    if line is not None:
+        print(json.dumps(line))
+    ctx.close()
+
+
+def run_secondary(args):
+    ctx = Ctx()
+    r = SECONDARY[args.workload](ctx, args.steps, args.warmup)
+    if r is not None:
+        print(json.dumps(r))
+    ctx.close()
 
 
 def run_regressor_train(args):
@@ -453,15 +617,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "ego_depth", "cvae_train", "crowd_eval", "regressor_train", "combo_train"],
-                    help="ppo = headline (BASELINE config 2); ego_depth = secondary config-5 sweep")
+    ap.add_argument("--workload", type=str, default="ppo",
+                    choices=["ppo", "single_env", "ego_depth", "cvae_train", "crowd_eval", "regressor_train", "combo_train"],
+                    help="ppo = headline (BASELINE config 2, with the secondary configs attached); the others run alone")
+    ap.add_argument("--no-secondary", action="store_true", help="ppo workload only: skip BASELINE configs 1, 3, 4, 5")
     args = ap.parse_args()
-    if args.workload == "ego_depth" and args.impl == "ours":
-        return run_ego_depth(args)
-    if args.workload == "cvae_train" and args.impl == "ours":
-        return run_cvae_train(args)
-    if args.workload == "crowd_eval" and args.impl == "ours":
-        return run_crowd_eval(args)
+    if args.workload in SECONDARY and args.impl == "ours":
+        return run_secondary(args)
     if args.workload == "regressor_train" and args.impl == "ours":
         return run_regressor_train(args)
     if args.workload == "combo_train" and args.impl == "ours":

@@ -103,6 +103,7 @@ PROTOTYPES = {
     "eg_env_step": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P]),
     "eg_env_reset": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
     "eg_env_reset_masked": (_I, [_P, C.POINTER(EgEnvBuffers), _P, _I, _P, _P, _P, _P, _P]),
+    "eg_egosensing": (_I, [_P, _P, _P, _I, _P, _I, C.c_double, _P, _I, _P, _P]),
     "eg_env_restart_from_pool": (_I, [C.POINTER(EgEnvBuffers), C.POINTER(EgEnvBuffers), _I, _P, _I, _P, _P]),
     "eg_policy_param_count": (_L, [C.POINTER(EgPolicyDims), C.POINTER(C.c_int64)]),
     "eg_policy_param_offsets": (_I, [C.POINTER(EgPolicyDims), C.POINTER(C.c_int64), _I]),

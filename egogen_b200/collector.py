@@ -194,18 +194,33 @@ class Collector:
 
     @torch.no_grad()
     def collect_episodes(self, n_episode: int, max_steps: int = 10000):
-        """test_collector.collect(n_episode=...) (main_ppo.py:242): run until n_episode episodes finished."""
+        """test_collector.collect(n_episode=...) (main_ppo.py:242). tianshou gives every env a quota (n_episode spread over
+        the envs, the first n_episode % E envs one more) and stops stepping an env once its quota is met, so long episodes
+        are not crowded out by envs that finish early; finished envs with quota left restart immediately.
+        When the env has ``save_rollout`` set, every finished episode is written as a rollout pickle (crowd_env_2f.py:305-309)."""
         self.reset()
+        E = self.E
+        quota = np.full(E, n_episode // E, dtype=np.int64)
+        quota[:n_episode % E] += 1
+        done_count = np.zeros(E, dtype=np.int64)
         rets, lens, steps = [], [], 0
-        while sum(len(r) for r in rets) < n_episode and steps < max_steps:
+        save = bool(getattr(self.venv, "save_rollout", False))
+        while int(done_count.sum()) < n_episode and steps < max_steps:
             out = self.policy.forward(Batch(obs=self.venv.observation()))
+            pre = self.venv.begin_rollout_step() if save else None
             _, rew, term, _, _ = self.venv.step(out.act)
-            self.ep_ret += rew; self.ep_len += 1
-            done = term.nonzero().view(-1)
+            active = torch.as_tensor(done_count < quota, device=self.dev)
+            self.ep_ret += rew * active; self.ep_len += active.to(self.ep_len.dtype)
+            if save:
+                self.venv.record_rollout(pre, term & active.to(term.dtype))
+            done = (term.bool() & active).nonzero().view(-1)
             if done.numel() > 0:
                 rets.append(self.ep_ret[done].cpu().numpy()); lens.append(self.ep_len[done].cpu().numpy())
                 self.ep_ret[done] = 0; self.ep_len[done] = 0
-                self.venv.reset(done)
+                done_count[done.cpu().numpy()] += 1
+            fin = term.bool().nonzero().view(-1)                    # envs past their quota keep idling on fresh episodes
+            if fin.numel() > 0:
+                self.venv.reset(fin)
             steps += 1
         r = np.concatenate(rets)[:n_episode] if rets else np.zeros(0)
         l = np.concatenate(lens)[:n_episode] if lens else np.zeros(0)

@@ -22,6 +22,23 @@ from . import _lib, assets
 from .sdf import calc_sdf, _grid3
 
 
+# eg_env_set_scene registers conservative sign grids for the SDF it is given, keyed by the grid's device pointer
+# (eg_sdf_prepare); several envs may share one grid tensor, so the registry entry is released with the last of them
+_SDF_REFS = {}
+
+
+def _sdf_unref(grid):
+    if grid is None:
+        return
+    k = grid.data_ptr()
+    n = _SDF_REFS.get(k, 0) - 1
+    if n <= 0:
+        _SDF_REFS.pop(k, None)
+        _lib.lib().eg_sdf_release(_lib.ptr(grid))
+    else:
+        _SDF_REFS[k] = n
+
+
 def default_cfg(finetuning: bool = False):
     """Values of crowd_ppo/cfg_samp20/MPVAEPolicy_samp_collision.yaml that the env reads."""
     return SimpleNamespace(
@@ -57,9 +74,15 @@ class BoxSceneSampler:
     start pose / goal pairs in the free space of one rasterised scene, returned as world-frame 2-frame
     SMPL-X seeds. Gender is always 'male' and betas 0 like the reference samplers (environments.py:191,254)."""
 
-    def __init__(self, scene_sdf: dict, lbs_model, device, floor_half: float = 4.0, seed: int = 0,
+    def __init__(self, scene_sdf: dict, lbs_model, device, floor_half: Optional[float] = None, seed: int = 0,
                  pose_noise: float = 0.05, min_goal_dist: float = 1.0):
-        self.sdf, self.dev, self.fh = scene_sdf, torch.device(device), floor_half
+        self.sdf, self.dev = scene_sdf, torch.device(device)
+        # sampling square: the SDF volume's own x/y extent (grid coordinate p = (x - center) * scale spans [-1, 1]) unless
+        # the caller gives a half-width; a scene that is not centred at the origin is therefore sampled where it is
+        c = scene_sdf["center"].reshape(-1).to(torch.float32).cpu()
+        sc = float(scene_sdf["scale"].reshape(-1)[0])
+        self.cx, self.cy = float(c[0]), float(c[1])
+        self.fh = float(floor_half) if floor_half is not None else min(4.0, 1.0 / max(sc, 1e-6))
         self.gen = torch.Generator(device=self.dev)
         self.gen.manual_seed(seed)
         self.pose_noise, self.min_goal = pose_noise, min_goal_dist
@@ -79,12 +102,18 @@ class BoxSceneSampler:
     def _free_xy(self, n):
         """n points whose column above the floor is at least 0.6 m from any obstacle (one host sync per call)."""
         out = torch.empty(0, 2, device=self.dev)
-        while out.shape[0] < n:
-            xy = (torch.rand(2 * n + 64, 2, device=self.dev, generator=self.gen) * 2 - 1) * (self.fh - 0.8)
+        ctr = torch.tensor([self.cx, self.cy], device=self.dev)
+        for _ in range(64):                                       # bounded: a scene without free space must not hang
+            if out.shape[0] >= n:
+                return out[:n]
+            xy = (torch.rand(2 * n + 64, 2, device=self.dev, generator=self.gen) * 2 - 1) * max(self.fh - 0.8, 0.1) + ctr
             pts = torch.cat([xy, torch.full((xy.shape[0], 1), 0.9, device=self.dev)], dim=1)
             d = calc_sdf(pts.unsqueeze(0), self.sdf)[0]
             out = torch.cat([out, xy[d > 0.6]], dim=0)
-        return out[:n]
+        if out.shape[0] >= n:
+            return out[:n]
+        raise _lib.EgError(f"BoxSceneSampler: found only {out.shape[0]} of {n} free start points within +-{self.fh - 0.8:.2f} m of "
+                           f"({self.cx:.2f}, {self.cy:.2f}); pass floor_half or a sampler that knows the scene")
 
     def _refill(self, n):
         """Pre-generate a pool of n candidates entirely on the device so that next_body() is sync-free slicing."""
@@ -178,8 +207,11 @@ class CrowdVectorEnv:
 
     def set_scene(self, scene_sdf, scene_rings):
         dev = self.dev
+        old = getattr(self, "_grid", None)
         self.scene_sdf = scene_sdf
         self._grid = _grid3(scene_sdf)
+        _SDF_REFS[self._grid.data_ptr()] = _SDF_REFS.get(self._grid.data_ptr(), 0) + 1
+        _sdf_unref(old)
         self._center = scene_sdf["center"].to(torch.float32).reshape(-1).contiguous()
         self._scale = scene_sdf["scale"].to(torch.float32).reshape(-1).contiguous()
         skip = torch.zeros(assets.V_SMPLX, dtype=torch.uint8)
@@ -325,27 +357,134 @@ class CrowdVectorEnv:
                                                _lib.ptr(_lib.f32c(betas, dev)), _lib.ptr(accept), _lib.stream_ptr(dev)))
         return accept
 
-    def step(self, action_z: torch.Tensor):
-        """action_z [E,128] CUDA float32 -> (obs, reward [E], terminated [E] uint8, truncated [E], info)."""
+    _STATE_KEYS = ("state", "seed", "R0", "T0", "betas", "dist", "steps", "goal", "ego", "obs_dist", "obs_time", "reward",
+                   "terminated", "goal_reached")
+
+    def _ids(self, id):
+        if id is None:
+            return None
+        ids = torch.as_tensor([id] if isinstance(id, (int, np.integer)) else np.asarray(id), dtype=torch.long, device=self.dev)
+        return None if (ids.numel() == self.E and bool((ids == torch.arange(self.E, device=self.dev)).all())) else ids
+
+    def step(self, action_z: torch.Tensor, id=None):
+        """action_z [E,128] CUDA float32 -> (obs, reward [E], terminated [E] uint8, truncated [E], info).
+        ``id`` (tianshou BaseVectorEnv.step, dummy_vector_env.py:41-45): step only those envs - actions, returned tensors and
+        ``info`` then follow the order of ``id``; the other envs keep their state. info[i]['env_id'] names the env of row i."""
+        ids = self._ids(id)
         z = _lib.f32c(action_z, self.dev)
+        keep = None
+        if ids is not None:
+            if z.shape != (ids.numel(), 128):
+                raise _lib.EgError(f"action must be [{ids.numel()},128] for {ids.numel()} env ids")
+            full = torch.zeros(self.E, 128, device=self.dev)
+            full[ids] = z
+            z = full
+            keep = {k: self.buf[k].clone() for k in self._STATE_KEYS if self.buf.get(k) is not None}
         if z.shape != (self.E, 128):
             raise _lib.EgError(f"action must be [{self.E},128]")
         with torch.cuda.device(self.dev):
             _lib.check(_lib.lib().eg_env_step(self._h, C.byref(self._cbuf), _lib.ptr(z), self.E,
                                               _lib.stream_ptr(self.dev)))
         b = self.buf
-        return self.observation(), b["reward"], b["terminated"], torch.zeros_like(b["terminated"]), {}
+        if ids is None:
+            return self.observation(), b["reward"], b["terminated"], torch.zeros_like(b["terminated"]), \
+                [{"env_id": j} for j in range(self.E)]
+        mask = torch.zeros(self.E, dtype=torch.bool, device=self.dev)
+        mask[ids] = True
+        out = {k: b[k][ids].clone() for k in ("state", "ego", "obs_dist", "obs_time", "reward", "terminated")}
+        for k, v in keep.items():                                  # envs that were not stepped keep their state
+            mk = mask.view(-1, *([1] * (v.dim() - 1)))
+            b[k].copy_(torch.where(mk, b[k], v))
+        obs = {"state": out["state"], "egosensing": out["ego"], "dist": out["obs_dist"].view(-1, 1), "time": out["obs_time"].view(-1, 1)}
+        return obs, out["reward"], out["terminated"], torch.zeros_like(out["terminated"]), [{"env_id": int(j)} for j in ids.tolist()]
+
+    # ---- rollout pickles at episode end (crowd_env_2f.py:154-155,305-309 -> utils.save_rollout_results) -----------
+    save_rollout = False
+    rollout_dir = "./log/eval_results/"
+
+    def begin_rollout_step(self):
+        """Call BEFORE step() when save_rollout is on: the canonical frame a primitive is recorded with is the one it was
+        generated in (:155 precedes the re-canonicalisation at :247)."""
+        return self.buf["R0"].clone(), self.buf["T0"].clone()
+
+    def record_rollout(self, pre, terminated):
+        """Call AFTER step() with begin_rollout_step()'s result: appends every env's primitive to its episode record and
+        writes ``motion_<time>.pkl`` for the envs whose episode ended. Host-side (one D2H of the flags); evaluation only.
+        Returns the files written."""
+        if self.buf.get("out_markers") is None:
+            raise _lib.EgError("record_rollout needs capture_rollout=True")
+        from .utils import save_rollout_results
+        if getattr(self, "_outmps", None) is None:
+            self._outmps = [[] for _ in range(self.E)]
+            self._wpath0 = [None] * self.E
+        R0, T0 = pre
+        b = self.buf
+        term = terminated.cpu().numpy().astype(bool)
+        files = []
+        for e in range(self.E):
+            if not self._outmps[e]:
+                self._wpath0[e] = T0[e].clone()                      # pelvis of the start frame = origin of the first frame
+            self._outmps[e].append([b["out_markers"][e:e + 1].clone(), b["out_params"][e:e + 1].clone(), b["betas"][e].clone(),
+                                    "male", R0[e], T0[e].view(1, 3), b["out_pelvis"][e:e + 1].clone(), "2-frame"])
+            if term[e]:
+                scene = {"wpath": torch.stack([self._wpath0[e], b["goal"][e]]),
+                         "navmesh_path": getattr(self.sampler, "navmesh_path", None),
+                         "scene_path": getattr(self.sampler, "scene_path", None)}
+                files.append(save_rollout_results(scene, self._outmps[e], self.rollout_dir))
+                self._outmps[e] = []
+        return files
+
+    def get_env_attr(self, key: str, id=None):
+        """tianshou BaseVectorEnv.get_env_attr: one value per env (a row of the device buffer `key`, or the Python attribute
+        shared by all envs)."""
+        ids = self._ids(id)
+        rows = range(self.E) if ids is None else ids.tolist()
+        src = self.buf.get(key) if key in self.buf else getattr(self, key)
+        if torch.is_tensor(src) and src.dim() >= 1 and src.shape[0] == self.E:
+            return [src[j] for j in rows]
+        return [src for _ in rows]
+
+    def set_env_attr(self, key: str, value, id=None):
+        """tianshou BaseVectorEnv.set_env_attr: write `value` (one value, or one per env) into the rows of buffer `key`."""
+        ids = self._ids(id)
+        rows = list(range(self.E)) if ids is None else ids.tolist()
+        dst = self.buf.get(key) if key in self.buf else getattr(self, key, None)
+        if not (torch.is_tensor(dst) and dst.dim() >= 1 and dst.shape[0] == self.E):
+            setattr(self, key, value)
+            return
+        vals = value if isinstance(value, (list, tuple)) and len(value) == len(rows) else [value] * len(rows)
+        for j, v in zip(rows, vals):
+            dst[j] = torch.as_tensor(v, dtype=dst.dtype, device=self.dev).reshape(dst[j].shape)
 
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().eg_env_destroy(self._h)
             self._h = None
+            _sdf_unref(getattr(self, "_grid", None))            # drop the conservative sign grids registered for this SDF
+            self._grid = None
 
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+
+def calc_egosensing(joints_local, R0, T0, scene_rings, ray_len: float = 7.0, holes=None):
+    """``CrowdEnv._calc_egosensing`` (crowd_env_2f.py:524-613) as a stand-alone operator: joints_local [n,2,127,3] CUDA
+    float32 body-frame joints of the 2-frame seed, R0 [n,3,3], T0 [n,3], the scene polygon rings (exterior + holes) and
+    optional per-item hole rectangles [n,H,4] -> [n,2,32] ray distances mapped to [-1,1]."""
+    dev = joints_local.device
+    j = _lib.f32c(joints_local, dev)
+    n = j.shape[0]
+    segs = torch.as_tensor(assets.rings_to_segments(scene_rings), dtype=torch.float64, device=dev).contiguous()
+    out = torch.zeros(n, 2, 32, dtype=torch.float32, device=dev)
+    hl = None if holes is None else _lib.f32c(holes, dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().eg_egosensing(_lib.ptr(j), _lib.ptr(_lib.f32c(R0, dev)), _lib.ptr(_lib.f32c(T0, dev)), n,
+                                            _lib.ptr(segs), segs.shape[0], float(ray_len), _lib.ptr(hl),
+                                            0 if hl is None else hl.shape[1], _lib.ptr(out), _lib.stream_ptr(dev)))
+    return out
 
 
 class CrowdSceneVectorEnv(CrowdVectorEnv):
@@ -410,7 +549,9 @@ class CrowdSceneVectorEnv(CrowdVectorEnv):
     def reset(self, env_ids=None, max_tries: int = 50):
         raise _lib.EgError("CrowdSceneVectorEnv starts from explicit per-agent data: use reset_from (main_crowd_eval.py:47)")
 
-    def step(self, action_z: torch.Tensor):
+    def step(self, action_z: torch.Tensor, id=None):
+        if self._ids(id) is not None:
+            raise NotImplementedError("the crowd scene steps all agents of all scenes together (DummyCrowdVectorEnv.step with id=None)")
         z = _lib.f32c(action_z, self.dev)
         if z.shape != (self.E, 128):
             raise _lib.EgError(f"action must be [{self.E},128]")
@@ -427,7 +568,8 @@ class CrowdSceneVectorEnv(CrowdVectorEnv):
                 self._set_crowd(None)
                 _lib.check(lib.eg_env_step(self._h, C.byref(self._cbuf), _lib.ptr(z), self.E, _lib.stream_ptr(self.dev)))
         b = self.buf
-        return self.observation(), b["reward"], b["terminated"], torch.zeros_like(b["terminated"]), {}
+        return self.observation(), b["reward"], b["terminated"], torch.zeros_like(b["terminated"]), \
+            [{"env_id": j} for j in range(self.E)]
 
 
 class CrowdEnv:
@@ -450,6 +592,8 @@ class CrowdEnv:
                                     self.scene_sampler.scene_rings, self.scene_sampler, 1, dev,
                                     self.feet_marker_idx, finetuning, capture_rollout=save_rollout)
         self.outmps, self.flag, self.steps = [], False, 0
+        self.rollout_dir = "./log/eval_results/"                   # crowd_env_2f.py:309
+        self.body_scene_data = None
 
     def seed(self, seed):
         np.random.seed(seed)
@@ -464,19 +608,28 @@ class CrowdEnv:
     def reset(self, seed=None, options=None):
         self.flag, self.steps, self.outmps = False, 0, []
         obs, info = self._venv.reset()
+        b = self._venv.buf
+        # what save_rollout_results reads from the sampler dict (utils.py:10-28): the way-points (start pelvis, goal) and
+        # the scene / navmesh file names when the sampler knows them
+        self.body_scene_data = {"wpath": torch.stack([b["T0"][0], b["goal"][0]]).clone(),
+                                "navmesh_path": getattr(self.scene_sampler, "navmesh_path", None),
+                                "scene_path": getattr(self.scene_sampler, "scene_path", None)}
         return self._single(obs), info
 
     def step(self, action_z):
         if self.flag:
             raise RuntimeError("the episode should be terminated! do not collect undefined states")
         z = torch.as_tensor(action_z, dtype=torch.float32, device=self._venv.dev).reshape(1, 128)
+        b = self._venv.buf
+        R0, T0 = b["R0"][0].clone(), b["T0"][0].clone().view(1, 3)      # frame of THIS primitive (:155 precedes :247)
         obs, rew, term, _, _ = self._venv.step(z)
         self.steps += 1
         terminated = bool(term[0].item())
         if self.save_rollout:
-            b = self._venv.buf
             self.outmps.append([b["out_markers"].clone(), b["out_params"].clone(), b["betas"][0].clone(), "male",
-                                b["R0"][0].clone(), b["T0"][0].clone().view(1, 3), b["out_pelvis"].clone(), "2-frame"])
+                                R0, T0, b["out_pelvis"].clone(), "2-frame"])
             if terminated:
                 self.flag = True
+                from .utils import save_rollout_results
+                self.last_rollout_file = save_rollout_results(self.body_scene_data, self.outmps, self.rollout_dir)   # :305-309
         return self._single(obs), float(rew[0].item()), terminated, False, {}

@@ -8,6 +8,8 @@
 //   -> eg_vposer_encode -> env_reward_recanon_kernel (8 reward terms, termination, new canonical frame,
 //   update_transl_glorot, marker/goal features -> next state) -> eg_lbs_forward (joints of the new
 //   2-frame seed) -> env_egosensing_kernel (2 x 32 fp64 rays against the scene polygon).
+#include <stdlib.h>
+
 #include <vector>
 
 #include "geom.cuh"
@@ -431,14 +433,15 @@ __global__ void __launch_bounds__(64)
 env_egosensing_kernel(const float* __restrict__ joints, const float* __restrict__ R0a,
                       const float* __restrict__ T0a, const int32_t* __restrict__ slot_ids,
                       const int32_t* __restrict__ accept, const double* __restrict__ segs, int S,
-                      double ray_len, float* __restrict__ ego, const float* __restrict__ holes_all, int n_holes) {
+                      double ray_len, float* __restrict__ ego, const float* __restrict__ holes_all, int n_holes,
+                      int frames = 2, int frame0 = 0) {
   const int i = blockIdx.x;
   if (accept && !accept[i]) return;
   const int t = threadIdx.x >> 5, ray = threadIdx.x & 31;
   const int slot = slot_ids ? slot_ids[i] : i;     // output row; R0/T0/joints are indexed by item i
   const float* R0 = R0a + (int64_t)i * 9;
   const float* T0 = T0a + (int64_t)i * 3;
-  const float* j = joints + ((int64_t)i * 2 + t) * NJ * 3;
+  const float* j = joints + ((int64_t)i * frames + frame0 + t) * NJ * 3;   // the item's frames frame0, frame0 + 1
   float w[4][2];
   const int ids[4] = {23, 24, 56, 57};
 #pragma unroll
@@ -528,6 +531,11 @@ struct EgEnv {
   float *Y = nullptr, *params = nullptr, *joints = nullptr, *mproj = nullptr, *vp = nullptr, *prest = nullptr;
   float *joints2 = nullptr, *R0c = nullptr, *T0c = nullptr, *seedc = nullptr;
   int32_t* counts = nullptr;
+  // VPoser (needs only the blended parameters) runs beside the LBS + SDF pass on a side stream
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int overlap = 1;          // EG_ENV_OVERLAP=0: everything on the caller's stream
+  int seed_lbs = 0;         // EG_ENV_SEED_LBS=1: ego-sensing joints from a second SMPL-X pass over the new seed (reference order)
 };
 
 static int env_ws(EgEnv* h, int E) {
@@ -559,11 +567,22 @@ extern "C" int eg_env_create(const EgEnvConfig* cfg, EgLbs* lbs, EgMotion* motio
   EgEnv* h = new EgEnv();
   h->device = device; h->cfg = *cfg; h->lbs = lbs; h->motion = motion; h->vposer = vposer;
   *out = h;
+  EG_CUDA_CHECK(cudaSetDevice(device));
+  EG_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  EG_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  EG_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  const char* e1 = getenv("EG_ENV_OVERLAP");
+  h->overlap = (e1 != nullptr && e1[0] == '0') ? 0 : 1;
+  const char* e2 = getenv("EG_ENV_SEED_LBS");
+  h->seed_lbs = (e2 != nullptr && e2[0] == '1') ? 1 : 0;
   return EG_OK;
 }
 
 extern "C" void eg_env_destroy(EgEnv* h) {
   if (!h) return;
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaSetDevice(h->device);
   float* fb[] = {h->Y, h->params, h->joints, h->mproj, h->vp, h->prest, h->joints2, h->R0c, h->T0c, h->seedc};
   for (auto p : fb) cudaFree(p);
@@ -620,6 +639,15 @@ extern "C" int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int 
   // c: history frames + parameter blending (:116-120)
   EG_LAUNCH(env_prepare_params_kernel, E, 128, 0, st, b->seed, h->params, E);
   stage_mark(st, 2);
+  // f: VPoser latent of every frame's body pose (:197-200) - independent of the body pass: side stream
+  void* vp_stream = stream;
+  if (h->overlap) {
+    EG_CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
+    EG_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    vp_stream = h->side;
+  }
+  EG_TRY(eg_vposer_encode(h->vposer, h->params + 6, 93, E * NT, h->vp, vp_stream));
+  if (h->overlap) EG_CUDA_CHECK(cudaEventRecord(h->ev_join, h->side));
   if (h->cfg.pene_mode == 1) {
     // box-scene env (crowd_env_2f_box.py): no vertex-level SDF query - joints and markers only
     EG_REQUIRE(h->tris != nullptr, "navmesh not set (eg_env_set_navmesh)");
@@ -630,19 +658,27 @@ extern "C" int eg_env_step(EgEnv* h, const EgEnvBuffers* b, const float* z, int 
                               h->D2, h->center, h->scale, h->skip, h->counts, h->joints, h->mproj, stream));
   }
   stage_mark(st, 3);
-  // f: VPoser latent of every frame's body pose (:197-200)
-  EG_TRY(eg_vposer_encode(h->vposer, h->params + 6, 93, E * NT, h->vp, stream));
+  if (h->overlap) EG_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join, 0));
   stage_mark(st, 4);
+  // i: ego-sensing of the new 2-frame seed (:290-296). The seed is frames 18 / 19 of this primitive, and re-canonicalising
+  // moves the FRAME, not the body: R0' j' + T0' = R0 j + T0. The world joints the rays start from are therefore the joints
+  // of frames 18 / 19 the body pass above already produced, under the frame of THIS step (before the reward kernel updates
+  // R0 / T0) - no second SMPL-X pass. (The reference re-evaluates SMPL-X on the updated parameters; same points up to fp32
+  // rounding of its axis-angle round trip. EG_ENV_SEED_LBS=1 keeps that order.)
+  if (!h->seed_lbs)
+    EG_LAUNCH(env_egosensing_kernel, E, 64, 0, st, h->joints, b->R0, b->T0, nullptr, nullptr, h->segs, h->S,
+              (double)h->cfg.ray_len, b->ego, h->holes, h->n_holes, NT, NT - 2);
   EG_TRY(eg_lbs_rest_pelvis(h->lbs, b->betas, E, E, h->prest, stream));
   StepArgs a{h->cfg, *b, h->Y, h->params, h->counts, h->joints, h->mproj, h->vp, h->prest, h->tris, h->n_tris,
              h->holes, h->n_holes, h->bbox_out, h->pene_terminates};
   EG_LAUNCH(env_reward_recanon_kernel, E, 256, 0, st, a);
   stage_mark(st, 5);
-  // i: all joints of the re-canonicalised seed for ego-sensing (:290-296)
-  EG_TRY(eg_lbs_forward(h->lbs, b->seed, b->betas, E, E * 2, nullptr, h->joints2, nullptr, stream));
-  stage_mark(st, 6);
-  EG_LAUNCH(env_egosensing_kernel, E, 64, 0, st, h->joints2, b->R0, b->T0, nullptr, nullptr, h->segs, h->S,
-            (double)h->cfg.ray_len, b->ego, h->holes, h->n_holes);
+  if (h->seed_lbs) {
+    EG_TRY(eg_lbs_forward(h->lbs, b->seed, b->betas, E, E * 2, nullptr, h->joints2, nullptr, stream));
+    stage_mark(st, 6);
+    EG_LAUNCH(env_egosensing_kernel, E, 64, 0, st, h->joints2, b->R0, b->T0, nullptr, nullptr, h->segs, h->S,
+              (double)h->cfg.ray_len, b->ego, h->holes, h->n_holes, 2, 0);
+  }
   stage_mark(st, 7);
   return EG_OK;
 }
@@ -681,6 +717,18 @@ extern "C" int eg_update_transl_glorot(EgLbs* lbs, const float* transf_rotmat, c
   if (rc) return rc;
   EG_LAUNCH(update_transl_glorot_kernel, (N + 127) / 128, 128, 0, as_stream(stream), transf_rotmat, transf_transl,
             (const float*)delta_T, xb, N, xb_out);
+  return EG_OK;
+}
+
+// ego-sensing alone (CrowdEnv._calc_egosensing, crowd_env_2f.py:524-613): the operator the step / reset paths launch,
+// exposed so it can be checked on GIVEN joints
+extern "C" int eg_egosensing(const float* joints_local, const float* R0, const float* T0, int n, const double* segments_dev,
+                             int n_segments, double ray_len, const float* holes_dev, int n_holes, float* ego_out, void* stream) {
+  EG_REQUIRE(joints_local && R0 && T0 && segments_dev && ego_out && n >= 0 && n_segments >= 0, "bad arguments");
+  EG_REQUIRE(holes_dev != nullptr || n_holes == 0, "holes pointer missing");
+  if (n == 0) return EG_OK;
+  EG_LAUNCH(env_egosensing_kernel, n, 64, 0, as_stream(stream), joints_local, R0, T0, nullptr, nullptr, segments_dev, n_segments,
+            ray_len, ego_out, holes_dev, n_holes);
   return EG_OK;
 }
 

@@ -119,6 +119,7 @@ lrelu_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ 
   const int col = blockIdx.x * 16 + cl;
   float s = 0.0f;
   if (col < N)
+#pragma unroll 8
     for (int m = rl; m < M; m += 16) {
       const int64_t i = (int64_t)m * N + col;
       const float g = y[i] > 0.0f ? dy[i] : dy[i] * slope;

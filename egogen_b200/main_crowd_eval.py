@@ -50,6 +50,11 @@ def get_args(argv=None):
                    help="step all agents against the previous step's boxes (one launch sequence) instead of the "
                         "reference's agent-by-agent update order")
     p.add_argument("--body-model-path", type=str, default=None)
+    p.add_argument("--motion-results-root", type=str, default="results/crowd_ppo")
+    p.add_argument("--predictor-dir", type=str, default=None)
+    p.add_argument("--regressor-dir", type=str, default=None)
+    p.add_argument("--vposer-dir", type=str, default=None)
+    p.add_argument("--synthetic-assets", default=False, action="store_true")
     return p.parse_args(argv)
 
 
@@ -72,14 +77,15 @@ def crowd_start_data(sampler, n_scenes, n_agents, device, seed=0):
     return wp.to(device), goals.to(device), betas.to(device)
 
 
-def build_crowd_world(device, n_scenes, n_agents=4, sequential=True, seed=0, body_model_path=None, args=None):
+def build_crowd_world(device, n_scenes, n_agents=4, sequential=True, seed=0, body_model_path=None, args=None,
+                      predictor_dir=None, regressor_dir=None, vposer_dir=None):
     dev = torch.device(device)
     cfg = default_cfg_box()
     markers = assets.marker_ids()
     lbs = get_lbs_model("male", dev, body_model_path=body_model_path, marker_vids=markers)
     genop = GAMMAPrimitiveComboGenOP(testconfig={"gpu_index": dev.index or 0})
-    genop.build_model(seed=0)
-    vposer, _ = load_vposer(seed=0, device=dev)
+    genop.build_model(load_pretrained_model=bool(predictor_dir), predictor_dir=predictor_dir, regressor_dir=regressor_dir, seed=0)
+    vposer, _ = load_vposer(vposer_dir, seed=0, device=dev)
     scene = assets.make_box_scene(seed, n_boxes=0)
     sdf = {k: v.to(dev) for k, v in assets.rasterize_scene_sdf(scene, D=64, device=str(dev)).items()}
     venv = CrowdSceneVectorEnv(cfg, genop.model, lbs, vposer, sdf, n_scenes, dev, n_agents=n_agents, sequential=sequential)
@@ -123,8 +129,10 @@ def main(args=None):
         torch.cuda.set_device(dev)
     np.random.seed(args.seed + rank)
     torch.manual_seed(args.seed + rank)
+    from .main_ppo import resolve_asset_dirs
+    pdir, rdir, vdir = resolve_asset_dirs(args)
     w = build_crowd_world(dev, args.n_scenes, args.n_agents, sequential=not args.jacobi, seed=args.seed + rank,
-                          body_model_path=args.body_model_path, args=args)
+                          body_model_path=args.body_model_path, args=args, predictor_dir=pdir, regressor_dir=rdir, vposer_dir=vdir)
     if args.resume_path and os.path.exists(args.resume_path):
         ckpt = torch.load(args.resume_path, map_location=dev)
         w["policy"].load_state_dict(ckpt["model"])

@@ -61,7 +61,34 @@ def get_args(argv=None):
     parser.add_argument("--scene-sdf", type=str, default=None, help="data/room0_sdf.pkl; synthetic box scene if absent")
     parser.add_argument("--scene-poly", type=str, default=None, help="data/replica_room0_shapely.pkl")
     parser.add_argument("--sdf-res", type=int, default=256)
+    parser.add_argument("--motion-results-root", type=str, default="results/crowd_ppo",
+                        help="root of the reference's GAMMA checkpoints (<root>/MPVAE_samp20_2frame_rollout/checkpoints/epoch-400.ckp, "
+                             "<root>/MoshRegressor_v3_male/checkpoints/epoch-100.ckp, primitive_model.py:56-72); used when present")
+    parser.add_argument("--predictor-dir", type=str, default=None, help="overrides the predictor checkpoint directory")
+    parser.add_argument("--regressor-dir", type=str, default=None, help="overrides the regressor checkpoint directory")
+    parser.add_argument("--vposer-dir", type=str, default=None,
+                        help="VPoser v1.0 expr dir (<body-model-path>/vposer_v1_0 in the reference, main_ppo.py:259)")
+    parser.add_argument("--synthetic-assets", default=False, action="store_true",
+                        help="run on seeded synthetic motion-model / VPoser weights without looking for checkpoints")
     return parser.parse_args(argv)
+
+
+def resolve_asset_dirs(args):
+    """Checkpoint directories of the motion model and VPoser: explicit flags win; otherwise the reference's relative
+    locations are used when they exist. A directory that was NAMED but lacks its checkpoint raises (build_world)."""
+    from .runtime import motion_checkpoint_dirs
+    if getattr(args, "synthetic_assets", False):
+        return None, None, None
+    pdir, rdir = args.predictor_dir, args.regressor_dir
+    if not (pdir and rdir):
+        cp, cr = motion_checkpoint_dirs(args.motion_results_root)
+        explicit_root = args.motion_results_root != "results/crowd_ppo"
+        if explicit_root or (os.path.isdir(cp) and os.path.isdir(cr)):
+            pdir, rdir = pdir or cp, rdir or cr
+    vdir = args.vposer_dir
+    if vdir is None and args.body_model_path and os.path.isdir(os.path.join(args.body_model_path, "vposer_v1_0")):
+        vdir = os.path.join(args.body_model_path, "vposer_v1_0")
+    return pdir, rdir, vdir
 
 
 def shard(total, world, rank, what):
@@ -96,16 +123,20 @@ def main(args=None):
     n_train = shard(args.training_num, world, rank, "training-num")
     n_collect = shard(args.step_per_collect, world, rank, "step-per-collect")
     n_batch = shard(args.batch_size, world, rank, "batch-size")
+    pdir, rdir, vdir = resolve_asset_dirs(args)
     w = build_world(dev, n_train, seed=args.seed + rank, sdf_res=args.sdf_res, finetuning=args.finetune,
                     body_model_path=args.body_model_path, scene_sdf=scene_sdf, scene_rings=scene_rings, args=args,
-                    box_mode=getattr(args, "box_mode", False))
+                    box_mode=getattr(args, "box_mode", False), predictor_dir=pdir, regressor_dir=rdir, vposer_dir=vdir)
     policy, optim, train_collector = w["policy"], w["optim"], w["collector"]
-    if world > 1:                                  # identical initial weights on every rank
-        dist.broadcast(policy.flat_params, src=0)
     tw = build_world(dev, args.test_num, seed=args.seed + 1000 + rank, sdf_res=args.sdf_res, finetuning=args.finetune,
                      body_model_path=args.body_model_path, scene_sdf=None if getattr(args, "box_mode", False) else w["scene_sdf"],
                      scene_rings=None if getattr(args, "box_mode", False) else w["scene_rings"], with_policy=False,
-                     box_mode=getattr(args, "box_mode", False))
+                     box_mode=getattr(args, "box_mode", False), predictor_dir=pdir, regressor_dir=rdir, vposer_dir=vdir,
+                     capture_rollout=True)
+    # the reference's CrowdEnv writes a rollout pickle at every episode end (save_rollout=True by default,
+    # crowd_env_2f.py:35,305-309); here the evaluation envs do, into the same folder
+    tw["venv"].save_rollout = True
+    tw["venv"].rollout_dir = os.path.join(args.logdir, "eval_results") if args.logdir != "./log" else "./log/eval_results/"
     test_collector = Collector(policy, tw["venv"])
     w["venv"].seed(args.seed + rank)
     tw["venv"].seed(args.seed + rank)
@@ -136,6 +167,15 @@ def main(args=None):
         train_collector.reset()
         env_step = gradient_step = 0
         best = -float("inf")
+        policy.eval()                                  # tianshou's trainer evaluates once before the first epoch
+        tr0 = test_collector.collect_episodes(args.test_num)
+        policy.train()
+        best = tr0["rew"]
+        if rank == 0:
+            print(f"Epoch #0: test_reward: {tr0['rew']:.6f} +/- {tr0['rew_std']:.6f}")
+            if writer:
+                writer.add_scalar("test/reward", tr0["rew"], 0)
+                writer.add_scalar("test/length", tr0["len"], 0)
         for epoch in range(1, args.epoch + 1):
             epoch_step = 0
             while epoch_step < args.step_per_epoch:

@@ -187,18 +187,26 @@ class GAMMAPrimitiveComboGenOP:
         self.model = None
 
     def build_model(self, load_pretrained_model=False, predictor_dir=None, regressor_dir=None, seed=0):
+        """load_pretrained_model=True reads ``<predictor_dir>/epoch-400.ckp`` (else epoch-200.ckp) and
+        ``<regressor_dir>/epoch-100.ckp`` like the reference (:1118-1134) and RAISES when one is missing; False fills
+        seeded synthetic weights and says so loudly (offline tests / benchmarks: no licensed checkpoints exist here)."""
         self.model = GAMMAPrimitiveCombo()
-        loaded = False
-        if load_pretrained_model and predictor_dir and regressor_dir:
-            for name in ("epoch-400.ckp", "epoch-200.ckp"):
-                p = os.path.join(predictor_dir, name)
-                if os.path.exists(p):
-                    self.model.predictor.load_state_dict(torch.load(p, map_location="cpu")["model_state_dict"])
-                    r = os.path.join(regressor_dir, "epoch-100.ckp")
-                    self.model.regressor.load_state_dict(torch.load(r, map_location="cpu")["model_state_dict"])
-                    loaded = True
-                    break
-        if not loaded:
+        if load_pretrained_model:
+            if not (predictor_dir and regressor_dir):
+                raise FileNotFoundError("load_pretrained_model=True needs predictor_dir and regressor_dir")
+            cand = [os.path.join(predictor_dir, n) for n in ("epoch-400.ckp", "epoch-200.ckp")]
+            ppath = next((c for c in cand if os.path.exists(c)), None)
+            rpath = os.path.join(regressor_dir, "epoch-100.ckp")
+            if ppath is None or not os.path.exists(rpath):
+                raise FileNotFoundError(f"motion-model checkpoints not found: {cand[0]} (or epoch-200.ckp) and {rpath}")
+            self.model.predictor.load_state_dict(torch.load(ppath, map_location="cpu")["model_state_dict"])
+            self.model.regressor.load_state_dict(torch.load(rpath, map_location="cpu")["model_state_dict"])
+            self.weights = {"predictor": ppath, "regressor": rpath}
+        else:
+            import warnings
+            warnings.warn("GAMMAPrimitiveComboGenOP: using seeded SYNTHETIC motion-model weights (no pretrained GAMMA "
+                          "checkpoints were requested); pass predictor_dir / regressor_dir for the real model", stacklevel=2)
+            self.weights = "synthetic"
             assets.fill_params_(self.model.predictor, seed=seed + 11)
             assets.fill_params_(self.model.regressor, seed=seed + 12, w_gain=0.7)
             with torch.no_grad():   # keep the synthetic primitives human-scale (cm per frame, small rotations)
@@ -265,8 +273,15 @@ def load_vposer(expr_dir=None, vp_model="snapshot", seed=0, device="cuda"):
     snaps = sorted(glob.glob(os.path.join(expr_dir, "snapshots", "*.pt"))) if expr_dir else []
     if snaps:
         sd = torch.load(snaps[-1], map_location="cpu")
-        vp.load_state_dict({k: v for k, v in sd.items() if k.startswith("bodyprior_enc")}, strict=False)
+        missing = vp.load_state_dict({k: v for k, v in sd.items() if k.startswith("bodyprior_enc")}, strict=False)
+        need = [k for k in missing.missing_keys if "logvar" not in k and "num_batches_tracked" not in k]
+        if need:
+            raise KeyError(f"VPoser snapshot {snaps[-1]} lacks encoder tensors: {need}")
+    elif expr_dir:
+        raise FileNotFoundError(f"no VPoser snapshot under {os.path.join(expr_dir, 'snapshots')}")
     else:
+        import warnings
+        warnings.warn("load_vposer: using seeded SYNTHETIC VPoser encoder weights (no expr_dir given)", stacklevel=2)
         assets.fill_params_(vp, seed=seed + 31)
     vp.eval()
     return vp.to(device), None

@@ -25,6 +25,26 @@ class Batch(SimpleNamespace):
     """Minimal stand-in for tianshou.data.Batch (attribute bag)."""
 
 
+class PolicyOutput(Batch):
+    """Return value of GAMMAPPOPolicy.forward. ``dist`` is the action distribution of the reference
+    (``dist_fn(*logits)``, main_ppo.py:148-149: Independent(Normal(mu, sigma), 1)); it is built on first access so the
+    collect loop, which only needs ``act`` / ``logp``, does not pay for a torch distribution object per step."""
+
+    def __init__(self, dist_fn=None, **kw):
+        super().__init__(**kw)
+        self._dist_fn, self._dist = dist_fn, None
+
+    @property
+    def dist(self):
+        if self._dist is None:
+            if self._dist_fn is not None:
+                self._dist = self._dist_fn(*self.logits)
+            else:
+                from torch.distributions import Independent, Normal
+                self._dist = Independent(Normal(*self.logits), 1)
+        return self._dist
+
+
 class GAMMAPPOPolicy(nn.Module):
     def __init__(self, actor, critic, shared_net, optim, dist_fn=None, eps_clip=0.2, weight_kld=1.0, dual_clip=None,
                  value_clip=False, advantage_normalization=True, recompute_advantage=False, discount_factor=0.99,
@@ -200,10 +220,37 @@ class GAMMAPPOPolicy(nn.Module):
         z_mu = oa[:, :Z]
         z_logvar = oa[:, Z:].clamp(self.actor.min_logvar, self.actor.max_logvar)
         z_var = torch.exp(z_logvar)
-        return Batch(logits=(z_mu, z_var ** 0.5), act=act, state=None, z_mu=z_mu, z_var=z_var, z_logvar=z_logvar,
-                     logp=logp, value=val)
+        return PolicyOutput(self.dist_fn, logits=(z_mu, z_var ** 0.5), act=act, state=None, z_mu=z_mu, z_var=z_var,
+                            z_logvar=z_logvar, logp=logp, value=val)
 
     # ---- returns / advantages ----------------------------------------------------------------
+    def process_fn(self, batch, buffer=None, indices=None):
+        """ppo_policy.py:93-140 (process_fn + _compute_returns): critic values of obs / obs_next, GAE returns and
+        advantages, old log-probabilities. ``batch``: obs, obs_next (observation dicts), act, rew, terminated, truncated as
+        flat [N] tensors in tianshou's buffer order (env-major: env 0's T steps, then env 1's, ...); ``buffer`` only has to
+        say how many envs that is (``buffer.E`` / ``buffer.buffer_num``; default: one trajectory). The last stored step of
+        every env closes its segment like tianshou's unfinished_index(). Adds v_s, returns, adv, logp_old to ``batch``."""
+        N = batch.act.shape[0]
+        E = int(getattr(buffer, "E", getattr(buffer, "buffer_num", 1)) or 1)
+        T = N // E
+        to = lambda x: torch.as_tensor(x, device=self.dev)
+        with torch.no_grad():
+            chunks = [(s, min(N, s + self._batch)) for s in range(0, N, self._batch)]
+            if len(chunks) > 1 and chunks[-1][1] - chunks[-1][0] < self._batch:      # split(..., merge_last=True)
+                chunks[-2:] = [(chunks[-2][0], N)]
+            v_s = torch.cat([self.net_forward({k: to(v)[a:b] for k, v in batch.obs.items()}, False, True)[1] for a, b in chunks])
+            v_n = torch.cat([self.net_forward({k: to(v)[a:b] for k, v in batch.obs_next.items()}, False, True)[1] for a, b in chunks])
+            tm = lambda x: to(x).reshape(E, T).t().contiguous()                          # env-major flat -> [T,E]
+            term = tm(batch.terminated).to(torch.uint8)
+            end = (term.bool() | tm(batch.truncated).bool()).to(torch.uint8)
+            end[-1] = 1
+            ret, adv = self.compute_returns(tm(v_s), tm(v_n), tm(batch.rew).to(torch.float32), term, end)
+            fl = lambda x: x.t().reshape(N).contiguous()
+            batch.v_s, batch.returns, batch.adv = v_s, fl(ret), fl(adv)
+            batch.act = to(batch.act).to(torch.float32)
+            batch.logp_old = self(Batch(obs={k: to(v) for k, v in batch.obs.items()})).dist.log_prob(batch.act)
+        return batch
+
     def compute_returns(self, v_s, v_next, rew, terminated, end_flag):
         """_compute_returns (:105-140) + tianshou compute_episodic_return on [T,E] time-major tensors."""
         T, E = rew.shape

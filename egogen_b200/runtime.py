@@ -42,23 +42,39 @@ def build_policy(cfg, device, args=None, process_group=None):
     return policy, optim
 
 
+def motion_checkpoint_dirs(results_root):
+    """Where the reference's ConfigCreator puts the GAMMA checkpoints (primitive_model.py:9-37,56-72):
+    <root>/MPVAE_samp20_2frame_rollout/checkpoints and <root>/MoshRegressor_v3_male/checkpoints."""
+    import os
+    return (os.path.join(results_root, "MPVAE_samp20_2frame_rollout", "checkpoints"),
+            os.path.join(results_root, "MoshRegressor_v3_male", "checkpoints"))
+
+
 def build_world(device, n_envs: int, seed: int = 0, sdf_res: int = 256, n_boxes: int = 1, finetuning: bool = False,
                 body_model_path=None, scene_sdf=None, scene_rings=None, args=None, with_policy: bool = True,
-                host_boundary: bool = False, process_group=None, cfg=None, box_mode: bool = False):
+                host_boundary: bool = False, process_group=None, cfg=None, box_mode: bool = False,
+                predictor_dir=None, regressor_dir=None, vposer_dir=None, sampler=None, capture_rollout: bool = False):
+    """predictor_dir / regressor_dir / vposer_dir: the pretrained GAMMA predictor, body regressor and VPoser v1.0 the
+    reference always loads (primitive_model.py:70, main_ppo.py:259); a missing file raises. Left out, seeded synthetic
+    weights are used (with a warning). sampler: any object with next_body(n) -> {world_params, goals, betas} (e.g. built
+    from scene_sampler.CrowdMotionSampler dicts); default BoxSceneSampler over the scene's own extent."""
     dev = torch.device(device)
     cfg = cfg or (default_cfg_box() if box_mode else default_cfg())
     scene = None
     markers = assets.marker_ids()
     lbs = get_lbs_model("male", dev, body_model_path=body_model_path, marker_vids=markers)
     genop = GAMMAPrimitiveComboGenOP(testconfig={"gpu_index": dev.index or 0})
-    genop.build_model(seed=0)
-    vposer, _ = load_vposer(seed=0, device=dev)
+    if bool(predictor_dir) != bool(regressor_dir):
+        raise ValueError("predictor_dir and regressor_dir must be given together")
+    genop.build_model(load_pretrained_model=bool(predictor_dir), predictor_dir=predictor_dir, regressor_dir=regressor_dir, seed=0)
+    vposer, _ = load_vposer(vposer_dir, seed=0, device=dev)
     if scene_sdf is None:
         scene = assets.make_box_scene(seed, n_boxes=n_boxes)
         scene_sdf = assets.rasterize_scene_sdf(scene, D=sdf_res, device=str(dev))
         scene_rings = assets.scene_polygon(scene)
     scene_sdf = {k: torch.as_tensor(v, dtype=torch.float32).to(dev) for k, v in scene_sdf.items()}
-    sampler = BoxSceneSampler(scene_sdf, lbs, dev, seed=seed)
+    if sampler is None:
+        sampler = BoxSceneSampler(scene_sdf, lbs, dev, seed=seed)
     sampler.scene_rings = scene_rings
     tris = None
     if box_mode:
@@ -66,7 +82,7 @@ def build_world(device, n_envs: int, seed: int = 0, sdf_res: int = 256, n_boxes:
             raise ValueError("box_mode needs a synthetic box scene (or pass navmesh triangles through CrowdVectorEnv)")
         tris = assets.scene_navmesh_triangles(scene)
     venv = CrowdVectorEnv(cfg, genop.model, lbs, vposer, scene_sdf, scene_rings, sampler, n_envs, dev,
-                          finetuning=finetuning, box_mode=box_mode, navmesh_tris=tris)
+                          finetuning=finetuning, box_mode=box_mode, navmesh_tris=tris, capture_rollout=capture_rollout)
     out = dict(cfg=cfg, lbs=lbs, genop=genop, vposer=vposer, scene_sdf=scene_sdf, scene_rings=scene_rings,
                sampler=sampler, venv=venv)
     if with_policy:

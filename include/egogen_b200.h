@@ -275,6 +275,11 @@ int eg_env_reset(EgEnv* h, const EgEnvBuffers* b, const int32_t* env_ids, int n,
  * host. accept [E] = 1 where a slot was restarted. */
 int eg_env_reset_masked(EgEnv* h, const EgEnvBuffers* b, const uint8_t* mask, int E, const float* world_params,
                         const float* goals, const float* betas_cand, int32_t* accept, void* stream);
+/* CrowdEnv._calc_egosensing (crowd_env_2f.py:524-613) on given joints: joints_local [n,2,127,3] body-frame SMPL-X joints of
+ * the 2-frame seed, R0 [n,3,3] / T0 [n,3] the canonical frame; 2 x 32 rays in float64 against the polygon boundary
+ * segments (and the optional per-item hole rectangles [n,n_holes,4]); ego_out [n,2,32] in [-1,1]. */
+int eg_egosensing(const float* joints_local, const float* R0, const float* T0, int n, const double* segments_dev,
+                  int n_segments, double ray_len, const float* holes_dev, int n_holes, float* ego_out, void* stream);
 /* Restart from a POOL of pre-computed initial states (rows of `pool`, the state fields of EgEnvBuffers as written by
  * eg_env_reset for accepted candidates): slot e with mask[e] != 0 takes pool row (cursor + rank(e)) mod pool_rows, rank(e) =
  * number of set mask entries below e, and the device cursor advances by the number of set entries - only finished

@@ -426,3 +426,114 @@ def test_masked_reset_edge_cases(dev, world):
     rc = _lib.lib().eg_env_reset_masked(venv._h, C.byref(venv._cbuf), None, E, _lib.ptr(wp), _lib.ptr(gl), _lib.ptr(be),
                                         _lib.ptr(acc32), _lib.stream_ptr(dev))
     assert rc < 0
+
+
+def test_product_sampler_matches_reference_golden(dev, world, golden_dir):
+    """The PRODUCT start-body sampler (egogen_b200/scene_sampler.py::CrowdMotionSampler.gen_init_bodies, SMPL-X joints from
+    the CUDA LBS operator) against the outputs of the reference's own CrowdMotion.gen_init_body
+    (exp_GAMMAPrimitive/utils/environments.py:1041-1131, tests/golden/gen_sampler_golden.py), batched over the three golden
+    cases, plus the sampler-dict contract (batched_to_dicts -> sampler_dicts_to_candidates -> a reset the env accepts)."""
+    import os
+    from scipy.spatial.transform import Rotation
+    from egogen_b200.scene_sampler import CrowdMotionSampler, batched_to_dicts, sampler_dicts_to_candidates
+    g = np.load(os.path.join(golden_dir, "sampler_golden.npz"))
+    seed = np.load(os.path.join(golden_dir, "locomotion_seed_00343.npz"))
+    smp = CrowdMotionSampler(world["lbs"], dev, {"poses": seed["poses"], "trans": seed["trans"], "betas": seed["betas"][:10]}, seed=0)
+    sf = g["start_frame"].astype(int)
+    ms = (np.stack([seed["betas"][:10]] * 3), np.stack([seed["poses"][f:f + 2, 3:66] for f in sf]),
+          np.stack([seed["poses"][f:f + 2, :3] for f in sf]), np.stack([seed["trans"][f:f + 2] for f in sf]))
+    out = smp.gen_init_bodies(g["start"], g["target"], motion_seed=ms, yaw=g["yaw"].astype(np.float32))
+    assert np.abs(out["transl"].cpu().numpy() - g["transl"]).max() < 5e-5
+    assert np.abs(out["wpath"].cpu().numpy() - g["wpath"]).max() < 5e-5
+    assert np.array_equal(out["body_pose"].cpu().numpy(), g["body_pose"]) and np.array_equal(out["betas"].cpu().numpy(), g["betas"])
+    R = Rotation.from_rotvec(out["global_orient"].cpu().numpy().reshape(-1, 3).astype(np.float64)).as_matrix()
+    R_ref = Rotation.from_rotvec(g["global_orient"].reshape(-1, 3).astype(np.float64)).as_matrix()
+    assert np.abs(R - R_ref).max() < 5e-5                      # same rotations (the axis-angle branch may differ at pi)
+    # random draws: frames come from the seed recording, bodies stand on the floor above their start point
+    rnd = smp.gen_init_bodies(g["start"], g["target"])
+    j = smp._joints(rnd["transl"], rnd["global_orient"], rnd["body_pose"], rnd["betas"])
+    assert float(j[:, 0, :, 2].amin(dim=1).abs().max()) < 1e-4
+    assert float((j[:, 0, 0, :2].cpu() - torch.as_tensor(g["start"][:, :2])).abs().max()) < 1e-4
+    # dict contract: reference-format dicts -> reset candidates -> accepted by the env on an empty floor
+    dicts = batched_to_dicts(out)
+    assert set(dicts[0]) == {"gender", "motion_seed", "betas", "wpath", "scene_path", "navmesh", "navmesh_path", "floor_height"}
+    wp, goals, betas = sampler_dicts_to_candidates(dicts, dev)
+    assert wp.shape == (3, 2, 93) and torch.allclose(goals.cpu(), torch.as_tensor(g["wpath"][:, 1]), atol=5e-5)
+    one = smp.next_body((g["start"][0], g["target"][0]), num_agents=1)
+    assert one["motion_seed"]["transl"].shape == (2, 3) and one["wpath"].shape == (2, 3)
+
+
+def test_env_step_at_bench_configuration(dev, world, smplx_model):
+    """BASELINE config 2 shape (crowd_env_2f.py:78-317 at 256 parallel envs, 256^3 SDF, full 10 475-vertex mesh): reset and
+    two vector steps of the tensor-core decode / regressor / fused LBS + SDF path against the CPU oracle, re-seeded from
+    the GPU state before each step (operator-level comparison on identical inputs)."""
+    from egogen_b200.crowd_env import BoxSceneSampler, CrowdVectorEnv, default_cfg
+    from oracle.env import CrowdEnvOracle
+    from oracle.smplx_lbs import SMPLXParserOracle
+    E = 256
+    markers = assets.marker_ids()
+    scene = assets.make_box_scene(7, n_boxes=2)
+    sdf_cpu = assets.rasterize_scene_sdf(scene, D=256)
+    sdf = {k: v.to(dev) for k, v in sdf_cpu.items()}
+    rings = assets.scene_polygon(scene)
+    venv = CrowdVectorEnv(default_cfg(), world["genop"].model, world["lbs"], world["vposer"], sdf, rings,
+                          BoxSceneSampler(sdf, world["lbs"], dev, seed=5), E, dev, debug_terms=True, capture_rollout=True)
+    orc = CrowdEnvOracle(SMPLXParserOracle(smplx_model, marker=markers), world["combo"].eval(), world["vp_o"].eval(), sdf_cpu,
+                         assets.rings_to_segments(rings), markers, assets.feet_marker_idx(), assets.feet_vids())
+    venv.reset()
+    g = torch.Generator().manual_seed(41)
+    n_term = 0
+    for it in range(2):
+        _sync_oracle(orc, venv)
+        z = torch.randn(E, 128, generator=g)
+        obs, rew, term, _, _ = venv.step(z.to(dev))
+        ref = orc.step(z)
+        b = venv.buf
+        assert torch.allclose(b["out_markers"].cpu(), ref["marker_b"], atol=1e-4)
+        assert torch.allclose(b["reward_terms"].cpu(), ref["terms"], atol=2e-4), (b["reward_terms"].cpu() - ref["terms"]).abs().max(0)
+        assert torch.allclose(rew.cpu(), ref["reward"], atol=5e-4)
+        assert torch.equal(term.cpu().bool(), ref["terminated"])
+        assert torch.allclose(obs["state"].cpu(), ref["state"], atol=2e-4)
+        assert torch.allclose(obs["egosensing"].cpu(), ref["egosensing"], atol=2e-3)
+        assert torch.allclose(obs["dist"].cpu()[:, 0], ref["dist"], atol=1e-4)
+        n_term += int(term.sum())
+    # the penetration term must have been exercised: some bodies touch the boxes / floor, most do not
+    pen = venv.buf["reward_terms"][:, 6].cpu()
+    assert int((pen < pen.max()).sum()) > 0 and int((pen == pen.max()).sum()) > 0
+    venv.close()
+
+
+def test_egosensing_operator_tight(dev):
+    """eg_egosensing (the kernel the step / reset paths launch) on GIVEN joints against the oracle's restatement of
+    CrowdEnv._calc_egosensing (crowd_env_2f.py:524-613): both take the same float32 joints and run the rays in float64, so
+    the ray distances agree to 1e-5 of the [-1,1] output (7e-5 m... in fact ~1e-7) - EXCEPT rays that graze a polygon
+    corner, where which segment is hit first flips with the last bit of the float32 world transform. Those are identified
+    from the oracle itself (its answer moves by more than 1e-5 when the joints move by 2e-6) and must stay below 1 %."""
+    from egogen_b200.crowd_env import calc_egosensing
+    from oracle.env import egosensing
+    scene = assets.make_box_scene(3, n_boxes=3)
+    rings = assets.scene_polygon(scene)
+    segs = assets.rings_to_segments(rings)
+    n = 200
+    g = torch.Generator().manual_seed(12)
+    j = torch.randn(n, 2, 127, 3, generator=g) * 0.05
+    j[:, :, 23, 0] += 0.03; j[:, :, 24, 0] -= 0.03               # eyes apart, eyeballs 56 / 57 ahead of them
+    j[:, :, 56] = j[:, :, 24] + torch.tensor([0.0, 0.0, 0.1]); j[:, :, 57] = j[:, :, 23] + torch.tensor([0.0, 0.0, 0.1])
+    ang = torch.rand(n, generator=g) * 6.2831853
+    R0 = torch.zeros(n, 3, 3)
+    R0[:, 0, 0] = ang.cos(); R0[:, 0, 2] = ang.sin(); R0[:, 1, 0] = ang.sin(); R0[:, 1, 2] = -ang.cos(); R0[:, 2, 1] = 1
+    T0 = torch.cat([(torch.rand(n, 2, generator=g) * 2 - 1) * 3.5, torch.full((n, 1), 1.5)], 1)
+    holes = torch.cat([T0[:, None, :2].roll(1, 0) - 0.3, T0[:, None, :2].roll(1, 0) + 0.3], dim=2)   # one rectangle per item
+
+    def world(jl):
+        return torch.einsum("nij,ntpj->ntpi", R0, jl) + T0[:, None, None]
+    for hl in (None, holes):
+        got = calc_egosensing(j.to(dev), R0.to(dev), T0.to(dev), rings, 7.0, None if hl is None else hl.to(dev)).cpu()
+        ref = egosensing(world(j), segs, 7.0, hl)
+        ref_p = egosensing(world(j) + 2e-6, segs, 7.0, hl)
+        ref_m = egosensing(world(j) - 2e-6, segs, 7.0, hl)
+        grazing = ((ref_p - ref).abs() > 1e-5) | ((ref_m - ref).abs() > 1e-5)
+        assert grazing.float().mean().item() < 0.01, grazing.float().mean()
+        err = (got - ref).abs()
+        assert err[~grazing].max().item() <= 1e-5, err[~grazing].max()
+        assert int((ref > -1).sum()) > 0 and int((ref < 1).sum()) > 0        # some eyes off the polygon, some rays hit

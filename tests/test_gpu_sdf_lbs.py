@@ -191,6 +191,32 @@ def test_fused_counts_at_bench_size(dev, parser):
     assert bool(((counts - c2).abs() <= near).all()), (counts - c2).abs().max()
     assert int((counts > 0).sum()) > E * T // 20, "bodies intersecting the floor / boxes must be present"
     assert int((counts == 0).sum()) > 0
+    # ... and an INDEPENDENT reference for the vertices: the fp32 SIMT mainloop (no tensor cores, no fp16 operands). The
+    # tcgen05 vertices deviate from it by <= 5e-5 m (tolerance 1e-4 relative, test_forward_matches_oracle) and the SDF is
+    # 1-Lipschitz in metres after un-scaling, so only vertices within 1e-4 of the zero level may flip.
+    bm.set_mainloop(False)
+    try:
+        verts32 = bm.forward(xb.to(dev), brow.to(dev), want_verts=True)[0]
+    finally:
+        bm.set_mainloop(True)
+    assert (verts32 - verts).abs().max().item() <= 1e-4
+    vw32 = torch.einsum("bij,btpj->btpi", R0.to(dev), verts32.view(E, T, -1, 3)) + T0.to(dev)[:, None]
+    sv32 = calc_sdf(vw32.reshape(E * T, -1, 3), sd)
+    c32 = penetration_count(sv32, skip.to(dev))
+    near32 = (sv32.abs() < 1e-4 * float(sd["scale"].reshape(-1)[0].abs().clamp_min(1.0))).sum(dim=1)
+    assert bool(((counts - c32).abs() <= near32).all()), ((counts - c32).abs() - near32).max()
+    # ... and the CPU oracle (dense LBS restatement + the reference-pinned calc_sdf) on the first 3 envs (60 bodies)
+    from oracle import sdf as osdf
+    from oracle.smplx_lbs import SMPLXParserOracle
+    nb = 3 * T
+    orc = SMPLXParserOracle(assets.make_surrogate_smplx(seed=0), marker=assets.marker_ids())
+    vo = orc.forward_smplx(brow[:nb], "male", xb[:nb], "raw").vertices
+    vwo = torch.einsum("bij,btpj->btpi", R0[:3], vo.view(3, T, -1, 3)) + T0[:3, None]
+    svo = osdf.calc_sdf(vwo.reshape(nb, -1, 3), {k: v.cpu() for k, v in sd.items() if torch.is_tensor(v)})
+    keep = (skip == 0)
+    co = ((svo < 0) & keep[None]).sum(dim=1)
+    nearo = (svo.abs() < 1e-4 * float(sd["scale"].reshape(-1)[0].abs().clamp_min(1.0))).sum(dim=1)
+    assert bool(((counts[:nb].cpu() - co).abs() <= nearo).all()), ((counts[:nb].cpu() - co).abs() - nearo).max()
 
 
 def test_markers_backward_matches_autograd(dev, parser, smplx_model):
