@@ -328,6 +328,45 @@ bn_eval_kernel(const float* __restrict__ x, int ldx, int M, int D, const float* 
   }
 }
 
+__global__ void __launch_bounds__(256)
+pad_rows_kernel(const float* __restrict__ src, int ld_src, int rows, int cols, float* __restrict__ dst, int ld_dst) {
+  const int64_t n = (int64_t)rows * ld_dst;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld_dst), c = (int)(i % ld_dst);
+    dst[i] = c < cols ? src[(int64_t)r * ld_src + c] : 0.0f;
+  }
+}
+
+int launch_pad_rows(cudaStream_t st, const float* src, int ld_src, int rows, int cols, float* dst, int ld_dst) {
+  const int64_t n = (int64_t)rows * ld_dst;
+  if (n <= 0) return EG_OK;
+  EG_LAUNCH(pad_rows_kernel, (int)std::min<int64_t>((n + 255) / 256, kNumSMs * 8), 256, 0, st, src, ld_src, rows, cols, dst, ld_dst);
+  return EG_OK;
+}
+
+// tensor-core prologue of sample_prior: the two history frames into Y[B,20,D] AND a 16-byte-pitched copy Yp[B,2,DP], and
+// the step-invariant GRUCell input row cin[b] = [hx (filled later) | z | y_0 | 0-pad] with pitch KP
+__global__ void prologue_pack_kernel(const float* __restrict__ X, int ldx_env, int ldx_frame, const float* __restrict__ z,
+                                     int B, int D, int DP, int H, int Z, int KP, float* __restrict__ Y, float* __restrict__ Yp,
+                                     float* __restrict__ cin) {
+  const int per = 2 * DP + (KP - H);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * per) return;
+  const int b = i / per, r = i % per;
+  if (r < 2 * DP) {
+    const int t = r / DP, d = r % DP;
+    const float v = d < D ? X[(int64_t)b * ldx_env + t * ldx_frame + d] : 0.0f;
+    Yp[((int64_t)b * 2 + t) * DP + d] = v;
+    if (d < D) Y[((int64_t)b * 20 + t) * D + d] = v;
+  } else {
+    const int c = H + (r - 2 * DP);                        // column of cin
+    float v = 0.0f;
+    if (c < H + Z) v = z[(int64_t)b * Z + (c - H)];
+    else if (c < H + Z + D) v = X[(int64_t)b * ldx_env + ldx_frame + (c - H - Z)];
+    cin[(int64_t)b * KP + c] = v;
+  }
+}
+
 // copy the two history frames' markers into Y[B,20,201]
 __global__ void copy_history_kernel(const float* __restrict__ X, int ldx_env, int ldx_frame, int B, int D,
                                     float* __restrict__ Y) {
@@ -954,6 +993,10 @@ struct EgMotion {
   RegW rw{};
   int fused = 1;
   mtc::MotionTc* tc = nullptr;            // tcgen05 decode / regressor (motion_tc.cu); nullptr or unavailable -> SIMT fused kernels
+  // 16-byte-pitched operands of the decode prologue (D = 201 and H + Z + D = 585 floats are not): x_enc W_ih [3H][DP],
+  // d_rnn W_ih [3H][KP], history frames [B,2,DP], GRUCell input rows [B][KP]
+  int DP = 0, KP = 0;
+  float *wx_pad = nullptr, *wd_pad = nullptr, *yp_pad = nullptr, *cin = nullptr;
 };
 
 namespace {
@@ -989,6 +1032,9 @@ int motion_ws(EgMotion* h, int B) {
   EG_CUDA_CHECK(cudaMalloc((void**)&h->hx2, 2 * b * d.h_dim * 4));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->yp2, 2 * b * (size_t)((d.in_dim + 3) & ~3) * 4));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->dcnt, ((b + dws::RB - 1) / dws::RB) * sizeof(unsigned)));
+  cudaFree(h->yp_pad); cudaFree(h->cin); h->yp_pad = h->cin = nullptr;
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->yp_pad, b * 2 * h->DP * 4));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->cin, b * h->KP * 4));
   h->cap_B = B;
   return EG_OK;
 }
@@ -1036,6 +1082,12 @@ static int motion_build_transposed(EgMotion* h, cudaStream_t st) {
   h->rw.WoT = tr(wb[nb * 4], Hr, BD, Hr, BD4);
   h->rw.b_out = wb[nb * 4 + 1];
   EG_CUDA_CHECK(cudaGetLastError());
+  // padded copies for the tensor-core prologue
+  if (!h->wx_pad) EG_CUDA_CHECK(cudaMalloc((void**)&h->wx_pad, (size_t)H3 * h->DP * sizeof(float)));
+  if (!h->wd_pad) EG_CUDA_CHECK(cudaMalloc((void**)&h->wd_pad, (size_t)H3 * h->KP * sizeof(float)));
+  int rc = launch_pad_rows(st, w[P_XENC_WIH], D, H3, D, h->wx_pad, h->DP);
+  if (rc) return rc;
+  if ((rc = launch_pad_rows(st, w[P_DRNN_WIH], Kin, H3, Kin, h->wd_pad, h->KP))) return rc;
   return EG_OK;
 }
 
@@ -1059,6 +1111,8 @@ extern "C" int eg_motion_create(const EgMotionDims* dims, const void* const* wei
   for (int i = 0; i < n_weights; ++i) EG_REQUIRE(weights_host[i] != nullptr, "null weight pointer");
   EgMotion* h = new EgMotion();
   h->device = device; h->d = *dims;
+  h->DP = (dims->in_dim + 3) & ~3;
+  h->KP = (dims->h_dim + dims->z_dim + dims->in_dim + 3) & ~3;
   h->w.assign((const float* const*)weights_host, (const float* const*)weights_host + n_weights);
   EG_CUDA_CHECK(cudaSetDevice(device));
   h->fused = (dims->reg_h == 128 && dims->mlp_dim <= 3 * dims->h_dim) ? 1 : 0;   // fused kernels' static assumptions
@@ -1097,7 +1151,8 @@ extern "C" void eg_motion_destroy(EgMotion* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->wt);
-  float* bufs[] = {h->gi, h->gh, h->h, h->hx, h->c, h->t1, h->t2, h->rh, h->rbase, h->rt, h->xbc, h->hx2, h->yp2};
+  float* bufs[] = {h->gi, h->gh, h->h, h->hx, h->c, h->t1, h->t2, h->rh, h->rbase, h->rt, h->xbc, h->hx2, h->yp2,
+                   h->wx_pad, h->wd_pad, h->yp_pad, h->cin};
   for (auto p : bufs) cudaFree(p);
   cudaFree(h->dcnt);
   mtc::destroy(h->tc);
@@ -1118,9 +1173,29 @@ extern "C" int eg_motion_sample_prior(EgMotion* hd, const float* X, int ldx_env,
   const int D = d.in_dim, H = d.h_dim, Z = d.z_dim, Hm = d.mlp_dim, H3 = 3 * H;
   const float* const* w = hd->w.data();
 #define EG_TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  const int ldY = 20 * D;
+  const int Kin = H + Z + D;
+  const bool tc_path = hd->fused && mtc::decode_available(hd->tc) && hd->wx_pad != nullptr;
+  if (tc_path) {
+    // every product of the prologue on the tensor-core dense layer: operands re-pitched to 16 bytes, and the three partial
+    // products of the first GRUCell input term become ONE layer over the concatenated row [hx | z | y_0] (the reference's
+    // torch.cat, models_GAMMA_primitive.py:93-94)
+    const int DP = hd->DP, KP = hd->KP;
+    const int per = 2 * DP + (KP - H);
+    EG_LAUNCH(prologue_pack_kernel, (B * per + 255) / 256, 256, 0, st, X, ldx_env, ldx_frame, z, B, D, DP, H, Z, KP, Y, hd->yp_pad, hd->cin);
+    EG_TRY(linear(st, hd->yp_pad, 2 * DP, B, hd->wx_pad, DP, w[P_XENC_BIH], D, H3, hd->gi, H3));
+    EG_TRY(launch_gru_gate(st, hd->gi, nullptr, w[P_XENC_BHH], nullptr, hd->h, B, H, H));
+    EG_TRY(linear(st, hd->yp_pad + DP, 2 * DP, B, hd->wx_pad, DP, w[P_XENC_BIH], D, H3, hd->gi, H3));
+    EG_TRY(linear(st, hd->h, H, B, w[P_XENC_WHH], H, w[P_XENC_BHH], H, H3, hd->gh, H3));
+    EG_TRY(launch_gru_gate(st, hd->gi, hd->gh, nullptr, hd->h, hd->cin, B, H, KP));            // hx -> cin[:, :H]
+    EG_TRY(linear(st, hd->cin, KP, B, w[P_DRNN_W0], H, w[P_DRNN_B0], H, Hm, hd->t1, Hm, ACT_TANH));
+    EG_TRY(linear(st, hd->t1, Hm, B, w[P_DRNN_W1], Hm, w[P_DRNN_B1], Hm, H, hd->t2, H, ACT_TANH));
+    EG_TRY(linear(st, hd->t2, H, B, w[P_DRNN_W2], H, w[P_DRNN_B2], H, H, hd->h, H, ACT_TANH));
+    EG_TRY(linear(st, hd->cin, KP, B, hd->wd_pad, KP, w[P_DRNN_BIH], Kin, H3, hd->c, H3));      // gi_1 = b_ih + [hx, z, y_0] W_ih^T
+    EG_TRY(mtc::decode(hd->tc, hd->c, hd->h, Y, B, st));
+  } else {
   EG_LAUNCH(copy_history_kernel, (B * 2 * D + 255) / 256, 256, 0, st, X, ldx_env, ldx_frame, B, D, Y);
   // ---- x_enc GRU over the 2 history frames (h0 = 0) ----
-  const int ldY = 20 * D;
   EG_TRY(linear(st, Y, ldY, B, w[P_XENC_WIH], D, w[P_XENC_BIH], D, H3, hd->gi, H3));
   EG_TRY(launch_gru_gate(st, hd->gi, nullptr, w[P_XENC_BHH], nullptr, hd->h, B, H, H));
   EG_TRY(linear(st, Y + D, ldY, B, w[P_XENC_WIH], D, w[P_XENC_BIH], D, H3, hd->gi, H3));
@@ -1131,7 +1206,6 @@ extern "C" int eg_motion_sample_prior(EgMotion* hd, const float* X, int ldx_env,
   EG_TRY(linear(st, hd->t1, Hm, B, w[P_DRNN_W1], Hm, w[P_DRNN_B1], Hm, H, hd->t2, H, ACT_TANH));
   EG_TRY(linear(st, hd->t2, H, B, w[P_DRNN_W2], H, w[P_DRNN_B2], H, H, hd->h, H, ACT_TANH));
   // ---- step-invariant part of the GRUCell input: [hx, z] W_ih[:, :H+Z]^T + b_ih ----
-  const int Kin = H + Z + D;
   EG_TRY(linear(st, hd->hx, H, B, w[P_DRNN_WIH], Kin, w[P_DRNN_BIH], H, H3, hd->c, H3));
   EG_TRY(linear(st, z, Z, B, w[P_DRNN_WIH] + H, Kin, nullptr, Z, H3, hd->c, H3, ACT_NONE, 0.f, nullptr, 0, 1));
   if (hd->decode_ws < 0) {
@@ -1162,6 +1236,7 @@ extern "C" int eg_motion_sample_prior(EgMotion* hd, const float* X, int ldx_env,
     EG_TRY(linear(st, hd->t1, Hm, B, w[P_DMLP_W1], Hm, w[P_DMLP_B1], Hm, H, hd->t2, H, ACT_TANH));
     EG_TRY(linear(st, hd->t2, H, B, w[P_DOUT_W], H, w[P_DOUT_B], H, D, yo, ldY, ACT_NONE, 0.f, yp, ldY));
   }
+  }   // !tc_path
   // ---- regressor over all B*20 marker frames (frames 0,1 are computed and discarded) ----
   const int M = B * 20, Hr = d.reg_h, BD = d.body_dim, Kr = D + BD + 10;
   if (hd->fused && mtc::regress_available(hd->tc)) {

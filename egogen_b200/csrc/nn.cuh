@@ -46,4 +46,7 @@ int launch_gru_gate(cudaStream_t st, const float* gi, const float* gh, const flo
                     float* r_save = nullptr, float* z_save = nullptr, float* n_save = nullptr,
                     float* ghn_save = nullptr);
 
+// dst[r, 0..ld_dst) = src[r, 0..cols) zero-padded: re-pitches rows to a multiple of 16 bytes so TMA can stage them
+int launch_pad_rows(cudaStream_t st, const float* src, int ld_src, int rows, int cols, float* dst, int ld_dst);
+
 }  // namespace eg

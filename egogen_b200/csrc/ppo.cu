@@ -149,16 +149,6 @@ gemv_rows_kernel(const float* __restrict__ x, int ldx, int M, int K, const float
   if (lane == 0) y[(int64_t)m * ldy] = s + (b ? __ldg(b) : 0.0f);
 }
 
-// dst[r, 0..ld_dst) = src[r, 0..cols) zero-padded: 16-byte aligned row pitch for the TMA operands of the dense layers
-__global__ void __launch_bounds__(256)
-pad_rows_kernel(const float* __restrict__ src, int ld_src, int rows, int cols, float* __restrict__ dst, int ld_dst) {
-  const int64_t n = (int64_t)rows * ld_dst;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / ld_dst), c = (int)(i % ld_dst);
-    dst[i] = c < cols ? src[(int64_t)r * ld_src + c] : 0.0f;
-  }
-}
-
 // GRU cell backward given dh (grad of the cell output); writes dgi, dgh [M,3H] and dh_prev = dh * z
 __global__ void __launch_bounds__(256)
 gru_bwd_kernel(const float* __restrict__ dh, int ld_dh, const float* __restrict__ r, const float* __restrict__ z,
@@ -513,8 +503,8 @@ extern "C" int eg_policy_forward(EgPolicy* h, const float* state, const float* e
   const int H = d.h_dim, D = L.hx_dim;
   // x_enc: the 402-float frames and W_ih rows are re-pitched to 404 floats (16 B) so the products are TMA-eligible
   const int IP = h->in_pad;
-  EG_LAUNCH(pad_rows_kernel, ew_grid((int64_t)B * 2 * IP), 256, 0, st, state, d.in_dim, B * 2, d.in_dim, h->xpad, IP);
-  EG_LAUNCH(pad_rows_kernel, ew_grid((int64_t)3 * H * IP), 256, 0, st, h->P + L.x_wih, d.in_dim, 3 * H, d.in_dim, h->wih_pad, IP);
+  EG_TRY(launch_pad_rows(st, state, d.in_dim, B * 2, d.in_dim, h->xpad, IP));
+  EG_TRY(launch_pad_rows(st, h->P + L.x_wih, d.in_dim, 3 * H, d.in_dim, h->wih_pad, IP));
   EG_TRY(gru2_forward(h, st, h->xpad, 2 * IP, IP, d.in_dim, B, h->wih_pad, IP, L.x_whh, L.x_bih, L.x_bhh, h->xr,
                       h->xz, h->xn, h->xg, h->xh1, h->hx, D));
   EG_TRY(gru2_forward(h, st, ego, 2 * d.ego_dim, d.ego_dim, d.ego_dim, B, h->P + L.e_wih, d.ego_dim, L.e_whh, L.e_bih, L.e_bhh, h->er,
