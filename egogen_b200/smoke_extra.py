@@ -21,8 +21,9 @@ def run(dev):
     torch.cuda.synchronize(dev)
     assert torch.isfinite(rew).all() and torch.isfinite(obs["state"]).all()
     print("smoke env step ok: reward", [round(float(r), 4) for r in rew])
-    # one 64-env step (weight-stationary decode kernel, split-k tensor-core layers) followed by a device-side restart;
-    # returns the motion model's decode of a fixed input so the caller (the smoke test) can check it against its oracle
+    # one 64-env step (tcgen05 decode cluster + regressor, tensor-core dense layers, fused LBS + SDF) followed by a device-side
+    # restart from the pool; returns the motion model's outputs for a fixed input so the caller (the smoke test) can check
+    # them against its oracle
     venv64 = CrowdVectorEnv(default_cfg(), genop.model, lbs, vposer, sdf, assets.scene_polygon(scene),
                             BoxSceneSampler(sdf, lbs, dev, seed=1), 64, dev)
     venv64.reset()
@@ -30,10 +31,10 @@ def run(dev):
     X = torch.randn(2, 64, 201, generator=g) * 0.3
     z = torch.randn(64, 128, generator=g)
     betas = torch.zeros(18, 64, 10)
-    Y, _ = genop.model.sample_prior(X.to(dev), betas.to(dev), z.to(dev))
+    Y, Yb = genop.model.sample_prior(X.to(dev), betas.to(dev), z.to(dev))
     _, rew, term, _, _ = venv64.step(z.to(dev))
     venv64.reset_masked(term)
     torch.cuda.synchronize(dev)
     assert torch.isfinite(rew).all()
     print(f"smoke 64-env step ok: restarted {int(term.sum())} envs")
-    return dict(genop=genop, X=X, z=z, betas=betas, Y=Y.cpu())
+    return dict(genop=genop, X=X, z=z, betas=betas, Y=Y.cpu(), Yb=Yb.cpu())
