@@ -112,10 +112,13 @@ PROTOTYPES = {
     "eg_policy_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "eg_gauss_sample": (_I, [_P, _P, _I, _I, _F, _F, _P, _P, _P]),
     "eg_ppo_loss_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _I, _P, _P]),
+    "eg_ppo_loss_backward_mlp": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _I, _P, _P]),
+    "eg_ppo_backward_encoders": (_I, [_P, _P, _I, _P]),
     "eg_moments": (_I, [_P, _L, _P, _P]),
     "eg_adv_normalize": (_I, [_P, _I, _P, _F, _P, _P]),
     "eg_clip_adamw_step": (_I, [_P, _P, _P, _F, _F, _F, _F, _F, _F, _I, _P]),
     "eg_dp_reduce_norm": (_I, [_P, _P, _I, _I, _L, _L, _P, _P, _P, _P]),
+    "eg_dp_reduce_range": (_I, [_P, _P, _I, _I, _L, _L, _L, _L, _I, _P, _P, _P, _P]),
     "eg_dp_adamw_gather": (_I, [_P, _P, _I, _I, _L, _L, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I, _P]),
     "eg_gae": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_double, C.c_double, _P, _P, _P]),
     "eg_cvae_param_count": (_L, [C.POINTER(EgCvaeDims)]),

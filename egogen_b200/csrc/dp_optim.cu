@@ -14,6 +14,10 @@
 // soon as the backward has finished, and the 369 MB optimiser pass of the single-GPU path shrinks to 1/N.
 // The buffers are torch symmetric-memory allocations (the caller passes the peer pointers and, when available, the
 // multicast pointer); the three barriers of a step are the caller's (symmetric-memory signal pads).
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace eg {
@@ -36,27 +40,46 @@ __device__ __forceinline__ void mc_st(float* mc, float4 v) {
 template <bool MC>
 __global__ void __launch_bounds__(256)
 dp_reduce_norm_kernel(PeerPtrs grads, const float* grads_mc, int world, int rank, int64_t chunk, int64_t n_clip,
-                      float* __restrict__ gred, PeerPtrs scratch, double* partial, unsigned* ticket) {
+                      float* __restrict__ gred, PeerPtrs scratch, double* partial, unsigned* ticket, int64_t i_lo, int64_t i_hi,
+                      int publish) {
+  // i_lo / i_hi: the part of this rank's slice to reduce now (slice-relative, multiples of 4)
   const int64_t base = (int64_t)rank * chunk;
   double q = 0.0;
-  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < chunk; i += (int64_t)gridDim.x * blockDim.x * 4) {
-    float4 g;
-    if (MC) {
-      g = mc_ld_reduce(grads_mc + base + i);
-    } else {
-      g = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < world; ++r) {
-        const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(grads.p[r]) + base + i);
-        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+  // 4 independent 16-byte (multicast / peer) loads in flight per thread: the reduce is bound by NVLink latency x bytes in
+  // flight, and a grid that is small enough to leave SMs to a concurrent backward still has to keep ~1 MB outstanding
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i0 = i_lo + (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i0 < i_hi; i0 += stride * U) {
+    float4 g[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < i_hi) {
+        if (MC) {
+          g[u] = mc_ld_reduce(grads_mc + base + i);
+        } else {
+          for (int r = 0; r < world; ++r) {
+            const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(grads.p[r]) + base + i);
+            g[u].x += v.x; g[u].y += v.y; g[u].z += v.z; g[u].w += v.w;
+          }
+        }
       }
     }
-    *reinterpret_cast<float4*>(gred + i) = g;
-    const int64_t gi = base + i;
-    if (gi < n_clip) q += (double)g.x * g.x;
-    if (gi + 1 < n_clip) q += (double)g.y * g.y;
-    if (gi + 2 < n_clip) q += (double)g.z * g.z;
-    if (gi + 3 < n_clip) q += (double)g.w * g.w;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < i_hi) {
+        *reinterpret_cast<float4*>(gred + i) = g[u];
+        const int64_t gi = base + i;
+        if (gi < n_clip) q += (double)g[u].x * g[u].x;
+        if (gi + 1 < n_clip) q += (double)g[u].y * g[u].y;
+        if (gi + 2 < n_clip) q += (double)g[u].z * g[u].z;
+        if (gi + 3 < n_clip) q += (double)g[u].w * g[u].w;
+      }
+    }
   }
+  if (!publish) return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   __shared__ double pq[8];
@@ -135,23 +158,35 @@ static int fill_peers(PeerPtrs& pp, const void* const* ptrs, int world) {
   return EG_OK;
 }
 
-extern "C" int eg_dp_reduce_norm(const void* const* grads_ptrs, const void* grads_mc, int world, int rank, int64_t n_pad,
-                                 int64_t n_clip, float* gred, const void* const* scratch_ptrs, void* work, void* stream) {
+extern "C" int eg_dp_reduce_range(const void* const* grads_ptrs, const void* grads_mc, int world, int rank, int64_t n_pad,
+                                  int64_t n_clip, int64_t elem_lo, int64_t elem_hi, int publish_norm, float* gred,
+                                  const void* const* scratch_ptrs, void* work, void* stream) {
   EG_REQUIRE(gred && work && rank >= 0 && rank < world, "bad arguments");
   EG_REQUIRE(n_pad > 0 && n_pad % (4 * (int64_t)world) == 0, "n_pad must be a multiple of 4 * world");
+  EG_REQUIRE(elem_lo >= 0 && elem_lo <= elem_hi && elem_hi <= n_pad && elem_lo % 4 == 0 && elem_hi % 4 == 0, "element range must be 4-aligned");
   PeerPtrs g, s;
   int rc;
   if ((rc = fill_peers(g, grads_ptrs, world))) return rc;
   if ((rc = fill_peers(s, scratch_ptrs, world))) return rc;
-  const int64_t chunk = n_pad / world;
-  const int grid = (int)std::min<int64_t>((chunk / 4 + 255) / 256, kNumSMs * 4);
+  const int64_t chunk = n_pad / world, base = (int64_t)rank * chunk;
+  const int64_t i_lo = std::min(std::max(elem_lo - base, (int64_t)0), chunk), i_hi = std::min(std::max(elem_hi - base, (int64_t)0), chunk);
+  if (i_hi <= i_lo && !publish_norm) return EG_OK;             // nothing of the range lies in this rank's slice
+  // EG_DP_REDUCE_BLOCKS caps the grid (default: 4 CTAs per SM; a smaller grid leaves SMs to a concurrent backward in the
+  // opt-in overlapped mode, EG_DP_OVERLAP=1)
+  static const int cap = getenv("EG_DP_REDUCE_BLOCKS") ? std::max(1, atoi(getenv("EG_DP_REDUCE_BLOCKS"))) : kNumSMs * 4;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((i_hi - i_lo) / 16 + 255) / 256, cap));
   double* partial = static_cast<double*>(work);
   unsigned* ticket = reinterpret_cast<unsigned*>(partial + 1);
   if (grads_mc) EG_LAUNCH(dp_reduce_norm_kernel<true>, grid, 256, 0, as_stream(stream), g, static_cast<const float*>(grads_mc), world, rank,
-                          chunk, n_clip, gred, s, partial, ticket);
+                          chunk, n_clip, gred, s, partial, ticket, i_lo, i_hi, publish_norm);
   else EG_LAUNCH(dp_reduce_norm_kernel<false>, grid, 256, 0, as_stream(stream), g, nullptr, world, rank, chunk, n_clip, gred, s,
-                 partial, ticket);
+                 partial, ticket, i_lo, i_hi, publish_norm);
   return EG_OK;
+}
+
+extern "C" int eg_dp_reduce_norm(const void* const* grads_ptrs, const void* grads_mc, int world, int rank, int64_t n_pad,
+                                 int64_t n_clip, float* gred, const void* const* scratch_ptrs, void* work, void* stream) {
+  return eg_dp_reduce_range(grads_ptrs, grads_mc, world, rank, n_pad, n_clip, 0, n_pad, 1, gred, scratch_ptrs, work, stream);
 }
 
 extern "C" int eg_dp_adamw_gather(const void* const* params_ptrs, void* params_mc, int world, int rank, int64_t n_pad,

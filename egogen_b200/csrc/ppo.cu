@@ -602,17 +602,19 @@ static int gru2_backward(EgPolicy* h, cudaStream_t st, const float* x, int ld_en
   return EG_OK;
 }
 
-extern "C" int eg_ppo_loss_backward(EgPolicy* h, const float* state, const float* ego, const float* dist,
-                                    const float* time, const float* act, const float* logp_old, const float* adv_norm,
-                                    const float* returns, int B, float inv_B, float eps_clip, float vf_coef,
-                                    float ent_coef, float min_logvar, float max_logvar, int zero_grads,
-                                    float* stats, void* stream) {
+// forward + loss head + backward of the actor and critic chains (everything whose gradients lie in the actor + critic
+// prefix of the flat buffer, i.e. the clip-grad-norm range), leaving d loss / d hx in h->dhx
+extern "C" int eg_ppo_loss_backward_mlp(EgPolicy* h, const float* state, const float* ego, const float* dist,
+                                        const float* time, const float* act, const float* logp_old, const float* adv_norm,
+                                        const float* returns, int B, float inv_B, float eps_clip, float vf_coef,
+                                        float ent_coef, float min_logvar, float max_logvar, int zero_grads,
+                                        float* stats, void* stream) {
   EG_REQUIRE(h && h->G && act && logp_old && adv_norm && returns && stats, "null pointer (was the policy created with a gradient buffer?)");
   if (B <= 0) return EG_OK;
   cudaStream_t st = as_stream(stream);
   const EgPolicyDims& d = h->d;
   const PolicyLayout& L = h->L;
-  const int H = d.h_dim, D = L.hx_dim;
+  const int D = L.hx_dim;
   EG_TRY(eg_policy_forward(h, state, ego, dist, time, B, 1, 1, nullptr, nullptr, nullptr, stream));
   if (zero_grads) EG_CUDA_CHECK(cudaMemsetAsync(h->G, 0, (size_t)L.n_total * 4, st));
   EG_LAUNCH(ppo_head_kernel, B, 128, 0, st, h->out_a, h->out_c, act, logp_old, adv_norm, returns, B, d.z_dim, inv_B,
@@ -631,12 +633,34 @@ extern "C" int eg_ppo_loss_backward(EgPolicy* h, const float* state, const float
     EG_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
   EG_LAUNCH_PDL(add_kernel, ew_grid(nD), 256, 0, st, h->dh, h->dh2, nD, h->dhx);      // d hx = actor path + critic path
-  const int IP = h->in_pad;
+  return EG_OK;
+}
+
+// backward of the two GRU encoders (the shared_net tail of the flat gradient) from h->dhx; call after eg_ppo_loss_backward_mlp
+// with the same state / ego / B
+extern "C" int eg_ppo_backward_encoders(EgPolicy* h, const float* ego, int B, void* stream) {
+  EG_REQUIRE(h && h->G && ego, "null pointer");
+  if (B <= 0) return EG_OK;
+  EG_REQUIRE(B <= h->cap, "eg_ppo_loss_backward_mlp must run first with the same batch");
+  cudaStream_t st = as_stream(stream);
+  const EgPolicyDims& d = h->d;
+  const PolicyLayout& L = h->L;
+  const int H = d.h_dim, D = L.hx_dim, IP = h->in_pad;
   EG_TRY(gru2_backward(h, st, h->xpad, 2 * IP, IP, d.in_dim, B, L.x_wih, L.x_whh, L.x_bih, L.x_bhh, h->xr,
                        h->xz, h->xn, h->xg, h->xh1, h->dhx, D));
   EG_TRY(gru2_backward(h, st, ego, 2 * d.ego_dim, d.ego_dim, d.ego_dim, B, L.e_wih, L.e_whh, L.e_bih, L.e_bhh, h->er,
                        h->ez, h->en, h->eg_, h->eh1, h->dhx + H, D));
   return EG_OK;
+}
+
+extern "C" int eg_ppo_loss_backward(EgPolicy* h, const float* state, const float* ego, const float* dist,
+                                    const float* time, const float* act, const float* logp_old, const float* adv_norm,
+                                    const float* returns, int B, float inv_B, float eps_clip, float vf_coef,
+                                    float ent_coef, float min_logvar, float max_logvar, int zero_grads,
+                                    float* stats, void* stream) {
+  EG_TRY(eg_ppo_loss_backward_mlp(h, state, ego, dist, time, act, logp_old, adv_norm, returns, B, inv_B, eps_clip, vf_coef,
+                                  ent_coef, min_logvar, max_logvar, zero_grads, stats, stream));
+  return eg_ppo_backward_encoders(h, ego, B, stream);
 }
 
 extern "C" int eg_moments(const float* x, int64_t n, double* out2, void* stream) {

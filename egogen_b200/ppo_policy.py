@@ -297,19 +297,29 @@ class GAMMAPPOPolicy(nn.Module):
         b1, b2 = g.get("betas", (0.9, 0.999))
         return float(g["lr"]), float(b1), float(b2), float(g.get("eps", 1e-8)), float(g.get("weight_decay", 0.01))
 
-    def loss_backward(self, mb, global_batch: Optional[int] = None, moments=None):
-        """forward + PPO loss + backward of one minibatch into flat_grads; stats land in self._stats."""
+    def loss_backward(self, mb, global_batch: Optional[int] = None, moments=None, part: str = "all"):
+        """forward + PPO loss + backward of one minibatch into flat_grads; stats land in self._stats.
+        part = "mlp" stops after the actor / critic chains (eg_ppo_loss_backward_mlp: every gradient of the actor + critic
+        prefix is final), part = "encoders" finishes the same minibatch (eg_ppo_backward_encoders)."""
+        if part == "encoders":
+            eg, B = self._pending
+            with torch.cuda.device(self.dev):
+                _lib.check(_lib.lib().eg_ppo_backward_encoders(self.handle(), _lib.ptr(eg), B, _lib.stream_ptr(self.dev)))
+            self._pending = None
+            return
         B = mb.act.shape[0]
         gb = global_batch if global_batch is not None else B * self._world()
         adv = self.normalize_adv(mb.adv.contiguous(), moments) if self._norm_adv else mb.adv.contiguous()
         st, eg, di, ti = self._obs_ptrs(mb.obs)
         self._stats.zero_()
+        fn = _lib.lib().eg_ppo_loss_backward_mlp if part == "mlp" else _lib.lib().eg_ppo_loss_backward
         with torch.cuda.device(self.dev):
-            _lib.check(_lib.lib().eg_ppo_loss_backward(
+            _lib.check(fn(
                 self.handle(), _lib.ptr(st), _lib.ptr(eg), _lib.ptr(di), _lib.ptr(ti), _lib.ptr(mb.act.contiguous()),
                 _lib.ptr(mb.logp_old.contiguous()), _lib.ptr(adv), _lib.ptr(mb.returns.contiguous()), B, 1.0 / gb,
                 float(self._eps_clip), float(self._weight_vf), float(self._weight_ent), float(self.actor.min_logvar),
                 float(self.actor.max_logvar), 1, _lib.ptr(self._stats), _lib.stream_ptr(self.dev)))
+        self._pending = (eg, B) if part == "mlp" else None
 
     def optimizer_step(self):
         """clip_grad_norm_(actor + critic) + AdamW (:241-247). With N > 1 ranks the gradient is first summed over the
@@ -340,12 +350,55 @@ class GAMMAPPOPolicy(nn.Module):
             _lib.check(lib.eg_clip_adamw_step(self.handle(), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                               float(self._grad_norm or 0.0), lr, b1, b2, eps, wd, self._opt_step, st))
 
+    def _dp_overlapped_step(self, mb, global_batch, moments):
+        """One minibatch with the gradient sum of the actor + critic prefix (94 % of the bytes, and the whole clip-norm range)
+        running on a side stream UNDER the encoders' backward: the NVLink traffic of the reduce phase is hidden, only the
+        small tail reduce, AdamW on the slice and the parameter broadcast stay on the critical path."""
+        import os
+        dp, lib = self._dp, _lib.lib()
+        W, rank, n_pad, n_ac = dp["world"], dp["rank"], dp["n_pad"], self.n_actor_critic
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(device=self.dev)
+            self._ev_a, self._ev_r = torch.cuda.Event(), torch.cuda.Event()
+        main = torch.cuda.current_stream(self.dev)
+        bar = dp["hdl"]["grads"].barrier
+        mcg, mcp = C.c_void_p(dp["mc"]["grads"] or None), C.c_void_p(dp["mc"]["params"] or None)
+        self.loss_backward(mb, global_batch, moments, part="mlp")
+        self._ev_a.record(main)
+        with torch.cuda.device(self.dev), torch.cuda.stream(self._comm):
+            self._comm.wait_event(self._ev_a)
+            bar(channel=1)                                         # every rank's actor / critic gradients are final
+            _lib.check(lib.eg_dp_reduce_range(dp["ptrs"]["grads"], mcg, W, rank, n_pad, n_ac, 0, n_ac, 1, _lib.ptr(dp["gred"]),
+                                              dp["ptrs"]["scratch"], _lib.ptr(dp["work"]), C.c_void_p(self._comm.cuda_stream)))
+            self._ev_r.record(self._comm)
+        self.loss_backward(None, part="encoders")
+        lr, b1, b2, eps, wd = self._opt_hparams()
+        self._opt_step += 1
+        st = _lib.stream_ptr(self.dev)
+        with torch.cuda.device(self.dev):
+            main.wait_event(self._ev_r)
+            bar(channel=0)                                         # every rank's encoder gradients are final
+            _lib.check(lib.eg_dp_reduce_range(dp["ptrs"]["grads"], mcg, W, rank, n_pad, n_ac, n_ac, n_pad, 0, _lib.ptr(dp["gred"]),
+                                              dp["ptrs"]["scratch"], _lib.ptr(dp["work"]), st))
+            bar(channel=0)                                         # all slices read, all norm shares published
+            _lib.check(lib.eg_dp_adamw_gather(dp["ptrs"]["params"], mcp, W, rank, n_pad, n_ac, _lib.ptr(dp["gred"]),
+                                              _lib.ptr(dp["scratch"]), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                              float(self._grad_norm or 0.0), lr, b1, b2, eps, wd, self._opt_step, st))
+            bar(channel=0)                                         # every rank's slice of the new parameters has landed
+
     def learn_minibatch(self, mb, global_batch: Optional[int] = None, moments=None, reduce_stats: bool = True):
         """One iteration of the inner loop of learn (:189-252). mb: Batch(obs, act, logp_old, adv, returns)
         with CUDA tensors. Returns a clone of the device stats tensor (rank-summed unless reduce_stats is False:
         learn() sums the statistics of all its minibatches in one collective at the end)."""
-        self.loss_backward(mb, global_batch, moments)
-        self.optimizer_step()
+        import os
+        # EG_DP_OVERLAP=1: gradient sum of the actor + critic prefix under the encoders' backward. Off by default: measured
+        # SLOWER at N = 2 (13.1-13.7 vs 12.9 ms per iteration for 24..296 reduce CTAs) - the encoders' backward is only
+        # ~0.15 ms long, and the extra barrier, the event hand-offs and the reduce CTAs it has to share the SMs with cost more
+        if self._dp is not None and os.environ.get("EG_DP_OVERLAP", "0") == "1":
+            self._dp_overlapped_step(mb, global_batch, moments)
+        else:
+            self.loss_backward(mb, global_batch, moments)
+            self.optimizer_step()
         if reduce_stats and self._world() > 1:
             import torch.distributed as dist
             dist.all_reduce(self._stats, group=self.pg)

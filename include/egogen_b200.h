@@ -331,6 +331,14 @@ int eg_ppo_loss_backward(EgPolicy* h, const float* state, const float* ego, cons
                          const float* act, const float* logp_old, const float* adv_norm, const float* returns,
                          int B, float inv_B, float eps_clip, float vf_coef, float ent_coef, float min_logvar,
                          float max_logvar, int zero_grads, float* stats, void* stream);
+/* The same in two calls, so that a data-parallel caller can start summing the actor + critic gradients (the prefix of the
+ * flat buffer, 94 % of it) over the ranks while the encoders' backward still runs: _mlp = forward, loss head and the
+ * backward of the actor / critic chains; _encoders = the GRU encoders' backward (the shared_net tail). */
+int eg_ppo_loss_backward_mlp(EgPolicy* h, const float* state, const float* ego, const float* dist, const float* time,
+                             const float* act, const float* logp_old, const float* adv_norm, const float* returns,
+                             int B, float inv_B, float eps_clip, float vf_coef, float ent_coef, float min_logvar,
+                             float max_logvar, int zero_grads, float* stats, void* stream);
+int eg_ppo_backward_encoders(EgPolicy* h, const float* ego, int B, void* stream);
 /* out2 (device double[2]) = {sum x, sum x^2} */
 int eg_moments(const float* x, int64_t n, double* out2, void* stream);
 /* (adv - mean) / (std_unbiased + eps) from moments3 (device double[3]) = {sum, sumsq, count} (:192-195) */
@@ -351,6 +359,12 @@ int eg_clip_adamw_step(EgPolicy* h, float* exp_avg, float* exp_avg_sq, float max
  *     [n_pad / world], local), updated parameters stored to every rank (params_mc multicast, or peer stores).
  *   -- and a barrier after it, before any rank reads the parameters again.
  * grads_ptrs / params_ptrs / scratch_ptrs are HOST arrays of `world` device pointers (index = rank). */
+/* eg_dp_reduce_norm restricted to the flat elements [elem_lo, elem_hi) (multiples of 4): the part of this rank's slice inside
+ * the range is summed over the ranks; publish_norm != 0 also publishes the squared-norm share (use it on the call whose range
+ * covers the clip prefix). */
+int eg_dp_reduce_range(const void* const* grads_ptrs, const void* grads_mc, int world, int rank, int64_t n_pad,
+                       int64_t n_clip, int64_t elem_lo, int64_t elem_hi, int publish_norm, float* gred,
+                       const void* const* scratch_ptrs, void* work, void* stream);
 int eg_dp_reduce_norm(const void* const* grads_ptrs, const void* grads_mc, int world, int rank, int64_t n_pad,
                       int64_t n_clip, float* gred, const void* const* scratch_ptrs, void* work, void* stream);
 int eg_dp_adamw_gather(const void* const* params_ptrs, void* params_mc, int world, int rank, int64_t n_pad,

@@ -51,7 +51,7 @@ def run(rank, world, port, out_dir, per_rank, env):
         pol = build(dev)
         pol.loss_backward(make_batch(per_rank * world, 100, dev))
         g1 = pol.flat_grads.clone()
-        pol.optimizer_step()
+        pol.learn_minibatch(make_batch(per_rank * world, 100, dev))        # same gradient again + optimiser step
         p1 = pol.flat_params.clone()
         pol.flat_grads.copy_(sum(synth_grad(pol.n_params, r) for r in range(world)).to(dev))
         pol.optimizer_step()
@@ -61,12 +61,13 @@ def run(rank, world, port, out_dir, per_rank, env):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     pol = build(dev)
     used = "nccl-allreduce" if pol._dp is None else ("multicast" if pol._dp["mc"]["grads"] else "peer")
+    if pol._dp is not None and os.environ.get("EG_DP_OVERLAP", "0") == "1":
+        used += "+overlap"
     full = make_batch(per_rank * world, 100, dev)
-    pol.loss_backward(shard(full, rank * per_rank, (rank + 1) * per_rank))
+    mine = shard(full, rank * per_rank, (rank + 1) * per_rank)
+    pol.loss_backward(mine)
     g_local = pol.flat_grads.clone()
-    stats = pol._stats.clone()
-    dist.all_reduce(stats)
-    pol.optimizer_step()
+    stats = pol.learn_minibatch(mine)              # the product path: (overlapped) gradient sum + sharded optimiser step
     p1 = pol.flat_params.clone()
     pol.flat_grads.copy_(synth_grad(pol.n_params, rank).to(dev))
     pol.optimizer_step()

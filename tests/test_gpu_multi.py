@@ -1,6 +1,7 @@
 """Multi-rank parity on hardware (needs >= 2 GPUs; skipped otherwise): N = 2 data-parallel PPO updates must reproduce
 the single-process update on the concatenated minibatch (reference ppo_policy.py:189-252 runs in one process), through
-each gradient path: NVSwitch multicast (multimem.ld_reduce / multimem.st), peer loads / stores, and the NCCL all_reduce fallback."""
+each gradient path: NVSwitch multicast (multimem.ld_reduce / multimem.st), the opt-in variant that overlaps the reduce of
+the actor + critic prefix with the encoders' backward, peer loads / stores, and the NCCL all_reduce fallback."""
 import os
 import socket
 import sys
@@ -17,8 +18,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("env,expect", [({}, ("multicast", "peer")), ({"EG_DP_MULTICAST": "0"}, ("peer",)),
-                                        ({"EG_DP_OPTIM": "0"}, ("nccl-allreduce",))])
+@pytest.mark.parametrize("env,expect", [({}, ("multicast", "peer")), ({"EG_DP_OVERLAP": "1"}, ("multicast+overlap", "peer+overlap")),
+                                        ({"EG_DP_MULTICAST": "0"}, ("peer",)), ({"EG_DP_OPTIM": "0"}, ("nccl-allreduce",))])
 def test_two_rank_update_matches_single_process(tmp_path, env, expect):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
