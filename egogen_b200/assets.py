@@ -204,6 +204,46 @@ def make_surrogate_smplx(seed: int = 0, nnz_per_vertex: int = 4) -> Dict[str, np
         lmk_bary=lmk_bary.astype(np.float32))
 
 
+def make_stress_smplx(seed: int = 0) -> Dict[str, np.ndarray]:
+    """The surrogate with the skinning structure of a HARD mesh for the tensor-core LBS kernel: 5..8 non-zero weights per
+    vertex (the kernel caches four slots per vertex and fetches the rest through its uncached path) drawn from the
+    vertex's kinematic neighbourhood (own joint, ancestors up to three levels, children, siblings), so that neighbouring
+    vertices disagree about their joint sets and 80-vertex tiles meet more than the 10 distinct joints a tile may hold
+    (the layout builder has to close tiles early). Everything else is the seed-0 surrogate."""
+    m = make_surrogate_smplx(seed=0)
+    rng = np.random.default_rng(1000 + seed)
+    V, J = V_SMPLX, J_SMPLX
+    parents = SMPLX_PARENTS.copy()
+    children = [[c for c in range(J) if parents[c] == j] for j in range(J)]
+    own = m["lbs_weights"].argmax(axis=1)
+    pools = []
+    for j in range(J):
+        p = {j}
+        a = j
+        for _ in range(3):
+            a = max(int(parents[a]), 0)
+            p.add(a)
+        p.update(children[j])
+        for c in children[j]:
+            p.update(children[c])
+        if parents[j] >= 0:
+            p.update(children[int(parents[j])])
+        pools.append(np.array(sorted(p), dtype=np.int64))
+    w = np.zeros((V, J))
+    for v in range(V):
+        pool = pools[own[v]]
+        k = int(min(rng.integers(5, 9), len(pool)))
+        js = rng.choice(pool, size=k, replace=False)
+        if own[v] not in js:
+            js[0] = own[v]
+        wr = rng.uniform(0.05, 1.0, size=k)
+        wr[js == own[v]] += 1.5
+        w[v, js] = wr / wr.sum()
+    m = dict(m)
+    m["lbs_weights"] = w.astype(np.float32)
+    return m
+
+
 def load_smplx_npz(path: str, num_betas: int = 10, num_expression: int = 10,
                    num_pca_comps: int = N_HAND_PCA) -> Dict[str, np.ndarray]:
     """Read a licensed ``SMPLX_{MALE,FEMALE,NEUTRAL}.npz`` into the SMPLX_KEYS layout, the way

@@ -245,3 +245,63 @@ def test_markers_backward_matches_autograd(dev, parser, smplx_model):
     (orc.forward_smplx(betas.repeat(5, 1), "male", xr, "markers") * w).sum().backward()
     got = parser.bm_male.markers_backward(xb.to(dev), betas.to(dev), w.to(dev)).cpu()
     assert (got - xr.grad).abs().max().item() <= 2e-4 * max(xr.grad.abs().max().item(), 1.0)
+
+
+def test_lbs_stress_mesh_many_weights(dev):
+    """A mesh that does NOT flatter the tensor-core kernel (assets.make_stress_smplx): 4..8 non-zero skinning weights per
+    vertex, so every vertex with more than four takes the epilogue's uncached extra-weight path, and joint sets that differ
+    from vertex to vertex, so the layout builder has to close tiles at the 10-joint limit. Vertices / joints against the
+    oracle in both mainloops, fused penetration counts against the unfused chain, and the kernel's time at the bench size."""
+    from egogen_b200 import SMPLXParser, calc_sdf, penetration_count
+    from oracle.smplx_lbs import SMPLXParserOracle
+    model = assets.make_stress_smplx(0)
+    nnz = (model["lbs_weights"] > 0).sum(axis=1)
+    assert nnz.max() == 8 and (nnz > 4).mean() > 0.5
+    sp = SMPLXParser({"n_batch": 8, "device": dev, "marker_placement": "ssm2_67", "smplx_models": {"male": model, "female": model}})
+    orc = SMPLXParserOracle(model, marker=assets.marker_ids())
+    for n in (4, 37):
+        xb, betas = _rand_inputs(n, 900 + n)
+        ref = orc.forward_smplx(betas, "male", xb, "raw")
+        for tcgen05 in (True, False):
+            sp.bm_male.set_mainloop(tcgen05)
+            out = sp.forward_smplx(betas.to(dev), "male", xb.to(dev), to_numpy=False, output_type="raw")
+            for a, b in ((out.vertices.cpu(), ref.vertices), (out.joints.cpu(), ref.joints)):
+                rel = (a - b).norm(dim=-1).max() / b.norm(dim=-1).max()
+                assert rel < 1e-4, (n, tcgen05, rel)
+                assert (a - b).abs().max() < (5e-5 if tcgen05 else 2e-5), (n, tcgen05, (a - b).abs().max())
+    sp.bm_male.set_mainloop(True)
+    # fused counts == unfused chain on the same vertices (64 envs x 20 frames)
+    E, T = 64, 20
+    g = torch.Generator().manual_seed(23)
+    xb = torch.randn(E * T, 93, generator=g) * 0.15
+    xb[:, 3] += 3.14159265 / 2
+    xb[:, :3] = 0.0
+    betas = torch.randn(E, 10, generator=g) * 0.5
+    sd = {k: v.to(dev) for k, v in assets.rasterize_scene_sdf(assets.make_box_scene(5, n_boxes=2), D=128, device=str(dev)).items()}
+    ang = torch.rand(E, generator=g) * 6.28
+    R0 = torch.zeros(E, 3, 3); R0[:, 0, 0] = ang.cos(); R0[:, 0, 1] = -ang.sin(); R0[:, 1, 0] = ang.sin(); R0[:, 1, 1] = ang.cos(); R0[:, 2, 2] = 1
+    T0 = torch.cat([torch.rand(E, 1, 2, generator=g) * 5 - 2.5, torch.full((E, 1, 1), 1.05)], dim=2)
+    skip = torch.zeros(assets.V_SMPLX, dtype=torch.uint8)
+    skip[assets.feet_vids()] = 1
+    bm = sp.bm_male
+    brow = betas.repeat_interleave(T, 0)
+    counts, _, _ = bm.forward_sdf(xb.to(dev), brow.to(dev), T, R0.to(dev), T0.to(dev), sd, skip.to(dev))
+    verts = bm.forward(xb.to(dev), brow.to(dev), want_verts=True)[0]
+    vw = torch.einsum("bij,btpj->btpi", R0.to(dev), verts.view(E, T, -1, 3)) + T0.to(dev)[:, None]
+    sv = calc_sdf(vw.reshape(E * T, -1, 3), sd)
+    c2 = penetration_count(sv, skip.to(dev))
+    near = (sv.abs() < 1e-5).sum(dim=1)
+    assert bool(((counts - c2).abs() <= near).all()), (counts - c2).abs().max()
+    assert int((counts > 0).sum()) > 0
+    # time of the fused kernel at the bench size on this mesh (reported, not asserted: profiles/README.md quotes it)
+    xb5 = xb.repeat(4, 1); b5 = brow.repeat(4, 1)
+    R5, T5 = R0.repeat(4, 1, 1).to(dev), T0.repeat(4, 1, 1).to(dev)
+    for _ in range(2):
+        bm.forward_sdf(xb5.to(dev), b5.to(dev), T, R5, T5, sd, skip.to(dev))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        bm.forward_sdf(xb5.to(dev), b5.to(dev), T, R5, T5, sd, skip.to(dev))
+    e1.record(); torch.cuda.synchronize()
+    print(f"stress mesh: fused LBS + SDF call for {xb5.shape[0]} bodies = {e0.elapsed_time(e1) / 5:.3f} ms (pose prep + tc + compact + finish)")
