@@ -1,7 +1,8 @@
-"""Summarise an ncu --set full report: key raw metrics + top stall instructions. usage: ncu_summary.py rep [topN]"""
+"""Summarise an ncu --set full report: key raw metrics + top stall instructions. usage: ncu_summary.py rep [topN] [kernel-regex]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+ksel = ["-k", "regex:" + sys.argv[3], "-c", "1"] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + ksel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h, u, v = rows[0], rows[1], rows[2]
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
@@ -13,7 +14,7 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 for i, name in enumerate(h):
     if name in want or ('issue_stalled' in name and 'per_issue_active' in name and float(v[i] or 0) > 0.15):
         print(f'{name:90s} {u[i]:15s} {v[i]}')
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + ksel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]; data = rows[2:]
 si = h.index('# Samples'); sc = h.index('Source'); ie = h.index('Instructions Executed')

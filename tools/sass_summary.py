@@ -1,5 +1,6 @@
 """Per-kernel counts of the SASS mnemonics that prove a Blackwell-native kernel (B200_PROFILING.md): tcgen05.mma -> UTC*MMA,
-tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG / UBLKCP, mbarrier -> SYNCS, cluster barrier -> UCGABAR, multimem -> *.MULTIMEM / REDG,
+tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG / UBLKCP, mbarrier -> SYNCS, cluster barrier -> UCGABAR, multimem.ld_reduce -> LDGMC, multimem.st -> STG.E.128.STRONG.SYS (a
+plain system-scope store to the multicast address; the switch replicates it),
 legacy mma.sync -> HMMA (must be 0). usage: python tools/sass_summary.py [lib.so] > profiles/r2_sass_summary.txt"""
 import collections
 import re
@@ -11,7 +12,8 @@ out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True
 pats = collections.OrderedDict([
     ("UTCHMMA", r"\bUTCHMMA"), ("UTCQMMA/other UTC*MMA", r"\bUTC(?!HMMA|BAR|ATOMSWS)[A-Z]*MMA"), ("UTCBAR", r"\bUTCBAR"),
     ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("UTMALDG", r"\bUTMALDG"), ("UBLKCP", r"\bUBLKCP"), ("SYNCS", r"\bSYNCS"),
-    ("UCGABAR", r"\bUCGABAR"), ("MULTIMEM", r"MULTIMEM|\bLDGMC|\bSTGMC|\bREDG?MC"), ("LDGSTS", r"\bLDGSTS"), ("HMMA (legacy)", r"\bHMMA"),
+    ("UCGABAR", r"\bUCGABAR"), ("LDGMC (multimem.ld_reduce)", r"MULTIMEM|\bLDGMC|\bSTGMC|\bREDG?MC"),
+    ("STG.SYS (multimem.st)", r"\bSTG\.E\.128\.STRONG\.SYS"), ("LDGSTS", r"\bLDGSTS"), ("HMMA (legacy)", r"\bHMMA"),
     ("FFMA", r"\bFFMA"), ("DFMA", r"\bDFMA")])
 cur, rows = None, collections.OrderedDict()
 for line in out.splitlines():
@@ -40,7 +42,7 @@ print("kernel | " + " | ".join(keys))
 tot = collections.Counter()
 for fn, c in rows.items():
     tot.update(c)
-    if not any(c[k] for k in keys[:10]):      # list every kernel that touches tensor cores / TMEM / TMA / mbarriers / clusters / multimem
+    if not any(c[k] for k in keys[:11]):      # list every kernel that touches tensor cores / TMEM / TMA / mbarriers / clusters / multimem
         continue
     print(demangle(fn) + " | " + " | ".join(str(c[k]) for k in keys))
 print("TOTAL (all %d kernels) | " % len(rows) + " | ".join(str(tot[k]) for k in keys))
