@@ -44,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")] + \
               [os.path.join(PKG_DIR, "..", "include", "egogen_b200.h")]
     t_hdr = max(os.path.getmtime(h) for h in headers)
-    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + \
+        os.environ.get("EG_NVCC_EXTRA", "").split()      # debug builds only (e.g. -DEG_LBS_PROF=1)
     jobs, objs = [], []
     for src in sources():
         obj = os.path.join(_obj_dir(), os.path.basename(src)[:-3] + ".o")

@@ -77,6 +77,7 @@ struct EgLbs {
   float4* rec_call = nullptr; // [n_pad_tc][3] per-call vertex records with the skip mask folded in
   int cap_Ntc = 0;
   int use_tc = 1;             // 1: tcgen05/TMEM/TMA mainloop for the full mesh, 0: SIMT mainloop
+  unsigned int* tile_sched = nullptr;   // {ticket, finished} counters of the tcgen05 kernel's tile scheduler
   int max_clusters = 64;      // co-resident 2-CTA clusters of the tcgen05 kernel (cudaOccupancyMaxActiveClusters)
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
   CUtensorMap mapA;
@@ -303,6 +304,7 @@ struct VertArgs {
   const float* tc_xw;
   int n_pad_tc;
   int A_rows;             // tc path: A is joint-major [J][A_rows][12]
+  unsigned int* tile_sched;   // tc path: {ticket counter, finished-CTA counter}; both return to 0 when a launch ends
 };
 
 // One (vertex, body) of the epilogue shared by the SIMT and tcgen05 kernels: skinning T = sum_k w_k A[n][j_k],
@@ -443,7 +445,22 @@ lbs_verts_kernel(const VertArgs a) {
 // --------------------------------------------------------------------------------------------
 // tcgen05 vertex kernel (full mesh): persistent, warp-specialised; see lbs_tc.cuh for the tile plan
 // --------------------------------------------------------------------------------------------
-template <bool FUSE_SDF>
+#ifndef EG_LBS_PROF
+#define EG_LBS_PROF 0
+#endif
+#if EG_LBS_PROF
+// per-CTA stall accounting of the tc kernel (debug builds only: EG_NVCC_EXTRA=-DEG_LBS_PROF=1; read with eg_lbs_prof_dump)
+__device__ unsigned long long g_lbs_prof[160][32];
+__device__ unsigned long long g_lbs_prof_vt[512];     // epilogue work clocks of warp 4, summed per vertex tile
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PROF_T0() const long long _pt0 = clock64()
+#define PROF_ADD(slot) do { if (lane == 0) g_lbs_prof[blockIdx.x][slot] += (unsigned long long)(clock64() - _pt0); } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_ADD(slot) do {} while (0)
+#endif
+
+template <bool FUSE_SDF, bool XW>      // XW: some vertex has more than 4 skinning weights (extras read uncached)
 __global__ void __cluster_dims__(tc::CLUSTER, 1, 1) __launch_bounds__(tc::THREADS, 1)
 lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const VertArgs a, int n_vt, int n_bt) {
@@ -457,15 +474,27 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint64_t* tab_full = tmem_empty + 2;       // [2] joint-transform table + vertex records
   uint64_t* tab_empty = tab_full + 2;        // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tab_empty + 2);
+  uint64_t* sched_full = tab_empty + 2;      // [NSCHED] tile-scheduler ring
+  uint64_t* sched_empty = sched_full + NSCHED;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sched_empty + NSCHED);
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_ptr + 1);   // [NSCHED]
   const uint32_t smem_base = smem_u32(smem);
+  static_assert(CLUSTER == 1, "the ticket scheduler hands tiles to single CTAs");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // work unit = (vertex tile, PAIR of body tiles); CTA `rank` of the cluster takes body tile 2*pair + rank
-  const int rank = (int)cluster_ctarank();
-  const int n_btp = (n_bt + CLUSTER - 1) / CLUSTER;
+  const int rank = 0;
+  const int n_btp = n_bt;
   const int n_tiles = n_vt * n_btp;
-  const int tile0 = blockIdx.x / CLUSTER, tile_step = gridDim.x / CLUSTER;
+  // every consumer role walks the scheduler ring with its own cursor: next tile or -1
+  int sc_slot = 0; uint32_t sc_phase = 0;
+  auto next_tile = [&](bool whole_warp) -> int {     // whole_warp: all 32 lanes call it (else lane 0 alone)
+    mbar_wait(&sched_full[sc_slot], sc_phase);
+    const int t = sched_tile[sc_slot];
+    if (whole_warp) __syncwarp();
+    if (lane == 0) mbar_arrive(&sched_empty[sc_slot]);
+    if (++sc_slot == NSCHED) { sc_slot = 0; sc_phase ^= 1u; }
+    return t < n_tiles ? t : -1;
+  };
 
   if (warp == 1) {
     if (lane == 0) {
@@ -474,6 +503,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS);
         mbar_init(&tab_full[b], 1); mbar_init(&tab_empty[b], EPI_WARPS);
       }
+      for (int s = 0; s < NSCHED; ++s) { mbar_init(&sched_full[s], 1); mbar_init(&sched_empty[s], 3 + EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -489,13 +519,12 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == 0) {
     // ===== operand producer: TMA ring =====
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0, it = 0;
-      for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = next_tile(false); tile >= 0; tile = next_tile(false)) {
         int vt, bt;
         tile_coords(tile, n_vt, n_btp, vt, bt);
-        bt = bt * CLUSTER + rank;
         for (int ch = 0; ch < NCHUNK; ++ch) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          { PROF_T0(); mbar_wait_relaxed(&empty_bar[stage], phase ^ 1); PROF_ADD(26); }
           unsigned char* st = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
 #pragma unroll
@@ -511,12 +540,11 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // ===== table producer: joint-transform table + vertex records of each tile (bulk copies), decoupled from the ring =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+      for (int tile = next_tile(false); tile >= 0; tile = next_tile(false), ++it) {
         int vt, bt;
         tile_coords(tile, n_vt, n_btp, vt, bt);
-        bt = bt * CLUSTER + rank;
         const uint32_t tb = it % NTAB, tph = (it / NTAB) & 1u;
-        mbar_wait(&tab_empty[tb], tph ^ 1u);                       // epilogue of tile it-NTAB is done with this buffer
+        { PROF_T0(); mbar_wait_relaxed(&tab_empty[tb], tph ^ 1u); PROF_ADD(27); }   // epilogue of tile it-NTAB is done with this buffer
         const int nj = __ldg(a.tc_nj + vt);
         mbar_expect_tx(&tab_full[tb], (uint32_t)nj * SLOT_BYTES + REC_BYTES);
         for (int s = 0; s < nj; ++s) {
@@ -530,12 +558,12 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer: A = feature tile (bodies -> TMEM lanes), B = basis tile of component c (vertices -> columns) =====
     int stage = 0; uint32_t phase = 0, it = 0;
-    for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+    for (int tile = next_tile(true); tile >= 0; tile = next_tile(true), ++it) {
       const uint32_t buf = it & 1u;
-      mbar_wait(&tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);         // epilogue of tile it-2 has drained this accumulator set
+      { PROF_T0(); mbar_wait(&tmem_empty[buf], ((it >> 1) & 1u) ^ 1u); PROF_ADD(24); }   // epilogue of tile it-2 has drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int ch = 0; ch < NCHUNK; ++ch) {
-        mbar_wait(&full_bar[stage], phase);
+        { PROF_T0(); mbar_wait(&full_bar[stage], phase); PROF_ADD(25); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
@@ -552,6 +580,20 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== tile scheduler: first tile = this CTA's index, then tickets; the entry past the last tile ends every role =====
+    if (lane == 0) {
+      int slot = 0; uint32_t phase = 0;
+      int tile = (int)blockIdx.x;
+      for (;;) {
+        mbar_wait_relaxed(&sched_empty[slot], phase ^ 1u);
+        sched_tile[slot] = tile;
+        mbar_arrive(&sched_full[slot]);
+        if (tile >= n_tiles) break;
+        tile = (int)gridDim.x + (int)atomicAdd(a.tile_sched, 1u);
+        if (++slot == NSCHED) { slot = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
@@ -581,11 +623,50 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");         // sign bits visible to every epilogue warp
     const uint32_t dmax0 = (uint32_t)(a.sdf.D0 - 1), dmax1 = (uint32_t)(a.sdf.D1 - 1), dmax2 = (uint32_t)(a.sdf.D2 - 1);
     const uint32_t cmax0 = (uint32_t)(a.sdf.C0 - 1), cmax1 = (uint32_t)(a.sdf.C1 - 1), cmax2 = (uint32_t)(a.sdf.C2 - 1);
+    // SDF work queues of this warp (see lbs_tc.cuh): entry = {world x, y, z, body}; stage 1 is a stack growing up from
+    // entry 0, stage 2 a stack growing down from entry QCAP-1; n1 + n2 <= 63 + 31 at any time
+    const uint32_t qbase = smem_base + OFF_Q + (uint32_t)(warp - 4) * Q_BYTES;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int n1 = 0, n2 = 0;                                             // warp-uniform
+    auto drain2 = [&](bool final) {
+      while (n2 >= 32 || (final && n2 > 0)) {
+        __syncwarp();
+        const int take = min(n2, 32);
+        n2 -= take;
+        if (lane < take) {
+          const float4 e = lds128(qbase + (uint32_t)(QCAP - 1 - (n2 + lane)) * 16u);
+          if (sdf_exact_negative(a.sdf.grid, a.sdf.D0, a.sdf.D1, a.sdf.D2, cx, cy, cz, sc, e.x, e.y, e.z))
+            atomicAdd(a.counts + __float_as_int(e.w), 1);
+        }
+        __syncwarp();
+      }
+    };
+    auto drain1 = [&](bool final) {
+      while (n1 >= 32 || (final && n1 > 0)) {
+        __syncwarp();
+        const int take = min(n1, 32);
+        n1 -= take;
+        bool pass = false;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < take) {
+          e = lds128(qbase + (uint32_t)(n1 + lane) * 16u);
+          const float s8 = (float)(1 << (kCoarseShift - 1));
+          const uint32_t f0 = min(__float2uint_rz(fmaf(e.x, gax, gbx) * s8), (dmax0 >> 1));
+          const uint32_t f1 = min(__float2uint_rz(fmaf(e.y, gay, gby) * s8), (dmax1 >> 1));
+          const uint32_t f2 = min(__float2uint_rz(fmaf(e.z, gaz, gbz) * s8), (dmax2 >> 1));
+          const uint32_t fi = (f0 * fd1 + f1) * fd2 + f2;
+          pass = ((__ldg(a.sdf.fine_bits + (fi >> 5)) >> (fi & 31u)) & 1u) != 0u;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (pass) sts128(qbase + (uint32_t)(QCAP - 1 - (n2 + __popc(m & lt_mask))) * 16u, e);
+        n2 += __popc(m);
+        drain2(false);
+      }
+    };
     uint32_t it = 0;
-    for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+    for (int tile = next_tile(true); tile >= 0; tile = next_tile(true), ++it) {
       int vt, bt;
       tile_coords(tile, n_vt, n_btp, vt, bt);
-        bt = bt * CLUSTER + rank;
       const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
       const uint32_t tb = it % NTAB, tph = (it / NTAB) & 1u;
       const uint32_t my_tab = smem_base + OFF_TAB + tb * TAB_BYTES + (uint32_t)(q * 32 + lane) * 48u;
@@ -595,6 +676,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const bool n_ok = n < a.N;
       float trx = 0.f, try_ = 0.f, trz = 0.f;
       if (!FUSE_SDF && n_ok) { const float* x = a.xb + (int64_t)n * EG_XB_DIM; trx = __ldg(x); try_ = __ldg(x + 1); trz = __ldg(x + 2); }
+      const float n_bits = __int_as_float(n);
       int cnt = 0;
       float2 C[4][6];                                               // register cache: slot k -> transform of MY body
 #pragma unroll
@@ -602,9 +684,10 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
         for (int e = 0; e < 6; ++e) C[k][e] = make_float2(0.f, 0.f);
       const int vbase = vt * TV + sub * VPW;
-      mbar_wait(&tab_full[tb], tph);                                // table + records landed
-      mbar_wait(&tmem_full[buf], ph);                               // accumulators complete
+      { PROF_T0(); mbar_wait(&tab_full[tb], tph); PROF_ADD(warp - 4); }          // table + records landed
+      { PROF_T0(); mbar_wait(&tmem_full[buf], ph); PROF_ADD(8 + warp - 4); }     // accumulators complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      PROF_T0();
 #pragma unroll 1
       for (int g = 0; g < VPW / 4; ++g) {
         float ax[4], ay[4], az[4];
@@ -634,7 +717,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           w2 = make_float2(r1.w, r1.w);
           c0 = __ffma2_rn(w2, C[3][0], c0); c1 = __ffma2_rn(w2, C[3][1], c1); c2 = __ffma2_rn(w2, C[3][2], c2);
           c3 = __ffma2_rn(w2, C[3][3], c3); z0 = __ffma2_rn(w2, C[3][4], z0); z1 = __ffma2_rn(w2, C[3][5], z1);
-          for (int k = 4; k < a.nnz; ++k) {                         // rare: more than 4 non-zero weights (uncached)
+          if (XW) for (int k = 4; k < a.nnz; ++k) {                 // rare: more than 4 non-zero weights (uncached)
             const int64_t xi = (int64_t)(k - 4) * a.n_pad_tc + vbase + g * 4 + u;
             const uint32_t xo = __ldg(a.tc_xoff + xi);
             const float xw = __ldg(a.tc_xw + xi);
@@ -688,19 +771,17 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               const uint32_t u2 = min(__float2uint_rz(fmaf(oz[u], gaz, gbz)), cmax2);
               const uint32_t ci = (u0 * (uint32_t)a.sdf.C1 + u1) * (uint32_t)a.sdf.C2 + u2;
               const uint32_t bit = (lds32(mask_u32 + (ci >> 5) * 4u) >> (ci & 31u)) & 1u;
-              m1 |= (pv[u] >= 0 ? bit : 0u) << u;
+              m1 |= ((pv[u] >= 0 && n_ok) ? bit : 0u) << u;
             }
-            if (m1) {                                    // rare: level 2 (2^3-cell bits, global), then the exact sample
+            if (__any_sync(0xffffffffu, m1 != 0u)) {     // queue the flagged (vertex, body) pairs; resolve them 32 at a time
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                if (m1 & (1u << u)) {
-                  const float s8 = (float)(1 << (kCoarseShift - 1));
-                  const uint32_t f0 = min(__float2uint_rz(fmaf(ox[u], gax, gbx) * s8), (dmax0 >> 1));
-                  const uint32_t f1 = min(__float2uint_rz(fmaf(oy[u], gay, gby) * s8), (dmax1 >> 1));
-                  const uint32_t f2 = min(__float2uint_rz(fmaf(oz[u], gaz, gbz) * s8), (dmax2 >> 1));
-                  const uint32_t fi = (f0 * fd1 + f1) * fd2 + f2;
-                  if ((__ldg(a.sdf.fine_bits + (fi >> 5)) >> (fi & 31u)) & 1u)
-                    cnt += sdf_exact_negative(a.sdf.grid, a.sdf.D0, a.sdf.D1, a.sdf.D2, cx, cy, cz, sc, ox[u], oy[u], oz[u]) ? 1 : 0;
+                const bool f = (m1 >> u) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                if (m) {
+                  if (f) sts128(qbase + (uint32_t)(n1 + __popc(m & lt_mask)) * 16u, make_float4(ox[u], oy[u], oz[u], n_bits));
+                  n1 += __popc(m);
+                  if (n1 >= 32) drain1(false);
                 }
               }
             }
@@ -721,14 +802,27 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           }
         }
       }
+      PROF_ADD(16 + warp - 4);
+#if EG_LBS_PROF
+      if (tid == 128) { atomicAdd(&g_lbs_prof_vt[vt & 511], (unsigned long long)(clock64() - _pt0)); g_lbs_prof[blockIdx.x][30] += 1; }
+#endif
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) { mbar_arrive(&tmem_empty[buf]); mbar_arrive(&tab_empty[tb]); }   // both buffers of this tile are free
       if (FUSE_SDF && n_ok && cnt > 0) atomicAdd(a.counts + n, cnt);
     }
+    if (FUSE_SDF) { drain1(true); drain2(true); }
   }
+#if EG_LBS_PROF
+  if (lane == 0 && warp >= 4) g_lbs_prof[blockIdx.x][28] = max(g_lbs_prof[blockIdx.x][28], gtimer());   // (racy max: debug only)
+  if (tid == 0) g_lbs_prof[blockIdx.x][29] = gtimer();
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();                     // no CTA leaves while its peer may still multicast into it
+  if (tid == 96) {                        // the scheduler lane: the last CTA to finish re-arms the ticket counter
+    __threadfence();
+    if (atomicInc(a.tile_sched + 1, gridDim.x - 1) == gridDim.x - 1) a.tile_sched[0] = 0u;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -1111,8 +1205,12 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
       const int n_btp = (n_bt + tc::CLUSTER - 1) / tc::CLUSTER;
       const int grid_tc = tc::CLUSTER * std::min(n_vt * n_btp, h->max_clusters);
       prof_begin(st, N);
-      if (fuse) EG_LAUNCH(lbs_verts_tc_kernel<true>, grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
-      else EG_LAUNCH(lbs_verts_tc_kernel<false>, grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
+      a.tile_sched = h->tile_sched;
+      const bool xw = s.nnz > 4;
+      if (fuse && xw) EG_LAUNCH((lbs_verts_tc_kernel<true, true>), grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
+      else if (fuse) EG_LAUNCH((lbs_verts_tc_kernel<true, false>), grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
+      else if (xw) EG_LAUNCH((lbs_verts_tc_kernel<false, true>), grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
+      else EG_LAUNCH((lbs_verts_tc_kernel<false, false>), grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA, mapB, a, n_vt, n_bt);
       prof_end(st);
     } else if (fuse) {
       prof_begin(st, N);
@@ -1174,7 +1272,7 @@ static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int3
         cur.clear(); joints.clear(); add.clear();
         for (int k = 0; k < cnt(v); ++k) { int j; float w; jw(v, k, j, w); add.push_back(j); }
       }
-      if ((int)add.size() > tc::NJ_MAX) return set_error(EG_ERR_INVALID_ARG, "a vertex has more skinning joints than the tensor-core tile table holds (10)");
+      if ((int)add.size() > tc::NJ_MAX) return set_error(EG_ERR_INVALID_ARG, "a vertex has more skinning joints than the tensor-core tile table holds (9)");
       joints.insert(joints.end(), add.begin(), add.end());
       cur.push_back(v);
     }
@@ -1316,8 +1414,10 @@ extern "C" int eg_lbs_create(const EgLbsModel* m, int device, EgLbs** out) {
   EG_CUDA_CHECK(cudaSetDevice(device));
   EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VERT_SMEM));
   EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VERT_SMEM));
-  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  EG_CUDA_CHECK(cudaFuncSetAttribute(lbs_verts_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
   EgLbs* h = new EgLbs();
   h->device = device;
   {
@@ -1328,12 +1428,14 @@ extern "C" int eg_lbs_create(const EgLbsModel* m, int device, EgLbs** out) {
     at.val.clusterDim.x = tc::CLUSTER; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, lbs_verts_tc_kernel<true>, &cfg) == cudaSuccess && nc > 0)
+    if (cudaOccupancyMaxActiveClusters(&nc, lbs_verts_tc_kernel<true, true>, &cfg) == cudaSuccess && nc > 0)
       h->max_clusters = std::min(nc, kNumSMs / tc::CLUSTER);
     else {
       cudaGetLastError();
       h->max_clusters = tc::CLUSTER == 1 ? kNumSMs : 64;
     }
+    EG_CUDA_CHECK(cudaMalloc((void**)&h->tile_sched, 2 * sizeof(unsigned int)));
+    EG_CUDA_CHECK(cudaMemset(h->tile_sched, 0, 2 * sizeof(unsigned int)));
   }
   {
     cudaDriverEntryPointQueryResult qres;
@@ -1440,6 +1542,7 @@ extern "C" void eg_lbs_destroy(EgLbs* h) {
   cudaFree(h->Jt); cudaFree(h->Js); cudaFree(h->hand_l); cudaFree(h->hand_r); cudaFree(h->pose_mean);
   cudaFree(h->parents); cudaFree(h->level_joints); cudaFree(h->level_start); cudaFree(h->lmk_bary);
   cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc); cudaFree(h->Aw); cudaFree(h->rec_call);
+  cudaFree(h->tile_sched);
   delete h;
 }
 
@@ -1509,3 +1612,17 @@ extern "C" int eg_lbs_set_mainloop(EgLbs* h, int use_tcgen05) {
   h->use_tc = use_tcgen05 ? 1 : 0;
   return EG_OK;
 }
+
+#if EG_LBS_PROF
+extern "C" int eg_lbs_prof_dump(unsigned long long* host_cta, unsigned long long* host_vt, int zero) {
+  using namespace eg;
+  cudaDeviceSynchronize();
+  if (host_cta) cudaMemcpyFromSymbol(host_cta, g_lbs_prof, sizeof(g_lbs_prof));
+  if (host_vt) cudaMemcpyFromSymbol(host_vt, g_lbs_prof_vt, sizeof(g_lbs_prof_vt));
+  if (zero) {
+    void* p; cudaGetSymbolAddress(&p, g_lbs_prof); cudaMemset(p, 0, sizeof(g_lbs_prof));
+    cudaGetSymbolAddress(&p, g_lbs_prof_vt); cudaMemset(p, 0, sizeof(g_lbs_prof_vt));
+  }
+  return 0;
+}
+#endif

@@ -12,18 +12,25 @@
 //            the JOINT-COHERENT vertex order built by eg_lbs_create (vertices sorted by their skinning-joint
 //            tuple, tiles closed at 80 vertices or NJ_MAX distinct joints).
 // Per CTA (persistent, 1 per SM): warp 0 = operand producer (TMA ring), warp 1 = MMA issuer (+TMEM alloc), warp 2 =
-// table producer (bulk copies of the tile's joint-transform table and vertex records), warps 4..11 = epilogue.
+// table producer (bulk copies of the tile's joint-transform table and vertex records), warp 3 = tile scheduler (first
+// tile = blockIdx, then tickets from a device counter, published to the other roles through a 4-slot ring - vertex
+// tiles differ 4x in epilogue cost, so a static round-robin left a 50 us tail), warps 4..11 = epilogue.
 // CTAs run as CLUSTERS OF 2 on the same vertex tile and adjacent body tiles: each CTA loads half of every basis tile
 // and multicasts it to both, so the basis (the bulk of the L2->SM traffic) crosses the fabric once per pair.
 // TMEM: TWO accumulator sets of 3 x 80 fp32 columns, so the MMA of tile i+1 runs under the epilogue of tile i.
-// smem: ring of 2 stages x (3 basis tiles 80x64 + 1 feature tile 128x64 fp16, SWIZZLE_128B) = 92 KB, two 60 KB tables
-// with the transforms of the tile's <= 10 joints for its 128 bodies (joint-major in HBM, so one 6 KB bulk copy per
-// joint), two 3.75 KB record buffers, 4 KB of SDF coarse-cell sign bits.
+// smem: ring of 2 stages x (3 basis tiles 80x64 + 1 feature tile 128x64 fp16, SWIZZLE_128B) = 92 KB, two 54 KB tables
+// with the transforms of the tile's <= 9 joints for its 128 bodies (joint-major in HBM, so one 6 KB bulk copy per
+// joint), two 3.75 KB record buffers, 4 KB of SDF coarse-cell sign bits, 12 KB of per-warp SDF work queues.
 // Epilogue thread = one BODY (its TMEM lane): it walks the tile's vertices, keeps the four skinning-slot transforms
 // of ITS body in registers and reloads a slot from the table only when the (warp-uniform) joint of that slot
 // changes between consecutive vertices - runs of vertices that share joints cost no shared-memory traffic at all,
-// where the vertex-per-lane form needed 12 ld.shared.v4 per (vertex, body). Penetration counts accumulate in a
-// register per body (one atomic per thread and tile).
+// where the vertex-per-lane form needed 12 ld.shared.v4 per (vertex, body).
+// Fused SDF: the 8^3-cell sign bit (smem) is tested inline; a (vertex, body) whose cell may hold a negative sample is
+// COMPACTED into the warp's shared-memory queue {x, y, z, body} instead of being resolved on the spot (a lane = a
+// body, so on the spot one flagged body dragged the other 31 through the 2^3-cell lookup and the 8-corner sample:
+// 11 and 9 of 32 lanes were active there and it was half of the epilogue's time). Whenever 32 entries are queued the
+// warp resolves them with every lane busy: stage 1 = 2^3-cell bit (global), survivors re-queued; stage 2 = the exact
+// trilinear sample, one atomic per negative sample. Queues persist across tiles and are drained at the end.
 #pragma once
 #include <cuda.h>
 
@@ -51,18 +58,23 @@ constexpr int EPI_SUB = 2;                       // epilogue warps per TMEM lane
 constexpr int EPI_WARPS = 4 * EPI_SUB;
 constexpr int THREADS = 128 + EPI_WARPS * 32;   // 384
 constexpr int VPW = TV / EPI_SUB;                // vertices per epilogue warp and tile
-constexpr int NJ_MAX = 10;                       // distinct skinning joints per vertex tile (tiles are closed earlier otherwise)
+constexpr int NJ_MAX = 9;                        // distinct skinning joints per vertex tile (tiles are closed earlier otherwise)
 constexpr int SLOT_BYTES = TB * 48;              // one joint's transforms for the tile's 128 bodies
 constexpr int TAB_BYTES = NJ_MAX * SLOT_BYTES;   // 60 KB
 constexpr int REC_BYTES = TV * 48;               // the tile's per-vertex records
 constexpr int NTAB = 2;                          // table / record buffers
 constexpr int MASK_WORDS = 1024;                 // coarse-cell sign bits of the SDF grid (32^3 cells for a 256^3 grid)
+constexpr int QCAP = 96;                         // entries of one epilogue warp's SDF queue pair (stage 1 grows up, stage 2 grows down)
+constexpr int Q_BYTES = QCAP * 16;
+constexpr int NSCHED = 4;                        // tile-scheduler ring slots
 constexpr int BAR_BYTES = 256;
 constexpr int OFF_BARS = STAGES * STAGE_BYTES;
 constexpr int OFF_TAB = OFF_BARS + BAR_BYTES;
 constexpr int OFF_REC = OFF_TAB + NTAB * TAB_BYTES;
 constexpr int OFF_MASK = OFF_REC + NTAB * REC_BYTES;
-constexpr int SMEM_BYTES = OFF_MASK + MASK_WORDS * 4 + 1024 /*align slack*/;
+constexpr int OFF_Q = OFF_MASK + MASK_WORDS * 4;
+constexpr int SMEM_BYTES = OFF_Q + EPI_WARPS * Q_BYTES + 1024 /*align slack*/;
+static_assert((2 * STAGES + 8 + 2 * NSCHED) * 8 + 4 + NSCHED * 4 <= BAR_BYTES, "barrier block");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(HALF_ROWS * CLUSTER == TV && HALF_BYTES % 1024 == 0, "multicast split");
 static_assert(VPW % 4 == 0 && STAGE_BYTES % 1024 == 0 && V_TILE_BYTES % 1024 == 0, "tile geometry");
@@ -87,6 +99,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
+}
+// for the single-lane producer roles, which run far ahead of their consumers: do not fight the epilogue warps of the
+// same scheduler for issue slots while waiting
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
