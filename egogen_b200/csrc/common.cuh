@@ -106,6 +106,10 @@ struct SdfGrid {
   const uint32_t* coarse_bits = nullptr;   // 1 bit per coarse cell (coarse <= 0), n_bit_words words
   int n_bit_words = 0;
   const uint32_t* fine_bits = nullptr;     // same for 2^3 cells ([ceil(D/2)]^3 bits, dilated), global memory
+  // exact per-cell class of the trilinear sample's sign, one bit pair per fine cell (x0, y0, z0) = floor of the sample
+  // index, 32 cells per uint2: .x bit = every in-range corner of the cell is > 0 (the sample IS a penetration),
+  // .y bit = corners of both signs / zero / tiny (the sample must be evaluated); neither = no corner is > 0 (never)
+  const uint2* cell_class = nullptr;
 };
 constexpr int kCoarseShift = 3;
 

@@ -450,7 +450,7 @@ lbs_verts_kernel(const VertArgs a) {
 #endif
 #if EG_LBS_PROF
 // per-CTA stall accounting of the tc kernel (debug builds only: EG_NVCC_EXTRA=-DEG_LBS_PROF=1; read with eg_lbs_prof_dump)
-__device__ unsigned long long g_lbs_prof[160][32];
+__device__ unsigned long long g_lbs_prof[160][48];
 __device__ unsigned long long g_lbs_prof_vt[512];     // epilogue work clocks of warp 4, summed per vertex tile
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define PROF_T0() const long long _pt0 = clock64()
@@ -565,20 +565,19 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       for (int ch = 0; ch < NCHUNK; ++ch) {
         { PROF_T0(); mbar_wait(&full_bar[stage], phase); PROF_ADD(25); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        PROF_T0();
         if (lane == 0) {
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           const uint64_t df = make_desc(sbase + 3 * V_TILE_BYTES);
+          const uint64_t dbs = make_desc(sbase);            // x, y, z basis tiles = one 240-row tile -> columns c * TV + v
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const uint64_t dbs = make_desc(sbase + c * V_TILE_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < BKT / UMMA_K; ++kk)     // UMMA_K = 16 fp16: advance 32 B inside the swizzle atom
-              umma_f16(tmem_base + buf * ACC_COLS + c * TV, df + (uint64_t)(kk * 2), dbs + (uint64_t)(kk * 2), (ch | kk) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < BKT / UMMA_K; ++kk)       // UMMA_K = 16 fp16: advance 32 B inside the swizzle atom
+            umma_f16(tmem_base + buf * ACC_COLS, df + (uint64_t)(kk * 2), dbs + (uint64_t)(kk * 2), (ch | kk) ? 1u : 0u);
           umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CLUSTER) - 1u));   // frees the slot in BOTH CTAs' rings
           if (ch == NCHUNK - 1) umma_commit(&tmem_full[buf]);   // accumulators complete
         }
         __syncwarp();
+        PROF_ADD(32);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -605,8 +604,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // corner (eg_sdf_prepare), which covers the rounding difference to the exact index sequence.
     float cx = 0.f, cy = 0.f, cz = 0.f, sc = 0.f, gax = 0.f, gay = 0.f, gaz = 0.f, gbx = 0.f, gby = 0.f, gbz = 0.f;
     const uint32_t mask_u32 = smem_base + OFF_MASK;
-    const bool smem_mask = FUSE_SDF && a.sdf.coarse_bits != nullptr && a.sdf.fine_bits != nullptr && a.sdf.n_bit_words <= MASK_WORDS;
-    const uint32_t fd1 = (uint32_t)((a.sdf.D1 + 1) / 2), fd2 = (uint32_t)((a.sdf.D2 + 1) / 2);
+    const bool smem_mask = FUSE_SDF && a.sdf.coarse_bits != nullptr && a.sdf.cell_class != nullptr && a.sdf.n_bit_words <= MASK_WORDS;
     if (FUSE_SDF) {
       cx = __ldg(a.sdf.center); cy = __ldg(a.sdf.center + 1); cz = __ldg(a.sdf.center + 2);
       sc = __ldg(a.sdf.scale);
@@ -620,47 +618,66 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         for (int i = eidx; i < a.sdf.n_bit_words; i += NEPI) mk[i] = __ldg(a.sdf.coarse_bits + i);
       }
     }
+    // level-1 cell index without F2I (a quarter-rate pipe, 12 per vertex group): s = sat((x' - 0.5) / Nx) with x' the
+    // coordinate in 8^3-cell units and Nx = C - 0.51, then s * Nx + 1.5 * 2^23 rounds to the integer cell in the low
+    // mantissa bits: round-to-nearest of x' - 0.5 is floor(x') except on exact cell boundaries (either neighbour; the
+    // bit grid's one-corner dilation covers both), s = 1 lands on the last cell, s = 0 on the first.
+    constexpr float kMagic = 12582912.0f;                           // bits 0x4B400000
+    float nn0 = (float)a.sdf.C0 - 0.51f, nn1 = (float)a.sdf.C1 - 0.51f, nn2 = (float)a.sdf.C2 - 0.51f;
+    float na0 = gax / nn0, nb0 = (gbx - 0.5f) / nn0, na1 = gay / nn1, nb1 = (gby - 0.5f) / nn1, na2 = gaz / nn2, nb2 = (gbz - 0.5f) / nn2;
+    const uint32_t kc = 0x4B400000u * ((uint32_t)a.sdf.C1 * (uint32_t)a.sdf.C2 + (uint32_t)a.sdf.C2 + 1u);
+    // keep the nine constants in registers (ptxas otherwise re-derives them from the kernel parameters in every group)
+    asm volatile("" : "+f"(na0), "+f"(nb0), "+f"(nn0), "+f"(na1), "+f"(nb1), "+f"(nn1), "+f"(na2), "+f"(nb2), "+f"(nn2));
     asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");         // sign bits visible to every epilogue warp
-    const uint32_t dmax0 = (uint32_t)(a.sdf.D0 - 1), dmax1 = (uint32_t)(a.sdf.D1 - 1), dmax2 = (uint32_t)(a.sdf.D2 - 1);
-    const uint32_t cmax0 = (uint32_t)(a.sdf.C0 - 1), cmax1 = (uint32_t)(a.sdf.C1 - 1), cmax2 = (uint32_t)(a.sdf.C2 - 1);
     // SDF work queues of this warp (see lbs_tc.cuh): entry = {world x, y, z, body}; stage 1 is a stack growing up from
     // entry 0, stage 2 a stack growing down from entry QCAP-1; n1 + n2 <= 63 + 31 at any time
     const uint32_t qbase = smem_base + OFF_Q + (uint32_t)(warp - 4) * Q_BYTES;
     const uint32_t lt_mask = (1u << lane) - 1u;
     int n1 = 0, n2 = 0;                                             // warp-uniform
-    auto drain2 = [&](bool final) {
-      while (n2 >= 32 || (final && n2 > 0)) {
-        __syncwarp();
-        const int take = min(n2, 32);
-        n2 -= take;
-        if (lane < take) {
-          const float4 e = lds128(qbase + (uint32_t)(QCAP - 1 - (n2 + lane)) * 16u);
-          if (sdf_exact_negative(a.sdf.grid, a.sdf.D0, a.sdf.D1, a.sdf.D2, cx, cy, cz, sc, e.x, e.y, e.z))
-            atomicAdd(a.counts + __float_as_int(e.w), 1);
-        }
-        __syncwarp();
+    // one batch (<= 32 entries) of stage 2: the exact trilinear sample, one atomic per negative sample
+    auto drain2_batch = [&]() {
+      __syncwarp();
+      const int take = min(n2, 32);
+      n2 -= take;
+      if (lane < take) {
+        const float4 e = lds128(qbase + (uint32_t)(QCAP - 1 - (n2 + lane)) * 16u);
+        if (sdf_exact_negative(a.sdf.grid, a.sdf.D0, a.sdf.D1, a.sdf.D2, cx, cy, cz, sc, e.x, e.y, e.z))
+          atomicAdd(a.counts + __float_as_int(e.w), 1);
       }
+      __syncwarp();
     };
-    auto drain1 = [&](bool final) {
-      while (n1 >= 32 || (final && n1 > 0)) {
-        __syncwarp();
-        const int take = min(n1, 32);
-        n1 -= take;
-        bool pass = false;
-        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < take) {
-          e = lds128(qbase + (uint32_t)(n1 + lane) * 16u);
-          const float s8 = (float)(1 << (kCoarseShift - 1));
-          const uint32_t f0 = min(__float2uint_rz(fmaf(e.x, gax, gbx) * s8), (dmax0 >> 1));
-          const uint32_t f1 = min(__float2uint_rz(fmaf(e.y, gay, gby) * s8), (dmax1 >> 1));
-          const uint32_t f2 = min(__float2uint_rz(fmaf(e.z, gaz, gbz) * s8), (dmax2 >> 1));
-          const uint32_t fi = (f0 * fd1 + f1) * fd2 + f2;
-          pass = ((__ldg(a.sdf.fine_bits + (fi >> 5)) >> (fi & 31u)) & 1u) != 0u;
+    // one batch of stage 1: the exact class of the sample's cell (same index sequence as the sampler, one 8-byte load):
+    // every corner > 0 -> counted here, no corner > 0 -> dropped, corners of both signs -> stage 2, which is drained
+    // when it holds a full batch
+    auto drain1_batch = [&]() {
+      __syncwarp();
+      const int take = min(n1, 32);
+      n1 -= take;
+      bool pass = false;
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < take) {
+        e = lds128(qbase + (uint32_t)(n1 + lane) * 16u);
+        const int x0 = (int)floorf(sdf_unnormalize(__fmul_rn(__fsub_rn(e.x, cx), sc), a.sdf.D0));
+        const int y0 = (int)floorf(sdf_unnormalize(__fmul_rn(__fsub_rn(e.y, cy), sc), a.sdf.D1));
+        const int z0 = (int)floorf(sdf_unnormalize(__fmul_rn(__fsub_rn(e.z, cz), sc), a.sdf.D2));
+        const uint32_t ci = ((uint32_t)x0 * (uint32_t)a.sdf.D1 + (uint32_t)y0) * (uint32_t)a.sdf.D2 + (uint32_t)z0;
+        const uint2 cl = __ldg(a.sdf.cell_class + (ci >> 5));
+        pass = ((cl.y >> (ci & 31u)) & 1u) != 0u;
+        if ((cl.x >> (ci & 31u)) & 1u) atomicAdd(a.counts + __float_as_int(e.w), 1);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (pass) sts128(qbase + (uint32_t)(QCAP - 1 - (n2 + __popc(m & lt_mask))) * 16u, e);
+      n2 += __popc(m);
+      while (n2 >= 32) drain2_batch();
+    };
+    // wait for a tile buffer; a warp that is ahead of its CTA resolves queued SDF work (partial batches too) instead of
+    // spinning, so the forced drains inside the vertex walk - the main source of skew between the warps - become rare
+    auto wait_busy = [&](uint64_t* bar, uint32_t parity) {
+      while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (FUSE_SDF) {
+          if (n2 > 0) drain2_batch();
+          else if (n1 > 0) drain1_batch();
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (pass) sts128(qbase + (uint32_t)(QCAP - 1 - (n2 + __popc(m & lt_mask))) * 16u, e);
-        n2 += __popc(m);
-        drain2(false);
       }
     };
     uint32_t it = 0;
@@ -684,8 +701,8 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
         for (int e = 0; e < 6; ++e) C[k][e] = make_float2(0.f, 0.f);
       const int vbase = vt * TV + sub * VPW;
-      { PROF_T0(); mbar_wait(&tab_full[tb], tph); PROF_ADD(warp - 4); }          // table + records landed
-      { PROF_T0(); mbar_wait(&tmem_full[buf], ph); PROF_ADD(8 + warp - 4); }     // accumulators complete
+      { PROF_T0(); wait_busy(&tab_full[tb], tph); PROF_ADD(warp - 4); }          // table + records landed
+      { PROF_T0(); wait_busy(&tmem_full[buf], ph); PROF_ADD(8 + warp - 4); }     // accumulators complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       PROF_T0();
 #pragma unroll 1
@@ -766,10 +783,10 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             uint32_t m1 = 0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const uint32_t u0 = min(__float2uint_rz(fmaf(ox[u], gax, gbx)), cmax0);
-              const uint32_t u1 = min(__float2uint_rz(fmaf(oy[u], gay, gby)), cmax1);
-              const uint32_t u2 = min(__float2uint_rz(fmaf(oz[u], gaz, gbz)), cmax2);
-              const uint32_t ci = (u0 * (uint32_t)a.sdf.C1 + u1) * (uint32_t)a.sdf.C2 + u2;
+              const uint32_t u0 = __float_as_uint(fmaf(__saturatef(fmaf(ox[u], na0, nb0)), nn0, kMagic));
+              const uint32_t u1 = __float_as_uint(fmaf(__saturatef(fmaf(oy[u], na1, nb1)), nn1, kMagic));
+              const uint32_t u2 = __float_as_uint(fmaf(__saturatef(fmaf(oz[u], na2, nb2)), nn2, kMagic));
+              const uint32_t ci = (u0 * (uint32_t)a.sdf.C1 + u1) * (uint32_t)a.sdf.C2 + u2 - kc;
               const uint32_t bit = (lds32(mask_u32 + (ci >> 5) * 4u) >> (ci & 31u)) & 1u;
               m1 |= ((pv[u] >= 0 && n_ok) ? bit : 0u) << u;
             }
@@ -781,7 +798,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 if (m) {
                   if (f) sts128(qbase + (uint32_t)(n1 + __popc(m & lt_mask)) * 16u, make_float4(ox[u], oy[u], oz[u], n_bits));
                   n1 += __popc(m);
-                  if (n1 >= 32) drain1(false);
+                  while (n1 >= 32) drain1_batch();
                 }
               }
             }
@@ -811,7 +828,10 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (lane == 0) { mbar_arrive(&tmem_empty[buf]); mbar_arrive(&tab_empty[tb]); }   // both buffers of this tile are free
       if (FUSE_SDF && n_ok && cnt > 0) atomicAdd(a.counts + n, cnt);
     }
-    if (FUSE_SDF) { drain1(true); drain2(true); }
+    if (FUSE_SDF) {
+      while (n1 > 0) drain1_batch();
+      while (n2 > 0) drain2_batch();
+    }
   }
 #if EG_LBS_PROF
   if (lane == 0 && warp >= 4) g_lbs_prof[blockIdx.x][28] = max(g_lbs_prof[blockIdx.x][28], gtimer());   // (racy max: debug only)

@@ -154,7 +154,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // cute::UMMA::InstrDescriptor for kind::f16 with fp16 A and B (a_format = b_format = 0), fp32 accumulate (c_format = 1),
 // K-major A and B, M = TB, N = TV
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TV >> 3) << 17) | ((uint32_t)(TB >> 4) << 24);
+// K-major A and B, M = TB, N = 3 * TV: the three component tiles of a stage are contiguous 80-row groups of one
+// 240-row K-major tile, so ONE UMMA per k-step feeds all three accumulators and the feature tile (A) is fetched from
+// shared memory once instead of three times (at N = 80 the operand fetch, 6.5 KB per 40-clock MMA, outran the 128 B/clk
+// shared-memory port; at N = 240 it is 11.5 KB per 120 clocks)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)((3 * TV) >> 3) << 17) | ((uint32_t)(TB >> 4) << 24);
+static_assert((3 * TV) % 16 == 0 && 3 * TV <= 256, "UMMA N");
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
   asm volatile(

@@ -124,6 +124,33 @@ __global__ void sdf_coarse_bits_kernel(const float* __restrict__ coarse, int n, 
   if ((threadIdx.x & 31) == 0 && i < ((n + 31) / 32) * 32) bits[i >> 5] = m;
 }
 
+// class of every fine cell (see SdfGrid::cell_class). The sample is sum_i w_i g_i over the cell's in-range corners with
+// w_i >= 0: all g_i > 0 (and not so tiny that a product could round to zero) => sample > 0; no g_i > 0 => sample <= 0.
+__global__ void __launch_bounds__(256)
+sdf_cell_class_kernel(const float* __restrict__ grid, int D0, int D1, int D2, int64_t n, uint2* __restrict__ cls) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool all_pos = false, mixed = false;
+  if (i < n) {
+    const int z = (int)(i % D2), y = (int)((i / D2) % D1), x = (int)(i / ((int64_t)D1 * D2));
+    int n_pos = 0, n_big = 0, n_c = 0;
+    bool bad = false;
+    for (int dx = 0; dx <= 1; ++dx)
+      for (int dy = 0; dy <= 1; ++dy)
+        for (int dz = 0; dz <= 1; ++dz) {
+          if (x + dx > D0 - 1 || y + dy > D1 - 1 || z + dz > D2 - 1) continue;
+          const float g = grid[((int64_t)(x + dx) * D1 + (y + dy)) * D2 + (z + dz)];
+          ++n_c;
+          if (!(g == g) || fabsf(g) > 1e30f) bad = true;
+          if (g > 0.0f) ++n_pos;
+          if (g > 1e-20f) ++n_big;
+        }
+    all_pos = !bad && n_big == n_c;
+    mixed = bad || (n_pos > 0 && !all_pos);
+  }
+  const unsigned mp = __ballot_sync(0xffffffffu, all_pos), mm = __ballot_sync(0xffffffffu, mixed);
+  if ((threadIdx.x & 31) == 0 && i < (n + 31) / 32 * 32) cls[i >> 5] = make_uint2(mp, mm);
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t b = (n + block - 1) / block;
   const int64_t cap = (int64_t)kNumSMs * 16;  // multiple of the SM count, grid-stride beyond
@@ -138,7 +165,7 @@ static inline int grid_for(int64_t n, int block) {
 #include <map>
 #include <mutex>
 namespace eg {
-struct CoarseEntry { float* coarse; int D0, D1, D2, C0, C1, C2; uint32_t* fine_bits = nullptr; };
+struct CoarseEntry { float* coarse; int D0, D1, D2, C0, C1, C2; uint32_t* fine_bits = nullptr; uint2* cell_class = nullptr; };
 static std::map<const float*, CoarseEntry> g_coarse;
 static std::mutex g_coarse_mu;
 void sdf_attach_coarse(SdfGrid& g) {
@@ -150,6 +177,7 @@ void sdf_attach_coarse(SdfGrid& g) {
   g.coarse_bits = reinterpret_cast<const uint32_t*>(it->second.coarse + (n + 31) / 32 * 32);
   g.n_bit_words = (n + 31) / 32;
   g.fine_bits = it->second.fine_bits;
+  g.cell_class = it->second.cell_class;
 }
 }  // namespace eg
 
@@ -162,7 +190,7 @@ extern "C" int eg_sdf_prepare(const float* grid, int D0, int D1, int D2, void* s
   {
     std::lock_guard<std::mutex> lk(g_coarse_mu);
     auto it = g_coarse.find(grid);
-    if (it != g_coarse.end()) { cudaFree(it->second.coarse); cudaFree(it->second.fine_bits); g_coarse.erase(it); }
+    if (it != g_coarse.end()) { cudaFree(it->second.coarse); cudaFree(it->second.fine_bits); cudaFree(it->second.cell_class); g_coarse.erase(it); }
   }
   const int n = e.C0 * e.C1 * e.C2;
   const int n32 = (n + 31) / 32 * 32;                     // floats, then one bit per cell
@@ -184,6 +212,9 @@ extern "C" int eg_sdf_prepare(const float* grid, int D0, int D1, int D2, void* s
     EG_LAUNCH(sdf_coarse_bits_kernel, (int)(nf32 / 128 + 1), 128, 0, as_stream(stream), dil, (int)nf, e.fine_bits);
     EG_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
     cudaFree(dil);
+    const int64_t nc = (int64_t)D0 * D1 * D2, nc32 = (nc + 31) / 32;
+    EG_CUDA_CHECK(cudaMalloc((void**)&e.cell_class, (size_t)nc32 * sizeof(uint2)));
+    EG_LAUNCH(sdf_cell_class_kernel, (int)((nc32 * 32 + 255) / 256), 256, 0, as_stream(stream), grid, D0, D1, D2, nc, e.cell_class);
   }
   EG_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
   std::lock_guard<std::mutex> lk(g_coarse_mu);
@@ -194,7 +225,7 @@ extern "C" int eg_sdf_prepare(const float* grid, int D0, int D1, int D2, void* s
 extern "C" int eg_sdf_release(const float* grid) {
   std::lock_guard<std::mutex> lk(g_coarse_mu);
   auto it = g_coarse.find(grid);
-  if (it != g_coarse.end()) { cudaFree(it->second.coarse); cudaFree(it->second.fine_bits); g_coarse.erase(it); }
+  if (it != g_coarse.end()) { cudaFree(it->second.coarse); cudaFree(it->second.fine_bits); cudaFree(it->second.cell_class); g_coarse.erase(it); }
   return EG_OK;
 }
 

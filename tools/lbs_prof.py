@@ -18,7 +18,7 @@ pol.train(); col.reset()
 lib = _lib.lib()
 for _ in range(3):
     col.collect(1024)
-cta = np.zeros((160, 32), dtype=np.uint64); vt = np.zeros(512, dtype=np.uint64)
+cta = np.zeros((160, 48), dtype=np.uint64); vt = np.zeros(512, dtype=np.uint64)
 lib.eg_lbs_prof_dump(None, None, 1)
 K = 4
 for _ in range(K):
@@ -37,6 +37,7 @@ for wi in range(8):
     row(f"   warp {wi + 4} work", cta[:, 16 + wi])
 row("mma wait accumulator-free", cta[:, 24])
 row("mma wait operands", cta[:, 25])
+row("mma issue block", cta[:, 32])
 row("producer wait ring slot", cta[:, 26])
 row("table producer wait buffer", cta[:, 27])
 print("tiles per CTA per launch: mean %.1f min %.0f max %.0f" % ((cta[:, 30] / L).mean(), (cta[:, 30] / L).min(), (cta[:, 30] / L).max()))
