@@ -20,6 +20,8 @@
 // sample + penetration count so vertices never reach HBM) -> lbs_finish_kernel (127 joints,
 // markers). The same vertex kernel runs on the full mesh and on a compact gathered vertex set
 // (markers + vertex joints + landmark corners) for the joints-only calls.
+#include <stdlib.h>
+
 #include <vector>
 #include <algorithm>
 
@@ -69,6 +71,9 @@ struct EgLbs {
   eg::VertexSet full, compact;
   // host copies needed to (re)build the compact set
   std::vector<int32_t> h_extra, h_lmk_verts;
+  std::vector<int32_t> h_sidx;          // [nnz][full.n_pad] skinning joints / weights / template of the full mesh (host)
+  std::vector<float> h_sw, h_vt;
+  std::vector<int32_t> h_row_of_vertex; // tc row of every mesh vertex in the full set's joint-coherent order
   // workspace
   int cap_N = 0;
   float *Ft = nullptr, *A = nullptr, *Jp = nullptr, *cout_ = nullptr;
@@ -80,7 +85,8 @@ struct EgLbs {
   unsigned int* tile_sched = nullptr;   // {ticket, finished} counters of the tcgen05 kernel's tile scheduler
   int max_clusters = 64;      // co-resident 2-CTA clusters of the tcgen05 kernel (cudaOccupancyMaxActiveClusters)
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
-  CUtensorMap mapA;
+  CUtensorMap mapA, mapA_c;   // K-major basis of the full / compact set
+  float* Al = nullptr;        // [J][cap_Ntc][12] joint-major LOCAL transforms (fused calls: Aw is world-composed)
 };
 
 namespace eg {
@@ -103,7 +109,7 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
                      const int32_t* __restrict__ level_joints, const int32_t* __restrict__ level_start,
                      float* __restrict__ Ft, __half* __restrict__ Ftc, float* __restrict__ A,
                      float* __restrict__ Jp, const float* __restrict__ R0w, const float* __restrict__ T0w,
-                     int frames_per_env, float* __restrict__ Aw, int AwRows) {
+                     int frames_per_env, float* __restrict__ Aw, int AwRows, float* __restrict__ Al) {
   const int n = blockIdx.x;
   const int t = threadIdx.x;
   __shared__ float pose[MAXJ * 3];
@@ -262,6 +268,12 @@ lbs_pose_prep_kernel(const float* __restrict__ xb, const float* __restrict__ bet
       w_out[0] = make_float4(M[0][0], M[1][0], M[0][1], M[1][1]);
       w_out[1] = make_float4(M[0][2], M[1][2], M[0][3], M[1][3]);
       w_out[2] = make_float4(M[2][0], M[2][1], M[2][2], M[2][3]);
+    }
+    if (Al != nullptr) {                       // the same layout with the LOCAL transforms (compact set beside a fused call)
+      float4* l_out = reinterpret_cast<float4*>(Al + ((int64_t)t * AwRows + n) * 12);
+      l_out[0] = make_float4(a_out[0], a_out[4], a_out[1], a_out[5]);
+      l_out[1] = make_float4(a_out[2], a_out[6], a_out[3], a_out[7]);
+      l_out[2] = make_float4(a_out[8], a_out[9], a_out[10], a_out[11]);
     }
   }
 }
@@ -692,7 +704,7 @@ lbs_verts_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const int n = bt * TB + q * 32 + lane;
       const bool n_ok = n < a.N;
       float trx = 0.f, try_ = 0.f, trz = 0.f;
-      if (!FUSE_SDF && n_ok) { const float* x = a.xb + (int64_t)n * EG_XB_DIM; trx = __ldg(x); try_ = __ldg(x + 1); trz = __ldg(x + 2); }
+      if (!FUSE_SDF && n_ok && a.add_transl) { const float* x = a.xb + (int64_t)n * EG_XB_DIM; trx = __ldg(x); try_ = __ldg(x + 1); trz = __ldg(x + 2); }
       const float n_bits = __int_as_float(n);
       int cnt = 0;
       float2 C[4][6];                                               // register cache: slot k -> transform of MY body
@@ -1064,13 +1076,60 @@ __global__ void __launch_bounds__(128)
 lbs_finish_kernel(const float* __restrict__ Jp, const float* __restrict__ cverts,
                   const float* __restrict__ xb, const float* __restrict__ lmk_bary, int N, int J,
                   int n_markers, int n_extra, int n_lmk, int nc, float* __restrict__ joints,
-                  float* __restrict__ markers) {
+                  float* __restrict__ markers, const VertArgs ex, int exact_extra) {
   const int n = blockIdx.x;
   const float* x = xb + (int64_t)n * EG_XB_DIM;
   const float tx = x[0], ty = x[1], tz = x[2];
   const float tr[3] = {tx, ty, tz};
   const float* cv = cverts + (int64_t)n * nc * 3;
   const int n_out = J + n_extra + n_lmk;
+  // exact_extra: the compact set came from the tcgen05 tiles (fp16-rounded pose rows, ~5e-6 m). The vertex joints feed
+  // DIFFERENCES of nearby points (ego-sensing's look-at = j57 - j23 + j56 - j24 over a few cm), so they are re-evaluated
+  // here in fp32: blend over the SIMT basis of the compact set, then the 4-weight skinning of vertex_epilogue.
+  __shared__ float Fsh[KPAD];
+  __shared__ float exj[32 * 3];
+  if (exact_extra && joints) {
+    for (int k = threadIdx.x; k < KPAD; k += blockDim.x) Fsh[k] = ex.Ft[(int64_t)k * ex.Npad + n];
+    __syncthreads();
+    const int ne = min(n_extra, 32);
+    __shared__ float part[4][32 * 3];
+    {   // warp w sums k = w, w + 4, ... for every output: lanes walk 3 * ne consecutive floats of one basis row
+      const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      float acc[3] = {0.f, 0.f, 0.f};
+      const float* bp = ex.basis + (int64_t)n_markers * 3;
+#pragma unroll 4
+      for (int k = w; k < KPAD; k += 4) {
+        const float f = Fsh[k];
+        const float* row = bp + (int64_t)k * 3 * ex.n_pad;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int o = lane + 32 * q;
+          if (o < ne * 3) acc[q] += f * __ldg(row + o);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) if (lane + 32 * q < ne * 3) part[w][lane + 32 * q] = acc[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < ne * 3) {
+      const int i = threadIdx.x / 3, c = threadIdx.x % 3, v = n_markers + i;
+      exj[threadIdx.x] = ex.vt[v * 3 + c] + (((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x]);
+    }
+    __syncthreads();
+    if (threadIdx.x < ne * 3) {
+      const int i = threadIdx.x / 3, c = threadIdx.x % 3, v = n_markers + i;
+      const float px = exj[i * 3 + 0], py = exj[i * 3 + 1], pz = exj[i * 3 + 2];
+      const float4* An = reinterpret_cast<const float4*>(ex.A + (int64_t)n * ex.J * 12);
+      float T0 = 0.f, T1 = 0.f, T2 = 0.f, T3 = 0.f;
+      for (int k = 0; k < ex.nnz; ++k) {
+        const int j = ex.skin_idx[k * ex.n_pad + v];
+        const float w = ex.skin_w[k * ex.n_pad + v];
+        const float4 r = __ldg(An + j * 3 + c);
+        T0 += w * r.x; T1 += w * r.y; T2 += w * r.z; T3 += w * r.w;
+      }
+      joints[((int64_t)n * n_out + J + i) * 3 + c] = __fadd_rn(T0 * px + T1 * py + T2 * pz + T3, tr[c]);
+    }
+  }
   if (joints) {
     for (int i = threadIdx.x; i < n_out * 3; i += blockDim.x) {
       const int j = i / 3, c = i % 3;
@@ -1078,6 +1137,7 @@ lbs_finish_kernel(const float* __restrict__ Jp, const float* __restrict__ cverts
       if (j < J) {
         v = Jp[((int64_t)n * J + j) * 3 + c];
       } else if (j < J + n_extra) {
+        if (exact_extra && j - J < 32) continue;        // written above
         v = cv[(n_markers + (j - J)) * 3 + c];
       } else {
         const int l = j - J - n_extra;
@@ -1138,8 +1198,8 @@ static int ensure_workspace(EgLbs* h, int N) {
   if (N <= h->cap_N) return EG_OK;
   int cap = std::max(N, 64);
   cap = (cap + 31) / 32 * 32;
-  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc); cudaFree(h->Aw);
-  h->Ft = h->A = h->Jp = h->cout_ = h->Aw = nullptr;
+  cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc); cudaFree(h->Aw); cudaFree(h->Al);
+  h->Ft = h->A = h->Jp = h->cout_ = h->Aw = h->Al = nullptr;
   h->Ftc = nullptr;
   h->cap_N = 0;
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Ft, (size_t)KPAD * cap * sizeof(float)));
@@ -1149,6 +1209,8 @@ static int ensure_workspace(EgLbs* h, int N) {
   EG_CUDA_CHECK(cudaMemset(h->A, 0, cap128 * h->J * 12 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Aw, cap128 * h->J * 12 * sizeof(float)));
   EG_CUDA_CHECK(cudaMemset(h->Aw, 0, cap128 * h->J * 12 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMalloc((void**)&h->Al, cap128 * h->J * 12 * sizeof(float)));
+  EG_CUDA_CHECK(cudaMemset(h->Al, 0, cap128 * h->J * 12 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->Jp, (size_t)cap * h->J * 3 * sizeof(float)));
   EG_CUDA_CHECK(cudaMalloc((void**)&h->cout_, (size_t)cap * 512 * 3 * sizeof(float)));
   h->cap_Ntc = (int)cap128;
@@ -1192,10 +1254,17 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
   if (rc) return rc;
   const int Npad = h->cap_N;   // row stride of Ft (fixed per workspace so tiles never read OOB)
   const bool want_tc = h->use_tc && h->full.basisT != nullptr && (verts != nullptr || fuse);
+  // the compact set (joints / markers) rides the same tcgen05 kernel when the features of this call are already in its layout
+  // (opt-in, EG_LBS_COMPACT_TC=1: -0.28 ms per 256-env iteration, but the fp16-rounded pose rows leave ~5e-6 m on the vertex
+  // joints, which ego-sensing's look-at differences amplify past its tolerance, and re-evaluating those joints in fp32 in
+  // the finish kernel costs more than the SIMT pass it replaces - DESIGN.md section 4)
+  static const bool compact_tc_on = [] { const char* e = getenv("EG_LBS_COMPACT_TC"); return e && e[0] == '1'; }();
+  const bool compact_tc = compact_tc_on && want_tc && (joints != nullptr || markers != nullptr) && h->compact.basisT != nullptr &&
+                          h->encode_fn != nullptr;
   EG_LAUNCH(lbs_pose_prep_kernel, N, 64, 0, st, xb, betas, betas_div, N, Npad, h->J, h->S,
             h->n_levels, h->hand_l, h->hand_r, h->pose_mean, h->Jt, h->Js, h->parents,
             h->level_joints, h->level_start, h->Ft, want_tc ? h->Ftc : nullptr, h->A, h->Jp, R0, T0,
-            frames_per_env, want_tc ? h->Aw : nullptr, h->cap_Ntc);
+            frames_per_env, want_tc ? h->Aw : nullptr, h->cap_Ntc, compact_tc && fuse ? h->Al : nullptr);
   VertArgs a{};
   a.Ft = h->Ft; a.A = h->A; a.xb = xb; a.N = N; a.Npad = Npad; a.J = h->J;
   const int by = (N + TILE_B - 1) / TILE_B;
@@ -1249,24 +1318,37 @@ static int run_forward(EgLbs* h, const float* xb, const float* betas, int betas_
     c.counts = nullptr;
     c.A = h->A;                     // local-frame transforms (the fused path may have switched a.A to Aw)
     dim3 grid(s.n_pad / TILE_V, by);
+    if (compact_tc) {
+      CUtensorMap mapB;
+      int rc2 = encode_map(h, &mapB, h->Ftc, (uint64_t)h->cap_Ntc, tc::TB);
+      if (rc2) return rc2;
+      const int n_vt = s.n_vt_tc, n_bt = (N + tc::TB - 1) / tc::TB;
+      c.tc_rec = s.tc_rec; c.tc_jl = s.tc_jl; c.tc_nj = s.tc_nj; c.tc_xoff = s.tc_xoff; c.tc_xw = s.tc_xw;
+      c.n_pad_tc = s.n_pad_tc; c.A_rows = h->cap_Ntc;
+      c.A = fuse ? h->Al : h->Aw;   // joint-major local transforms
+      c.tile_sched = h->tile_sched;
+      const int grid_tc = std::min(n_vt * n_bt, h->max_clusters);
+      if (s.nnz > 4) EG_LAUNCH((lbs_verts_tc_kernel<false, true>), grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA_c, mapB, c, n_vt, n_bt);
+      else EG_LAUNCH((lbs_verts_tc_kernel<false, false>), grid_tc, tc::THREADS, tc::SMEM_BYTES, st, h->mapA_c, mapB, c, n_vt, n_bt);
+    } else
     EG_LAUNCH(lbs_verts_kernel<false>, grid, VERT_THREADS, VERT_SMEM, st, c);
+    c.A = h->A; c.Ft = h->Ft;      // fp32 operands of the exact vertex-joint pass
     EG_LAUNCH(lbs_finish_kernel, N, 128, 0, st, h->Jp, h->cout_, xb, h->lmk_bary, N, h->J,
-              h->n_markers, h->n_extra, h->n_lmk, s.n, joints, markers);
+              h->n_markers, h->n_extra, h->n_lmk, s.n, joints, markers, c, compact_tc ? 1 : 0);
   }
   return EG_OK;
 }
 
-// Joint-coherent layout of the full mesh for the tcgen05 kernel (lbs_tc.cuh): vertices sorted by their tuple of
-// skinning joints, cut into tiles of <= 128 vertices touching <= NJ_MAX distinct joints; inside a tile every vertex
-// keeps as many of its (up to 4) register slots as possible on the joint the previous vertex had there, so the
-// epilogue's per-body register cache is reloaded only where the joint really changes.
-static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int32_t>& sidx, const std::vector<float>& sw) {
-  VertexSet& s = h->full;
-  const int V = s.n, nnz = s.nnz, P = h->P, S = h->S;
-  auto jw = [&](int v, int k, int& j, float& w) { j = sidx[(size_t)k * s.n_pad + v]; w = sw[(size_t)k * s.n_pad + v]; };
-  auto cnt = [&](int v) { int c = 0; for (int k = 0; k < nnz; ++k) c += sw[(size_t)k * s.n_pad + v] != 0.0f; return c; };
-  std::vector<int> order(V);
-  for (int v = 0; v < V; ++v) order[v] = v;
+// records / joint lists / extra-weight tables of vertex set `s` for the list `items` of mesh vertex ids (the record's id
+// field is the INDEX into `items`, i.e. the output slot); perm[row] = item of tc row `row` or -1
+static int build_tc_records(EgLbs* h, VertexSet& s, const std::vector<int32_t>& items, std::vector<int>& perm) {
+  const int n_items = (int)items.size(), nnz = h->full.nnz, npf = h->full.n_pad;
+  const std::vector<int32_t>& sidx = h->h_sidx;
+  const std::vector<float>& sw = h->h_sw;
+  auto jw = [&](int it, int k, int& j, float& w) { j = sidx[(size_t)k * npf + items[it]]; w = sw[(size_t)k * npf + items[it]]; };
+  auto cnt = [&](int it) { int c = 0; for (int k = 0; k < nnz; ++k) c += sw[(size_t)k * npf + items[it]] != 0.0f; return c; };
+  std::vector<int> order(n_items);
+  for (int v = 0; v < n_items; ++v) order[v] = v;
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
     for (int k = 0; k < nnz; ++k) {
       int jx, jy; float wx, wy;
@@ -1305,7 +1387,7 @@ static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int3
   std::vector<int32_t> jl((size_t)n_vt * tc::NJ_MAX, 0), nj(n_vt, 0);
   std::vector<uint32_t> xoff((size_t)std::max(nx, 1) * n_pad, 0u);
   std::vector<float> xw((size_t)std::max(nx, 1) * n_pad, 0.0f);
-  std::vector<int> perm(n_pad, -1);
+  perm.assign(n_pad, -1);
   for (int t = 0; t < n_vt; ++t) {
     const std::vector<int>& J = tile_joints[t];
     nj[t] = (int)J.size();
@@ -1341,7 +1423,8 @@ static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int3
             ++xk;
           }
         }
-        r[0] = m->v_template[(size_t)v * 3 + 0]; r[1] = m->v_template[(size_t)v * 3 + 1]; r[2] = m->v_template[(size_t)v * 3 + 2];
+        const float* vtp = &h->h_vt[(size_t)items[v] * 3];
+        r[0] = vtp[0]; r[1] = vtp[1]; r[2] = vtp[2];
       }
       memcpy(&r[3], &id, 4);
       // bit 24+q of the first offset word: slot q differs from the previous vertex of the same epilogue warp's
@@ -1359,6 +1442,30 @@ static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int3
       }
     }
   }
+  s.n_pad_tc = n_pad; s.n_vt_tc = n_vt;
+  int rc = dev_alloc_copy(reinterpret_cast<float**>(&s.tc_rec), rec.data(), rec.size());
+  rc |= dev_alloc_copy(&s.tc_jl, jl.data(), jl.size());
+  rc |= dev_alloc_copy(&s.tc_nj, nj.data(), nj.size());
+  rc |= dev_alloc_copy(&s.tc_xoff, xoff.data(), xoff.size());
+  rc |= dev_alloc_copy(&s.tc_xw, xw.data(), xw.size());
+  return rc;
+}
+
+// Joint-coherent layout of the full mesh for the tcgen05 kernel (lbs_tc.cuh): vertices sorted by their tuple of
+// skinning joints, cut into tiles of <= 80 vertices touching <= NJ_MAX distinct joints; inside a tile every vertex
+// keeps as many of its (up to 4) register slots as possible on the joint the previous vertex had there, so the
+// epilogue's per-body register cache is reloaded only where the joint really changes.
+static int build_tc_layout(EgLbs* h, const EgLbsModel* m) {
+  VertexSet& s = h->full;
+  const int V = s.n, P = h->P, S = h->S;
+  std::vector<int32_t> items(V);
+  for (int v = 0; v < V; ++v) items[v] = v;
+  std::vector<int> perm;
+  int rc = build_tc_records(h, s, items, perm);
+  if (rc) return rc;
+  const int n_pad = s.n_pad_tc;
+  h->h_row_of_vertex.assign(V, 0);
+  for (int row = 0; row < n_pad; ++row) if (perm[row] >= 0) h->h_row_of_vertex[perm[row]] = row;
   // planar K-major fp16 copy of the basis in tc order: basisT[c][row][k]; shape rows in hi/hi, hi(again), lo form
   auto rnd = [](float x) { return __half2float(__float2half_rn(x)); };
   std::vector<__half> bt((size_t)3 * n_pad * tc::KT, __float2half_rn(0.0f));
@@ -1376,15 +1483,46 @@ static int build_tc_layout(EgLbs* h, const EgLbsModel* m, const std::vector<int3
         dst[P + 2 * S + k] = __float2half_rn(p - hi);   // x shape_hi
       }
     }
-  s.n_pad_tc = n_pad; s.n_vt_tc = n_vt;
-  int rc = dev_alloc_copy(&s.basisT, bt.data(), bt.size());
-  rc |= dev_alloc_copy(reinterpret_cast<float**>(&s.tc_rec), rec.data(), rec.size());
-  rc |= dev_alloc_copy(reinterpret_cast<float**>(&h->rec_call), rec.data(), rec.size());
-  rc |= dev_alloc_copy(&s.tc_jl, jl.data(), jl.size());
-  rc |= dev_alloc_copy(&s.tc_nj, nj.data(), nj.size());
-  rc |= dev_alloc_copy(&s.tc_xoff, xoff.data(), xoff.size());
-  rc |= dev_alloc_copy(&s.tc_xw, xw.data(), xw.size());
+  rc = dev_alloc_copy(&s.basisT, bt.data(), bt.size());
+  {
+    std::vector<float> rec((size_t)n_pad * 12);
+    if (!rc && cudaMemcpy(rec.data(), s.tc_rec, rec.size() * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) rc = EG_ERR_CUDA;
+    rc |= dev_alloc_copy(reinterpret_cast<float**>(&h->rec_call), rec.data(), rec.size());
+  }
   if (!rc && h->encode_fn) rc |= encode_map(h, &h->mapA, s.basisT, (uint64_t)3 * n_pad, tc::HALF_ROWS);
+  return rc;
+}
+
+// rows of the compact set's K-major basis are rows of the full set's (same fp16 values): dst[c][r] = src[c][src_row[r]]
+__global__ void gather_basisT_kernel(const __half* __restrict__ src, int src_pad, const int32_t* __restrict__ src_row,
+                                     int dst_pad, __half* __restrict__ dst) {
+  const int r = blockIdx.x, c = blockIdx.y;
+  const int sr = src_row[r];
+  if (sr < 0) return;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + ((size_t)c * src_pad + sr) * tc::KT);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + ((size_t)c * dst_pad + r) * tc::KT);
+  for (int i = threadIdx.x; i < tc::KT * 2 / 16; i += blockDim.x) d4[i] = s4[i];
+}
+
+// tensor-core layout of the compact set (markers + vertex joints + landmark corners): the 20-frame env pass evaluates
+// it with the same tcgen05 kernel right after the full mesh instead of a second SIMT pass
+static int build_tc_compact(EgLbs* h, VertexSet& s, const std::vector<int32_t>& vids) {
+  if (h->full.basisT == nullptr || vids.empty()) return EG_OK;
+  std::vector<int> perm;
+  int rc = build_tc_records(h, s, vids, perm);
+  if (rc) return rc;
+  const int n_pad = s.n_pad_tc;
+  std::vector<int32_t> src_row(n_pad, -1);
+  for (int r = 0; r < n_pad; ++r) if (perm[r] >= 0) src_row[r] = h->h_row_of_vertex[vids[perm[r]]];
+  int32_t* d_rows = nullptr;
+  rc = dev_alloc_copy(&d_rows, src_row.data(), src_row.size());
+  if (rc) return rc;
+  EG_CUDA_CHECK(cudaMalloc((void**)&s.basisT, (size_t)3 * n_pad * tc::KT * sizeof(__half)));
+  EG_CUDA_CHECK(cudaMemset(s.basisT, 0, (size_t)3 * n_pad * tc::KT * sizeof(__half)));
+  EG_LAUNCH(gather_basisT_kernel, dim3(n_pad, 3), 64, 0, 0, h->full.basisT, h->full.n_pad_tc, d_rows, n_pad, s.basisT);
+  EG_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaFree(d_rows);
+  if (h->encode_fn) rc = encode_map(h, &h->mapA_c, s.basisT, (uint64_t)3 * n_pad, tc::HALF_ROWS);
   return rc;
 }
 
@@ -1415,6 +1553,8 @@ static int build_compact(EgLbs* h, const int32_t* marker_vids, int n_markers) {
             s.nnz, d_vids, n, s.n_pad, s.basis, s.vt, s.skin_idx, s.skin_w);
   EG_CUDA_CHECK(cudaDeviceSynchronize());
   cudaFree(d_vids);
+  rc = build_tc_compact(h, s, vids);
+  if (rc) { free_vertex_set(s); return rc; }
   h->compact = s;
   h->n_markers = n_markers;
   return EG_OK;
@@ -1533,7 +1673,9 @@ extern "C" int eg_lbs_create(const EgLbsModel* m, int device, EgLbs** out) {
   ls.push_back((int32_t)lj.size());
   h->n_levels = maxd + 1;
   int rc = 0;
-  rc |= build_tc_layout(h, m, sidx, sw);
+  h->h_sidx = sidx; h->h_sw = sw;
+  h->h_vt.assign(m->v_template, m->v_template + (size_t)V * 3);
+  rc |= build_tc_layout(h, m);
   rc |= dev_alloc_copy(&s.basis, basis.data(), basis.size());
   rc |= dev_alloc_copy(&s.vt, vt.data(), vt.size());
   rc |= dev_alloc_copy(&s.skin_idx, sidx.data(), sidx.size());
@@ -1562,7 +1704,7 @@ extern "C" void eg_lbs_destroy(EgLbs* h) {
   cudaFree(h->Jt); cudaFree(h->Js); cudaFree(h->hand_l); cudaFree(h->hand_r); cudaFree(h->pose_mean);
   cudaFree(h->parents); cudaFree(h->level_joints); cudaFree(h->level_start); cudaFree(h->lmk_bary);
   cudaFree(h->Ft); cudaFree(h->A); cudaFree(h->Jp); cudaFree(h->cout_); cudaFree(h->Ftc); cudaFree(h->Aw); cudaFree(h->rec_call);
-  cudaFree(h->tile_sched);
+  cudaFree(h->tile_sched); cudaFree(h->Al);
   delete h;
 }
 

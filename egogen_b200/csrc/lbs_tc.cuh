@@ -66,7 +66,7 @@ constexpr int NTAB = 2;                          // table / record buffers
 constexpr int MASK_WORDS = 1024;                 // coarse-cell sign bits of the SDF grid (32^3 cells for a 256^3 grid)
 constexpr int QCAP = 96;                         // entries of one epilogue warp's SDF queue pair (stage 1 grows up, stage 2 grows down)
 constexpr int Q_BYTES = QCAP * 16;
-constexpr int NSCHED = 4;                        // tile-scheduler ring slots
+constexpr int NSCHED = 2;                        // tile-scheduler ring slots
 constexpr int BAR_BYTES = 256;
 constexpr int OFF_BARS = STAGES * STAGE_BYTES;
 constexpr int OFF_TAB = OFF_BARS + BAR_BYTES;

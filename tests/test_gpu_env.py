@@ -177,7 +177,8 @@ def test_step_matches_oracle(dev, world):
         assert torch.allclose(b["T0"].cpu(), ref["T0"][:, 0], atol=1e-4)
         assert torch.allclose(b["seed"].cpu(), ref["seed"], atol=3e-4, rtol=1e-3)
         assert torch.allclose(obs["state"].cpu(), ref["state"], atol=2e-4)
-        assert torch.allclose(obs["egosensing"].cpu(), ref["egosensing"], atol=2e-3)
+        d_ego = (obs["egosensing"].cpu() - ref["egosensing"]).abs()
+        assert torch.allclose(obs["egosensing"].cpu(), ref["egosensing"], atol=2e-3), (it, float(d_ego.max()), int((d_ego > 2e-3).sum()), d_ego.flatten().topk(4).values)
         assert torch.allclose(obs["dist"].cpu()[:, 0], ref["dist"], atol=1e-4)
         assert torch.allclose(obs["time"].cpu()[:, 0], ref["time"], atol=1e-6)
         assert int(b["steps"][0]) == it + 1
