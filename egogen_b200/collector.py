@@ -112,8 +112,11 @@ class Collector:
             self.buf = RolloutBuffer(T, E, self.dev)
         b, pol, venv = self.buf, self.policy, self.venv
         rets, lens = [], []
-        if not self.host_boundary and hasattr(venv, "reset_masked") and getattr(venv, "sampler", None) is not None:
+        maskable = hasattr(venv, "reset_masked") and getattr(venv, "sampler", None) is not None
+        if not self.host_boundary and maskable:
             return self._collect_sync_free(T)
+        if self.host_boundary and maskable:
+            return self._collect_host(T)
         for t in range(T):
             obs = self._policy_obs()
             out = pol.forward(Batch(obs=obs), want_value=True)
@@ -147,6 +150,65 @@ class Collector:
                       act=fl(b.act), logp_old=fl(b.logp), adv=fl(adv), returns=fl(ret), v_s=fl(b.v_s))
         self.collect_step += n_step
         stats = {"n/st": n_step, "n/ep": 0}
+        if rets:
+            r, l = torch.cat(rets), torch.cat(lens)
+            self.collect_episode += r.numel()
+            stats.update({"n/ep": int(r.numel()), "rew": float(r.mean()), "len": float(l.float().mean()),
+                          "rews": r.cpu().numpy(), "lens": l.cpu().numpy()})
+        return batch, stats
+
+    @torch.no_grad()
+    def _collect_host(self, T: int):
+        """collect() through the reference's host-side data path with TWO host synchronisations per vector step, the
+        number tianshou's loop has (act -> numpy before env.step; obs_next / rew / done -> numpy after it): finished envs are
+        restarted on the device from the step's `terminated` buffer, so the observation of the next step travels to the host
+        together with this step's reward and flags."""
+        E = self.E
+        b, pol, venv = self.buf, self.policy, self.venv
+        h, stream = self._h, torch.cuda.current_stream(self.dev)
+        rets, lens = [], []
+
+        def obs_to_host():
+            for k, v in venv.observation().items():
+                h[k].copy_(v, non_blocking=True)
+                self.d2h_bytes += v.numel() * 4
+
+        obs_to_host()
+        stream.synchronize()
+        for t in range(T):
+            obs = {}
+            for k in ("state", "egosensing", "dist", "time"):      # H2D (host observation -> policy)
+                obs[k] = h[k].to(self.dev, non_blocking=True)
+                self.h2d_bytes += obs[k].numel() * 4
+            out = pol.forward(Batch(obs=obs), want_value=True)
+            b.state[t].copy_(obs["state"]); b.ego[t].copy_(obs["egosensing"])
+            b.dist[t].copy_(obs["dist"].view(-1)); b.time[t].copy_(obs["time"].view(-1))
+            b.act[t].copy_(out.act); b.logp[t].copy_(out.logp); b.v_s[t].copy_(out.value)
+            _, rew, term, _, _ = venv.step(self._env_act(out.act))  # sync 1: act -> host -> env
+            b.rew[t].copy_(rew); b.term[t].copy_(term)
+            self.ep_ret += rew; self.ep_len += 1
+            venv.reset_masked(b.term[t])
+            h["rew"].copy_(b.rew[t], non_blocking=True); h["term"].copy_(b.term[t], non_blocking=True)
+            self.d2h_bytes += E * 5
+            obs_to_host()
+            stream.synchronize()                                    # sync 2: obs_next, rew, done -> host
+            done = h["term"].nonzero().view(-1)
+            if done.numel() > 0:
+                done = done.to(self.dev)
+                rets.append(self.ep_ret[done].clone()); lens.append(self.ep_len[done].clone())
+                self.ep_ret[done] = 0; self.ep_len[done] = 0
+        _, v_last = pol.net_forward(venv.observation(), want_actor=False, want_critic=True)
+        if T > 1:
+            b.v_next[:-1].copy_(b.v_s[1:])
+        b.v_next[-1].copy_(v_last)
+        end = b.term.clone()
+        end[-1] = 1
+        ret, adv = pol.compute_returns(b.v_s, b.v_next, b.rew, b.term, end)
+        fl = lambda x: x.transpose(0, 1).reshape(T * E, *x.shape[2:]).contiguous()
+        batch = Batch(obs={"state": fl(b.state), "egosensing": fl(b.ego), "dist": fl(b.dist), "time": fl(b.time)},
+                      act=fl(b.act), logp_old=fl(b.logp), adv=fl(adv), returns=fl(ret), v_s=fl(b.v_s))
+        self.collect_step += T * E
+        stats = {"n/st": T * E, "n/ep": 0}
         if rets:
             r, l = torch.cat(rets), torch.cat(lens)
             self.collect_episode += r.numel()

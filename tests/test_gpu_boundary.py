@@ -160,3 +160,32 @@ def test_main_ppo_cli_with_checkpoint_tree(dev, tmp_path, monkeypatch):
     # a named root without checkpoints must raise
     with pytest.raises(FileNotFoundError):
         main_ppo.main(main_ppo.get_args(argv[:-5] + ["--motion-results-root", str(tmp_path / "nowhere"), "--deterministic-eval"]))
+
+
+def test_host_boundary_collect_matches_device_collect(dev):
+    """bench.py's e2e path: the collector with the reference's host-side data path (pinned host buffers, two host
+    synchronisations per vector step) produces the transitions of the device-resident collector bit for bit from the same
+    seeds, and counts the bytes it moved."""
+    from egogen_b200.collector import Collector
+    from egogen_b200.runtime import build_world
+    outs = []
+    for host in (False, True):
+        torch.manual_seed(11); np.random.seed(11)
+        w = build_world(dev, 16, seed=7, sdf_res=64)
+        w["policy"].train()
+        col = Collector(w["policy"], w["venv"], host_boundary=host)
+        col.reset()
+        torch.manual_seed(12)
+        n_ep = 0
+        for _ in range(4):                                   # 16 vector steps: 13-step episodes end and restart inside
+            batch, st = col.collect(16 * 4)
+            n_ep += int(st["n/ep"])
+        outs.append((batch, n_ep, col))
+    (b0, e0, _), (b1, e1, c1) = outs
+    assert e0 == e1 and e0 > 0
+    for k in ("state", "egosensing", "dist", "time"):
+        assert torch.equal(b0.obs[k], b1.obs[k]), k
+    assert torch.equal(b0.act, b1.act) and torch.equal(b0.returns, b1.returns) and torch.equal(b0.adv, b1.adv)
+    per_step = 16 * (2 * 402 + 2 * 32 + 1 + 1) * 4
+    assert c1.h2d_bytes == 16 * (per_step + 16 * 128 * 4)
+    assert c1.d2h_bytes == (16 + 4) * per_step + 16 * (16 * 128 * 4 + 16 * 5)
