@@ -108,7 +108,10 @@ class GAMMAPrimitiveComboTrainOP:
             if ck:
                 c = torch.load(ck[-1], map_location=self.device)
                 self.model.load_state_dict(c["model_state_dict"])
+                self._pop.load_optimizer_state_dict(c["optimizer_state_dict"])
                 start = c["epoch"]
+            else:
+                log("[INFO] resume_training set but no checkpoint under %s: training from scratch (as the reference does)" % tc["save_dir"])
         history = []
         for epoch in range(start, tc["num_epochs"]):
             tot, n, t0 = np.zeros(4), 0, time.time()

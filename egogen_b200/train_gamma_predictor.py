@@ -211,6 +211,19 @@ class GAMMAPrimitiveVAETrainOP:
         return {"state": st, "param_groups": [{"lr": self.trainconfig["learning_rate"], "betas": (0.9, 0.999), "eps": 1e-8,
                                                "weight_decay": 0, "params": list(range(len(st)))}]}
 
+    def load_optimizer_state_dict(self, sd):
+        """optimizer.load_state_dict(checkpoint['optimizer_state_dict']) of the reference's resume path: the per-parameter
+        Adam moments go back into the flat moment buffers and the step count (bias correction) continues."""
+        off = 0
+        for i, p in enumerate(self.model.parameters()):
+            k = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1).to(self.exp_avg))
+                self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1).to(self.exp_avg_sq))
+                self._step = int(float(st["step"]))
+            off += k
+
     def train(self, batch_gen, log=print):
         """train (:507-589)."""
         self.build_model()
@@ -223,6 +236,7 @@ class GAMMAPrimitiveVAETrainOP:
             c = torch.load(ck[-1], map_location=self.device)
             self.model.load_state_dict(c["model_state_dict"])
             if not tc.get("fine_tune", False):
+                self.load_optimizer_state_dict(c["optimizer_state_dict"])
                 start = c["epoch"]
         for epoch in range(start, tc["num_epochs"]):
             tot, n, t0 = np.zeros(3), 0, time.time()

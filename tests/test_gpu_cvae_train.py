@@ -77,3 +77,32 @@ def test_train_loop_reduces_loss(tmp_path):
     ck = torch.load(tmp_path / "epoch-3.ckp", map_location="cpu")
     assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict"} and ck["epoch"] == 3
     assert "d_rnn.weight_ih" in ck["model_state_dict"] and "x_enc.weight_ih_l0" in ck["model_state_dict"]
+
+
+def test_resume_restores_adam_state(tmp_path):
+    """resume_training (models_GAMMA_primitive.py:517-531): weights, Adam moments and step count continue from the
+    last checkpoint, so a 2-epoch run resumed for the third epoch ends where the uninterrupted 3-epoch run ends."""
+    from egogen_b200.train_gamma_predictor import GAMMAPrimitiveVAETrainOP, SyntheticPrimitiveBatchGen
+    dev = torch.device("cuda:0")
+    base = {"batch_size": 32, "num_epochs_fix": 1, "max_rollout": 2, "saving_per_X_ep": 1}
+
+    def run(num_epochs, save_dir, resume):
+        torch.manual_seed(5)
+        op = GAMMAPrimitiveVAETrainOP(trainconfig=dict(base, num_epochs=num_epochs, save_dir=str(save_dir), resume_training=resume),
+                                      device=dev)
+        op.train(SyntheticPrimitiveBatchGen(64, 60, dev, seed=3), log=lambda *_: None)
+        return op
+
+    full = run(3, tmp_path / "full", False)
+    part = run(2, tmp_path / "part", False)
+    ck = torch.load(tmp_path / "part" / "epoch-2.ckp", map_location="cpu")
+    resumed = GAMMAPrimitiveVAETrainOP(trainconfig=dict(base, num_epochs=3, save_dir=str(tmp_path / "part"), resume_training=True),
+                                       device=dev)
+    resumed.build_model()
+    resumed.load_optimizer_state_dict(ck["optimizer_state_dict"])
+    assert resumed._step == part._step > 0
+    assert torch.equal(resumed.exp_avg, part.exp_avg) and torch.equal(resumed.exp_avg_sq, part.exp_avg_sq)
+    with pytest.raises(FileExistsError):
+        GAMMAPrimitiveVAETrainOP(trainconfig=dict(base, num_epochs=3, save_dir=str(tmp_path / "none"), resume_training=True),
+                                 device=dev).train(SyntheticPrimitiveBatchGen(64, 60, dev, seed=3), log=lambda *_: None)
+    assert full._step == 3 * part._step // 2
