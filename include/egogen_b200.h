@@ -63,9 +63,10 @@ int eg_sdf_sample(const float* grid, int D0, int D1, int D2, const float* center
                   const float* scale_dev, const float* pts, int64_t P, float* val,
                   int32_t* base_idx, void* stream);
 
-/* Optional: register a conservative 8^3-cell coarse grid for `grid` (kept inside the library, keyed by the
- * pointer). The fused penetration count (eg_lbs_forward_sdf / eg_env_step) then answers "sdf < 0 ?" for vertices
- * whose whole cell is positive without touching the fine grid; results are identical to the full sample.
+/* Optional: register the sign structures of `grid` (kept inside the library, keyed by the pointer): a conservative
+ * 8^3-cell coarse grid with its sign bits, 2^3-cell sign bits, and an exact 2-bit class per fine cell (every corner > 0 /
+ * no corner > 0 / both), D0*D1*D2/4 bytes. The fused penetration count (eg_lbs_forward_sdf / eg_env_step) then answers
+ * "sdf < 0 ?" without the 8-corner sample wherever the class decides it; results are identical to the full sample.
  * Call again after mutating the grid in place; eg_sdf_release drops the entry. Synchronises `stream`. */
 int eg_sdf_prepare(const float* grid, int D0, int D1, int D2, void* stream);
 int eg_sdf_release(const float* grid);
