@@ -421,12 +421,14 @@ class GAMMAPPOPolicy(nn.Module):
                 starts = starts[:-1]                                   # merge_last
             bounds = [(s, N if i == len(starts) - 1 else s + batch_size) for i, s in enumerate(starts)]
             perm_dev = torch.as_tensor(perm, device=self.dev)          # one H2D copy of the permutation per repeat
-            mbs = []
-            for s0, e0 in bounds:
-                idx = perm_dev[s0:e0]
-                mbs.append(Batch(obs={k: v.index_select(0, idx) for k, v in batch.obs.items()},
-                                 act=batch.act.index_select(0, idx), logp_old=batch.logp_old.index_select(0, idx),
-                                 adv=batch.adv.index_select(0, idx), returns=batch.returns.index_select(0, idx)))
+            # ONE gather per field over the whole permutation (8 launches per repeat instead of 8 per minibatch); a
+            # minibatch is a contiguous row range of the permuted copies
+            take = perm_dev[:bounds[-1][1]] if bounds else perm_dev
+            pobs = {k: v.index_select(0, take) for k, v in batch.obs.items()}
+            pact, plogp = batch.act.index_select(0, take), batch.logp_old.index_select(0, take)
+            padv, pret = batch.adv.index_select(0, take), batch.returns.index_select(0, take)
+            mbs = [Batch(obs={k: v[s0:e0] for k, v in pobs.items()}, act=pact[s0:e0], logp_old=plogp[s0:e0],
+                         adv=padv[s0:e0], returns=pret[s0:e0]) for s0, e0 in bounds]
             moms = None
             if self._norm_adv:                                         # advantage moments of every minibatch, ONE collective
                 moms = torch.zeros(len(mbs), 3, dtype=torch.float64, device=self.dev)

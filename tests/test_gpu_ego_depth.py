@@ -25,11 +25,16 @@ def test_ego_depth_matches_oracle():
     up = torch.cross(right, fwd, dim=1)
     cam = torch.cat([eye, right, up, fwd], 1)
     depth, steps = ego_depth(sdf, cam.to(dev), H=32, W=32, fx=20.0, fy=20.0, return_steps=True)
-    ref, _ = oed.ego_depth(sdf_cpu, cam, H=32, W=32, fx=20.0, fy=20.0)
+    ref, ref_steps = oed.ego_depth(sdf_cpu, cam, H=32, W=32, fx=20.0, fy=20.0)
     d, r = depth.cpu(), ref
-    # sphere tracing is discontinuous at silhouettes: compare where both agree on hit / miss, allow 1 % outliers
-    close = (d - r).abs() < 2e-3
-    assert close.float().mean() > 0.99, close.float().mean()
+    # rays that march the same number of steps took the same path: fp32 agreement (measured: every ray, max 6.7e-6).
+    # Sphere tracing is discontinuous at silhouettes, so a ray may stop one step apart; those are the ONLY exclusions,
+    # they are counted (< 0.5 %) and still bounded by one hit threshold
+    same = steps.cpu() == ref_steps
+    assert same.float().mean() > 0.995, same.float().mean()
+    assert (d - r).abs()[same].max() < 2e-5, (d - r).abs()[same].max()
+    if (~same).any():
+        assert (d - r).abs()[~same].max() < 5e-3, (d - r).abs()[~same].max()
     assert d.min() >= 0 and d.max() <= 7.0
     assert (d < 6.99).float().mean() > 0.2          # the scene is actually visible
     # empty batch

@@ -100,10 +100,11 @@ def test_ppo_minibatch_matches_autograd(dev, B):
                             list(oa.parameters()) + list(oc.parameters()) + list(os_.parameters())):
         gg, gr = p.grad.cpu(), q.grad
         scale = gr.abs().max().item() + 1e-8
-        # leaky-relu is non-smooth: a pre-activation within rounding of 0 may take the other slope for one row,
-        # so the element-wise bound is loose and the tensor-wise (norm) bound is the tight one
-        assert (gg - gr).abs().max().item() <= 2e-2 * scale + 1e-7, (name, (gg - gr).abs().max().item(), scale)
-        assert (gg - gr).norm().item() <= 2e-3 * gr.norm().item() + 1e-7, (name, (gg - gr).norm().item(), gr.norm().item())
+        # measured (tools/grad_error_probe.py, against float64 autograd): worst element 4.3e-5 of the tensor's max, worst
+        # norm ratio 3.4e-5 at B = 256 (the fp32 oracle itself: 1.5e-5 / 1.1e-5); leaky-relu is non-smooth, so a
+        # pre-activation within rounding of 0 may take the other slope for one row - the bounds keep a 5x margin for that
+        assert (gg - gr).abs().max().item() <= 3e-4 * scale + 1e-7, (name, (gg - gr).abs().max().item(), scale)
+        assert (gg - gr).norm().item() <= 2e-4 * gr.norm().item() + 1e-7, (name, (gg - gr).norm().item(), gr.norm().item())
     # clip (actor+critic only) + AdamW on IDENTICAL gradients (the first Adam step is ~lr*sign(g), so the
     # optimiser is compared operator-level, not through the 1e-3-relative gradient differences)
     for p, q in zip(pol._ordered_params(), list(oa.parameters()) + list(oc.parameters()) + list(os_.parameters())):
