@@ -163,20 +163,26 @@ __device__ __forceinline__ void put_split(__half* dst, int64_t hi_idx, int64_t l
 
 namespace dtc {
 constexpr int S = 16;                         // column slices = CTAs per cluster
-constexpr int TBR = 128;                      // rows per cluster (UMMA M)
+constexpr int TBR = 128;                      // UMMA M (TMEM lanes)
+constexpr int ROWS = 64;                      // REAL rows per cluster: the upper 64 rows of every A tile are whatever lies behind
+                                              // the stage in shared memory (their accumulator lanes are never read). A phase is
+                                              // bound by the activation bytes a CTA can keep in flight (48 KB of ring against
+                                              // ~0.8 us of L2 latency), so half the rows per cluster = half the bytes per phase on
+                                              // twice the SMs (4 clusters = 64 CTAs at 256 envs)
 constexpr int H = 256, HM = 512, D = 201;     // the only dimensions this kernel is built for
 constexpr int NA = 80, NB = 16, NC = 64;      // per-CTA output columns: A = 32 t1 + 3 x 16 gh, B = 16 t2, C = 16 y + 3 x 16 gi
 constexpr int YS = 13;                        // y columns owned per slice (16 x 13 = 208 >= 201)
-constexpr int CH = TBR * 128;                 // one activation chunk: 128 rows x 64 fp16
+constexpr int CH = ROWS * 128;                // one activation chunk: 64 rows x 64 fp16
 constexpr int WA_CH = NA * 128, WB_CH = NB * 128, WC_CH = NC * 128;
-constexpr int OFF_WA = 0;                               // [4 k-chunks][hi | lo]
+constexpr int RING = 6;
+constexpr int OFF_RING = 0;                             // the ring comes FIRST: the 128-row A descriptor of the last stage reads
+                                                        // 8 KB past it, which must still be this CTA's shared memory (the weights)
+constexpr int OFF_WA = OFF_RING + RING * CH;            // [4 k-chunks][hi | lo]
 constexpr int OFF_WB = OFF_WA + 4 * 2 * WA_CH;          // [8][hi | lo]
 constexpr int OFF_WC = OFF_WB + 8 * 2 * WB_CH;          // [4][hi | lo]
-constexpr int OFF_RING = OFF_WC + 4 * 2 * WC_CH;
-constexpr int RING = 3;
-constexpr int OFF_BARS = OFF_RING + RING * CH;
+constexpr int OFF_BARS = OFF_WC + 4 * 2 * WC_CH;
 constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
-constexpr int W_BYTES = OFF_RING;
+constexpr int W_BYTES = OFF_BARS - OFF_WA;
 constexpr int THREADS = 320;                  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 // TMEM: every product has TWO accumulators - the hi*hi pass and the two correction passes (hi*lo + lo*hi, 2^-11 smaller).
 // The tensor core truncates when it folds an MMA into its accumulator; kept apart, the large accumulator sees K/16
@@ -185,7 +191,9 @@ constexpr int THREADS = 320;                  // warp 0 producer, warp 1 MMA, wa
 constexpr int TM_A = 0, TM_B = 80, TM_C = 96, TM_CORR = 256, TMEM_COLS = 512;
 constexpr int N_PHASES = 1 + 3 * 18;
 constexpr float ACT_SCALE = 1024.0f, ACT_INV = 1.0f / 1024.0f;   // h, t1, t2 are gate / tanh outputs in [-1, 1]
-static_assert(OFF_WB % 1024 == 0 && OFF_WC % 1024 == 0 && OFF_RING % 1024 == 0 && WA_CH % 1024 == 0 && WB_CH % 1024 == 0, "swizzle atoms");
+static_assert(OFF_WA % 1024 == 0 && OFF_WB % 1024 == 0 && OFF_WC % 1024 == 0 && OFF_RING % 1024 == 0 && WA_CH % 1024 == 0 && WB_CH % 1024 == 0 &&
+              CH % 1024 == 0, "swizzle atoms");
+static_assert(OFF_RING + RING * CH + (TBR - ROWS) * 128 <= OFF_BARS, "the A descriptor's upper rows stay inside the CTA's shared memory");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 enum { SC_W1 = 0, SC_WHH, SC_W2, SC_WO, SC_WF, N_SC };
 }  // namespace dtc
@@ -249,7 +257,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap mapWA, const __grid_constan
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j = blockIdx.x;                  // column slice = rank in the cluster
   const int rt = blockIdx.y;                 // row tile
-  const int row0 = rt * TBR;
+  const int row0 = rt * ROWS;
 
   if (warp == 1) {
     if (lane == 0) {
@@ -357,6 +365,11 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap mapWA, const __grid_constan
   } else {
     // ===== epilogue warps: thread = row (TMEM lane q*32 + lane), `half` = which half of the phase's columns =====
     const int q = warp & 3, half = (warp - 2) >> 2;
+    if (q >= ROWS / 32) {
+      // TMEM lanes 64..127 carry no rows: these warps only keep the cluster barriers of every phase company
+      cluster_arrive(); cluster_wait();                // barrier 0
+      for (int ph = 0; ph < N_PHASES; ++ph) { cluster_arrive(); cluster_wait(); }
+    } else {
     const int row = q * 32 + lane;
     const int rg = row0 + row;                          // row of the exchange buffers (always allocated)
     const int b = min(rg, a.B - 1);                     // env this row mirrors (rows >= B duplicate the last env)
@@ -474,6 +487,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap mapWA, const __grid_constan
       fence_async_all();                                  // my global writes -> peers' TMA reads after the barrier
       tc_fence_before();
       cluster_arrive(); cluster_wait();
+    }
     }
   }
   tc_fence_before();
@@ -1067,7 +1081,7 @@ bool regress_available(const MotionTc* m) { return m && m->reg_ok; }
 int decode(MotionTc* m, const float* gi1, const float* h0, float* Y, int B, cudaStream_t st) {
   using namespace dtc;
   EG_REQUIRE(m && m->dec_ok, "tensor-core decode unavailable");
-  const int n_rt = (B + TBR - 1) / TBR, rows = n_rt * TBR;
+  const int n_rt = (B + ROWS - 1) / ROWS, rows = n_rt * ROWS;
   if (rows > m->cap_rows) {
     EG_CUDA_CHECK(cudaStreamSynchronize(st));
     cudaFree(m->Hact); cudaFree(m->T1act); cudaFree(m->T2act);
@@ -1076,9 +1090,9 @@ int decode(MotionTc* m, const float* gi1, const float* h0, float* Y, int B, cuda
     EG_CUDA_CHECK(cudaMalloc((void**)&m->T1act, (size_t)2 * rows * HM * sizeof(__half)));
     EG_CUDA_CHECK(cudaMalloc((void**)&m->T2act, (size_t)2 * rows * H * sizeof(__half)));
     int rc;
-    if ((rc = encode_f16_2d(m, &m->mapH, m->Hact, 2 * rows, H, TBR))) return rc;
-    if ((rc = encode_f16_2d(m, &m->mapT1, m->T1act, 2 * rows, HM, TBR))) return rc;
-    if ((rc = encode_f16_2d(m, &m->mapT2, m->T2act, 2 * rows, H, TBR))) return rc;
+    if ((rc = encode_f16_2d(m, &m->mapH, m->Hact, 2 * rows, H, ROWS))) return rc;
+    if ((rc = encode_f16_2d(m, &m->mapT1, m->T1act, 2 * rows, HM, ROWS))) return rc;
+    if ((rc = encode_f16_2d(m, &m->mapT2, m->T2act, 2 * rows, H, ROWS))) return rc;
     m->cap_rows = rows;
   }
   DtcArgs a{h0, gi1, Y, m->Hact, m->T1act, m->T2act, m->cap_rows, m->b1, m->bhh, m->b2, m->bo, m->bf, m->scale, m->inv, B};
