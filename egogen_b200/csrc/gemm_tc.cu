@@ -33,6 +33,9 @@ constexpr int BM = 128, BK = 32;                     // BK fp32 = 128 B = one sw
 #ifndef EG_GEMM_TC_STAGES
 #define EG_GEMM_TC_STAGES 2                             // ring depth (48 KB per stage at BN = 64); see DESIGN 6b for the 3 / 4-stage A/B
 #endif
+#ifndef EG_GEMM_TC_TS
+#define EG_GEMM_TC_TS 1                                 // 1: the A lo tile lives in TMEM (UMMA TMEM-A operand), 3-stage ring in 96 KB
+#endif
 constexpr int A_BYTES = BM * BK * 4;                // 16 KB
 constexpr int XF_WARPS = 8;                          // transform + epilogue warps
 constexpr int THREADS = 64 + XF_WARPS * 32;          // 320
@@ -42,15 +45,23 @@ template <int BN, bool DEEP = false>
 struct Geo {
   static constexpr int B_BYTES = BN * BK * 4;                   // 8 / 16 KB
   // DEEP: 4 (BN = 64) / 3 (BN = 128) stages, opt-in per launch through EG_GEMM_TC_DEEP
-  static constexpr int STAGES = DEEP ? (BN == 64 ? 4 : 3) : ((BN == 64 || EG_GEMM_TC_STAGES < 3) ? EG_GEMM_TC_STAGES : 3);
-  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // raw(hi) A, raw(hi) B, lo A, lo B = 48 / 64 KB
-  static constexpr int TMEM_COLS = BN;
+  // TS (default, not DEEP): the lo copy of the A tile is written to TMEM by the transform warps and read as the UMMA's
+  // TMEM A operand, so a stage holds raw A, raw B and lo B only (32 KB at BN = 64): THREE stages fit the 96 KB the 2-stage
+  // hi + lo ring used - two CTAs per SM stay co-resident (the PDL chain and the actor / critic stream overlap need that,
+  // DESIGN 6b) with 1.5x the operand bytes in flight.
+  static constexpr bool TS = !DEEP && EG_GEMM_TC_TS;
+  static constexpr int STAGES = TS ? 3 : (DEEP ? (BN == 64 ? 4 : 3) : ((BN == 64 || EG_GEMM_TC_STAGES < 3) ? EG_GEMM_TC_STAGES : 3));
+  static constexpr int STAGE_BYTES = TS ? (A_BYTES + 2 * B_BYTES) : 2 * (A_BYTES + B_BYTES);   // raw A, raw B, (lo A,) lo B
+  static constexpr int OFF_LO = TS ? (A_BYTES + B_BYTES) : (A_BYTES + B_BYTES);                 // lo tiles inside a stage (TS: lo B only)
+  static constexpr int TMEM_COLS = TS ? 256 : BN;               // accumulator + 3 x 32 columns of A lo, power of two
+  static constexpr int TM_ALO = BN;                             // first A lo column
   static constexpr int EPI_COLS = BN / (XF_WARPS / 4);          // columns per epilogue thread (two warps share a TMEM lane quarter)
   static constexpr int RED_LD = BN + 1;                         // padded row of the split-k reduction buffer
   static constexpr int OFF_BARS = STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
   static_assert(BM * RED_LD * 4 <= STAGES * STAGE_BYTES, "reduction buffer aliases the operand ring");
-  static_assert((A_BYTES + B_BYTES) / 16 % XF_THREADS == 0, "transform work split");
+  static_assert((A_BYTES + B_BYTES) / 16 % XF_THREADS == 0 && B_BYTES / 16 % XF_THREADS == 0, "transform work split");
+  static_assert(!TS || BN + STAGES * BK <= TMEM_COLS, "TMEM budget");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,6 +120,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same instruction with the A operand in TMEM (lane = row, 8 consecutive 32-bit columns = one k step); A from TMEM is
+// K-major by construction, so bit 15 stays clear whatever the layout of the raw A tile
+template <bool B_MN, int BN>
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate) {
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
+}
+__device__ __forceinline__ float lo_tf32(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -235,13 +266,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         constexpr uint32_t CH = BK * 128;                  // bytes of one 32-wide MN chunk ([32 k][128 B])
         const uint64_t a_hi = A_MN ? make_desc_mn(st, CH) : make_desc(st);
         const uint64_t b_hi = B_MN ? make_desc_mn(st + A_BYTES, CH) : make_desc(st + A_BYTES);
-        const uint64_t a_lo = A_MN ? make_desc_mn(st + A_BYTES + B_BYTES, CH) : make_desc(st + A_BYTES + B_BYTES);
-        const uint64_t b_lo = B_MN ? make_desc_mn(st + 2 * A_BYTES + B_BYTES, CH) : make_desc(st + 2 * A_BYTES + B_BYTES);
+        const uint32_t lo_b_addr = G::TS ? st + A_BYTES + B_BYTES : st + 2 * A_BYTES + B_BYTES;
+        const uint64_t a_lo = A_MN ? make_desc_mn(st + A_BYTES + B_BYTES, CH) : make_desc(st + A_BYTES + B_BYTES);   // (not TS)
+        const uint64_t b_lo = B_MN ? make_desc_mn(lo_b_addr, CH) : make_desc(lo_b_addr);
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {
           // one 8-wide k step: K-major advances 32 B inside the swizzle atom, MN-major one 8-row group (1024 B)
           const uint64_t oa = (uint64_t)(A_MN ? kk * 64 : kk * 2), ob = (uint64_t)(B_MN ? kk * 64 : kk * 2);
-          umma_tf32<A_MN, B_MN, BN>(tmem_base, a_lo + oa, b_hi + ob, (i | kk) ? 1u : 0u);
+          if (G::TS) umma_tf32_ts<B_MN, BN>(tmem_base, tmem_base + (uint32_t)(G::TM_ALO + s * BK + kk * 8), b_hi + ob, (i | kk) ? 1u : 0u);
+          else umma_tf32<A_MN, B_MN, BN>(tmem_base, a_lo + oa, b_hi + ob, (i | kk) ? 1u : 0u);
           umma_tf32<A_MN, B_MN, BN>(tmem_base, a_hi + oa, b_lo + ob, 1u);
           umma_tf32<A_MN, B_MN, BN>(tmem_base, a_hi + oa, b_hi + ob, 1u);
         }
@@ -258,6 +291,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&full_bar[s], ph);
       const uint32_t raw = smem_base + s * STAGE_BYTES;                    // A then B, contiguous
       const uint32_t lo = raw + A_BYTES + B_BYTES;
+      if (G::TS) {
+        // lo B: element-wise into shared memory (layout-agnostic); lo A: this thread's row (TMEM lane), 16 of the 32 k
+        // columns, read through the tile's swizzle and written to the stage's TMEM columns
+        float4 xb[B_BYTES / 16 / XF_THREADS];
+#pragma unroll
+        for (int q = 0; q < B_BYTES / 16 / XF_THREADS; ++q) xb[q] = lds128(raw + A_BYTES + (uint32_t)(xt + q * XF_THREADS) * 16u);
+        const int rq = warp & 3, hf = (warp - 2) >> 2, r = rq * 32 + lane;
+        float av[16];
+        if (A_MN) {
+          // [32 k][32 m] chunks of 128 B rows, 32 B units XOR-swizzled with (k & 3) (SWIZZLE_128B_ATOM_32B)
+          const uint32_t cb = raw + (uint32_t)rq * (BK * 128) + (uint32_t)((lane & 7) << 2);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int k = 16 * hf + e;
+            av[e] = lds32f(cb + (uint32_t)(k * 128) + (uint32_t)((((lane >> 3) ^ (k & 3)) & 3) << 5));
+          }
+        } else {
+          const uint32_t rb = raw + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 x = lds128(rb + (uint32_t)(((4 * hf + c) ^ (r & 7)) << 4));
+            av[4 * c + 0] = x.x; av[4 * c + 1] = x.y; av[4 * c + 2] = x.z; av[4 * c + 3] = x.w;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) av[e] = lo_tf32(av[e]);
+        tmem_st16(tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)(G::TM_ALO + s * BK + 16 * hf), av);
+#pragma unroll
+        for (int q = 0; q < B_BYTES / 16 / XF_THREADS; ++q) {
+          float4 l;
+          l.x = lo_tf32(xb[q].x); l.y = lo_tf32(xb[q].y); l.z = lo_tf32(xb[q].z); l.w = lo_tf32(xb[q].w);
+          sts128(lo + (uint32_t)(xt + q * XF_THREADS) * 16u, l);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the UMMA reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready_bar[s]);
+        continue;
+      }
       float4 xs[(A_BYTES + B_BYTES) / 16 / XF_THREADS];
 #pragma unroll
       for (int q = 0; q < (A_BYTES + B_BYTES) / 16 / XF_THREADS; ++q) xs[q] = lds128(raw + (uint32_t)(xt + q * XF_THREADS) * 16u);
