@@ -236,11 +236,14 @@ def measure_ppo(ctx, args):
         # ---- e2e: same iteration with the reference's host-side data path ---------------------
         col2 = Collector(pol, w["venv"], host_boundary=True)
         col2.reset()
-        iteration(col2)
+        for _ in range(max(args.warmup, 3)):               # the same warm-up as the device-resident arm
+            iteration(col2)
+        torch.cuda.synchronize(dev)
         col2.h2d_bytes = col2.d2h_bytes = 0
-        e2e_ms, _ = ctx.time_steps(lambda: iteration(col2), args.steps)
+        e2e_ms, e2e_list = ctx.time_steps(lambda: iteration(col2), args.steps)
     e2e = {"value": STEP_PER_COLLECT * world_size * args.steps / (e2e_ms / 1e3), "unit": "env-steps/s",
-           "h2d_bytes_per_step": col2.h2d_bytes // args.steps, "d2h_bytes_per_step": (col2.d2h_bytes + 5 * 8 * 4) // args.steps}
+           "h2d_bytes_per_step": col2.h2d_bytes // args.steps, "d2h_bytes_per_step": (col2.d2h_bytes + 5 * 8 * 4) // args.steps,
+           "ms_per_step_rank0": [round(x, 3) for x in e2e_list]}
     # sanity (outside every timed region): the rollouts and the updated policy are finite
     assert bool(torch.isfinite(last["batch"].returns).all()) and bool(torch.isfinite(pol.flat_params).all()), \
         "non-finite values after the timed iterations"

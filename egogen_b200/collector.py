@@ -151,10 +151,10 @@ class Collector:
         self.collect_step += n_step
         stats = {"n/st": n_step, "n/ep": 0}
         if rets:
-            r, l = torch.cat(rets), torch.cat(lens)
-            self.collect_episode += r.numel()
-            stats.update({"n/ep": int(r.numel()), "rew": float(r.mean()), "len": float(l.float().mean()),
-                          "rews": r.cpu().numpy(), "lens": l.cpu().numpy()})
+            rl = torch.cat([torch.cat(rets), torch.cat(lens).to(torch.float32)]).cpu().numpy()      # ONE device -> host read
+            r, l = rl[:len(rl) // 2], rl[len(rl) // 2:].astype(np.int32)
+            self.collect_episode += r.size
+            stats.update({"n/ep": int(r.size), "rew": float(r.mean()), "len": float(l.mean()), "rews": r, "lens": l})
         return batch, stats
 
     @torch.no_grad()
@@ -175,10 +175,12 @@ class Collector:
 
         obs_to_host()
         stream.synchronize()
+        if getattr(self, "_obs_dev", None) is None:                 # persistent device copies: no allocation per step
+            self._obs_dev = {k: torch.empty_like(h[k], device=self.dev) for k in ("state", "egosensing", "dist", "time")}
         for t in range(T):
-            obs = {}
+            obs = self._obs_dev
             for k in ("state", "egosensing", "dist", "time"):      # H2D (host observation -> policy)
-                obs[k] = h[k].to(self.dev, non_blocking=True)
+                obs[k].copy_(h[k], non_blocking=True)
                 self.h2d_bytes += obs[k].numel() * 4
             out = pol.forward(Batch(obs=obs), want_value=True)
             b.state[t].copy_(obs["state"]); b.ego[t].copy_(obs["egosensing"])
@@ -210,10 +212,10 @@ class Collector:
         self.collect_step += T * E
         stats = {"n/st": T * E, "n/ep": 0}
         if rets:
-            r, l = torch.cat(rets), torch.cat(lens)
-            self.collect_episode += r.numel()
-            stats.update({"n/ep": int(r.numel()), "rew": float(r.mean()), "len": float(l.float().mean()),
-                          "rews": r.cpu().numpy(), "lens": l.cpu().numpy()})
+            rl = torch.cat([torch.cat(rets), torch.cat(lens).to(torch.float32)]).cpu().numpy()      # ONE device -> host read
+            r, l = rl[:len(rl) // 2], rl[len(rl) // 2:].astype(np.int32)
+            self.collect_episode += r.size
+            stats.update({"n/ep": int(r.size), "rew": float(r.mean()), "len": float(l.mean()), "rews": r, "lens": l})
         return batch, stats
 
     @torch.no_grad()

@@ -139,6 +139,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
         "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
         "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
 }
+// distributed shared memory through 32-bit shared::cluster addresses (half the registers of generic pointers)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float lo_tf32(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -190,7 +201,7 @@ struct Params {
 // A_MN / B_MN: the operand is stored with its M / N index contiguous (dW = dY^T X has both, dX = dY W has B) instead of
 // its k index (nn.Linear forward). MN-major tiles are staged as 32-wide chunks, one TMA box [32 k][32 mn] each.
 template <bool A_MN, bool B_MN, int BN, bool DEEP>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)          // two CTAs per SM must stay possible: <= 96 registers after allocation granularity
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
   namespace cg = cooperative_groups;
   using G = Geo<BN, DEEP>;
@@ -392,22 +403,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     cg::cluster_group cluster = cg::this_cluster();
     cluster.sync();                                         // every rank's partial tile is in its shared memory
     if (warp >= 2) {
-      float* red = reinterpret_cast<float*>(smem);
       const int rows_per = (BM + n_split - 1) / n_split;    // rows this rank reduces and writes
       const int r_lo = split * rows_per, r_n = max(0, min(BM, r_lo + rows_per) - r_lo);
       const int xt = tid - 64;
-      for (int e = xt; e < r_n * BN; e += XF_THREADS) {
-        const int r = r_lo + e / BN, c = e % BN;
-        float v = 0.0f;
-        for (int k = 0; k < n_split; ++k) v += cluster.map_shared_rank(red, k)[r * RED_LD + c];
-        const int m = m0 + r, n = n0 + c;
-        if (m < p.M && n < p.N) {
-          v *= p.alpha;
-          if (p.bias) v += __ldg(p.bias + n);
-          if (p.beta) v += p.C[(int64_t)m * p.ldc + n];
-          v = act_apply(v, p.act, p.slope);
-          if (p.residual) v += p.residual[(int64_t)m * p.ldr + n];
-          p.C[(int64_t)m * p.ldc + n] = v;
+      // four elements per pass and the rank loop unrolled: all remote loads of a pass are in flight together (the rolled
+      // form waited one distributed-shared-memory round trip per rank and element); ranks are still summed in order
+      uint32_t rk[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rk[k] = mapa_u32(smem_base, (uint32_t)(k < n_split ? k : 0));
+      for (int e0 = xt; e0 < r_n * BN; e0 += 4 * XF_THREADS) {
+        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        int off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = min(e0 + u * XF_THREADS, r_n * BN - 1);
+          off[u] = ((r_lo + e / BN) * RED_LD + e % BN) * 4;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k < n_split) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] += ld_dsmem_f32(rk[k] + (uint32_t)off[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * XF_THREADS;
+          if (e >= r_n * BN) break;
+          const int r = r_lo + e / BN, c = e % BN;
+          const int m = m0 + r, n = n0 + c;
+          if (m < p.M && n < p.N) {
+            float w = v[u] * p.alpha;
+            if (p.bias) w += __ldg(p.bias + n);
+            if (p.beta) w += p.C[(int64_t)m * p.ldc + n];
+            w = act_apply(w, p.act, p.slope);
+            if (p.residual) w += p.residual[(int64_t)m * p.ldr + n];
+            p.C[(int64_t)m * p.ldc + n] = w;
+          }
         }
       }
     }
