@@ -147,7 +147,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t addr) {
   float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  asm("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr));       // (pure load: ordered by the cluster.sync() around the reduction)
   return v;
 }
 __device__ __forceinline__ float lo_tf32(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -385,6 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int c = 0; c < EPI_COLS; ++c) sts32(smem_base + (uint32_t)(row * RED_LD + c0 + c) * 4u, acc[c]);
     if (n_split == 1) {
       asm volatile("bar.sync 1, %0;" ::"n"(XF_THREADS) : "memory");
+#pragma unroll 8
       for (int e = xt; e < BM * BN; e += XF_THREADS) {
         const int r = e / BN, c = e % BN;
         const int m = m0 + r, n = n0 + c;
