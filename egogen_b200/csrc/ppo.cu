@@ -89,23 +89,42 @@ add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, 
     c[i] = a[i] + b[i];
 }
 
-// db[n] += sum_m dY[m, n]   (block = 32 columns x 8 row lanes)
-__global__ void __launch_bounds__(256)
+// db[n] += sum_m dY[m, n]: a cluster of 4 CTAs per 32-column block (each a quarter of the rows, 8 row lanes), partial sums
+// added by rank 0 in rank order through distributed shared memory (deterministic)
+__global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dY, int ld, int M, int N, float* __restrict__ db) {
   __shared__ float part[8][33];
+  __shared__ float csum[32];
   eg_pdl_enter();
-  const int col = blockIdx.x * 32 + threadIdx.x % 32, rl = threadIdx.x / 32;
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cl;
+  const int rows_per = (M + 3) / 4, r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
   float s = 0.0f;
   if (col < N)
-    for (int m = rl; m < M; m += 8) s += dY[(int64_t)m * ld + col];
-  part[rl][threadIdx.x % 32] = s;
+#pragma unroll 4
+    for (int m = r0 + rl; m < r1; m += 8) s += dY[(int64_t)m * ld + col];
+  part[rl][cl] = s;
   __syncthreads();
-  if (rl == 0 && col < N) {
+  if (rl == 0) {
     float t = 0.0f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += part[q][threadIdx.x];
+    for (int q = 0; q < 8; ++q) t += part[q][cl];
+    csum[cl] = t;
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (blockIdx.y == 0 && rl == 0 && col < N) {
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(&csum[cl]);
+    float t = 0.0f;
+#pragma unroll
+    for (uint32_t r = 0; r < 4; ++r) {
+      uint32_t remote; float v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+      t += v;
+    }
     db[col] += t;
   }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // remote reads done
 }
 
 // dx = dy * lrelu'(y) and, in the same pass, db[n] += sum_m dx[m, n] (the bias gradient of the layer that produced y), as
@@ -566,7 +585,7 @@ static int linear_backward(EgPolicy* h, cudaStream_t st, const float* dY, int ld
   float* G = h->G;
   GemmArgs gw{dY, ld_dy, 1, X, ldx, G + l.w, l.in, nullptr, nullptr, 0, l.out, l.in, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(gw, true, false, st));
-  if (!bias_done) EG_LAUNCH_PDL(colsum_kernel, (l.out + 31) / 32, 256, 0, st, dY, ld_dy, B, l.out, G + l.b);
+  if (!bias_done) EG_LAUNCH_PDL(colsum_kernel, dim3((l.out + 31) / 32, 4), 256, 0, st, dY, ld_dy, B, l.out, G + l.b);
   if (dX) {
     GemmArgs gx{dY, ld_dy, 1, P + l.w, l.in, dX, ld_dx, nullptr, nullptr, 0, B, l.in, l.out, ACT_NONE, 0.f, dx_beta, 1.0f};
     EG_TRY(launch_gemm(gx, false, false, st));
@@ -603,10 +622,10 @@ static int gru2_backward(EgPolicy* h, cudaStream_t st, const float* x, int ld_en
             h->dgh, h->dh1);
   GemmArgs w1{h->dgi, H3, 1, x + ld_frame, ld_env, G + wih, in_dim, nullptr, nullptr, 0, H3, in_dim, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(w1, true, false, st));
-  EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgi, H3, B, H3, G + bih);
+  EG_LAUNCH_PDL(colsum_kernel, dim3((H3 + 31) / 32, 4), 256, 0, st, h->dgi, H3, B, H3, G + bih);
   GemmArgs w2{h->dgh, H3, 1, h1, H, G + whh, H, nullptr, nullptr, 0, H3, H, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(w2, true, false, st));
-  EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + bhh);
+  EG_LAUNCH_PDL(colsum_kernel, dim3((H3 + 31) / 32, 4), 256, 0, st, h->dgh, H3, B, H3, G + bhh);
   // dh1 = dh2 * z + dgh W_hh
   GemmArgs x2{h->dgh, H3, 1, P + whh, H, h->dh1, H, nullptr, nullptr, 0, B, H, H3, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(x2, false, false, st));
@@ -615,8 +634,8 @@ static int gru2_backward(EgPolicy* h, cudaStream_t st, const float* x, int ld_en
             h->dgi, h->dgh, nullptr);
   GemmArgs w3{h->dgi, H3, 1, x, ld_env, G + wih, in_dim, nullptr, nullptr, 0, H3, in_dim, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(w3, true, false, st));
-  EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgi, H3, B, H3, G + bih);
-  EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + bhh);
+  EG_LAUNCH_PDL(colsum_kernel, dim3((H3 + 31) / 32, 4), 256, 0, st, h->dgi, H3, B, H3, G + bih);
+  EG_LAUNCH_PDL(colsum_kernel, dim3((H3 + 31) / 32, 4), 256, 0, st, h->dgh, H3, B, H3, G + bhh);
   return EG_OK;
 }
 
@@ -961,7 +980,7 @@ int lin_bwd(EgCvae* h, cudaStream_t st, const float* dY, int ld_dy, const float*
             int in, int out, int ldw, float* dX, int ld_dx, int dx_beta) {
   GemmArgs gw{dY, ld_dy, 1, X, ldx, h->G + w, ldw, nullptr, nullptr, 0, out, in, B, ACT_NONE, 0.f, 1, 1.0f};
   EG_TRY(launch_gemm(gw, true, false, st));
-  if (b >= 0) EG_LAUNCH_PDL(colsum_kernel, (out + 31) / 32, 256, 0, st, dY, ld_dy, B, out, h->G + b);
+  if (b >= 0) EG_LAUNCH_PDL(colsum_kernel, dim3((out + 31) / 32, 4), 256, 0, st, dY, ld_dy, B, out, h->G + b);
   if (dX) {
     GemmArgs gx{dY, ld_dy, 1, h->P + w, ldw, dX, ld_dx, nullptr, nullptr, 0, B, in, out, ACT_NONE, 0.f, dx_beta, 1.0f};
     EG_TRY(launch_gemm(gx, false, false, st));
@@ -1103,7 +1122,7 @@ static int cvae_backward(EgCvae* h, const float* X, const float* Y, const float*
                 h->dgh, h->dhp);
       EG_TRY(lin_bwd(h, st, h->dgi, H3, X + t * BD, D, B, L.x_wih, L.x_bih, D, H3, D, nullptr, 0, 0));
       if (t > 0) EG_TRY(lin_bwd(h, st, h->dgh, H3, hp, H, B, L.x_whh, L.x_bhh, H, H3, H, h->dhp, H, 1));
-      else EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + L.x_bhh);
+      else EG_LAUNCH_PDL(colsum_kernel, dim3((H3 + 31) / 32, 4), 256, 0, st, h->dgh, H3, B, H3, G + L.x_bhh);
       dcur = h->dhp;
     }
   }
@@ -1115,7 +1134,7 @@ static int cvae_backward(EgCvae* h, const float* X, const float* Y, const float*
               h->dgh, h->dhp);
     EG_TRY(lin_bwd(h, st, h->dgi, H3, Y + t * BD, D, B, L.e_wih, L.e_bih, D, H3, D, nullptr, 0, 0));
     if (t > 0) EG_TRY(lin_bwd(h, st, h->dgh, H3, hp, H, B, L.e_whh, L.e_bhh, H, H3, H, h->dhp, H, 1));
-    else EG_LAUNCH_PDL(colsum_kernel, (H3 + 31) / 32, 256, 0, st, h->dgh, H3, B, H3, G + L.e_bhh);
+    else EG_LAUNCH_PDL(colsum_kernel, dim3((H3 + 31) / 32, 4), 256, 0, st, h->dgh, H3, B, H3, G + L.e_bhh);
     std::swap(h->dh, h->dhp);
   }
   return EG_OK;
@@ -1388,7 +1407,7 @@ int lin_bwd_pg(const float* P, float* G, cudaStream_t st, const float* dY, int l
   if (wgrad) {
     GemmArgs gw{dY, ld_dy, 1, X, ldx, G + w, ldw, nullptr, nullptr, 0, out, in, B, ACT_NONE, 0.f, 1, 1.0f};
     EG_TRY(launch_gemm(gw, true, false, st));
-    EG_LAUNCH_PDL(colsum_kernel, (out + 31) / 32, 256, 0, st, dY, ld_dy, B, out, G + b);
+    EG_LAUNCH_PDL(colsum_kernel, dim3((out + 31) / 32, 4), 256, 0, st, dY, ld_dy, B, out, G + b);
   }
   if (dX) {
     GemmArgs gx{dY, ld_dy, 1, P + w, ldw, dX, ld_dx, nullptr, nullptr, 0, B, in, out, ACT_NONE, 0.f, dx_beta, 1.0f};
