@@ -9,10 +9,10 @@
 // of the 3xTF32 dense layers (gemm_tc.cu) at half the shared-memory bytes and twice the tensor rate. A value beyond fp16's
 // range turns into inf/NaN and surfaces in the outputs (no silent saturation).
 //
-// decode_tc_kernel - the 18 GRUCell + MLP steps (reference models_GAMMA_primitive.py:91-99) for 128 rows per 16-CTA
-//   cluster. CTA j owns 1/16 of every layer's OUTPUT columns and keeps that weight slice (176 KB, hi + lo) resident in
+// decode_tc_kernel - the 18 GRUCell + MLP steps (reference models_GAMMA_primitive.py:91-99) for 64 rows per 16-CTA
+//   cluster (UMMA M stays 128; see dtc::ROWS). CTA j owns 1/16 of every layer's OUTPUT columns and keeps that weight slice (176 KB, hi + lo) resident in
 //   shared memory for all steps; the cluster exchanges each layer's activations as fp16 hi/lo rows through L2
-//   (st.global -> barrier.cluster release/acquire -> TMA loads into a 3-stage ring), so a step costs 3 hardware cluster
+//   (st.global -> barrier.cluster release/acquire -> TMA loads into a 6-stage ring), so a step costs 3 hardware cluster
 //   barriers instead of the 4 global arrival-counter rounds of the SIMT weight-stationary kernel (nn.cu). Step algebra:
 //     gh_{t+1} = h_t Whh^T                      is produced together with t1_t = tanh(h_t W1^T + b1)      (phase A, K = 256)
 //     t2_t     = tanh(t1_t W2^T + b2)                                                                   (phase B, K = 512)
